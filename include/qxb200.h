@@ -1,0 +1,125 @@
+/* libqxb200 -- C ABI of the B200-native executor for the QXTools contraction hot path.
+ *
+ * The reference has no FFI: its hot path sits behind three Julia-level seams, and
+ * these entry points are what a `ccall` binding for each of them needs
+ * (INTEGRATION.md shows the Julia side):
+ *
+ *   B1  single_amplitude(tnc, plan, amplitude)        /root/reference/src/simulation.jl:86-91
+ *       -> QXTns.contract_tn!                         /root/reference/src/simulation.jl:89
+ *   B2  build_compute_graph(tnc, plan, bond_groups)   /root/reference/src/compute_graph/compute_graph.jl:15-98
+ *       -> ComputeGraph(root, tensors): Load/Output/View/Contract/Save commands
+ *   B3  QXContexts.execute(dsl, input, param, output; ...)   /root/reference/bin/qxrun.jl:83-87
+ *       -> the per-bitstring x per-slice contraction loop + reduction
+ *
+ * Conventions: plain C types only; every function returns 0 on success and a
+ * negative code on error, with the message available from qxb_last_error()
+ * (thread-local, owned by the library).  Names are NUL-terminated.  Dims and
+ * labels are int64 arrays in Julia (column-major) order.  All tensor data
+ * crossing the boundary is interleaved complex (re, im).  No exceptions cross
+ * the boundary and no callbacks are taken.
+ *
+ * There is NO CPU fallback: every compute entry point fails with QXB_ERR_CUDA
+ * when no CUDA device is usable.
+ */
+#ifndef QXB200_H
+#define QXB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QXB_OK            0
+#define QXB_ERR_ARG      -1   /* bad argument / malformed program            */
+#define QXB_ERR_STATE    -2   /* call out of order (e.g. not compiled)        */
+#define QXB_ERR_CUDA     -3   /* CUDA runtime error or no device              */
+#define QXB_ERR_UNSUPP   -4   /* valid program the executor does not handle   */
+#define QXB_ERR_MEM      -5   /* does not fit the HBM budget                  */
+
+#define QXB_C32 0             /* ComplexF32 */
+#define QXB_C64 1             /* ComplexF64 */
+
+typedef struct qxb_graph qxb_graph;
+
+typedef struct qxb_options {
+    int64_t hbm_budget_bytes;  /* workspace budget per device; 0 = 60% of free memory            */
+    int64_t amp_batch;         /* max bitstrings contracted per launch; 0 = as many as fit       */
+    int32_t profile;           /* 1 = record a CUDA-event pair around every op (qxb_profile_dump) */
+    int32_t reserved;
+} qxb_options;
+
+/* library */
+int         qxb_version(void);
+const char* qxb_last_error(void);
+/* Select the CUDA device this process drives (one process per GPU). */
+int         qxb_init(int device);
+int         qxb_shutdown(void);
+/* Launch on an existing CUDA stream (a cudaStream_t, e.g. torch's current stream); NULL = library stream. */
+int         qxb_set_stream(void* cuda_stream);
+int         qxb_device_synchronize(void);
+
+/* graph construction: one call per DSL statement, in DSL (post-order) order.
+ * Replaces the Load/Output/View/Contract/Save command objects built at
+ * compute_graph.jl:27,33,49,66,94. */
+int  qxb_graph_create(qxb_graph** g, int dtype);
+void qxb_graph_destroy(qxb_graph* g);
+int  qxb_graph_load  (qxb_graph* g, const char* name, const char* data_label, const int64_t* dims, int rank);
+int  qxb_graph_output(qxb_graph* g, const char* name, int64_t output_idx /*1-based qubit*/, int64_t dim);
+int  qxb_graph_view  (qxb_graph* g, const char* name, const char* target, const char* slice_sym,
+                      int64_t index_pos /*1-based mode*/, int64_t dim);
+int  qxb_graph_ncon  (qxb_graph* g, const char* out, const int64_t* out_labels, int n_out,
+                      const char* a, const int64_t* a_labels, int n_a,
+                      const char* b, const int64_t* b_labels, int n_b);   /* n == 0 is the DSL's "0" scalar */
+int  qxb_graph_save  (qxb_graph* g, const char* label, const char* name);
+/* Same as the calls above, from the text of a .qx file (docs/src/users_guide.md:93-164). */
+int  qxb_graph_parse_dsl(qxb_graph* g, const char* qx_text, size_t nbytes);
+/* Leaf tensor values: ComplexF64, column-major (tensor_cache.jl:52-53,90-94).  Copied. */
+int  qxb_graph_set_data(qxb_graph* g, const char* data_label, const void* c64_colmajor,
+                        const int64_t* dims, int rank);
+
+/* queries (pure host logic; usable without a GPU) */
+int  qxb_graph_num_outputs(const qxb_graph* g, int* n_outputs);
+/* k slice symbols v1..vk and their extents; dims may be NULL to query k only. */
+int  qxb_graph_num_slice_vars(const qxb_graph* g, int* k, int64_t* dims);
+int  qxb_graph_num_slices(const qxb_graph* g, int64_t* n_slices);
+/* Linear slice id -> 0-based values of v1..vk (v1 fastest).  Bit-exact bookkeeping, see DESIGN.md. */
+int  qxb_slice_values(const qxb_graph* g, int64_t slice_id, int64_t* values /*[k]*/);
+/* Lowering report (JSON): per contraction the bit-level (batch, M, N, K) split, layouts,
+ * dependency class, algorithmic flops/bytes.  `n_free` = how many low slice variables are
+ * batched (the rest are fixed); -1 = all.  Returns the number of bytes needed (incl. NUL). */
+int64_t qxb_graph_describe(qxb_graph* g, int n_free, char* buf, int64_t buflen);
+
+/* Lower the program, upload leaves, fold constants, size the workspace. */
+int  qxb_graph_compile(qxb_graph* g, const qxb_options* opts);
+
+/* THE HOT PATH.  amplitude[a] = sum_{s in [slice_begin, slice_end)} root(bits[a], s).
+ * bits: [n_amp][n_outputs] bytes, 0/1 (2 = '+', 3 = '-', basics.md:62), char i <-> qubit i.
+ * out:  [n_amp] interleaved complex of the graph's dtype.
+ * Host-pointer form: H2D of bits, compute, D2H of out, synchronised on return
+ * (replaces the "Simulation" section of QXContexts.execute and contract_tn!). */
+int  qxb_amplitudes(qxb_graph* g, const uint8_t* bits, int64_t n_amp,
+                    int64_t slice_begin, int64_t slice_end, void* out);
+/* Device-pointer form: bits and out already in HBM; asynchronous on the stream. */
+int  qxb_amplitudes_device(qxb_graph* g, const uint8_t* d_bits, int64_t n_amp,
+                           int64_t slice_begin, int64_t slice_end, void* d_out);
+
+/* Counters of the last qxb_amplitudes* call. */
+typedef struct qxb_stats {
+    int64_t kernel_launches;     /* kernels of this library launched                   */
+    int64_t contract_launches;   /* of which the contraction kernel                    */
+    double  flops;               /* algorithmic real flops executed (8 per complex MAC) */
+    double  bytes;               /* algorithmic bytes: s*(|A|+|B|+|C|) summed over launches */
+    int64_t workspace_bytes;     /* arena high-water mark                              */
+    int64_t amp_batch;           /* bitstrings per batch actually used                 */
+    int64_t n_blocks;            /* aligned slice blocks the range was split into      */
+} qxb_stats;
+int  qxb_last_stats(const qxb_graph* g, qxb_stats* st);
+/* Per-op table (name, shape, flops, bytes, ms) of the last profiled call, as JSON. */
+int  qxb_profile_dump(qxb_graph* g, const char* json_path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QXB200_H */

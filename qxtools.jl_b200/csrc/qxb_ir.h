@@ -1,0 +1,147 @@
+// qxb200 -- host-side IR of a .qx program and its bit-level lowering.
+//
+// The op set is the one build_compute_graph emits
+// (/root/reference/src/compute_graph/compute_graph.jl:15-98) with the textual
+// form of /root/reference/docs/src/users_guide.md:93-164.
+#pragma once
+#include <complex>
+#include <cstdint>
+#include <map>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace qxb {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+// ----------------------------------------------------------------- DSL level
+enum CmdKind { CMD_LOAD, CMD_OUTPUT, CMD_VIEW, CMD_NCON, CMD_SAVE };
+
+struct Cmd {
+    CmdKind kind;
+    std::string name;              // defined symbol (load/output/view/ncon) or save label
+    std::string a, b;              // view target / ncon operands / save source
+    std::string label;             // load: data label; view: slice symbol
+    std::vector<int64_t> dims;     // load dims
+    std::vector<int64_t> cl, al, bl;
+    int64_t idx = 0;               // output: 1-based qubit; view: 1-based mode
+    int64_t dim = 0;               // output dim / view bond dim
+};
+
+struct HostData {
+    std::vector<int64_t> dims;
+    std::vector<std::complex<double>> v;   // column-major
+};
+
+struct SliceVar {
+    std::string sym;
+    int64_t dim;
+    int nbits;                     // ceil(log2(dim)): free variables are padded to a power of two
+};
+
+// One DSL-level mode of a tensor.
+struct Mode {
+    int64_t ext;                   // extent seen by ncon label lists (1 once sliced)
+    int64_t full_ext;              // extent of the stored mode
+    int nbits;                     // ceil(log2(full_ext))
+    int var;                       // -1, or the slice variable this mode was viewed with
+};
+
+enum TKind { T_LOAD, T_OUTPUT, T_VIEW, T_NCON };
+
+struct TensorDef {
+    TKind kind;
+    std::string name;
+    std::vector<Mode> modes;
+    int leaf = -1;                 // load/output/view: index of the underlying load/output def
+    std::string data_label;        // load
+    int64_t out_idx = 0;           // output (1-based)
+    int a = -1, b = -1;            // ncon operands (TensorDef indices)
+    std::vector<int64_t> cl, al, bl;
+    std::set<int> vars;            // slice variables the value depends on
+    bool amp = false;              // depends on the output bitstring
+    int uses = 0;
+};
+
+struct Program {
+    std::vector<Cmd> cmds;
+    std::vector<TensorDef> defs;
+    std::map<std::string, int> by_name;
+    std::vector<SliceVar> vars;    // v1..vk in numeric order
+    std::map<std::string, int> var_by_sym;
+    int n_outputs = 0;             // max output index
+    int root = -1;                 // def index of the saved tensor
+    bool analysed = false;
+};
+
+// parsing / construction ------------------------------------------------------
+void parse_dsl(Program& p, const char* text, size_t n);
+void add_cmd(Program& p, const Cmd& c);
+// resolve names, modes, dependency sets; validates labels and extents
+void analyse(Program& p);
+int64_t num_slices(const Program& p);
+void slice_values(const Program& p, int64_t s, int64_t* out);
+
+// --------------------------------------------------------------- bit level
+// A lowered tensor is a 2^n array; "entries" say which address bits belong to
+// which logical mode.  key >= 0: DSL mode index of the def; key < 0: ~var.
+struct LayEntry { int key; int nbits; int pos; };
+
+enum Phase { PH_CONST = 0, PH_BLOCK = 1, PH_CHUNK = 2 };
+
+struct Seg { uint8_t src, dst, len, pad; };
+
+struct LTensor {
+    int def = -1;
+    std::vector<LayEntry> lay;
+    int span_bits = 0;             // address span per amplitude (dense for intermediates)
+    bool amp = false;
+    Phase phase = PH_CONST;
+    bool is_leaf = false;          // operand reads the uploaded leaf buffer directly
+    std::string data_label;        // leaf: which buffer
+    bool is_output_leaf = false;   // materialised per batch from the bitstrings
+    int64_t out_idx = 0;
+    std::vector<std::pair<int, int>> fixed;   // leaf: (var, bit position) of fixed variables
+    int64_t offset = -1;           // element offset in its phase arena
+    int first_use = -1, last_use = -1;        // op indices (within the lowered op list)
+    bool persistent = false;       // consumed by a later phase
+};
+
+struct LOp {
+    int c, a, b;                   // LTensor indices
+    Phase phase;
+    int nC = 0, nK = 0;
+    int n_batch = 0, n_m = 0, n_n = 0;   // bit counts of the (batch, M, N) split; nK bits of K
+    std::vector<Seg> segA, segB, segKA, segKB;
+    double macs_per_amp = 0;       // complex MACs per amplitude row (2^(nC+nK))
+    double elems_a = 0, elems_b = 0, elems_c = 0;   // stored elements per amplitude row
+    std::string name;
+};
+
+struct Lowered {
+    int n_free = 0;                // variables [0, n_free) are batched, the rest fixed
+    std::vector<LTensor> tensors;
+    std::vector<LOp> ops;
+    std::vector<int> output_leaves;          // LTensor indices materialised from the bitstrings
+    int root = -1;
+    int root_missing_var_factor_bits = 0;    // unused
+    std::vector<int> root_vars;              // free vars present in the root layout, in layout order
+    double root_scale = 1.0;                 // prod of extents of free vars the root does not depend on
+    // arena sizes in elements: const, block, and chunk = fixed + per_amp * n_amp
+    int64_t const_elems = 0, block_elems = 0, chunk_fixed_elems = 0, chunk_elems_per_amp = 0;
+};
+
+// Lower for a given number of free (batched) low slice variables.
+Lowered lower(const Program& p, int n_free);
+// Plan arena offsets for a batch of n_amp bitstrings (fills LTensor::offset and the arena sizes).
+void plan_memory(Lowered& L, int64_t n_amp);
+std::string describe_json(const Program& p, const Lowered& L);
+
+inline int ceil_log2(int64_t x) { int b = 0; while ((int64_t(1) << b) < x) ++b; return b; }
+
+}  // namespace qxb

@@ -1,0 +1,48 @@
+// qxb200 -- device kernels (sm_100a).
+//
+// Every tensor is a 2^n array of interleaved complex numbers; a contraction node
+// is   C[u][c] = sum_k A[u*sUA + fA(c) + gA(k)] * B[u*sUB + fB(c) + gB(k)]
+// where u is the bitstring (amplitude) row, c runs over the bits of C (tensor
+// modes AND batched slice-variable bits), and fA/fB/gA/gB are bit-scatter maps
+// given as a handful of (src, dst, len) segments.  C inherits the bit order of
+// its larger operand, so consecutive threads write consecutive C elements and
+// read (near-)consecutive A elements: the kernel streams at HBM rate for the
+// "big x small" nodes that carry the bytes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qxb {
+
+constexpr int kMaxSeg = 32;
+constexpr int kMaxKSeg = 16;
+constexpr int kKTab = 16;
+constexpr int kThreads = 256;
+constexpr int kMaxEpt = 4;          // elements per thread per tile -> tile of up to 1024 elements
+
+struct DSeg { unsigned char src, dst, len, pad; };
+
+struct OpParams {
+    const void* A;
+    const void* B;
+    void* C;
+    long long sUA, sUB, sUC;        // elements between consecutive amplitude rows (0 = shared)
+    long long tiles;                // U << (nC - tb)
+    int nC, tb, nK, U;
+    int nsA, nsB, nkA, nkB;
+    long long ktabA[kKTab], ktabB[kKTab];   // k -> offsets, used when nK <= 4
+    DSeg sA[kMaxSeg], sB[kMaxSeg], kA[kMaxKSeg], kB[kMaxKSeg];
+};
+
+struct OutLeafDesc { long long offset_per_amp; int span_bits; int out_idx; };
+
+void launch_contract(int dtype, const OpParams& p, int grid, cudaStream_t st);
+void launch_output_leaves(int dtype, void* chunk_base, const OutLeafDesc* d_desc, int n_leaves,
+                          const unsigned char* d_bits, int n_outputs, long long amp0, long long n,
+                          cudaStream_t st);
+// acc[amp0 + u] += scale * sum_{i < 2^span} root[u*sU + i]
+void launch_reduce_root(int dtype, const void* root, long long sU, int span_bits, long long n,
+                        double scale, double* acc /*interleaved*/, long long amp0, cudaStream_t st);
+void launch_finalize(int dtype, const double* acc, void* out, long long n, cudaStream_t st);
+
+}  // namespace qxb

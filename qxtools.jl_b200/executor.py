@@ -1,0 +1,189 @@
+"""Host-side handle on a compiled contraction program in ``libqxb200.so``.
+
+``Graph`` is the Python face of ``qxb_graph`` (include/qxb200.h): built either from
+``.qx`` text (``execute`` path, /root/reference/bin/qxrun.jl:83-87) or from a
+``ComputeGraph`` object (``single_amplitude`` path,
+/root/reference/src/simulation.jl:86-91 through build_compute_graph).
+All compute runs on the GPU in the library; nothing here computes amplitudes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import QXB_C32, QXB_C64, Options, Stats, check
+
+_DT = {"c32": QXB_C32, "c64": QXB_C64, "complex64": QXB_C32, "complex128": QXB_C64,
+       "ComplexF32": QXB_C32, "ComplexF64": QXB_C64}
+_CHARS = {"0": 0, "1": 1, "+": 2, "-": 3}
+
+
+def bits_from_strings(bitstrings: Sequence[str], n_outputs: int) -> np.ndarray:
+    """char i <-> qubit i <-> ``output`` index i (docs/src/basics.md:55)."""
+    out = np.zeros((len(bitstrings), max(n_outputs, 1)), dtype=np.uint8)
+    for r, s in enumerate(bitstrings):
+        if len(s) < n_outputs:
+            raise ValueError(f"bitstring {s!r} shorter than the {n_outputs} outputs of the program")
+        for c in range(n_outputs):
+            try:
+                out[r, c] = _CHARS[s[c]]
+            except KeyError:
+                raise ValueError(f"bad bitstring character {s[c]!r}") from None
+    return out[:, :n_outputs] if n_outputs else out[:, :0]
+
+
+class Graph:
+    def __init__(self, dtype: str = "c64"):
+        self._lib = _lib.load()
+        self.dtype = _DT[dtype]
+        self.np_dtype = np.complex64 if self.dtype == QXB_C32 else np.complex128
+        h = C.c_void_p()
+        check(self._lib.qxb_graph_create(C.byref(h), self.dtype))
+        self._h = h
+        self.compiled = False
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.qxb_graph_destroy(h)
+            self._h = None
+
+    # -- construction ------------------------------------------------------
+    @classmethod
+    def from_dsl(cls, text: str, data: Dict[str, np.ndarray], dtype: str = "c64") -> "Graph":
+        g = cls(dtype)
+        b = text.encode()
+        check(g._lib.qxb_graph_parse_dsl(g._h, b, len(b)))
+        g.set_data(data)
+        return g
+
+    @classmethod
+    def from_compute_graph(cls, cg, dtype: str = "c64") -> "Graph":
+        """Walk the tree post-order and issue one qxb_graph_* call per command --
+        exactly what the Julia shim does with a ``ComputeGraph``."""
+        from .compute_graph import (LoadCommand, OutputCommand, ViewCommand, ContractCommand, SaveCommand)
+        g = cls(dtype)
+        L = g._lib
+        arr = lambda xs: (C.c_int64 * max(len(xs), 1))(*xs)
+        for op in cg.commands():
+            if isinstance(op, LoadCommand):
+                check(L.qxb_graph_load(g._h, op.name.encode(), op.label.encode(), arr(op.dims), len(op.dims)))
+            elif isinstance(op, OutputCommand):
+                check(L.qxb_graph_output(g._h, op.name.encode(), op.idx, op.dim))
+            elif isinstance(op, ViewCommand):
+                check(L.qxb_graph_view(g._h, op.name.encode(), op.target.encode(), op.slice_sym.encode(),
+                                       op.bond_index, op.bond_dim))
+            elif isinstance(op, ContractCommand):
+                check(L.qxb_graph_ncon(g._h, op.output_name.encode(), arr(op.output_idxs), len(op.output_idxs),
+                                       op.left_name.encode(), arr(op.left_idxs), len(op.left_idxs),
+                                       op.right_name.encode(), arr(op.right_idxs), len(op.right_idxs)))
+            elif isinstance(op, SaveCommand):
+                check(L.qxb_graph_save(g._h, op.label.encode(), op.name.encode()))
+            else:
+                raise TypeError(op)
+        g.set_data(cg.tensors)
+        return g
+
+    def set_data(self, data: Dict[str, np.ndarray]) -> None:
+        for label, a in data.items():
+            a = np.asarray(a)
+            flat = np.ascontiguousarray(a.reshape(-1, order="F").astype(np.complex128))
+            dims = (C.c_int64 * max(a.ndim, 1))(*a.shape)
+            check(self._lib.qxb_graph_set_data(self._h, label.encode(), flat.ctypes.data_as(C.c_void_p), dims, a.ndim))
+
+    # -- queries (host logic only) -------------------------------------------
+    @property
+    def n_outputs(self) -> int:
+        n = C.c_int()
+        check(self._lib.qxb_graph_num_outputs(self._h, C.byref(n)))
+        return n.value
+
+    @property
+    def slice_dims(self) -> List[int]:
+        k = C.c_int()
+        check(self._lib.qxb_graph_num_slice_vars(self._h, C.byref(k), None))
+        d = (C.c_int64 * max(k.value, 1))()
+        check(self._lib.qxb_graph_num_slice_vars(self._h, C.byref(k), d))
+        return list(d[:k.value])
+
+    @property
+    def n_slices(self) -> int:
+        n = C.c_int64()
+        check(self._lib.qxb_graph_num_slices(self._h, C.byref(n)))
+        return n.value
+
+    def slice_values(self, s: int) -> List[int]:
+        k = len(self.slice_dims)
+        v = (C.c_int64 * max(k, 1))()
+        check(self._lib.qxb_slice_values(self._h, s, v))
+        return list(v[:k])
+
+    def describe(self, n_free: int = -1) -> dict:
+        need = check(self._lib.qxb_graph_describe(self._h, n_free, None, 0))
+        buf = C.create_string_buffer(need)
+        check(self._lib.qxb_graph_describe(self._h, n_free, buf, need))
+        return json.loads(buf.value.decode())
+
+    # -- compute -------------------------------------------------------------
+    def compile(self, hbm_budget_bytes: int = 0, amp_batch: int = 0, profile: bool = False) -> "Graph":
+        o = Options(hbm_budget_bytes, amp_batch, 1 if profile else 0, 0)
+        check(self._lib.qxb_graph_compile(self._h, C.byref(o)))
+        self.compiled = True
+        return self
+
+    def amplitudes(self, bitstrings, slice_begin: int = 0, slice_end: Optional[int] = None) -> np.ndarray:
+        """Host-buffer entry: H2D of the bitstrings, compute, D2H of the amplitudes."""
+        if isinstance(bitstrings, np.ndarray) and bitstrings.dtype == np.uint8:
+            bits = np.ascontiguousarray(bitstrings)
+        else:
+            bits = np.ascontiguousarray(bits_from_strings(list(bitstrings), self.n_outputs))
+        n = bits.shape[0]
+        if slice_end is None:
+            slice_end = self.n_slices
+        out = np.zeros(n, dtype=self.np_dtype)
+        check(self._lib.qxb_amplitudes(self._h, bits.ctypes.data_as(C.c_void_p), n, slice_begin, slice_end,
+                                       out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def amplitudes_device(self, d_bits_ptr: int, n_amp: int, d_out_ptr: int, slice_begin: int = 0,
+                          slice_end: Optional[int] = None) -> None:
+        """Device-pointer entry (asynchronous on the library's stream)."""
+        if slice_end is None:
+            slice_end = self.n_slices
+        check(self._lib.qxb_amplitudes_device(self._h, C.c_void_p(d_bits_ptr), n_amp, slice_begin, slice_end,
+                                              C.c_void_p(d_out_ptr)))
+
+    def stats(self) -> dict:
+        s = Stats()
+        check(self._lib.qxb_last_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def profile_dump(self, path: str) -> dict:
+        check(self._lib.qxb_profile_dump(self._h, path.encode()))
+        with open(path) as f:
+            return json.load(f)
+
+
+def init(device: int = 0) -> None:
+    check(_lib.load().qxb_init(device))
+
+
+def set_stream(stream_ptr: int) -> None:
+    check(_lib.load().qxb_set_stream(C.c_void_p(stream_ptr)))
+
+
+def synchronize() -> None:
+    check(_lib.load().qxb_device_synchronize())
+
+
+def amplitudes_for_network(tnc, plan, bitstrings: Sequence[str], dtype: str = "c64") -> np.ndarray:
+    """``contract_tn!`` for a batch of bitstrings: build the (unsliced) compute graph
+    once, then one library call (simulation.jl:86-91, compute_graph.jl:15-98)."""
+    from .compute_graph import build_compute_graph
+    cg = build_compute_graph(tnc, plan)
+    g = Graph.from_compute_graph(cg, dtype).compile()
+    return g.amplitudes(list(bitstrings))
