@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- amplitudes/s of the QXTools contraction hot path on B200.
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+`--amps` output bitstrings x ALL slices of the sliced RQC program, summed to
+amplitudes (what QXContexts.execute's "Simulation" section does,
+/root/reference/bin/qxrun.jl:83-87; reference timings docs/src/distributed.md:79-103).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference ...                     # the CPU restatement (oracle/) on host cores
+
+value : whole-job amplitudes/s, bitstrings already resident in HBM, timed with CUDA
+        events on the launching stream (max over ranks)
+e2e   : the same through the host-buffer C-ABI call qxb_amplitudes (pinned host
+        bitstrings -> H2D -> contraction -> D2H of the amplitudes inside the timed region)
+N > 1 : the linear slice-id space is split into N contiguous ranges, one process
+        per GPU (torchrun), partial amplitudes combined by ONE NCCL all-reduce of
+        [n_amp] complex numbers -> "scaling": "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+WORKLOADS = {
+    # BASELINE.json configs[3]: RQC 7x7 depth 20, ComplexF64, 2^12 slices (the multi-GPU config)
+    "rqc_7x7_d20_c64_s4096": dict(rows=7, cols=7, depth=20, n_slice=12, dtype="c64", seed=42),
+    # BASELINE.json configs[2]: RQC 6x6 depth 16, ComplexF32, 2^6 slices
+    "rqc_6x6_d16_c32_s64": dict(rows=6, cols=6, depth=16, n_slice=6, dtype="c32", seed=42),
+    "rqc_4x4_d12_c64_s16": dict(rows=4, cols=4, depth=12, n_slice=4, dtype="c64", seed=42),
+}
+DEFAULT_WORKLOAD = "rqc_7x7_d20_c64_s4096"
+
+
+def build_workload(name):
+    """Seeded synthetic file triple (the reference planner/FlowCutter cannot run here)."""
+    import qxb200 as q
+    w = WORKLOADS[name]
+    cache = os.path.join(ROOT, "workloads", name)
+    if os.path.exists(cache + ".qx") and os.path.exists(cache + ".npz"):
+        txt = open(cache + ".qx").read()
+        data = dict(np.load(cache + ".npz"))
+    else:
+        circ = q.create_rqc_circuit(w["rows"], w["cols"], w["depth"], w["seed"])
+        tnc = q.convert_to_tnc(circ)
+        bg, plan, meta = q.contraction_scheme(tnc, w["n_slice"], time=0, seed=w["seed"])
+        cg = q.build_compute_graph(tnc, plan, bg)
+        txt, data = cg.dsl(meta), dict(cg.tensors)
+    return txt, data, w
+
+
+def synth_bits(n_amp, n_qubits, seed=2020):
+    return np.random.default_rng(seed).integers(0, 2, (n_amp, n_qubits)).astype(np.uint8)
+
+
+# ------------------------------------------------------------------ CPU arms
+def _cpu_task(args):
+    txt, data, bitstring, s0, s1, dtype = args
+    from oracle import qx_oracle as orc
+    cmds = _cpu_task.cache.get(hash(txt))
+    if cmds is None:
+        cmds = orc.parse_dsl(txt)
+        _cpu_task.cache[hash(txt)] = cmds
+    return orc.amplitude(cmds, data, bitstring, np.complex64 if dtype == "c32" else np.complex128, s0, s1)
+
+
+_cpu_task.cache = {}
+
+
+def cpu_sample(txt, data, w, n_bitstrings, n_slices_sample, cores):
+    """Time the oracle (the CPU restatement of the reference loop) on a bounded
+    sample: n_bitstrings x the first n_slices_sample slices, spread over `cores`
+    processes; extrapolate linearly in the slice count (slices are independent,
+    equal-cost units) to amplitudes/s for the full slice space."""
+    import multiprocessing as mp
+    from oracle import qx_oracle as orc
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    n_q = w["rows"] * w["cols"]
+    bits = synth_bits(n_bitstrings, n_q)
+    bss = ["".join("01"[b] for b in row) for row in bits]
+    total_slices = 1
+    for _, d in orc.slice_dims(orc.parse_dsl(txt)):
+        total_slices *= d
+    n_slices_sample = min(n_slices_sample, total_slices)
+    per = max(1, n_slices_sample // max(1, cores // max(1, n_bitstrings)))
+    tasks = []
+    for b in bss:
+        for s0 in range(0, n_slices_sample, per):
+            tasks.append((txt, data, b, s0, min(s0 + per, n_slices_sample), w["dtype"]))
+    t0 = time.perf_counter()
+    if cores > 1:
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_cpu_task, tasks, chunksize=1)
+    else:
+        for t in tasks:
+            _cpu_task(t)
+    dt = time.perf_counter() - t0
+    inst_per_s = n_bitstrings * n_slices_sample / dt
+    amps_per_s = inst_per_s / total_slices
+    sample = (f"{n_bitstrings} bitstrings x first {n_slices_sample} of {total_slices} slices "
+              f"({n_bitstrings * n_slices_sample} contractions) in {dt:.1f}s, numpy {np.__version__} oracle, "
+              f"{cores} processes x 1 BLAS thread; extrapolated linearly to all slices")
+    return amps_per_s, dt, sample
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores.  The
+    real reference (Julia QXContexts) cannot be installed here (no Julia, no network;
+    DESIGN.md), so this is the oracle port."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    txt, data, w = build_workload(args.workload)
+    cores = os.cpu_count() or 1
+    vals, times = [], []
+    sample = ""
+    n_bs = max(1, min(4, cores))
+    for i in range(args.warmup + args.steps):
+        v, dt, sample = cpu_sample(txt, data, w, n_bs, args.ref_slices, cores)
+        if i >= args.warmup:
+            vals.append(v)
+            times.append(dt)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "RQC amplitudes/sec", "value": value, "unit": "amplitudes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+        "config": {"workload": args.workload, "n_amp": n_bs, "sample_slices": args.ref_slices},
+        "cpu_baseline": {"value": value, "unit": "amplitudes/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "amplitudes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from qxb200.executor import Graph, init, set_stream
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    init(local)
+    dev = torch.device("cuda", local)
+    # a real (non-null) stream shared by torch (events, NCCL) and the library's launches
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    set_stream(stream.cuda_stream)
+
+    txt, data, w = build_workload(args.workload)
+    n_q = w["rows"] * w["cols"]
+    g = Graph.from_dsl(txt, data, w["dtype"]).compile(amp_batch=args.amp_batch, cuda_graph=not args.no_graph)
+    S = g.n_slices
+    # contiguous slice-range partition; identical bitstrings on every rank
+    s0, s1 = (S * rank) // world, (S * (rank + 1)) // world
+    n_amp = args.amps
+    bits_h = torch.from_numpy(synth_bits(n_amp, n_q)).pin_memory()
+    bits_d = bits_h.to(dev)
+    cdt = torch.complex64 if w["dtype"] == "c32" else torch.complex128
+    out_d = torch.zeros(n_amp, dtype=cdt, device=dev)
+    out_h = torch.zeros(n_amp, dtype=cdt).pin_memory()
+    out_h_np = out_h.numpy()
+    bits_h_np = bits_h.numpy()
+
+    def step_device():
+        g.amplitudes_device(bits_d.data_ptr(), n_amp, out_d.data_ptr(), s0, s1)
+        if world > 1:
+            dist.all_reduce(torch.view_as_real(out_d))
+
+    def step_e2e():
+        # the public host-buffer call: pinned bitstrings -> H2D -> contraction -> D2H, synchronised
+        from qxb200._lib import check
+        import ctypes as C
+        check(g._lib.qxb_amplitudes(g._h, C.c_void_p(bits_h.data_ptr()), n_amp, s0, s1, C.c_void_p(out_h.data_ptr())))
+        if world > 1:
+            t = torch.view_as_real(out_h.to(dev, non_blocking=True))
+            dist.all_reduce(t)
+            out_h.copy_(torch.view_as_complex(t), non_blocking=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    st = g.stats()
+    # e2e
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    ms_e2e = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    result = out_d.cpu().numpy()
+
+    if rank == 0:
+        ms_step = ms / args.steps
+        value = n_amp / (ms_step * 1e-3)
+        e2e = n_amp / (ms_e2e / args.steps * 1e-3)
+        # sanity: Porter-Thomas / norm check -- mean |amp|^2 * 2^n should be ~1 for an RQC
+        norm = float(np.mean(np.abs(result) ** 2) * 2.0 ** n_q)
+        roof = roofline(args, g, txt, data, w, bits_d, out_d, n_amp, s0, s1)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            v, dt, sample = cpu_sample(txt, data, w, max(1, min(4, cores)), args.ref_slices, cores)
+            cpu = {"value": v, "unit": "amplitudes/s", "cores": cores, "kind": "port", "sample": sample}
+        es = 8 if w["dtype"] == "c32" else 16
+        line = {
+            "metric": "RQC amplitudes/sec", "value": value, "unit": "amplitudes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64" if w["dtype"] == "c64" else "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "n_amp_per_step": n_amp, "n_slices": S,
+                       "n_qubits": n_q, "complex": w["dtype"], "slice_partition": f"contiguous/{world}",
+                       "l2": f"working set {st['workspace_bytes'] / 1e9:.2f} GB per GPU >> 126 MB L2 (no flush needed)",
+                       "amp_batch": st["amp_batch"], "mean_p_times_2^n": norm},
+            "e2e": {"value": e2e, "unit": "amplitudes/s", "h2d_bytes_per_step": int(n_amp * n_q),
+                    "d2h_bytes_per_step": int(n_amp * es)},
+            "gpu_launches": int(st["kernel_launches"]) * args.steps,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "algorithmic": {"gflop_per_step": st["flops"] / 1e9, "gb_per_step": st["bytes"] / 1e9,
+                            "launches_per_step": int(st["kernel_launches"])},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline(args, g, txt, data, w, bits_d, out_d, n_amp, s0, s1):
+    """Per-op CUDA-event timing of one more step (same stream, same inputs) on a
+    profiled clone of the graph; the reported kernel is the contraction kernel over
+    the DOMINANT contractions = top ops by FLOPs covering >= 80% of the step's FLOPs
+    (SURVEY.md 8d).  achieved = algorithmic bytes s*(|A|+|B|+|C|) / event time."""
+    from qxb200.executor import Graph
+    gp = Graph.from_dsl(txt, data, w["dtype"]).compile(amp_batch=args.amp_batch, profile=True)
+    for _ in range(2):
+        gp.amplitudes_device(bits_d.data_ptr(), n_amp, out_d.data_ptr(), s0, s1)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    prof = gp.profile_dump(os.path.join(ROOT, "gpurun_out", f"op_profile_{args.workload}.json"))
+    ops = [o for v in prof["variants"] for o in v["ops"]]
+    tot_fl = sum(o["flops"] for o in ops) or 1.0
+    ops.sort(key=lambda o: -o["flops"])
+    dom, acc = [], 0.0
+    for o in ops:
+        dom.append(o); acc += o["flops"]
+        if acc >= 0.8 * tot_fl:
+            break
+    by = sum(o["bytes"] for o in dom); ms = sum(o["ms"] for o in dom); fl = sum(o["flops"] for o in dom)
+    launches = sum(o["launches"] for o in dom)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload)
+    all_ms = sum(o["ms"] for o in ops)
+    return {"bound": "hbm", "kernel": "contract_kernel (dominant contractions: top ops by FLOPs covering >=80%)",
+            "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s",
+            "frac": achieved / peak if peak else None, "traffic": traffic,
+            "bytes_per_launch": by / max(launches, 1), "ms_per_launch": ms / max(launches, 1),
+            "dominant_ops": len(dom), "dominant_ms": ms, "all_contract_ms": all_ms,
+            "dominant_gflops": fl / (ms * 1e-3) / 1e9 if ms > 0 else 0.0,
+            "all_ops_achieved": sum(o["bytes"] for o in ops) / (all_ms * 1e-3) / 1e9 if all_ms > 0 else 0.0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="qxb200", choices=["qxb200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--amps", type=int, default=1024, help="bitstrings per step")
+    ap.add_argument("--amp-batch", type=int, default=0)
+    ap.add_argument("--ref-slices", type=int, default=64, help="slices per bitstring in the CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels directly (no CUDA-graph replay)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -47,7 +47,7 @@ typedef struct qxb_options {
     int64_t hbm_budget_bytes;  /* workspace budget per device; 0 = 60% of free memory            */
     int64_t amp_batch;         /* max bitstrings contracted per launch; 0 = as many as fit       */
     int32_t profile;           /* 1 = record a CUDA-event pair around every op (qxb_profile_dump) */
-    int32_t reserved;
+    int32_t no_cuda_graph;     /* 1 = launch every kernel directly instead of replaying a captured step */
 } qxb_options;
 
 /* library */

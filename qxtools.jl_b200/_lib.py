@@ -33,7 +33,7 @@ class QxbError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("hbm_budget_bytes", C.c_int64), ("amp_batch", C.c_int64),
-                ("profile", C.c_int32), ("reserved", C.c_int32)]
+                ("profile", C.c_int32), ("no_cuda_graph", C.c_int32)]
 
 
 class Stats(C.Structure):

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <memory>
 #include <sstream>
+#include <tuple>
 
 #include "../../include/qxb200.h"
 #include "qxb_ir.h"
@@ -55,8 +56,8 @@ void ensure_init() {
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
-    void reserve(size_t n) {
-        if (n <= bytes) return;
+    bool reserve(size_t n) {      // true when the buffer moved
+        if (n <= bytes) return false;
         if (p) { cudaFree(p); p = nullptr; bytes = 0; }
         cudaError_t e = cudaMalloc(&p, n);
         if (e != cudaSuccess) {
@@ -64,6 +65,7 @@ struct DevBuf {
             throw Error(QXB_ERR_MEM, "cudaMalloc of " + std::to_string(n) + " bytes failed: " + cudaGetErrorString(e));
         }
         bytes = n;
+        return true;
     }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
@@ -80,6 +82,16 @@ struct Variant {
 
 struct EventPair { cudaEvent_t a, b; int variant, op; };
 
+// A whole qxb_amplitudes step captured as a CUDA graph, keyed by everything the
+// launches depend on.  Replay removes ~550 launch gaps per step.
+struct StepKey {
+    const void* bits; void* out; int64_t n_amp, s0, s1; cudaStream_t st;
+    bool operator<(const StepKey& o) const {
+        return std::tie(bits, out, n_amp, s0, s1, st) < std::tie(o.bits, o.out, o.n_amp, o.s0, o.s1, o.st);
+    }
+};
+struct StepGraph { cudaGraphExec_t exec = nullptr; qxb_stats stats{}; };
+
 }  // namespace
 
 struct qxb_graph {
@@ -94,12 +106,18 @@ struct qxb_graph {
     qxb_stats stats{};
     std::vector<EventPair> events;
     size_t events_used = 0;
+    std::map<StepKey, StepGraph> step_graphs;
+    void drop_step_graphs() {
+        for (auto& kv : step_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        step_graphs.clear();
+    }
     size_t es() const { return dtype == QXB_C32 ? 8 : 16; }
     ~qxb_graph() {
         for (auto& kv : leafbuf) kv.second.release();
         for (auto& kv : variants) { kv.second->const_arena.release(); kv.second->outleaf_desc.release(); }
         block_arena.release(); chunk_arena.release(); acc.release(); d_bits.release(); d_out.release();
         for (auto& e : events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        drop_step_graphs();
     }
 };
 
@@ -173,24 +191,87 @@ char* tensor_ptr(const RunCtx& c, const LTensor& T) {
     return (char*)c.v->const_arena.p + (T.offset + off) * es;
 }
 
-void build_templates(Variant& v) {
+// Split the bits of C into thread bits / register-tile bits / hi bits and compose
+// the address maps accordingly (see contract_kernel).
+void build_templates(Variant& v, int dtype) {
     v.tmpl.resize(v.L.ops.size());
     v.prof.assign(v.L.ops.size(), OpProfile{});
     for (size_t i = 0; i < v.L.ops.size(); ++i) {
         const LOp& op = v.L.ops[i];
         OpParams& p = v.tmpl[i];
         memset(&p, 0, sizeof(p));
-        if (op.segA.size() > kMaxSeg || op.segB.size() > kMaxSeg || op.segKA.size() > kMaxKSeg ||
-            op.segKB.size() > kMaxKSeg)
-            throw Error(QXB_ERR_UNSUPP, "ncon " + op.name + ": too many address segments");
-        p.nC = op.nC; p.nK = op.nK;
-        p.tb = std::min(op.nC, 8 + 2);
-        p.nsA = (int)op.segA.size(); p.nsB = (int)op.segB.size();
-        p.nkA = (int)op.segKA.size(); p.nkB = (int)op.segKB.size();
-        auto cp = [](DSeg* dst, const std::vector<Seg>& s) {
-            for (size_t j = 0; j < s.size(); ++j) dst[j] = DSeg{s[j].src, s[j].dst, s[j].len, 0};
+        const int nC = op.nC;
+        std::vector<int> mapA(nC, -1), mapB(nC, -1);
+        for (auto& s : op.segA) for (int b = 0; b < s.len; ++b) mapA[s.src + b] = s.dst + b;
+        for (auto& s : op.segB) for (int b = 0; b < s.len; ++b) mapB[s.src + b] = s.dst + b;
+        p.nC = nC; p.nK = op.nK;
+        p.lob = std::min(nC, 8);
+        // register tile: lowest M-only / N-only bits above the thread bits
+        const int kk = op.nK <= 3 ? (1 << op.nK) : 1;
+        const int regs_per = dtype == QXB_C32 ? 2 : 4;
+        int max_tile_loads = 96 / (regs_per * kk);           // (2^ma + 2^nb) * K * regs <= ~96
+        std::vector<int> mbits, nbits;
+        for (int b = p.lob; b < nC; ++b) {
+            if (mapA[b] >= 0 && mapB[b] < 0 && mbits.size() < 2) mbits.push_back(b);
+            else if (mapB[b] >= 0 && mapA[b] < 0 && nbits.size() < 2) nbits.push_back(b);
+        }
+        while ((int)((1u << mbits.size()) + (1u << nbits.size())) > std::max(2, max_tile_loads)) {
+            if (mbits.size() >= nbits.size() && !mbits.empty()) mbits.pop_back();
+            else if (!nbits.empty()) nbits.pop_back();
+            else break;
+        }
+        p.ma = (int)mbits.size(); p.nb = (int)nbits.size();
+        std::vector<bool> is_tile(nC, false);
+        for (int b : mbits) is_tile[b] = true;
+        for (int b : nbits) is_tile[b] = true;
+        for (int jm = 0; jm < (1 << p.ma); ++jm) {
+            long long a = 0, c = 0;
+            for (int t = 0; t < p.ma; ++t) if ((jm >> t) & 1) { a |= 1ll << mapA[mbits[t]]; c |= 1ll << mbits[t]; }
+            p.aT[jm] = a;
+            for (int jn = 0; jn < (1 << p.nb); ++jn) {
+                long long b = 0, c2 = c;
+                for (int t = 0; t < p.nb; ++t) if ((jn >> t) & 1) { b |= 1ll << mapB[nbits[t]]; c2 |= 1ll << nbits[t]; }
+                p.bT[jn] = b;
+                p.cT[jm * (1 << p.nb) + jn] = c2;
+            }
+        }
+        // thread-bit and hi-bit segment maps
+        std::vector<std::pair<int, std::pair<int, int>>> alo, blo, ahi, bhi, chi;
+        for (int b = 0; b < p.lob; ++b) {
+            if (mapA[b] >= 0) alo.push_back({b, {mapA[b], 1}});
+            if (mapB[b] >= 0) blo.push_back({b, {mapB[b], 1}});
+        }
+        int h = 0;
+        for (int b = p.lob; b < nC; ++b) {
+            if (is_tile[b]) continue;
+            chi.push_back({h, {b, 1}});
+            if (mapA[b] >= 0) ahi.push_back({h, {mapA[b], 1}});
+            if (mapB[b] >= 0) bhi.push_back({h, {mapB[b], 1}});
+            ++h;
+        }
+        p.hb = h;
+        auto merge = [](const std::vector<std::pair<int, std::pair<int, int>>>& parts, DSeg* dst, int cap,
+                        const std::string& name) {
+            int n = 0;
+            for (auto& pr : parts) {
+                const int src = pr.first, d = pr.second.first, len = pr.second.second;
+                if (n > 0 && dst[n - 1].src + dst[n - 1].len == src && dst[n - 1].dst + dst[n - 1].len == d) {
+                    dst[n - 1].len = (unsigned char)(dst[n - 1].len + len);
+                } else {
+                    if (n == cap) throw Error(QXB_ERR_UNSUPP, "ncon " + name + ": too many address segments");
+                    dst[n++] = DSeg{(unsigned char)src, (unsigned char)d, (unsigned char)len, 0};
+                }
+            }
+            return n;
         };
-        cp(p.sA, op.segA); cp(p.sB, op.segB); cp(p.kA, op.segKA); cp(p.kB, op.segKB);
+        p.nsAlo = merge(alo, p.sAlo, 8, op.name); p.nsBlo = merge(blo, p.sBlo, 8, op.name);
+        p.nsAhi = merge(ahi, p.sAhi, kMaxSeg, op.name); p.nsBhi = merge(bhi, p.sBhi, kMaxSeg, op.name);
+        p.nsChi = merge(chi, p.sChi, kMaxSeg, op.name);
+        if (op.segKA.size() > kMaxKSeg || op.segKB.size() > kMaxKSeg)
+            throw Error(QXB_ERR_UNSUPP, "ncon " + op.name + ": too many address segments");
+        p.nkA = (int)op.segKA.size(); p.nkB = (int)op.segKB.size();
+        for (size_t j = 0; j < op.segKA.size(); ++j) p.kA[j] = DSeg{op.segKA[j].src, op.segKA[j].dst, op.segKA[j].len, 0};
+        for (size_t j = 0; j < op.segKB.size(); ++j) p.kB[j] = DSeg{op.segKB[j].src, op.segKB[j].dst, op.segKB[j].len, 0};
         if (op.nK <= 4) {
             for (int k = 0; k < (1 << op.nK); ++k) {
                 long long a = 0, b = 0;
@@ -216,8 +297,8 @@ void run_phase(const RunCtx& c, Phase ph) {
         p.sUB = B.amp ? (1ll << B.span_bits) : 0;
         p.sUC = C.amp ? (1ll << C.span_bits) : 0;
         p.U = C.amp ? (int)c.n : 1;
-        p.tiles = (long long)p.U << (p.nC - p.tb);
-        const int sub_bits = p.tb < 8 ? 8 - p.tb : 0;
+        p.tiles = (long long)p.U << p.hb;
+        const int sub_bits = 8 - p.lob;
         long long blocks = (p.tiles + (1ll << sub_bits) - 1) >> sub_bits;
         const long long cap = (long long)g_num_sms * 8;
         const int grid = (int)std::max<long long>(1, std::min(blocks, cap));
@@ -254,7 +335,7 @@ Variant* get_variant(qxb_graph* g, int n_free) {
     std::unique_ptr<Variant> v(new Variant());
     v->L = lower(g->prog, n_free);
     plan_memory(v->L, 1);
-    build_templates(*v);
+    build_templates(*v, g->dtype);
     const size_t es = g->es();
     v->const_arena.reserve(std::max<int64_t>(v->L.const_elems, 2) * es);
     std::vector<OutLeafDesc> descs;
@@ -297,49 +378,64 @@ std::vector<Block> decompose(const Program& p, int64_t b, int64_t e) {
     return out;
 }
 
-void run_amplitudes(qxb_graph* g, const uint8_t* d_bits, int64_t n_amp, int64_t s0, int64_t s1, void* d_out) {
-    if (!g->compiled) throw Error(QXB_ERR_STATE, "graph not compiled");
-    const int64_t S = num_slices(g->prog);
-    if (s0 < 0 || s1 > S || s0 > s1) throw Error(QXB_ERR_ARG, "slice range out of bounds");
-    if (n_amp < 0) throw Error(QXB_ERR_ARG, "negative amplitude count");
-    g->stats = qxb_stats{};
-    g->events_used = 0;
-    for (auto& kv : g->variants) kv.second->prof.assign(kv.second->L.ops.size(), OpProfile{});
-    cudaStream_t st = stream();
-    if (n_amp == 0) return;
-    g->acc.reserve(sizeof(double) * 2 * n_amp);
-    CUDA_OK(cudaMemsetAsync(g->acc.p, 0, sizeof(double) * 2 * n_amp, st));
-    const size_t es = g->es();
-    std::vector<Block> blocks = decompose(g->prog, s0, s1);
-    g->stats.n_blocks = (int64_t)blocks.size();
+struct StepPlan {
+    std::vector<Block> blocks;
+    std::vector<Variant*> variants;
+    int64_t chunk = 0;
+};
+
+// Everything that may allocate, synchronise or query the device happens here,
+// outside stream capture.
+StepPlan prepare_step(qxb_graph* g, int64_t n_amp, int64_t s0, int64_t s1) {
+    StepPlan sp;
+    sp.blocks = decompose(g->prog, s0, s1);
     size_t free_b = 0, total_b = 0;
     CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
-    for (const Block& blk : blocks) {
+    const size_t es = g->es();
+    int64_t budget = g->opts.hbm_budget_bytes > 0
+                         ? g->opts.hbm_budget_bytes
+                         : (int64_t)(0.6 * (double)(free_b + g->block_arena.bytes + g->chunk_arena.bytes));
+    int64_t chunk = n_amp;
+    if (g->opts.amp_batch > 0) chunk = std::min<int64_t>(chunk, g->opts.amp_batch);
+    int64_t max_block = 2 * (int64_t)es, max_per_amp = 2 * (int64_t)es;
+    for (const Block& blk : sp.blocks) {
         Variant* v = get_variant(g, blk.n_free);
-        Lowered& L = v->L;
-        // workspace sizing against the HBM budget
-        int64_t budget = g->opts.hbm_budget_bytes > 0
-                             ? g->opts.hbm_budget_bytes
-                             : (int64_t)(0.6 * (double)(free_b + g->block_arena.bytes + g->chunk_arena.bytes));
-        const int64_t block_bytes = std::max<int64_t>(L.block_elems, 2) * es;
-        const int64_t per_amp = std::max<int64_t>(L.chunk_elems_per_amp, 2) * es;
-        int64_t chunk = n_amp;
-        if (g->opts.amp_batch > 0) chunk = std::min<int64_t>(chunk, g->opts.amp_batch);
+        sp.variants.push_back(v);
+        const int64_t block_bytes = std::max<int64_t>(v->L.block_elems, 2) * es;
+        const int64_t per_amp = std::max<int64_t>(v->L.chunk_elems_per_amp, 2) * es;
         const int64_t fit = (budget - block_bytes) / per_amp;
         if (fit < 1)
             throw Error(QXB_ERR_MEM, "workspace for one bitstring (" + std::to_string(block_bytes + per_amp) +
                                          " bytes) exceeds the HBM budget (" + std::to_string(budget) + ")");
         chunk = std::min(chunk, fit);
-        g->block_arena.reserve(block_bytes);
-        g->chunk_arena.reserve(per_amp * chunk);
-        g->stats.amp_batch = chunk;
+        max_block = std::max(max_block, block_bytes);
+        max_per_amp = std::max(max_per_amp, per_amp);
         g->stats.workspace_bytes = std::max<int64_t>(g->stats.workspace_bytes,
-                                                      block_bytes + per_amp * chunk + (int64_t)v->const_arena.bytes);
+                                                      block_bytes + (int64_t)v->const_arena.bytes);
+    }
+    sp.chunk = chunk;
+    bool moved = g->acc.reserve(sizeof(double) * 2 * n_amp);
+    moved |= g->block_arena.reserve(max_block);
+    moved |= g->chunk_arena.reserve(max_per_amp * chunk);
+    if (moved) g->drop_step_graphs();
+    g->stats.workspace_bytes += max_per_amp * chunk;
+    g->stats.amp_batch = chunk;
+    g->stats.n_blocks = (int64_t)sp.blocks.size();
+    return sp;
+}
+
+void issue_step(qxb_graph* g, const StepPlan& sp, const uint8_t* d_bits, int64_t n_amp, void* d_out) {
+    cudaStream_t st = stream();
+    CUDA_OK(cudaMemsetAsync(g->acc.p, 0, sizeof(double) * 2 * n_amp, st));
+    for (size_t bi = 0; bi < sp.blocks.size(); ++bi) {
+        const Block& blk = sp.blocks[bi];
+        Variant* v = sp.variants[bi];
+        Lowered& L = v->L;
         RunCtx c{g, v, blk.n_free, blk.vals.data(), 1};
         run_phase(c, PH_BLOCK);
         const LTensor& R = L.tensors[L.root];
-        for (int64_t a0 = 0; a0 < n_amp; a0 += chunk) {
-            c.n = std::min(chunk, n_amp - a0);
+        for (int64_t a0 = 0; a0 < n_amp; a0 += sp.chunk) {
+            c.n = std::min(sp.chunk, n_amp - a0);
             if (!L.output_leaves.empty()) {
                 launch_output_leaves(g->dtype, g->chunk_arena.p, (const OutLeafDesc*)v->outleaf_desc.p,
                                      (int)L.output_leaves.size(), d_bits, g->prog.n_outputs, a0, c.n, st);
@@ -353,7 +449,50 @@ void run_amplitudes(qxb_graph* g, const uint8_t* d_bits, int64_t n_amp, int64_t 
     }
     launch_finalize(g->dtype, (const double*)g->acc.p, d_out, n_amp, st);
     g->stats.kernel_launches++;
-    CUDA_OK(cudaGetLastError());
+}
+
+void run_amplitudes(qxb_graph* g, const uint8_t* d_bits, int64_t n_amp, int64_t s0, int64_t s1, void* d_out) {
+    if (!g->compiled) throw Error(QXB_ERR_STATE, "graph not compiled");
+    const int64_t S = num_slices(g->prog);
+    if (s0 < 0 || s1 > S || s0 > s1) throw Error(QXB_ERR_ARG, "slice range out of bounds");
+    if (n_amp < 0) throw Error(QXB_ERR_ARG, "negative amplitude count");
+    g->stats = qxb_stats{};
+    g->events_used = 0;
+    for (auto& kv : g->variants) kv.second->prof.assign(kv.second->L.ops.size(), OpProfile{});
+    if (n_amp == 0) return;
+    cudaStream_t st = stream();
+    StepPlan sp = prepare_step(g, n_amp, s0, s1);
+    const bool use_graph = !g->opts.profile && !g->opts.no_cuda_graph;
+    if (!use_graph) {
+        issue_step(g, sp, d_bits, n_amp, d_out);
+        CUDA_OK(cudaGetLastError());
+        return;
+    }
+    StepKey key{d_bits, d_out, n_amp, s0, s1, st};
+    auto it = g->step_graphs.find(key);
+    if (it == g->step_graphs.end()) {
+        if (g->step_graphs.size() >= 32) g->drop_step_graphs();
+        const qxb_stats pre = g->stats;
+        CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        cudaGraph_t graph = nullptr;
+        try {
+            issue_step(g, sp, d_bits, n_amp, d_out);
+        } catch (...) {
+            cudaStreamEndCapture(st, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            g->stats = pre;
+            throw;
+        }
+        CUDA_OK(cudaStreamEndCapture(st, &graph));
+        StepGraph sg;
+        cudaError_t e = cudaGraphInstantiate(&sg.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) throw Error(QXB_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        sg.stats = g->stats;
+        it = g->step_graphs.emplace(key, sg).first;
+    }
+    g->stats = it->second.stats;
+    CUDA_OK(cudaGraphLaunch(it->second.exec, st));
 }
 
 void collect_profile(qxb_graph* g) {

@@ -27,11 +27,18 @@ struct OpParams {
     const void* B;
     void* C;
     long long sUA, sUB, sUC;        // elements between consecutive amplitude rows (0 = shared)
-    long long tiles;                // U << (nC - tb)
-    int nC, tb, nK, U;
-    int nsA, nsB, nkA, nkB;
+    long long tiles;                // U << hb
+    int nC, nK, U;
+    int lob;                        // low C bits covered by the threads of a block (<= 8)
+    int ma, nb;                     // register tile: 2^ma M-only bits x 2^nb N-only bits per thread
+    int hb;                         // remaining ("hi") C bits, enumerated by the tile index
+    int nsAlo, nsBlo, nsAhi, nsBhi, nsChi, nkA, nkB;
     long long ktabA[kKTab], ktabB[kKTab];   // k -> offsets, used when nK <= 4
-    DSeg sA[kMaxSeg], sB[kMaxSeg], kA[kMaxKSeg], kB[kMaxKSeg];
+    long long aT[4], bT[4];         // register-tile offsets into A (M bits) and B (N bits)
+    long long cT[16];               // register-tile offsets into C, index jm * 2^nb + jn
+    DSeg sAlo[8], sBlo[8];          // thread-bit part of the address maps
+    DSeg sAhi[kMaxSeg], sBhi[kMaxSeg], sChi[kMaxSeg];   // hi-index part
+    DSeg kA[kMaxKSeg], kB[kMaxKSeg];
 };
 
 struct OutLeafDesc { long long offset_per_amp; int span_bits; int out_idx; };
