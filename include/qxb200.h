@@ -48,6 +48,9 @@ typedef struct qxb_options {
     int64_t amp_batch;         /* max bitstrings contracted per launch; 0 = as many as fit       */
     int32_t profile;           /* 1 = record a CUDA-event pair around every op (qxb_profile_dump) */
     int32_t no_cuda_graph;     /* 1 = launch every kernel directly instead of replaying a captured step */
+    int32_t sum_at_root;       /* 1 = keep every batched slice variable open until the root and sum there;
+                                  0 (default) = sum each one at the lowest node covering all its leaves   */
+    int32_t reserved;
 } qxb_options;
 
 /* library */
@@ -91,6 +94,8 @@ int  qxb_slice_values(const qxb_graph* g, int64_t slice_id, int64_t* values /*[k
  * batched (the rest are fixed); -1 = all.  Returns the number of bytes needed (incl. NUL). */
 int64_t qxb_graph_describe(qxb_graph* g, int n_free, char* buf, int64_t buflen);
 
+/* Set options before qxb_graph_describe / qxb_graph_compile (compile(opts != NULL) overrides). */
+int  qxb_graph_configure(qxb_graph* g, const qxb_options* opts);
 /* Lower the program, upload leaves, fold constants, size the workspace. */
 int  qxb_graph_compile(qxb_graph* g, const qxb_options* opts);
 

@@ -20,7 +20,7 @@ SYMBOLS = [
     "qxb_graph_create", "qxb_graph_destroy", "qxb_graph_load", "qxb_graph_output", "qxb_graph_view",
     "qxb_graph_ncon", "qxb_graph_save", "qxb_graph_parse_dsl", "qxb_graph_set_data",
     "qxb_graph_num_outputs", "qxb_graph_num_slice_vars", "qxb_graph_num_slices", "qxb_slice_values",
-    "qxb_graph_describe", "qxb_graph_compile", "qxb_amplitudes", "qxb_amplitudes_device",
+    "qxb_graph_describe", "qxb_graph_configure", "qxb_graph_compile", "qxb_amplitudes", "qxb_amplitudes_device",
     "qxb_last_stats", "qxb_profile_dump",
 ]
 
@@ -33,7 +33,8 @@ class QxbError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("hbm_budget_bytes", C.c_int64), ("amp_batch", C.c_int64),
-                ("profile", C.c_int32), ("no_cuda_graph", C.c_int32)]
+                ("profile", C.c_int32), ("no_cuda_graph", C.c_int32),
+                ("sum_at_root", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -76,6 +77,7 @@ def load():
         "qxb_graph_num_slices": (i32, [p, pi64]),
         "qxb_slice_values": (i32, [p, i64, pi64]),
         "qxb_graph_describe": (i64, [p, i32, cp, i64]),
+        "qxb_graph_configure": (i32, [p, C.POINTER(Options)]),
         "qxb_graph_compile": (i32, [p, C.POINTER(Options)]),
         "qxb_amplitudes": (i32, [p, p, i64, i64, i64, p]),
         "qxb_amplitudes_device": (i32, [p, p, i64, i64, i64, p]),

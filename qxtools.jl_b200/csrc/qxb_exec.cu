@@ -207,19 +207,16 @@ void build_templates(Variant& v, int dtype) {
         p.nC = nC; p.nK = op.nK;
         p.lob = std::min(nC, 8);
         // register tile: lowest M-only / N-only bits above the thread bits
-        const int kk = op.nK <= 3 ? (1 << op.nK) : 1;
-        const int regs_per = dtype == QXB_C32 ? 2 : 4;
-        int max_tile_loads = 96 / (regs_per * kk);           // (2^ma + 2^nb) * K * regs <= ~96
         std::vector<int> mbits, nbits;
         for (int b = p.lob; b < nC; ++b) {
             if (mapA[b] >= 0 && mapB[b] < 0 && mbits.size() < 2) mbits.push_back(b);
             else if (mapB[b] >= 0 && mapA[b] < 0 && nbits.size() < 2) nbits.push_back(b);
         }
-        while ((int)((1u << mbits.size()) + (1u << nbits.size())) > std::max(2, max_tile_loads)) {
-            if (mbits.size() >= nbits.size() && !mbits.empty()) mbits.pop_back();
-            else if (!nbits.empty()) nbits.pop_back();
-            else break;
-        }
+        // K chunk: keep (2^ma + 2^nb) * 2^kc operand loads (<= 64 registers) in flight
+        const int budget_loads = dtype == QXB_C32 ? 32 : 16;
+        int kc = std::min(op.nK, 3);
+        while (kc > 0 && (int)(((1u << mbits.size()) + (1u << nbits.size())) << kc) > budget_loads) --kc;
+        p.kc = kc;
         p.ma = (int)mbits.size(); p.nb = (int)nbits.size();
         std::vector<bool> is_tile(nC, false);
         for (int b : mbits) is_tile[b] = true;
@@ -272,13 +269,11 @@ void build_templates(Variant& v, int dtype) {
         p.nkA = (int)op.segKA.size(); p.nkB = (int)op.segKB.size();
         for (size_t j = 0; j < op.segKA.size(); ++j) p.kA[j] = DSeg{op.segKA[j].src, op.segKA[j].dst, op.segKA[j].len, 0};
         for (size_t j = 0; j < op.segKB.size(); ++j) p.kB[j] = DSeg{op.segKB[j].src, op.segKB[j].dst, op.segKB[j].len, 0};
-        if (op.nK <= 4) {
-            for (int k = 0; k < (1 << op.nK); ++k) {
-                long long a = 0, b = 0;
-                for (auto& s : op.segKA) a |= (long long)((k >> s.src) & ((1 << s.len) - 1)) << s.dst;
-                for (auto& s : op.segKB) b |= (long long)((k >> s.src) & ((1 << s.len) - 1)) << s.dst;
-                p.ktabA[k] = a; p.ktabB[k] = b;
-            }
+        for (int k = 0; k < (1 << std::min(op.nK, 4)); ++k) {
+            long long a = 0, b = 0;
+            for (auto& s : op.segKA) a |= (long long)((k >> s.src) & ((1 << s.len) - 1)) << s.dst;
+            for (auto& s : op.segKB) b |= (long long)((k >> s.src) & ((1 << s.len) - 1)) << s.dst;
+            p.ktabA[k] = a; p.ktabB[k] = b;
         }
     }
 }
@@ -333,7 +328,7 @@ Variant* get_variant(qxb_graph* g, int n_free) {
     auto it = g->variants.find(n_free);
     if (it != g->variants.end()) return it->second.get();
     std::unique_ptr<Variant> v(new Variant());
-    v->L = lower(g->prog, n_free);
+    v->L = lower(g->prog, n_free, !g->opts.sum_at_root);
     plan_memory(v->L, 1);
     build_templates(*v, g->dtype);
     const size_t es = g->es();
@@ -695,13 +690,21 @@ int64_t qxb_graph_describe(qxb_graph* g, int n_free, char* buf, int64_t buflen) 
     int rc = guard([&] {
         if (!g) throw Error(QXB_ERR_ARG, "null graph");
         ensure_analysed(g);
-        Lowered L = lower(g->prog, n_free);
+        Lowered L = lower(g->prog, n_free, !g->opts.sum_at_root);
         plan_memory(L, 1);
         std::string s = describe_json(g->prog, L);
         need = (int64_t)s.size() + 1;
         if (buf && buflen >= need) memcpy(buf, s.c_str(), need);
     });
     return rc == QXB_OK ? need : rc;
+}
+
+int qxb_graph_configure(qxb_graph* g, const qxb_options* opts) {
+    return guard([&] {
+        need_graph(g);
+        if (!opts) throw Error(QXB_ERR_ARG, "null options");
+        g->opts = *opts;
+    });
 }
 
 int qxb_graph_compile(qxb_graph* g, const qxb_options* opts) {

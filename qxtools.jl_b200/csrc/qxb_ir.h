@@ -125,6 +125,7 @@ struct LOp {
 
 struct Lowered {
     int n_free = 0;                // variables [0, n_free) are batched, the rest fixed
+    bool early_sum = true;         // batched variables summed at the lowest covering node (else at the root)
     std::vector<LTensor> tensors;
     std::vector<LOp> ops;
     std::vector<int> output_leaves;          // LTensor indices materialised from the bitstrings
@@ -137,7 +138,7 @@ struct Lowered {
 };
 
 // Lower for a given number of free (batched) low slice variables.
-Lowered lower(const Program& p, int n_free);
+Lowered lower(const Program& p, int n_free, bool early_sum = true);
 // Plan arena offsets for a batch of n_amp bitstrings (fills LTensor::offset and the arena sizes).
 void plan_memory(Lowered& L, int64_t n_amp);
 std::string describe_json(const Program& p, const Lowered& L);

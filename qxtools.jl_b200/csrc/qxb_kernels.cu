@@ -31,16 +31,16 @@ __device__ __forceinline__ long long segeval(const DSeg* s, int n, unsigned long
 // 2^ma x 2^nb register tile per thread (so 2^ma*K loads of A and 2^nb*K loads of
 // B feed 2^(ma+nb) outputs -- the nodes that broadcast small operands into a big
 // C are otherwise L1/L2-read-bound), and the remaining "hi" bits are enumerated
-// by the tile index through segment maps.  NK = log2(K) when K <= 8 (all loads of
-// a tile are issued before the first FMA), NK = -1 is the generic K loop.
-template <typename R2, int NK, int MA, int NB>
+// by the tile index through segment maps.  K is walked in chunks of 2^KC: all
+// (2^ma + 2^nb) * 2^KC loads of a chunk are issued before its FMAs (the kernel
+// lives on memory-level parallelism), accumulators stay in registers.
+template <typename R2, int KC, int MA, int NB>
 __global__ void __launch_bounds__(kThreads)
 contract_kernel(const __grid_constant__ OpParams p) {
     const R2* __restrict__ A = reinterpret_cast<const R2*>(p.A);
     const R2* __restrict__ B = reinterpret_cast<const R2*>(p.B);
     R2* __restrict__ C = reinterpret_cast<R2*>(p.C);
-    constexpr int TM = 1 << MA, TN = 1 << NB;
-    constexpr int KK = NK >= 0 ? (1 << NK) : 1;
+    constexpr int TM = 1 << MA, TN = 1 << NB, KK = 1 << KC;
     const int tid = threadIdx.x;
     const int lob = p.lob;
     const int sub_bits = 8 - lob;
@@ -48,18 +48,16 @@ contract_kernel(const __grid_constant__ OpParams p) {
     const unsigned lo = tid & ((1u << lob) - 1u);
     const long long aLo = segeval(p.sAlo, p.nsAlo, lo);
     const long long bLo = segeval(p.sBlo, p.nsBlo, lo);
-    long long aT[TM], bT[TN];
+    long long aT[TM], bT[TN], kA[KK], kB[KK];
 #pragma unroll
     for (int j = 0; j < TM; ++j) aT[j] = p.aT[j];
 #pragma unroll
     for (int j = 0; j < TN; ++j) bT[j] = p.bT[j];
-    long long kA[KK], kB[KK];
-    if (NK >= 0) {
 #pragma unroll
-        for (int k = 0; k < KK; ++k) { kA[k] = p.ktabA[k]; kB[k] = p.ktabB[k]; }
-    }
+    for (int k = 0; k < KK; ++k) { kA[k] = p.ktabA[k]; kB[k] = p.ktabB[k]; }
     const int hb = p.hb;
     const long long hmask = (1ll << hb) - 1ll;
+    const int nchunks = 1 << (p.nK - KC);
     for (long long t0 = ((long long)blockIdx.x << sub_bits); t0 < p.tiles;
          t0 += ((long long)gridDim.x << sub_bits)) {
         const long long tile = t0 + sub;
@@ -69,80 +67,71 @@ contract_kernel(const __grid_constant__ OpParams p) {
         const R2* Ap = A + u * p.sUA + segeval(p.sAhi, p.nsAhi, hh) + aLo;
         const R2* Bp = B + u * p.sUB + segeval(p.sBhi, p.nsBhi, hh) + bLo;
         R2* Cp = C + u * p.sUC + segeval(p.sChi, p.nsChi, hh) + lo;
-        if (NK >= 0) {
+        R2 acc[TM][TN];
+#pragma unroll
+        for (int jm = 0; jm < TM; ++jm)
+#pragma unroll
+            for (int jn = 0; jn < TN; ++jn) { acc[jm][jn].x = 0; acc[jm][jn].y = 0; }
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const R2* Ac = Ap;
+            const R2* Bc = Bp;
+            if (nchunks > 1) {
+                const unsigned long long kb = (unsigned long long)ch << KC;
+                Ac += segeval(p.kA, p.nkA, kb);
+                Bc += segeval(p.kB, p.nkB, kb);
+            }
             R2 av[TM][KK], bv[TN][KK];
 #pragma unroll
             for (int j = 0; j < TM; ++j)
 #pragma unroll
-                for (int k = 0; k < KK; ++k) av[j][k] = __ldg(Ap + aT[j] + kA[k]);
+                for (int k = 0; k < KK; ++k) av[j][k] = __ldg(Ac + aT[j] + kA[k]);
 #pragma unroll
             for (int j = 0; j < TN; ++j)
 #pragma unroll
-                for (int k = 0; k < KK; ++k) bv[j][k] = __ldg(Bp + bT[j] + kB[k]);
+                for (int k = 0; k < KK; ++k) bv[j][k] = __ldg(Bc + bT[j] + kB[k]);
 #pragma unroll
-            for (int jm = 0; jm < TM; ++jm) {
+            for (int jm = 0; jm < TM; ++jm)
 #pragma unroll
-                for (int jn = 0; jn < TN; ++jn) {
-                    R2 acc; acc.x = 0; acc.y = 0;
+                for (int jn = 0; jn < TN; ++jn)
 #pragma unroll
-                    for (int k = 0; k < KK; ++k) cmac(acc, av[jm][k], bv[jn][k]);
-                    Cp[p.cT[jm * TN + jn]] = acc;
-                }
-            }
-        } else {
-            const int nk = 1 << p.nK;
-#pragma unroll
-            for (int jm = 0; jm < TM; ++jm) {
-#pragma unroll
-                for (int jn = 0; jn < TN; ++jn) {
-                    R2 acc; acc.x = 0; acc.y = 0;
-                    if (p.nK <= 4) {
-                        for (int k = 0; k < nk; ++k)
-                            cmac(acc, __ldg(Ap + aT[jm] + p.ktabA[k]), __ldg(Bp + bT[jn] + p.ktabB[k]));
-                    } else {
-                        for (int k = 0; k < nk; ++k) {
-                            const long long ak = segeval(p.kA, p.nkA, (unsigned long long)k);
-                            const long long bk = segeval(p.kB, p.nkB, (unsigned long long)k);
-                            cmac(acc, __ldg(Ap + aT[jm] + ak), __ldg(Bp + bT[jn] + bk));
-                        }
-                    }
-                    Cp[p.cT[jm * TN + jn]] = acc;
-                }
-            }
+                    for (int k = 0; k < KK; ++k) cmac(acc[jm][jn], av[jm][k], bv[jn][k]);
         }
+#pragma unroll
+        for (int jm = 0; jm < TM; ++jm)
+#pragma unroll
+            for (int jn = 0; jn < TN; ++jn) Cp[p.cT[jm * TN + jn]] = acc[jm][jn];
     }
 }
 
-template <typename R2, int NK, int MA>
+template <typename R2, int KC, int MA>
 static void launch_nb(const OpParams& p, int grid, cudaStream_t st) {
     switch (p.nb) {
-    case 0: contract_kernel<R2, NK, MA, 0><<<grid, kThreads, 0, st>>>(p); break;
-    case 1: contract_kernel<R2, NK, MA, 1><<<grid, kThreads, 0, st>>>(p); break;
-    default: contract_kernel<R2, NK, MA, 2><<<grid, kThreads, 0, st>>>(p); break;
+    case 0: contract_kernel<R2, KC, MA, 0><<<grid, kThreads, 0, st>>>(p); break;
+    case 1: contract_kernel<R2, KC, MA, 1><<<grid, kThreads, 0, st>>>(p); break;
+    default: contract_kernel<R2, KC, MA, 2><<<grid, kThreads, 0, st>>>(p); break;
     }
 }
-template <typename R2, int NK>
+template <typename R2, int KC>
 static void launch_ma(const OpParams& p, int grid, cudaStream_t st) {
     switch (p.ma) {
-    case 0: launch_nb<R2, NK, 0>(p, grid, st); break;
-    case 1: launch_nb<R2, NK, 1>(p, grid, st); break;
-    default: launch_nb<R2, NK, 2>(p, grid, st); break;
+    case 0: launch_nb<R2, KC, 0>(p, grid, st); break;
+    case 1: launch_nb<R2, KC, 1>(p, grid, st); break;
+    default: launch_nb<R2, KC, 2>(p, grid, st); break;
     }
 }
 template <typename R2>
-static void launch_nk(const OpParams& p, int grid, cudaStream_t st) {
-    switch (p.nK) {
+static void launch_kc(const OpParams& p, int grid, cudaStream_t st) {
+    switch (p.kc) {
     case 0: launch_ma<R2, 0>(p, grid, st); break;
     case 1: launch_ma<R2, 1>(p, grid, st); break;
     case 2: launch_ma<R2, 2>(p, grid, st); break;
-    case 3: launch_ma<R2, 3>(p, grid, st); break;
-    default: launch_ma<R2, -1>(p, grid, st); break;
+    default: launch_ma<R2, 3>(p, grid, st); break;
     }
 }
 
 void launch_contract(int dtype, const OpParams& p, int grid, cudaStream_t st) {
-    if (dtype == 0) launch_nk<float2>(p, grid, st);
-    else launch_nk<double2>(p, grid, st);
+    if (dtype == 0) launch_kc<float2>(p, grid, st);
+    else launch_kc<double2>(p, grid, st);
 }
 
 // Output leaves: one-hot (or +/-) vectors selected by the bitstring

@@ -265,12 +265,26 @@ int find_entry(const LTensor& t, int key) {
 }
 }  // namespace
 
-Lowered lower(const Program& p, int n_free) {
+Lowered lower(const Program& p, int n_free, bool early_sum) {
     if (!p.analysed) throw Error(QXB_ERR_STATE, "program not analysed");
     const int k = (int)p.vars.size();
     if (n_free < 0 || n_free > k) n_free = k;
     Lowered L; L.n_free = n_free;
     std::vector<int> lt_of_def(p.defs.size(), -1);
+    // Early summation of a batched slice variable: v is summed (becomes a K index) at
+    // the node whose subtree holds ALL leaf uses that depend on v -- sum-product
+    // reordering, exact because nothing outside that subtree depends on v.  Needs a
+    // tree: if any contraction result is used twice, fall back to summing at the root.
+    std::vector<int> total_uses(k, 0);
+    for (const TensorDef& d : p.defs) {
+        if (d.kind != T_NCON) continue;
+        if (d.uses > 1) early_sum = false;
+        for (int o : {d.a, d.b})
+            if (p.defs[o].kind != T_NCON)
+                for (int v : p.defs[o].vars) total_uses[v]++;
+    }
+    L.early_sum = early_sum;
+    std::vector<std::map<int, int>> use_cnt;      // per LTensor: var -> leaf uses inside its subtree
 
     auto leaf_tensor = [&](int di) -> int {
         if (lt_of_def[di] >= 0) return lt_of_def[di];
@@ -303,6 +317,9 @@ Lowered lower(const Program& p, int n_free) {
         }
         lt_of_def[di] = (int)L.tensors.size();
         L.tensors.push_back(std::move(t));
+        std::map<int, int> cnt;
+        for (int v : d.vars) cnt[v] = 1;
+        use_cnt.push_back(std::move(cnt));
         return lt_of_def[di];
     };
 
@@ -339,11 +356,14 @@ Lowered lower(const Program& p, int n_free) {
         // free slice variables ride along as batch bits
         std::set<int> vs(DA.vars.begin(), DA.vars.end());
         vs.insert(DB.vars.begin(), DB.vars.end());
+        std::map<int, int> cntC = use_cnt[ia_t];
+        for (auto& kv : use_cnt[ib_t]) cntC[kv.first] += kv.second;
         for (int v : vs) {
             if (v >= n_free || p.vars[v].nbits == 0) continue;
             int posA = find_entry(L.tensors[ia_t], ~v), posB = find_entry(L.tensors[ib_t], ~v);
-            if (posA < 0 && posB < 0) throw Error(QXB_ERR_STATE, "ncon " + d.name + ": lost slice variable");
-            items.push_back(Item{p.vars[v].nbits, posA, posB, ~v, -1});
+            if (posA < 0 && posB < 0) continue;          // already summed further down
+            const bool done = early_sum && cntC[v] == total_uses[v];
+            items.push_back(Item{p.vars[v].nbits, posA, posB, done ? NONE : ~v, -1});
         }
         // layout of C: follow the bigger operand's bit order, then the other's extra bits
         const bool a_big = L.tensors[ia_t].span_bits >= L.tensors[ib_t].span_bits;
@@ -400,6 +420,7 @@ Lowered lower(const Program& p, int n_free) {
         }
         lt_of_def[di] = op.c;
         L.tensors.push_back(std::move(C));
+        use_cnt.push_back(std::move(cntC));
         L.ops.push_back(std::move(op));
     }
     const TensorDef& R = p.defs[p.root];
@@ -492,7 +513,7 @@ static void seg_json(std::ostringstream& o, const std::vector<Seg>& s) {
 
 std::string describe_json(const Program& p, const Lowered& L) {
     std::ostringstream o;
-    o << "{\"n_free\":" << L.n_free << ",\"n_slice_vars\":" << p.vars.size() << ",\"n_outputs\":" << p.n_outputs
+    o << "{\"early_sum\":" << (L.early_sum ? "true" : "false") << ",\"n_free\":" << L.n_free << ",\"n_slice_vars\":" << p.vars.size() << ",\"n_outputs\":" << p.n_outputs
       << ",\"slice_vars\":[";
     for (size_t i = 0; i < p.vars.size(); ++i)
         o << (i ? "," : "") << "{\"sym\":\"" << p.vars[i].sym << "\",\"dim\":" << p.vars[i].dim << "}";

@@ -1,0 +1,139 @@
+"""``execute``: run a simulation file triple -- the entry point behind
+``bin/qxrun.jl`` (/root/reference/bin/qxrun.jl:66-97), i.e. QXContexts.execute
+(call site :83-87) with the same keyword set.
+
+    execute(dsl_file, input_file=None, param_file=None, output_file=None;
+            use_mpi=False, sub_comm_size=1, use_gpu=True,
+            max_amplitudes=None, max_slices=None, timings=False)
+
+* ``param_file`` defaults to the DSL name with ``.yml``, ``input_file`` to the DSL
+  name with the data suffix (qxrun.jl:21,25).  Data files are ``.npz`` in this
+  Python harness (no HDF5/JLD2 library in the image; the Julia shim reads ``.jld2``).
+* ``max_amplitudes`` / ``max_slices`` keep the FIRST N of the parameter file /
+  slice space (qxrun.jl:32-39).
+* ``use_mpi`` -> torch.distributed (one process per GPU, launched by torchrun);
+  ``sub_comm_size`` ranks share the slices of a bitstring group (qxrun.jl:40-46).
+* ``use_gpu=False`` is an error: this executor has no CPU path.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import time
+from collections import OrderedDict
+from typing import Optional
+
+import numpy as np
+import yaml
+
+from .dist import Distribution
+from .simulation import amplitudes_uniform
+
+
+def _bitstrings_from_params(params: dict, max_amplitudes: Optional[int]):
+    out = params["output"]
+    method, p = out["method"], out["params"]
+    if method == "List":                                  # outputs.jl:63-68
+        bs = list(p["bitstrings"])
+    elif method == "Uniform":                             # outputs.jl:69-72
+        bs = list(amplitudes_uniform(int(p["num_qubits"]), p.get("seed"), int(p["num_samples"])))
+    else:
+        raise NotImplementedError(f"output method {method!r}: only List and Uniform are wired to the executor "
+                                  "(Rejection sampling is a 'next' row, SURVEY.md 8f-2)")
+    if max_amplitudes is not None:
+        bs = bs[:max_amplitudes]
+    return bs
+
+
+def execute(dsl_file: str, input_file: Optional[str] = None, param_file: Optional[str] = None,
+            output_file: Optional[str] = None, use_mpi: bool = False, sub_comm_size: int = 1,
+            use_gpu: bool = True, max_amplitudes: Optional[int] = None, max_slices: Optional[int] = None,
+            timings: bool = False, dtype: str = "c32"):
+    """Returns ``OrderedDict{bitstring => amplitude}`` on rank 0 (None elsewhere)."""
+    if not use_gpu:
+        raise RuntimeError("qxb200 has no CPU path: use_gpu must be True")
+    from .executor import Graph, init
+    stem = os.path.splitext(dsl_file)[0]
+    param_file = param_file or stem + ".yml"
+    input_file = input_file or stem + ".npz"
+    t = OrderedDict()
+    t0 = time.perf_counter()
+    text = open(dsl_file).read()
+    data = dict(np.load(input_file))
+    params = yaml.safe_load(open(param_file))
+    t["Parse input files"] = time.perf_counter() - t0
+
+    t0 = time.perf_counter()
+    rank, world = 0, 1
+    td = None
+    if use_mpi:
+        import torch
+        import torch.distributed as td
+        if not td.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+            td.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+        rank, world = td.get_rank(), td.get_world_size()
+    init(int(os.environ.get("LOCAL_RANK", "0")))
+    g = Graph.from_dsl(text, data, dtype).compile()
+    t["Create Context"] = time.perf_counter() - t0
+
+    t0 = time.perf_counter()
+    bitstrings = _bitstrings_from_params(params, max_amplitudes)
+    n_slices = g.n_slices if max_slices is None else min(max_slices, g.n_slices)
+    d = Distribution(len(bitstrings), n_slices, world, rank, sub_comm_size if use_mpi else 1)
+    t["Create sampler"] = time.perf_counter() - t0
+
+    t0 = time.perf_counter()
+    mine = bitstrings[d.amp_begin:d.amp_end]
+    part = g.amplitudes(mine, d.slice_begin, d.slice_end) if mine else np.zeros(0, g.np_dtype)
+    full = np.zeros(len(bitstrings), dtype=g.np_dtype)
+    full[d.amp_begin:d.amp_end] = part
+    if use_mpi and world > 1:
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device()) if td.get_backend() == "nccl" else torch.device("cpu")
+        buf = torch.from_numpy(full).to(dev)
+        td.all_reduce(torch.view_as_real(buf))       # slices summed inside a group, groups are disjoint in bitstrings
+        full = buf.cpu().numpy()
+    t["Simulation"] = time.perf_counter() - t0
+
+    results = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        results = OrderedDict((b, complex(a)) for b, a in zip(bitstrings, full))
+        if output_file:
+            np.savez(output_file if output_file.endswith(".npz") else output_file + ".npz",
+                     bitstrings=np.array(bitstrings), amplitudes=full)
+        t["Write results"] = time.perf_counter() - t0
+        if timings:
+            for k, v in t.items():
+                print(f"  {k:<20s} {v * 1e3:10.3f} ms")
+    return results
+
+
+def main(argv=None):
+    """CLI with the flags of bin/qxrun.jl:15-57."""
+    ap = argparse.ArgumentParser("qxrun (qxb200)")
+    ap.add_argument("--dsl", "-d", required=True, help="DSL file path")
+    ap.add_argument("--parameter-file", "-p", default=None)
+    ap.add_argument("--input-file", "-i", default=None)
+    ap.add_argument("--output-file", "-o", required=True)
+    ap.add_argument("--number-amplitudes", "-a", type=int, default=None)
+    ap.add_argument("--number-slices", "-n", type=int, default=None)
+    ap.add_argument("--sub-comm-size", "-s", type=int, default=1)
+    ap.add_argument("--mpi", "-m", action="store_true")
+    ap.add_argument("--gpu", "-g", action="store_true", help="accepted for compatibility; the GPU is always used")
+    ap.add_argument("--timings", "-t", action="store_true")
+    ap.add_argument("--blas-threads", "-b", type=int, default=8, help="ignored (no BLAS on the path)")
+    ap.add_argument("--dtype", default="c32", choices=["c32", "c64"])
+    a = ap.parse_args(argv)
+    kw = dict(use_mpi=a.mpi, sub_comm_size=a.sub_comm_size, use_gpu=True, max_amplitudes=a.number_amplitudes,
+              max_slices=a.number_slices, timings=a.timings, dtype=a.dtype)
+    res = execute(a.dsl, a.input_file, a.parameter_file, a.output_file, **kw)
+    if a.timings:                 # qxrun.jl:89-96 runs twice so the second table excludes warm-up
+        res = execute(a.dsl, a.input_file, a.parameter_file, a.output_file, **kw)
+    return res
+
+
+if __name__ == "__main__":
+    main()

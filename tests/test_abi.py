@@ -1,0 +1,105 @@
+"""The C-ABI library loads on a CPU-only box, exports every symbol include/qxb200.h
+declares, and its host-side logic (parser, analysis, slice enumeration, lowering
+report, error behaviour) works without a GPU.  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from qxb200 import _lib
+from qxb200._lib import QxbError
+from qxb200.executor import Graph
+from oracle import qx_oracle as orc
+from cases import kat0, rqc_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported(lib_built):
+    hdr = open(os.path.join(ROOT, "include", "qxb200.h")).read()
+    declared = set(re.findall(r"\b(qxb_[a-z_]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS)
+    for s in declared:
+        assert hasattr(lib_built, s), s
+    assert lib_built.qxb_version() >= 100
+
+
+def test_parse_and_queries(lib_built):
+    txt, data = kat0()
+    g = Graph.from_dsl(txt, data)
+    assert g.n_outputs == 2 and g.slice_dims == [2, 2] and g.n_slices == 4
+    cmds = orc.parse_dsl(txt)
+    dims = orc.slice_dims(cmds)
+    for s in range(4):                       # bit-exact slice bookkeeping vs the oracle
+        assert g.slice_values(s) == list(orc.slice_values(s, dims).values())
+    with pytest.raises(QxbError):
+        g.slice_values(4)
+
+
+def test_builder_calls_equal_parser(lib_built):
+    import qxb200 as q
+    tnc = q.convert_to_tnc(q.create_rqc_circuit(3, 3, 8, 3))
+    bg, plan, _ = q.contraction_scheme(tnc, 2, time=0)
+    cg = q.build_compute_graph(tnc, plan, bg)
+    a = Graph.from_compute_graph(cg).describe()
+    b = Graph.from_dsl(cg.dsl(), cg.tensors).describe()
+    assert a == b
+
+
+@pytest.mark.parametrize("bad,code", [
+    ("load t1 data_1 2\n", -1),                                   # no version line
+    ("# version: 0.4.0\nfoo t1\n", -1),                           # unknown instruction
+    ("# version: 0.4.0\nload t1 data_1 2\nncon t2 1 t1 1 t9 1\nsave output t2\n", -1),   # undefined symbol
+    ("# version: 0.4.0\nload t1 data_1 2\nload t2 data_1 2\nncon t3 0 t1 1,2 t2 1\nsave output t3\n", -1),  # rank
+    ("# version: 0.4.0\nload t1 data_1 2\nload t2 data_1 2\nncon t3 0 t1 1 t2 1\n", -1),  # no save
+    ("# version: 0.4.0\nload t1 data_1 2\nview t1_s t1 v1 2 2\n", -1),                    # mode out of range
+    ("# version: 0.4.0\nload t1 data_1 2\nview t1_s t1 v1 1 3\n", -1),                    # bond dim mismatch
+    ("# version: 0.4.0\nload t1 data_1 2,2\nload t2 data_1 2\nncon t3 1 t1 1,2 t2 2\nview x t3 v1 1 2\nsave output t3\n", -4),
+])
+def test_malformed_programs(lib_built, bad, code):
+    g = Graph()
+    b = bad.encode()
+    rc = g._lib.qxb_graph_parse_dsl(g._h, b, len(b))
+    if rc == 0:
+        n = C.c_int64()
+        rc = g._lib.qxb_graph_num_slices(g._h, C.byref(n))      # forces analysis
+    assert rc == code, g._lib.qxb_last_error()
+    assert len(g._lib.qxb_last_error()) > 0
+
+
+def test_non_scalar_root_rejected(lib_built):
+    g = Graph.from_dsl("# version: 0.4.0\nload a d 2,2\nload b d 2,2\nncon c 1,3 a 1,2 b 2,3\nsave output c\n",
+                       {"d": np.eye(2)})
+    with pytest.raises(QxbError) as e:
+        g.describe()
+    assert e.value.code == -4
+
+
+def test_compute_fails_loudly_without_gpu(lib_built):
+    """No CPU fallback: on a box without CUDA the compute entry points must error."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    txt, data = kat0()
+    g = Graph.from_dsl(txt, data)
+    with pytest.raises(QxbError) as e:
+        g.compile()
+    assert e.value.code == -3
+    with pytest.raises(QxbError):
+        g.amplitudes(["00"])
+
+
+def test_describe_split_is_consistent(lib_built):
+    txt, data, _ = rqc_case(4, 4, 12, 4)
+    g = Graph.from_dsl(txt, data)
+    for n_free in (0, 2, 4):
+        d = g.describe(n_free)
+        assert d["n_free"] == n_free and d["n_slice_vars"] == 4
+        for op in d["ops"]:
+            assert op["batch_bits"] + op["m_bits"] + op["n_bits"] == op["nC"]
+            assert sum(s[2] for s in op["segA"]) + sum(s[2] for s in op["segKA"]) <= op["a_bits"]
+        # fully fixed: nothing is batched over slices, so no op has more bits than the unsliced tensors
+        if n_free == 0:
+            assert max(op["nC"] for op in d["ops"]) <= 8
