@@ -211,8 +211,11 @@ def run_gpu(args):
     n_q = w["rows"] * w["cols"]
     g = Graph.from_dsl(txt, data, w["dtype"]).compile(amp_batch=args.amp_batch, cuda_graph=not args.no_graph)
     S = g.n_slices
-    # contiguous slice-range partition; identical bitstrings on every rank
+    # slice-space partition: the ranks fix different values of the slice variables
+    # the cost model picks (qxb_partition_vars); identical bitstrings on every rank.  Fallback:
+    # contiguous ranges of the linear slice id.
     s0, s1 = (S * rank) // world, (S * (rank + 1)) // world
+    assign = g.partition_assignment(world, rank) if world > 1 else None
     n_amp = args.amps
     bits_h = torch.from_numpy(synth_bits(n_amp, n_q)).pin_memory()
     bits_d = bits_h.to(dev)
@@ -223,7 +226,10 @@ def run_gpu(args):
     bits_h_np = bits_h.numpy()
 
     def step_device():
-        g.amplitudes_device(bits_d.data_ptr(), n_amp, out_d.data_ptr(), s0, s1)
+        if assign is not None:
+            g.amplitudes_subspace_device(bits_d.data_ptr(), n_amp, out_d.data_ptr(), assign[0], assign[1])
+        else:
+            g.amplitudes_device(bits_d.data_ptr(), n_amp, out_d.data_ptr(), s0, s1)
         if world > 1:
             dist.all_reduce(torch.view_as_real(out_d))
 
@@ -231,7 +237,14 @@ def run_gpu(args):
         # the public host-buffer call: pinned bitstrings -> H2D -> contraction -> D2H, synchronised
         from qxb200._lib import check
         import ctypes as C
-        check(g._lib.qxb_amplitudes(g._h, C.c_void_p(bits_h.data_ptr()), n_amp, s0, s1, C.c_void_p(out_h.data_ptr())))
+        if assign is not None:
+            fv = (C.c_int32 * max(len(assign[0]), 1))(*assign[0])
+            fx = (C.c_int64 * max(len(assign[1]), 1))(*assign[1])
+            check(g._lib.qxb_amplitudes_subspace(g._h, C.c_void_p(bits_h.data_ptr()), n_amp, fv, fx, len(assign[0]),
+                                                 C.c_void_p(out_h.data_ptr()), 0))
+        else:
+            check(g._lib.qxb_amplitudes(g._h, C.c_void_p(bits_h.data_ptr()), n_amp, s0, s1,
+                                        C.c_void_p(out_h.data_ptr())))
         if world > 1:
             t = torch.view_as_real(out_h.to(dev, non_blocking=True))
             dist.all_reduce(t)
@@ -279,7 +292,7 @@ def run_gpu(args):
         e2e = n_amp / (ms_e2e / args.steps * 1e-3)
         # sanity: Porter-Thomas / norm check -- mean |amp|^2 * 2^n should be ~1 for an RQC
         norm = float(np.mean(np.abs(result) ** 2) * 2.0 ** n_q)
-        roof = roofline(args, g, txt, data, w, bits_d, out_d, n_amp, s0, s1)
+        roof = roofline(args, g, txt, data, w, bits_d, out_d, n_amp, s0, s1, assign)
         cpu = None
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
@@ -292,7 +305,9 @@ def run_gpu(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if w["dtype"] == "c64" else "f32", "data": "synthetic",
             "config": {"workload": args.workload, "n_amp_per_step": n_amp, "n_slices": S,
-                       "n_qubits": n_q, "complex": w["dtype"], "slice_partition": f"contiguous/{world}",
+                       "n_qubits": n_q, "complex": w["dtype"],
+                       "slice_partition": (f"fixed slice variables {[v + 1 for v in assign[0]]} over {world} ranks"
+                                           if assign is not None else f"contiguous ranges / {world}"),
                        "l2": f"working set {st['workspace_bytes'] / 1e9:.2f} GB per GPU >> 126 MB L2 (no flush needed)",
                        "amp_batch": st["amp_batch"], "mean_p_times_2^n": norm},
             "e2e": {"value": e2e, "unit": "amplitudes/s", "h2d_bytes_per_step": int(n_amp * n_q),
@@ -307,7 +322,7 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def roofline(args, g, txt, data, w, bits_d, out_d, n_amp, s0, s1):
+def roofline(args, g, txt, data, w, bits_d, out_d, n_amp, s0, s1, assign=None):
     """Per-op CUDA-event timing of one more step (same stream, same inputs) on a
     profiled clone of the graph; the reported kernel is the contraction kernel over
     the DOMINANT contractions = top ops by FLOPs covering >= 80% of the step's FLOPs
@@ -315,7 +330,10 @@ def roofline(args, g, txt, data, w, bits_d, out_d, n_amp, s0, s1):
     from qxb200.executor import Graph
     gp = Graph.from_dsl(txt, data, w["dtype"]).compile(amp_batch=args.amp_batch, profile=True)
     for _ in range(2):
-        gp.amplitudes_device(bits_d.data_ptr(), n_amp, out_d.data_ptr(), s0, s1)
+        if assign is not None:
+            gp.amplitudes_subspace_device(bits_d.data_ptr(), n_amp, out_d.data_ptr(), assign[0], assign[1])
+        else:
+            gp.amplitudes_device(bits_d.data_ptr(), n_amp, out_d.data_ptr(), s0, s1)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     prof = gp.profile_dump(os.path.join(ROOT, "gpurun_out", f"op_profile_{args.workload}.json"))
     ops = [o for v in prof["variants"] for o in v["ops"]]

@@ -110,6 +110,21 @@ int  qxb_amplitudes(qxb_graph* g, const uint8_t* bits, int64_t n_amp,
 int  qxb_amplitudes_device(qxb_graph* g, const uint8_t* d_bits, int64_t n_amp,
                            int64_t slice_begin, int64_t slice_end, void* d_out);
 
+/* Slice SUB-SPACE form: every slice assignment in which the n_fixed variables fixed_vars[i]
+ * (0-based: 0 = v1) take the values fixed_vals[i] and all other variables run over their full
+ * extent.  This is the unit of multi-GPU sharding: the ranks fix different values of the same
+ * variables and one all-reduce of `out` over the ranks gives the full sum.  on_device != 0:
+ * bits/out are device pointers and the call is asynchronous. */
+int  qxb_amplitudes_subspace(qxb_graph* g, const uint8_t* bits, int64_t n_amp, const int32_t* fixed_vars,
+                             const int64_t* fixed_vals, int n_fixed, void* out, int on_device);
+/* Which slice variables to fix when sharding over n_parts ranks: chosen greedily so that the
+ * work left per rank is smallest (with dependency tracking, fixing a variable that few nodes
+ * depend on saves nothing).  n_vars_out = 0 when the extents cannot factor n_parts (shard by
+ * contiguous slice ranges instead).  Pure host logic. */
+int  qxb_partition_vars(qxb_graph* g, int n_parts, int32_t* vars_out /*may be NULL*/, int* n_vars_out);
+/* qxb_graph_describe for an arbitrary set of batched variables (bit v of free_mask = v(v+1)). */
+int64_t qxb_graph_describe_mask(qxb_graph* g, uint64_t free_mask, char* buf, int64_t buflen);
+
 /* Counters of the last qxb_amplitudes* call. */
 typedef struct qxb_stats {
     int64_t kernel_launches;     /* kernels of this library launched                   */

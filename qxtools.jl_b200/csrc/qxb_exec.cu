@@ -74,6 +74,7 @@ struct OpProfile { double ms = 0; double flops = 0; double bytes = 0; long long 
 
 struct Variant {
     Lowered L;
+    int key = 0;                         // dense id (profile bookkeeping)
     DevBuf const_arena;
     DevBuf outleaf_desc;
     std::vector<OpParams> tmpl;          // per op, pointers unset
@@ -85,9 +86,10 @@ struct EventPair { cudaEvent_t a, b; int variant, op; };
 // A whole qxb_amplitudes step captured as a CUDA graph, keyed by everything the
 // launches depend on.  Replay removes ~550 launch gaps per step.
 struct StepKey {
-    const void* bits; void* out; int64_t n_amp, s0, s1; cudaStream_t st;
+    const void* bits; void* out; int64_t n_amp, s0, s1; uint64_t mask, vals_hash; cudaStream_t st;
     bool operator<(const StepKey& o) const {
-        return std::tie(bits, out, n_amp, s0, s1, st) < std::tie(o.bits, o.out, o.n_amp, o.s0, o.s1, o.st);
+        return std::tie(bits, out, n_amp, s0, s1, mask, vals_hash, st) <
+               std::tie(o.bits, o.out, o.n_amp, o.s0, o.s1, o.mask, o.vals_hash, o.st);
     }
 };
 struct StepGraph { cudaGraphExec_t exec = nullptr; qxb_stats stats{}; };
@@ -101,7 +103,7 @@ struct qxb_graph {
     bool compiled = false;
     qxb_options opts{};
     std::map<std::string, DevBuf> leafbuf;
-    std::map<int, std::unique_ptr<Variant>> variants;
+    std::map<uint64_t, std::unique_ptr<Variant>> variants;
     DevBuf block_arena, chunk_arena, acc, d_bits, d_out;
     qxb_stats stats{};
     std::vector<EventPair> events;
@@ -278,57 +280,86 @@ void build_templates(Variant& v, int dtype) {
     }
 }
 
-void run_phase(const RunCtx& c, Phase ph) {
+// ------------------------------------------------------------------ step nodes
+// A step is a DAG of kernel nodes.  Edges: producer -> consumer, last reader ->
+// re-user of an arena region (from plan_memory), and the serial spine
+// memset -> [block: (chunk: output leaves -> ... -> root reduce)*]* -> finalize.
+// The same list is either launched in order on the stream (profiling / no-graph
+// mode) or instantiated as a CUDA graph with exactly these edges, so independent
+// branches of the contraction tree run concurrently.
+struct Node {
+    const void* func = nullptr;          // nullptr: memset node
+    dim3 grid{1, 1, 1}, block{1, 1, 1};
+    std::vector<char> argmem;            // packed argument values
+    std::vector<size_t> argoff;          // offset of each argument in argmem
+    std::vector<int> deps;
+    void* ms_ptr = nullptr; size_t ms_bytes = 0;
+    int variant = -1, op = -1;           // contraction nodes: where to book profile time
+    double flops = 0, bytes = 0;
+    template <typename T> void arg(const T& v) {
+        size_t off = (argmem.size() + alignof(T) - 1) / alignof(T) * alignof(T);
+        if (alignof(T) < 16 && sizeof(T) >= 16) off = (argmem.size() + 15) / 16 * 16;
+        argmem.resize(off + sizeof(T));
+        memcpy(argmem.data() + off, &v, sizeof(T));
+        argoff.push_back(off);
+    }
+};
+
+Node contract_node(const RunCtx& c, int i) {
     qxb_graph* g = c.g;
     Lowered& L = c.v->L;
-    cudaStream_t st = stream();
-    for (size_t i = 0; i < L.ops.size(); ++i) {
-        const LOp& op = L.ops[i];
-        if (op.phase != ph) continue;
-        const LTensor &A = L.tensors[op.a], &B = L.tensors[op.b], &C = L.tensors[op.c];
-        OpParams p = c.v->tmpl[i];
-        p.A = tensor_ptr(c, A); p.B = tensor_ptr(c, B); p.C = tensor_ptr(c, C);
-        p.sUA = A.amp ? (1ll << A.span_bits) : 0;
-        p.sUB = B.amp ? (1ll << B.span_bits) : 0;
-        p.sUC = C.amp ? (1ll << C.span_bits) : 0;
-        p.U = C.amp ? (int)c.n : 1;
-        p.tiles = (long long)p.U << p.hb;
-        const int sub_bits = 8 - p.lob;
-        long long blocks = (p.tiles + (1ll << sub_bits) - 1) >> sub_bits;
-        const long long cap = (long long)g_num_sms * 8;
-        const int grid = (int)std::max<long long>(1, std::min(blocks, cap));
-        const double u = (double)p.U;
-        const double flops = 8.0 * op.macs_per_amp * u;
-        const double bytes = (double)g->es() * (op.elems_a * (A.amp ? c.n : 1) + op.elems_b * (B.amp ? c.n : 1) +
-                                                op.elems_c * u);
-        EventPair* ev = nullptr;
-        if (g->opts.profile) {
-            if (g->events_used == g->events.size()) {
-                EventPair e{};
-                CUDA_OK(cudaEventCreate(&e.a)); CUDA_OK(cudaEventCreate(&e.b));
-                g->events.push_back(e);
-            }
-            ev = &g->events[g->events_used++];
-            ev->variant = c.variant_key; ev->op = (int)i;
-            CUDA_OK(cudaEventRecord(ev->a, st));
-        }
-        launch_contract(g->dtype, p, grid, st);
-        if (ev) CUDA_OK(cudaEventRecord(ev->b, st));
-        g->stats.kernel_launches++; g->stats.contract_launches++;
-        g->stats.flops += flops; g->stats.bytes += bytes;
-        if (g->opts.profile) {
-            OpProfile& pr = c.v->prof[i];
-            pr.flops += flops; pr.bytes += bytes; pr.launches++;
-        }
+    const LOp& op = L.ops[i];
+    const LTensor &A = L.tensors[op.a], &B = L.tensors[op.b], &C = L.tensors[op.c];
+    OpParams p = c.v->tmpl[i];
+    p.A = tensor_ptr(c, A); p.B = tensor_ptr(c, B); p.C = tensor_ptr(c, C);
+    p.sUA = A.amp ? (1ll << A.span_bits) : 0;
+    p.sUB = B.amp ? (1ll << B.span_bits) : 0;
+    p.sUC = C.amp ? (1ll << C.span_bits) : 0;
+    p.U = C.amp ? (int)c.n : 1;
+    p.tiles = (long long)p.U << p.hb;
+    const int sub_bits = 8 - p.lob;
+    const long long blocks = (p.tiles + (1ll << sub_bits) - 1) >> sub_bits;
+    const long long cap = (long long)g_num_sms * 8;
+    Node n;
+    const double outputs = (double)p.U * std::ldexp(1.0, p.nC);
+    if (p.nK >= 5 && p.nC <= 8 && outputs < 32768.0) {
+        // reduction-shaped: too few outputs to fill the GPU with one thread each
+        n.func = kreduce_func(g->dtype);
+        const long long warps = (long long)outputs;
+        n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>((warps * 32 + kThreads - 1) / kThreads, cap)));
+    } else {
+        n.func = contract_func(g->dtype, p.kc, p.ma, p.nb);
+        n.grid = dim3((unsigned)std::max<long long>(1, std::min(blocks, cap)));
     }
+    n.block = dim3(kThreads);
+    n.arg(p);
+    n.variant = c.variant_key; n.op = i;
+    const double u = (double)p.U;
+    n.flops = 8.0 * op.macs_per_amp * u;
+    n.bytes = (double)g->es() * (op.elems_a * (A.amp ? c.n : 1) + op.elems_b * (B.amp ? c.n : 1) + op.elems_c * u);
+    return n;
+}
+
+void launch_node(const Node& n, cudaStream_t st) {
+    if (!n.func) { CUDA_OK(cudaMemsetAsync(n.ms_ptr, 0, n.ms_bytes, st)); return; }
+    void* args[12];
+    for (size_t a = 0; a < n.argoff.size(); ++a) args[a] = (void*)(n.argmem.data() + n.argoff[a]);
+    CUDA_OK(cudaLaunchKernel(n.func, n.grid, n.block, args, 0, st));
+}
+
+// constant folding at compile time: serial launches of the const-phase nodes
+void run_const_phase(const RunCtx& c) {
+    Lowered& L = c.v->L;
+    for (size_t i = 0; i < L.ops.size(); ++i)
+        if (L.ops[i].phase == PH_CONST) launch_node(contract_node(c, (int)i), stream());
     CUDA_OK(cudaGetLastError());
 }
 
-Variant* get_variant(qxb_graph* g, int n_free) {
-    auto it = g->variants.find(n_free);
+Variant* get_variant(qxb_graph* g, uint64_t free_mask) {
+    auto it = g->variants.find(free_mask);
     if (it != g->variants.end()) return it->second.get();
     std::unique_ptr<Variant> v(new Variant());
-    v->L = lower(g->prog, n_free, !g->opts.sum_at_root);
+    v->L = lower(g->prog, free_mask, !g->opts.sum_at_root);
     plan_memory(v->L, 1);
     build_templates(*v, g->dtype);
     const size_t es = g->es();
@@ -344,19 +375,18 @@ Variant* get_variant(qxb_graph* g, int n_free) {
     }
     // constant folding: nodes that depend on no slice variable and no output bit run once
     std::vector<int64_t> zeros(g->prog.vars.size() + 1, 0);
-    RunCtx c{g, v.get(), n_free, zeros.data(), 1};
-    const int prof = g->opts.profile;
-    g->opts.profile = 0;
-    run_phase(c, PH_CONST);
-    g->opts.profile = prof;
+    v->key = (int)g->variants.size();
+    RunCtx c{g, v.get(), v->key, zeros.data(), 1};
+    run_const_phase(c);
     CUDA_OK(cudaStreamSynchronize(stream()));
     Variant* raw = v.get();
-    g->variants[n_free] = std::move(v);
+    g->variants[free_mask] = std::move(v);
     return raw;
 }
 
-struct Block { int n_free; std::vector<int64_t> vals; };
+struct Block { uint64_t free_mask; std::vector<int64_t> vals; };
 
+// aligned blocks of a contiguous range of linear slice ids (low variables free)
 std::vector<Block> decompose(const Program& p, int64_t b, int64_t e) {
     const int k = (int)p.vars.size();
     std::vector<int64_t> place(k + 1, 1);
@@ -365,7 +395,7 @@ std::vector<Block> decompose(const Program& p, int64_t b, int64_t e) {
     while (b < e) {
         int j = 0;
         while (j < k && b % place[j + 1] == 0 && b + place[j + 1] <= e) ++j;
-        Block blk; blk.n_free = j; blk.vals.assign(k + 1, 0);
+        Block blk; blk.free_mask = low_mask(j); blk.vals.assign(k + 1, 0);
         slice_values(p, b, blk.vals.data());
         out.push_back(std::move(blk));
         b += place[j];
@@ -380,10 +410,10 @@ struct StepPlan {
 };
 
 // Everything that may allocate, synchronise or query the device happens here,
-// outside stream capture.
-StepPlan prepare_step(qxb_graph* g, int64_t n_amp, int64_t s0, int64_t s1) {
+// before any node is built.
+StepPlan prepare_step(qxb_graph* g, std::vector<Block> blocks, int64_t n_amp) {
     StepPlan sp;
-    sp.blocks = decompose(g->prog, s0, s1);
+    sp.blocks = std::move(blocks);
     size_t free_b = 0, total_b = 0;
     CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
     const size_t es = g->es();
@@ -394,7 +424,7 @@ StepPlan prepare_step(qxb_graph* g, int64_t n_amp, int64_t s0, int64_t s1) {
     if (g->opts.amp_batch > 0) chunk = std::min<int64_t>(chunk, g->opts.amp_batch);
     int64_t max_block = 2 * (int64_t)es, max_per_amp = 2 * (int64_t)es;
     for (const Block& blk : sp.blocks) {
-        Variant* v = get_variant(g, blk.n_free);
+        Variant* v = get_variant(g, blk.free_mask);
         sp.variants.push_back(v);
         const int64_t block_bytes = std::max<int64_t>(v->L.block_elems, 2) * es;
         const int64_t per_amp = std::max<int64_t>(v->L.chunk_elems_per_amp, 2) * es;
@@ -419,31 +449,178 @@ StepPlan prepare_step(qxb_graph* g, int64_t n_amp, int64_t s0, int64_t s1) {
     return sp;
 }
 
-void issue_step(qxb_graph* g, const StepPlan& sp, const uint8_t* d_bits, int64_t n_amp, void* d_out) {
-    cudaStream_t st = stream();
-    CUDA_OK(cudaMemsetAsync(g->acc.p, 0, sizeof(double) * 2 * n_amp, st));
+std::vector<Node> build_step(qxb_graph* g, const StepPlan& sp, const uint8_t* d_bits, int64_t n_amp, void* d_out) {
+    std::vector<Node> nodes;
+    {
+        Node m; m.ms_ptr = g->acc.p; m.ms_bytes = sizeof(double) * 2 * n_amp;
+        nodes.push_back(std::move(m));
+    }
+    int sink = 0;                                     // last node of the serial spine
     for (size_t bi = 0; bi < sp.blocks.size(); ++bi) {
         const Block& blk = sp.blocks[bi];
         Variant* v = sp.variants[bi];
         Lowered& L = v->L;
-        RunCtx c{g, v, blk.n_free, blk.vals.data(), 1};
-        run_phase(c, PH_BLOCK);
+        RunCtx c{g, v, v->key, blk.vals.data(), 1};
+        std::vector<int> node_of(L.ops.size(), -1);   // block-phase ops of this block
+        for (size_t i = 0; i < L.ops.size(); ++i) {
+            if (L.ops[i].phase != PH_BLOCK) continue;
+            Node n = contract_node(c, (int)i);
+            for (int d : L.ops[i].deps) if (node_of[d] >= 0) n.deps.push_back(node_of[d]);
+            if (n.deps.empty()) n.deps.push_back(sink);
+            node_of[i] = (int)nodes.size();
+            nodes.push_back(std::move(n));
+        }
         const LTensor& R = L.tensors[L.root];
+        int root_op = -1;
+        for (size_t i = 0; i < L.ops.size(); ++i) if (L.ops[i].c == L.root) root_op = (int)i;
         for (int64_t a0 = 0; a0 < n_amp; a0 += sp.chunk) {
             c.n = std::min(sp.chunk, n_amp - a0);
+            int start = sink;
             if (!L.output_leaves.empty()) {
-                launch_output_leaves(g->dtype, g->chunk_arena.p, (const OutLeafDesc*)v->outleaf_desc.p,
-                                     (int)L.output_leaves.size(), d_bits, g->prog.n_outputs, a0, c.n, st);
-                g->stats.kernel_launches++;
+                Node n;
+                n.func = outleaf_func(g->dtype);
+                const long long nb = std::min<long long>(64, std::max<long long>(1, (c.n * 2 + 255) / 256));
+                n.grid = dim3((unsigned)nb, (unsigned)L.output_leaves.size()); n.block = dim3(256);
+                n.arg((void*)g->chunk_arena.p); n.arg((const OutLeafDesc*)v->outleaf_desc.p); n.arg((const unsigned char*)d_bits);
+                n.arg((int)g->prog.n_outputs); n.arg((long long)a0); n.arg((long long)c.n);
+                n.deps.push_back(sink);
+                start = (int)nodes.size();
+                nodes.push_back(std::move(n));
             }
-            run_phase(c, PH_CHUNK);
-            launch_reduce_root(g->dtype, tensor_ptr(c, R), R.amp ? (1ll << R.span_bits) : 0, R.span_bits, c.n,
-                               L.root_scale, (double*)g->acc.p, a0, st);
-            g->stats.kernel_launches++;
+            std::vector<int> cnode(L.ops.size(), -1);
+            for (size_t i = 0; i < L.ops.size(); ++i) {
+                if (L.ops[i].phase != PH_CHUNK) continue;
+                Node n = contract_node(c, (int)i);
+                for (int d : L.ops[i].deps) {
+                    const int nd = L.ops[d].phase == PH_CHUNK ? cnode[d] : node_of[d];
+                    if (nd >= 0) n.deps.push_back(nd);
+                }
+                if (L.tensors[L.ops[i].a].is_output_leaf || L.tensors[L.ops[i].b].is_output_leaf || n.deps.empty())
+                    n.deps.push_back(start);
+                cnode[i] = (int)nodes.size();
+                nodes.push_back(std::move(n));
+            }
+            Node r;
+            r.func = reduce_root_func(g->dtype);
+            long long rb = (c.n * 32 + 255) / 256;
+            r.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(rb, 148 * 8))); r.block = dim3(256);
+            r.arg((const void*)tensor_ptr(c, R)); r.arg((long long)(R.amp ? (1ll << R.span_bits) : 0)); r.arg((int)R.span_bits);
+            r.arg((long long)c.n); r.arg((double)L.root_scale); r.arg((double*)g->acc.p); r.arg((long long)a0);
+            r.deps.push_back(sink);
+            if (start != sink) r.deps.push_back(start);
+            if (root_op >= 0) {
+                const int nd = L.ops[root_op].phase == PH_CHUNK ? cnode[root_op] : node_of[root_op];
+                if (nd >= 0) r.deps.push_back(nd);
+            }
+            // every node of this iteration must be done before the spine moves on
+            for (size_t i = 0; i < L.ops.size(); ++i) if (cnode[i] >= 0 && L.tensors[L.ops[i].c].last_use == -1) r.deps.push_back(cnode[i]);
+            sink = (int)nodes.size();
+            nodes.push_back(std::move(r));
         }
     }
-    launch_finalize(g->dtype, (const double*)g->acc.p, d_out, n_amp, st);
-    g->stats.kernel_launches++;
+    Node f;
+    f.func = finalize_func(g->dtype);
+    f.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>((n_amp + 255) / 256, 1024))); f.block = dim3(256);
+    f.arg((const double*)g->acc.p); f.arg((void*)d_out); f.arg((long long)n_amp);
+    f.deps.push_back(sink);
+    nodes.push_back(std::move(f));
+    return nodes;
+}
+
+void account(qxb_graph* g, const std::vector<Node>& nodes) {
+    for (const Node& n : nodes) {
+        if (n.func) g->stats.kernel_launches++;
+        if (n.op >= 0) { g->stats.contract_launches++; g->stats.flops += n.flops; g->stats.bytes += n.bytes; }
+    }
+}
+
+void launch_serial(qxb_graph* g, const std::vector<Node>& nodes) {
+    cudaStream_t st = stream();
+    for (const Node& n : nodes) {
+        EventPair* ev = nullptr;
+        if (g->opts.profile && n.op >= 0) {
+            if (g->events_used == g->events.size()) {
+                EventPair e{};
+                CUDA_OK(cudaEventCreate(&e.a)); CUDA_OK(cudaEventCreate(&e.b));
+                g->events.push_back(e);
+            }
+            ev = &g->events[g->events_used++];
+            ev->variant = n.variant; ev->op = n.op;
+            CUDA_OK(cudaEventRecord(ev->a, st));
+        }
+        launch_node(n, st);
+        if (ev) {
+            CUDA_OK(cudaEventRecord(ev->b, st));
+            for (auto& kv : g->variants)
+                if (kv.second->key == n.variant) {
+                    OpProfile& pr = kv.second->prof[n.op];
+                    pr.flops += n.flops; pr.bytes += n.bytes; pr.launches++;
+                }
+        }
+    }
+    CUDA_OK(cudaGetLastError());
+}
+
+cudaGraphExec_t instantiate(const std::vector<Node>& nodes) {
+    cudaGraph_t graph = nullptr;
+    CUDA_OK(cudaGraphCreate(&graph, 0));
+    std::vector<cudaGraphNode_t> gn(nodes.size(), nullptr);
+    try {
+        for (size_t i = 0; i < nodes.size(); ++i) {
+            const Node& n = nodes[i];
+            std::vector<cudaGraphNode_t> deps;
+            for (int d : n.deps) deps.push_back(gn[d]);
+            std::sort(deps.begin(), deps.end());
+            deps.erase(std::unique(deps.begin(), deps.end()), deps.end());
+            if (!n.func) {
+                cudaMemsetParams mp{};
+                mp.dst = n.ms_ptr; mp.value = 0; mp.elementSize = 1; mp.width = n.ms_bytes; mp.height = 1; mp.pitch = n.ms_bytes;
+                CUDA_OK(cudaGraphAddMemsetNode(&gn[i], graph, deps.data(), deps.size(), &mp));
+            } else {
+                void* args[12];
+                for (size_t a = 0; a < n.argoff.size(); ++a) args[a] = (void*)(n.argmem.data() + n.argoff[a]);
+                cudaKernelNodeParams kp{};
+                kp.func = (void*)n.func; kp.gridDim = n.grid; kp.blockDim = n.block; kp.sharedMemBytes = 0;
+                kp.kernelParams = args; kp.extra = nullptr;
+                CUDA_OK(cudaGraphAddKernelNode(&gn[i], graph, deps.data(), deps.size(), &kp));
+            }
+        }
+        cudaGraphExec_t exec = nullptr;
+        CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        return exec;
+    } catch (...) {
+        cudaGraphDestroy(graph);
+        throw;
+    }
+}
+
+void run_blocks(qxb_graph* g, std::vector<Block> blocks, StepKey key, const uint8_t* d_bits, int64_t n_amp, void* d_out) {
+    g->stats = qxb_stats{};
+    g->events_used = 0;
+    for (auto& kv : g->variants) kv.second->prof.assign(kv.second->L.ops.size(), OpProfile{});
+    if (n_amp == 0) return;
+    cudaStream_t st = stream();
+    key.st = st;
+    const bool use_graph = !g->opts.profile && !g->opts.no_cuda_graph;
+    if (use_graph) {
+        auto it = g->step_graphs.find(key);
+        if (it != g->step_graphs.end()) {
+            g->stats = it->second.stats;
+            CUDA_OK(cudaGraphLaunch(it->second.exec, st));
+            return;
+        }
+    }
+    StepPlan sp = prepare_step(g, std::move(blocks), n_amp);
+    std::vector<Node> nodes = build_step(g, sp, d_bits, n_amp, d_out);
+    account(g, nodes);
+    if (!use_graph) { launch_serial(g, nodes); return; }
+    if (g->step_graphs.size() >= 32) g->drop_step_graphs();
+    StepGraph sg;
+    sg.exec = instantiate(nodes);
+    sg.stats = g->stats;
+    g->step_graphs.emplace(key, sg);
+    CUDA_OK(cudaGraphLaunch(sg.exec, st));
 }
 
 void run_amplitudes(qxb_graph* g, const uint8_t* d_bits, int64_t n_amp, int64_t s0, int64_t s1, void* d_out) {
@@ -451,43 +628,29 @@ void run_amplitudes(qxb_graph* g, const uint8_t* d_bits, int64_t n_amp, int64_t 
     const int64_t S = num_slices(g->prog);
     if (s0 < 0 || s1 > S || s0 > s1) throw Error(QXB_ERR_ARG, "slice range out of bounds");
     if (n_amp < 0) throw Error(QXB_ERR_ARG, "negative amplitude count");
-    g->stats = qxb_stats{};
-    g->events_used = 0;
-    for (auto& kv : g->variants) kv.second->prof.assign(kv.second->L.ops.size(), OpProfile{});
-    if (n_amp == 0) return;
-    cudaStream_t st = stream();
-    StepPlan sp = prepare_step(g, n_amp, s0, s1);
-    const bool use_graph = !g->opts.profile && !g->opts.no_cuda_graph;
-    if (!use_graph) {
-        issue_step(g, sp, d_bits, n_amp, d_out);
-        CUDA_OK(cudaGetLastError());
-        return;
+    StepKey key{d_bits, d_out, n_amp, s0, s1, 0, 0, nullptr};
+    run_blocks(g, decompose(g->prog, s0, s1), key, d_bits, n_amp, d_out);
+}
+
+void run_subspace(qxb_graph* g, const uint8_t* d_bits, int64_t n_amp, const int32_t* fvars, const int64_t* fvals,
+                  int n_fixed, void* d_out) {
+    if (!g->compiled) throw Error(QXB_ERR_STATE, "graph not compiled");
+    if (n_amp < 0 || n_fixed < 0) throw Error(QXB_ERR_ARG, "negative count");
+    const int k = (int)g->prog.vars.size();
+    Block blk; blk.free_mask = low_mask(k); blk.vals.assign(k + 1, 0);
+    uint64_t vh = 1469598103934665603ull;
+    for (int i = 0; i < n_fixed; ++i) {
+        const int v = fvars[i];
+        if (v < 0 || v >= k) throw Error(QXB_ERR_ARG, "fixed slice variable out of range");
+        if (!((blk.free_mask >> v) & 1ull)) throw Error(QXB_ERR_ARG, "slice variable fixed twice");
+        if (fvals[i] < 0 || fvals[i] >= g->prog.vars[v].dim) throw Error(QXB_ERR_ARG, "fixed value out of range");
+        blk.free_mask &= ~(1ull << v);
+        blk.vals[v] = fvals[i];
     }
-    StepKey key{d_bits, d_out, n_amp, s0, s1, st};
-    auto it = g->step_graphs.find(key);
-    if (it == g->step_graphs.end()) {
-        if (g->step_graphs.size() >= 32) g->drop_step_graphs();
-        const qxb_stats pre = g->stats;
-        CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        cudaGraph_t graph = nullptr;
-        try {
-            issue_step(g, sp, d_bits, n_amp, d_out);
-        } catch (...) {
-            cudaStreamEndCapture(st, &graph);
-            if (graph) cudaGraphDestroy(graph);
-            g->stats = pre;
-            throw;
-        }
-        CUDA_OK(cudaStreamEndCapture(st, &graph));
-        StepGraph sg;
-        cudaError_t e = cudaGraphInstantiate(&sg.exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (e != cudaSuccess) throw Error(QXB_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
-        sg.stats = g->stats;
-        it = g->step_graphs.emplace(key, sg).first;
-    }
-    g->stats = it->second.stats;
-    CUDA_OK(cudaGraphLaunch(it->second.exec, st));
+    for (int v = 0; v < k; ++v) vh = (vh ^ (uint64_t)blk.vals[v]) * 1099511628211ull;
+    StepKey key{d_bits, d_out, n_amp, -1, -1, blk.free_mask, vh, nullptr};
+    std::vector<Block> blocks; blocks.push_back(std::move(blk));
+    run_blocks(g, std::move(blocks), key, d_bits, n_amp, d_out);
 }
 
 void collect_profile(qxb_graph* g) {
@@ -495,8 +658,8 @@ void collect_profile(qxb_graph* g) {
         EventPair& e = g->events[i];
         float ms = 0;
         if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
-            auto it = g->variants.find(e.variant);
-            if (it != g->variants.end() && e.op < (int)it->second->prof.size()) it->second->prof[e.op].ms += ms;
+            for (auto& kv : g->variants)
+                if (kv.second->key == e.variant && e.op < (int)kv.second->prof.size()) kv.second->prof[e.op].ms += ms;
         }
     }
     g->events_used = 0;
@@ -690,7 +853,8 @@ int64_t qxb_graph_describe(qxb_graph* g, int n_free, char* buf, int64_t buflen) 
     int rc = guard([&] {
         if (!g) throw Error(QXB_ERR_ARG, "null graph");
         ensure_analysed(g);
-        Lowered L = lower(g->prog, n_free, !g->opts.sum_at_root);
+        const int k = (int)g->prog.vars.size();
+        Lowered L = lower(g->prog, low_mask(n_free < 0 || n_free > k ? k : n_free), !g->opts.sum_at_root);
         plan_memory(L, 1);
         std::string s = describe_json(g->prog, L);
         need = (int64_t)s.size() + 1;
@@ -716,7 +880,7 @@ int qxb_graph_compile(qxb_graph* g, const qxb_options* opts) {
         upload_leaves(g);
         g->compiled = true;
         try {
-            get_variant(g, (int)g->prog.vars.size());     // lower + fold constants for the all-free case
+            get_variant(g, low_mask((int)g->prog.vars.size()));     // lower + fold constants for the all-free case
         } catch (...) {
             g->compiled = false;
             throw;
@@ -760,6 +924,60 @@ int qxb_amplitudes(qxb_graph* g, const uint8_t* bits, int64_t n_amp, int64_t s0,
     });
 }
 
+int qxb_amplitudes_subspace(qxb_graph* g, const uint8_t* bits, int64_t n_amp, const int32_t* fixed_vars,
+                            const int64_t* fixed_vals, int n_fixed, void* out, int on_device) {
+    return guard([&] {
+        if (!g) throw Error(QXB_ERR_ARG, "null graph");
+        if (n_amp < 0) throw Error(QXB_ERR_ARG, "negative amplitude count");
+        if (n_amp == 0) return;
+        if (!out || (!bits && g->prog.n_outputs > 0) || (n_fixed > 0 && (!fixed_vars || !fixed_vals)))
+            throw Error(QXB_ERR_ARG, "null buffer");
+        if (!g->compiled) throw Error(QXB_ERR_STATE, "graph not compiled");
+        ensure_init();
+        cudaStream_t st = stream();
+        if (on_device) {
+            run_subspace(g, bits, n_amp, fixed_vars, fixed_vals, n_fixed, out);
+            if (g->opts.profile) { CUDA_OK(cudaStreamSynchronize(st)); collect_profile(g); }
+            return;
+        }
+        for (size_t i = 0; i < (size_t)n_amp * g->prog.n_outputs; ++i)
+            if (bits[i] > 3) throw Error(QXB_ERR_ARG, "bitstring entries must be 0, 1, 2 ('+') or 3 ('-')");
+        g->d_bits.reserve((size_t)n_amp * std::max(1, g->prog.n_outputs));
+        g->d_out.reserve((size_t)n_amp * g->es());
+        if (g->prog.n_outputs > 0)
+            CUDA_OK(cudaMemcpyAsync(g->d_bits.p, bits, (size_t)n_amp * g->prog.n_outputs, cudaMemcpyHostToDevice, st));
+        run_subspace(g, (const uint8_t*)g->d_bits.p, n_amp, fixed_vars, fixed_vals, n_fixed, g->d_out.p);
+        CUDA_OK(cudaMemcpyAsync(out, g->d_out.p, (size_t)n_amp * g->es(), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        if (g->opts.profile) collect_profile(g);
+    });
+}
+
+int qxb_partition_vars(qxb_graph* g, int n_parts, int32_t* vars_out, int* n_vars_out) {
+    return guard([&] {
+        if (!g || !n_vars_out) throw Error(QXB_ERR_ARG, "null argument");
+        if (n_parts < 1) throw Error(QXB_ERR_ARG, "n_parts must be >= 1");
+        ensure_analysed(g);
+        std::vector<int> v = partition_vars(g->prog, n_parts, !g->opts.sum_at_root);
+        *n_vars_out = (int)v.size();
+        if (vars_out) for (size_t i = 0; i < v.size(); ++i) vars_out[i] = v[i];
+    });
+}
+
+int64_t qxb_graph_describe_mask(qxb_graph* g, uint64_t free_mask, char* buf, int64_t buflen) {
+    int64_t need = 0;
+    int rc = guard([&] {
+        if (!g) throw Error(QXB_ERR_ARG, "null graph");
+        ensure_analysed(g);
+        Lowered L = lower(g->prog, free_mask, !g->opts.sum_at_root);
+        plan_memory(L, 1);
+        std::string s = describe_json(g->prog, L);
+        need = (int64_t)s.size() + 1;
+        if (buf && buflen >= need) memcpy(buf, s.c_str(), need);
+    });
+    return rc == QXB_OK ? need : rc;
+}
+
 int qxb_last_stats(const qxb_graph* g, qxb_stats* st) {
     return guard([&] {
         if (!g || !st) throw Error(QXB_ERR_ARG, "null argument");
@@ -776,7 +994,8 @@ int qxb_profile_dump(qxb_graph* g, const char* path) {
         bool firstv = true;
         for (auto& kv : g->variants) {
             Variant& v = *kv.second;
-            fprintf(f, "%s{\"n_free\":%d,\"ops\":[", firstv ? "" : ",", kv.first);
+            fprintf(f, "%s{\"n_free\":%d,\"free_mask\":%llu,\"ops\":[", firstv ? "" : ",", v.L.n_free,
+                    (unsigned long long)kv.first);
             firstv = false;
             bool first = true;
             for (size_t i = 0; i < v.L.ops.size(); ++i) {

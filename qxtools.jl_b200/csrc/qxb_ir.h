@@ -118,13 +118,16 @@ struct LOp {
     int nC = 0, nK = 0;
     int n_batch = 0, n_m = 0, n_n = 0;   // bit counts of the (batch, M, N) split; nK bits of K
     std::vector<Seg> segA, segB, segKA, segKB;
+    std::vector<int> deps;         // ops that must finish first: producers of A/B and, after plan_memory,
+                                   // the last readers of any arena region C overwrites (write-after-read)
     double macs_per_amp = 0;       // complex MACs per amplitude row (2^(nC+nK))
     double elems_a = 0, elems_b = 0, elems_c = 0;   // stored elements per amplitude row
     std::string name;
 };
 
 struct Lowered {
-    int n_free = 0;                // variables [0, n_free) are batched, the rest fixed
+    uint64_t free_mask = 0;        // bit v set: slice variable v is batched; clear: fixed by the caller
+    int n_free = 0;                // popcount(free_mask)
     bool early_sum = true;         // batched variables summed at the lowest covering node (else at the root)
     std::vector<LTensor> tensors;
     std::vector<LOp> ops;
@@ -137,8 +140,13 @@ struct Lowered {
     int64_t const_elems = 0, block_elems = 0, chunk_fixed_elems = 0, chunk_elems_per_amp = 0;
 };
 
-// Lower for a given number of free (batched) low slice variables.
-Lowered lower(const Program& p, int n_free, bool early_sum = true);
+// Lower for a given set of free (batched) slice variables.
+Lowered lower(const Program& p, uint64_t free_mask, bool early_sum = true);
+inline uint64_t low_mask(int n) { return n >= 64 ? ~0ull : ((1ull << n) - 1ull); }
+// Greedy choice of slice variables to FIX when sharding the slice space over n_parts ranks:
+// at each step the variable whose fixing leaves the least work (bytes moved) per rank.
+std::vector<int> partition_vars(const Program& p, int n_parts, bool early_sum = true);
+double lowered_cost_bytes(const Lowered& L, double n_amp, double elem_bytes);
 // Plan arena offsets for a batch of n_amp bitstrings (fills LTensor::offset and the arena sizes).
 void plan_memory(Lowered& L, int64_t n_amp);
 std::string describe_json(const Program& p, const Lowered& L);

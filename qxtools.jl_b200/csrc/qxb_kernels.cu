@@ -104,34 +104,79 @@ contract_kernel(const __grid_constant__ OpParams p) {
 }
 
 template <typename R2, int KC, int MA>
-static void launch_nb(const OpParams& p, int grid, cudaStream_t st) {
-    switch (p.nb) {
-    case 0: contract_kernel<R2, KC, MA, 0><<<grid, kThreads, 0, st>>>(p); break;
-    case 1: contract_kernel<R2, KC, MA, 1><<<grid, kThreads, 0, st>>>(p); break;
-    default: contract_kernel<R2, KC, MA, 2><<<grid, kThreads, 0, st>>>(p); break;
+static const void* pick_nb(int nb) {
+    switch (nb) {
+    case 0: return (const void*)&contract_kernel<R2, KC, MA, 0>;
+    case 1: return (const void*)&contract_kernel<R2, KC, MA, 1>;
+    default: return (const void*)&contract_kernel<R2, KC, MA, 2>;
     }
 }
 template <typename R2, int KC>
-static void launch_ma(const OpParams& p, int grid, cudaStream_t st) {
-    switch (p.ma) {
-    case 0: launch_nb<R2, KC, 0>(p, grid, st); break;
-    case 1: launch_nb<R2, KC, 1>(p, grid, st); break;
-    default: launch_nb<R2, KC, 2>(p, grid, st); break;
+static const void* pick_ma(int ma, int nb) {
+    switch (ma) {
+    case 0: return pick_nb<R2, KC, 0>(nb);
+    case 1: return pick_nb<R2, KC, 1>(nb);
+    default: return pick_nb<R2, KC, 2>(nb);
     }
 }
 template <typename R2>
-static void launch_kc(const OpParams& p, int grid, cudaStream_t st) {
-    switch (p.kc) {
-    case 0: launch_ma<R2, 0>(p, grid, st); break;
-    case 1: launch_ma<R2, 1>(p, grid, st); break;
-    case 2: launch_ma<R2, 2>(p, grid, st); break;
-    default: launch_ma<R2, 3>(p, grid, st); break;
+static const void* pick_kc(int kc, int ma, int nb) {
+    switch (kc) {
+    case 0: return pick_ma<R2, 0>(ma, nb);
+    case 1: return pick_ma<R2, 1>(ma, nb);
+    case 2: return pick_ma<R2, 2>(ma, nb);
+    default: return pick_ma<R2, 3>(ma, nb);
     }
 }
 
-void launch_contract(int dtype, const OpParams& p, int grid, cudaStream_t st) {
-    if (dtype == 0) launch_kc<float2>(p, grid, st);
-    else launch_kc<double2>(p, grid, st);
+const void* contract_func(int dtype, int kc, int ma, int nb) {
+    return dtype == 0 ? pick_kc<float2>(kc, ma, nb) : pick_kc<double2>(kc, ma, nb);
+}
+
+// Reduction-shaped nodes (few C elements, long K -- e.g. the root after the batched
+// slice variables were summed early): one warp per C element, lanes stride over k,
+// shuffle reduction.  Requires nC <= 8 (all C bits are "thread bits" in OpParams).
+template <typename R2>
+__global__ void __launch_bounds__(kThreads)
+kreduce_kernel(const __grid_constant__ OpParams p) {
+    const R2* __restrict__ A = reinterpret_cast<const R2*>(p.A);
+    const R2* __restrict__ B = reinterpret_cast<const R2*>(p.B);
+    R2* __restrict__ C = reinterpret_cast<R2*>(p.C);
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long total = (long long)p.U << p.nC;
+    const unsigned cmask = (1u << p.nC) - 1u;
+    const long long K = 1ll << p.nK;
+    for (long long o = warp; o < total; o += nwarps) {
+        const long long u = o >> p.nC;
+        const unsigned c = (unsigned)o & cmask;
+        const R2* Ap = A + u * p.sUA + segeval(p.sAlo, p.nsAlo, c);
+        const R2* Bp = B + u * p.sUB + segeval(p.sBlo, p.nsBlo, c);
+        R2 acc0, acc1; acc0.x = acc0.y = acc1.x = acc1.y = 0;
+        long long k = lane;
+        for (; k + 32 < K; k += 64) {
+            const R2 a0 = __ldg(Ap + segeval(p.kA, p.nkA, (unsigned long long)k));
+            const R2 b0 = __ldg(Bp + segeval(p.kB, p.nkB, (unsigned long long)k));
+            const R2 a1 = __ldg(Ap + segeval(p.kA, p.nkA, (unsigned long long)(k + 32)));
+            const R2 b1 = __ldg(Bp + segeval(p.kB, p.nkB, (unsigned long long)(k + 32)));
+            cmac(acc0, a0, b0); cmac(acc1, a1, b1);
+        }
+        for (; k < K; k += 32)
+            cmac(acc0, __ldg(Ap + segeval(p.kA, p.nkA, (unsigned long long)k)),
+                 __ldg(Bp + segeval(p.kB, p.nkB, (unsigned long long)k)));
+        acc0.x += acc1.x; acc0.y += acc1.y;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            acc0.x += __shfl_xor_sync(0xffffffffu, acc0.x, s);
+            acc0.y += __shfl_xor_sync(0xffffffffu, acc0.y, s);
+        }
+        if (lane == 0) C[u * p.sUC + c] = acc0;
+    }
+}
+
+const void* kreduce_func(int dtype) {
+    return dtype == 0 ? (const void*)&kreduce_kernel<float2> : (const void*)&kreduce_kernel<double2>;
 }
 
 // Output leaves: one-hot (or +/-) vectors selected by the bitstring
@@ -157,14 +202,8 @@ __global__ void outleaf_kernel(R2* base, const OutLeafDesc* __restrict__ d, cons
     }
 }
 
-void launch_output_leaves(int dtype, void* chunk_base, const OutLeafDesc* d_desc, int n_leaves,
-                          const unsigned char* d_bits, int n_outputs, long long amp0, long long n,
-                          cudaStream_t st) {
-    if (n_leaves == 0 || n == 0) return;
-    dim3 grid((unsigned)((n * 2 + 255) / 256 > 64 ? 64 : (n * 2 + 255) / 256), (unsigned)n_leaves);
-    if (grid.x == 0) grid.x = 1;
-    if (dtype == 0) outleaf_kernel<float2><<<grid, 256, 0, st>>>((float2*)chunk_base, d_desc, d_bits, n_outputs, amp0, n);
-    else outleaf_kernel<double2><<<grid, 256, 0, st>>>((double2*)chunk_base, d_desc, d_bits, n_outputs, amp0, n);
+const void* outleaf_func(int dtype) {
+    return dtype == 0 ? (const void*)&outleaf_kernel<float2> : (const void*)&outleaf_kernel<double2>;
 }
 
 // Sum of the saved scalar over the batched slice bits, in double, one warp per
@@ -195,15 +234,8 @@ __global__ void reduce_root_kernel(const R2* __restrict__ root, long long sU, in
     }
 }
 
-void launch_reduce_root(int dtype, const void* root, long long sU, int span_bits, long long n,
-                        double scale, double* acc, long long amp0, cudaStream_t st) {
-    if (n == 0) return;
-    long long blocks = (n * 32 + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    if (dtype == 0)
-        reduce_root_kernel<float2><<<(unsigned)blocks, 256, 0, st>>>((const float2*)root, sU, span_bits, n, scale, acc, amp0);
-    else
-        reduce_root_kernel<double2><<<(unsigned)blocks, 256, 0, st>>>((const double2*)root, sU, span_bits, n, scale, acc, amp0);
+const void* reduce_root_func(int dtype) {
+    return dtype == 0 ? (const void*)&reduce_root_kernel<float2> : (const void*)&reduce_root_kernel<double2>;
 }
 
 template <typename R2>
@@ -217,12 +249,8 @@ __global__ void finalize_kernel(const double* __restrict__ acc, R2* __restrict__
     }
 }
 
-void launch_finalize(int dtype, const double* acc, void* out, long long n, cudaStream_t st) {
-    if (n == 0) return;
-    long long blocks = (n + 255) / 256;
-    if (blocks > 1024) blocks = 1024;
-    if (dtype == 0) finalize_kernel<float2><<<(unsigned)blocks, 256, 0, st>>>(acc, (float2*)out, n);
-    else finalize_kernel<double2><<<(unsigned)blocks, 256, 0, st>>>(acc, (double2*)out, n);
+const void* finalize_func(int dtype) {
+    return dtype == 0 ? (const void*)&finalize_kernel<float2> : (const void*)&finalize_kernel<double2>;
 }
 
 }  // namespace qxb

@@ -44,13 +44,16 @@ struct OpParams {
 
 struct OutLeafDesc { long long offset_per_amp; int span_bits; int out_idx; };
 
-void launch_contract(int dtype, const OpParams& p, int grid, cudaStream_t st);
-void launch_output_leaves(int dtype, void* chunk_base, const OutLeafDesc* d_desc, int n_leaves,
-                          const unsigned char* d_bits, int n_outputs, long long amp0, long long n,
-                          cudaStream_t st);
-// acc[amp0 + u] += scale * sum_{i < 2^span} root[u*sU + i]
-void launch_reduce_root(int dtype, const void* root, long long sU, int span_bits, long long n,
-                        double scale, double* acc /*interleaved*/, long long amp0, cudaStream_t st);
-void launch_finalize(int dtype, const double* acc, void* out, long long n, cudaStream_t st);
+// Kernel entry points as function pointers (for cudaLaunchKernel / cudaGraphAddKernelNode).
+// contract: one argument (OpParams by value).
+const void* contract_func(int dtype, int kc, int ma, int nb);
+// warp-per-output reduction variant for nC <= 8 and long K (same OpParams argument)
+const void* kreduce_func(int dtype);
+// outleaf:  (R2* base, const OutLeafDesc* d, const unsigned char* bits, int n_outputs, long long amp0, long long n)
+const void* outleaf_func(int dtype);
+// reduce:   (const R2* root, long long sU, int span_bits, long long n, double scale, double* acc, long long amp0)
+const void* reduce_root_func(int dtype);
+// finalize: (const double* acc, R2* out, long long n)
+const void* finalize_func(int dtype);
 
 }  // namespace qxb

@@ -265,11 +265,14 @@ int find_entry(const LTensor& t, int key) {
 }
 }  // namespace
 
-Lowered lower(const Program& p, int n_free, bool early_sum) {
+Lowered lower(const Program& p, uint64_t free_mask, bool early_sum) {
     if (!p.analysed) throw Error(QXB_ERR_STATE, "program not analysed");
     const int k = (int)p.vars.size();
-    if (n_free < 0 || n_free > k) n_free = k;
-    Lowered L; L.n_free = n_free;
+    if (k > 63) throw Error(QXB_ERR_UNSUPP, "more than 63 slice variables");
+    free_mask &= low_mask(k);
+    auto is_free = [&](int v) { return ((free_mask >> v) & 1ull) != 0; };
+    Lowered L; L.free_mask = free_mask; L.n_free = __builtin_popcountll(free_mask);
+    std::vector<int> producer;                    // per LTensor: op that writes it (-1: leaf)
     std::vector<int> lt_of_def(p.defs.size(), -1);
     // Early summation of a batched slice variable: v is summed (becomes a K index) at
     // the node whose subtree holds ALL leaf uses that depend on v -- sum-product
@@ -296,7 +299,7 @@ Lowered lower(const Program& p, int n_free, bool early_sum) {
             const Mode& md = d.modes[m];
             if (md.var == -1) {
                 if (md.nbits > 0) t.lay.push_back(LayEntry{(int)m, md.nbits, pos});
-            } else if (md.var < n_free) {
+            } else if (is_free(md.var)) {
                 if (md.full_ext != p.vars[md.var].dim)
                     throw Error(QXB_ERR_ARG, "view on " + d.name + ": extent does not match the slice variable");
                 if (md.nbits > 0) t.lay.push_back(LayEntry{~md.var, md.nbits, pos});
@@ -320,6 +323,7 @@ Lowered lower(const Program& p, int n_free, bool early_sum) {
         std::map<int, int> cnt;
         for (int v : d.vars) cnt[v] = 1;
         use_cnt.push_back(std::move(cnt));
+        producer.push_back(-1);
         return lt_of_def[di];
     };
 
@@ -359,7 +363,7 @@ Lowered lower(const Program& p, int n_free, bool early_sum) {
         std::map<int, int> cntC = use_cnt[ia_t];
         for (auto& kv : use_cnt[ib_t]) cntC[kv.first] += kv.second;
         for (int v : vs) {
-            if (v >= n_free || p.vars[v].nbits == 0) continue;
+            if (!is_free(v) || p.vars[v].nbits == 0) continue;
             int posA = find_entry(L.tensors[ia_t], ~v), posB = find_entry(L.tensors[ib_t], ~v);
             if (posA < 0 && posB < 0) continue;          // already summed further down
             const bool done = early_sum && cntC[v] == total_uses[v];
@@ -418,9 +422,12 @@ Lowered lower(const Program& p, int n_free, bool early_sum) {
             T.last_use = oi;
             if (T.phase != op.phase) T.persistent = true;
         }
+        for (int t : {ia_t, ib_t})
+            if (producer[t] >= 0 && L.ops[producer[t]].phase != PH_CONST) op.deps.push_back(producer[t]);
         lt_of_def[di] = op.c;
         L.tensors.push_back(std::move(C));
         use_cnt.push_back(std::move(cntC));
+        producer.push_back(oi);
         L.ops.push_back(std::move(op));
     }
     const TensorDef& R = p.defs[p.root];
@@ -432,8 +439,8 @@ Lowered lower(const Program& p, int n_free, bool early_sum) {
         L.root_vars.push_back(~e.key);
     }
     L.root_scale = 1.0;
-    for (int v = 0; v < n_free; ++v)
-        if (!R.vars.count(v)) L.root_scale *= (double)p.vars[v].dim;
+    for (int v = 0; v < k; ++v)
+        if (is_free(v) && !R.vars.count(v)) L.root_scale *= (double)p.vars[v].dim;
     return L;
 }
 
@@ -480,7 +487,15 @@ inline int64_t unit_elems(const LTensor& t) { return std::max<int64_t>(2, int64_
 void plan_memory(Lowered& L, int64_t /*n_amp*/) {
     // Chunk-phase tensors all carry the amplitude axis, so their offsets are planned
     // per amplitude row and scaled by the batch size at launch time.
+    //
+    // The step runs as a dependency graph, not a serial stream: a buffer that reuses
+    // freed arena space must wait for the last reader of whatever lived there
+    // (write-after-read edge).  Small tensors are never recycled, so the hundreds of
+    // tiny nodes stay free of false dependencies; only the big ones share space.
+    const int64_t kNoReuseBelow = 512;       // elements per amplitude row
     Arena ar[3];
+    struct Freed { int phase; int64_t off, size; int last_reader; };
+    std::vector<Freed> freed;
     for (int ti : L.output_leaves) {
         LTensor& t = L.tensors[ti];
         t.offset = ar[PH_CHUNK].alloc(unit_elems(t));
@@ -488,12 +503,19 @@ void plan_memory(Lowered& L, int64_t /*n_amp*/) {
     for (size_t oi = 0; oi < L.ops.size(); ++oi) {
         LOp& op = L.ops[oi];
         LTensor& C = L.tensors[op.c];
-        C.offset = ar[op.phase].alloc(unit_elems(C));
+        const int64_t n = unit_elems(C);
+        C.offset = ar[op.phase].alloc(n);
+        for (const Freed& f : freed)
+            if (f.phase == (int)op.phase && f.off < C.offset + n && C.offset < f.off + f.size &&
+                std::find(op.deps.begin(), op.deps.end(), f.last_reader) == op.deps.end())
+                op.deps.push_back(f.last_reader);
         for (int ti : {op.a, op.b}) {
             LTensor& T = L.tensors[ti];
             if (T.is_leaf || T.persistent || T.offset < 0) continue;
-            if (T.last_use == (int)oi && T.phase == op.phase) {
+            if (T.last_use == (int)oi && T.phase == op.phase && unit_elems(T) >= kNoReuseBelow) {
                 ar[T.phase].release(T.offset, unit_elems(T));
+                freed.push_back(Freed{(int)T.phase, T.offset, unit_elems(T), (int)oi});
+                T.last_use = -2;          // released once, even if it is both operands
             }
         }
     }
@@ -501,6 +523,37 @@ void plan_memory(Lowered& L, int64_t /*n_amp*/) {
     L.block_elems = ar[PH_BLOCK].peak;
     L.chunk_fixed_elems = 0;
     L.chunk_elems_per_amp = ar[PH_CHUNK].peak;
+}
+
+double lowered_cost_bytes(const Lowered& L, double n_amp, double elem_bytes) {
+    double b = 0;
+    for (const LOp& op : L.ops) {
+        if (op.phase == PH_CONST) continue;
+        b += op.elems_a * (L.tensors[op.a].amp ? n_amp : 1) + op.elems_b * (L.tensors[op.b].amp ? n_amp : 1) +
+             op.elems_c * (L.tensors[op.c].amp ? n_amp : 1);
+    }
+    return b * elem_bytes;
+}
+
+std::vector<int> partition_vars(const Program& p, int n_parts, bool early_sum) {
+    const int k = (int)p.vars.size();
+    uint64_t mask = low_mask(k);
+    std::vector<int> chosen;
+    int64_t remaining = n_parts;
+    while (remaining > 1) {
+        int best = -1; double best_cost = 0;
+        for (int v = 0; v < k; ++v) {
+            if (!((mask >> v) & 1ull) || p.vars[v].dim < 2 || remaining % p.vars[v].dim) continue;
+            Lowered L = lower(p, mask & ~(1ull << v), early_sum);
+            const double c = lowered_cost_bytes(L, 1024.0, 1.0);
+            if (best < 0 || c < best_cost) { best = v; best_cost = c; }
+        }
+        if (best < 0) return {};              // the extents do not factor n_parts: caller falls back to ranges
+        chosen.push_back(best);
+        mask &= ~(1ull << best);
+        remaining /= p.vars[best].dim;
+    }
+    return chosen;
 }
 
 // ------------------------------------------------------------------- describe
@@ -513,7 +566,7 @@ static void seg_json(std::ostringstream& o, const std::vector<Seg>& s) {
 
 std::string describe_json(const Program& p, const Lowered& L) {
     std::ostringstream o;
-    o << "{\"early_sum\":" << (L.early_sum ? "true" : "false") << ",\"n_free\":" << L.n_free << ",\"n_slice_vars\":" << p.vars.size() << ",\"n_outputs\":" << p.n_outputs
+    o << "{\"early_sum\":" << (L.early_sum ? "true" : "false") << ",\"n_free\":" << L.n_free << ",\"free_mask\":" << L.free_mask << ",\"n_slice_vars\":" << p.vars.size() << ",\"n_outputs\":" << p.n_outputs
       << ",\"slice_vars\":[";
     for (size_t i = 0; i < p.vars.size(); ++i)
         o << (i ? "," : "") << "{\"sym\":\"" << p.vars[i].sym << "\",\"dim\":" << p.vars[i].dim << "}";
@@ -545,7 +598,9 @@ std::string describe_json(const Program& p, const Lowered& L) {
           << ",\"b_amp\":" << (L.tensors[op.b].amp ? "true" : "false") << ",\"segA\":";
         seg_json(o, op.segA); o << ",\"segB\":"; seg_json(o, op.segB);
         o << ",\"segKA\":"; seg_json(o, op.segKA); o << ",\"segKB\":"; seg_json(o, op.segKB);
-        o << "}";
+        o << ",\"deps\":[";
+        for (size_t j = 0; j < op.deps.size(); ++j) o << (j ? "," : "") << op.deps[j];
+        o << "]}";
     }
     o << "]}";
     return o.str();

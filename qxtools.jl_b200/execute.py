@@ -86,7 +86,17 @@ def execute(dsl_file: str, input_file: Optional[str] = None, param_file: Optiona
 
     t0 = time.perf_counter()
     mine = bitstrings[d.amp_begin:d.amp_end]
-    part = g.amplitudes(mine, d.slice_begin, d.slice_end) if mine else np.zeros(0, g.np_dtype)
+    # inside a sub-communicator the slice space is split by FIXING the slice variables the cost
+    # model picks (they carry the work); contiguous ranges when -n truncates the slice space
+    assign = None
+    if d.sub_comm_size > 1 and n_slices == g.n_slices:
+        assign = g.partition_assignment(d.sub_comm_size, d.rank_in_group)
+    if not mine:
+        part = np.zeros(0, g.np_dtype)
+    elif assign is not None:
+        part = g.amplitudes_subspace(mine, assign[0], assign[1])
+    else:
+        part = g.amplitudes(mine, d.slice_begin, d.slice_end)
     full = np.zeros(len(bitstrings), dtype=g.np_dtype)
     full[d.amp_begin:d.amp_end] = part
     if use_mpi and world > 1:

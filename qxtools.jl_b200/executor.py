@@ -128,6 +128,31 @@ class Graph:
         check(self._lib.qxb_graph_describe(self._h, n_free, buf, need))
         return json.loads(buf.value.decode())
 
+    def describe_mask(self, free_mask: int) -> dict:
+        need = check(self._lib.qxb_graph_describe_mask(self._h, free_mask, None, 0))
+        buf = C.create_string_buffer(need)
+        check(self._lib.qxb_graph_describe_mask(self._h, free_mask, buf, need))
+        return json.loads(buf.value.decode())
+
+    def partition_vars(self, n_parts: int) -> List[int]:
+        """0-based slice variables to fix when sharding over ``n_parts`` ranks ([] = use ranges)."""
+        n = C.c_int()
+        out = (C.c_int32 * 64)()
+        check(self._lib.qxb_partition_vars(self._h, n_parts, out, C.byref(n)))
+        return list(out[:n.value])
+
+    def partition_assignment(self, n_parts: int, part: int):
+        """(fixed_vars, fixed_vals) of rank ``part``, or None when ranges must be used."""
+        vs = self.partition_vars(n_parts)
+        if n_parts > 1 and not vs:
+            return None
+        dims = self.slice_dims
+        vals, r = [], part
+        for v in vs:
+            vals.append(r % dims[v])
+            r //= dims[v]
+        return vs, vals
+
     # -- compute -------------------------------------------------------------
     def configure(self, hbm_budget_bytes: int = 0, amp_batch: int = 0, profile: bool = False,
                   cuda_graph: bool = True, sum_at_root: bool = False) -> "Graph":
@@ -165,6 +190,25 @@ class Graph:
             slice_end = self.n_slices
         check(self._lib.qxb_amplitudes_device(self._h, C.c_void_p(d_bits_ptr), n_amp, slice_begin, slice_end,
                                               C.c_void_p(d_out_ptr)))
+
+    def amplitudes_subspace(self, bitstrings, fixed_vars: Sequence[int], fixed_vals: Sequence[int]) -> np.ndarray:
+        if isinstance(bitstrings, np.ndarray) and bitstrings.dtype == np.uint8:
+            bits = np.ascontiguousarray(bitstrings)
+        else:
+            bits = np.ascontiguousarray(bits_from_strings(list(bitstrings), self.n_outputs))
+        n = bits.shape[0]
+        out = np.zeros(n, dtype=self.np_dtype)
+        fv = (C.c_int32 * max(len(fixed_vars), 1))(*fixed_vars)
+        fx = (C.c_int64 * max(len(fixed_vals), 1))(*fixed_vals)
+        check(self._lib.qxb_amplitudes_subspace(self._h, bits.ctypes.data_as(C.c_void_p), n, fv, fx, len(fixed_vars),
+                                                out.ctypes.data_as(C.c_void_p), 0))
+        return out
+
+    def amplitudes_subspace_device(self, d_bits_ptr: int, n_amp: int, d_out_ptr: int, fixed_vars, fixed_vals) -> None:
+        fv = (C.c_int32 * max(len(fixed_vars), 1))(*fixed_vars)
+        fx = (C.c_int64 * max(len(fixed_vals), 1))(*fixed_vals)
+        check(self._lib.qxb_amplitudes_subspace(self._h, C.c_void_p(d_bits_ptr), n_amp, fv, fx, len(fixed_vars),
+                                                C.c_void_p(d_out_ptr), 1))
 
     def stats(self) -> dict:
         s = Stats()

@@ -62,8 +62,10 @@ def decompose(dims, b, e):
     return out
 
 
-def run_block(desc, data, bits, fixed_vals, dtype=np.complex128):
-    """Execute one aligned block; returns the per-bitstring partial sums."""
+def run_block(desc, data, bits, fixed_vals, dtype=np.complex128, shuffle_seed=None):
+    """Execute one aligned block; returns the per-bitstring partial sums.
+    shuffle_seed: run the non-const ops in a RANDOM topological order of their `deps`
+    edges (what a CUDA graph is allowed to do) instead of program order."""
     n = bits.shape[0]
     T = desc["tensors"]
     ar = desc["arena_elems"]
@@ -97,10 +99,22 @@ def run_block(desc, data, bits, fixed_vals, dtype=np.complex128):
                 else: v[0], v[1] = 1, -1
                 buf[base + u * sU: base + u * sU + (1 << span)] = v
 
-    for phase in ("const", "block", "chunk"):
-        for op in desc["ops"]:
-            if op["phase"] != phase:
-                continue
+    ops = desc["ops"]
+    order = [i for i, o in enumerate(ops) if o["phase"] == "const"]
+    rest = [i for i, o in enumerate(ops) if o["phase"] != "const"]
+    if shuffle_seed is None:
+        order += [i for i in rest if ops[i]["phase"] == "block"] + [i for i in rest if ops[i]["phase"] == "chunk"]
+    else:
+        rng = np.random.default_rng(shuffle_seed)
+        done, pending = set(order), set(rest)
+        while pending:
+            ready = sorted(i for i in pending if all(d in done or ops[d]["phase"] == "const" for d in ops[i]["deps"]))
+            assert ready, "dependency cycle"
+            pick = ready[int(rng.integers(len(ready)))]
+            order.append(pick); done.add(pick); pending.discard(pick)
+    for _phase in (0,):
+        for oi in order:
+            op = ops[oi]
             A, a0, sUA = locate(T[op["a"]])
             B, b0, sUB = locate(T[op["b"]])
             Cb, c0, sUC = locate(T[op["c"]])
@@ -122,7 +136,7 @@ def run_block(desc, data, bits, fixed_vals, dtype=np.complex128):
     return out
 
 
-def amplitudes(graph, data, bits, slice_begin=0, slice_end=None, dtype=np.complex128):
+def amplitudes(graph, data, bits, slice_begin=0, slice_end=None, dtype=np.complex128, shuffle_seed=None):
     """graph: qxb200 executor.Graph (only its host-side queries are used)."""
     dims = graph.slice_dims
     if slice_end is None:
@@ -132,5 +146,15 @@ def amplitudes(graph, data, bits, slice_begin=0, slice_end=None, dtype=np.comple
     for n_free, vals in decompose(dims, slice_begin, slice_end):
         if n_free not in cache:
             cache[n_free] = graph.describe(n_free)
-        total += run_block(cache[n_free], data, bits, vals, dtype)
+        total += run_block(cache[n_free], data, bits, vals, dtype, shuffle_seed)
     return total.astype(dtype)
+
+
+def amplitudes_subspace(graph, data, bits, fixed_vars, fixed_vals, dtype=np.complex128, shuffle_seed=None):
+    k = len(graph.slice_dims)
+    mask = (1 << k) - 1
+    vals = [0] * k
+    for v, x in zip(fixed_vars, fixed_vals):
+        mask &= ~(1 << v)
+        vals[v] = x
+    return run_block(graph.describe_mask(mask), data, bits, vals, dtype, shuffle_seed).astype(dtype)

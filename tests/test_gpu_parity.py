@@ -73,3 +73,93 @@ def test_amp_batching_and_budget(gpu):
     out = g.amplitudes(bs)
     assert g.stats()["amp_batch"] == 5
     assert rel_err(out, ref, 12) < 1e-10
+
+
+@pytest.mark.parametrize("dtype", ["c64", "c32"])
+def test_golden_vectors(gpu, dtype):
+    import json, os
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = json.load(open(os.path.join(here, "golden", "golden_rqc.json")))
+    for case in gold["cases"]:
+        txt = open(os.path.join(here, "golden", case["qx"])).read()
+        data = dict(np.load(os.path.join(here, "golden", case["npz"])))
+        g = Graph.from_dsl(txt, data, dtype).compile()
+        ref = np.array(case["re"]) + 1j * np.array(case["im"])
+        assert rel_err(g.amplitudes(case["bitstrings"]), ref, case["n_qubits"]) < TOL[dtype]
+        # every single slice of bitstring 0 (slice enumeration must match the oracle's)
+        per = np.array(case["slice_re_bs0"]) + 1j * np.array(case["slice_im_bs0"])
+        got = np.array([g.amplitudes(case["bitstrings"][:1], s, s + 1)[0] for s in range(0, len(per), 3)])
+        assert rel_err(got, per[::3], case["n_qubits"]) < TOL[dtype]
+
+
+@pytest.mark.parametrize("cuda_graph", [True, False])
+@pytest.mark.parametrize("sum_at_root", [False, True])
+def test_execution_modes_agree(gpu, cuda_graph, sum_at_root):
+    txt, data, bs = rqc_case(4, 4, 12, 4, n_amp=33)
+    ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
+    g = Graph.from_dsl(txt, data, "c64").compile(cuda_graph=cuda_graph, sum_at_root=sum_at_root)
+    for _ in range(3):                      # replayed graph must stay correct
+        assert rel_err(g.amplitudes(bs), ref, 16) < 1e-10
+    assert rel_err(g.amplitudes(bs[:7]), ref[:7], 16) < 1e-10
+
+
+def test_subspace_partition(gpu):
+    txt, data, bs = rqc_case(4, 4, 12, 4, n_amp=9)
+    ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
+    g = Graph.from_dsl(txt, data, "c64").compile()
+    for n_parts in (2, 4, 8):
+        tot = np.zeros(len(bs), dtype=np.complex128)
+        for part in range(n_parts):
+            fv, fx = g.partition_assignment(n_parts, part)
+            tot += g.amplitudes_subspace(bs, fv, fx)
+        assert rel_err(tot, ref, 16) < 1e-10
+    # a fully fixed sub-space is one slice
+    dims = g.slice_dims
+    s = 5
+    one = g.amplitudes_subspace(bs, list(range(len(dims))), g.slice_values(s))
+    assert rel_err(one, g.amplitudes(bs, s, s + 1), 16) < 1e-12
+
+
+def test_non_power_of_two_extents(gpu):
+    rng = np.random.default_rng(3)
+    A = rng.normal(size=(3, 2)) + 1j * rng.normal(size=(3, 2))
+    B = rng.normal(size=(3, 3)) + 1j * rng.normal(size=(3, 3))
+    Cc = rng.normal(size=(3, 2)) + 1j * rng.normal(size=(3, 2))
+    txt = ("# version: 0.4.0\nload a dA 3,2\nview a_s a v1 1 3\nload b dB 3,3\nview b_s b v1 1 3\n"
+           "load c dC 3,2\noutput o1 1 2\noutput o2 2 2\n"
+           "ncon ab 1,2,3 a_s 1,2 b_s 1,3\nncon abc 1,2,4 ab 1,2,3 c 3,4\nncon x 1,4 abc 1,2,4 o1 2\n"
+           "ncon y 0 x 1,4 o2 4\nsave output y\n")
+    data = {"dA": A, "dB": B, "dC": Cc}
+    g = Graph.from_dsl(txt, data, "c64").compile()
+    bs = ["00", "01", "10", "11"]
+    cmds = orc.parse_dsl(txt)
+    for (b, e) in [(0, 3), (0, 1), (1, 3), (2, 3)]:
+        ref = orc.amplitudes(cmds, data, bs, slice_begin=b, slice_end=e)
+        assert np.allclose(g.amplitudes(bs, b, e), ref, atol=1e-12)
+
+
+def test_large_k_and_qft(gpu):
+    """QFT-8 unsliced (controlled-phase hyper-edges) and a deep GHZ: exercises K chunks > 1."""
+    txt, data, _ = circuit_case(q.create_qft_circuit(8))
+    allb = list(q.amplitudes_all(8))
+    g = Graph.from_dsl(txt, data, "c64").compile()
+    out = g.amplitudes(allb)
+    assert np.allclose(np.abs(out), 2.0 ** -4, atol=1e-12)
+    assert rel_err(out[::17], orc.amplitudes(orc.parse_dsl(txt), data, allb[::17]), 8) < 1e-10
+
+
+def test_execute_file_triple(gpu, tmp_path):
+    from qxb200.execute import execute
+    prefix = str(tmp_path / "rqc")
+    circ = q.create_rqc_circuit(3, 3, 8, 42)
+    q.generate_simulation_files(circ, prefix, 3, seed=42, time=0, output_args=q.output_params_dict(9, 6, seed=5))
+    res = execute(prefix + ".qx", output_file=prefix + "_out.npz", dtype="c64")
+    txt = open(prefix + ".qx").read()
+    data = dict(np.load(prefix + ".npz"))
+    ref = orc.amplitudes(orc.parse_dsl(txt), data, list(res.keys()))
+    assert rel_err(np.array(list(res.values())), ref, 9) < 1e-10
+    res2 = execute(prefix + ".qx", max_amplitudes=2, max_slices=3, dtype="c64")
+    ref2 = orc.amplitudes(orc.parse_dsl(txt), data, list(res.keys())[:2], slice_begin=0, slice_end=3)
+    assert len(res2) == 2 and rel_err(np.array(list(res2.values())), ref2, 9) < 1e-10
+    out = np.load(prefix + "_out.npz")
+    assert list(out["bitstrings"]) == list(res.keys())

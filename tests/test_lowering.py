@@ -112,3 +112,67 @@ def test_early_sum_and_root_sum_agree(lib_built):
         assert np.allclose(em.amplitudes(g, data, bits), ref, atol=1e-14)
         work[mode] = sum(2.0 ** (op["nC"] + op["nK"]) for op in d["ops"])
     assert work[False] <= work[True]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_dependency_edges_allow_any_topological_order(lib_built, seed):
+    """The step runs as a CUDA graph: any order that respects `deps` (producer edges +
+    write-after-read edges of the arena plan) must give the same amplitudes."""
+    txt, data, bs = rqc_case(4, 4, 12, 4, n_amp=3)
+    g = Graph.from_dsl(txt, data)
+    bits = bits_from_strings(bs, 16)
+    ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
+    assert np.allclose(em.amplitudes(g, data, bits, shuffle_seed=seed), ref, atol=1e-14)
+    assert np.allclose(em.amplitudes(g, data, bits, 3, 14, shuffle_seed=seed),
+                       orc.amplitudes(orc.parse_dsl(txt), data, bs, slice_begin=3, slice_end=14), atol=1e-14)
+
+
+def test_memory_plan_has_no_unordered_overlap(lib_built):
+    """Two tensors that share arena space must be ordered by the dependency edges:
+    the later writer is a descendant of every reader of the earlier tenant."""
+    txt, data, _ = rqc_case(6, 6, 16, 8, n_amp=1)
+    g = Graph.from_dsl(txt, data)
+    d = g.describe()
+    ops, T = d["ops"], d["tensors"]
+    anc = []                                   # transitive closure of deps
+    for i, o in enumerate(ops):
+        a = set()
+        for p in o["deps"]:
+            a |= anc[p] | {p}
+        anc.append(a)
+    prod = {o["c"]: i for i, o in enumerate(ops)}
+    readers = {}
+    for i, o in enumerate(ops):
+        for t in (o["a"], o["b"]):
+            readers.setdefault(t, []).append(i)
+    size = lambda t: max(2, 1 << T[t]["span_bits"])
+    inter = [t for t in prod if ops[prod[t]]["phase"] != "const"]
+    n_shared = 0
+    for x in inter:
+        for y in inter:
+            if prod[x] >= prod[y] or T[x]["phase"] != T[y]["phase"]:
+                continue
+            if T[x]["offset"] < T[y]["offset"] + size(y) and T[y]["offset"] < T[x]["offset"] + size(x):
+                n_shared += 1
+                for r in readers.get(x, []):
+                    assert r in anc[prod[y]] or r == prod[y], (T[x]["name"], T[y]["name"])
+    assert n_shared > 0
+
+
+def test_subspace_partition_sums_to_full(lib_built):
+    txt, data, bs = rqc_case(4, 4, 12, 4, n_amp=3)
+    g = Graph.from_dsl(txt, data)
+    bits = bits_from_strings(bs, 16)
+    ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
+    for n_parts in (2, 4, 8):
+        total = np.zeros(len(bs), dtype=np.complex128)
+        seen = set()
+        for part in range(n_parts):
+            fv, fx = g.partition_assignment(n_parts, part)
+            assert len(fv) == int(np.log2(n_parts)) and len(set(fv)) == len(fv)
+            seen.add(tuple(fx))
+            total += em.amplitudes_subspace(g, data, bits, fv, fx, shuffle_seed=part)
+        assert len(seen) == n_parts
+        assert np.allclose(total, ref, atol=1e-14)
+    assert g.partition_vars(1) == []
+    assert g.partition_vars(3) == []          # extents are all 2: 3 ranks cannot be factored
