@@ -163,3 +163,24 @@ def test_execute_file_triple(gpu, tmp_path):
     assert len(res2) == 2 and rel_err(np.array(list(res2.values())), ref2, 9) < 1e-10
     out = np.load(prefix + "_out.npz")
     assert list(out["bitstrings"]) == list(res.keys())
+
+
+@pytest.mark.parametrize("dtype", ["c64", "c32"])
+def test_reduction_shaped_nodes(gpu, dtype):
+    """Few outputs, long K (K = 64 and K = 128 with a bitstring axis): the warp-reduce kernel."""
+    rng = np.random.default_rng(5)
+    A = rng.normal(size=(2,) * 6) + 1j * rng.normal(size=(2,) * 6)
+    B = rng.normal(size=(2,) * 7) + 1j * rng.normal(size=(2,) * 7)
+    Cc = rng.normal(size=(2,) * 8) + 1j * rng.normal(size=(2,) * 8)
+    txt = ("# version: 0.4.0\nload a dA 2,2,2,2,2,2\nload b dB 2,2,2,2,2,2,2\nload c dC 2,2,2,2,2,2,2,2\n"
+           "output o1 1 2\noutput o2 2 2\n"
+           "ncon t 7 a 1,2,3,4,5,6 b 1,2,3,4,5,6,7\n"            # const phase, K = 64
+           "ncon w 1,2,3,4,5,6,7 c 1,2,3,4,5,6,7,8 o1 8\n"       # chunk phase
+           "ncon x 7 w 1,2,3,4,5,6,7 a 1,2,3,4,5,6\n"            # chunk phase, K = 64, 2 outputs per bitstring
+           "ncon y 7 x 7 t 7\nncon z 0 y 7 o2 7\nsave output z\n")
+    data = {"dA": A, "dB": B, "dC": Cc}
+    bs = ["00", "01", "10", "11"]
+    ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
+    g = Graph.from_dsl(txt, data, dtype).compile()
+    got = g.amplitudes(bs)
+    assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 2e-5)
