@@ -373,7 +373,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="qxb200", choices=["qxb200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--amps", type=int, default=1024, help="bitstrings per step")
+    ap.add_argument("--amps", type=int, default=4096, help="bitstrings per step")
     ap.add_argument("--amp-batch", type=int, default=0)
     ap.add_argument("--ref-slices", type=int, default=64, help="slices per bitstring in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")

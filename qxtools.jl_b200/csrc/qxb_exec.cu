@@ -214,10 +214,18 @@ void build_templates(Variant& v, int dtype) {
             if (mapA[b] >= 0 && mapB[b] < 0 && mbits.size() < 2) mbits.push_back(b);
             else if (mapB[b] >= 0 && mapA[b] < 0 && nbits.size() < 2) nbits.push_back(b);
         }
-        // K chunk: keep (2^ma + 2^nb) * 2^kc operand loads (<= 64 registers) in flight
+        // K chunk: keep (2^ma + 2^nb) * 2^kc operand loads (<= 64 registers) in flight.  When K
+        // needs several chunks the accumulators stay live too, so shrink the tile to <= 8 outputs
+        // (c64) / 16 (c32) to stay under 128 registers (2 blocks per SM).
         const int budget_loads = dtype == QXB_C32 ? 32 : 16;
         int kc = std::min(op.nK, 3);
         while (kc > 0 && (int)(((1u << mbits.size()) + (1u << nbits.size())) << kc) > budget_loads) --kc;
+        if (kc < op.nK) {
+            const size_t max_tile_bits = dtype == QXB_C32 ? 4 : 3;
+            while (mbits.size() + nbits.size() > max_tile_bits) {
+                if (nbits.size() >= mbits.size()) nbits.pop_back(); else mbits.pop_back();
+            }
+        }
         p.kc = kc;
         p.ma = (int)mbits.size(); p.nb = (int)nbits.size();
         std::vector<bool> is_tile(nC, false);
@@ -328,7 +336,7 @@ Node contract_node(const RunCtx& c, int i) {
         const long long warps = (long long)outputs;
         n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>((warps * 32 + kThreads - 1) / kThreads, cap)));
     } else {
-        n.func = contract_func(g->dtype, p.kc, p.ma, p.nb);
+        n.func = contract_func(g->dtype, p.kc, p.ma, p.nb, p.kc == p.nK);
         n.grid = dim3((unsigned)std::max<long long>(1, std::min(blocks, cap)));
     }
     n.block = dim3(kThreads);

@@ -34,8 +34,8 @@ __device__ __forceinline__ long long segeval(const DSeg* s, int n, unsigned long
 // by the tile index through segment maps.  K is walked in chunks of 2^KC: all
 // (2^ma + 2^nb) * 2^KC loads of a chunk are issued before its FMAs (the kernel
 // lives on memory-level parallelism), accumulators stay in registers.
-template <typename R2, int KC, int MA, int NB>
-__global__ void __launch_bounds__(kThreads)
+template <typename R2, int KC, int MA, int NB, bool ONE>
+__global__ void __launch_bounds__(kThreads, 2)
 contract_kernel(const __grid_constant__ OpParams p) {
     const R2* __restrict__ A = reinterpret_cast<const R2*>(p.A);
     const R2* __restrict__ B = reinterpret_cast<const R2*>(p.B);
@@ -48,16 +48,8 @@ contract_kernel(const __grid_constant__ OpParams p) {
     const unsigned lo = tid & ((1u << lob) - 1u);
     const long long aLo = segeval(p.sAlo, p.nsAlo, lo);
     const long long bLo = segeval(p.sBlo, p.nsBlo, lo);
-    long long aT[TM], bT[TN], kA[KK], kB[KK];
-#pragma unroll
-    for (int j = 0; j < TM; ++j) aT[j] = p.aT[j];
-#pragma unroll
-    for (int j = 0; j < TN; ++j) bT[j] = p.bT[j];
-#pragma unroll
-    for (int k = 0; k < KK; ++k) { kA[k] = p.ktabA[k]; kB[k] = p.ktabB[k]; }
     const int hb = p.hb;
     const long long hmask = (1ll << hb) - 1ll;
-    const int nchunks = 1 << (p.nK - KC);
     for (long long t0 = ((long long)blockIdx.x << sub_bits); t0 < p.tiles;
          t0 += ((long long)gridDim.x << sub_bits)) {
         const long long tile = t0 + sub;
@@ -67,70 +59,95 @@ contract_kernel(const __grid_constant__ OpParams p) {
         const R2* Ap = A + u * p.sUA + segeval(p.sAhi, p.nsAhi, hh) + aLo;
         const R2* Bp = B + u * p.sUB + segeval(p.sBhi, p.nsBhi, hh) + bLo;
         R2* Cp = C + u * p.sUC + segeval(p.sChi, p.nsChi, hh) + lo;
-        R2 acc[TM][TN];
-#pragma unroll
-        for (int jm = 0; jm < TM; ++jm)
-#pragma unroll
-            for (int jn = 0; jn < TN; ++jn) { acc[jm][jn].x = 0; acc[jm][jn].y = 0; }
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const R2* Ac = Ap;
-            const R2* Bc = Bp;
-            if (nchunks > 1) {
-                const unsigned long long kb = (unsigned long long)ch << KC;
-                Ac += segeval(p.kA, p.nkA, kb);
-                Bc += segeval(p.kB, p.nkB, kb);
-            }
+        if (ONE) {
+            // K fits one register chunk: load everything, then each output is a short
+            // dot product that is stored at once (no accumulator array kept live)
             R2 av[TM][KK], bv[TN][KK];
 #pragma unroll
             for (int j = 0; j < TM; ++j)
 #pragma unroll
-                for (int k = 0; k < KK; ++k) av[j][k] = __ldg(Ac + aT[j] + kA[k]);
+                for (int k = 0; k < KK; ++k) av[j][k] = __ldg(Ap + p.aT[j] + p.ktabA[k]);
 #pragma unroll
             for (int j = 0; j < TN; ++j)
 #pragma unroll
-                for (int k = 0; k < KK; ++k) bv[j][k] = __ldg(Bc + bT[j] + kB[k]);
+                for (int k = 0; k < KK; ++k) bv[j][k] = __ldg(Bp + p.bT[j] + p.ktabB[k]);
+#pragma unroll
+            for (int jm = 0; jm < TM; ++jm) {
+#pragma unroll
+                for (int jn = 0; jn < TN; ++jn) {
+                    R2 acc; acc.x = 0; acc.y = 0;
+#pragma unroll
+                    for (int k = 0; k < KK; ++k) cmac(acc, av[jm][k], bv[jn][k]);
+                    Cp[p.cT[jm * TN + jn]] = acc;
+                }
+            }
+        } else {
+            const int nchunks = 1 << (p.nK - KC);
+            R2 acc[TM][TN];
 #pragma unroll
             for (int jm = 0; jm < TM; ++jm)
 #pragma unroll
-                for (int jn = 0; jn < TN; ++jn)
+                for (int jn = 0; jn < TN; ++jn) { acc[jm][jn].x = 0; acc[jm][jn].y = 0; }
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const unsigned long long kb = (unsigned long long)ch << KC;
+                const R2* Ac = Ap + segeval(p.kA, p.nkA, kb);
+                const R2* Bc = Bp + segeval(p.kB, p.nkB, kb);
+                R2 av[TM][KK], bv[TN][KK];
 #pragma unroll
-                    for (int k = 0; k < KK; ++k) cmac(acc[jm][jn], av[jm][k], bv[jn][k]);
+                for (int j = 0; j < TM; ++j)
+#pragma unroll
+                    for (int k = 0; k < KK; ++k) av[j][k] = __ldg(Ac + p.aT[j] + p.ktabA[k]);
+#pragma unroll
+                for (int j = 0; j < TN; ++j)
+#pragma unroll
+                    for (int k = 0; k < KK; ++k) bv[j][k] = __ldg(Bc + p.bT[j] + p.ktabB[k]);
+#pragma unroll
+                for (int jm = 0; jm < TM; ++jm)
+#pragma unroll
+                    for (int jn = 0; jn < TN; ++jn)
+#pragma unroll
+                        for (int k = 0; k < KK; ++k) cmac(acc[jm][jn], av[jm][k], bv[jn][k]);
+            }
+#pragma unroll
+            for (int jm = 0; jm < TM; ++jm)
+#pragma unroll
+                for (int jn = 0; jn < TN; ++jn) Cp[p.cT[jm * TN + jn]] = acc[jm][jn];
         }
-#pragma unroll
-        for (int jm = 0; jm < TM; ++jm)
-#pragma unroll
-            for (int jn = 0; jn < TN; ++jn) Cp[p.cT[jm * TN + jn]] = acc[jm][jn];
     }
 }
 
+template <typename R2, int KC, int MA, int NB>
+static const void* pick_one(bool one) {
+    return one ? (const void*)&contract_kernel<R2, KC, MA, NB, true> : (const void*)&contract_kernel<R2, KC, MA, NB, false>;
+}
 template <typename R2, int KC, int MA>
-static const void* pick_nb(int nb) {
+static const void* pick_nb(int nb, bool one) {
     switch (nb) {
-    case 0: return (const void*)&contract_kernel<R2, KC, MA, 0>;
-    case 1: return (const void*)&contract_kernel<R2, KC, MA, 1>;
-    default: return (const void*)&contract_kernel<R2, KC, MA, 2>;
+    case 0: return pick_one<R2, KC, MA, 0>(one);
+    case 1: return pick_one<R2, KC, MA, 1>(one);
+    default: return pick_one<R2, KC, MA, 2>(one);
     }
 }
 template <typename R2, int KC>
-static const void* pick_ma(int ma, int nb) {
+static const void* pick_ma(int ma, int nb, bool one) {
     switch (ma) {
-    case 0: return pick_nb<R2, KC, 0>(nb);
-    case 1: return pick_nb<R2, KC, 1>(nb);
-    default: return pick_nb<R2, KC, 2>(nb);
+    case 0: return pick_nb<R2, KC, 0>(nb, one);
+    case 1: return pick_nb<R2, KC, 1>(nb, one);
+    default: return pick_nb<R2, KC, 2>(nb, one);
     }
 }
 template <typename R2>
-static const void* pick_kc(int kc, int ma, int nb) {
+static const void* pick_kc(int kc, int ma, int nb, bool one) {
     switch (kc) {
-    case 0: return pick_ma<R2, 0>(ma, nb);
-    case 1: return pick_ma<R2, 1>(ma, nb);
-    case 2: return pick_ma<R2, 2>(ma, nb);
-    default: return pick_ma<R2, 3>(ma, nb);
+    case 0: return pick_ma<R2, 0>(ma, nb, one);
+    case 1: return pick_ma<R2, 1>(ma, nb, one);
+    case 2: return pick_ma<R2, 2>(ma, nb, one);
+    default: return pick_ma<R2, 3>(ma, nb, one);
     }
 }
 
-const void* contract_func(int dtype, int kc, int ma, int nb) {
-    return dtype == 0 ? pick_kc<float2>(kc, ma, nb) : pick_kc<double2>(kc, ma, nb);
+const void* contract_func(int dtype, int kc, int ma, int nb, bool single_chunk) {
+    return dtype == 0 ? pick_kc<float2>(kc, ma, nb, single_chunk) : pick_kc<double2>(kc, ma, nb, single_chunk);
 }
 
 // Reduction-shaped nodes (few C elements, long K -- e.g. the root after the batched

@@ -46,7 +46,7 @@ struct OutLeafDesc { long long offset_per_amp; int span_bits; int out_idx; };
 
 // Kernel entry points as function pointers (for cudaLaunchKernel / cudaGraphAddKernelNode).
 // contract: one argument (OpParams by value).
-const void* contract_func(int dtype, int kc, int ma, int nb);
+const void* contract_func(int dtype, int kc, int ma, int nb, bool single_chunk);
 // warp-per-output reduction variant for nC <= 8 and long K (same OpParams argument)
 const void* kreduce_func(int dtype);
 // outleaf:  (R2* base, const OutLeafDesc* d, const unsigned char* bits, int n_outputs, long long amp0, long long n)
