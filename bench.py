@@ -258,17 +258,33 @@ def run_gpu(args):
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
+    ws_bytes = g.stats()["workspace_bytes"]
+    flush = ws_bytes < 4 * 126e6            # working set could sit in the 126 MB L2 -> flush between steps
+    flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev) if flush else None
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    ev1.record(stream)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    if not flush:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        l2_note = f"working set {ws_bytes / 1e9:.2f} GB per GPU >> 126 MB L2 (no flush needed)"
+    else:
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in evs:
+            flush_buf.fill_(1)              # evicts L2; not inside the timed event pair
+            a.record(stream)
+            step_device()
+            b.record(stream)
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        l2_note = (f"working set {ws_bytes / 1e6:.0f} MB could fit the 126 MB L2: a 512 MB buffer is written between "
+                   "steps (outside the per-step CUDA-event pairs) to flush it")
     st = g.stats()
     # e2e
     for _ in range(2):
@@ -308,7 +324,7 @@ def run_gpu(args):
                        "n_qubits": n_q, "complex": w["dtype"],
                        "slice_partition": (f"fixed slice variables {[v + 1 for v in assign[0]]} over {world} ranks"
                                            if assign is not None else f"contiguous ranges / {world}"),
-                       "l2": f"working set {st['workspace_bytes'] / 1e9:.2f} GB per GPU >> 126 MB L2 (no flush needed)",
+                       "l2": l2_note,
                        "amp_batch": st["amp_batch"], "mean_p_times_2^n": norm},
             "e2e": {"value": e2e, "unit": "amplitudes/s", "h2d_bytes_per_step": int(n_amp * n_q),
                     "d2h_bytes_per_step": int(n_amp * es)},
