@@ -38,6 +38,8 @@ WORKLOADS = {
     # BASELINE.json configs[2]: RQC 6x6 depth 16, ComplexF32, 2^6 slices
     "rqc_6x6_d16_c32_s64": dict(rows=6, cols=6, depth=16, n_slice=6, dtype="c32", seed=42),
     "rqc_4x4_d12_c64_s16": dict(rows=4, cols=4, depth=12, n_slice=4, dtype="c64", seed=42),
+    # BASELINE.json configs[1]: QFT on 20 qubits, 1024 bitstrings, no slicing
+    "qft_20_unsliced": dict(qft=20, rows=20, cols=1, n_slice=0, dtype="c64", seed=42),
 }
 DEFAULT_WORKLOAD = "rqc_7x7_d20_c64_s4096"
 
@@ -51,7 +53,8 @@ def build_workload(name):
         txt = open(cache + ".qx").read()
         data = dict(np.load(cache + ".npz"))
     else:
-        circ = q.create_rqc_circuit(w["rows"], w["cols"], w["depth"], w["seed"])
+        circ = (q.create_qft_circuit(w["qft"]) if "qft" in w else
+                q.create_rqc_circuit(w["rows"], w["cols"], w["depth"], w["seed"]))
         tnc = q.convert_to_tnc(circ)
         bg, plan, meta = q.contraction_scheme(tnc, w["n_slice"], time=0, seed=w["seed"])
         cg = q.build_compute_graph(tnc, plan, bg)
@@ -368,10 +371,14 @@ def roofline(args, g, txt, data, w, bits_d, out_d, n_amp, s0, s1, assign=None):
     else:
         peak, src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    # DRAM bytes per launch of the dominant kernels from the committed ncu --set full capture
+    # (taken at 1024 bitstrings per step; the traffic of these launches is linear in the batch)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.workload)
+        t = json.load(open(tpath)).get(args.workload)
+        if t:
+            traffic = t["bytes_per_launch_mean_top5_at_1024_amps"] * n_amp / 1024.0
     all_ms = sum(o["ms"] for o in ops)
     return {"bound": "hbm", "kernel": "contract_kernel (dominant contractions: top ops by FLOPs covering >=80%)",
             "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s",

@@ -1,0 +1,80 @@
+"""Parity at BASELINE.json's full sizes.  The oracle needs ~35 ms per (bitstring, slice)
+contraction, so single slices of the full-size programs are checked against it
+directly; whole amplitudes (4096 slices x many bitstrings) are checked through
+size-independent properties: partitions of the slice space sum to the whole,
+ComplexF32 agrees with ComplexF64, QFT moduli are exactly 2^{-n/2}."""
+import numpy as np
+import pytest
+
+import qxb200 as q
+from qxb200.executor import Graph
+from oracle import qx_oracle as orc
+from cases import rel_err
+import bench
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rqc77(gpu):
+    txt, data, w = bench.build_workload("rqc_7x7_d20_c64_s4096")
+    return txt, data, Graph.from_dsl(txt, data, "c64").compile()
+
+
+def test_rqc_7x7_single_slices_vs_oracle(rqc77):
+    txt, data, g = rqc77
+    cmds = orc.parse_dsl(txt)
+    bits = bench.synth_bits(3, 49)
+    bss = ["".join("01"[b] for b in row) for row in bits]
+    assert g.n_slices == 4096 and g.n_outputs == 49
+    for s in (0, 1, 2049, 4095):
+        ref = orc.amplitudes(cmds, data, bss, slice_begin=s, slice_end=s + 1)
+        assert rel_err(g.amplitudes(bss, s, s + 1), ref, 49) < 1e-10
+    # a short unaligned range (several aligned blocks)
+    ref = orc.amplitudes(cmds, data, bss[:1], slice_begin=1021, slice_end=1030)
+    assert rel_err(g.amplitudes(bss[:1], 1021, 1030), ref, 49) < 1e-10
+
+
+def test_rqc_7x7_partitions_sum_to_whole(rqc77):
+    txt, data, g = rqc77
+    bits = bench.synth_bits(256, 49)
+    full = g.amplitudes(bits)
+    # contiguous halves / quarters of the linear slice id
+    parts = sum(g.amplitudes(bits, b, b + 1024) for b in range(0, 4096, 1024))
+    assert rel_err(parts, full, 49) < 1e-10
+    # the multi-GPU partition: fixed slice variables chosen by the cost model
+    tot = np.zeros_like(full)
+    for r in range(8):
+        fv, fx = g.partition_assignment(8, r)
+        tot += g.amplitudes_subspace(bits, fv, fx)
+    assert rel_err(tot, full, 49) < 1e-10
+    # Porter-Thomas: mean probability of random bitstrings of a deep RQC is ~2^-n
+    assert 0.7 < np.mean(np.abs(full) ** 2) * 2.0 ** 49 < 1.4
+
+
+def test_rqc_7x7_c32_matches_c64(rqc77):
+    txt, data, g = rqc77
+    bits = bench.synth_bits(64, 49)
+    g32 = Graph.from_dsl(txt, data, "c32").compile()
+    assert rel_err(g32.amplitudes(bits), g.amplitudes(bits), 49) < 1e-5
+
+
+def test_rqc_7x7_batching_is_invisible(rqc77):
+    """Same amplitudes whether 300 bitstrings go down in one batch or in chunks of 37."""
+    txt, data, g = rqc77
+    bits = bench.synth_bits(300, 49)
+    gb = Graph.from_dsl(txt, data, "c64").compile(amp_batch=37)
+    assert rel_err(gb.amplitudes(bits), g.amplitudes(bits), 49) < 1e-12
+
+
+@pytest.mark.parametrize("dtype,tol", [("c64", 1e-10), ("c32", 1e-5)])
+def test_qft20_moduli(gpu, dtype, tol):
+    """BASELINE.json configs[1]: QFT-20, 1024 bitstrings, no slicing: every amplitude has modulus 2^-10."""
+    txt, data, w = bench.build_workload("qft_20_unsliced")
+    g = Graph.from_dsl(txt, data, dtype).compile()
+    bits = bench.synth_bits(1024, 20)
+    out = g.amplitudes(bits)
+    assert np.max(np.abs(np.abs(out) - 2.0 ** -10)) / 2.0 ** -10 < tol
+    cmds = orc.parse_dsl(txt)
+    bss = ["".join("01"[b] for b in row) for row in bits[:3]]
+    assert rel_err(out[:3], orc.amplitudes(cmds, data, bss), 20) < tol
