@@ -212,14 +212,45 @@ def run_gpu(args):
 
     txt, data, w = build_workload(args.workload)
     n_q = w["rows"] * w["cols"]
-    g = Graph.from_dsl(txt, data, w["dtype"]).compile(amp_batch=args.amp_batch, cuda_graph=not args.no_graph)
+    replan_s = 0.0 if args.no_replan else args.replan_seconds
+    # the search is wall-clock bounded, so only rank 0 re-plans and every rank runs ITS program
+    # (the slice-variable partition must be derived from one and the same contraction tree)
+    info = None
+    plan_txt = txt
+    if replan_s > 0 and rank == 0:
+        from qxb200.replan import replan_dsl
+        plan_txt, info = replan_dsl(txt, n_amp=args.amps, time=replan_s, dtype=w["dtype"])
+    if world > 1:
+        box = [plan_txt, info]
+        dist.broadcast_object_list(box, src=0)
+        plan_txt, info = box
+    g = Graph.from_dsl(plan_txt, data, w["dtype"])
+    g.replan_info = info
+    g.compile(amp_batch=args.amp_batch, cuda_graph=not args.no_graph)
     S = g.n_slices
-    # slice-space partition: the ranks fix different values of the slice variables
-    # the cost model picks (qxb_partition_vars); identical bitstrings on every rank.  Fallback:
-    # contiguous ranges of the linear slice id.
-    s0, s1 = (S * rank) // world, (S * (rank + 1)) // world
-    assign = g.partition_assignment(world, rank) if world > 1 else None
     n_amp = args.amps
+    # How the ranks share a step: either each rank takes a share of the bitstrings
+    # over all slices, or all ranks take all bitstrings and fix different values of the slice
+    # variables the cost model picks (qxb_partition_vars) -- whichever leaves less work per rank;
+    # either way the partial results meet in ONE NCCL all-reduce of [n_amp] complex numbers.
+    s0, s1 = 0, S
+    assign, a0, a1 = None, 0, n_amp
+    if world > 1:
+        mode, how = g.choose_partition(n_amp, world, rank)
+        if args.partition == "slices":
+            assign = g.partition_assignment(world, rank)
+            mode = "slices" if assign is not None else "ranges"
+            how = assign if assign is not None else ((S * rank) // world, (S * (rank + 1)) // world)
+        elif args.partition == "amps":
+            mode, how = "amps", ((n_amp * rank) // world, (n_amp * (rank + 1)) // world)
+        if mode == "amps":
+            a0, a1 = how
+        elif mode == "slices":
+            assign = how
+        else:
+            s0, s1 = how
+    else:
+        mode = "single"
     bits_h = torch.from_numpy(synth_bits(n_amp, n_q)).pin_memory()
     bits_d = bits_h.to(dev)
     cdt = torch.complex64 if w["dtype"] == "c32" else torch.complex128
@@ -228,8 +259,15 @@ def run_gpu(args):
     out_h_np = out_h.numpy()
     bits_h_np = bits_h.numpy()
 
+    es = 8 if w["dtype"] == "c32" else 16
+    n_mine = a1 - a0
+
     def step_device():
-        if assign is not None:
+        if mode == "amps":
+            out_d.zero_()
+            if n_mine:
+                g.amplitudes_device(bits_d.data_ptr() + a0 * n_q, n_mine, out_d.data_ptr() + a0 * es, 0, S)
+        elif assign is not None:
             g.amplitudes_subspace_device(bits_d.data_ptr(), n_amp, out_d.data_ptr(), assign[0], assign[1])
         else:
             g.amplitudes_device(bits_d.data_ptr(), n_amp, out_d.data_ptr(), s0, s1)
@@ -240,7 +278,12 @@ def run_gpu(args):
         # the public host-buffer call: pinned bitstrings -> H2D -> contraction -> D2H, synchronised
         from qxb200._lib import check
         import ctypes as C
-        if assign is not None:
+        if mode == "amps":
+            out_h.zero_()
+            if n_mine:
+                check(g._lib.qxb_amplitudes(g._h, C.c_void_p(bits_h.data_ptr() + a0 * n_q), n_mine, 0, S,
+                                            C.c_void_p(out_h.data_ptr() + a0 * es)))
+        elif assign is not None:
             fv = (C.c_int32 * max(len(assign[0]), 1))(*assign[0])
             fx = (C.c_int64 * max(len(assign[1]), 1))(*assign[1])
             check(g._lib.qxb_amplitudes_subspace(g._h, C.c_void_p(bits_h.data_ptr()), n_amp, fv, fx, len(assign[0]),
@@ -311,7 +354,26 @@ def run_gpu(args):
         e2e = n_amp / (ms_e2e / args.steps * 1e-3)
         # sanity: Porter-Thomas / norm check -- mean |amp|^2 * 2^n should be ~1 for an RQC
         norm = float(np.mean(np.abs(result) ** 2) * 2.0 ** n_q)
-        roof = roofline(args, g, txt, data, w, bits_d, out_d, n_amp, s0, s1, assign)
+        roof = roofline(args, plan_txt, data, w, bits_d, out_d, n_amp if mode != "amps" else n_mine, s0, s1, assign,
+                        bits_off=a0 * n_q if mode == "amps" else 0)
+        as_given = None
+        if world == 1 and g.replan_info and g.replan_info.get("replanned") and not args.no_as_given:
+            # the same step on the contraction order exactly as the file gives it (no re-planning)
+            g0 = Graph.from_dsl(txt, data, w["dtype"]).compile(amp_batch=args.amp_batch)
+            for _ in range(3):
+                g0.amplitudes_device(bits_d.data_ptr(), n_amp, out_d.data_ptr(), 0, S)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(5):
+                g0.amplitudes_device(bits_d.data_ptr(), n_amp, out_d.data_ptr(), 0, S)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            t_ms = e0.elapsed_time(e1) / 5
+            given = out_d.cpu().numpy()
+            as_given = {"value": n_amp / (t_ms * 1e-3), "ms_per_step": t_ms, "gb_per_step": g0.stats()["bytes"] / 1e9,
+                        "max_rel_diff_vs_replanned": float(np.max(np.abs(given - result)) / np.max(np.abs(given)))}
+            del g0
         cpu = None
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
@@ -325,8 +387,15 @@ def run_gpu(args):
             "dtype": "f64" if w["dtype"] == "c64" else "f32", "data": "synthetic",
             "config": {"workload": args.workload, "n_amp_per_step": n_amp, "n_slices": S,
                        "n_qubits": n_q, "complex": w["dtype"],
-                       "slice_partition": (f"fixed slice variables {[v + 1 for v in assign[0]]} over {world} ranks"
-                                           if assign is not None else f"contiguous ranges / {world}"),
+                       "partition": ("single GPU" if world == 1 else
+                                     f"bitstrings split over {world} ranks, all slices each" if mode == "amps" else
+                                     f"all bitstrings on every rank, slice variables {[v + 1 for v in assign[0]]} fixed per rank"
+                                     if assign is not None else f"contiguous slice ranges / {world}"),
+                       "plan": ("re-planned for batched execution (host-side exact re-association, replan.py): "
+                                f"{g.replan_info['given_bytes'] / 1e9:.2f} -> {g.replan_info['bytes'] / 1e9:.2f} GB per "
+                                f"{g.replan_info['n_amp_model']} bitstrings") if g.replan_info and g.replan_info.get("replanned")
+                               else "contraction order as given by the file",
+                       "as_given_plan": as_given,
                        "l2": l2_note,
                        "amp_batch": st["amp_batch"], "mean_p_times_2^n": norm},
             "e2e": {"value": e2e, "unit": "amplitudes/s", "h2d_bytes_per_step": int(n_amp * n_q),
@@ -341,7 +410,7 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def roofline(args, g, txt, data, w, bits_d, out_d, n_amp, s0, s1, assign=None):
+def roofline(args, txt, data, w, bits_d, out_d, n_amp, s0, s1, assign=None, bits_off=0):
     """Per-op CUDA-event timing of one more step (same stream, same inputs) on a
     profiled clone of the graph; the reported kernel is the contraction kernel over
     the DOMINANT contractions = top ops by FLOPs covering >= 80% of the step's FLOPs
@@ -352,7 +421,7 @@ def roofline(args, g, txt, data, w, bits_d, out_d, n_amp, s0, s1, assign=None):
         if assign is not None:
             gp.amplitudes_subspace_device(bits_d.data_ptr(), n_amp, out_d.data_ptr(), assign[0], assign[1])
         else:
-            gp.amplitudes_device(bits_d.data_ptr(), n_amp, out_d.data_ptr(), s0, s1)
+            gp.amplitudes_device(bits_d.data_ptr() + bits_off, n_amp, out_d.data_ptr(), s0, s1)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     prof = gp.profile_dump(os.path.join(ROOT, "gpurun_out", f"op_profile_{args.workload}.json"))
     ops = [o for v in prof["variants"] for o in v["ops"]]
@@ -400,6 +469,10 @@ def main():
     ap.add_argument("--amp-batch", type=int, default=0)
     ap.add_argument("--ref-slices", type=int, default=64, help="slices per bitstring in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-replan", action="store_true", help="run the contraction order exactly as the file gives it")
+    ap.add_argument("--replan-seconds", type=float, default=4.0)
+    ap.add_argument("--no-as-given", action="store_true", help="skip the extra as-given-plan measurement")
+    ap.add_argument("--partition", default="auto", choices=["auto", "amps", "slices"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly (no CUDA-graph replay)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -122,6 +122,10 @@ int  qxb_amplitudes_subspace(qxb_graph* g, const uint8_t* bits, int64_t n_amp, c
  * depend on saves nothing).  n_vars_out = 0 when the extents cannot factor n_parts (shard by
  * contiguous slice ranges instead).  Pure host logic. */
 int  qxb_partition_vars(qxb_graph* g, int n_parts, int32_t* vars_out /*may be NULL*/, int* n_vars_out);
+/* Cost model of one step: algorithmic bytes moved by the non-constant nodes when the variables in
+ * free_mask are batched (the others fixed) and n_amp bitstrings are contracted.  Host logic only;
+ * used to choose between sharding bitstrings and sharding slice variables over the ranks. */
+int  qxb_graph_cost_bytes(qxb_graph* g, uint64_t free_mask, int64_t n_amp, double* bytes_out);
 /* qxb_graph_describe for an arbitrary set of batched variables (bit v of free_mask = v(v+1)). */
 int64_t qxb_graph_describe_mask(qxb_graph* g, uint64_t free_mask, char* buf, int64_t buflen);
 

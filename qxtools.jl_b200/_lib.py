@@ -21,7 +21,7 @@ SYMBOLS = [
     "qxb_graph_ncon", "qxb_graph_save", "qxb_graph_parse_dsl", "qxb_graph_set_data",
     "qxb_graph_num_outputs", "qxb_graph_num_slice_vars", "qxb_graph_num_slices", "qxb_slice_values",
     "qxb_graph_describe", "qxb_graph_configure", "qxb_graph_compile", "qxb_amplitudes", "qxb_amplitudes_device",
-    "qxb_amplitudes_subspace", "qxb_partition_vars", "qxb_graph_describe_mask",
+    "qxb_amplitudes_subspace", "qxb_partition_vars", "qxb_graph_describe_mask", "qxb_graph_cost_bytes",
     "qxb_last_stats", "qxb_profile_dump",
 ]
 
@@ -85,6 +85,7 @@ def load():
         "qxb_amplitudes_subspace": (i32, [p, p, i64, C.POINTER(C.c_int32), pi64, i32, p, i32]),
         "qxb_partition_vars": (i32, [p, i32, C.POINTER(C.c_int32), C.POINTER(i32)]),
         "qxb_graph_describe_mask": (i64, [p, C.c_uint64, cp, i64]),
+        "qxb_graph_cost_bytes": (i32, [p, C.c_uint64, i64, C.POINTER(C.c_double)]),
         "qxb_last_stats": (i32, [p, C.POINTER(Stats)]),
         "qxb_profile_dump": (i32, [p, cp]),
     }

@@ -972,6 +972,15 @@ int qxb_partition_vars(qxb_graph* g, int n_parts, int32_t* vars_out, int* n_vars
     });
 }
 
+int qxb_graph_cost_bytes(qxb_graph* g, uint64_t free_mask, int64_t n_amp, double* bytes_out) {
+    return guard([&] {
+        if (!g || !bytes_out) throw Error(QXB_ERR_ARG, "null argument");
+        ensure_analysed(g);
+        Lowered L = lower(g->prog, free_mask, !g->opts.sum_at_root);
+        *bytes_out = lowered_cost_bytes(L, (double)std::max<int64_t>(n_amp, 1), (double)g->es());
+    });
+}
+
 int64_t qxb_graph_describe_mask(qxb_graph* g, uint64_t free_mask, char* buf, int64_t buflen) {
     int64_t need = 0;
     int rc = guard([&] {

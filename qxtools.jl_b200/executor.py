@@ -54,8 +54,16 @@ class Graph:
 
     # -- construction ------------------------------------------------------
     @classmethod
-    def from_dsl(cls, text: str, data: Dict[str, np.ndarray], dtype: str = "c64") -> "Graph":
+    def from_dsl(cls, text: str, data: Dict[str, np.ndarray], dtype: str = "c64", replan: float = 0.0,
+                 replan_n_amp: int = 1024) -> "Graph":
+        """``replan`` > 0: re-derive the contraction order for batched execution first
+        (host-side DSL -> DSL rewrite, exact; ``replan`` = seconds of search, see replan.py)."""
         g = cls(dtype)
+        g.replan_info = None
+        if replan and replan > 0:
+            from .replan import replan_dsl
+            text, g.replan_info = replan_dsl(text, n_amp=replan_n_amp, time=float(replan), dtype=dtype)
+        g.text = text
         b = text.encode()
         check(g._lib.qxb_graph_parse_dsl(g._h, b, len(b)))
         g.set_data(data)
@@ -133,6 +141,35 @@ class Graph:
         buf = C.create_string_buffer(need)
         check(self._lib.qxb_graph_describe_mask(self._h, free_mask, buf, need))
         return json.loads(buf.value.decode())
+
+    def cost_bytes(self, n_amp: int, fixed_vars: Sequence[int] = ()) -> float:
+        """Algorithmic bytes of one step (cost model; host logic only)."""
+        mask = (1 << len(self.slice_dims)) - 1
+        for v in fixed_vars:
+            mask &= ~(1 << v)
+        out = C.c_double()
+        check(self._lib.qxb_graph_cost_bytes(self._h, mask, n_amp, C.byref(out)))
+        return out.value
+
+    def choose_partition(self, n_amp: int, n_parts: int, part: int):
+        """How rank ``part`` of ``n_parts`` shares a step: by bitstrings (the reference's top
+        level of parallelism, docs/src/users_guide.md:12-13) or by fixing slice variables
+        (its lower level, :14-20) -- whichever leaves less work per rank under the cost model.
+        -> ("amps", (begin, end)) | ("slices", (fixed_vars, fixed_vals)) | ("ranges", (s0, s1))"""
+        from .dist import partition_range
+        if n_parts <= 1:
+            return "amps", (0, n_amp)
+        a0, a1 = partition_range(n_amp, n_parts, part)
+        per_rank_amps = self.cost_bytes(max(1, (n_amp + n_parts - 1) // n_parts))
+        assign = self.partition_assignment(n_parts, part)
+        if assign is None:
+            if n_amp >= n_parts:
+                return "amps", (a0, a1)
+            return "ranges", partition_range(self.n_slices, n_parts, part)
+        per_rank_slices = self.cost_bytes(n_amp, assign[0])
+        if per_rank_amps <= per_rank_slices and n_amp >= n_parts:
+            return "amps", (a0, a1)
+        return "slices", assign
 
     def partition_vars(self, n_parts: int) -> List[int]:
         """0-based slice variables to fix when sharding over ``n_parts`` ranks ([] = use ranges)."""

@@ -78,3 +78,17 @@ def test_qft20_moduli(gpu, dtype, tol):
     cmds = orc.parse_dsl(txt)
     bss = ["".join("01"[b] for b in row) for row in bits[:3]]
     assert rel_err(out[:3], orc.amplitudes(cmds, data, bss), 20) < tol
+
+
+def test_rqc_7x7_replanned_matches_given_plan(rqc77):
+    """The re-planned program (what bench.py times by default) gives the amplitudes of the
+    program as written, on the full-size workload, and single slices still match the oracle."""
+    txt, data, g = rqc77
+    bits = bench.synth_bits(128, 49)
+    gr = Graph.from_dsl(txt, data, "c64", replan=3.0).compile()
+    assert gr.replan_info["replanned"] and gr.replan_info["bytes"] < 0.5 * gr.replan_info["given_bytes"]
+    assert rel_err(gr.amplitudes(bits), g.amplitudes(bits), 49) < 1e-10
+    cmds = orc.parse_dsl(txt)
+    bss = ["".join("01"[b] for b in row) for row in bits[:2]]
+    for s in (7, 4000):
+        assert rel_err(gr.amplitudes(bss, s, s + 1), orc.amplitudes(cmds, data, bss, slice_begin=s, slice_end=s + 1), 49) < 1e-10

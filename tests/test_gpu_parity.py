@@ -184,3 +184,16 @@ def test_reduction_shaped_nodes(gpu, dtype):
     g = Graph.from_dsl(txt, data, dtype).compile()
     got = g.amplitudes(bs)
     assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 2e-5)
+
+
+@pytest.mark.parametrize("dtype", ["c64", "c32"])
+def test_replanned_graph_on_gpu(gpu, dtype):
+    txt, data, bs = rqc_case(4, 5, 14, 5, n_amp=17)
+    cmds = orc.parse_dsl(txt)
+    ref = orc.amplitudes(cmds, data, bs)
+    g = Graph.from_dsl(txt, data, dtype, replan=0.3, replan_n_amp=64).compile()
+    assert g.replan_info["replanned"]
+    assert rel_err(g.amplitudes(bs), ref, 20) < TOL[dtype]
+    assert rel_err(g.amplitudes(bs, 3, 29), orc.amplitudes(cmds, data, bs, slice_begin=3, slice_end=29), 20) < TOL[dtype]
+    tot = sum(g.amplitudes_subspace(bs, *g.partition_assignment(4, r)) for r in range(4))
+    assert rel_err(tot, ref, 20) < TOL[dtype]

@@ -1,0 +1,69 @@
+"""The batch-aware re-planner is a DSL -> DSL rewrite that must not change the value of
+the program: same leaves and views, same amplitudes for every slice range."""
+import numpy as np
+import pytest
+
+import qxb200 as q
+from qxb200.executor import Graph, bits_from_strings
+from qxb200.replan import replan_dsl, recover_network
+from oracle import qx_oracle as orc
+import lowered_emulator as em
+from cases import kat0, rqc_case, circuit_case
+
+
+def _leaf_lines(txt):
+    return [ln for ln in txt.splitlines() if ln.split() and ln.split()[0] in ("load", "output", "view")]
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 8, 2), (4, 4, 12, 4), (4, 5, 14, 5)])
+def test_replanned_program_is_equivalent(lib_built, shape):
+    r, c, d, ns = shape
+    txt, data, bs = rqc_case(r, c, d, ns, n_amp=4)
+    new, info = replan_dsl(txt, n_amp=64, time=0.3)
+    assert info["replanned"] and info["bytes"] < info["given_bytes"]
+    assert _leaf_lines(new) == _leaf_lines(txt)                 # leaves and views untouched
+    c0, c1 = orc.parse_dsl(txt), orc.parse_dsl(new)
+    assert orc.slice_dims(c0) == orc.slice_dims(c1)
+    assert np.allclose(orc.amplitudes(c1, data, bs), orc.amplitudes(c0, data, bs), atol=1e-15)
+    S = 2 ** ns
+    for (b, e) in [(0, 1), (1, S - 1), (S - 1, S)]:               # per-slice values are preserved too
+        assert np.allclose(orc.amplitudes(c1, data, bs, slice_begin=b, slice_end=e),
+                           orc.amplitudes(c0, data, bs, slice_begin=b, slice_end=e), atol=1e-15)
+    # and the lowered form of the re-planned program executes correctly (random topological order)
+    g = Graph.from_dsl(new, data)
+    assert np.allclose(em.amplitudes(g, data, bits_from_strings(bs, r * c), shuffle_seed=3),
+                       orc.amplitudes(c0, data, bs), atol=1e-14)
+
+
+def test_replan_docs_example_and_unsliced(lib_built):
+    txt, data = kat0()
+    new, info = replan_dsl(txt, n_amp=4, time=0.1)
+    got = orc.amplitudes(orc.parse_dsl(new), data, ["00", "11", "01", "10"])
+    assert np.allclose(got, [1 / np.sqrt(2), 1 / np.sqrt(2), 0, 0], atol=1e-15)
+    txt, data, _ = circuit_case(q.create_qft_circuit(6))
+    new, info = replan_dsl(txt, n_amp=16, time=0.2)
+    allb = list(q.amplitudes_all(6))
+    assert np.allclose(orc.amplitudes(orc.parse_dsl(new), data, allb), orc.amplitudes(orc.parse_dsl(txt), data, allb),
+                       atol=1e-15)
+
+
+def test_recover_network_classes(lib_built):
+    txt, data = kat0()
+    header, leaf_lines, leaves, dims, sliced, scalar = recover_network(txt)
+    assert scalar and len(leaves) == 7 and set(sliced.values()) == {"v1", "v2"}
+    # every index class is shared by at least two leaves (closed network)
+    cnt = {}
+    for lf in leaves:
+        for cl in set(lf.classes):
+            cnt[cl] = cnt.get(cl, 0) + 1
+    assert min(cnt.values()) >= 2
+
+
+def test_from_dsl_replan_flag(lib_built):
+    txt, data, bs = rqc_case(4, 4, 12, 4, n_amp=3)
+    g = Graph.from_dsl(txt, data, "c64", replan=0.2, replan_n_amp=64)
+    assert g.replan_info["replanned"]
+    assert g.cost_bytes(64) < Graph.from_dsl(txt, data, "c64").cost_bytes(64)
+    # partition chooser is consistent: every rank gets the same kind of share
+    kinds = {g.choose_partition(64, 4, r)[0] for r in range(4)}
+    assert len(kinds) == 1
