@@ -207,24 +207,31 @@ void build_templates(Variant& v, int dtype) {
         for (auto& s : op.segA) for (int b = 0; b < s.len; ++b) mapA[s.src + b] = s.dst + b;
         for (auto& s : op.segB) for (int b = 0; b < s.len; ++b) mapB[s.src + b] = s.dst + b;
         p.nC = nC; p.nK = op.nK;
-        p.lob = std::min(nC, 8);
-        // register tile: lowest M-only / N-only bits above the thread bits
+        // register tile: lowest M-only / N-only bits at C positions >= 5, so the 32 lanes of a warp
+        // still cover C bits 0..4 (one contiguous 32-element store per warp and tile element)
         std::vector<int> mbits, nbits;
-        for (int b = p.lob; b < nC; ++b) {
-            if (mapA[b] >= 0 && mapB[b] < 0 && mbits.size() < 2) mbits.push_back(b);
-            else if (mapB[b] >= 0 && mapA[b] < 0 && nbits.size() < 2) nbits.push_back(b);
-        }
-        // K chunk: keep (2^ma + 2^nb) * 2^kc operand loads (<= 64 registers) in flight.  When K
-        // needs several chunks the accumulators stay live too, so shrink the tile to <= 8 outputs
-        // (c64) / 16 (c32) to stay under 128 registers (2 blocks per SM).
-        const int budget_loads = dtype == QXB_C32 ? 32 : 16;
-        int kc = std::min(op.nK, 3);
-        while (kc > 0 && (int)(((1u << mbits.size()) + (1u << nbits.size())) << kc) > budget_loads) --kc;
-        if (kc < op.nK) {
-            const size_t max_tile_bits = dtype == QXB_C32 ? 4 : 3;
-            while (mbits.size() + nbits.size() > max_tile_bits) {
-                if (nbits.size() >= mbits.size()) nbits.pop_back(); else mbits.pop_back();
+        if (nC > 8) {
+            for (int b = 5; b < nC; ++b) {
+                if (mapA[b] >= 0 && mapB[b] < 0 && mbits.size() < 2) mbits.push_back(b);
+                else if (mapB[b] >= 0 && mapA[b] < 0 && nbits.size() < 2) nbits.push_back(b);
             }
+            while ((int)(mbits.size() + nbits.size()) > nC - 8) {      // keep 8 thread bits
+                if (nbits.size() >= mbits.size() && !nbits.empty()) nbits.pop_back(); else mbits.pop_back();
+            }
+        }
+        // K chunk.  Registers ~ RP * ((2^ma + 2^nb) * 2^kc  [staged operands]
+        //                              + 2^(ma+nb)             [accumulators, only when K needs > 1 chunk]).
+        // The tile comes first (it is what cuts L1/L2 traffic: (2^ma + 2^nb) / 2^(ma+nb) loads per output
+        // and k); with a full 4x4 tile and K > 2^kc the schedule is the GEMM rank-1 update (kc = 0).
+        const int rp = dtype == QXB_C32 ? 2 : 4;
+        const int tmn = (int)((1u << mbits.size()) + (1u << nbits.size()));
+        const int tile = 1 << (mbits.size() + nbits.size());
+        int kc = std::min(op.nK, 3);
+        while (kc > 0) {
+            const bool multi = kc < op.nK;
+            const int regs = rp * ((tmn << kc) + (multi ? tile : 0));
+            if (regs <= (multi ? 96 : 64)) break;
+            --kc;
         }
         p.kc = kc;
         p.ma = (int)mbits.size(); p.nb = (int)nbits.size();
@@ -242,19 +249,23 @@ void build_templates(Variant& v, int dtype) {
                 p.cT[jm * (1 << p.nb) + jn] = c2;
             }
         }
-        // thread-bit and hi-bit segment maps
-        std::vector<std::pair<int, std::pair<int, int>>> alo, blo, ahi, bhi, chi;
-        for (int b = 0; b < p.lob; ++b) {
-            if (mapA[b] >= 0) alo.push_back({b, {mapA[b], 1}});
-            if (mapB[b] >= 0) blo.push_back({b, {mapB[b], 1}});
-        }
-        int h = 0;
-        for (int b = p.lob; b < nC; ++b) {
+        // thread bits = the lowest 8 (or fewer) non-tile positions, hi bits = the rest
+        p.lob = std::min(nC - p.ma - p.nb, 8);
+        std::vector<std::pair<int, std::pair<int, int>>> alo, blo, clo, ahi, bhi, chi;
+        int t = 0, h = 0;
+        for (int b = 0; b < nC; ++b) {
             if (is_tile[b]) continue;
-            chi.push_back({h, {b, 1}});
-            if (mapA[b] >= 0) ahi.push_back({h, {mapA[b], 1}});
-            if (mapB[b] >= 0) bhi.push_back({h, {mapB[b], 1}});
-            ++h;
+            if (t < p.lob) {
+                clo.push_back({t, {b, 1}});
+                if (mapA[b] >= 0) alo.push_back({t, {mapA[b], 1}});
+                if (mapB[b] >= 0) blo.push_back({t, {mapB[b], 1}});
+                ++t;
+            } else {
+                chi.push_back({h, {b, 1}});
+                if (mapA[b] >= 0) ahi.push_back({h, {mapA[b], 1}});
+                if (mapB[b] >= 0) bhi.push_back({h, {mapB[b], 1}});
+                ++h;
+            }
         }
         p.hb = h;
         auto merge = [](const std::vector<std::pair<int, std::pair<int, int>>>& parts, DSeg* dst, int cap,
@@ -272,6 +283,7 @@ void build_templates(Variant& v, int dtype) {
             return n;
         };
         p.nsAlo = merge(alo, p.sAlo, 8, op.name); p.nsBlo = merge(blo, p.sBlo, 8, op.name);
+        p.nsClo = merge(clo, p.sClo, 8, op.name);
         p.nsAhi = merge(ahi, p.sAhi, kMaxSeg, op.name); p.nsBhi = merge(bhi, p.sBhi, kMaxSeg, op.name);
         p.nsChi = merge(chi, p.sChi, kMaxSeg, op.name);
         if (op.segKA.size() > kMaxKSeg || op.segKB.size() > kMaxKSeg)

@@ -48,6 +48,7 @@ contract_kernel(const __grid_constant__ OpParams p) {
     const unsigned lo = tid & ((1u << lob) - 1u);
     const long long aLo = segeval(p.sAlo, p.nsAlo, lo);
     const long long bLo = segeval(p.sBlo, p.nsBlo, lo);
+    const long long cLo = segeval(p.sClo, p.nsClo, lo);
     const int hb = p.hb;
     const long long hmask = (1ll << hb) - 1ll;
     for (long long t0 = ((long long)blockIdx.x << sub_bits); t0 < p.tiles;
@@ -58,7 +59,7 @@ contract_kernel(const __grid_constant__ OpParams p) {
         const unsigned long long hh = (unsigned long long)(tile & hmask);
         const R2* Ap = A + u * p.sUA + segeval(p.sAhi, p.nsAhi, hh) + aLo;
         const R2* Bp = B + u * p.sUB + segeval(p.sBhi, p.nsBhi, hh) + bLo;
-        R2* Cp = C + u * p.sUC + segeval(p.sChi, p.nsChi, hh) + lo;
+        R2* Cp = C + u * p.sUC + segeval(p.sChi, p.nsChi, hh) + cLo;
         if (ONE) {
             // K fits one register chunk: load everything, then each output is a short
             // dot product that is stored at once (no accumulator array kept live)

@@ -33,11 +33,12 @@ struct OpParams {
     int ma, nb;                     // register tile: 2^ma M-only bits x 2^nb N-only bits per thread
     int kc;                         // log2 of the K chunk staged in registers per step (<= 3, <= nK)
     int hb;                         // remaining ("hi") C bits, enumerated by the tile index
-    int nsAlo, nsBlo, nsAhi, nsBhi, nsChi, nkA, nkB;
+    int nsAlo, nsBlo, nsClo, nsAhi, nsBhi, nsChi, nkA, nkB;
     long long ktabA[kKTab], ktabB[kKTab];   // offsets of the low min(nK,4) bits of k
     long long aT[4], bT[4];         // register-tile offsets into A (M bits) and B (N bits)
     long long cT[16];               // register-tile offsets into C, index jm * 2^nb + jn
-    DSeg sAlo[8], sBlo[8];          // thread-bit part of the address maps
+    DSeg sAlo[8], sBlo[8], sClo[8]; // thread-bit part of the address maps (thread bits are the lowest
+                                    // C positions that are not register-tile bits)
     DSeg sAhi[kMaxSeg], sBhi[kMaxSeg], sChi[kMaxSeg];   // hi-index part
     DSeg kA[kMaxKSeg], kB[kMaxKSeg];
 };
