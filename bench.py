@@ -212,14 +212,14 @@ def run_gpu(args):
 
     txt, data, w = build_workload(args.workload)
     n_q = w["rows"] * w["cols"]
-    replan_s = 0.0 if args.no_replan else args.replan_seconds
+    replan_s = 0 if args.no_replan else args.replan_candidates
     # the search is wall-clock bounded, so only rank 0 re-plans and every rank runs ITS program
     # (the slice-variable partition must be derived from one and the same contraction tree)
     info = None
     plan_txt = txt
     if replan_s > 0 and rank == 0:
         from qxb200.replan import replan_dsl
-        plan_txt, info = replan_dsl(txt, n_amp=args.amps, time=replan_s, dtype=w["dtype"])
+        plan_txt, info = replan_dsl(txt, n_amp=args.amps, candidates=replan_s, dtype=w["dtype"])
     if world > 1:
         box = [plan_txt, info]
         dist.broadcast_object_list(box, src=0)
@@ -465,12 +465,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="qxb200", choices=["qxb200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--amps", type=int, default=4096, help="bitstrings per step")
+    ap.add_argument("--amps", type=int, default=32768, help="bitstrings per step")
     ap.add_argument("--amp-batch", type=int, default=0)
     ap.add_argument("--ref-slices", type=int, default=64, help="slices per bitstring in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-replan", action="store_true", help="run the contraction order exactly as the file gives it")
-    ap.add_argument("--replan-seconds", type=float, default=4.0)
+    ap.add_argument("--replan-candidates", type=int, default=24, help="orders scored by the re-planner (seeded)")
     ap.add_argument("--no-as-given", action="store_true", help="skip the extra as-given-plan measurement")
     ap.add_argument("--partition", default="auto", choices=["auto", "amps", "slices"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly (no CUDA-graph replay)")

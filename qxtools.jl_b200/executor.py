@@ -57,12 +57,13 @@ class Graph:
     def from_dsl(cls, text: str, data: Dict[str, np.ndarray], dtype: str = "c64", replan: float = 0.0,
                  replan_n_amp: int = 1024) -> "Graph":
         """``replan`` > 0: re-derive the contraction order for batched execution first
-        (host-side DSL -> DSL rewrite, exact; ``replan`` = seconds of search, see replan.py)."""
+        (host-side DSL -> DSL rewrite, exact; ``replan`` = number of candidate orders, see replan.py)."""
         g = cls(dtype)
         g.replan_info = None
         if replan and replan > 0:
             from .replan import replan_dsl
-            text, g.replan_info = replan_dsl(text, n_amp=replan_n_amp, time=float(replan), dtype=dtype)
+            text, g.replan_info = replan_dsl(text, n_amp=replan_n_amp, candidates=max(1, int(round(replan))),
+                                             dtype=dtype)
         g.text = text
         b = text.encode()
         check(g._lib.qxb_graph_parse_dsl(g._h, b, len(b)))

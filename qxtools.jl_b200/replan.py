@@ -278,10 +278,12 @@ def _cost(text: str, data_dims: Dict[str, Tuple[int, ...]], n_amp: int, dtype: s
     return tot * es
 
 
-def replan_dsl(text: str, n_amp: int = 1024, time: float = 2.0, seed: int = 0, dtype: str = "c64",
-               verbose: bool = False):
-    """Return (new_text, info).  ``time`` seconds of randomised min-fill restarts; the original
-    program is kept when nothing cheaper is found."""
+def replan_dsl(text: str, n_amp: int = 1024, time: float = 30.0, seed: int = 0, dtype: str = "c64",
+               verbose: bool = False, candidates: int = 24):
+    """Return (new_text, info).  Tries the deterministic min-fill order and then randomised
+    restarts (seeded) until ``candidates`` orders were scored or ``time`` seconds passed -- with
+    the default bounds the count is what stops the search, so the result is reproducible.
+    The original program is kept when nothing cheaper is found."""
     header, leaf_lines, leaves, dims, sliced, scalar = recover_network(text)
     if not scalar:
         return text, {"replanned": False, "reason": "saved tensor is not a scalar"}
@@ -295,7 +297,7 @@ def replan_dsl(text: str, n_amp: int = 1024, time: float = 2.0, seed: int = 0, d
     rng = np.random.default_rng(seed)
     t_end = _time.time() + max(0.0, time)
     first = True
-    while first or _time.time() < t_end:
+    while first or (_time.time() < t_end and tries < candidates):
         _, order = min_fill(lg, None if first else rng)
         first = False
         plan, root = _plan_from_order(net, order)

@@ -85,7 +85,7 @@ def test_rqc_7x7_replanned_matches_given_plan(rqc77):
     program as written, on the full-size workload, and single slices still match the oracle."""
     txt, data, g = rqc77
     bits = bench.synth_bits(128, 49)
-    gr = Graph.from_dsl(txt, data, "c64", replan=3.0).compile()
+    gr = Graph.from_dsl(txt, data, "c64", replan=12).compile()
     assert gr.replan_info["replanned"] and gr.replan_info["bytes"] < 0.5 * gr.replan_info["given_bytes"]
     assert rel_err(gr.amplitudes(bits), g.amplitudes(bits), 49) < 1e-10
     cmds = orc.parse_dsl(txt)

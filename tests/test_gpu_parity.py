@@ -191,7 +191,7 @@ def test_replanned_graph_on_gpu(gpu, dtype):
     txt, data, bs = rqc_case(4, 5, 14, 5, n_amp=17)
     cmds = orc.parse_dsl(txt)
     ref = orc.amplitudes(cmds, data, bs)
-    g = Graph.from_dsl(txt, data, dtype, replan=0.3, replan_n_amp=64).compile()
+    g = Graph.from_dsl(txt, data, dtype, replan=6, replan_n_amp=64).compile()
     assert g.replan_info["replanned"]
     assert rel_err(g.amplitudes(bs), ref, 20) < TOL[dtype]
     assert rel_err(g.amplitudes(bs, 3, 29), orc.amplitudes(cmds, data, bs, slice_begin=3, slice_end=29), 20) < TOL[dtype]

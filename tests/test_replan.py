@@ -19,7 +19,7 @@ def _leaf_lines(txt):
 def test_replanned_program_is_equivalent(lib_built, shape):
     r, c, d, ns = shape
     txt, data, bs = rqc_case(r, c, d, ns, n_amp=4)
-    new, info = replan_dsl(txt, n_amp=64, time=0.3)
+    new, info = replan_dsl(txt, n_amp=64, candidates=6)
     assert info["replanned"] and info["bytes"] < info["given_bytes"]
     assert _leaf_lines(new) == _leaf_lines(txt)                 # leaves and views untouched
     c0, c1 = orc.parse_dsl(txt), orc.parse_dsl(new)
@@ -37,11 +37,11 @@ def test_replanned_program_is_equivalent(lib_built, shape):
 
 def test_replan_docs_example_and_unsliced(lib_built):
     txt, data = kat0()
-    new, info = replan_dsl(txt, n_amp=4, time=0.1)
+    new, info = replan_dsl(txt, n_amp=4, candidates=6)
     got = orc.amplitudes(orc.parse_dsl(new), data, ["00", "11", "01", "10"])
     assert np.allclose(got, [1 / np.sqrt(2), 1 / np.sqrt(2), 0, 0], atol=1e-15)
     txt, data, _ = circuit_case(q.create_qft_circuit(6))
-    new, info = replan_dsl(txt, n_amp=16, time=0.2)
+    new, info = replan_dsl(txt, n_amp=16, candidates=6)
     allb = list(q.amplitudes_all(6))
     assert np.allclose(orc.amplitudes(orc.parse_dsl(new), data, allb), orc.amplitudes(orc.parse_dsl(txt), data, allb),
                        atol=1e-15)
@@ -61,7 +61,7 @@ def test_recover_network_classes(lib_built):
 
 def test_from_dsl_replan_flag(lib_built):
     txt, data, bs = rqc_case(4, 4, 12, 4, n_amp=3)
-    g = Graph.from_dsl(txt, data, "c64", replan=0.2, replan_n_amp=64)
+    g = Graph.from_dsl(txt, data, "c64", replan=6, replan_n_amp=64)
     assert g.replan_info["replanned"]
     assert g.cost_bytes(64) < Graph.from_dsl(txt, data, "c64").cost_bytes(64)
     # partition chooser is consistent: every rank gets the same kind of share
