@@ -447,7 +447,7 @@ def roofline(args, txt, data, w, bits_d, out_d, n_amp, s0, s1, assign=None, bits
     if os.path.exists(tpath):
         t = json.load(open(tpath)).get(args.workload)
         if t:
-            traffic = t["bytes_per_launch_mean_top5_at_1024_amps"] * n_amp / 1024.0
+            traffic = t["bytes_per_launch_mean_dominant"] * n_amp / float(t["at_amps"])
     all_ms = sum(o["ms"] for o in ops)
     return {"bound": "hbm", "kernel": "contract_kernel (dominant contractions: top ops by FLOPs covering >=80%)",
             "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s",

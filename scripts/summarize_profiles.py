@@ -85,10 +85,13 @@ def ncu_reports():
             v, u = s.split()
             return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u]
         big = [d for d in out if "dram__bytes_write.sum" in d]
-        big.sort(key=lambda d: -gb(d["dram__bytes_write.sum"]) - gb(d["dram__bytes_read.sum"]))
-        top = big[:5]
-        traffic = sum(gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"]) for d in top) / len(top)
-        json.dump({"rqc_7x7_d20_c64_s4096": {"bytes_per_launch_mean_top5_at_1024_amps": traffic,
+        tot = lambda d: gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"])
+        mx = max(tot(d) for d in big)
+        top = [d for d in big if tot(d) > 0.1 * mx]          # the dominant launches among the captured ones
+        traffic = sum(tot(d) for d in top) / len(top)
+        amps = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+        json.dump({"rqc_7x7_d20_c64_s4096": {"bytes_per_launch_mean_dominant": traffic, "at_amps": amps,
+                                             "n_launches": len(top),
                                              "source": f"profiles/{tag}_ncu_top_kernels.json"}},
                   open(os.path.join(PROF, "ncu_traffic.json"), "w"), indent=1)
     print("ncu kernels:", len(out))
