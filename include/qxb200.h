@@ -50,7 +50,7 @@ typedef struct qxb_options {
     int32_t no_cuda_graph;     /* 1 = launch every kernel directly instead of replaying a captured step */
     int32_t sum_at_root;       /* 1 = keep every batched slice variable open until the root and sum there;
                                   0 (default) = sum each one at the lowest node covering all its leaves   */
-    int32_t reserved;
+    int32_t no_smem_stage;     /* 1 = never use the shared-memory-staged kernel for broadcast-type nodes */
 } qxb_options;
 
 /* library */

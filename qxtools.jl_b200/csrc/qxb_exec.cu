@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <set>
 #include <sstream>
 #include <tuple>
 
@@ -316,6 +317,7 @@ struct Node {
     void* ms_ptr = nullptr; size_t ms_bytes = 0;
     int variant = -1, op = -1;           // contraction nodes: where to book profile time
     double flops = 0, bytes = 0;
+    size_t smem = 0;
     template <typename T> void arg(const T& v) {
         size_t off = (argmem.size() + alignof(T) - 1) / alignof(T) * alignof(T);
         if (alignof(T) < 16 && sizeof(T) >= 16) off = (argmem.size() + 15) / 16 * 16;
@@ -348,11 +350,31 @@ Node contract_node(const RunCtx& c, int i) {
         const long long warps = (long long)outputs;
         n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>((warps * 32 + kThreads - 1) / kThreads, cap)));
     } else {
-        n.func = contract_func(g->dtype, p.kc, p.ma, p.nb, p.kc == p.nK);
-        n.grid = dim3((unsigned)std::max<long long>(1, std::min(blocks, cap)));
+        // broadcast-type node: both operands small per bitstring row, C much larger -> stage them in
+        // shared memory once per row (otherwise every output re-reads them through L1/L2)
+        const size_t stage = ((size_t(1) << A.span_bits) + (size_t(1) << B.span_bits)) * g->es();
+        const void* sf = nullptr;
+        if (!g->opts.no_smem_stage && p.lob == 8 && p.ma >= 1 && p.nb >= 1 && stage <= 96 * 1024 && p.hb >= 1 &&
+            A.lay.size() && B.lay.size() && op.elems_c >= 4.0 * (op.elems_a + op.elems_b) &&
+            op.elems_a == std::ldexp(1.0, A.span_bits) && op.elems_b == std::ldexp(1.0, B.span_bits) && p.U >= g_num_sms)
+            sf = contract_smem_func(g->dtype, p.kc, p.ma, p.nb, p.kc == p.nK);
+        if (sf) {
+            p.aBits = A.span_bits; p.bBits = B.span_bits;
+            n.func = sf;
+            n.smem = stage;
+            n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(p.U, (long long)g_num_sms * 2)));
+            static std::set<const void*> configured;
+            if (stage > 48 * 1024 && !configured.count(sf)) {
+                CUDA_OK(cudaFuncSetAttribute(sf, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                configured.insert(sf);
+            }
+        } else {
+            n.func = contract_func(g->dtype, p.kc, p.ma, p.nb, p.kc == p.nK);
+            n.grid = dim3((unsigned)std::max<long long>(1, std::min(blocks, cap)));
+        }
     }
     n.block = dim3(kThreads);
-    n.arg(p);
+    n.arg(p);      // p is final here (aBits/bBits set above)
     n.variant = c.variant_key; n.op = i;
     const double u = (double)p.U;
     n.flops = 8.0 * op.macs_per_amp * u;
@@ -364,7 +386,7 @@ void launch_node(const Node& n, cudaStream_t st) {
     if (!n.func) { CUDA_OK(cudaMemsetAsync(n.ms_ptr, 0, n.ms_bytes, st)); return; }
     void* args[12];
     for (size_t a = 0; a < n.argoff.size(); ++a) args[a] = (void*)(n.argmem.data() + n.argoff[a]);
-    CUDA_OK(cudaLaunchKernel(n.func, n.grid, n.block, args, 0, st));
+    CUDA_OK(cudaLaunchKernel(n.func, n.grid, n.block, args, n.smem, st));
 }
 
 // constant folding at compile time: serial launches of the const-phase nodes
@@ -600,7 +622,7 @@ cudaGraphExec_t instantiate(const std::vector<Node>& nodes) {
                 void* args[12];
                 for (size_t a = 0; a < n.argoff.size(); ++a) args[a] = (void*)(n.argmem.data() + n.argoff[a]);
                 cudaKernelNodeParams kp{};
-                kp.func = (void*)n.func; kp.gridDim = n.grid; kp.blockDim = n.block; kp.sharedMemBytes = 0;
+                kp.func = (void*)n.func; kp.gridDim = n.grid; kp.blockDim = n.block; kp.sharedMemBytes = (unsigned)n.smem;
                 kp.kernelParams = args; kp.extra = nullptr;
                 CUDA_OK(cudaGraphAddKernelNode(&gn[i], graph, deps.data(), deps.size(), &kp));
             }

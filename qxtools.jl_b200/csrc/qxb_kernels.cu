@@ -34,13 +34,75 @@ __device__ __forceinline__ long long segeval(const DSeg* s, int n, unsigned long
 // by the tile index through segment maps.  K is walked in chunks of 2^KC: all
 // (2^ma + 2^nb) * 2^KC loads of a chunk are issued before its FMAs (the kernel
 // lives on memory-level parallelism), accumulators stay in registers.
+// One register tile: Ap/Bp/Cp already include every address part except the tile / k offsets.
+// SM = operands live in shared memory (plain loads) instead of global memory (__ldg).
+template <typename R2, int KC, int MA, int NB, bool ONE, bool SM>
+__device__ __forceinline__ void tile_compute(const R2* __restrict__ Ap, const R2* __restrict__ Bp,
+                                             R2* __restrict__ Cp, const OpParams& p) {
+    constexpr int TM = 1 << MA, TN = 1 << NB, KK = 1 << KC;
+    auto ld = [](const R2* q) -> R2 { return SM ? *q : __ldg(q); };
+    if (ONE) {
+        // K fits one register chunk: load everything, then each output is a short
+        // dot product that is stored at once (no accumulator array kept live)
+        R2 av[TM][KK], bv[TN][KK];
+#pragma unroll
+        for (int j = 0; j < TM; ++j)
+#pragma unroll
+            for (int k = 0; k < KK; ++k) av[j][k] = ld(Ap + p.aT[j] + p.ktabA[k]);
+#pragma unroll
+        for (int j = 0; j < TN; ++j)
+#pragma unroll
+            for (int k = 0; k < KK; ++k) bv[j][k] = ld(Bp + p.bT[j] + p.ktabB[k]);
+#pragma unroll
+        for (int jm = 0; jm < TM; ++jm) {
+#pragma unroll
+            for (int jn = 0; jn < TN; ++jn) {
+                R2 acc; acc.x = 0; acc.y = 0;
+#pragma unroll
+                for (int k = 0; k < KK; ++k) cmac(acc, av[jm][k], bv[jn][k]);
+                Cp[p.cT[jm * TN + jn]] = acc;
+            }
+        }
+    } else {
+        const int nchunks = 1 << (p.nK - KC);
+        R2 acc[TM][TN];
+#pragma unroll
+        for (int jm = 0; jm < TM; ++jm)
+#pragma unroll
+            for (int jn = 0; jn < TN; ++jn) { acc[jm][jn].x = 0; acc[jm][jn].y = 0; }
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const unsigned long long kb = (unsigned long long)ch << KC;
+            const R2* Ac = Ap + segeval(p.kA, p.nkA, kb);
+            const R2* Bc = Bp + segeval(p.kB, p.nkB, kb);
+            R2 av[TM][KK], bv[TN][KK];
+#pragma unroll
+            for (int j = 0; j < TM; ++j)
+#pragma unroll
+                for (int k = 0; k < KK; ++k) av[j][k] = ld(Ac + p.aT[j] + p.ktabA[k]);
+#pragma unroll
+            for (int j = 0; j < TN; ++j)
+#pragma unroll
+                for (int k = 0; k < KK; ++k) bv[j][k] = ld(Bc + p.bT[j] + p.ktabB[k]);
+#pragma unroll
+            for (int jm = 0; jm < TM; ++jm)
+#pragma unroll
+                for (int jn = 0; jn < TN; ++jn)
+#pragma unroll
+                    for (int k = 0; k < KK; ++k) cmac(acc[jm][jn], av[jm][k], bv[jn][k]);
+        }
+#pragma unroll
+        for (int jm = 0; jm < TM; ++jm)
+#pragma unroll
+            for (int jn = 0; jn < TN; ++jn) Cp[p.cT[jm * TN + jn]] = acc[jm][jn];
+    }
+}
+
 template <typename R2, int KC, int MA, int NB, bool ONE>
 __global__ void __launch_bounds__(kThreads, 2)
 contract_kernel(const __grid_constant__ OpParams p) {
     const R2* __restrict__ A = reinterpret_cast<const R2*>(p.A);
     const R2* __restrict__ B = reinterpret_cast<const R2*>(p.B);
     R2* __restrict__ C = reinterpret_cast<R2*>(p.C);
-    constexpr int TM = 1 << MA, TN = 1 << NB, KK = 1 << KC;
     const int tid = threadIdx.x;
     const int lob = p.lob;
     const int sub_bits = 8 - lob;
@@ -60,61 +122,73 @@ contract_kernel(const __grid_constant__ OpParams p) {
         const R2* Ap = A + u * p.sUA + segeval(p.sAhi, p.nsAhi, hh) + aLo;
         const R2* Bp = B + u * p.sUB + segeval(p.sBhi, p.nsBhi, hh) + bLo;
         R2* Cp = C + u * p.sUC + segeval(p.sChi, p.nsChi, hh) + cLo;
-        if (ONE) {
-            // K fits one register chunk: load everything, then each output is a short
-            // dot product that is stored at once (no accumulator array kept live)
-            R2 av[TM][KK], bv[TN][KK];
-#pragma unroll
-            for (int j = 0; j < TM; ++j)
-#pragma unroll
-                for (int k = 0; k < KK; ++k) av[j][k] = __ldg(Ap + p.aT[j] + p.ktabA[k]);
-#pragma unroll
-            for (int j = 0; j < TN; ++j)
-#pragma unroll
-                for (int k = 0; k < KK; ++k) bv[j][k] = __ldg(Bp + p.bT[j] + p.ktabB[k]);
-#pragma unroll
-            for (int jm = 0; jm < TM; ++jm) {
-#pragma unroll
-                for (int jn = 0; jn < TN; ++jn) {
-                    R2 acc; acc.x = 0; acc.y = 0;
-#pragma unroll
-                    for (int k = 0; k < KK; ++k) cmac(acc, av[jm][k], bv[jn][k]);
-                    Cp[p.cT[jm * TN + jn]] = acc;
-                }
-            }
-        } else {
-            const int nchunks = 1 << (p.nK - KC);
-            R2 acc[TM][TN];
-#pragma unroll
-            for (int jm = 0; jm < TM; ++jm)
-#pragma unroll
-                for (int jn = 0; jn < TN; ++jn) { acc[jm][jn].x = 0; acc[jm][jn].y = 0; }
-            for (int ch = 0; ch < nchunks; ++ch) {
-                const unsigned long long kb = (unsigned long long)ch << KC;
-                const R2* Ac = Ap + segeval(p.kA, p.nkA, kb);
-                const R2* Bc = Bp + segeval(p.kB, p.nkB, kb);
-                R2 av[TM][KK], bv[TN][KK];
-#pragma unroll
-                for (int j = 0; j < TM; ++j)
-#pragma unroll
-                    for (int k = 0; k < KK; ++k) av[j][k] = __ldg(Ac + p.aT[j] + p.ktabA[k]);
-#pragma unroll
-                for (int j = 0; j < TN; ++j)
-#pragma unroll
-                    for (int k = 0; k < KK; ++k) bv[j][k] = __ldg(Bc + p.bT[j] + p.ktabB[k]);
-#pragma unroll
-                for (int jm = 0; jm < TM; ++jm)
-#pragma unroll
-                    for (int jn = 0; jn < TN; ++jn)
-#pragma unroll
-                        for (int k = 0; k < KK; ++k) cmac(acc[jm][jn], av[jm][k], bv[jn][k]);
-            }
-#pragma unroll
-            for (int jm = 0; jm < TM; ++jm)
-#pragma unroll
-                for (int jn = 0; jn < TN; ++jn) Cp[p.cT[jm * TN + jn]] = acc[jm][jn];
+        tile_compute<R2, KC, MA, NB, ONE, false>(Ap, Bp, Cp, p);
+    }
+}
+
+// Broadcast-type nodes (two small operands, large C -- e.g. the outer-product-like steps of
+// a re-planned tree): one CTA owns one bitstring row at a time, stages A[u] and B[u]
+// (2^aBits + 2^bBits elements) in shared memory once, then produces all 2^nC outputs of that
+// row from shared memory.  Needs lob == 8 (nC - ma - nb >= 8).
+template <typename R2, int KC, int MA, int NB, bool ONE>
+__global__ void __launch_bounds__(kThreads, 2)
+contract_smem_kernel(const __grid_constant__ OpParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R2* sA = reinterpret_cast<R2*>(smem_raw);
+    R2* sB = sA + (1ll << p.aBits);
+    const R2* __restrict__ A = reinterpret_cast<const R2*>(p.A);
+    const R2* __restrict__ B = reinterpret_cast<const R2*>(p.B);
+    R2* __restrict__ C = reinterpret_cast<R2*>(p.C);
+    const int tid = threadIdx.x;
+    const unsigned lo = tid;
+    const long long aLo = segeval(p.sAlo, p.nsAlo, lo);
+    const long long bLo = segeval(p.sBlo, p.nsBlo, lo);
+    const long long cLo = segeval(p.sClo, p.nsClo, lo);
+    const long long nA = 1ll << p.aBits, nB = 1ll << p.bBits;
+    const long long tiles_u = 1ll << p.hb;
+    for (long long u = blockIdx.x; u < p.U; u += gridDim.x) {
+        __syncthreads();                       // previous row fully consumed
+        const R2* Au = A + u * p.sUA;
+        const R2* Bu = B + u * p.sUB;
+        for (long long i = tid; i < nA; i += kThreads) sA[i] = __ldg(Au + i);
+        for (long long i = tid; i < nB; i += kThreads) sB[i] = __ldg(Bu + i);
+        __syncthreads();
+        R2* Cu = C + u * p.sUC + cLo;
+        for (long long hh = 0; hh < tiles_u; ++hh) {
+            const R2* Ap = sA + segeval(p.sAhi, p.nsAhi, (unsigned long long)hh) + aLo;
+            const R2* Bp = sB + segeval(p.sBhi, p.nsBhi, (unsigned long long)hh) + bLo;
+            R2* Cp = Cu + segeval(p.sChi, p.nsChi, (unsigned long long)hh);
+            tile_compute<R2, KC, MA, NB, ONE, true>(Ap, Bp, Cp, p);
         }
     }
+}
+
+template <typename R2, int KC, int MA, int NB>
+static const void* pick_smem_one(bool one) {
+    return one ? (const void*)&contract_smem_kernel<R2, KC, MA, NB, true>
+               : (const void*)&contract_smem_kernel<R2, KC, MA, NB, false>;
+}
+template <typename R2, int KC>
+static const void* pick_smem_tile(int ma, int nb, bool one) {
+    if (ma == 1 && nb == 1) return pick_smem_one<R2, KC, 1, 1>(one);
+    if (ma == 1 && nb == 2) return pick_smem_one<R2, KC, 1, 2>(one);
+    if (ma == 2 && nb == 1) return pick_smem_one<R2, KC, 2, 1>(one);
+    if (ma == 2 && nb == 2) return pick_smem_one<R2, KC, 2, 2>(one);
+    return nullptr;
+}
+template <typename R2>
+static const void* pick_smem_kc(int kc, int ma, int nb, bool one) {
+    switch (kc) {
+    case 0: return pick_smem_tile<R2, 0>(ma, nb, one);
+    case 1: return pick_smem_tile<R2, 1>(ma, nb, one);
+    case 2: return pick_smem_tile<R2, 2>(ma, nb, one);
+    default: return nullptr;
+    }
+}
+
+// nullptr when there is no shared-memory variant for this shape
+const void* contract_smem_func(int dtype, int kc, int ma, int nb, bool single_chunk) {
+    return dtype == 0 ? pick_smem_kc<float2>(kc, ma, nb, single_chunk) : pick_smem_kc<double2>(kc, ma, nb, single_chunk);
 }
 
 template <typename R2, int KC, int MA, int NB>

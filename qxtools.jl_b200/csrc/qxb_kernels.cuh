@@ -33,6 +33,7 @@ struct OpParams {
     int ma, nb;                     // register tile: 2^ma M-only bits x 2^nb N-only bits per thread
     int kc;                         // log2 of the K chunk staged in registers per step (<= 3, <= nK)
     int hb;                         // remaining ("hi") C bits, enumerated by the tile index
+    int aBits, bBits;               // log2 of the stored elements of A and B per bitstring row
     int nsAlo, nsBlo, nsClo, nsAhi, nsBhi, nsChi, nkA, nkB;
     long long ktabA[kKTab], ktabB[kKTab];   // offsets of the low min(nK,4) bits of k
     long long aT[4], bT[4];         // register-tile offsets into A (M bits) and B (N bits)
@@ -48,6 +49,9 @@ struct OutLeafDesc { long long offset_per_amp; int span_bits; int out_idx; };
 // Kernel entry points as function pointers (for cudaLaunchKernel / cudaGraphAddKernelNode).
 // contract: one argument (OpParams by value).
 const void* contract_func(int dtype, int kc, int ma, int nb, bool single_chunk);
+// shared-memory-staged variant for broadcast-type nodes (nullptr if the shape has none); dynamic
+// shared memory = (2^aBits + 2^bBits) * sizeof(element)
+const void* contract_smem_func(int dtype, int kc, int ma, int nb, bool single_chunk);
 // warp-per-output reduction variant for nC <= 8 and long K (same OpParams argument)
 const void* kreduce_func(int dtype);
 // outleaf:  (R2* base, const OutLeafDesc* d, const unsigned char* bits, int n_outputs, long long amp0, long long n)

@@ -92,3 +92,15 @@ def test_rqc_7x7_replanned_matches_given_plan(rqc77):
     bss = ["".join("01"[b] for b in row) for row in bits[:2]]
     for s in (7, 4000):
         assert rel_err(gr.amplitudes(bss, s, s + 1), orc.amplitudes(cmds, data, bss, slice_begin=s, slice_end=s + 1), 49) < 1e-10
+
+
+def test_smem_staged_kernel_matches(rqc77):
+    """Broadcast-type nodes of the re-planned program run through the shared-memory-staged
+    kernel; switching it off must not change the amplitudes."""
+    txt, data, g = rqc77
+    bits = bench.synth_bits(512, 49)
+    a = Graph.from_dsl(txt, data, "c64", replan=12).compile()
+    b = Graph.from_dsl(txt, data, "c64", replan=12).compile(smem_stage=False)
+    assert rel_err(a.amplitudes(bits), b.amplitudes(bits), 49) < 1e-12
+    a32 = Graph.from_dsl(txt, data, "c32", replan=12).compile()
+    assert rel_err(a32.amplitudes(bits), b.amplitudes(bits), 49) < 1e-5
