@@ -197,3 +197,38 @@ def test_replanned_graph_on_gpu(gpu, dtype):
     assert rel_err(g.amplitudes(bs, 3, 29), orc.amplitudes(cmds, data, bs, slice_begin=3, slice_end=29), 20) < TOL[dtype]
     tot = sum(g.amplitudes_subspace(bs, *g.partition_assignment(4, r)) for r in range(4))
     assert rel_err(tot, ref, 20) < TOL[dtype]
+
+
+def test_edge_cases_and_errors(gpu):
+    from qxb200._lib import QxbError
+    txt, data, bs = rqc_case(3, 4, 10, 3, n_amp=6)
+    cmds = orc.parse_dsl(txt)
+    g = Graph.from_dsl(txt, data, "c64").compile()
+    # empty slice range -> zeros; empty batch -> empty result; a single bitstring
+    assert np.all(g.amplitudes(bs, 2, 2) == 0)
+    assert g.amplitudes([]).shape == (0,)
+    assert rel_err(g.amplitudes(bs[:1]), orc.amplitudes(cmds, data, bs[:1]), 12) < 1e-10
+    # out-of-range slices / malformed bitstrings are argument errors, not crashes
+    for bad in ((-1, 2), (0, 9), (5, 3)):
+        with pytest.raises(QxbError) as e:
+            g.amplitudes(bs, *bad)
+        assert e.value.code == -1
+    with pytest.raises(QxbError):
+        g.amplitudes(np.full((2, 12), 7, dtype=np.uint8))
+    with pytest.raises(ValueError):
+        g.amplitudes(["01"])                     # shorter than the number of outputs
+    with pytest.raises(QxbError) as e:
+        g.compile()                              # already compiled
+    assert e.value.code == -2
+    # a budget that cannot hold one bitstring row is a memory error, and a tight one forces batching
+    with pytest.raises(QxbError) as e:
+        Graph.from_dsl(txt, data, "c64").compile(hbm_budget_bytes=64).amplitudes(bs)
+    assert e.value.code == -5
+    gt = Graph.from_dsl(txt, data, "c64").compile(hbm_budget_bytes=40_000)
+    out = gt.amplitudes(bs)
+    assert gt.stats()["amp_batch"] < len(bs)
+    assert rel_err(out, orc.amplitudes(cmds, data, bs), 12) < 1e-10
+    # missing leaf data
+    with pytest.raises(QxbError) as e:
+        Graph.from_dsl(txt, {k: v for k, v in list(data.items())[1:]}, "c64").compile()
+    assert e.value.code == -2
