@@ -31,15 +31,17 @@ from .simulation import amplitudes_uniform
 
 
 def _bitstrings_from_params(params: dict, max_amplitudes: Optional[int]):
+    """List / Uniform give the bitstrings up front; Rejection returns None (sampled on the fly)."""
     out = params["output"]
     method, p = out["method"], out["params"]
     if method == "List":                                  # outputs.jl:63-68
         bs = list(p["bitstrings"])
     elif method == "Uniform":                             # outputs.jl:69-72
         bs = list(amplitudes_uniform(int(p["num_qubits"]), p.get("seed"), int(p["num_samples"])))
+    elif method == "Rejection":                           # outputs.jl:57-62
+        return None
     else:
-        raise NotImplementedError(f"output method {method!r}: only List and Uniform are wired to the executor "
-                                  "(Rejection sampling is a 'next' row, SURVEY.md 8f-2)")
+        raise ValueError(f"output method {method!r} not supported")
     if max_amplitudes is not None:
         bs = bs[:max_amplitudes]
     return bs
@@ -81,6 +83,28 @@ def execute(dsl_file: str, input_file: Optional[str] = None, param_file: Optiona
     t0 = time.perf_counter()
     bitstrings = _bitstrings_from_params(params, max_amplitudes)
     n_slices = g.n_slices if max_slices is None else min(max_slices, g.n_slices)
+    if bitstrings is None:
+        # Rejection sampling: every candidate batch is one amplitudes call on this rank's GPU
+        # (rank 0 only; the sampler is sequential in its acceptance bound M)
+        from .samplers import rejection_sample
+        p = params["output"]["params"]
+        n_samp = int(p["num_samples"]) if max_amplitudes is None else min(int(p["num_samples"]), max_amplitudes)
+        t["Create sampler"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        results = None
+        if rank == 0:
+            bs, amps, info = rejection_sample(lambda bits: g.amplitudes(bits, 0, n_slices), int(p["num_qubits"]), n_samp,
+                                              M=float(p.get("M", 0.0001)), fix_M=bool(p.get("fix_M", False)),
+                                              seed=p.get("seed"))
+            t["Simulation"] = time.perf_counter() - t0
+            results = OrderedDict(zip(bs, amps))
+            if output_file:
+                np.savez(output_file if output_file.endswith(".npz") else output_file + ".npz",
+                         bitstrings=np.array(bs), amplitudes=np.array(amps), M=info["M"], drawn=info["drawn"])
+            if timings:
+                for k, v in t.items():
+                    print(f"  {k:<20s} {v * 1e3:10.3f} ms")
+        return results
     d = Distribution(len(bitstrings), n_slices, world, rank, sub_comm_size if use_mpi else 1)
     t["Create sampler"] = time.perf_counter() - t0
 

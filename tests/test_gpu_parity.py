@@ -232,3 +232,17 @@ def test_edge_cases_and_errors(gpu):
     with pytest.raises(QxbError) as e:
         Graph.from_dsl(txt, {k: v for k, v in list(data.items())[1:]}, "c64").compile()
     assert e.value.code == -2
+
+
+def test_execute_rejection_sampler(gpu, tmp_path):
+    """qxrun on a Rejection parameter file (outputs.jl:57-62): GHZ-5 yields only its two outcomes."""
+    from qxb200.execute import execute
+    prefix = str(tmp_path / "ghz5")
+    q.generate_simulation_files(q.create_ghz_circuit(5), prefix, 1, time=0,
+                                output_args=q.output_params_dict(5, 12, output_method="Rejection", M=16.0,
+                                                                 fix_M=True, seed=4))
+    res = execute(prefix + ".qx", output_file=prefix + "_out.npz", dtype="c64")
+    assert 1 <= len(res) <= 2 and set(res) <= {"00000", "11111"}
+    assert all(abs(abs(a) - 1 / np.sqrt(2)) < 1e-12 for a in res.values())
+    out = np.load(prefix + "_out.npz")
+    assert len(out["bitstrings"]) == 12 and abs(float(out["M"]) - 16.0) < 1e-12
