@@ -355,7 +355,7 @@ Node contract_node(const RunCtx& c, int i) {
         const size_t stage = ((size_t(1) << A.span_bits) + (size_t(1) << B.span_bits)) * g->es();
         const void* sf = nullptr;
         if (!g->opts.no_smem_stage && p.lob == 8 && p.ma >= 1 && p.nb >= 1 && stage <= 96 * 1024 && p.hb >= 1 &&
-            A.lay.size() && B.lay.size() && op.elems_c >= 4.0 * (op.elems_a + op.elems_b) &&
+            A.lay.size() && B.lay.size() && op.elems_c >= 1.5 * (op.elems_a + op.elems_b) &&
             op.elems_a == std::ldexp(1.0, A.span_bits) && op.elems_b == std::ldexp(1.0, B.span_bits) && p.U >= g_num_sms)
             sf = contract_smem_func(g->dtype, p.kc, p.ma, p.nb, p.kc == p.nK);
         if (sf) {
