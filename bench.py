@@ -212,20 +212,10 @@ def run_gpu(args):
 
     txt, data, w = build_workload(args.workload)
     n_q = w["rows"] * w["cols"]
-    replan_s = 0 if args.no_replan else args.replan_candidates
-    # the search is wall-clock bounded, so only rank 0 re-plans and every rank runs ITS program
-    # (the slice-variable partition must be derived from one and the same contraction tree)
-    info = None
-    plan_txt = txt
-    if replan_s > 0 and rank == 0:
-        from qxb200.replan import replan_dsl
-        plan_txt, info = replan_dsl(txt, n_amp=args.amps, candidates=replan_s, dtype=w["dtype"])
-    if world > 1:
-        box = [plan_txt, info]
-        dist.broadcast_object_list(box, src=0)
-        plan_txt, info = box
-    g = Graph.from_dsl(plan_txt, data, w["dtype"])
-    g.replan_info = info
+    # batch-aware re-planning inside the library (qxb_graph_replan: seeded, hence identical on every rank)
+    g = Graph.from_dsl(txt, data, w["dtype"], replan=0 if args.no_replan else args.replan_candidates,
+                       replan_n_amp=args.amps)
+    plan_txt = g.text
     g.compile(amp_batch=args.amp_batch, cuda_graph=not args.no_graph)
     S = g.n_slices
     n_amp = args.amps
@@ -391,7 +381,7 @@ def run_gpu(args):
                                      f"bitstrings split over {world} ranks, all slices each" if mode == "amps" else
                                      f"all bitstrings on every rank, slice variables {[v + 1 for v in assign[0]]} fixed per rank"
                                      if assign is not None else f"contiguous slice ranges / {world}"),
-                       "plan": ("re-planned for batched execution (host-side exact re-association, replan.py): "
+                       "plan": ("re-planned for batched execution (qxb_graph_replan, exact re-association): "
                                 f"{g.replan_info['given_bytes'] / 1e9:.2f} -> {g.replan_info['bytes'] / 1e9:.2f} GB per "
                                 f"{g.replan_info['n_amp_model']} bitstrings") if g.replan_info and g.replan_info.get("replanned")
                                else "contraction order as given by the file",
@@ -470,7 +460,7 @@ def main():
     ap.add_argument("--ref-slices", type=int, default=64, help="slices per bitstring in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-replan", action="store_true", help="run the contraction order exactly as the file gives it")
-    ap.add_argument("--replan-candidates", type=int, default=24, help="orders scored by the re-planner (seeded)")
+    ap.add_argument("--replan-candidates", type=int, default=128, help="orders scored by the re-planner (seeded)")
     ap.add_argument("--no-as-given", action="store_true", help="skip the extra as-given-plan measurement")
     ap.add_argument("--partition", default="auto", choices=["auto", "amps", "slices"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly (no CUDA-graph replay)")

@@ -94,6 +94,15 @@ int  qxb_slice_values(const qxb_graph* g, int64_t slice_id, int64_t* values /*[k
  * batched (the rest are fixed); -1 = all.  Returns the number of bytes needed (incl. NUL). */
 int64_t qxb_graph_describe(qxb_graph* g, int n_free, char* buf, int64_t buflen);
 
+/* Batch-aware re-planning (before compile): keep every load/output/view statement, recover the
+ * tensor network behind the ncon tree and replace the tree by the cheapest of `candidates`
+ * seeded min-fill orders of the UNSLICED network under the executor's cost model for batches of
+ * n_amp_model bitstrings.  Exact re-association: the value of the program does not change.
+ * The planner-side counterpart is contraction_scheme, src/contraction_planning.jl:219-299, which
+ * plans for one slice at a time.  given/new_bytes (may be NULL) report the model cost. */
+int  qxb_graph_replan(qxb_graph* g, int candidates, int64_t n_amp_model, double* given_bytes, double* new_bytes);
+/* The program as .qx text (after re-planning: the re-planned one).  Returns bytes needed incl. NUL. */
+int64_t qxb_graph_program_text(qxb_graph* g, char* buf, int64_t buflen);
 /* Set options before qxb_graph_describe / qxb_graph_compile (compile(opts != NULL) overrides). */
 int  qxb_graph_configure(qxb_graph* g, const qxb_options* opts);
 /* Lower the program, upload leaves, fold constants, size the workspace. */

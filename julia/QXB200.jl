@@ -85,10 +85,13 @@ function Graph(cg::QXContexts.ComputeGraph; dtype::Cint=C64)
     g
 end
 
-function Graph(dsl_text::String, tensors::AbstractDict; dtype::Cint=C32)
+function Graph(dsl_text::String, tensors::AbstractDict; dtype::Cint=C32, replan::Int=64, n_amp_model::Int=1024)
     g = Graph(dtype)
     check(ccall((:qxb_graph_parse_dsl, LIB), Cint, (Ptr{Cvoid}, Cstring, Csize_t), g.h, dsl_text, sizeof(dsl_text)))
     set_data!(g, tensors)
+    # batch-aware re-planning of the ncon tree (exact; leaves and views untouched)
+    replan > 0 && check(ccall((:qxb_graph_replan, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Cdouble}, Ptr{Cdouble}),
+                              g.h, replan, n_amp_model, C_NULL, C_NULL))
     check(ccall((:qxb_graph_compile, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), g.h, C_NULL))
     g
 end

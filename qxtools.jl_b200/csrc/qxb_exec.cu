@@ -905,6 +905,29 @@ int64_t qxb_graph_describe(qxb_graph* g, int n_free, char* buf, int64_t buflen) 
     return rc == QXB_OK ? need : rc;
 }
 
+int qxb_graph_replan(qxb_graph* g, int candidates, int64_t n_amp_model, double* given_bytes, double* new_bytes) {
+    return guard([&] {
+        need_graph(g);
+        ensure_analysed(g);
+        double a = 0, b = 0;
+        replan(g->prog, candidates, 0x9E3779B97F4A7C15ull, (double)std::max<int64_t>(n_amp_model, 1), !g->opts.sum_at_root,
+               &a, &b, (double)g->es());
+        if (given_bytes) *given_bytes = a;
+        if (new_bytes) *new_bytes = b;
+    });
+}
+
+int64_t qxb_graph_program_text(qxb_graph* g, char* buf, int64_t buflen) {
+    int64_t need = 0;
+    int rc = guard([&] {
+        if (!g) throw Error(QXB_ERR_ARG, "null graph");
+        std::string s = program_text(g->prog);
+        need = (int64_t)s.size() + 1;
+        if (buf && buflen >= need) memcpy(buf, s.c_str(), need);
+    });
+    return rc == QXB_OK ? need : rc;
+}
+
 int qxb_graph_configure(qxb_graph* g, const qxb_options* opts) {
     return guard([&] {
         need_graph(g);

@@ -147,6 +147,11 @@ inline uint64_t low_mask(int n) { return n >= 64 ? ~0ull : ((1ull << n) - 1ull);
 // at each step the variable whose fixing leaves the least work (bytes moved) per rank.
 std::vector<int> partition_vars(const Program& p, int n_parts, bool early_sum = true);
 double lowered_cost_bytes(const Lowered& L, double n_amp, double elem_bytes);
+// Batch-aware re-planning of the ncon tree (qxb_replan.cpp).  Returns true when a cheaper
+// program replaced p.cmds (leaf statements are kept verbatim).
+bool replan(Program& p, int candidates, uint64_t seed, double n_amp, bool early_sum, double* given_bytes,
+            double* new_bytes, double elem_bytes);
+std::string program_text(const Program& p);
 // Plan arena offsets for a batch of n_amp bitstrings (fills LTensor::offset and the arena sizes).
 void plan_memory(Lowered& L, int64_t n_amp);
 std::string describe_json(const Program& p, const Lowered& L);

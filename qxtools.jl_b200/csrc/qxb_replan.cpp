@@ -1,0 +1,334 @@
+// qxb200 -- batch-aware re-planning of the ncon tree (planner-side lowering).
+//
+// QXTools plans for one slice of one bitstring: contraction_scheme
+// (/root/reference/src/contraction_planning.jl:219-299) takes the sliced hyper-edges out
+// of the line graph and orders the rest.  This executor batches the sliced hyper-edges and
+// the bitstrings, so that order drags batch bits through every large intermediate.  Here
+// the tensor network behind the program is recovered (index identity = labels matched in
+// an ncon), new elimination orders are drawn (min-fill on the line graph of the UNSLICED
+// network, contraction_planning.jl:47-63,127-176, seeded random tie-breaking), turned into
+// pairwise plans (:386-448, smallest batched result first inside a hyper-edge) and scored
+// with the executor's own cost model (bytes moved by the lowered program).  Leaves and
+// views are kept verbatim; only the ncon statements are re-derived -- an exact
+// re-association, the program's value is unchanged.
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <random>
+#include <set>
+#include <sstream>
+
+#include "../../include/qxb200.h"
+#include "qxb_ir.h"
+
+namespace qxb {
+
+namespace {
+
+struct UF {
+    std::vector<int> p;
+    int make() { p.push_back((int)p.size()); return (int)p.size() - 1; }
+    int find(int x) { while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; } return x; }
+    void unite(int a, int b) { a = find(a); b = find(b); if (a != b) p[b] = a; }
+};
+
+struct Net {
+    std::vector<std::string> names;            // leaf tensors (top of their view chains)
+    std::vector<std::vector<int>> ids;         // classes per leaf (deduplicated), AMP appended for outputs
+    std::vector<std::vector<int>> modes;       // class per DSL mode (for label emission)
+    std::vector<double> dim;                   // extent per class (AMP last)
+    int amp = -1;
+};
+
+// min-fill elimination order over classes [0, n) (AMP excluded by the caller)
+std::vector<int> min_fill_order(std::vector<std::set<int>> adj, std::mt19937_64* rng) {
+    const int n = (int)adj.size();
+    std::vector<char> alive(n, 1);
+    auto fill = [&](int v) {
+        std::vector<int> nb(adj[v].begin(), adj[v].end());
+        int f = 0;
+        for (size_t i = 0; i < nb.size(); ++i)
+            for (size_t j = i + 1; j < nb.size(); ++j)
+                if (!adj[nb[i]].count(nb[j])) ++f;
+        return f;
+    };
+    std::vector<int> cost(n, 0);
+    for (int v = 0; v < n; ++v) cost[v] = fill(v);
+    std::vector<int> order;
+    for (int step = 0; step < n; ++step) {
+        int best = -1;
+        for (int v = 0; v < n; ++v) if (alive[v] && (best < 0 || cost[v] < best)) best = cost[v];
+        std::vector<int> cands;
+        size_t mind = SIZE_MAX;
+        for (int v = 0; v < n; ++v)
+            if (alive[v] && cost[v] == best) mind = std::min(mind, adj[v].size());
+        for (int v = 0; v < n; ++v)
+            if (alive[v] && cost[v] == best && adj[v].size() == mind) cands.push_back(v);
+        int v = cands[0];
+        if (rng && cands.size() > 1) v = cands[(size_t)((*rng)() % cands.size())];
+        std::set<int> nb = adj[v];
+        alive[v] = 0;
+        order.push_back(v);
+        std::set<int> touched(nb.begin(), nb.end());
+        for (int a : nb) adj[a].erase(v);
+        for (int a : nb)
+            for (int b : nb)
+                if (a != b && adj[a].insert(b).second) { touched.insert(adj[a].begin(), adj[a].end()); }
+        for (int a : nb) touched.insert(adj[a].begin(), adj[a].end());
+        adj[v].clear();
+        for (int a : touched) if (alive[a]) cost[a] = fill(a);
+    }
+    return order;
+}
+
+struct PlanStep { int a, b; };                 // indices into the growing tensor list
+
+// elimination order -> pairwise plan over tensor ids [0, n_leaves) + intermediates
+void plan_from_order(const Net& net, const std::vector<int>& order, std::vector<PlanStep>& plan,
+                     std::vector<std::vector<int>>& t_ids, int& root) {
+    const int nl = (int)net.ids.size();
+    t_ids.assign(net.ids.begin(), net.ids.end());
+    std::vector<char> alive(nl, 1);
+    std::map<int, std::set<int>> owners;
+    for (int t = 0; t < nl; ++t) for (int i : t_ids[t]) owners[i].insert(t);
+    auto size = [&](const std::vector<int>& ids) { double r = 1; for (int i : ids) r *= net.dim[i]; return r; };
+    auto result = [&](int a, int b) {
+        std::set<int> res(t_ids[a].begin(), t_ids[a].end());
+        res.insert(t_ids[b].begin(), t_ids[b].end());
+        for (int i : t_ids[a]) {
+            if (i == net.amp) continue;
+            if (std::find(t_ids[b].begin(), t_ids[b].end(), i) == t_ids[b].end()) continue;
+            const std::set<int>& ow = owners[i];
+            bool others = false;
+            for (int o : ow) if (o != a && o != b) { others = true; break; }
+            if (!others) res.erase(i);
+        }
+        return std::vector<int>(res.begin(), res.end());
+    };
+    auto contract = [&](int a, int b) {
+        std::vector<int> res = result(a, b);
+        const int c = (int)t_ids.size();
+        plan.push_back(PlanStep{a, b});
+        for (int i : t_ids[a]) owners[i].erase(a);
+        for (int i : t_ids[b]) owners[i].erase(b);
+        for (int i : res) owners[i].insert(c);
+        alive[a] = alive[b] = 0;
+        alive.push_back(1);
+        t_ids.push_back(std::move(res));
+        return c;
+    };
+    std::vector<int> full(order);
+    if (net.amp >= 0) full.push_back(net.amp);
+    for (int ix : full) {
+        std::vector<int> group(owners[ix].begin(), owners[ix].end());
+        std::sort(group.begin(), group.end(), [&](int x, int y) {
+            const double sx = size(t_ids[x]), sy = size(t_ids[y]);
+            return sx != sy ? sx < sy : x < y;
+        });
+        while (group.size() > 1) {
+            double best = -1; size_t bx = 0, by = 1;
+            for (size_t x = 0; x < group.size(); ++x)
+                for (size_t y = x + 1; y < group.size(); ++y) {
+                    const double s = size(result(group[x], group[y]));
+                    if (best < 0 || s < best) { best = s; bx = x; by = y; }
+                }
+            const int c = contract(group[bx], group[by]);
+            std::vector<int> g2;
+            for (size_t k = 0; k < group.size(); ++k) if (k != bx && k != by) g2.push_back(group[k]);
+            g2.push_back(c);
+            group.swap(g2);
+        }
+    }
+    std::vector<int> rest;
+    for (size_t t = 0; t < alive.size(); ++t) if (alive[t]) rest.push_back((int)t);
+    while (rest.size() > 1) {                 // disconnected components: join the scalars
+        const int c = contract(rest[0], rest[1]);
+        rest.erase(rest.begin(), rest.begin() + 2);
+        rest.insert(rest.begin(), c);
+    }
+    root = rest[0];
+}
+
+}  // namespace
+
+bool replan(Program& prog, int candidates, uint64_t seed, double n_amp, bool early_sum, double* given_bytes,
+            double* new_bytes, double elem_bytes) {
+    if (!prog.analysed) analyse(prog);
+    const Lowered L0 = lower(prog, low_mask((int)prog.vars.size()), early_sum);
+    const double base = lowered_cost_bytes(L0, n_amp, elem_bytes);
+    if (given_bytes) *given_bytes = base;
+    if (new_bytes) *new_bytes = base;
+
+    // ---- recover the network: classes of modes identified through ncon labels
+    UF uf;
+    std::vector<std::vector<int>> h(prog.defs.size());
+    std::vector<char> is_operand(prog.defs.size(), 0);
+    for (size_t di = 0; di < prog.defs.size(); ++di) {
+        const TensorDef& d = prog.defs[di];
+        if (d.kind == T_LOAD || d.kind == T_OUTPUT) {
+            for (size_t m = 0; m < d.modes.size(); ++m) h[di].push_back(uf.make());
+        } else if (d.kind == T_VIEW) {
+            // the view's target is the previous link of the chain: same modes, same handles
+            int tgt = -1;
+            for (const Cmd& c : prog.cmds)
+                if (c.kind == CMD_VIEW && c.name == d.name) tgt = prog.by_name.at(c.a);
+            h[di] = h[tgt];
+        } else {
+            is_operand[d.a] = is_operand[d.b] = 1;
+            std::map<int64_t, int> by;
+            auto scan = [&](const std::vector<int64_t>& ls, int t) {
+                for (size_t i = 0; i < ls.size(); ++i) {
+                    auto it = by.find(ls[i]);
+                    if (it == by.end()) by[ls[i]] = h[t][i]; else uf.unite(it->second, h[t][i]);
+                }
+            };
+            scan(d.al, d.a); scan(d.bl, d.b);
+            for (int64_t l : d.cl) h[di].push_back(by.at(l));
+        }
+    }
+    if (prog.defs[prog.root].kind != T_NCON || !prog.defs[prog.root].modes.empty()) return false;
+    for (const TensorDef& d : prog.defs) if (d.kind == T_NCON && d.uses > 1) return false;   // needs a tree
+
+    Net net;
+    std::map<int, int> cls;                    // uf root -> dense class id
+    auto cls_of = [&](int handle) {
+        const int r = uf.find(handle);
+        auto it = cls.find(r);
+        if (it != cls.end()) return it->second;
+        const int id = (int)cls.size();
+        cls[r] = id;
+        return id;
+    };
+    std::vector<int> leaf_defs;
+    for (size_t di = 0; di < prog.defs.size(); ++di) {
+        const TensorDef& d = prog.defs[di];
+        if (d.kind == T_NCON || !is_operand[di]) continue;
+        leaf_defs.push_back((int)di);
+        std::vector<int> modes, ids;
+        for (size_t m = 0; m < d.modes.size(); ++m) {
+            const int c = cls_of(h[di][m]);
+            if (std::find(modes.begin(), modes.end(), c) != modes.end()) return false;   // repeated index in one tensor
+            modes.push_back(c);
+        }
+        ids = modes;
+        net.names.push_back(d.name);
+        net.modes.push_back(modes);
+        net.ids.push_back(ids);
+    }
+    const int ncls = (int)cls.size();
+    net.dim.assign(ncls + 1, 1.0);
+    for (size_t li = 0; li < leaf_defs.size(); ++li) {
+        const TensorDef& d = prog.defs[leaf_defs[li]];
+        for (size_t m = 0; m < d.modes.size(); ++m) net.dim[net.modes[li][m]] = (double)d.modes[m].full_ext;
+    }
+    bool any_out = false;
+    for (size_t li = 0; li < leaf_defs.size(); ++li)
+        if (prog.defs[prog.defs[leaf_defs[li]].leaf].kind == T_OUTPUT) { net.ids[li].push_back(ncls); any_out = true; }
+    net.amp = any_out ? ncls : -1;
+    net.dim[ncls] = std::max(2.0, n_amp);
+    if (leaf_defs.size() < 3) return false;
+
+    std::vector<std::set<int>> lg(ncls);
+    for (const auto& modes : net.modes)
+        for (int a : modes) for (int b : modes) if (a != b) lg[a].insert(b);
+
+    // leaf statements verbatim, in program order
+    std::vector<Cmd> leaf_cmds;
+    std::set<std::string> taken;
+    for (const Cmd& c : prog.cmds)
+        if (c.kind == CMD_LOAD || c.kind == CMD_OUTPUT || c.kind == CMD_VIEW) { leaf_cmds.push_back(c); taken.insert(c.name); }
+    std::string prefix = "R";
+    while (true) {
+        bool clash = false;
+        for (const std::string& s : taken) if (s.rfind(prefix, 0) == 0) { clash = true; break; }
+        if (!clash) break;
+        prefix += "_";
+    }
+    std::string save_label = "output";
+    for (const Cmd& c : prog.cmds) if (c.kind == CMD_SAVE) save_label = c.name;
+
+    std::mt19937_64 rng(seed);
+    double best = base;
+    std::vector<Cmd> best_cmds;
+    for (int it = 0; it < std::max(1, candidates); ++it) {
+        std::vector<int> order = min_fill_order(lg, it == 0 ? nullptr : &rng);
+        std::vector<PlanStep> plan;
+        std::vector<std::vector<int>> t_ids;
+        int root = -1;
+        plan_from_order(net, order, plan, t_ids, root);
+        // ---- emit
+        const int nl = (int)net.names.size();
+        std::vector<std::string> names(net.names);
+        std::vector<std::vector<int>> cur(net.modes);          // classes per mode of every tensor (DSL order)
+        std::map<int, int> cnt;
+        for (const auto& m : net.modes) for (int i : m) cnt[i]++;
+        std::vector<Cmd> cmds(leaf_cmds);
+        for (size_t s = 0; s < plan.size(); ++s) {
+            const int a = plan[s].a, b = plan[s].b;
+            const std::vector<int>&ia = cur[a], &ib = cur[b];
+            std::map<int, int64_t> label;
+            for (int i : ia) if (!label.count(i)) label[i] = (int64_t)label.size() + 1;
+            for (int i : ib) if (!label.count(i)) label[i] = (int64_t)label.size() + 1;
+            auto in = [](const std::vector<int>& v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); };
+            auto others = [&](int i) { return cnt[i] - (in(ia, i) ? 1 : 0) - (in(ib, i) ? 1 : 0); };
+            std::vector<int> keep;
+            for (int i : ia) if (others(i) > 0) keep.push_back(i);
+            for (int i : ib) if (!in(keep, i) && others(i) > 0) keep.push_back(i);
+            Cmd c; c.kind = CMD_NCON;
+            c.name = prefix + std::to_string(s + 1);
+            c.a = names[a]; c.b = names[b];
+            for (int i : keep) c.cl.push_back(label[i]);
+            for (int i : ia) c.al.push_back(label[i]);
+            for (int i : ib) c.bl.push_back(label[i]);
+            for (int i : ia) cnt[i]--;
+            for (int i : ib) cnt[i]--;
+            for (int i : keep) cnt[i]++;
+            names.push_back(c.name);
+            cur.push_back(keep);
+            cmds.push_back(std::move(c));
+        }
+        (void)nl;
+        Cmd sv; sv.kind = CMD_SAVE; sv.name = save_label; sv.a = names[root];
+        cmds.push_back(sv);
+        // ---- score with the executor's own model
+        Program cand;
+        cand.cmds = cmds;
+        try {
+            analyse(cand);
+            Lowered L = lower(cand, low_mask((int)cand.vars.size()), early_sum);
+            const double c = lowered_cost_bytes(L, n_amp, elem_bytes);
+            if (c < best) { best = c; best_cmds = std::move(cmds); }
+        } catch (const Error&) {
+            continue;                           // a candidate the lowering rejects is simply skipped
+        }
+    }
+    if (best_cmds.empty()) return false;
+    prog.cmds = std::move(best_cmds);
+    prog.analysed = false;
+    analyse(prog);
+    if (new_bytes) *new_bytes = best;
+    return true;
+}
+
+std::string program_text(const Program& p) {
+    std::ostringstream o;
+    o << "# version: 0.4.0\n";
+    auto lab = [](const std::vector<int64_t>& v) {
+        if (v.empty()) return std::string("0");
+        std::string s;
+        for (size_t i = 0; i < v.size(); ++i) s += (i ? "," : "") + std::to_string(v[i]);
+        return s;
+    };
+    for (const Cmd& c : p.cmds) {
+        switch (c.kind) {
+        case CMD_LOAD: o << "load " << c.name << " " << c.label << " " << lab(c.dims) << "\n"; break;
+        case CMD_OUTPUT: o << "output " << c.name << " " << c.idx << " " << c.dim << "\n"; break;
+        case CMD_VIEW: o << "view " << c.name << " " << c.a << " " << c.label << " " << c.idx << " " << c.dim << "\n"; break;
+        case CMD_NCON: o << "ncon " << c.name << " " << lab(c.cl) << " " << c.a << " " << lab(c.al) << " " << c.b << " " << lab(c.bl) << "\n"; break;
+        case CMD_SAVE: o << "save " << c.name << " " << c.a << "\n"; break;
+        }
+    }
+    return o.str();
+}
+
+}  // namespace qxb

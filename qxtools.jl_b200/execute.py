@@ -50,7 +50,7 @@ def _bitstrings_from_params(params: dict, max_amplitudes: Optional[int]):
 def execute(dsl_file: str, input_file: Optional[str] = None, param_file: Optional[str] = None,
             output_file: Optional[str] = None, use_mpi: bool = False, sub_comm_size: int = 1,
             use_gpu: bool = True, max_amplitudes: Optional[int] = None, max_slices: Optional[int] = None,
-            timings: bool = False, dtype: str = "c32", replan: int = 16):
+            timings: bool = False, dtype: str = "c32", replan: int = 64):
     """Returns ``OrderedDict{bitstring => amplitude}`` on rank 0 (None elsewhere)."""
     if not use_gpu:
         raise RuntimeError("qxb200 has no CPU path: use_gpu must be True")

@@ -60,14 +60,12 @@ class Graph:
         (host-side DSL -> DSL rewrite, exact; ``replan`` = number of candidate orders, see replan.py)."""
         g = cls(dtype)
         g.replan_info = None
-        if replan and replan > 0:
-            from .replan import replan_dsl
-            text, g.replan_info = replan_dsl(text, n_amp=replan_n_amp, candidates=max(1, int(round(replan))),
-                                             dtype=dtype)
         g.text = text
         b = text.encode()
         check(g._lib.qxb_graph_parse_dsl(g._h, b, len(b)))
         g.set_data(data)
+        if replan and replan > 0:
+            g.replan(max(1, int(round(replan))), replan_n_amp)
         return g
 
     @classmethod
@@ -136,6 +134,21 @@ class Graph:
         buf = C.create_string_buffer(need)
         check(self._lib.qxb_graph_describe(self._h, n_free, buf, need))
         return json.loads(buf.value.decode())
+
+    def replan(self, candidates: int = 24, n_amp: int = 1024) -> dict:
+        """In-library batch-aware re-planning (qxb_graph_replan); call before compile()."""
+        a, b = C.c_double(), C.c_double()
+        check(self._lib.qxb_graph_replan(self._h, candidates, n_amp, C.byref(a), C.byref(b)))
+        self.replan_info = {"replanned": b.value < a.value, "given_bytes": a.value, "bytes": b.value,
+                            "candidates": candidates, "n_amp_model": n_amp}
+        self.text = self.program_text()
+        return self.replan_info
+
+    def program_text(self) -> str:
+        need = check(self._lib.qxb_graph_program_text(self._h, None, 0))
+        buf = C.create_string_buffer(need)
+        check(self._lib.qxb_graph_program_text(self._h, buf, need))
+        return buf.value.decode()
 
     def describe_mask(self, free_mask: int) -> dict:
         need = check(self._lib.qxb_graph_describe_mask(self._h, free_mask, None, 0))

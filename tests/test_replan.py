@@ -67,3 +67,35 @@ def test_from_dsl_replan_flag(lib_built):
     # partition chooser is consistent: every rank gets the same kind of share
     kinds = {g.choose_partition(64, 4, r)[0] for r in range(4)}
     assert len(kinds) == 1
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 8, 2), (4, 4, 12, 4), (4, 5, 14, 5)])
+def test_in_library_replan_is_equivalent(lib_built, shape):
+    """qxb_graph_replan (C++, what Graph.from_dsl(replan=N) uses): same contract as replan_dsl."""
+    r, c, d, ns = shape
+    txt, data, bs = rqc_case(r, c, d, ns, n_amp=4)
+    g = Graph.from_dsl(txt, data, "c64")
+    info = g.replan(16, 64)
+    new = g.program_text()
+    assert info["replanned"] and info["bytes"] < info["given_bytes"]
+    assert _leaf_lines(new) == _leaf_lines(txt)
+    c0, c1 = orc.parse_dsl(txt), orc.parse_dsl(new)
+    assert np.allclose(orc.amplitudes(c1, data, bs), orc.amplitudes(c0, data, bs), atol=1e-15)
+    S = 2 ** ns
+    assert np.allclose(orc.amplitudes(c1, data, bs, slice_begin=1, slice_end=S - 1),
+                       orc.amplitudes(c0, data, bs, slice_begin=1, slice_end=S - 1), atol=1e-15)
+    assert np.allclose(em.amplitudes(g, data, bits_from_strings(bs, r * c), shuffle_seed=5),
+                       orc.amplitudes(c0, data, bs), atol=1e-14)
+    # seeded: the same call gives the same program
+    g2 = Graph.from_dsl(txt, data, "c64")
+    g2.replan(16, 64)
+    assert g2.program_text() == new
+
+
+def test_in_library_replan_keeps_programs_it_cannot_improve(lib_built):
+    txt, data = kat0()
+    g = Graph.from_dsl(txt, data)
+    info = g.replan(8, 4)
+    got = orc.amplitudes(orc.parse_dsl(g.program_text()), data, ["00", "11", "01", "10"])
+    assert np.allclose(got, [1 / np.sqrt(2), 1 / np.sqrt(2), 0, 0], atol=1e-15)
+    assert info["bytes"] <= info["given_bytes"]
