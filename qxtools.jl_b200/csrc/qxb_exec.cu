@@ -140,15 +140,8 @@ void upload_leaves(qxb_graph* g) {
         const HostData& h = it->second;
         std::vector<int64_t> dims;
         for (const Mode& m : d.modes) dims.push_back(m.full_ext);
-        // a rank-0 / all-ones-extent mismatch is tolerated only when shapes agree exactly
-        if (h.dims != dims) {
-            int64_t n1 = 1, n2 = 1;
-            for (auto x : h.dims) n1 *= x;
-            for (auto x : dims) n2 *= x;
-            if (n1 != n2 || h.dims.size() != dims.size())
-                throw Error(QXB_ERR_ARG, "load " + d.name + ": dims do not match the data of '" + d.data_label + "'");
+        if (h.dims != dims)
             throw Error(QXB_ERR_ARG, "load " + d.name + ": dims do not match the data of '" + d.data_label + "'");
-        }
         if (g->leafbuf.count(d.data_label)) continue;
         int span = 0;
         std::vector<int> pos(dims.size());
@@ -402,7 +395,7 @@ Variant* get_variant(qxb_graph* g, uint64_t free_mask) {
     if (it != g->variants.end()) return it->second.get();
     std::unique_ptr<Variant> v(new Variant());
     v->L = lower(g->prog, free_mask, !g->opts.sum_at_root);
-    plan_memory(v->L, 1);
+    plan_memory(v->L);
     build_templates(*v, g->dtype);
     const size_t es = g->es();
     v->const_arena.reserve(std::max<int64_t>(v->L.const_elems, 2) * es);
@@ -897,7 +890,7 @@ int64_t qxb_graph_describe(qxb_graph* g, int n_free, char* buf, int64_t buflen) 
         ensure_analysed(g);
         const int k = (int)g->prog.vars.size();
         Lowered L = lower(g->prog, low_mask(n_free < 0 || n_free > k ? k : n_free), !g->opts.sum_at_root);
-        plan_memory(L, 1);
+        plan_memory(L);
         std::string s = describe_json(g->prog, L);
         need = (int64_t)s.size() + 1;
         if (buf && buflen >= need) memcpy(buf, s.c_str(), need);
@@ -1044,7 +1037,7 @@ int64_t qxb_graph_describe_mask(qxb_graph* g, uint64_t free_mask, char* buf, int
         if (!g) throw Error(QXB_ERR_ARG, "null graph");
         ensure_analysed(g);
         Lowered L = lower(g->prog, free_mask, !g->opts.sum_at_root);
-        plan_memory(L, 1);
+        plan_memory(L);
         std::string s = describe_json(g->prog, L);
         need = (int64_t)s.size() + 1;
         if (buf && buflen >= need) memcpy(buf, s.c_str(), need);

@@ -133,11 +133,10 @@ struct Lowered {
     std::vector<LOp> ops;
     std::vector<int> output_leaves;          // LTensor indices materialised from the bitstrings
     int root = -1;
-    int root_missing_var_factor_bits = 0;    // unused
-    std::vector<int> root_vars;              // free vars present in the root layout, in layout order
+    std::vector<int> root_vars;              // batched variables still open in the root (summed by reduce_root)
     double root_scale = 1.0;                 // prod of extents of free vars the root does not depend on
-    // arena sizes in elements: const, block, and chunk = fixed + per_amp * n_amp
-    int64_t const_elems = 0, block_elems = 0, chunk_fixed_elems = 0, chunk_elems_per_amp = 0;
+    // arena sizes in elements: const, block, and chunk = per_amp * n_amp
+    int64_t const_elems = 0, block_elems = 0, chunk_elems_per_amp = 0;
 };
 
 // Lower for a given set of free (batched) slice variables.
@@ -152,8 +151,9 @@ double lowered_cost_bytes(const Lowered& L, double n_amp, double elem_bytes);
 bool replan(Program& p, int candidates, uint64_t seed, double n_amp, bool early_sum, double* given_bytes,
             double* new_bytes, double elem_bytes);
 std::string program_text(const Program& p);
-// Plan arena offsets for a batch of n_amp bitstrings (fills LTensor::offset and the arena sizes).
-void plan_memory(Lowered& L, int64_t n_amp);
+// Plan arena offsets (fills LTensor::offset, the arena sizes and the write-after-read edges).
+// Chunk-phase offsets are per bitstring row and scale with the batch at launch time.
+void plan_memory(Lowered& L);
 std::string describe_json(const Program& p, const Lowered& L);
 
 inline int ceil_log2(int64_t x) { int b = 0; while ((int64_t(1) << b) < x) ++b; return b; }

@@ -484,7 +484,7 @@ struct Arena {
 inline int64_t unit_elems(const LTensor& t) { return std::max<int64_t>(2, int64_t(1) << t.span_bits); }
 }  // namespace
 
-void plan_memory(Lowered& L, int64_t /*n_amp*/) {
+void plan_memory(Lowered& L) {
     // Chunk-phase tensors all carry the amplitude axis, so their offsets are planned
     // per amplitude row and scaled by the batch size at launch time.
     //
@@ -521,7 +521,6 @@ void plan_memory(Lowered& L, int64_t /*n_amp*/) {
     }
     L.const_elems = ar[PH_CONST].peak;
     L.block_elems = ar[PH_BLOCK].peak;
-    L.chunk_fixed_elems = 0;
     L.chunk_elems_per_amp = ar[PH_CHUNK].peak;
 }
 

@@ -63,8 +63,14 @@ WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
 
 def ncu_reports():
     out = []
-    for rep in sorted(glob.glob(os.path.join(OUT, f"prof_{tag}_*.ncu-rep"))):
-        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    reps = sorted(glob.glob(os.path.join(OUT, f"prof_{tag}_*.ncu-rep")))
+    csvs = sorted(glob.glob(os.path.join(OUT, f"prof_{tag}_*.raw.csv")))     # `ncu -i X --page raw --csv` done on the box
+    done = {os.path.basename(c)[:-8] for c in csvs}
+    for rep in csvs + [r for r in reps if os.path.basename(r)[:-8] not in done]:
+        if rep.endswith(".csv"):
+            txt = open(rep).read()
+        else:
+            txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(txt.splitlines()))
         if len(rows) < 3:
             continue
