@@ -50,7 +50,7 @@ def _bitstrings_from_params(params: dict, max_amplitudes: Optional[int]):
 def execute(dsl_file: str, input_file: Optional[str] = None, param_file: Optional[str] = None,
             output_file: Optional[str] = None, use_mpi: bool = False, sub_comm_size: int = 1,
             use_gpu: bool = True, max_amplitudes: Optional[int] = None, max_slices: Optional[int] = None,
-            timings: bool = False, dtype: str = "c32", replan: int = 64):
+            timings: bool = False, dtype: str = "c32", replan: int = -1):
     """Returns ``OrderedDict{bitstring => amplitude}`` on rank 0 (None elsewhere)."""
     if not use_gpu:
         raise RuntimeError("qxb200 has no CPU path: use_gpu must be True")
@@ -77,11 +77,12 @@ def execute(dsl_file: str, input_file: Optional[str] = None, param_file: Optiona
             td.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
         rank, world = td.get_rank(), td.get_world_size()
     init(int(os.environ.get("LOCAL_RANK", "0")))
-    g = Graph.from_dsl(text, data, dtype, replan=replan).compile()
+    bitstrings = _bitstrings_from_params(params, max_amplitudes)
+    n_model = len(bitstrings) if bitstrings is not None else 1024
+    g = Graph.from_dsl(text, data, dtype, replan=replan, replan_n_amp=max(1, n_model)).compile()
     t["Create Context"] = time.perf_counter() - t0
 
     t0 = time.perf_counter()
-    bitstrings = _bitstrings_from_params(params, max_amplitudes)
     n_slices = g.n_slices if max_slices is None else min(max_slices, g.n_slices)
     if bitstrings is None:
         # Rejection sampling: every candidate batch is one amplitudes call on this rank's GPU

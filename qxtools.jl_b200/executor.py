@@ -57,7 +57,8 @@ class Graph:
     def from_dsl(cls, text: str, data: Dict[str, np.ndarray], dtype: str = "c64", replan: float = 0.0,
                  replan_n_amp: int = 1024) -> "Graph":
         """``replan`` > 0: re-derive the contraction order for batched execution first
-        (host-side DSL -> DSL rewrite, exact; ``replan`` = number of candidate orders, see replan.py)."""
+        (qxb_graph_replan, exact; ``replan`` = number of candidate orders); ``replan`` < 0: decide
+        from the cost model whether the search can pay for itself."""
         g = cls(dtype)
         g.replan_info = None
         g.text = text
@@ -66,6 +67,12 @@ class Graph:
         g.set_data(data)
         if replan and replan > 0:
             g.replan(max(1, int(round(replan))), replan_n_amp)
+        elif replan and replan < 0:
+            # auto: re-plan only when the modelled run time (bytes / ~5 TB/s) can pay for the search
+            # (~20 ms per candidate order)
+            t_run = g.cost_bytes(replan_n_amp) / 5e12
+            if t_run > 0.02:
+                g.replan(int(min(128, max(8, t_run / 0.02))), replan_n_amp)
         return g
 
     @classmethod
