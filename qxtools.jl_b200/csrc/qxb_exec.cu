@@ -110,6 +110,7 @@ struct qxb_graph {
     std::vector<EventPair> events;
     size_t events_used = 0;
     std::map<StepKey, StepGraph> step_graphs;
+    std::map<uint64_t, int64_t> ws_cache;       // free-variable mask -> workspace bytes per bitstring row
     void drop_step_graphs() {
         for (auto& kv : step_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         step_graphs.clear();
@@ -444,17 +445,53 @@ struct StepPlan {
     int64_t chunk = 0;
 };
 
+int64_t hbm_budget(qxb_graph* g) {
+    if (g->opts.hbm_budget_bytes > 0) return g->opts.hbm_budget_bytes;
+    size_t free_b = 0, total_b = 0;
+    CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+    return (int64_t)(0.6 * (double)(free_b + g->block_arena.bytes + g->chunk_arena.bytes));
+}
+
+// Workspace (bytes) of one bitstring row + the block arena when the variables in `mask` are batched.
+// Pure host computation (lowering + arena plan), cached per mask.
+int64_t workspace_per_amp(qxb_graph* g, uint64_t mask) {
+    auto it = g->ws_cache.find(mask);
+    if (it != g->ws_cache.end()) return it->second;
+    Lowered L = lower(g->prog, mask, !g->opts.sum_at_root);
+    plan_memory(L);
+    const int64_t es = (int64_t)g->es();
+    const int64_t b = std::max<int64_t>(L.block_elems, 2) * es + std::max<int64_t>(L.chunk_elems_per_amp, 2) * es;
+    g->ws_cache[mask] = b;
+    return b;
+}
+
+// Batching every slice variable can need more HBM than there is (the sliced modes come back as
+// batch bits).  Fix variables -- the one whose fixing shrinks the workspace most first -- and loop
+// over their values until one bitstring row fits the budget.
+void expand_blocks(qxb_graph* g, const Block& blk, int64_t budget, std::vector<Block>& out) {
+    if (workspace_per_amp(g, blk.free_mask) <= budget || blk.free_mask == 0) { out.push_back(blk); return; }
+    const int k = (int)g->prog.vars.size();
+    int best = -1; int64_t best_ws = 0;
+    for (int v = 0; v < k; ++v) {
+        if (!((blk.free_mask >> v) & 1ull)) continue;
+        const int64_t ws = workspace_per_amp(g, blk.free_mask & ~(1ull << v));
+        if (best < 0 || ws < best_ws) { best = v; best_ws = ws; }
+    }
+    for (int64_t val = 0; val < g->prog.vars[best].dim; ++val) {
+        Block sub = blk;
+        sub.free_mask &= ~(1ull << best);
+        sub.vals[best] = val;
+        expand_blocks(g, sub, budget, out);
+    }
+}
+
 // Everything that may allocate, synchronise or query the device happens here,
 // before any node is built.
 StepPlan prepare_step(qxb_graph* g, std::vector<Block> blocks, int64_t n_amp) {
     StepPlan sp;
-    sp.blocks = std::move(blocks);
-    size_t free_b = 0, total_b = 0;
-    CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
     const size_t es = g->es();
-    int64_t budget = g->opts.hbm_budget_bytes > 0
-                         ? g->opts.hbm_budget_bytes
-                         : (int64_t)(0.6 * (double)(free_b + g->block_arena.bytes + g->chunk_arena.bytes));
+    const int64_t budget = hbm_budget(g);
+    for (const Block& b : blocks) expand_blocks(g, b, budget, sp.blocks);
     int64_t chunk = n_amp;
     if (g->opts.amp_batch > 0) chunk = std::min<int64_t>(chunk, g->opts.amp_batch);
     int64_t max_block = 2 * (int64_t)es, max_per_amp = 2 * (int64_t)es;
@@ -649,7 +686,7 @@ void run_blocks(qxb_graph* g, std::vector<Block> blocks, StepKey key, const uint
     StepPlan sp = prepare_step(g, std::move(blocks), n_amp);
     std::vector<Node> nodes = build_step(g, sp, d_bits, n_amp, d_out);
     account(g, nodes);
-    if (!use_graph) { launch_serial(g, nodes); return; }
+    if (!use_graph || nodes.size() > 100000) { launch_serial(g, nodes); return; }   // huge steps: not worth a graph
     if (g->step_graphs.size() >= 32) g->drop_step_graphs();
     StepGraph sg;
     sg.exec = instantiate(nodes);

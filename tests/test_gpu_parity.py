@@ -246,3 +246,20 @@ def test_execute_rejection_sampler(gpu, tmp_path):
     assert all(abs(abs(a) - 1 / np.sqrt(2)) < 1e-12 for a in res.values())
     out = np.load(prefix + "_out.npz")
     assert len(out["bitstrings"]) == 12 and abs(float(out["M"]) - 16.0) < 1e-12
+
+
+def test_variables_fixed_automatically_to_fit_hbm(gpu):
+    """When batching every slice variable needs more workspace than the budget allows, the
+    executor fixes variables (loops over their values) instead of failing."""
+    txt, data, bs = rqc_case(4, 4, 12, 4, n_amp=5)
+    ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
+    g0 = Graph.from_dsl(txt, data, "c64")
+    d = g0.describe()
+    need = 16 * (d["arena_elems"]["chunk_per_amp"] + d["arena_elems"]["block"])
+    for frac in (0.7, 0.4):
+        g = Graph.from_dsl(txt, data, "c64").compile(hbm_budget_bytes=int(frac * need))
+        out = g.amplitudes(bs)
+        st = g.stats()
+        assert st["n_blocks"] > 1 and st["amp_batch"] >= 1
+        assert rel_err(out, ref, 16) < 1e-10
+        assert rel_err(g.amplitudes(bs, 3, 11), orc.amplitudes(orc.parse_dsl(txt), data, bs, slice_begin=3, slice_end=11), 16) < 1e-10
