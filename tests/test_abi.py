@@ -103,3 +103,31 @@ def test_describe_split_is_consistent(lib_built):
         # fully fixed: nothing is batched over slices, so no op has more bits than the unsliced tensors
         if n_free == 0:
             assert max(op["nC"] for op in d["ops"]) <= 8
+
+
+def _build_consumer(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "abi_consumer")
+    pkg = os.path.join(ROOT, "qxtools.jl_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "abi_consumer.c"), "-o", exe, "-L", pkg, "-lqxb200", "-lm",
+                    f"-Wl,-rpath,{pkg}"], check=True)
+    return exe
+
+
+def test_plain_c_consumer_host_side(lib_built, tmp_path):
+    """The header is valid C99 and the ABI is usable without Python (what a Julia ccall sees)."""
+    import subprocess
+    exe = _build_consumer(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "abi consumer ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_consumer_on_gpu(gpu, tmp_path):
+    import subprocess
+    exe = _build_consumer(tmp_path)
+    r = subprocess.run([exe, "gpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "gpu amplitudes ok" in r.stdout
