@@ -149,6 +149,114 @@ void plan_from_order(const Net& net, const std::vector<int>& order, std::vector<
     root = rest[0];
 }
 
+
+// ---- local refinement: tree rotations  (A.B).E -> (A.E).B  -------------------------------
+// Y = ncon(D; X, E) with X = ncon(X; A, B) used only by Y.  If every label contracted at Y lives
+// on A's side (none on B), E can be applied to A first: A' = ncon(A, E), D = ncon(A', B).  Exact
+// (sum-product re-association); accepted only when the executor's cost model gets cheaper.
+bool rotate(std::vector<Cmd>& cmds, size_t yi, int x_pos /*0: X is operand a, 1: operand b*/, bool toward_a,
+            const std::map<std::string, int>& uses) {
+    const Cmd& Y = cmds[yi];
+    if (Y.kind != CMD_NCON) return false;
+    const std::string& xn = x_pos == 0 ? Y.a : Y.b;
+    const std::vector<int64_t>& xl = x_pos == 0 ? Y.al : Y.bl;
+    const std::string& en = x_pos == 0 ? Y.b : Y.a;
+    const std::vector<int64_t>& el = x_pos == 0 ? Y.bl : Y.al;
+    size_t xi = cmds.size();
+    for (size_t i = 0; i < yi; ++i) if (cmds[i].kind == CMD_NCON && cmds[i].name == xn) xi = i;
+    if (xi == cmds.size()) return false;
+    auto u = uses.find(xn);
+    if (u == uses.end() || u->second != 1) return false;
+    const Cmd& X = cmds[xi];
+    if (X.cl.size() != xl.size()) return false;
+    const std::string& an = toward_a ? X.a : X.b;
+    const std::string& bn = toward_a ? X.b : X.a;
+    const std::vector<int64_t>& al = toward_a ? X.al : X.bl;
+    const std::vector<int64_t>& bl = toward_a ? X.bl : X.al;
+    if (an == en || bn == en) return false;
+    int64_t M = 1;
+    for (int64_t l : Y.cl) M = std::max(M, l + 1);
+    for (int64_t l : xl) M = std::max(M, l + 1);
+    for (int64_t l : el) M = std::max(M, l + 1);
+    std::map<int64_t, int64_t> tr;
+    for (size_t j = 0; j < X.cl.size(); ++j) tr[X.cl[j]] = xl[j];
+    auto T = [&](const std::vector<int64_t>& ls) {
+        std::vector<int64_t> out;
+        for (int64_t l : ls) { auto it = tr.find(l); out.push_back(it != tr.end() ? it->second : l + M); }
+        return out;
+    };
+    const std::vector<int64_t> aU = T(al), bU = T(bl);
+    auto in = [](const std::vector<int64_t>& v, int64_t x) { return std::find(v.begin(), v.end(), x) != v.end(); };
+    for (int64_t l : xl)
+        if (in(el, l) && !in(Y.cl, l) && in(bU, l)) return false;       // contracted at Y but also on B's side
+    std::vector<int64_t> outp;
+    for (int64_t l : aU) {
+        const bool summed = in(el, l) && !in(Y.cl, l) && !in(bU, l);
+        if (!summed) outp.push_back(l);
+    }
+    for (int64_t l : el)
+        if (!in(aU, l) && (in(Y.cl, l) || in(bU, l)) && !in(outp, l)) outp.push_back(l);
+    Cmd c1; c1.kind = CMD_NCON; c1.name = xn + "r"; c1.cl = outp; c1.a = an; c1.al = aU; c1.b = en; c1.bl = el;
+    Cmd c2; c2.kind = CMD_NCON; c2.name = Y.name; c2.cl = Y.cl; c2.a = c1.name; c2.al = outp; c2.b = bn; c2.bl = bU;
+    for (const Cmd& c : cmds) if (c.name == c1.name && c.kind != CMD_SAVE) return false;    // name clash
+    std::vector<Cmd> out;
+    for (size_t i = 0; i < cmds.size(); ++i) {
+        if (i == xi) continue;
+        if (i == yi) { out.push_back(c1); out.push_back(c2); continue; }
+        out.push_back(cmds[i]);
+    }
+    cmds.swap(out);
+    return true;
+}
+
+double program_cost(const std::vector<Cmd>& cmds, double n_amp, bool early_sum, double elem_bytes) {
+    Program cand;
+    cand.cmds = cmds;
+    analyse(cand);
+    Lowered L = lower(cand, low_mask((int)cand.vars.size()), early_sum);
+    return lowered_cost_bytes(L, n_amp, elem_bytes);
+}
+
+// Greedy descent over rotations of the largest nodes; returns the improved cost.
+double refine_by_rotations(std::vector<Cmd>& cmds, double cost, double n_amp, bool early_sum, double elem_bytes,
+                           int max_accept) {
+    for (int acc = 0; acc < max_accept; ++acc) {
+        Program cur;
+        cur.cmds = cmds;
+        analyse(cur);
+        Lowered L = lower(cur, low_mask((int)cur.vars.size()), early_sum);
+        std::map<std::string, int> uses;
+        for (const Cmd& c : cmds)
+            if (c.kind == CMD_NCON) { uses[c.a]++; uses[c.b]++; } else if (c.kind == CMD_VIEW || c.kind == CMD_SAVE) uses[c.a]++;
+        // candidates: the nodes that move the most bytes
+        std::vector<std::pair<double, std::string>> big;
+        for (const LOp& op : L.ops) {
+            if (op.phase == PH_CONST) continue;
+            const double w = op.elems_c * (L.tensors[op.c].amp ? n_amp : 1) + op.elems_a * (L.tensors[op.a].amp ? n_amp : 1) +
+                             op.elems_b * (L.tensors[op.b].amp ? n_amp : 1);
+            big.push_back({-w, op.name});
+        }
+        std::sort(big.begin(), big.end());
+        if (big.size() > 48) big.resize(48);
+        bool improved = false;
+        for (auto& cand : big) {
+            size_t yi = cmds.size();
+            for (size_t i = 0; i < cmds.size(); ++i) if (cmds[i].kind == CMD_NCON && cmds[i].name == cand.second) yi = i;
+            if (yi == cmds.size()) continue;
+            for (int variant = 0; variant < 4 && !improved; ++variant) {
+                std::vector<Cmd> trial = cmds;
+                if (!rotate(trial, yi, variant & 1, (variant & 2) == 0, uses)) continue;
+                double c;
+                try { c = program_cost(trial, n_amp, early_sum, elem_bytes); } catch (const Error&) { continue; }
+                if (c < cost * 0.998) { cmds.swap(trial); cost = c; improved = true; }
+            }
+            if (improved) break;
+        }
+        if (!improved) break;
+    }
+    return cost;
+}
+
 }  // namespace
 
 bool replan(Program& prog, int candidates, uint64_t seed, double n_amp, bool early_sum, double* given_bytes,
@@ -302,7 +410,12 @@ bool replan(Program& prog, int candidates, uint64_t seed, double n_amp, bool ear
             continue;                           // a candidate the lowering rejects is simply skipped
         }
     }
-    if (best_cmds.empty()) return false;
+    if (best_cmds.empty()) best_cmds = prog.cmds;          // nothing cheaper among the orders: refine the given tree
+    try {
+        best = refine_by_rotations(best_cmds, best, n_amp, early_sum, elem_bytes, 48);
+    } catch (const Error&) {
+    }
+    if (!(best < base)) return false;
     prog.cmds = std::move(best_cmds);
     prog.analysed = false;
     analyse(prog);
