@@ -1005,8 +1005,12 @@ int qxb_amplitudes(qxb_graph* g, const uint8_t* bits, int64_t n_amp, int64_t s0,
         if (!g->compiled) throw Error(QXB_ERR_STATE, "graph not compiled");
         ensure_init();
         const size_t nb = (size_t)n_amp * std::max(1, g->prog.n_outputs);
-        for (size_t i = 0; i < (size_t)n_amp * g->prog.n_outputs; ++i)
-            if (bits[i] > 3) throw Error(QXB_ERR_ARG, "bitstring entries must be 0, 1, 2 ('+') or 3 ('-')");
+        {
+            unsigned char seen = 0;                       // OR-reduction: vectorises, unlike an early-exit loop
+            const size_t nbits = (size_t)n_amp * g->prog.n_outputs;
+            for (size_t i = 0; i < nbits; ++i) seen |= bits[i];
+            if (seen > 3) throw Error(QXB_ERR_ARG, "bitstring entries must be 0, 1, 2 ('+') or 3 ('-')");
+        }
         cudaStream_t st = stream();
         g->d_bits.reserve(nb);
         g->d_out.reserve((size_t)n_amp * g->es());
@@ -1035,8 +1039,12 @@ int qxb_amplitudes_subspace(qxb_graph* g, const uint8_t* bits, int64_t n_amp, co
             if (g->opts.profile) { CUDA_OK(cudaStreamSynchronize(st)); collect_profile(g); }
             return;
         }
-        for (size_t i = 0; i < (size_t)n_amp * g->prog.n_outputs; ++i)
-            if (bits[i] > 3) throw Error(QXB_ERR_ARG, "bitstring entries must be 0, 1, 2 ('+') or 3 ('-')");
+        {
+            unsigned char seen = 0;                       // OR-reduction: vectorises, unlike an early-exit loop
+            const size_t nbits = (size_t)n_amp * g->prog.n_outputs;
+            for (size_t i = 0; i < nbits; ++i) seen |= bits[i];
+            if (seen > 3) throw Error(QXB_ERR_ARG, "bitstring entries must be 0, 1, 2 ('+') or 3 ('-')");
+        }
         g->d_bits.reserve((size_t)n_amp * std::max(1, g->prog.n_outputs));
         g->d_out.reserve((size_t)n_amp * g->es());
         if (g->prog.n_outputs > 0)
