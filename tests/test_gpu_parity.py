@@ -263,3 +263,30 @@ def test_variables_fixed_automatically_to_fit_hbm(gpu):
         assert st["n_blocks"] > 1 and st["amp_batch"] >= 1
         assert rel_err(out, ref, 16) < 1e-10
         assert rel_err(g.amplitudes(bs, 3, 11), orc.amplitudes(orc.parse_dsl(txt), data, bs, slice_begin=3, slice_end=11), 16) < 1e-10
+
+
+def test_undecomposed_gates(gpu):
+    """decompose=false keeps 2-qubit gates as rank-4 tensors (test/test_tn_conversion.jl:10-12)."""
+    circ = q.create_rqc_circuit(3, 3, 8, 9)
+    txt, data, bs = circuit_case(circ, n_slice=2, decompose=False, n_amp=6)
+    ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
+    for replan in (0, 8):
+        g = Graph.from_dsl(txt, data, "c64", replan=replan, replan_n_amp=8).compile()
+        assert rel_err(g.amplitudes(bs), ref, 9) < 1e-10
+
+
+def test_network_without_outputs(gpu):
+    """A closed network with no `output` statement: one value, whatever bitstrings are passed."""
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(2, 2, 2)) + 1j * rng.normal(size=(2, 2, 2))
+    B = rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2))
+    txt = ("# version: 0.4.0\nload a dA 2,2,2\nview a_s a v1 3 2\nload b dB 2,2\nload c dB 2,2\nview c_s c v1 1 2\n"
+           "ncon ab 2,3 a_s 1,2,3 b 1,2\nncon r 0 ab 2,3 c_s 3,2\nsave output r\n")
+    data = {"dA": A, "dB": B}
+    ref = orc.amplitudes(orc.parse_dsl(txt), data, ["", "", ""])
+    g = Graph.from_dsl(txt, data, "c64").compile()
+    assert g.n_outputs == 0 and g.n_slices == 2
+    out = g.amplitudes(np.zeros((3, 0), dtype=np.uint8))
+    assert np.allclose(out, ref, atol=1e-12)
+    assert np.allclose(g.amplitudes(np.zeros((3, 0), dtype=np.uint8), 1, 2),
+                       orc.amplitudes(orc.parse_dsl(txt), data, ["", "", ""], slice_begin=1, slice_end=2), atol=1e-12)
