@@ -40,6 +40,9 @@ WORKLOADS = {
     "rqc_4x4_d12_c64_s16": dict(rows=4, cols=4, depth=12, n_slice=4, dtype="c64", seed=42),
     # BASELINE.json configs[1]: QFT on 20 qubits, 1024 bitstrings, no slicing
     "qft_20_unsliced": dict(qft=20, rows=20, cols=1, n_slice=0, dtype="c64", seed=42),
+    # towards configs[4]: Sycamore-like 53 qubits (fSim, extent-4 bonds), depth 7, ComplexF32, 8 sliced bonds.
+    # GEMM-shaped nodes (K up to 512): compute-bound, unlike the RQC grids.  Depth 12 needs a stronger planner.
+    "sycamore53_d7_c32": dict(sycamore=7, rows=53, cols=1, n_slice=8, dtype="c32", seed=1),
 }
 DEFAULT_WORKLOAD = "rqc_7x7_d20_c64_s4096"
 
@@ -54,6 +57,7 @@ def build_workload(name):
         data = dict(np.load(cache + ".npz"))
     else:
         circ = (q.create_qft_circuit(w["qft"]) if "qft" in w else
+                q.create_sycamore_like_circuit(w["sycamore"], seed=w["seed"]) if "sycamore" in w else
                 q.create_rqc_circuit(w["rows"], w["cols"], w["depth"], w["seed"]))
         tnc = q.convert_to_tnc(circ)
         bg, plan, meta = q.contraction_scheme(tnc, w["n_slice"], time=0, seed=w["seed"])

@@ -290,3 +290,16 @@ def test_network_without_outputs(gpu):
     assert np.allclose(out, ref, atol=1e-12)
     assert np.allclose(g.amplitudes(np.zeros((3, 0), dtype=np.uint8), 1, 2),
                        orc.amplitudes(orc.parse_dsl(txt), data, ["", "", ""], slice_begin=1, slice_end=2), atol=1e-12)
+
+
+@pytest.mark.parametrize("dtype", ["c64", "c32"])
+def test_fsim_circuit_extent4_bonds(gpu, dtype):
+    circ = q.create_sycamore_like_circuit(4, seed=3, n_qubits=12)
+    txt, data, bs = circuit_case(circ, n_slice=3, n_amp=9)
+    cmds = orc.parse_dsl(txt)
+    ref = orc.amplitudes(cmds, data, bs)
+    for replan in (0, 8):
+        g = Graph.from_dsl(txt, data, dtype, replan=replan, replan_n_amp=16).compile()
+        assert rel_err(g.amplitudes(bs), ref, 12) < TOL[dtype]
+        S = g.n_slices
+        assert rel_err(g.amplitudes(bs, 5, S - 3), orc.amplitudes(cmds, data, bs, slice_begin=5, slice_end=S - 3), 12) < TOL[dtype]

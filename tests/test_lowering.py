@@ -176,3 +176,22 @@ def test_subspace_partition_sums_to_full(lib_built):
         assert np.allclose(total, ref, atol=1e-14)
     assert g.partition_vars(1) == []
     assert g.partition_vars(3) == []          # extents are all 2: 3 ranks cannot be factored
+
+
+def test_fsim_circuit_extent4_bonds(lib_built):
+    """Sycamore-like fSim gates have operator-Schmidt rank 4: extent-4 bonds and extent-4 slice
+    variables (two address bits per mode)."""
+    circ = q.create_sycamore_like_circuit(4, seed=3, n_qubits=12)
+    tnc = q.convert_to_tnc(circ)
+    assert sorted(set(tnc.index_dim.values())) == [2, 4]
+    bg, plan, _ = q.contraction_scheme(tnc, 3, time=0)
+    cg = q.build_compute_graph(tnc, plan, bg)
+    txt, data = cg.dsl(), dict(cg.tensors)
+    bs = list(q.amplitudes_uniform(12, 1, 3))
+    g = Graph.from_dsl(txt, data)
+    assert 4 in g.slice_dims
+    ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
+    assert np.allclose(em.amplitudes(g, data, bits_from_strings(bs, 12), shuffle_seed=2), ref, atol=1e-14)
+    S = g.n_slices
+    assert np.allclose(em.amplitudes(g, data, bits_from_strings(bs, 12), 5, S - 3),
+                       orc.amplitudes(orc.parse_dsl(txt), data, bs, slice_begin=5, slice_end=S - 3), atol=1e-14)

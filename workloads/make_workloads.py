@@ -18,7 +18,9 @@ import bench                      # noqa: E402
 import qxb200 as q                # noqa: E402
 
 for name, w in bench.WORKLOADS.items():
-    circ = q.create_qft_circuit(w["qft"]) if "qft" in w else q.create_rqc_circuit(w["rows"], w["cols"], w["depth"], w["seed"])
+    circ = (q.create_qft_circuit(w["qft"]) if "qft" in w else
+            q.create_sycamore_like_circuit(w["sycamore"], seed=w["seed"]) if "sycamore" in w else
+            q.create_rqc_circuit(w["rows"], w["cols"], w["depth"], w["seed"]))
     n_q = circ.num_qubits
     prefix = os.path.join(ROOT, "workloads", name)
     q.generate_simulation_files(circ, prefix, w["n_slice"], seed=w["seed"], time=0,
