@@ -51,6 +51,8 @@ typedef struct qxb_options {
     int32_t sum_at_root;       /* 1 = keep every batched slice variable open until the root and sum there;
                                   0 (default) = sum each one at the lowest node covering all its leaves   */
     int32_t no_smem_stage;     /* 1 = never use the shared-memory-staged kernel for broadcast-type nodes */
+    int32_t no_gemm;           /* 1 = never use the tiled GEMM kernel for GEMM-shaped nodes               */
+    int32_t reserved;
 } qxb_options;
 
 /* library */

@@ -35,7 +35,8 @@ class QxbError(RuntimeError):
 class Options(C.Structure):
     _fields_ = [("hbm_budget_bytes", C.c_int64), ("amp_batch", C.c_int64),
                 ("profile", C.c_int32), ("no_cuda_graph", C.c_int32),
-                ("sum_at_root", C.c_int32), ("no_smem_stage", C.c_int32)]
+                ("sum_at_root", C.c_int32), ("no_smem_stage", C.c_int32),
+                ("no_gemm", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):

@@ -79,6 +79,8 @@ struct Variant {
     DevBuf const_arena;
     DevBuf outleaf_desc;
     std::vector<OpParams> tmpl;          // per op, pointers unset
+    std::vector<GemmParams> gtmpl;       // per op: tiled-GEMM parameters (valid when gemm_tmb > 0)
+    std::vector<int> gemm_tmb, gemm_tnb;
     std::vector<OpProfile> prof;
 };
 
@@ -192,6 +194,8 @@ char* tensor_ptr(const RunCtx& c, const LTensor& T) {
 // the address maps accordingly (see contract_kernel).
 void build_templates(Variant& v, int dtype) {
     v.tmpl.resize(v.L.ops.size());
+    v.gtmpl.resize(v.L.ops.size());
+    v.gemm_tmb.assign(v.L.ops.size(), 0); v.gemm_tnb.assign(v.L.ops.size(), 0);
     v.prof.assign(v.L.ops.size(), OpProfile{});
     for (size_t i = 0; i < v.L.ops.size(); ++i) {
         const LOp& op = v.L.ops[i];
@@ -292,6 +296,54 @@ void build_templates(Variant& v, int dtype) {
             for (auto& s : op.segKB) b |= (long long)((k >> s.src) & ((1 << s.len) - 1)) << s.dst;
             p.ktabA[k] = a; p.ktabB[k] = b;
         }
+        // ---- GEMM-shaped node?  (K >= 2^kcb, >= 5 M-only and >= 5 N-only bits, spans <= 2^30)
+        const int kcb = gemm_kcb(dtype);
+        std::vector<int> mall, nall;
+        for (int b = 0; b < nC; ++b) {
+            if (mapA[b] >= 0 && mapB[b] < 0) mall.push_back(b);
+            else if (mapB[b] >= 0 && mapA[b] < 0) nall.push_back(b);
+        }
+        const LTensor &TA = v.L.tensors[op.a], &TB = v.L.tensors[op.b];
+        if (op.nK >= kcb && mall.size() >= 5 && nall.size() >= 5 && nC <= 30 && TA.span_bits <= 30 && TB.span_bits <= 30) {
+            GemmParams& q = v.gtmpl[i];
+            memset(&q, 0, sizeof(q));
+            const int tmb = (int)std::min<size_t>(6, mall.size()), tnb = (int)std::min<size_t>(6, nall.size());
+            // tile bits: the M-only (N-only) bits that sit lowest in A (B): ascending operand addresses per load
+            std::sort(mall.begin(), mall.end(), [&](int x, int y) { return mapA[x] < mapA[y]; });
+            std::sort(nall.begin(), nall.end(), [&](int x, int y) { return mapB[x] < mapB[y]; });
+            std::vector<int> mt(mall.begin(), mall.begin() + tmb), nt(nall.begin(), nall.begin() + tnb);
+            std::vector<long long> kposA(op.nK, 0), kposB(op.nK, 0);
+            for (auto& s : op.segKA) for (int b = 0; b < s.len; ++b) kposA[s.src + b] = 1ll << (s.dst + b);
+            for (auto& s : op.segKB) for (int b = 0; b < s.len; ++b) kposB[s.src + b] = 1ll << (s.dst + b);
+            std::vector<std::pair<long long, int>> la, lb;        // (global offset, smem contribution)
+            for (int t = 0; t < tmb; ++t) la.push_back({1ll << mapA[mt[t]], 1 << t});
+            for (int c = 0; c < kcb; ++c) la.push_back({kposA[c], (1 << c) << tmb});
+            for (int t = 0; t < tnb; ++t) lb.push_back({1ll << mapB[nt[t]], 1 << t});
+            for (int c = 0; c < kcb; ++c) lb.push_back({kposB[c], (1 << c) << tnb});
+            std::sort(la.begin(), la.end()); std::sort(lb.begin(), lb.end());
+            for (size_t j = 0; j < la.size(); ++j) { q.aLoadOff[j] = la[j].first; q.aLoadSm[j] = la[j].second; }
+            for (size_t j = 0; j < lb.size(); ++j) { q.bLoadOff[j] = lb[j].first; q.bLoadSm[j] = lb[j].second; }
+            for (int t = 0; t < tmb; ++t) q.cM[t] = 1ll << mt[t];
+            for (int t = 0; t < tnb; ++t) q.cN[t] = 1ll << nt[t];
+            std::vector<bool> tile_bit(nC, false);
+            for (int b : mt) tile_bit[b] = true;
+            for (int b : nt) tile_bit[b] = true;
+            std::vector<std::pair<int, std::pair<int, int>>> gah, gbh, gch;
+            int gh = 0;
+            for (int b = 0; b < nC; ++b) {
+                if (tile_bit[b]) continue;
+                gch.push_back({gh, {b, 1}});
+                if (mapA[b] >= 0) gah.push_back({gh, {mapA[b], 1}});
+                if (mapB[b] >= 0) gbh.push_back({gh, {mapB[b], 1}});
+                ++gh;
+            }
+            q.hb = gh; q.nK = op.nK;
+            q.nsAhi = merge(gah, q.sAhi, kMaxSeg, op.name); q.nsBhi = merge(gbh, q.sBhi, kMaxSeg, op.name);
+            q.nsChi = merge(gch, q.sChi, kMaxSeg, op.name);
+            q.nkA = p.nkA; q.nkB = p.nkB;
+            memcpy(q.kA, p.kA, sizeof(q.kA)); memcpy(q.kB, p.kB, sizeof(q.kB));
+            if (gemm_func(dtype, tmb, tnb)) { v.gemm_tmb[i] = tmb; v.gemm_tnb[i] = tnb; }
+        }
     }
 }
 
@@ -338,6 +390,22 @@ Node contract_node(const RunCtx& c, int i) {
     const long long cap = (long long)g_num_sms * 8;
     Node n;
     const double outputs = (double)p.U * std::ldexp(1.0, p.nC);
+    if (!g->opts.no_gemm && c.v->gemm_tmb[i] > 0 && outputs >= 65536.0) {
+        // GEMM-shaped node: shared-memory-tiled FMA GEMM
+        GemmParams q = c.v->gtmpl[i];
+        q.A = p.A; q.B = p.B; q.C = p.C; q.sUA = p.sUA; q.sUB = p.sUB; q.sUC = p.sUC; q.U = p.U;
+        q.tiles = (long long)p.U << q.hb;
+        const int tmb = c.v->gemm_tmb[i], tnb = c.v->gemm_tnb[i];
+        n.func = gemm_func(g->dtype, tmb, tnb);
+        n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(q.tiles, (long long)g_num_sms * 2)));
+        n.block = dim3(1u << (tmb + tnb - 4));
+        n.arg(q);
+        n.variant = c.variant_key; n.op = i;
+        const double u = (double)p.U;
+        n.flops = 8.0 * op.macs_per_amp * u;
+        n.bytes = (double)g->es() * (op.elems_a * (A.amp ? c.n : 1) + op.elems_b * (B.amp ? c.n : 1) + op.elems_c * u);
+        return n;
+    }
     if (p.nK >= 5 && p.nC <= 8 && outputs < 32768.0) {
         // reduction-shaped: too few outputs to fill the GPU with one thread each
         n.func = kreduce_func(g->dtype);

@@ -225,6 +225,127 @@ const void* contract_func(int dtype, int kc, int ma, int nb, bool single_chunk) 
     return dtype == 0 ? pick_kc<float2>(kc, ma, nb, single_chunk) : pick_kc<double2>(kc, ma, nb, single_chunk);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tiled complex GEMM (SIMT FMA).  The compute-bound regime: large K, many M-only and N-only
+// bits (Sycamore-like networks: K = 2^9, M x N = 2^9 x 2^11 per bitstring, ~60 flop/B).
+// B200 has no tcgen05 kind for FP64, and a 3xTF32 split needs ~12 real MMAs per complex FP32
+// product to keep fp32 accuracy, which caps it near the FFMA peak: so this is a classic
+// shared-memory-tiled FMA GEMM -- 2^TMB x 2^TNB x 2^KCB block tile, 4x4 complex micro-tile per
+// thread, register-prefetched operand tiles gathered through the bit maps (consecutive threads
+// read ascending global addresses), strided micro-tile so shared-memory reads are
+// conflict-free.
+template <typename R2, int TMB, int TNB, int KCB>
+__global__ void __launch_bounds__(1 << (TMB + TNB - 4))
+gemm_kernel(const __grid_constant__ GemmParams p) {
+    constexpr int BM = 1 << TMB, BN = 1 << TNB, BK = 1 << KCB;
+    constexpr int NT = 1 << (TMB + TNB - 4);
+    constexpr int LA = (BM * BK) / NT, LB = (BN * BK) / NT;
+    constexpr int TX = BN / 4, TY = BM / 4;          // thread grid; micro-tile rows ty + i*TY, cols tx + j*TX
+    __shared__ R2 sA[BK * BM];
+    __shared__ R2 sB[BK * BN];
+    const R2* __restrict__ A = reinterpret_cast<const R2*>(p.A);
+    const R2* __restrict__ B = reinterpret_cast<const R2*>(p.B);
+    R2* __restrict__ C = reinterpret_cast<R2*>(p.C);
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+    // per-thread load slots
+    int aOff[LA], bOff[LB];          // 32-bit: the host only picks this kernel for spans <= 2^30
+    int aSm[LA], bSm[LB];
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+        const int e = tid + i * NT;
+        int o = 0, sm = 0;
+#pragma unroll
+        for (int j = 0; j < TMB + KCB; ++j) if ((e >> j) & 1) { o += (int)p.aLoadOff[j]; sm += p.aLoadSm[j]; }
+        aOff[i] = o; aSm[i] = sm;
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+        const int e = tid + i * NT;
+        int o = 0, sm = 0;
+#pragma unroll
+        for (int j = 0; j < TNB + KCB; ++j) if ((e >> j) & 1) { o += (int)p.bLoadOff[j]; sm += p.bLoadSm[j]; }
+        bOff[i] = o; bSm[i] = sm;
+    }
+    int cMo[4], cNo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = ty + i * TY, n = tx + i * TX;
+        int om = 0, on = 0;
+#pragma unroll
+        for (int t = 0; t < TMB; ++t) if ((m >> t) & 1) om += (int)p.cM[t];
+#pragma unroll
+        for (int t = 0; t < TNB; ++t) if ((n >> t) & 1) on += (int)p.cN[t];
+        cMo[i] = om; cNo[i] = on;
+    }
+    const long long hmask = (1ll << p.hb) - 1ll;
+    const int nchunks = 1 << (p.nK - KCB);
+    for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        const long long u = tile >> p.hb;
+        const unsigned long long hh = (unsigned long long)(tile & hmask);
+        const R2* Ap = A + u * p.sUA + segeval(p.sAhi, p.nsAhi, hh);
+        const R2* Bp = B + u * p.sUB + segeval(p.sBhi, p.nsBhi, hh);
+        R2* Cp = C + u * p.sUC + segeval(p.sChi, p.nsChi, hh);
+        R2 acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acc[i][j].x = 0; acc[i][j].y = 0; }
+        R2 ra[LA], rb[LB];
+#pragma unroll
+        for (int i = 0; i < LA; ++i) ra[i] = __ldg(Ap + aOff[i]);
+#pragma unroll
+        for (int i = 0; i < LB; ++i) rb[i] = __ldg(Bp + bOff[i]);
+        for (int ch = 0; ch < nchunks; ++ch) {
+            __syncthreads();                     // previous chunk fully consumed
+#pragma unroll
+            for (int i = 0; i < LA; ++i) sA[aSm[i]] = ra[i];
+#pragma unroll
+            for (int i = 0; i < LB; ++i) sB[bSm[i]] = rb[i];
+            __syncthreads();
+            if (ch + 1 < nchunks) {              // prefetch the next chunk while computing this one
+                const unsigned long long kb = (unsigned long long)(ch + 1) << KCB;
+                const R2* An = Ap + segeval(p.kA, p.nkA, kb);
+                const R2* Bn = Bp + segeval(p.kB, p.nkB, kb);
+#pragma unroll
+                for (int i = 0; i < LA; ++i) ra[i] = __ldg(An + aOff[i]);
+#pragma unroll
+                for (int i = 0; i < LB; ++i) rb[i] = __ldg(Bn + bOff[i]);
+            }
+#pragma unroll
+            for (int kk = 0; kk < BK; ++kk) {
+                R2 a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = sA[kk * BM + ty + i * TY];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = sB[kk * BN + tx + j * TX];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cmac(acc[i][j], a[i], b[j]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Cp[cMo[i] + cNo[j]] = acc[i][j];
+    }
+}
+
+int gemm_kcb(int dtype) { return dtype == 0 ? 4 : 3; }
+
+template <typename R2, int KCB>
+static const void* pick_gemm(int tmb, int tnb) {
+    if (tmb == 6 && tnb == 6) return (const void*)&gemm_kernel<R2, 6, 6, KCB>;
+    if (tmb == 5 && tnb == 6) return (const void*)&gemm_kernel<R2, 5, 6, KCB>;
+    if (tmb == 6 && tnb == 5) return (const void*)&gemm_kernel<R2, 6, 5, KCB>;
+    if (tmb == 5 && tnb == 5) return (const void*)&gemm_kernel<R2, 5, 5, KCB>;
+    return nullptr;
+}
+const void* gemm_func(int dtype, int tmb, int tnb) {
+    return dtype == 0 ? pick_gemm<float2, 4>(tmb, tnb) : pick_gemm<double2, 3>(tmb, tnb);
+}
+
 // Reduction-shaped nodes (few C elements, long K -- e.g. the root after the batched
 // slice variables were summed early): one warp per C element, lanes stride over k,
 // shuffle reduction.  Requires nC <= 8 (all C bits are "thread bits" in OpParams).

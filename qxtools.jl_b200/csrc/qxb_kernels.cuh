@@ -44,6 +44,31 @@ struct OpParams {
     DSeg kA[kMaxKSeg], kB[kMaxKSeg];
 };
 
+// Tiled complex GEMM for GEMM-shaped nodes (K >= 2^kcb, >= 5 M-only and >= 5 N-only bits).
+// Block tile = 2^tmb M-only bits x 2^tnb N-only bits x 2^kcb K bits; every other C bit
+// (batch bits, further M/N bits) and the bitstring row are enumerated by the tile index.
+struct GemmParams {
+    const void* A;
+    const void* B;
+    void* C;
+    long long sUA, sUB, sUC;
+    long long tiles;                 // U << hb
+    int U, hb;
+    int nK;                          // total K bits (chunk bits are the low kcb of the k index)
+    int nsAhi, nsBhi, nsChi, nkA, nkB;
+    // operand tile loads: load-index bit j -> global offset / shared-memory index contribution
+    // (bits sorted by ascending global offset so consecutive threads read ascending addresses)
+    long long aLoadOff[10], bLoadOff[10];
+    int aLoadSm[10], bLoadSm[10];
+    long long cM[6], cN[6];          // C offset of each M-tile / N-tile bit
+    DSeg sAhi[kMaxSeg], sBhi[kMaxSeg], sChi[kMaxSeg];
+    DSeg kA[kMaxKSeg], kB[kMaxKSeg]; // k index (all nK bits) -> offsets; chunk c covers k = c << kcb ...
+};
+
+// nullptr when the shape has no instantiation; threads = 2^(tmb + tnb - 4)
+const void* gemm_func(int dtype, int tmb, int tnb);
+int gemm_kcb(int dtype);             // K chunk bits the kernels are built for (4 for c32, 3 for c64)
+
 struct OutLeafDesc { long long offset_per_amp; int span_bits; int out_idx; };
 
 // Kernel entry points as function pointers (for cudaLaunchKernel / cudaGraphAddKernelNode).

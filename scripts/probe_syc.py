@@ -8,14 +8,14 @@ from oracle import qx_oracle as orc
 init(0)
 txt, data, w = bench.build_workload("sycamore53_d7_c32")
 bits = bench.synth_bits(64, 53)
-for dt in ("c32", "c64"):
-    g = Graph.from_dsl(txt, data, dt, replan=64, replan_n_amp=64).compile()
+for dt, gemm in (("c32", True), ("c32", False), ("c64", True), ("c64", False)):
+    g = Graph.from_dsl(txt, data, dt, replan=64, replan_n_amp=64).compile(gemm=gemm)
     out = g.amplitudes(bits)
     best = 1e9
     for _ in range(3):
         t = time.time(); out = g.amplitudes(bits); best = min(best, time.time() - t)
     st = g.stats()
-    print(dt, f"{best*1e3:.1f} ms per 64 bitstrings -> {64/best:.0f} amp/s; {st['flops']/best/1e12:.2f} TFLOP/s, {st['bytes']/best/1e9:.0f} GB/s, ws {st['workspace_bytes']/1e9:.1f} GB, mean p*2^n {np.mean(np.abs(out)**2)*2.0**53:.3f}", flush=True)
+    print(dt, "gemm" if gemm else "stream", f"{best*1e3:.1f} ms per 64 bitstrings -> {64/best:.0f} amp/s; {st['flops']/best/1e12:.2f} TFLOP/s, {st['bytes']/best/1e9:.0f} GB/s, ws {st['workspace_bytes']/1e9:.1f} GB, mean p*2^n {np.mean(np.abs(out)**2)*2.0**53:.3f}", flush=True)
     if dt == "c64":
         ref64 = out
     else:
