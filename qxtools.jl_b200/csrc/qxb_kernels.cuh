@@ -15,7 +15,7 @@
 namespace qxb {
 
 constexpr int kMaxSeg = 32;
-constexpr int kMaxKSeg = 16;
+constexpr int kMaxKSeg = 32;
 constexpr int kKTab = 16;
 constexpr int kThreads = 256;
 constexpr int kMaxEpt = 4;          // elements per thread per tile -> tile of up to 1024 elements
