@@ -408,9 +408,14 @@ Node contract_node(const RunCtx& c, int i) {
     }
     if (p.nK >= 5 && p.nC <= 8 && outputs < 32768.0) {
         // reduction-shaped: too few outputs to fill the GPU with one thread each
-        n.func = kreduce_func(g->dtype);
-        const long long warps = (long long)outputs;
-        n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>((warps * 32 + kThreads - 1) / kThreads, cap)));
+        if (p.nK >= 12 && outputs <= 8192.0) {
+            n.func = kreduce_block_func(g->dtype);           // very long K, few outputs: a block per output
+            n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>((long long)outputs, cap)));
+        } else {
+            n.func = kreduce_func(g->dtype);
+            const long long warps = (long long)outputs;
+            n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>((warps * 32 + kThreads - 1) / kThreads, cap)));
+        }
     } else {
         // broadcast-type node: both operands small per bitstring row, C much larger -> stage them in
         // shared memory once per row (otherwise every output re-reads them through L1/L2)

@@ -388,6 +388,58 @@ kreduce_kernel(const __grid_constant__ OpParams p) {
     }
 }
 
+// Same, one 256-thread block per C element: for very long K with few outputs (the root of a
+// GEMM-shaped tree: K = 2^20, one output per bitstring).
+template <typename R2>
+__global__ void __launch_bounds__(kThreads)
+kreduce_block_kernel(const __grid_constant__ OpParams p) {
+    const R2* __restrict__ A = reinterpret_cast<const R2*>(p.A);
+    const R2* __restrict__ B = reinterpret_cast<const R2*>(p.B);
+    R2* __restrict__ C = reinterpret_cast<R2*>(p.C);
+    __shared__ R2 part[kThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long total = (long long)p.U << p.nC;
+    const unsigned cmask = (1u << p.nC) - 1u;
+    const long long K = 1ll << p.nK;
+    for (long long o = blockIdx.x; o < total; o += gridDim.x) {
+        const long long u = o >> p.nC;
+        const unsigned c = (unsigned)o & cmask;
+        const R2* Ap = A + u * p.sUA + segeval(p.sAlo, p.nsAlo, c);
+        const R2* Bp = B + u * p.sUB + segeval(p.sBlo, p.nsBlo, c);
+        R2 acc0, acc1; acc0.x = acc0.y = acc1.x = acc1.y = 0;
+        long long k = threadIdx.x;
+        for (; k + kThreads < K; k += 2 * kThreads) {
+            const R2 a0 = __ldg(Ap + segeval(p.kA, p.nkA, (unsigned long long)k));
+            const R2 b0 = __ldg(Bp + segeval(p.kB, p.nkB, (unsigned long long)k));
+            const R2 a1 = __ldg(Ap + segeval(p.kA, p.nkA, (unsigned long long)(k + kThreads)));
+            const R2 b1 = __ldg(Bp + segeval(p.kB, p.nkB, (unsigned long long)(k + kThreads)));
+            cmac(acc0, a0, b0); cmac(acc1, a1, b1);
+        }
+        for (; k < K; k += kThreads)
+            cmac(acc0, __ldg(Ap + segeval(p.kA, p.nkA, (unsigned long long)k)),
+                 __ldg(Bp + segeval(p.kB, p.nkB, (unsigned long long)k)));
+        acc0.x += acc1.x; acc0.y += acc1.y;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            acc0.x += __shfl_xor_sync(0xffffffffu, acc0.x, s);
+            acc0.y += __shfl_xor_sync(0xffffffffu, acc0.y, s);
+        }
+        __syncthreads();                         // part[] free again
+        if (lane == 0) part[warp] = acc0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            R2 t = part[0];
+#pragma unroll
+            for (int w = 1; w < kThreads / 32; ++w) { t.x += part[w].x; t.y += part[w].y; }
+            C[u * p.sUC + c] = t;
+        }
+    }
+}
+
+const void* kreduce_block_func(int dtype) {
+    return dtype == 0 ? (const void*)&kreduce_block_kernel<float2> : (const void*)&kreduce_block_kernel<double2>;
+}
+
 const void* kreduce_func(int dtype) {
     return dtype == 0 ? (const void*)&kreduce_kernel<float2> : (const void*)&kreduce_kernel<double2>;
 }

@@ -303,3 +303,22 @@ def test_fsim_circuit_extent4_bonds(gpu, dtype):
         assert rel_err(g.amplitudes(bs), ref, 12) < TOL[dtype]
         S = g.n_slices
         assert rel_err(g.amplitudes(bs, 5, S - 3), orc.amplitudes(cmds, data, bs, slice_begin=5, slice_end=S - 3), 12) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", ["c64", "c32"])
+def test_long_k_block_reduction(gpu, dtype):
+    """K = 2^13 with one output per bitstring: the block-per-output reduction kernel."""
+    rng = np.random.default_rng(11)
+    A = (rng.normal(size=(2,) * 13) + 1j * rng.normal(size=(2,) * 13)) / 8
+    B = (rng.normal(size=(2,) * 14) + 1j * rng.normal(size=(2,) * 14)) / 8
+    l13 = ",".join(str(i) for i in range(1, 14))
+    l14 = ",".join(str(i) for i in range(1, 15))
+    txt = ("# version: 0.4.0\nload a dA " + ",".join(["2"] * 13) + "\nload b dB " + ",".join(["2"] * 14) + "\noutput o1 1 2\n"
+           f"ncon w {l13} b {l14} o1 14\n"            # chunk phase: 2^13 elements per bitstring
+           f"ncon z 0 w {l13} a {l13}\nsave output z\n")   # K = 2^13, nC = 0
+    data = {"dA": A, "dB": B}
+    bs = ["0", "1", "+", "-"]
+    ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
+    g = Graph.from_dsl(txt, data, dtype).compile()
+    got = g.amplitudes(bs)
+    assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 5e-5)
