@@ -52,7 +52,8 @@ typedef struct qxb_options {
                                   0 (default) = sum each one at the lowest node covering all its leaves   */
     int32_t no_smem_stage;     /* 1 = never use the shared-memory-staged kernel for broadcast-type nodes */
     int32_t no_gemm;           /* 1 = never use the tiled GEMM kernel for GEMM-shaped nodes               */
-    int32_t reserved;
+    int32_t gemm_mode;         /* GEMM-shaped nodes: 0 = auto, 1 = SIMT FMA kernel only, 2 = tensor-core kernel
+                                  (DMMA for ComplexF64, 3xTF32 for ComplexF32) wherever the tile shape allows */
 } qxb_options;
 
 /* library */
@@ -153,6 +154,10 @@ typedef struct qxb_stats {
 int  qxb_last_stats(const qxb_graph* g, qxb_stats* st);
 /* Per-op table (name, shape, flops, bytes, ms) of the last profiled call, as JSON. */
 int  qxb_profile_dump(qxb_graph* g, const char* json_path);
+
+/* test hook (not part of the drop-in surface): shared-memory offset contributed by tile-index bit `bit` in the
+ * tensor-core GEMM kernels' staging layouts; tests/test_mma_layout.py replays the kernels' index arithmetic on the CPU */
+int  qxb_debug_mma_smem_bit(int dtype, int is_b, int tile_bits, int bit);
 
 #ifdef __cplusplus
 }

@@ -39,7 +39,9 @@ struct Options
     profile::Int32
     no_cuda_graph::Int32
     sum_at_root::Int32
-    reserved::Int32
+    no_smem_stage::Int32
+    no_gemm::Int32
+    gemm_mode::Int32        # 0 = auto, 1 = SIMT FMA GEMM only, 2 = tensor-core GEMM (DMMA / 3xTF32)
 end
 
 i64(v) = Int64.(collect(v))

@@ -22,7 +22,7 @@ SYMBOLS = [
     "qxb_graph_num_outputs", "qxb_graph_num_slice_vars", "qxb_graph_num_slices", "qxb_slice_values",
     "qxb_graph_describe", "qxb_graph_replan", "qxb_graph_program_text", "qxb_graph_configure", "qxb_graph_compile", "qxb_amplitudes", "qxb_amplitudes_device",
     "qxb_amplitudes_subspace", "qxb_partition_vars", "qxb_graph_describe_mask", "qxb_graph_cost_bytes",
-    "qxb_last_stats", "qxb_profile_dump",
+    "qxb_last_stats", "qxb_profile_dump", "qxb_debug_mma_smem_bit",
 ]
 
 
@@ -36,7 +36,7 @@ class Options(C.Structure):
     _fields_ = [("hbm_budget_bytes", C.c_int64), ("amp_batch", C.c_int64),
                 ("profile", C.c_int32), ("no_cuda_graph", C.c_int32),
                 ("sum_at_root", C.c_int32), ("no_smem_stage", C.c_int32),
-                ("no_gemm", C.c_int32), ("reserved", C.c_int32)]
+                ("no_gemm", C.c_int32), ("gemm_mode", C.c_int32)]
 
 
 class Stats(C.Structure):

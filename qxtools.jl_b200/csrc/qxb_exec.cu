@@ -11,7 +11,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <cstdlib>
 #include <set>
 #include <sstream>
 #include <tuple>
@@ -321,8 +323,15 @@ void build_templates(Variant& v, int dtype) {
             for (int t = 0; t < tnb; ++t) lb.push_back({1ll << mapB[nt[t]], 1 << t});
             for (int c = 0; c < kcb; ++c) lb.push_back({kposB[c], (1 << c) << tnb});
             std::sort(la.begin(), la.end()); std::sort(lb.begin(), lb.end());
-            for (size_t j = 0; j < la.size(); ++j) { q.aLoadOff[j] = la[j].first; q.aLoadSm[j] = la[j].second; }
-            for (size_t j = 0; j < lb.size(); ++j) { q.bLoadOff[j] = lb[j].first; q.bLoadSm[j] = lb[j].second; }
+            auto bitpos = [](int mask) { int b = 0; while ((1 << b) < mask) ++b; return b; };
+            for (size_t j = 0; j < la.size(); ++j) {
+                q.aLoadOff[j] = la[j].first; q.aLoadSm[j] = la[j].second;
+                q.aLoadSmT[j] = gemm_mma_smem_bit(dtype, false, tmb, bitpos(la[j].second));
+            }
+            for (size_t j = 0; j < lb.size(); ++j) {
+                q.bLoadOff[j] = lb[j].first; q.bLoadSm[j] = lb[j].second;
+                q.bLoadSmT[j] = gemm_mma_smem_bit(dtype, true, tnb, bitpos(lb[j].second));
+            }
             for (int t = 0; t < tmb; ++t) q.cM[t] = 1ll << mt[t];
             for (int t = 0; t < tnb; ++t) q.cN[t] = 1ll << nt[t];
             std::vector<bool> tile_bit(nC, false);
@@ -373,6 +382,14 @@ struct Node {
     }
 };
 
+// 0 (auto) resolves to the kernel measured faster on B200 for the dtype; QXB_GEMM_MODE overrides (experiments)
+int gemm_mode(const qxb_graph* g) {
+    static const int env = [] { const char* e = getenv("QXB_GEMM_MODE"); return e ? atoi(e) : 0; }();
+    int m = env ? env : g->opts.gemm_mode;
+    if (m == 0) m = 1;
+    return m;
+}
+
 Node contract_node(const RunCtx& c, int i) {
     qxb_graph* g = c.g;
     Lowered& L = c.v->L;
@@ -396,9 +413,27 @@ Node contract_node(const RunCtx& c, int i) {
         q.A = p.A; q.B = p.B; q.C = p.C; q.sUA = p.sUA; q.sUB = p.sUB; q.sUC = p.sUC; q.U = p.U;
         q.tiles = (long long)p.U << q.hb;
         const int tmb = c.v->gemm_tmb[i], tnb = c.v->gemm_tnb[i];
-        n.func = gemm_func(g->dtype, tmb, tnb);
-        n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(q.tiles, (long long)g_num_sms * 2)));
-        n.block = dim3(1u << (tmb + tnb - 4));
+        const void* tc = gemm_mode(g) == 2 ? gemm_mma_func(g->dtype, tmb, tnb) : nullptr;
+        if (tc) {
+            // tensor-core variant (DMMA / 3xTF32 mma.sync); persistent grid = SMs x resident CTAs
+            n.func = tc;
+            n.block = dim3((unsigned)gemm_mma_threads(g->dtype));
+            n.smem = gemm_mma_smem_bytes(g->dtype);
+            static std::map<const void*, int> resident;
+            auto it = resident.find(tc);
+            if (it == resident.end()) {
+                int nb = 0;
+                if (n.smem > 48 * 1024)
+                    CUDA_OK(cudaFuncSetAttribute(tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n.smem));
+                CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tc, (int)n.block.x, n.smem));
+                it = resident.emplace(tc, std::max(nb, 1)).first;
+            }
+            n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(q.tiles, (long long)g_num_sms * it->second)));
+        } else {
+            n.func = gemm_func(g->dtype, tmb, tnb);
+            n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(q.tiles, (long long)g_num_sms * 2)));
+            n.block = dim3(1u << (tmb + tnb - 4));
+        }
         n.arg(q);
         n.variant = c.variant_key; n.op = i;
         const double u = (double)p.U;
@@ -1198,6 +1233,11 @@ int qxb_profile_dump(qxb_graph* g, const char* path) {
         fprintf(f, "]}\n");
         fclose(f);
     });
+}
+
+// test hook: shared-memory layout table of the tensor-core GEMM kernels (tests/test_mma_layout.py)
+int qxb_debug_mma_smem_bit(int dtype, int is_b, int tile_bits, int bit) {
+    return qxb::gemm_mma_smem_bit(dtype, is_b != 0, tile_bits, bit);
 }
 
 }  // extern "C"

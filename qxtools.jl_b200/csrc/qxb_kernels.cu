@@ -346,6 +346,390 @@ const void* gemm_func(int dtype, int tmb, int tnb) {
     return dtype == 0 ? pick_gemm<float2, 4>(tmb, tnb) : pick_gemm<double2, 3>(tmb, tnb);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core complex GEMMs (warp-level mma.sync), same GemmParams / tile enumeration as
+// gemm_kernel.  Block tile 64 x 64 complex, K chunk 16 (c32) / 8 (c64).
+//
+//  ComplexF64 (gemm_dmma_kernel): DMMA mma.sync.m8n8k4.f64 -- 4 real MMAs per complex tile
+//      product (re += Ar*Br, re += (-Ai)*Bi, im += Ar*Bi, im += Ai*Br); warp tile 16 x 32, 8 warps.
+//      Shared tiles are [k][m] double2 with a row stride of 64 + 2 elements: the fragment loads
+//      of a quarter warp (lanes g = 0..1, t = 0..3 -> element t * 66 + g) hit 8 distinct
+//      16-byte bank groups.
+//  ComplexF32 (gemm_tf32x3_kernel): 3xTF32 mma.sync.m16n8k8 -- every fp32 operand is split
+//      once, while it is staged into shared memory, into a tf32 head and a tf32 tail
+//      (x = hi + lo, |lo| <= 2^-11 |x|); each of the 4 real products is hi*hi + lo*hi + hi*lo
+//      accumulated in fp32 (the dropped lo*lo term is ~2^-22 relative, i.e. fp32 rounding level):
+//      12 MMAs per complex tile product against 4 FFMA per complex MAC, so per complex MAC the
+//      tensor pipe has (tf32 MAC rate / 12) against (FFMA rate / 4).  Warp tile 32 x 32, 4 warps.
+//      Shared tiles are stored FRAGMENT-MAJOR: for every (k8 step, m16 tile, plane) the 128 floats
+//      a warp needs are laid out [lane][a0 a1 a2 a3], so one conflict-free LDS.128 per lane yields
+//      the four consecutive registers of an MMA A operand (planes: re_hi, im_hi, re_lo, im_lo);
+//      B likewise as [lane][re b0 b1, im b0 b1] for the hi and the lo halves.
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const float4 a, const float b0, const float b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)),
+                   "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+__device__ __forceinline__ void mma_tf32_z(float (&d)[4], const float4 a, const float b0, const float b1) {   // C = 0
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};\n"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)),
+                   "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)), "f"(0.f));
+}
+__device__ __forceinline__ void mma_f64(double (&d)[2], const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+// round-to-nearest (ties away) to the 10-bit tf32 mantissa with two integer ops (what cvt.rna.tf32.f32 does,
+// which compiles to ~5 instructions here); finite inputs only
+__device__ __forceinline__ float to_tf32(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ float fneg_bits(float x) { return __uint_as_float(__float_as_uint(x) ^ 0x80000000u); }
+
+template <int NBITS>
+__device__ __forceinline__ int bit_offset(int idx, const long long* tbl) {
+    int o = 0;
+#pragma unroll
+    for (int t = 0; t < NBITS; ++t) if ((idx >> t) & 1) o += (int)tbl[t];
+    return o;
+}
+
+// Load-slot bookkeeping shared by both kernels: slot e = tid + i * NT (i < L); bit j of e selects a
+// global-offset contribution off[j] and a shared-memory contribution sm(j).  The thread part (bits
+// below LOGNT) is summed into registers once; the slot part is uniform and re-derived from the
+// parameter block where it is used.
+template <int LOGNT, int NB_, typename F>
+__device__ __forceinline__ int slot_sum(int i, F f) {
+    int o = 0;
+#pragma unroll
+    for (int j = LOGNT; j < NB_; ++j) if ((i >> (j - LOGNT)) & 1) o += f(j);
+    return o;
+}
+
+// bank swizzle of the fragment-major tiles: within a 128-float block (32 lane slots of 16 bytes) lane slot
+// bits 0..1 are XORed with bits 3..4, so operand stores whose lanes run over m (n) land in 8 distinct
+// 16-byte bank groups (8- and 16-way conflicts otherwise) while a quarter warp's LDS.128 stays conflict-free
+__device__ __forceinline__ int frag_swz(int off) { return off ^ (((off >> 5) & 3) << 2); }
+
+template <int TMB, int TNB>
+__global__ void __launch_bounds__(((1 << (TMB + TNB)) / 1024) * 32, 2)
+gemm_tf32x3_kernel(const __grid_constant__ GemmParams p) {
+    using R2 = float2;
+    constexpr int KCB = 4;
+    constexpr int BM = 1 << TMB, BN = 1 << TNB, BK = 1 << KCB;
+    constexpr int WGM = BM / 32, WGN = BN / 32;
+    constexpr int NT = 32 * WGM * WGN;
+    constexpr int LOGNT = TMB + TNB - 5;
+    constexpr int LA = (BM * BK) / NT, LB = (BN * BK) / NT;
+    constexpr int MT = 2, NTL = 4;                    // m16 / n8 MMA tiles per 32 x 32 warp tile
+    constexpr int MTC = BM / 16, NTC = BN / 8;        // MMA tiles per block tile
+    constexpr int SA = (BK / 8) * MTC * 512, SB = (BK / 8) * NTC * 256;   // floats per stage
+    static_assert(NT == (1 << LOGNT), "thread count");
+    extern __shared__ __align__(16) float smem_f[];   // two stages of [A tile | B tile]
+    const R2* __restrict__ A = reinterpret_cast<const R2*>(p.A);
+    const R2* __restrict__ B = reinterpret_cast<const R2*>(p.B);
+    R2* __restrict__ C = reinterpret_cast<R2*>(p.C);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp % WGM) * 32, wn0 = (warp / WGM) * 32;
+    int aOffT = 0, aSmT = 0, bOffT = 0, bSmT = 0;
+#pragma unroll
+    for (int j = 0; j < LOGNT; ++j) {
+        if ((tid >> j) & 1) {
+            aOffT += (int)p.aLoadOff[j]; aSmT += p.aLoadSmT[j];
+            bOffT += (int)p.bLoadOff[j]; bSmT += p.bLoadSmT[j];
+        }
+    }
+    aSmT = frag_swz(aSmT); bSmT = frag_swz(bSmT);     // the swizzle is XOR-linear over the disjoint bit fields
+    auto aOffI = [&](int i) { return slot_sum<LOGNT, TMB + KCB>(i, [&](int j) { return (int)p.aLoadOff[j]; }); };
+    auto bOffI = [&](int i) { return slot_sum<LOGNT, TNB + KCB>(i, [&](int j) { return (int)p.bLoadOff[j]; }); };
+    auto aSmI = [&](int i) { return frag_swz(slot_sum<LOGNT, TMB + KCB>(i, [&](int j) { return p.aLoadSmT[j]; })); };
+    auto bSmI = [&](int i) { return frag_swz(slot_sum<LOGNT, TNB + KCB>(i, [&](int j) { return p.bLoadSmT[j]; })); };
+    const long long hmask = (1ll << p.hb) - 1ll;
+    const int nchunks = 1 << (p.nK - KCB);
+    const int lsw = lane ^ (lane >> 3);
+    const int fAo = (wm0 / 16) * 128 + lsw;           // float4 index: + (ks*MTC + mt)*128 + plane*32
+    const int fBo = (wn0 / 8) * 64 + lsw;             // float4 index: + (ks*NTC + nt)*64 + half*32
+    R2 ra[LA], rb[LB];
+    auto stage = [&](float* sA, float* sB) {          // split into tf32 head / tail + scatter
+#pragma unroll
+        for (int i = 0; i < LA; ++i) {                // A: four planes re_hi, im_hi, re_lo, im_lo
+            float* d = sA + (aSmT ^ aSmI(i));
+            const float hr = to_tf32(ra[i].x), hi = to_tf32(ra[i].y);
+            d[0] = hr; d[128] = hi; d[256] = to_tf32(ra[i].x - hr); d[384] = to_tf32(ra[i].y - hi);
+        }
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {                // B: [re b0 b1, im b0 b1] x {hi, lo}
+            float* d = sB + (bSmT ^ bSmI(i));
+            const float hr = to_tf32(rb[i].x), hi = to_tf32(rb[i].y);
+            d[0] = hr; d[2] = hi; d[128] = to_tf32(rb[i].x - hr); d[130] = to_tf32(rb[i].y - hi);
+        }
+    };
+    for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        const long long u = tile >> p.hb;
+        const unsigned long long hh = (unsigned long long)(tile & hmask);
+        const R2* Ap = A + u * p.sUA + segeval(p.sAhi, p.nsAhi, hh);
+        const R2* Bp = B + u * p.sUB + segeval(p.sBhi, p.nsBhi, hh);
+        R2* Cp = C + u * p.sUC + segeval(p.sChi, p.nsChi, hh);
+        float cre[MT][NTL][4], cim[MT][NTL][4];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NTL; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { cre[i][j][e] = 0.f; cim[i][j][e] = 0.f; }
+#pragma unroll
+        for (int i = 0; i < LA; ++i) ra[i] = __ldg(Ap + aOffT + aOffI(i));
+#pragma unroll
+        for (int i = 0; i < LB; ++i) rb[i] = __ldg(Bp + bOffT + bOffI(i));
+        stage(smem_f, smem_f + SA);              // (the previous tile ended on a barrier: both stages are free)
+        __syncthreads();
+        // two-stage pipeline, one barrier per chunk: global loads of chunk ch+1 are in flight while chunk ch
+        // is multiplied out of stage ch&1, then split + stored into the other stage
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const float* sA = smem_f + (ch & 1) * (SA + SB);
+            const float* sB = sA + SA;
+            if (ch + 1 < nchunks) {
+                const unsigned long long kb = (unsigned long long)(ch + 1) << KCB;
+                const R2* An = Ap + segeval(p.kA, p.nkA, kb);
+                const R2* Bn = Bp + segeval(p.kB, p.nkB, kb);
+#pragma unroll
+                for (int i = 0; i < LA; ++i) ra[i] = __ldg(An + aOffT + aOffI(i));
+#pragma unroll
+                for (int i = 0; i < LB; ++i) rb[i] = __ldg(Bn + bOffT + bOffI(i));
+            }
+            const float4* fA = reinterpret_cast<const float4*>(sA) + fAo;
+            const float4* fB = reinterpret_cast<const float4*>(sB) + fBo;
+#pragma unroll 1
+            for (int ks = 0; ks < BK / 8; ++ks) {
+                float4 ahr[MT], ahi[MT], alr[MT], ali[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const float4* q = fA + (ks * MTC + mt) * 128;
+                    ahr[mt] = q[0]; ahi[mt] = q[32]; alr[mt] = q[64]; ali[mt] = q[96];
+                }
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt) {
+                    const float4* q = fB + (ks * NTC + nt) * 64;
+                    const float4 bh = q[0], bl = q[32];            // {re b0, re b1, im b0, im b1}
+                    const float nh0 = fneg_bits(bh.z), nh1 = fneg_bits(bh.w);
+                    const float nl0 = fneg_bits(bl.z), nl1 = fneg_bits(bl.w);
+                    // Each k8 partial product is chained inside the tensor core from a ZERO accumulator (cross
+                    // terms first, head x head last) and then added to the running sums with FADD: the MMA adds
+                    // with truncation, and chaining all of K through it biases every sum towards zero by
+                    // ~2^-24 per MMA (measured 2.4e-5 relative on K = 2^9 trees, against 3e-6 this way).
+                    float dre[MT][4], dim[MT][4];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma_tf32_z(dre[mt], alr[mt], bh.x, bh.y);
+                        mma_tf32_z(dim[mt], alr[mt], bh.z, bh.w);
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma_tf32(dre[mt], ahr[mt], bl.x, bl.y);
+                        mma_tf32(dim[mt], ahr[mt], bl.z, bl.w);
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma_tf32(dre[mt], ali[mt], nh0, nh1);
+                        mma_tf32(dim[mt], ali[mt], bh.x, bh.y);
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma_tf32(dre[mt], ahi[mt], nl0, nl1);
+                        mma_tf32(dim[mt], ahi[mt], bl.x, bl.y);
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma_tf32(dre[mt], ahr[mt], bh.x, bh.y);
+                        mma_tf32(dim[mt], ahr[mt], bh.z, bh.w);
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma_tf32(dre[mt], ahi[mt], nh0, nh1);
+                        mma_tf32(dim[mt], ahi[mt], bh.x, bh.y);
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { cre[mt][nt][e] += dre[mt][e]; cim[mt][nt][e] += dim[mt][e]; }
+                }
+            }
+            if (ch + 1 < nchunks) {
+                float* nA = smem_f + ((ch + 1) & 1) * (SA + SB);
+                stage(nA, nA + SA);
+            }
+            __syncthreads();
+        }
+        // epilogue: accumulator c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1) -> C through the tile-bit tables
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int ro = bit_offset<TMB>(wm0 + mt * 16 + g + h * 8, p.cM);
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int co = bit_offset<TNB>(wn0 + nt * 8 + 2 * t + j, p.cN);
+                        Cp[ro + co] = make_float2(cre[mt][nt][h * 2 + j], cim[mt][nt][h * 2 + j]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int TMB, int TNB>
+__global__ void __launch_bounds__(((1 << (TMB + TNB)) / 512) * 32, 2)
+gemm_dmma_kernel(const __grid_constant__ GemmParams p) {
+    using R2 = double2;
+    constexpr int KCB = 3;
+    constexpr int BM = 1 << TMB, BN = 1 << TNB, BK = 1 << KCB;
+    constexpr int WGM = BM / 16, WGN = BN / 32;
+    constexpr int NT = 32 * WGM * WGN;
+    constexpr int LOGNT = TMB + TNB - 4;
+    constexpr int LDA = BM + 2, LDB = BN + 2;
+    constexpr int LA = (BM * BK) / NT, LB = (BN * BK) / NT;
+    constexpr int MT = 2, NTL = 4;                    // m8 / n8 MMA tiles per 16 x 32 warp tile
+    static_assert(NT == (1 << LOGNT), "thread count");
+    constexpr int SA = BK * LDA, SB = BK * LDB;       // elements per stage
+    __shared__ __align__(16) R2 smem_d[2 * (SA + SB)]; // two stages of [A tile | B tile]
+    const R2* __restrict__ A = reinterpret_cast<const R2*>(p.A);
+    const R2* __restrict__ B = reinterpret_cast<const R2*>(p.B);
+    R2* __restrict__ C = reinterpret_cast<R2*>(p.C);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp % WGM) * 16, wn0 = (warp / WGM) * 32;
+    int aOffT = 0, aSmT = 0, bOffT = 0, bSmT = 0;
+#pragma unroll
+    for (int j = 0; j < LOGNT; ++j) {
+        if ((tid >> j) & 1) {
+            aOffT += (int)p.aLoadOff[j]; aSmT += p.aLoadSmT[j];
+            bOffT += (int)p.bLoadOff[j]; bSmT += p.bLoadSmT[j];
+        }
+    }
+    auto aOffI = [&](int i) { return slot_sum<LOGNT, TMB + KCB>(i, [&](int j) { return (int)p.aLoadOff[j]; }); };
+    auto bOffI = [&](int i) { return slot_sum<LOGNT, TNB + KCB>(i, [&](int j) { return (int)p.bLoadOff[j]; }); };
+    auto aSmI = [&](int i) { return slot_sum<LOGNT, TMB + KCB>(i, [&](int j) { return p.aLoadSmT[j]; }); };
+    auto bSmI = [&](int i) { return slot_sum<LOGNT, TNB + KCB>(i, [&](int j) { return p.bLoadSmT[j]; }); };
+    const long long hmask = (1ll << p.hb) - 1ll;
+    const int nchunks = 1 << (p.nK - KCB);
+    for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        const long long u = tile >> p.hb;
+        const unsigned long long hh = (unsigned long long)(tile & hmask);
+        const R2* Ap = A + u * p.sUA + segeval(p.sAhi, p.nsAhi, hh);
+        const R2* Bp = B + u * p.sUB + segeval(p.sBhi, p.nsBhi, hh);
+        R2* Cp = C + u * p.sUC + segeval(p.sChi, p.nsChi, hh);
+        double cre[MT][NTL][2], cim[MT][NTL][2];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NTL; ++j) { cre[i][j][0] = cre[i][j][1] = 0.0; cim[i][j][0] = cim[i][j][1] = 0.0; }
+        R2 ra[LA], rb[LB];
+#pragma unroll
+        for (int i = 0; i < LA; ++i) ra[i] = __ldg(Ap + aOffT + aOffI(i));
+#pragma unroll
+        for (int i = 0; i < LB; ++i) rb[i] = __ldg(Bp + bOffT + bOffI(i));
+#pragma unroll
+        for (int i = 0; i < LA; ++i) smem_d[aSmT + aSmI(i)] = ra[i];     // (the previous tile ended on a barrier)
+#pragma unroll
+        for (int i = 0; i < LB; ++i) smem_d[SA + bSmT + bSmI(i)] = rb[i];
+        __syncthreads();
+        // two-stage pipeline, one barrier per chunk (see gemm_tf32x3_kernel)
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const R2* sA = smem_d + (ch & 1) * (SA + SB);
+            const R2* sB = sA + SA;
+            if (ch + 1 < nchunks) {
+                const unsigned long long kb = (unsigned long long)(ch + 1) << KCB;
+                const R2* An = Ap + segeval(p.kA, p.nkA, kb);
+                const R2* Bn = Bp + segeval(p.kB, p.nkB, kb);
+#pragma unroll
+                for (int i = 0; i < LA; ++i) ra[i] = __ldg(An + aOffT + aOffI(i));
+#pragma unroll
+                for (int i = 0; i < LB; ++i) rb[i] = __ldg(Bn + bOffT + bOffI(i));
+            }
+#pragma unroll
+            for (int ks = 0; ks < BK / 4; ++ks) {
+                // A fragment of an m8 tile: a0 (row g, k = t); B fragment of an n8 tile: b0 (k = t, n = g)
+                const R2* ab = sA + (ks * 4 + t) * LDA + wm0 + g;
+                const R2* bb = sB + (ks * 4 + t) * LDB + wn0 + g;
+                R2 af[MT];
+                double nai[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) { af[mt] = ab[mt * 8]; nai[mt] = -af[mt].y; }
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt) {
+                    const R2 bv = bb[nt * 8];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma_f64(cre[mt][nt], af[mt].x, bv.x);
+                        mma_f64(cim[mt][nt], af[mt].x, bv.y);
+                        mma_f64(cre[mt][nt], nai[mt], bv.y);
+                        mma_f64(cim[mt][nt], af[mt].y, bv.x);
+                    }
+                }
+            }
+            if (ch + 1 < nchunks) {
+                R2* nA = smem_d + ((ch + 1) & 1) * (SA + SB);
+#pragma unroll
+                for (int i = 0; i < LA; ++i) nA[aSmT + aSmI(i)] = ra[i];
+#pragma unroll
+                for (int i = 0; i < LB; ++i) nA[SA + bSmT + bSmI(i)] = rb[i];
+            }
+            __syncthreads();
+        }
+        // epilogue: accumulator c0 (g, 2t) c1 (g, 2t+1) -> C through the tile-bit tables
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int ro = bit_offset<TMB>(wm0 + mt * 8 + g, p.cM);
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int co = bit_offset<TNB>(wn0 + nt * 8 + 2 * t + j, p.cN);
+                    Cp[ro + co] = make_double2(cre[mt][nt][j], cim[mt][nt][j]);
+                }
+            }
+        }
+    }
+}
+
+// Shared-memory contribution of tile-index bit `b` (bit positions: [0, tb) = M (N) tile bits, [tb, tb + kcb)
+// = K chunk bits) in the layouts of the tensor-core kernels; filled into GemmParams::a/bLoadSmT by the host.
+int gemm_mma_smem_bit(int dtype, bool is_b, int tb, int b) {
+    if (dtype != 0) {                                            // c64: [k][m] double2, row stride 2^tb + 2
+        return b < tb ? (1 << b) : (1 << (b - tb)) * ((1 << tb) + 2);
+    }
+    const int c = b - tb;
+    if (!is_b) {                                                 // c32 A: [k8 step][m16 tile][plane][lane][a0..a3] floats
+        if (b < 3) return 16 << b;                               // g
+        if (b == 3) return 1;                                    // row + 8 -> a1 / a3
+        if (b < tb) return 512 << (b - 4);                       // m16 tile (4 planes x 128 floats)
+        if (c < 2) return 4 << c;                                // t
+        if (c == 2) return 2;                                    // k + 4 -> a2 / a3
+        return ((1 << tb) / 16) * 512;                           // k8 step
+    }
+    if (b < 3) return 16 << b;                                   // c32 B: [k8 step][n8 tile][hi/lo][lane][re b0 b1, im b0 b1]
+    if (b < tb) return 256 << (b - 3);
+    if (c < 2) return 4 << c;
+    if (c == 2) return 1;                                        // k + 4 -> b1
+    return ((1 << tb) / 8) * 256;
+}
+
+int gemm_mma_threads(int dtype) { return dtype == 0 ? 128 : 256; }
+// dynamic shared memory: two stages of (64 x 16 A + 64 x 16 B) x 4 tf32 planes for c32; c64 uses static storage
+size_t gemm_mma_smem_bytes(int dtype) { return dtype == 0 ? 2 * (4096 + 4096) * sizeof(float) : 0; }
+
+const void* gemm_mma_func(int dtype, int tmb, int tnb) {
+    if (tmb != 6 || tnb != 6) return nullptr;
+    return dtype == 0 ? (const void*)&gemm_tf32x3_kernel<6, 6> : (const void*)&gemm_dmma_kernel<6, 6>;
+}
+
 // Reduction-shaped nodes (few C elements, long K -- e.g. the root after the batched
 // slice variables were summed early): one warp per C element, lanes stride over k,
 // shuffle reduction.  Requires nC <= 8 (all C bits are "thread bits" in OpParams).

@@ -60,6 +60,7 @@ struct GemmParams {
     // (bits sorted by ascending global offset so consecutive threads read ascending addresses)
     long long aLoadOff[10], bLoadOff[10];
     int aLoadSm[10], bLoadSm[10];
+    int aLoadSmT[10], bLoadSmT[10];  // same for the tensor-core kernels' shared-memory layouts (gemm_mma_smem_bit)
     long long cM[6], cN[6];          // C offset of each M-tile / N-tile bit
     DSeg sAhi[kMaxSeg], sBhi[kMaxSeg], sChi[kMaxSeg];
     DSeg kA[kMaxKSeg], kB[kMaxKSeg]; // k index (all nK bits) -> offsets; chunk c covers k = c << kcb ...
@@ -68,6 +69,12 @@ struct GemmParams {
 // nullptr when the shape has no instantiation; threads = 2^(tmb + tnb - 4)
 const void* gemm_func(int dtype, int tmb, int tnb);
 int gemm_kcb(int dtype);             // K chunk bits the kernels are built for (4 for c32, 3 for c64)
+// tensor-core variant (mma.sync: DMMA for c64, 3xTF32 for c32) on the same GemmParams; nullptr when
+// the tile shape has no instantiation (needs tmb == tnb == 6)
+const void* gemm_mma_func(int dtype, int tmb, int tnb);
+int gemm_mma_threads(int dtype);
+size_t gemm_mma_smem_bytes(int dtype);
+int gemm_mma_smem_bit(int dtype, bool is_b, int tb, int bit);
 
 struct OutLeafDesc { long long offset_per_amp; int span_bits; int out_idx; };
 

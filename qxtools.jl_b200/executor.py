@@ -214,17 +214,17 @@ class Graph:
     # -- compute -------------------------------------------------------------
     def configure(self, hbm_budget_bytes: int = 0, amp_batch: int = 0, profile: bool = False,
                   cuda_graph: bool = True, sum_at_root: bool = False, smem_stage: bool = True,
-                  gemm: bool = True) -> "Graph":
+                  gemm: bool = True, gemm_mode: int = 0) -> "Graph":
         o = Options(hbm_budget_bytes, amp_batch, 1 if profile else 0, 0 if cuda_graph else 1,
-                    1 if sum_at_root else 0, 0 if smem_stage else 1, 0 if gemm else 1, 0)
+                    1 if sum_at_root else 0, 0 if smem_stage else 1, 0 if gemm else 1, gemm_mode)
         check(self._lib.qxb_graph_configure(self._h, C.byref(o)))
         return self
 
     def compile(self, hbm_budget_bytes: int = 0, amp_batch: int = 0, profile: bool = False,
                 cuda_graph: bool = True, sum_at_root: bool = False, smem_stage: bool = True,
-                gemm: bool = True) -> "Graph":
+                gemm: bool = True, gemm_mode: int = 0) -> "Graph":
         o = Options(hbm_budget_bytes, amp_batch, 1 if profile else 0, 0 if cuda_graph else 1,
-                    1 if sum_at_root else 0, 0 if smem_stage else 1, 0 if gemm else 1, 0)
+                    1 if sum_at_root else 0, 0 if smem_stage else 1, 0 if gemm else 1, gemm_mode)
         check(self._lib.qxb_graph_compile(self._h, C.byref(o)))
         self.compiled = True
         return self

@@ -125,3 +125,20 @@ def test_gemm_kernel_on_sycamore_like(gpu):
     # the program as given (no re-planning) through the GEMM path as well
     c = Graph.from_dsl(txt, data, "c64").compile()
     assert rel_err(c.amplitudes(bits[:2]), gb[:2], 53) < 1e-10
+
+
+def test_tensor_core_gemm_on_sycamore_like(gpu):
+    """Same workload through the tensor-core GEMM kernels (gemm_mode 2): DMMA for ComplexF64 must agree
+    with the SIMT kernel to fp64 rounding, 3xTF32 for ComplexF32 within the ComplexF32 tolerance."""
+    txt, data, w = bench.build_workload("sycamore53_d7_c32")
+    bits = bench.synth_bits(6, 53)
+    ref = Graph.from_dsl(txt, data, "c64", replan=32, replan_n_amp=64).compile(gemm_mode=1).amplitudes(bits)
+    t64 = Graph.from_dsl(txt, data, "c64", replan=32, replan_n_amp=64).compile(gemm_mode=2)
+    assert rel_err(t64.amplitudes(bits), ref, 53) < 1e-12
+    t32 = Graph.from_dsl(txt, data, "c32", replan=32, replan_n_amp=64).compile(gemm_mode=2)
+    assert rel_err(t32.amplitudes(bits), ref, 53) < 1e-5
+    cmds = orc.parse_dsl(txt)
+    bss = ["".join("01"[x] for x in row) for row in bits[:1]]
+    refs = orc.amplitudes(cmds, data, bss, slice_begin=17, slice_end=18)
+    assert rel_err(t64.amplitudes(bss, 17, 18), refs, 53) < 1e-10
+    assert rel_err(t32.amplitudes(bss, 17, 18), refs, 53) < 1e-5

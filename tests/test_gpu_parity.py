@@ -322,3 +322,36 @@ def test_long_k_block_reduction(gpu, dtype):
     g = Graph.from_dsl(txt, data, dtype).compile()
     got = g.amplitudes(bs)
     assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 5e-5)
+
+
+@pytest.mark.parametrize("dtype", ["c64", "c32"])
+@pytest.mark.parametrize("gemm_mode", [1, 2])
+@pytest.mark.parametrize("seed", [0, 1])
+def test_gemm_shaped_node_random(gpu, dtype, gemm_mode, seed):
+    """One GEMM-shaped node on random data with shuffled mode orders: M = 2^8, N = 2^8, K = 2^6 per
+    bitstring, through the SIMT tile kernel (gemm_mode 1) and the tensor-core kernel (gemm_mode 2:
+    DMMA for ComplexF64, 3xTF32 for ComplexF32)."""
+    rng = np.random.default_rng(100 + seed)
+    nm, nn, nk = 8, 8, 6
+    M = list(range(1, nm + 1)); N = list(range(nm + 1, nm + nn + 1)); K = list(range(nm + nn + 1, nm + nn + nk + 1))
+    o_lab = nm + nn + nk + 1
+    la = list(rng.permutation(M + K)); lb = list(rng.permutation(N + K)) + [o_lab]
+    lb2 = [x for x in lb if x != o_lab]
+    lc = list(rng.permutation(M + N))
+    A = (rng.normal(size=(2,) * len(la)) + 1j * rng.normal(size=(2,) * len(la))) / 4
+    B = (rng.normal(size=(2,) * len(lb)) + 1j * rng.normal(size=(2,) * len(lb))) / 4
+    V = (rng.normal(size=(2,) * len(lc)) + 1j * rng.normal(size=(2,) * len(lc))) / 16
+    j = lambda l: ",".join(str(int(i)) for i in l)
+    txt = ("# version: 0.4.0\n"
+           f"load a dA {j([2] * len(la))}\nload b dB {j([2] * len(lb))}\nload v dV {j([2] * len(lc))}\noutput o1 1 2\n"
+           f"ncon b2 {j(lb2)} b {j(lb)} o1 {o_lab}\n"
+           f"ncon c {j(lc)} a {j(la)} b2 {j(lb2)}\n"
+           f"ncon z 0 c {j(lc)} v {j(lc)}\nsave output z\n")
+    data = {"dA": A, "dB": B, "dV": V}
+    bs = ["0", "1", "+", "-"]
+    ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
+    g = Graph.from_dsl(txt, data, dtype).compile(gemm_mode=gemm_mode)
+    got = g.amplitudes(bs)
+    d = [o for o in g.describe()["ops"] if o["name"] == "c"][0]
+    assert d["m_bits"] == nm and d["n_bits"] == nn and d["nK"] == nk
+    assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 2e-5)
