@@ -386,7 +386,7 @@ struct Node {
 int gemm_mode(const qxb_graph* g) {
     static const int env = [] { const char* e = getenv("QXB_GEMM_MODE"); return e ? atoi(e) : 0; }();
     int m = env ? env : g->opts.gemm_mode;
-    if (m == 0) m = 1;
+    if (m == 0) m = 2;      // measured (profiles/r1p_gemm.md): DMMA 27 vs DFMA 18 TFLOP/s; 3xTF32 49 vs FFMA 38 TFLOP/s
     return m;
 }
 

@@ -20,6 +20,7 @@
 
 #include "../../include/qxb200.h"
 #include "qxb_ir.h"
+#include "qxb_treeopt.h"
 
 namespace qxb {
 
@@ -209,6 +210,35 @@ bool rotate(std::vector<Cmd>& cmds, size_t yi, int x_pos /*0: X is operand a, 1:
     return true;
 }
 
+TreeCostModel cost_model_for(double elem_bytes) {
+    TreeCostModel cm;
+    cm.elem_bytes = elem_bytes;
+    cm.bandwidth = 6.0e12;                                  // streaming kernels: 93 % of 6.45 TB/s (profiles/r1_summary.md)
+    cm.flop_rate = elem_bytes <= 8 ? 40e12 : 27e12;         // GEMM kernels: c32 SIMT / 3xTF32 ~40, c64 DMMA 27 TFLOP/s
+    return cm;
+}
+
+// modelled seconds of a lowered program: per node max(bytes / bandwidth, flops / rate)
+double lowered_cost_seconds(const Lowered& L, double n_amp, const TreeCostModel& cm) {
+    double t = 0;
+    for (const LOp& op : L.ops) {
+        const double u = L.tensors[op.c].amp ? n_amp : 1;
+        const double bytes = cm.elem_bytes * (op.elems_a * (L.tensors[op.a].amp ? n_amp : 1) +
+                                              op.elems_b * (L.tensors[op.b].amp ? n_amp : 1) + op.elems_c * u);
+        const double flops = 8.0 * op.macs_per_amp * u;
+        t += (op.phase == PH_CONST ? cm.const_weight : 1.0) * (std::max(bytes / cm.bandwidth, flops / cm.flop_rate) + cm.launch_s);
+    }
+    return t;
+}
+
+double program_seconds(const std::vector<Cmd>& cmds, double n_amp, bool early_sum, const TreeCostModel& cm) {
+    Program cand;
+    cand.cmds = cmds;
+    analyse(cand);
+    Lowered L = lower(cand, low_mask((int)cand.vars.size()), early_sum);
+    return lowered_cost_seconds(L, n_amp, cm);
+}
+
 double program_cost(const std::vector<Cmd>& cmds, double n_amp, bool early_sum, double elem_bytes) {
     Program cand;
     cand.cmds = cmds;
@@ -262,8 +292,14 @@ double refine_by_rotations(std::vector<Cmd>& cmds, double cost, double n_amp, bo
 bool replan(Program& prog, int candidates, uint64_t seed, double n_amp, bool early_sum, double* given_bytes,
             double* new_bytes, double elem_bytes) {
     if (!prog.analysed) analyse(prog);
-    const Lowered L0 = lower(prog, low_mask((int)prog.vars.size()), early_sum);
-    const double base = lowered_cost_bytes(L0, n_amp, elem_bytes);
+    const TreeCostModel cm = cost_model_for(elem_bytes);
+    double base = INFINITY, base_time = INFINITY;      // a given plan the lowering rejects (tensor too large) costs infinity
+    try {
+        const Lowered L0 = lower(prog, low_mask((int)prog.vars.size()), early_sum);
+        base = lowered_cost_bytes(L0, n_amp, elem_bytes);
+        base_time = lowered_cost_seconds(L0, n_amp, cm);
+    } catch (const Error&) {
+    }
     if (given_bytes) *given_bytes = base;
     if (new_bytes) *new_bytes = base;
 
@@ -355,17 +391,8 @@ bool replan(Program& prog, int candidates, uint64_t seed, double n_amp, bool ear
     std::string save_label = "output";
     for (const Cmd& c : prog.cmds) if (c.kind == CMD_SAVE) save_label = c.name;
 
-    std::mt19937_64 rng(seed);
-    double best = base;
-    std::vector<Cmd> best_cmds;
-    for (int it = 0; it < std::max(1, candidates); ++it) {
-        std::vector<int> order = min_fill_order(lg, it == 0 ? nullptr : &rng);
-        std::vector<PlanStep> plan;
-        std::vector<std::vector<int>> t_ids;
-        int root = -1;
-        plan_from_order(net, order, plan, t_ids, root);
-        // ---- emit
-        const int nl = (int)net.names.size();
+    // ---- emit the ncon statements of a pairwise plan (labels like build_compute_graph assigns them)
+    auto emit = [&](const std::vector<PlanStep>& plan, int root) {
         std::vector<std::string> names(net.names);
         std::vector<std::vector<int>> cur(net.modes);          // classes per mode of every tensor (DSL order)
         std::map<int, int> cnt;
@@ -395,31 +422,79 @@ bool replan(Program& prog, int candidates, uint64_t seed, double n_amp, bool ear
             cur.push_back(keep);
             cmds.push_back(std::move(c));
         }
-        (void)nl;
         Cmd sv; sv.kind = CMD_SAVE; sv.name = save_label; sv.a = names[root];
         cmds.push_back(sv);
-        // ---- score with the executor's own model
+        return cmds;
+    };
+    // ---- score with the executor's own lowering: modelled seconds (bytes for the streaming nodes, flops for
+    //      GEMM-shaped ones); a candidate the lowering rejects is simply skipped
+    double best = base_time, best_b = base;
+    std::vector<Cmd> best_cmds;
+    auto consider = [&](std::vector<Cmd>&& cmds) {
         Program cand;
         cand.cmds = cmds;
         try {
             analyse(cand);
             Lowered L = lower(cand, low_mask((int)cand.vars.size()), early_sum);
-            const double c = lowered_cost_bytes(L, n_amp, elem_bytes);
-            if (c < best) { best = c; best_cmds = std::move(cmds); }
+            const double c = lowered_cost_seconds(L, n_amp, cm);
+            if (c < best) { best = c; best_b = lowered_cost_bytes(L, n_amp, elem_bytes); best_cmds = std::move(cmds); return true; }
         } catch (const Error&) {
-            continue;                           // a candidate the lowering rejects is simply skipped
         }
+        return false;
+    };
+
+    std::mt19937_64 rng(seed);
+    std::vector<PlanStep> best_mf_plan; int best_mf_root = -1;
+    const int n_mf = std::max(1, std::min(candidates, 32));
+    for (int it = 0; it < n_mf; ++it) {
+        std::vector<int> order = min_fill_order(lg, it == 0 ? nullptr : &rng);
+        std::vector<PlanStep> plan;
+        std::vector<std::vector<int>> t_ids;
+        int root = -1;
+        plan_from_order(net, order, plan, t_ids, root);
+        if (consider(emit(plan, root))) { best_mf_plan = plan; best_mf_root = root; }
     }
-    if (best_cmds.empty()) best_cmds = prog.cmds;          // nothing cheaper among the orders: refine the given tree
+    // ---- tree search on the network (greedy restarts + subtree reconfiguration), seeded with the best order-based tree
+    {
+        TreeNet tn;
+        tn.ncls = ncls + 1;
+        tn.amp = net.amp;
+        tn.wbits.assign(ncls + 1, 0.0);
+        for (int c = 0; c < ncls; ++c) tn.wbits[c] = std::ceil(std::log2(std::max(1.0, net.dim[c])) - 1e-9);
+        tn.wbits[ncls] = std::log2(std::max(2.0, n_amp));
+        tn.total.assign(ncls + 1, 0);
+        tn.leaf_ids = net.ids;
+        for (const auto& ids : net.ids) for (int i : ids) tn.total[i]++;
+        for (size_t li = 0; li < leaf_defs.size(); ++li) tn.leaf_var.push_back(prog.defs[leaf_defs[li]].vars.empty() ? 0 : 1);
+        std::vector<std::vector<std::pair<int, int>>> seeds;
+        std::vector<int> seed_roots;
+        if (best_mf_root >= 0) {
+            std::vector<std::pair<int, int>> sp;
+            for (const PlanStep& st : best_mf_plan) sp.push_back({st.a, st.b});
+            seeds.push_back(sp); seed_roots.push_back(best_mf_root);
+        }
+        std::vector<std::pair<int, int>> tplan;
+        int troot = -1;
+        TreeReport rep;
+        optimize_tree(tn, cm, std::max(4, candidates), 24, seed ^ 0xD1B54A32D192ED03ull, seeds, seed_roots, tplan, troot, &rep);
+        std::vector<PlanStep> plan;
+        for (auto& st : tplan) plan.push_back(PlanStep{st.first, st.second});
+        consider(emit(plan, troot));
+    }
+    if (best_cmds.empty()) {                               // nothing cheaper among the candidates: refine the given tree
+        if (!std::isfinite(base)) return false;
+        best_cmds = prog.cmds;
+    }
     try {
-        best = refine_by_rotations(best_cmds, best, n_amp, early_sum, elem_bytes, 48);
+        best_b = refine_by_rotations(best_cmds, best_b, n_amp, early_sum, elem_bytes, 48);
+        best = std::min(best, program_seconds(best_cmds, n_amp, early_sum, cm));
     } catch (const Error&) {
     }
-    if (!(best < base)) return false;
+    if (!(best < base_time)) return false;
     prog.cmds = std::move(best_cmds);
     prog.analysed = false;
     analyse(prog);
-    if (new_bytes) *new_bytes = best;
+    if (new_bytes) *new_bytes = best_b;
     return true;
 }
 

@@ -1,0 +1,39 @@
+// qxb200 -- contraction-tree search (qxb_treeopt.cpp); used by the re-planner (qxb_replan.cpp).
+#pragma once
+#include <cstdint>
+#include <utility>
+#include <vector>
+
+namespace qxb {
+
+// The tensor network behind a program: index classes (wires, bonds, hyper-edges, sliced hyper-edges,
+// and one class for the bitstring axis shared by all output leaves).
+struct TreeNet {
+    int ncls = 0;
+    int amp = -1;                               // class of the bitstring axis (-1: no output leaves)
+    std::vector<double> wbits;                  // log2 of the stored extent per class (extents are padded to
+                                                // powers of two; 0 for a slice variable the caller fixes)
+    std::vector<int> total;                     // number of leaves carrying each class
+    std::vector<std::vector<int>> leaf_ids;     // classes per leaf (amp included for output leaves)
+    std::vector<char> leaf_var;                 // leaf depends on a slice variable (never constant-folded)
+};
+
+struct TreeCostModel {
+    double elem_bytes = 16;                     // 8 for ComplexF32
+    double bandwidth = 6.0e12;                  // B/s the streaming kernels reach on B200 (93 % of the measured peak)
+    double flop_rate = 27e12;                   // flop/s of the GEMM kernels (c64 DMMA 27e12, c32 ~40e12)
+    double launch_s = 0.0;
+    double const_weight = 1.0;                  // share of a constant-folded node's cost that counts (1 = as if run once per step)
+    double time(double a_bits, double b_bits, double c_bits, double union_bits) const;
+};
+
+struct TreeReport { double seconds = 0, flops = 0, bytes = 0, max_bits = 0; };
+
+// Randomised greedy construction (`restarts` trees) + the given seed plans, the best few refined by
+// subtree reconfiguration.  Returns the modelled seconds of the best tree; `plan` lists its pairwise
+// steps over tensor ids [0, n_leaves) + intermediates in creation order, `root` the last tensor.
+double optimize_tree(const TreeNet& net, const TreeCostModel& cm, int restarts, int refine_rounds, uint64_t seed,
+                     const std::vector<std::vector<std::pair<int, int>>>& seed_plans, const std::vector<int>& seed_roots,
+                     std::vector<std::pair<int, int>>& plan, int& root, TreeReport* report);
+
+}  // namespace qxb
