@@ -104,6 +104,15 @@ int64_t qxb_graph_describe(qxb_graph* g, int n_free, char* buf, int64_t buflen);
  * The planner-side counterpart is contraction_scheme, src/contraction_planning.jl:219-299, which
  * plans for one slice at a time.  given/new_bytes (may be NULL) report the model cost. */
 int  qxb_graph_replan(qxb_graph* g, int candidates, int64_t n_amp_model, double* given_bytes, double* new_bytes);
+/* Same, for a run that batches only the first n_free slice variables (the others are fixed per block, as
+ * qxb_amplitudes does when the all-batched workspace exceeds the HBM budget).  n_free = -1: all; -2: choose the
+ * count that minimises blocks x modelled seconds with the largest node (and its operands) inside budget_bytes;
+ * -3: GPU-aware slicing -- ADD slice variables (views on every leaf of the chosen index classes, exactly what
+ * build_compute_graph emits for a bond group, compute_graph.jl:39-58) until the largest tensor of the searched
+ * tree fits budget_bytes / 3; the new variables come after the file's own (v_{k+1}...).
+ * Outputs (each may be NULL): the count used, the modelled seconds of one block, algorithmic bytes before/after. */
+int  qxb_graph_replan_ex(qxb_graph* g, int candidates, int64_t n_amp_model, int n_free, int64_t budget_bytes,
+                         uint64_t seed, int* n_free_out, double* seconds_per_block, double* given_bytes, double* new_bytes);
 /* The program as .qx text (after re-planning: the re-planned one).  Returns bytes needed incl. NUL. */
 int64_t qxb_graph_program_text(qxb_graph* g, char* buf, int64_t buflen);
 /* Set options before qxb_graph_describe / qxb_graph_compile (compile(opts != NULL) overrides). */

@@ -20,7 +20,7 @@ SYMBOLS = [
     "qxb_graph_create", "qxb_graph_destroy", "qxb_graph_load", "qxb_graph_output", "qxb_graph_view",
     "qxb_graph_ncon", "qxb_graph_save", "qxb_graph_parse_dsl", "qxb_graph_set_data",
     "qxb_graph_num_outputs", "qxb_graph_num_slice_vars", "qxb_graph_num_slices", "qxb_slice_values",
-    "qxb_graph_describe", "qxb_graph_replan", "qxb_graph_program_text", "qxb_graph_configure", "qxb_graph_compile", "qxb_amplitudes", "qxb_amplitudes_device",
+    "qxb_graph_describe", "qxb_graph_replan", "qxb_graph_replan_ex", "qxb_graph_program_text", "qxb_graph_configure", "qxb_graph_compile", "qxb_amplitudes", "qxb_amplitudes_device",
     "qxb_amplitudes_subspace", "qxb_partition_vars", "qxb_graph_describe_mask", "qxb_graph_cost_bytes",
     "qxb_last_stats", "qxb_profile_dump", "qxb_debug_mma_smem_bit",
 ]
@@ -80,6 +80,8 @@ def load():
         "qxb_slice_values": (i32, [p, i64, pi64]),
         "qxb_graph_describe": (i64, [p, i32, cp, i64]),
         "qxb_graph_replan": (i32, [p, i32, i64, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "qxb_graph_replan_ex": (i32, [p, i32, i64, i32, i64, C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "qxb_graph_program_text": (i64, [p, cp, i64]),
         "qxb_graph_configure": (i32, [p, C.POINTER(Options)]),
         "qxb_graph_compile": (i32, [p, C.POINTER(Options)]),

@@ -1055,6 +1055,22 @@ int qxb_graph_replan(qxb_graph* g, int candidates, int64_t n_amp_model, double* 
     });
 }
 
+int qxb_graph_replan_ex(qxb_graph* g, int candidates, int64_t n_amp_model, int n_free, int64_t budget_bytes,
+                        uint64_t seed, int* n_free_out, double* seconds_per_block, double* given_bytes, double* new_bytes) {
+    return guard([&] {
+        need_graph(g);
+        ensure_analysed(g);
+        double a = 0, b = 0, sec = 0;
+        int nf = 0;
+        replan(g->prog, candidates, seed ? seed : 0x9E3779B97F4A7C15ull, (double)std::max<int64_t>(n_amp_model, 1),
+               !g->opts.sum_at_root, &a, &b, (double)g->es(), n_free, (double)budget_bytes, &nf, &sec);
+        if (given_bytes) *given_bytes = a;
+        if (new_bytes) *new_bytes = b;
+        if (n_free_out) *n_free_out = nf;
+        if (seconds_per_block) *seconds_per_block = sec;
+    });
+}
+
 int64_t qxb_graph_program_text(qxb_graph* g, char* buf, int64_t buflen) {
     int64_t need = 0;
     int rc = guard([&] {

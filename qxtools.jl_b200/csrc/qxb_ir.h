@@ -148,8 +148,12 @@ std::vector<int> partition_vars(const Program& p, int n_parts, bool early_sum = 
 double lowered_cost_bytes(const Lowered& L, double n_amp, double elem_bytes);
 // Batch-aware re-planning of the ncon tree (qxb_replan.cpp).  Returns true when a cheaper
 // program replaced p.cmds (leaf statements are kept verbatim).
+// n_free: how many slice variables (v1..v_n_free) the plan is optimised and scored for as batched, the rest
+// being fixed per block; -1 = all, -2 = choose the count that minimises blocks x modelled seconds under
+// budget_bytes (largest node with its operands).  seconds_out: modelled seconds of one block.
 bool replan(Program& p, int candidates, uint64_t seed, double n_amp, bool early_sum, double* given_bytes,
-            double* new_bytes, double elem_bytes);
+            double* new_bytes, double elem_bytes, int n_free = -1, double budget_bytes = 0, int* n_free_out = nullptr,
+            double* seconds_out = nullptr);
 std::string program_text(const Program& p);
 // Plan arena offsets (fills LTensor::offset, the arena sizes and the write-after-read edges).
 // Chunk-phase offsets are per bitstring row and scale with the batch at launch time.

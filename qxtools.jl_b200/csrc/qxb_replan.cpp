@@ -12,6 +12,8 @@
 // views are kept verbatim; only the ncon statements are re-derived -- an exact
 // re-association, the program's value is unchanged.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <map>
 #include <random>
@@ -210,6 +212,13 @@ bool rotate(std::vector<Cmd>& cmds, size_t yi, int x_pos /*0: X is operand a, 1:
     return true;
 }
 
+// number of batched (free) slice variables the plan is scored for; -1 = all (set by replan for its helpers)
+thread_local int g_plan_n_free = -1;
+uint64_t plan_mask(size_t n_vars) {
+    const int k = (int)n_vars;
+    return low_mask(g_plan_n_free < 0 || g_plan_n_free > k ? k : g_plan_n_free);
+}
+
 TreeCostModel cost_model_for(double elem_bytes) {
     TreeCostModel cm;
     cm.elem_bytes = elem_bytes;
@@ -235,7 +244,7 @@ double program_seconds(const std::vector<Cmd>& cmds, double n_amp, bool early_su
     Program cand;
     cand.cmds = cmds;
     analyse(cand);
-    Lowered L = lower(cand, low_mask((int)cand.vars.size()), early_sum);
+    Lowered L = lower(cand, plan_mask(cand.vars.size()), early_sum);
     return lowered_cost_seconds(L, n_amp, cm);
 }
 
@@ -243,7 +252,7 @@ double program_cost(const std::vector<Cmd>& cmds, double n_amp, bool early_sum, 
     Program cand;
     cand.cmds = cmds;
     analyse(cand);
-    Lowered L = lower(cand, low_mask((int)cand.vars.size()), early_sum);
+    Lowered L = lower(cand, plan_mask(cand.vars.size()), early_sum);
     return lowered_cost_bytes(L, n_amp, elem_bytes);
 }
 
@@ -254,7 +263,7 @@ double refine_by_rotations(std::vector<Cmd>& cmds, double cost, double n_amp, bo
         Program cur;
         cur.cmds = cmds;
         analyse(cur);
-        Lowered L = lower(cur, low_mask((int)cur.vars.size()), early_sum);
+        Lowered L = lower(cur, plan_mask(cur.vars.size()), early_sum);
         std::map<std::string, int> uses;
         for (const Cmd& c : cmds)
             if (c.kind == CMD_NCON) { uses[c.a]++; uses[c.b]++; } else if (c.kind == CMD_VIEW || c.kind == CMD_SAVE) uses[c.a]++;
@@ -290,12 +299,19 @@ double refine_by_rotations(std::vector<Cmd>& cmds, double cost, double n_amp, bo
 }  // namespace
 
 bool replan(Program& prog, int candidates, uint64_t seed, double n_amp, bool early_sum, double* given_bytes,
-            double* new_bytes, double elem_bytes) {
+            double* new_bytes, double elem_bytes, int n_free, double budget_bytes, int* n_free_out, double* seconds_out) {
     if (!prog.analysed) analyse(prog);
+    const int n_vars = (int)prog.vars.size();
+    const bool auto_free = n_free == -2;
+    const bool autoslice = n_free == -3;
+    g_plan_n_free = (auto_free || autoslice) ? -1 : n_free;
+    struct Reset { ~Reset() { g_plan_n_free = -1; } } reset_guard;
+    if (n_free_out) *n_free_out = g_plan_n_free < 0 ? n_vars : std::min(g_plan_n_free, n_vars);
+    if (seconds_out) *seconds_out = INFINITY;
     const TreeCostModel cm = cost_model_for(elem_bytes);
     double base = INFINITY, base_time = INFINITY;      // a given plan the lowering rejects (tensor too large) costs infinity
     try {
-        const Lowered L0 = lower(prog, low_mask((int)prog.vars.size()), early_sum);
+        const Lowered L0 = lower(prog, plan_mask(prog.vars.size()), early_sum);
         base = lowered_cost_bytes(L0, n_amp, elem_bytes);
         base_time = lowered_cost_seconds(L0, n_amp, cm);
     } catch (const Error&) {
@@ -364,6 +380,11 @@ bool replan(Program& prog, int candidates, uint64_t seed, double n_amp, bool ear
     for (size_t li = 0; li < leaf_defs.size(); ++li) {
         const TensorDef& d = prog.defs[leaf_defs[li]];
         for (size_t m = 0; m < d.modes.size(); ++m) net.dim[net.modes[li][m]] = (double)d.modes[m].full_ext;
+    }
+    std::vector<int> cls_var(ncls + 1, -1);            // slice variable a class is viewed with (-1: none)
+    for (size_t li = 0; li < leaf_defs.size(); ++li) {
+        const TensorDef& d = prog.defs[leaf_defs[li]];
+        for (size_t m = 0; m < d.modes.size(); ++m) if (d.modes[m].var >= 0) cls_var[net.modes[li][m]] = d.modes[m].var;
     }
     bool any_out = false;
     for (size_t li = 0; li < leaf_defs.size(); ++li)
@@ -435,7 +456,7 @@ bool replan(Program& prog, int candidates, uint64_t seed, double n_amp, bool ear
         cand.cmds = cmds;
         try {
             analyse(cand);
-            Lowered L = lower(cand, low_mask((int)cand.vars.size()), early_sum);
+            Lowered L = lower(cand, plan_mask(cand.vars.size()), early_sum);
             const double c = lowered_cost_seconds(L, n_amp, cm);
             if (c < best) { best = c; best_b = lowered_cost_bytes(L, n_amp, elem_bytes); best_cmds = std::move(cmds); return true; }
         } catch (const Error&) {
@@ -455,17 +476,122 @@ bool replan(Program& prog, int candidates, uint64_t seed, double n_amp, bool ear
         if (consider(emit(plan, root))) { best_mf_plan = plan; best_mf_root = root; }
     }
     // ---- tree search on the network (greedy restarts + subtree reconfiguration), seeded with the best order-based tree
-    {
+    auto make_tn = [&](int nf) {
         TreeNet tn;
         tn.ncls = ncls + 1;
         tn.amp = net.amp;
         tn.wbits.assign(ncls + 1, 0.0);
-        for (int c = 0; c < ncls; ++c) tn.wbits[c] = std::ceil(std::log2(std::max(1.0, net.dim[c])) - 1e-9);
+        for (int c = 0; c < ncls; ++c) {
+            const bool fixed = cls_var[c] >= 0 && nf >= 0 && cls_var[c] >= nf;          // variables >= nf are fixed by the caller
+            tn.wbits[c] = fixed ? 0.0 : std::ceil(std::log2(std::max(1.0, net.dim[c])) - 1e-9);
+        }
         tn.wbits[ncls] = std::log2(std::max(2.0, n_amp));
         tn.total.assign(ncls + 1, 0);
         tn.leaf_ids = net.ids;
         for (const auto& ids : net.ids) for (int i : ids) tn.total[i]++;
         for (size_t li = 0; li < leaf_defs.size(); ++li) tn.leaf_var.push_back(prog.defs[leaf_defs[li]].vars.empty() ? 0 : 1);
+        return tn;
+    };
+    if (getenv("QXB_TREEOPT_PROBE")) {                     // planner experiments: search only, print the report
+        const int rounds = atoi(getenv("QXB_TREEOPT_PROBE"));
+        TreeNet tn = make_tn(g_plan_n_free);
+        std::vector<std::pair<int, int>> tplan; int troot = -1; TreeReport rep;
+        optimize_tree(tn, cm, std::max(1, candidates), rounds, seed, {}, {}, tplan, troot, &rep);
+        fprintf(stderr, "[treeopt] restarts %d rounds %d n_free %d: %.4g s (2^%.2f flops, %.4g GB, largest node 2^%.0f)\n",
+                candidates, rounds, g_plan_n_free, rep.seconds, std::log2(std::max(rep.flops, 1.0)), rep.bytes / 1e9, rep.max_bits);
+        return false;
+    }
+    if (autoslice) {
+        // GPU-aware slicing: search a tree for the network as it is, then add slice variables
+        // (views on every leaf of the chosen index classes, like build_compute_graph does for a bond group,
+        // compute_graph.jl:39-58) until the largest tensor fits the budget.  Exact: a sliced index is summed by
+        // the executor's slice loop instead of inside a contraction.
+        TreeNet tn = make_tn(-1);
+        std::vector<std::vector<std::pair<int, int>>> seeds;
+        std::vector<int> seed_roots;
+        if (best_mf_root >= 0) {
+            std::vector<std::pair<int, int>> sp;
+            for (const PlanStep& st : best_mf_plan) sp.push_back({st.a, st.b});
+            seeds.push_back(sp); seed_roots.push_back(best_mf_root);
+        }
+        std::vector<std::pair<int, int>> tplan;
+        int troot = -1;
+        TreeReport rep, rep2;
+        optimize_tree(tn, cm, std::max(4, candidates), 32, seed ^ 0xD1B54A32D192ED03ull, seeds, seed_roots, tplan, troot, &rep);
+        const double max_node_bits = std::floor(std::log2(std::max(budget_bytes, 3.0 * elem_bytes) / (3.0 * elem_bytes)));
+        std::vector<char> sliceable(ncls + 1, 0);
+        for (int c = 0; c < ncls; ++c) sliceable[c] = cls_var[c] < 0;
+        const std::vector<int> chosen = slice_tree(tn, cm, tplan, troot, max_node_bits, sliceable, 48, seed, &rep2);
+        if (getenv("QXB_REPLAN_VERBOSE")) {
+            double blocks = 1;
+            for (int c : chosen) blocks *= net.dim[c];
+            fprintf(stderr, "[autoslice] unsliced tree %.3g s (2^%.1f flops, largest 2^%.0f); %zu indices sliced (%.3g slices): "
+                            "%.3g s per slice, largest 2^%.0f -> %.3g s\n", rep.seconds, std::log2(std::max(rep.flops, 1.0)),
+                    rep.max_bits, chosen.size(), blocks, rep2.seconds, rep2.max_bits, rep2.seconds * blocks);
+        }
+        if (rep2.max_bits > max_node_bits) return false;
+        for (size_t j = 0; j < chosen.size(); ++j) {
+            const int c = chosen[j];
+            const std::string sym = "v" + std::to_string(n_vars + (int)j + 1);
+            for (size_t li = 0; li < net.modes.size(); ++li) {
+                for (size_t m = 0; m < net.modes[li].size(); ++m) {
+                    if (net.modes[li][m] != c) continue;
+                    Cmd v; v.kind = CMD_VIEW;
+                    v.name = net.names[li] + "_s";
+                    while (taken.count(v.name)) v.name += "_s";
+                    taken.insert(v.name);
+                    v.a = net.names[li]; v.label = sym; v.idx = (int64_t)m + 1; v.dim = (int64_t)net.dim[c];
+                    leaf_cmds.push_back(v);
+                    net.names[li] = v.name;
+                }
+            }
+        }
+        std::vector<PlanStep> plan;
+        for (auto& st : tplan) plan.push_back(PlanStep{st.first, st.second});
+        std::vector<Cmd> cmds = emit(plan, troot);
+        Program cand;
+        cand.cmds = cmds;
+        analyse(cand);
+        const Lowered L = lower(cand, low_mask(n_vars), early_sum);      // the new variables fixed (one slice per block)
+        if (seconds_out) *seconds_out = lowered_cost_seconds(L, n_amp, cm);
+        if (new_bytes) *new_bytes = lowered_cost_bytes(L, n_amp, elem_bytes);
+        if (n_free_out) *n_free_out = n_vars;
+        prog.cmds = std::move(cmds);
+        prog.analysed = false;
+        analyse(prog);
+        return true;
+    }
+    if (auto_free) {
+        // how many variables to batch: the count that minimises (blocks x modelled seconds of the best quick tree)
+        // among those whose largest node (three operands live) fits the budget
+        double best_total = INFINITY;
+        int best_nf = -1;
+        for (int nf = n_vars; nf >= 0; --nf) {
+            TreeNet tn = make_tn(nf);
+            std::vector<std::pair<int, int>> tplan; int troot = -1; TreeReport rep;
+            optimize_tree(tn, cm, 6, 6, seed ^ (uint64_t)nf, {}, {}, tplan, troot, &rep);
+            double blocks = 1;
+            for (int v = nf; v < n_vars; ++v) blocks *= (double)prog.vars[v].dim;
+            const bool fits = budget_bytes <= 0 || 3.0 * elem_bytes * std::exp2(rep.max_bits) <= budget_bytes;
+            if (getenv("QXB_REPLAN_VERBOSE"))
+                fprintf(stderr, "[replan] n_free %d: blocks %.3g, quick tree %.3g s/block (2^%.1f flops, %.3g GB, largest node 2^%.0f) -> %.3g s%s\n",
+                        nf, blocks, rep.seconds, std::log2(std::max(rep.flops, 1.0)), rep.bytes / 1e9, rep.max_bits,
+                        rep.seconds * blocks, fits ? "" : "  (over budget)");
+            if (fits && rep.seconds * blocks < best_total) { best_total = rep.seconds * blocks; best_nf = nf; }
+            if (fits && rep.seconds * blocks > 4.0 * best_total) break;                  // further fixing only multiplies the work
+        }
+        if (best_nf < 0) return false;
+        g_plan_n_free = best_nf;
+        if (n_free_out) *n_free_out = best_nf;
+        best = INFINITY; best_b = INFINITY; best_cmds.clear();                          // re-score everything for this mask
+        try {
+            const Lowered L0 = lower(prog, plan_mask(prog.vars.size()), early_sum);
+            best = lowered_cost_seconds(L0, n_amp, cm); best_b = lowered_cost_bytes(L0, n_amp, elem_bytes);
+            base_time = best;
+        } catch (const Error&) { base_time = INFINITY; }
+    }
+    {
+        TreeNet tn = make_tn(g_plan_n_free);
         std::vector<std::vector<std::pair<int, int>>> seeds;
         std::vector<int> seed_roots;
         if (best_mf_root >= 0) {
@@ -495,6 +621,7 @@ bool replan(Program& prog, int candidates, uint64_t seed, double n_amp, bool ear
     prog.analysed = false;
     analyse(prog);
     if (new_bytes) *new_bytes = best_b;
+    if (seconds_out) *seconds_out = best;
     return true;
 }
 

@@ -18,6 +18,7 @@
 #include <cmath>
 #include <functional>
 #include <cstdint>
+#include <cstdlib>
 #include <map>
 #include <queue>
 #include <random>
@@ -103,6 +104,18 @@ struct Tree {
             n[t].amp = net->amp >= 0 && std::binary_search(ids.begin(), ids.end(), net->amp);
             n[t].var = net->leaf_var[t] != 0;
             n[t].bits = bits_of(n[t].ids);
+        }
+    }
+    void recompute_all() {                         // children before parents (slots are reused by reconfiguration)
+        const int nl = (int)net->leaf_ids.size();
+        for (int t = 0; t < nl; ++t) { n[t].bits = bits_of(n[t].ids); n[t].var = net->leaf_var[t] != 0; }
+        std::vector<std::pair<int, int>> st{{root, 0}};
+        while (!st.empty()) {
+            auto [v, state] = st.back();
+            st.pop_back();
+            if (n[v].l < 0) continue;
+            if (state == 0) { st.push_back({v, 1}); st.push_back({n[v].r, 0}); st.push_back({n[v].l, 0}); }
+            else recompute(v);
         }
     }
     int add(int a, int b) {
@@ -368,7 +381,7 @@ double optimize_tree(const TreeNet& net, const TreeCostModel& cm, int restarts, 
                      const std::vector<std::vector<std::pair<int, int>>>& seeds_plans, const std::vector<int>& seeds_roots,
                      std::vector<std::pair<int, int>>& plan, int& root, TreeReport* report) {
     std::mt19937_64 rng(seed);
-    const int L = 10;
+    const int L = getenv("QXB_TREEOPT_L") ? atoi(getenv("QXB_TREEOPT_L")) : 10;
     double best = -1;
     Tree bestT;
     auto consider = [&](Tree& T) {
@@ -381,7 +394,7 @@ double optimize_tree(const TreeNet& net, const TreeCostModel& cm, int restarts, 
         const double c = T.total();
         pool.push_back({c, std::move(T)});
         std::sort(pool.begin(), pool.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
-        if (pool.size() > 4) pool.pop_back();
+        if (pool.size() > 8) pool.pop_back();
     };
     for (size_t s = 0; s < seeds_plans.size(); ++s) {
         Tree T; T.net = &net; T.cm = &cm;
@@ -418,6 +431,47 @@ double optimize_tree(const TreeNet& net, const TreeCostModel& cm, int restarts, 
         report->flops = fl; report->bytes = by;
     }
     return best;
+}
+
+std::vector<int> slice_tree(TreeNet net, const TreeCostModel& cm, std::vector<std::pair<int, int>>& plan, int& root,
+                            double max_node_bits, const std::vector<char>& sliceable, int max_slices, uint64_t seed,
+                            TreeReport* report) {
+    std::mt19937_64 rng(seed);
+    Tree T; T.net = &net; T.cm = &cm;
+    tree_from_plan(T, plan, root);
+    std::vector<int> chosen;
+    const int nl = (int)net.leaf_ids.size();
+    while ((int)chosen.size() < max_slices) {
+        int big = -1;
+        for (int v = 0; v < (int)T.n.size(); ++v) if (big < 0 || T.n[v].bits > T.n[big].bits) big = v;
+        if (T.n[big].bits <= max_node_bits) break;
+        // candidates: the classes of the largest node (and of its operands)
+        std::set<int> cands;
+        auto collect = [&](int v) { for (auto& ic : T.n[v].ids) if (ic.first != net.amp && net.wbits[ic.first] > 0 && sliceable[ic.first]) cands.insert(ic.first); };
+        collect(big);
+        if (T.n[big].l >= 0) { collect(T.n[big].l); collect(T.n[big].r); }
+        if (cands.empty()) break;
+        int pick = -1; double best = -1;
+        for (int c : cands) {
+            const double w = net.wbits[c];
+            net.wbits[c] = 0;
+            T.recompute_all();
+            // work of all slices of this index; prefer indices that also shrink the largest node
+            const double tot = T.total() * std::exp2(w) * (T.max_bits() < T.n[big].bits ? 1.0 : 4.0);
+            net.wbits[c] = w;
+            if (pick < 0 || tot < best) { pick = c; best = tot; }
+        }
+        net.wbits[pick] = 0;
+        for (int t = 0; t < nl; ++t)
+            if (std::find(net.leaf_ids[t].begin(), net.leaf_ids[t].end(), pick) != net.leaf_ids[t].end()) net.leaf_var[t] = 1;
+        T.recompute_all();
+        chosen.push_back(pick);
+        refine(T, 2, 10, rng);
+    }
+    refine(T, 8, 10, rng);
+    tree_to_plan(T, plan, root);
+    if (report) { report->seconds = T.total(); report->max_bits = T.max_bits(); report->flops = 0; report->bytes = 0; }
+    return chosen;
 }
 
 }  // namespace qxb

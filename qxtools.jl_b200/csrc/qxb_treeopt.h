@@ -36,4 +36,11 @@ double optimize_tree(const TreeNet& net, const TreeCostModel& cm, int restarts, 
                      const std::vector<std::vector<std::pair<int, int>>>& seed_plans, const std::vector<int>& seed_roots,
                      std::vector<std::pair<int, int>>& plan, int& root, TreeReport* report);
 
+// GPU-aware slicing: starting from `plan`, zero the extent of one index class at a time (the class whose slicing
+// costs the least total work among those of the largest node) until no tensor exceeds 2^max_node_bits elements;
+// the tree is re-refined after every choice.  Returns the chosen classes in order; plan/root are updated.
+std::vector<int> slice_tree(TreeNet net, const TreeCostModel& cm, std::vector<std::pair<int, int>>& plan, int& root,
+                            double max_node_bits, const std::vector<char>& sliceable, int max_slices, uint64_t seed,
+                            TreeReport* report);
+
 }  // namespace qxb

@@ -142,12 +142,16 @@ class Graph:
         check(self._lib.qxb_graph_describe(self._h, n_free, buf, need))
         return json.loads(buf.value.decode())
 
-    def replan(self, candidates: int = 24, n_amp: int = 1024) -> dict:
-        """In-library batch-aware re-planning (qxb_graph_replan); call before compile()."""
-        a, b = C.c_double(), C.c_double()
-        check(self._lib.qxb_graph_replan(self._h, candidates, n_amp, C.byref(a), C.byref(b)))
-        self.replan_info = {"replanned": b.value < a.value, "given_bytes": a.value, "bytes": b.value,
-                            "candidates": candidates, "n_amp_model": n_amp}
+    def replan(self, candidates: int = 24, n_amp: int = 1024, n_free: int = -1, budget_bytes: int = 0,
+               seed: int = 0) -> dict:
+        """In-library batch-aware re-planning (qxb_graph_replan_ex); call before compile().
+        ``n_free``: slice variables batched per block (-1 all, -2 chosen against ``budget_bytes``)."""
+        a, b, sec, nf = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+        check(self._lib.qxb_graph_replan_ex(self._h, candidates, n_amp, n_free, budget_bytes, seed, C.byref(nf),
+                                            C.byref(sec), C.byref(a), C.byref(b)))
+        self.replan_info = {"replanned": np.isfinite(sec.value), "given_bytes": a.value, "bytes": b.value,
+                            "candidates": candidates, "n_amp_model": n_amp, "n_free": nf.value,
+                            "model_seconds_per_block": sec.value}
         self.text = self.program_text()
         return self.replan_info
 

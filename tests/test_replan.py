@@ -99,3 +99,38 @@ def test_in_library_replan_keeps_programs_it_cannot_improve(lib_built):
     got = orc.amplitudes(orc.parse_dsl(g.program_text()), data, ["00", "11", "01", "10"])
     assert np.allclose(got, [1 / np.sqrt(2), 1 / np.sqrt(2), 0, 0], atol=1e-15)
     assert info["bytes"] <= info["given_bytes"]
+
+
+@pytest.mark.parametrize("case", ["rqc_unsliced", "rqc_sliced", "fsim"])
+def test_autoslice_adds_exact_slice_variables(lib_built, case):
+    """GPU-aware slicing (qxb_graph_replan_ex, n_free = -3): with a budget far below the largest tensor of the
+    searched tree the library must ADD slice variables (views on every leaf of the chosen index classes) and the
+    sliced program must still produce the original amplitudes -- summed over all slices, and range by range."""
+    if case == "rqc_unsliced":
+        txt, data, bs = circuit_case(q.create_rqc_circuit(4, 4, 14, 7), n_slice=0, n_amp=4)
+        n_q = 16
+    elif case == "rqc_sliced":
+        txt, data, bs = rqc_case(4, 4, 14, 2, n_amp=4)
+        n_q = 16
+    else:
+        txt, data, bs = circuit_case(q.create_sycamore_like_circuit(8, seed=3, n_qubits=18), n_slice=0, n_amp=4)
+        n_q = 18
+    lim = 5 if case == "fsim" else 4                                      # no tensor above 2^lim elements
+    c0 = orc.parse_dsl(txt)
+    g = Graph.from_dsl(txt, data, "c64")
+    k0 = len(g.slice_dims)
+    info = g.replan(8, 1, n_free=-3, budget_bytes=3 * 16 * 2 ** lim)
+    g2 = Graph.from_dsl(g.text, data, "c64")
+    assert info["replanned"] and len(g2.slice_dims) > k0 and info["n_free"] == k0
+    assert g2.slice_dims[:k0] == g.slice_dims[:k0]
+    c1 = orc.parse_dsl(g.text)
+    ref = orc.amplitudes(c0, data, bs)
+    assert np.allclose(orc.amplitudes(c1, data, bs), ref, atol=1e-14)
+    S = g2.n_slices
+    parts = sum(orc.amplitudes(c1, data, bs, slice_begin=b, slice_end=min(b + 5, S)) for b in range(0, S, 5))
+    assert np.allclose(parts, ref, atol=1e-14)
+    # every tensor of the sliced program, one slice at a time, is within the budget
+    d = g2.describe(k0)
+    assert max(o["nC"] for o in d["ops"] if o["phase"] != "const") <= lim
+    # and the lowered form executes correctly
+    assert np.allclose(em.amplitudes(g2, data, bits_from_strings(bs, n_q), shuffle_seed=5), ref, atol=1e-13)
