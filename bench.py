@@ -43,6 +43,10 @@ WORKLOADS = {
     # towards configs[4]: Sycamore-like 53 qubits (fSim, extent-4 bonds), depth 7, ComplexF32, 8 sliced bonds.
     # GEMM-shaped nodes (K up to 512): compute-bound, unlike the RQC grids.  Depth 12 needs a stronger planner.
     "sycamore53_d7_c32": dict(sycamore=7, rows=53, cols=1, n_slice=8, dtype="c32", seed=1),
+    # BASELINE.json configs[4]: Sycamore-like 53 qubits, 12 cycles, ComplexF32; sliced by the library's GPU-aware
+    # slicing so that the largest tensor of a slice is 2^31 elements (17 GB in HBM); file written by
+    # workloads/make_sycamore12.py.  A parity / capability case (scripts/probe_syc12.py), not a bench line.
+    "sycamore53_d12_c32_s2048": dict(sycamore=12, rows=53, cols=1, n_slice=0, dtype="c32", seed=1),
 }
 DEFAULT_WORKLOAD = "rqc_7x7_d20_c64_s4096"
 
@@ -459,7 +463,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="qxb200", choices=["qxb200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--amps", type=int, default=32768, help="bitstrings per step")
+    ap.add_argument("--amps", type=int, default=131072, help="bitstrings per step")
     ap.add_argument("--amp-batch", type=int, default=0)
     ap.add_argument("--ref-slices", type=int, default=64, help="slices per bitstring in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")

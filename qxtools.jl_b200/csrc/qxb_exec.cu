@@ -298,7 +298,8 @@ void build_templates(Variant& v, int dtype) {
             for (auto& s : op.segKB) b |= (long long)((k >> s.src) & ((1 << s.len) - 1)) << s.dst;
             p.ktabA[k] = a; p.ktabB[k] = b;
         }
-        // ---- GEMM-shaped node?  (K >= 2^kcb, >= 5 M-only and >= 5 N-only bits, spans <= 2^30)
+        // ---- GEMM-shaped node?  (K >= 2^kcb, >= 5 M-only and >= 5 N-only bits, spans <= 2^31: the kernels add
+        //      distinct power-of-two offsets below 2^31 in 32-bit registers)
         const int kcb = gemm_kcb(dtype);
         std::vector<int> mall, nall;
         for (int b = 0; b < nC; ++b) {
@@ -306,7 +307,7 @@ void build_templates(Variant& v, int dtype) {
             else if (mapB[b] >= 0 && mapA[b] < 0) nall.push_back(b);
         }
         const LTensor &TA = v.L.tensors[op.a], &TB = v.L.tensors[op.b];
-        if (op.nK >= kcb && mall.size() >= 5 && nall.size() >= 5 && nC <= 30 && TA.span_bits <= 30 && TB.span_bits <= 30) {
+        if (op.nK >= kcb && mall.size() >= 5 && nall.size() >= 5 && nC <= 31 && TA.span_bits <= 31 && TB.span_bits <= 31) {
             GemmParams& q = v.gtmpl[i];
             memset(&q, 0, sizeof(q));
             const int tmb = (int)std::min<size_t>(6, mall.size()), tnb = (int)std::min<size_t>(6, nall.size());
@@ -370,6 +371,7 @@ struct Node {
     std::vector<size_t> argoff;          // offset of each argument in argmem
     std::vector<int> deps;
     void* ms_ptr = nullptr; size_t ms_bytes = 0;
+    void* pre_zero_ptr = nullptr; size_t pre_zero_bytes = 0;   // kernel nodes: region to clear first (split-K partial sums)
     int variant = -1, op = -1;           // contraction nodes: where to book profile time
     double flops = 0, bytes = 0;
     size_t smem = 0;
@@ -443,7 +445,16 @@ Node contract_node(const RunCtx& c, int i) {
     }
     if (p.nK >= 5 && p.nC <= 8 && outputs < 32768.0) {
         // reduction-shaped: too few outputs to fill the GPU with one thread each
-        if (p.nK >= 12 && outputs <= 8192.0) {
+        if (p.nK >= 16 && outputs * 2 <= (double)cap && !g->opts.no_gemm) {
+            // huge K, a handful of outputs (root of a GEMM-shaped tree): split K over several blocks per output
+            int sb = 0;
+            while (outputs * std::ldexp(1.0, sb) < (double)cap && p.nK - sb > 13) ++sb;
+            p.kc = sb;
+            n.func = kreduce_split_func(g->dtype);
+            n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>((long long)std::ldexp(outputs, sb), cap)));
+            n.pre_zero_ptr = p.C;                                // partial sums are combined with atomicAdd
+            n.pre_zero_bytes = (size_t)((C.amp ? c.n : 1) << C.span_bits) * g->es();
+        } else if (p.nK >= 12 && outputs <= 8192.0) {
             n.func = kreduce_block_func(g->dtype);           // very long K, few outputs: a block per output
             n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>((long long)outputs, cap)));
         } else {
@@ -486,6 +497,7 @@ Node contract_node(const RunCtx& c, int i) {
 
 void launch_node(const Node& n, cudaStream_t st) {
     if (!n.func) { CUDA_OK(cudaMemsetAsync(n.ms_ptr, 0, n.ms_bytes, st)); return; }
+    if (n.pre_zero_bytes) CUDA_OK(cudaMemsetAsync(n.pre_zero_ptr, 0, n.pre_zero_bytes, st));
     void* args[12];
     for (size_t a = 0; a < n.argoff.size(); ++a) args[a] = (void*)(n.argmem.data() + n.argoff[a]);
     CUDA_OK(cudaLaunchKernel(n.func, n.grid, n.block, args, n.smem, st));
@@ -757,6 +769,14 @@ cudaGraphExec_t instantiate(const std::vector<Node>& nodes) {
                 mp.dst = n.ms_ptr; mp.value = 0; mp.elementSize = 1; mp.width = n.ms_bytes; mp.height = 1; mp.pitch = n.ms_bytes;
                 CUDA_OK(cudaGraphAddMemsetNode(&gn[i], graph, deps.data(), deps.size(), &mp));
             } else {
+                if (n.pre_zero_bytes) {          // clear C first; the kernel then depends on the memset alone
+                    cudaMemsetParams mp{};
+                    mp.dst = n.pre_zero_ptr; mp.value = 0; mp.elementSize = 1; mp.width = n.pre_zero_bytes; mp.height = 1;
+                    mp.pitch = n.pre_zero_bytes;
+                    cudaGraphNode_t z = nullptr;
+                    CUDA_OK(cudaGraphAddMemsetNode(&z, graph, deps.data(), deps.size(), &mp));
+                    deps.assign(1, z);
+                }
                 void* args[12];
                 for (size_t a = 0; a < n.argoff.size(); ++a) args[a] = (void*)(n.argmem.data() + n.argoff[a]);
                 cudaKernelNodeParams kp{};

@@ -820,6 +820,69 @@ kreduce_block_kernel(const __grid_constant__ OpParams p) {
     }
 }
 
+// Split-K variant for the root-like nodes of GEMM-shaped trees (K = 2^20 .. 2^30 against a handful of
+// outputs): 2^p.kc blocks share one output, each reduces a contiguous 1 / 2^p.kc of the k range and adds its
+// partial sum into C with atomicAdd (C is zeroed by a memset node in front of this launch).  With one block per
+// output such a node leaves most of the SMs idle and is latency-bound on a few KB of loads in flight.
+template <typename R2>
+__global__ void __launch_bounds__(kThreads)
+kreduce_split_kernel(const __grid_constant__ OpParams p) {
+    const R2* __restrict__ A = reinterpret_cast<const R2*>(p.A);
+    const R2* __restrict__ B = reinterpret_cast<const R2*>(p.B);
+    R2* __restrict__ C = reinterpret_cast<R2*>(p.C);
+    __shared__ R2 part[kThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sb = p.kc;                                         // log2 of the splits per output
+    const long long total = ((long long)p.U << p.nC) << sb;
+    const unsigned cmask = (1u << p.nC) - 1u;
+    const long long Kc = 1ll << (p.nK - sb);
+    for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+        const long long o = w >> sb;
+        const long long k0 = (w & ((1ll << sb) - 1ll)) * Kc;
+        const long long u = o >> p.nC;
+        const unsigned c = (unsigned)o & cmask;
+        const R2* Ap = A + u * p.sUA + segeval(p.sAlo, p.nsAlo, c);
+        const R2* Bp = B + u * p.sUB + segeval(p.sBlo, p.nsBlo, c);
+        R2 acc0, acc1, acc2, acc3;
+        acc0.x = acc0.y = acc1.x = acc1.y = acc2.x = acc2.y = acc3.x = acc3.y = 0;
+        long long k = threadIdx.x;
+        for (; k + 3 * kThreads < Kc; k += 4 * kThreads) {       // 8 loads in flight per thread
+            const R2 a0 = __ldg(Ap + segeval(p.kA, p.nkA, (unsigned long long)(k0 + k)));
+            const R2 b0 = __ldg(Bp + segeval(p.kB, p.nkB, (unsigned long long)(k0 + k)));
+            const R2 a1 = __ldg(Ap + segeval(p.kA, p.nkA, (unsigned long long)(k0 + k + kThreads)));
+            const R2 b1 = __ldg(Bp + segeval(p.kB, p.nkB, (unsigned long long)(k0 + k + kThreads)));
+            const R2 a2 = __ldg(Ap + segeval(p.kA, p.nkA, (unsigned long long)(k0 + k + 2 * kThreads)));
+            const R2 b2 = __ldg(Bp + segeval(p.kB, p.nkB, (unsigned long long)(k0 + k + 2 * kThreads)));
+            const R2 a3 = __ldg(Ap + segeval(p.kA, p.nkA, (unsigned long long)(k0 + k + 3 * kThreads)));
+            const R2 b3 = __ldg(Bp + segeval(p.kB, p.nkB, (unsigned long long)(k0 + k + 3 * kThreads)));
+            cmac(acc0, a0, b0); cmac(acc1, a1, b1); cmac(acc2, a2, b2); cmac(acc3, a3, b3);
+        }
+        for (; k < Kc; k += kThreads)
+            cmac(acc0, __ldg(Ap + segeval(p.kA, p.nkA, (unsigned long long)(k0 + k))),
+                 __ldg(Bp + segeval(p.kB, p.nkB, (unsigned long long)(k0 + k))));
+        acc0.x += acc1.x + acc2.x + acc3.x; acc0.y += acc1.y + acc2.y + acc3.y;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            acc0.x += __shfl_xor_sync(0xffffffffu, acc0.x, s);
+            acc0.y += __shfl_xor_sync(0xffffffffu, acc0.y, s);
+        }
+        __syncthreads();                         // part[] free again
+        if (lane == 0) part[warp] = acc0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            R2 t = part[0];
+#pragma unroll
+            for (int w2 = 1; w2 < kThreads / 32; ++w2) { t.x += part[w2].x; t.y += part[w2].y; }
+            atomicAdd(&C[u * p.sUC + c].x, t.x);
+            atomicAdd(&C[u * p.sUC + c].y, t.y);
+        }
+    }
+}
+
+const void* kreduce_split_func(int dtype) {
+    return dtype == 0 ? (const void*)&kreduce_split_kernel<float2> : (const void*)&kreduce_split_kernel<double2>;
+}
+
 const void* kreduce_block_func(int dtype) {
     return dtype == 0 ? (const void*)&kreduce_block_kernel<float2> : (const void*)&kreduce_block_kernel<double2>;
 }

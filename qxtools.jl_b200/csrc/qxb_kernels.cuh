@@ -88,6 +88,8 @@ const void* contract_smem_func(int dtype, int kc, int ma, int nb, bool single_ch
 const void* kreduce_func(int dtype);
 // block-per-output variant for very long K (>= 2^12) and few outputs
 const void* kreduce_block_func(int dtype);
+// split-K variant: 2^OpParams::kc blocks per output, partial sums combined with atomicAdd into a zeroed C
+const void* kreduce_split_func(int dtype);
 // outleaf:  (R2* base, const OutLeafDesc* d, const unsigned char* bits, int n_outputs, long long amp0, long long n)
 const void* outleaf_func(int dtype);
 // reduce:   (const R2* root, long long sU, int span_bits, long long n, double scale, double* acc, long long amp0)

@@ -355,3 +355,33 @@ def test_gemm_shaped_node_random(gpu, dtype, gemm_mode, seed):
     d = [o for o in g.describe()["ops"] if o["name"] == "c"][0]
     assert d["m_bits"] == nm and d["n_bits"] == nn and d["nK"] == nk
     assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 2e-5)
+
+
+@pytest.mark.parametrize("dtype", ["c64", "c32"])
+def test_split_k_reduction(gpu, dtype):
+    """K = 2^17 against 2 x 4 outputs: the split-K reduction kernel (several blocks per output, atomicAdd
+    into a zeroed C) that the root-like nodes of GEMM-shaped trees go through."""
+    rng = np.random.default_rng(12)
+    nk = 17
+    A = (rng.normal(size=(2,) * (nk + 1)) + 1j * rng.normal(size=(2,) * (nk + 1))) / 16
+    B = (rng.normal(size=(2,) * (nk + 2)) + 1j * rng.normal(size=(2,) * (nk + 2))) / 16
+    ks = list(range(1, nk + 1))
+    la = ks + [nk + 1]                       # one M-only mode
+    lb = [nk + 2] + ks + [nk + 3]            # one N-only mode + the output wire
+    lb2 = [nk + 2] + ks
+    j = lambda l: ",".join(str(i) for i in l)
+    txt = ("# version: 0.4.0\n"
+           f"load a dA {j([2] * len(la))}\nload b dB {j([2] * len(lb))}\nload w dW 2,2\noutput o1 1 2\n"
+           f"ncon b2 {j(lb2)} b {j(lb)} o1 {nk + 3}\n"
+           f"ncon c {nk + 1},{nk + 2} a {j(la)} b2 {j(lb2)}\n"       # K = 2^17, nC = 2
+           f"ncon z 0 c 1,2 w 1,2\nsave output z\n")
+    W = rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2))
+    data = {"dA": A, "dB": B, "dW": W}
+    bs = ["0", "1", "+", "-"]
+    ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
+    g = Graph.from_dsl(txt, data, dtype).compile()
+    got = g.amplitudes(bs)
+    d = [o for o in g.describe()["ops"] if o["name"] == "c"][0]
+    assert d["nK"] == nk and d["nC"] == 2
+    assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 5e-5)
+    assert np.max(np.abs(g.amplitudes(bs) - got)) / np.max(np.abs(ref)) < (1e-14 if dtype == "c64" else 1e-6)   # replay
