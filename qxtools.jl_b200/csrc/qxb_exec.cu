@@ -467,8 +467,18 @@ Node contract_node(const RunCtx& c, int i) {
         // shared memory once per row (otherwise every output re-reads them through L1/L2)
         const size_t stage = ((size_t(1) << A.span_bits) + (size_t(1) << B.span_bits)) * g->es();
         const void* sf = nullptr;
-        if (!g->opts.no_smem_stage && p.lob == 8 && p.ma >= 1 && p.nb >= 1 && stage <= 96 * 1024 && p.hb >= 1 &&
-            A.lay.size() && B.lay.size() && op.elems_c >= 1.5 * (op.elems_a + op.elems_b) &&
+        // experiments: QXB_SMEM_RATIO (minimum |C| / (|A| + |B|) for staging), QXB_SMEM_MINHB (minimum hi bits)
+        const double smem_ratio = [] { const char* e = getenv("QXB_SMEM_RATIO"); return e ? atof(e) : 1.5; }();
+        const int smem_minhb = [] { const char* e = getenv("QXB_SMEM_MINHB"); return e ? atoi(e) : 1; }();
+        // QXB_SMEM_SHARED=1: also stage nodes with one operand shared by all rows (it is loaded once per CTA and may
+        // take up to 200 KB: one CTA per SM); the register tile may then be one-sided
+        const int smem_shared = [] { const char* e = getenv("QXB_SMEM_SHARED"); return e ? atoi(e) : 0; }();
+        const bool one_shared = smem_shared && (A.amp != B.amp) && p.U >= 4 * g_num_sms;
+        const size_t cap_bytes = one_shared ? 200 * 1024 : 96 * 1024;
+        const double amp_elems = (A.amp ? op.elems_a : 0) + (B.amp ? op.elems_b : 0);
+        if (!g->opts.no_smem_stage && p.lob == 8 && (one_shared ? p.ma + p.nb >= 1 : (p.ma >= 1 && p.nb >= 1)) &&
+            stage <= cap_bytes && p.hb >= (one_shared ? 0 : smem_minhb) &&
+            A.lay.size() && B.lay.size() && op.elems_c >= (one_shared ? 0.25 * amp_elems : smem_ratio * (op.elems_a + op.elems_b)) &&
             op.elems_a == std::ldexp(1.0, A.span_bits) && op.elems_b == std::ldexp(1.0, B.span_bits) && p.U >= g_num_sms)
             sf = contract_smem_func(g->dtype, p.kc, p.ma, p.nb, p.kc == p.nK);
         if (sf) {
@@ -478,7 +488,7 @@ Node contract_node(const RunCtx& c, int i) {
             n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(p.U, (long long)g_num_sms * 2)));
             static std::set<const void*> configured;
             if (stage > 48 * 1024 && !configured.count(sf)) {
-                CUDA_OK(cudaFuncSetAttribute(sf, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                CUDA_OK(cudaFuncSetAttribute(sf, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 configured.insert(sf);
             }
         } else {
@@ -577,10 +587,15 @@ int64_t hbm_budget(qxb_graph* g) {
 int64_t workspace_per_amp(qxb_graph* g, uint64_t mask) {
     auto it = g->ws_cache.find(mask);
     if (it != g->ws_cache.end()) return it->second;
-    Lowered L = lower(g->prog, mask, !g->opts.sum_at_root);
-    plan_memory(L);
-    const int64_t es = (int64_t)g->es();
-    const int64_t b = std::max<int64_t>(L.block_elems, 2) * es + std::max<int64_t>(L.chunk_elems_per_amp, 2) * es;
+    int64_t b = INT64_MAX;                      // a mask the lowering rejects (tensor too large) never fits
+    try {
+        Lowered L = lower(g->prog, mask, !g->opts.sum_at_root);
+        plan_memory(L);
+        const int64_t es = (int64_t)g->es();
+        b = std::max<int64_t>(L.block_elems, 2) * es + std::max<int64_t>(L.chunk_elems_per_amp, 2) * es;
+    } catch (const Error& e) {
+        if (e.code != QXB_ERR_UNSUPP || mask == 0) throw;
+    }
     g->ws_cache[mask] = b;
     return b;
 }
@@ -1120,6 +1135,10 @@ int qxb_graph_compile(qxb_graph* g, const qxb_options* opts) {
         g->compiled = true;
         try {
             get_variant(g, low_mask((int)g->prog.vars.size()));     // lower + fold constants for the all-free case
+        } catch (const Error& e) {
+            // heavily sliced programs (2^31-element tensors per slice) cannot batch every variable at all: the
+            // variants with fewer batched variables are lowered on demand by the first call that needs them
+            if (e.code != QXB_ERR_UNSUPP || g->prog.vars.empty()) { g->compiled = false; throw; }
         } catch (...) {
             g->compiled = false;
             throw;

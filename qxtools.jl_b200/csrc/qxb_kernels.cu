@@ -146,12 +146,16 @@ contract_smem_kernel(const __grid_constant__ OpParams p) {
     const long long cLo = segeval(p.sClo, p.nsClo, lo);
     const long long nA = 1ll << p.aBits, nB = 1ll << p.bBits;
     const long long tiles_u = 1ll << p.hb;
+    // an operand shared by every bitstring row (stride 0) is staged once per CTA, not once per row
+    const bool sharedA = p.sUA == 0, sharedB = p.sUB == 0;
+    if (sharedA) for (long long i = tid; i < nA; i += kThreads) sA[i] = __ldg(A + i);
+    if (sharedB) for (long long i = tid; i < nB; i += kThreads) sB[i] = __ldg(B + i);
     for (long long u = blockIdx.x; u < p.U; u += gridDim.x) {
         __syncthreads();                       // previous row fully consumed
         const R2* Au = A + u * p.sUA;
         const R2* Bu = B + u * p.sUB;
-        for (long long i = tid; i < nA; i += kThreads) sA[i] = __ldg(Au + i);
-        for (long long i = tid; i < nB; i += kThreads) sB[i] = __ldg(Bu + i);
+        if (!sharedA) for (long long i = tid; i < nA; i += kThreads) sA[i] = __ldg(Au + i);
+        if (!sharedB) for (long long i = tid; i < nB; i += kThreads) sB[i] = __ldg(Bu + i);
         __syncthreads();
         R2* Cu = C + u * p.sUC + cLo;
         for (long long hh = 0; hh < tiles_u; ++hh) {
@@ -174,6 +178,10 @@ static const void* pick_smem_tile(int ma, int nb, bool one) {
     if (ma == 1 && nb == 2) return pick_smem_one<R2, KC, 1, 2>(one);
     if (ma == 2 && nb == 1) return pick_smem_one<R2, KC, 2, 1>(one);
     if (ma == 2 && nb == 2) return pick_smem_one<R2, KC, 2, 2>(one);
+    if (ma == 0 && nb == 1) return pick_smem_one<R2, KC, 0, 1>(one);
+    if (ma == 0 && nb == 2) return pick_smem_one<R2, KC, 0, 2>(one);
+    if (ma == 1 && nb == 0) return pick_smem_one<R2, KC, 1, 0>(one);
+    if (ma == 2 && nb == 0) return pick_smem_one<R2, KC, 2, 0>(one);
     return nullptr;
 }
 template <typename R2>
@@ -182,6 +190,7 @@ static const void* pick_smem_kc(int kc, int ma, int nb, bool one) {
     case 0: return pick_smem_tile<R2, 0>(ma, nb, one);
     case 1: return pick_smem_tile<R2, 1>(ma, nb, one);
     case 2: return pick_smem_tile<R2, 2>(ma, nb, one);
+    case 3: return pick_smem_tile<R2, 3>(ma, nb, one);
     default: return nullptr;
     }
 }
