@@ -87,13 +87,20 @@ function Graph(cg::QXContexts.ComputeGraph; dtype::Cint=C64)
     g
 end
 
-function Graph(dsl_text::String, tensors::AbstractDict; dtype::Cint=C32, replan::Int=64, n_amp_model::Int=1024)
+function Graph(dsl_text::String, tensors::AbstractDict; dtype::Cint=C32, replan::Int=64, n_amp_model::Int=1024,
+               autoslice_budget::Int=0)
     g = Graph(dtype)
     check(ccall((:qxb_graph_parse_dsl, LIB), Cint, (Ptr{Cvoid}, Cstring, Csize_t), g.h, dsl_text, sizeof(dsl_text)))
     set_data!(g, tensors)
-    # batch-aware re-planning of the ncon tree (exact; leaves and views untouched)
-    replan > 0 && check(ccall((:qxb_graph_replan, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Cdouble}, Ptr{Cdouble}),
-                              g.h, replan, n_amp_model, C_NULL, C_NULL))
+    # batch-aware re-planning of the ncon tree (exact; leaves and views untouched).  With autoslice_budget > 0 the
+    # library also ADDS slice variables (views, as compute_graph.jl:39-58 emits them) until the largest tensor of
+    # the searched tree fits autoslice_budget / 3 bytes: GPU-aware slicing instead of contraction_scheme's `num`.
+    if replan > 0
+        n_free = autoslice_budget > 0 ? Cint(-3) : Cint(-1)
+        check(ccall((:qxb_graph_replan_ex, LIB), Cint,
+                    (Ptr{Cvoid}, Cint, Int64, Cint, Int64, UInt64, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                    g.h, replan, n_amp_model, n_free, autoslice_budget, UInt64(0), C_NULL, C_NULL, C_NULL, C_NULL))
+    end
     check(ccall((:qxb_graph_compile, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), g.h, C_NULL))
     g
 end

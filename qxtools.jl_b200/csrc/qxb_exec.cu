@@ -6,6 +6,7 @@
 //     for bitstring: for slice: run every ncon; acc += scalar
 // Here the two loops are batch axes of each node's single launch (qxb_lower.cpp).
 #include <cuda_runtime.h>
+#include <cuda_profiler_api.h>
 
 #include <algorithm>
 #include <cmath>
@@ -741,9 +742,30 @@ void account(qxb_graph* g, const std::vector<Node>& nodes) {
     }
 }
 
+// QXB_NCU_OPS=R474,R260,...: bracket exactly those ops with cudaProfilerStart/Stop (serial-launch mode), so that
+// `ncu --profile-from-start off` captures the named contractions and nothing else
+const std::set<std::string>& ncu_ops() {
+    static const std::set<std::string> ops = [] {
+        std::set<std::string> s;
+        if (const char* e = getenv("QXB_NCU_OPS")) {
+            std::stringstream ss(e);
+            std::string tok;
+            while (std::getline(ss, tok, ',')) if (!tok.empty()) s.insert(tok);
+        }
+        return s;
+    }();
+    return ops;
+}
+
 void launch_serial(qxb_graph* g, const std::vector<Node>& nodes) {
     cudaStream_t st = stream();
     for (const Node& n : nodes) {
+        bool bracket = false;
+        if (n.op >= 0 && !ncu_ops().empty())
+            for (auto& kv : g->variants)
+                if (kv.second->key == n.variant && ncu_ops().count(kv.second->L.ops[n.op].name)) bracket = true;
+        if (bracket) { CUDA_OK(cudaStreamSynchronize(st)); cudaProfilerStart(); }
+        struct Stop { bool on; cudaStream_t s; ~Stop() { if (on) { cudaStreamSynchronize(s); cudaProfilerStop(); } } } stop{bracket, st};
         EventPair* ev = nullptr;
         if (g->opts.profile && n.op >= 0) {
             if (g->events_used == g->events.size()) {
