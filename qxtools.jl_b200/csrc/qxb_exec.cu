@@ -196,6 +196,9 @@ char* tensor_ptr(const RunCtx& c, const LTensor& T) {
 // Split the bits of C into thread bits / register-tile bits / hi bits and compose
 // the address maps accordingly (see contract_kernel).
 void build_templates(Variant& v, int dtype) {
+    // register budget of the K chunk (experiments: QXB_KC_REGS_MULTI / QXB_KC_REGS_ONE)
+    const int kc_regs_multi = [] { const char* e = getenv("QXB_KC_REGS_MULTI"); return e ? atoi(e) : 96; }();
+    const int kc_regs_one = [] { const char* e = getenv("QXB_KC_REGS_ONE"); return e ? atoi(e) : 64; }();
     v.tmpl.resize(v.L.ops.size());
     v.gtmpl.resize(v.L.ops.size());
     v.gemm_tmb.assign(v.L.ops.size(), 0); v.gemm_tnb.assign(v.L.ops.size(), 0);
@@ -232,7 +235,7 @@ void build_templates(Variant& v, int dtype) {
         while (kc > 0) {
             const bool multi = kc < op.nK;
             const int regs = rp * ((tmn << kc) + (multi ? tile : 0));
-            if (regs <= (multi ? 96 : 64)) break;
+            if (regs <= (multi ? kc_regs_multi : kc_regs_one)) break;
             --kc;
         }
         p.kc = kc;
@@ -493,7 +496,9 @@ Node contract_node(const RunCtx& c, int i) {
                 configured.insert(sf);
             }
         } else {
-            n.func = contract_func(g->dtype, p.kc, p.ma, p.nb, p.kc == p.nK);
+            // QXB_MINB=3 (experiment): the register allocation bounded for three resident CTAs per SM where it does not spill
+            const int minb = [] { const char* e = getenv("QXB_MINB"); return e ? atoi(e) : 2; }();
+            n.func = contract_func(g->dtype, p.kc, p.ma, p.nb, p.kc == p.nK, minb);
             n.grid = dim3((unsigned)std::max<long long>(1, std::min(blocks, cap)));
         }
     }

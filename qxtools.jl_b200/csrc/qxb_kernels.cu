@@ -97,8 +97,9 @@ __device__ __forceinline__ void tile_compute(const R2* __restrict__ Ap, const R2
     }
 }
 
-template <typename R2, int KC, int MA, int NB, bool ONE>
-__global__ void __launch_bounds__(kThreads, 2)
+// MINB = resident CTAs per SM the register allocation is bounded for (2: <= 128 registers, 3: <= 85)
+template <typename R2, int KC, int MA, int NB, bool ONE, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 contract_kernel(const __grid_constant__ OpParams p) {
     const R2* __restrict__ A = reinterpret_cast<const R2*>(p.A);
     const R2* __restrict__ B = reinterpret_cast<const R2*>(p.B);
@@ -201,37 +202,46 @@ const void* contract_smem_func(int dtype, int kc, int ma, int nb, bool single_ch
 }
 
 template <typename R2, int KC, int MA, int NB>
-static const void* pick_one(bool one) {
-    return one ? (const void*)&contract_kernel<R2, KC, MA, NB, true> : (const void*)&contract_kernel<R2, KC, MA, NB, false>;
+static const void* pick_one(bool one, int minb) {
+    if (minb >= 3)
+        return one ? (const void*)&contract_kernel<R2, KC, MA, NB, true, 3> : (const void*)&contract_kernel<R2, KC, MA, NB, false, 3>;
+    return one ? (const void*)&contract_kernel<R2, KC, MA, NB, true, 2> : (const void*)&contract_kernel<R2, KC, MA, NB, false, 2>;
 }
 template <typename R2, int KC, int MA>
-static const void* pick_nb(int nb, bool one) {
+static const void* pick_nb(int nb, bool one, int minb) {
     switch (nb) {
-    case 0: return pick_one<R2, KC, MA, 0>(one);
-    case 1: return pick_one<R2, KC, MA, 1>(one);
-    default: return pick_one<R2, KC, MA, 2>(one);
+    case 0: return pick_one<R2, KC, MA, 0>(one, minb);
+    case 1: return pick_one<R2, KC, MA, 1>(one, minb);
+    default: return pick_one<R2, KC, MA, 2>(one, minb);
     }
 }
 template <typename R2, int KC>
-static const void* pick_ma(int ma, int nb, bool one) {
+static const void* pick_ma(int ma, int nb, bool one, int minb) {
     switch (ma) {
-    case 0: return pick_nb<R2, KC, 0>(nb, one);
-    case 1: return pick_nb<R2, KC, 1>(nb, one);
-    default: return pick_nb<R2, KC, 2>(nb, one);
+    case 0: return pick_nb<R2, KC, 0>(nb, one, minb);
+    case 1: return pick_nb<R2, KC, 1>(nb, one, minb);
+    default: return pick_nb<R2, KC, 2>(nb, one, minb);
     }
 }
 template <typename R2>
-static const void* pick_kc(int kc, int ma, int nb, bool one) {
+static const void* pick_kc(int kc, int ma, int nb, bool one, int minb) {
     switch (kc) {
-    case 0: return pick_ma<R2, 0>(ma, nb, one);
-    case 1: return pick_ma<R2, 1>(ma, nb, one);
-    case 2: return pick_ma<R2, 2>(ma, nb, one);
-    default: return pick_ma<R2, 3>(ma, nb, one);
+    case 0: return pick_ma<R2, 0>(ma, nb, one, minb);
+    case 1: return pick_ma<R2, 1>(ma, nb, one, minb);
+    case 2: return pick_ma<R2, 2>(ma, nb, one, minb);
+    default: return pick_ma<R2, 3>(ma, nb, one, minb);
     }
 }
 
-const void* contract_func(int dtype, int kc, int ma, int nb, bool single_chunk) {
-    return dtype == 0 ? pick_kc<float2>(kc, ma, nb, single_chunk) : pick_kc<double2>(kc, ma, nb, single_chunk);
+// min_blocks = 3 returns the variant compiled for three resident CTAs per SM, or the two-CTA one when that
+// variant spills (local memory > 0): more warps only pay when the registers really fit
+const void* contract_func(int dtype, int kc, int ma, int nb, bool single_chunk, int min_blocks) {
+    const void* f2 = dtype == 0 ? pick_kc<float2>(kc, ma, nb, single_chunk, 2) : pick_kc<double2>(kc, ma, nb, single_chunk, 2);
+    if (min_blocks < 3) return f2;
+    const void* f3 = dtype == 0 ? pick_kc<float2>(kc, ma, nb, single_chunk, 3) : pick_kc<double2>(kc, ma, nb, single_chunk, 3);
+    cudaFuncAttributes at{};
+    if (cudaFuncGetAttributes(&at, f3) != cudaSuccess || at.localSizeBytes > 0) { cudaGetLastError(); return f2; }
+    return f3;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -80,7 +80,7 @@ struct OutLeafDesc { long long offset_per_amp; int span_bits; int out_idx; };
 
 // Kernel entry points as function pointers (for cudaLaunchKernel / cudaGraphAddKernelNode).
 // contract: one argument (OpParams by value).
-const void* contract_func(int dtype, int kc, int ma, int nb, bool single_chunk);
+const void* contract_func(int dtype, int kc, int ma, int nb, bool single_chunk, int min_blocks = 2);
 // shared-memory-staged variant for broadcast-type nodes (nullptr if the shape has none); dynamic
 // shared memory = (2^aBits + 2^bBits) * sizeof(element)
 const void* contract_smem_func(int dtype, int kc, int ma, int nb, bool single_chunk);

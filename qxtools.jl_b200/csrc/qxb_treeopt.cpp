@@ -193,7 +193,7 @@ struct Bits {                      // up to 256 local classes
     void set(int i) { w[i >> 6] |= 1ull << (i & 63); }
 };
 
-bool reconfigure_at(Tree& T, int top, int L, std::vector<int>* scratch) {
+bool reconfigure_at(Tree& T, int top, int L, std::mt19937_64* rng) {
     const TreeNet& net = *T.net;
     if (T.n[top].l < 0) return false;
     // grow the region: frontier starts as {children of top}; expand the largest internal frontier node
@@ -201,12 +201,17 @@ bool reconfigure_at(Tree& T, int top, int L, std::vector<int>* scratch) {
     std::vector<int> inner{top};
     while ((int)frontier.size() < L) {
         int pick = -1; double best = -1;
+        std::vector<int> internal;
         for (size_t i = 0; i < frontier.size(); ++i) {
             const TNode& f = T.n[frontier[i]];
             if (f.l < 0) continue;
+            internal.push_back((int)i);
             if (f.bits > best) { best = f.bits; pick = (int)i; }
         }
         if (pick < 0) break;
+        // stochastic sweeps grow the region through a random internal frontier node half of the time:
+        // differently shaped regions reach re-associations the largest-first regions cannot
+        if (rng && ((*rng)() & 1)) pick = internal[(size_t)((*rng)() % internal.size())];
         const int v = frontier[pick];
         inner.push_back(v);
         frontier[pick] = T.n[v].l;
@@ -313,7 +318,6 @@ bool reconfigure_at(Tree& T, int top, int L, std::vector<int>* scratch) {
     build(FULL, true);
     T.n[top].parent = parent_of_top;
     for (int v : order) T.recompute(v);
-    (void)scratch;
     return true;
 }
 
@@ -377,6 +381,23 @@ static double refine(Tree& T, int rounds, int L, std::mt19937_64& rng) {
     return cost;
 }
 
+// stochastic phase: random tops, randomly grown regions; every accepted move is a strict improvement
+static double refine_random(Tree& T, int sweeps, int L, std::mt19937_64& rng) {
+    const int nl = (int)T.net->leaf_ids.size();
+    std::vector<int> internal;
+    for (int v = nl; v < (int)T.n.size(); ++v) internal.push_back(v);
+    for (int s = 0; s < sweeps; ++s) {
+        std::shuffle(internal.begin(), internal.end(), rng);
+        bool any = false;
+        for (int v : internal) {
+            if (T.n[v].cost <= 0 && (rng() & 3)) continue;           // mostly skip free (constant) nodes
+            if (reconfigure_at(T, v, L, &rng)) any = true;
+        }
+        if (!any && s >= 2) break;
+    }
+    return T.total();
+}
+
 double optimize_tree(const TreeNet& net, const TreeCostModel& cm, int restarts, int refine_rounds, uint64_t seed,
                      const std::vector<std::vector<std::pair<int, int>>>& seeds_plans, const std::vector<int>& seeds_roots,
                      std::vector<std::pair<int, int>>& plan, int& root, TreeReport* report) {
@@ -412,7 +433,16 @@ double optimize_tree(const TreeNet& net, const TreeCostModel& cm, int restarts, 
     }
     for (auto& pr : pool) {
         refine(pr.second, refine_rounds, L, rng);
-        consider(pr.second);
+        pr.first = pr.second.total();
+    }
+    std::sort(pool.begin(), pool.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+    const int sweeps = getenv("QXB_TREEOPT_SWEEPS") ? atoi(getenv("QXB_TREEOPT_SWEEPS")) : 6;
+    for (size_t i = 0; i < pool.size(); ++i) {
+        if (i < 3 && sweeps > 0) {                                   // the best three also get the stochastic phase
+            refine_random(pool[i].second, sweeps, L, rng);
+            refine(pool[i].second, 4, L, rng);
+        }
+        consider(pool[i].second);
     }
     tree_to_plan(bestT, plan, root);
     if (report) {

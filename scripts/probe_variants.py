@@ -1,5 +1,5 @@
 """GPU probe: whole-step time and per-node profile of the headline workload (RQC 7x7 d20) under several settings of
-the kernel-selection knobs (QXB_SMEM_RATIO, QXB_SMEM_MINHB, QXB_SMEM_SHARED; read by the library at node-build time).
+the kernel-selection knobs (QXB_MINB, QXB_KC_REGS_*, QXB_SMEM_*; read by the library when a graph is lowered / its nodes are built).
 Writes gpurun_out/op_profile_7x7_<tag>.json per setting and gpurun_out/probe_variants.json."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -17,10 +17,15 @@ g0 = Graph.from_dsl(txt, data, w["dtype"], replan=128, replan_n_amp=n_amp)
 plan_txt = g0.text
 del g0
 CONFIGS = [("default", {}),
-           ("stage_more", {"QXB_SMEM_RATIO": "0.3", "QXB_SMEM_MINHB": "0"}),
-           ("stage_more_shared", {"QXB_SMEM_RATIO": "0.3", "QXB_SMEM_MINHB": "0", "QXB_SMEM_SHARED": "1"}),
-           ("shared_only", {"QXB_SMEM_SHARED": "1"})]
-KNOBS = ("QXB_SMEM_RATIO", "QXB_SMEM_MINHB", "QXB_SMEM_SHARED")
+           ("minb3", {"QXB_MINB": "3"}),
+           ("minb3_kc128", {"QXB_MINB": "3", "QXB_KC_REGS_MULTI": "128", "QXB_KC_REGS_ONE": "96"}),
+           ("kc128", {"QXB_KC_REGS_MULTI": "128", "QXB_KC_REGS_ONE": "96"})]
+if os.environ.get("PROBE_CONFIGS") == "smem":
+    CONFIGS = [("default", {}),
+               ("stage_more", {"QXB_SMEM_RATIO": "0.3", "QXB_SMEM_MINHB": "0"}),
+               ("stage_more_shared", {"QXB_SMEM_RATIO": "0.3", "QXB_SMEM_MINHB": "0", "QXB_SMEM_SHARED": "1"}),
+               ("shared_only", {"QXB_SMEM_SHARED": "1"})]
+KNOBS = ("QXB_SMEM_RATIO", "QXB_SMEM_MINHB", "QXB_SMEM_SHARED", "QXB_MINB", "QXB_KC_REGS_MULTI", "QXB_KC_REGS_ONE")
 results, ref = {}, None
 for tag, env in CONFIGS:
     for k in KNOBS:
