@@ -224,6 +224,7 @@ TreeCostModel cost_model_for(double elem_bytes) {
     cm.elem_bytes = elem_bytes;
     cm.bandwidth = 6.0e12;                                  // streaming kernels: 93 % of 6.45 TB/s (profiles/r1_summary.md)
     cm.flop_rate = elem_bytes <= 8 ? 40e12 : 27e12;         // GEMM kernels: c32 SIMT / 3xTF32 ~40, c64 DMMA 27 TFLOP/s
+    cm.shared_reread = getenv("QXB_PLAN_SHARED_REREAD") && atoi(getenv("QXB_PLAN_SHARED_REREAD")) != 0;   // experiment, off
     return cm;
 }
 
@@ -232,8 +233,9 @@ double lowered_cost_seconds(const Lowered& L, double n_amp, const TreeCostModel&
     double t = 0;
     for (const LOp& op : L.ops) {
         const double u = L.tensors[op.c].amp ? n_amp : 1;
-        const double bytes = cm.elem_bytes * (op.elems_a * (L.tensors[op.a].amp ? n_amp : 1) +
-                                              op.elems_b * (L.tensors[op.b].amp ? n_amp : 1) + op.elems_c * u);
+        const bool rr = cm.shared_reread && L.tensors[op.c].amp;
+        const double bytes = cm.elem_bytes * (op.elems_a * ((L.tensors[op.a].amp || rr) ? n_amp : 1) +
+                                              op.elems_b * ((L.tensors[op.b].amp || rr) ? n_amp : 1) + op.elems_c * u);
         const double flops = 8.0 * op.macs_per_amp * u;
         t += (op.phase == PH_CONST ? cm.const_weight : 1.0) * (std::max(bytes / cm.bandwidth, flops / cm.flop_rate) + cm.launch_s);
     }

@@ -76,7 +76,12 @@ struct Tree {
         // nodes without bitstring / slice-variable dependence are folded once at compile time; they are charged
         // const_weight of their cost so the search cannot hide unbounded work (or memory) in that phase
         const double w = (!c.amp && !c.var) ? cm->const_weight : 1.0;
-        return w * cm->time(a.bits, b.bits, c.bits, union_bits);
+        // shared_reread: an operand without the bitstring axis is streamed through L1/L2 once per bitstring row by
+        // the kernels (ncu: R260 of the 7x7 program, L1 at 96 %), so it costs like a per-row operand
+        const double ab = net->amp >= 0 ? net->wbits[net->amp] : 0.0;
+        const double ea = (cm->shared_reread && c.amp && !a.amp) ? a.bits + ab : a.bits;
+        const double eb = (cm->shared_reread && c.amp && !b.amp) ? b.bits + ab : b.bits;
+        return w * cm->time(ea, eb, c.bits, union_bits);
     }
     void recompute(int v) {
         TNode& c = n[v];
@@ -294,7 +299,9 @@ bool reconfigure_at(Tree& T, int top, int L, std::mt19937_64* rng) {
                 for (int k = 0; k < 4; ++k) u.w[k] = open[S1].w[k] | open[S2].w[k];
                 const bool ua = amp_loc >= 0 && ((u.w[amp_loc >> 6] >> (amp_loc & 63)) & 1);
                 const double ub = wsum(u) + (ua ? amp_bits : 0.0);
-                c += ((s_amp[S] || s_var[S]) ? 1.0 : T.cm->const_weight) * T.cm->time(s_bits[S1], s_bits[S2], s_bits[S], ub);
+                const double e1 = (T.cm->shared_reread && s_amp[S] && !s_amp[S1]) ? s_bits[S1] + amp_bits : s_bits[S1];
+                const double e2 = (T.cm->shared_reread && s_amp[S] && !s_amp[S2]) ? s_bits[S2] + amp_bits : s_bits[S2];
+                c += ((s_amp[S] || s_var[S]) ? 1.0 : T.cm->const_weight) * T.cm->time(e1, e2, s_bits[S], ub);
             }
             if (bc < 0 || c < bc) { bc = c; bs = S1; }
         }

@@ -134,3 +134,33 @@ def test_autoslice_adds_exact_slice_variables(lib_built, case):
     assert max(o["nC"] for o in d["ops"] if o["phase"] != "const") <= lim
     # and the lowered form executes correctly
     assert np.allclose(em.amplitudes(g2, data, bits_from_strings(bs, n_q), shuffle_seed=5), ref, atol=1e-13)
+
+
+def test_replan_for_partially_batched_runs(lib_built):
+    """qxb_graph_replan_ex with n_free >= 0 / -2: the plan is searched and scored for a run that batches only the
+    first n_free slice variables; the program stays equivalent for every slice range."""
+    txt, data, bs = rqc_case(4, 4, 14, 4, n_amp=4)
+    c0 = orc.parse_dsl(txt)
+    ref = orc.amplitudes(c0, data, bs)
+    for n_free in (0, 2, -2):
+        g = Graph.from_dsl(txt, data, "c64")
+        info = g.replan(8, 16, n_free=n_free, budget_bytes=3 * 16 * 2 ** 9 if n_free == -2 else 0)
+        assert 0 <= info["n_free"] <= 4 and (n_free < 0 or info["n_free"] == n_free)
+        assert _leaf_lines(g.text) == _leaf_lines(txt)
+        c1 = orc.parse_dsl(g.text)
+        assert np.allclose(orc.amplitudes(c1, data, bs), ref, atol=1e-14)
+        assert np.allclose(orc.amplitudes(c1, data, bs, slice_begin=3, slice_end=11),
+                           orc.amplitudes(c0, data, bs, slice_begin=3, slice_end=11), atol=1e-14)
+        if info["replanned"]:
+            assert np.isfinite(info["model_seconds_per_block"]) and info["model_seconds_per_block"] > 0
+
+
+def test_replan_is_deterministic_and_tree_search_beats_orders(lib_built):
+    """Same seed, same program; and on a sliced RQC the tree search must not be worse than the order-based
+    re-planner of the first version (qxb200.replan.replan_dsl scores elimination orders only)."""
+    txt, data, bs = rqc_case(4, 5, 14, 5, n_amp=4)
+    a = Graph.from_dsl(txt, data, "c64"); ia = a.replan(8, 1024)
+    b = Graph.from_dsl(txt, data, "c64"); ib = b.replan(8, 1024)
+    assert a.text == b.text and ia["bytes"] == ib["bytes"]
+    _, info = replan_dsl(txt, n_amp=1024, candidates=8)
+    assert ia["bytes"] <= info["bytes"] * 1.0001
