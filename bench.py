@@ -47,6 +47,9 @@ WORKLOADS = {
     # slicing so that the largest tensor of a slice is 2^31 elements (17 GB in HBM); file written by
     # workloads/make_sycamore12.py.  A parity / capability case (scripts/probe_syc12.py), not a bench line.
     "sycamore53_d12_c32_s2048": dict(sycamore=12, rows=53, cols=1, n_slice=0, dtype="c32", seed=1),
+    # same circuit, sliced and planned by the current tree search (stochastic reconfiguration + bisection seeds):
+    # 16 slices, 2^38 MACs per slice -- modelled 0.06 s per slice; not yet measured (profiles/r1p_summary.md)
+    "sycamore53_d12_c32_s16": dict(sycamore=12, rows=53, cols=1, n_slice=0, dtype="c32", seed=1),
 }
 DEFAULT_WORKLOAD = "rqc_7x7_d20_c64_s4096"
 

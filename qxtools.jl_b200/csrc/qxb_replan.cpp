@@ -494,11 +494,14 @@ bool replan(Program& prog, int candidates, uint64_t seed, double n_amp, bool ear
         for (size_t li = 0; li < leaf_defs.size(); ++li) tn.leaf_var.push_back(prog.defs[leaf_defs[li]].vars.empty() ? 0 : 1);
         return tn;
     };
+    TreeCostModel cm_search = cm;                          // the search may use extra tree builders
+    if (autoslice) cm_search.bisection_restarts = 16;      // GPU-aware slicing: also seed with recursive-bisection trees
+    if (getenv("QXB_TREEOPT_BISECT")) cm_search.bisection_restarts = atoi(getenv("QXB_TREEOPT_BISECT"));
     if (getenv("QXB_TREEOPT_PROBE")) {                     // planner experiments: search only, print the report
         const int rounds = atoi(getenv("QXB_TREEOPT_PROBE"));
         TreeNet tn = make_tn(g_plan_n_free);
         std::vector<std::pair<int, int>> tplan; int troot = -1; TreeReport rep;
-        optimize_tree(tn, cm, std::max(1, candidates), rounds, seed, {}, {}, tplan, troot, &rep);
+        optimize_tree(tn, cm_search, std::max(1, candidates), rounds, seed, {}, {}, tplan, troot, &rep);
         fprintf(stderr, "[treeopt] restarts %d rounds %d n_free %d: %.4g s (2^%.2f flops, %.4g GB, largest node 2^%.0f)\n",
                 candidates, rounds, g_plan_n_free, rep.seconds, std::log2(std::max(rep.flops, 1.0)), rep.bytes / 1e9, rep.max_bits);
         return false;
@@ -519,7 +522,7 @@ bool replan(Program& prog, int candidates, uint64_t seed, double n_amp, bool ear
         std::vector<std::pair<int, int>> tplan;
         int troot = -1;
         TreeReport rep, rep2;
-        optimize_tree(tn, cm, std::max(4, candidates), 32, seed ^ 0xD1B54A32D192ED03ull, seeds, seed_roots, tplan, troot, &rep);
+        optimize_tree(tn, cm_search, std::max(4, candidates), 32, seed ^ 0xD1B54A32D192ED03ull, seeds, seed_roots, tplan, troot, &rep);
         const double max_node_bits = std::floor(std::log2(std::max(budget_bytes, 3.0 * elem_bytes) / (3.0 * elem_bytes)));
         std::vector<char> sliceable(ncls + 1, 0);
         for (int c = 0; c < ncls; ++c) sliceable[c] = cls_var[c] < 0;

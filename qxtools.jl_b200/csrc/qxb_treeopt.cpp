@@ -15,6 +15,7 @@
 // The result is a list of pairwise steps; qxb_replan.cpp emits the ncon statements and scores the
 // finished program with the executor's exact lowering before accepting it.
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <functional>
 #include <cstdint>
@@ -190,6 +191,127 @@ void greedy_build(Tree& T, double alpha, double temperature, std::mt19937_64& rn
         for (int o : neighbours(c)) push(c, o);
     }
     for (size_t t = 0; t < alive.size(); ++t) if (alive[t]) T.root = (int)t;
+}
+
+// ------------------------------------------------------------------ recursive bisection
+// Partition-based construction: split the leaves into two balanced halves with a small cut (sum of the bits of the
+// index classes that have owners on both sides; Fiduccia-Mattheyses passes from a breadth-first seed partition),
+// recurse, and contract the two halves last.  Lattice-like networks (Sycamore) get much narrower trees this way
+// than from greedy agglomeration; small groups are finished greedily.
+struct Bisector {
+    Tree& T;
+    std::mt19937_64& rng;
+    double imbalance;                           // each side keeps at least (0.5 - imbalance) of the vertices
+    const TreeNet& net;
+    Bisector(Tree& t, std::mt19937_64& r, double imb) : T(t), rng(r), imbalance(imb), net(*t.net) {}
+
+    int small_group(std::vector<int> nodes) {   // smallest-result-first agglomeration of a handful of tensors
+        while (nodes.size() > 1) {
+            double best = -1; size_t bi = 0, bj = 1;
+            for (size_t i = 0; i < nodes.size(); ++i)
+                for (size_t j = i + 1; j < nodes.size(); ++j) {
+                    TNode c; double ub;
+                    T.merge(T.n[nodes[i]], T.n[nodes[j]], c, &ub);
+                    const double sc = std::exp2(c.bits) - std::exp2(T.n[nodes[i]].bits) - std::exp2(T.n[nodes[j]].bits);
+                    if (best < 0 || sc < best) { best = sc; bi = i; bj = j; if (best < -1e300) break; }
+                }
+            const int c = T.add(nodes[bi], nodes[bj]);
+            nodes.erase(nodes.begin() + bj); nodes.erase(nodes.begin() + bi);
+            nodes.push_back(c);
+        }
+        return nodes[0];
+    }
+
+    int build(const std::vector<int>& leaves) {
+        const int n = (int)leaves.size();
+        if (n <= 6) return small_group(leaves);
+        // local hypergraph: classes with >= 2 pins inside this group
+        std::map<int, std::vector<int>> pins;                       // class -> local vertex ids
+        for (int i = 0; i < n; ++i)
+            for (int c : net.leaf_ids[leaves[i]]) if (c != net.amp && net.wbits[c] > 0) pins[c].push_back(i);
+        std::vector<std::vector<int>> vcls(n);                       // per vertex: indices into `edges`
+        std::vector<std::vector<int>> edges; std::vector<double> ew;
+        for (auto& kv : pins) {
+            if (kv.second.size() < 2) continue;
+            for (int v : kv.second) vcls[v].push_back((int)edges.size());
+            edges.push_back(kv.second); ew.push_back(net.wbits[kv.first]);
+        }
+        // seed partition: breadth-first growth from a random vertex until half of the vertices are taken
+        std::vector<char> side(n, 1);
+        {
+            std::vector<char> seen(n, 0);
+            std::vector<int> queue{(int)(rng() % n)};
+            seen[queue[0]] = 1;
+            size_t head = 0; int taken = 0;
+            while (taken < n / 2) {
+                if (head == queue.size()) {                          // disconnected: jump to an unseen vertex
+                    for (int v = 0; v < n; ++v) if (!seen[v]) { queue.push_back(v); seen[v] = 1; break; }
+                }
+                const int v = queue[head++];
+                side[v] = 0; ++taken;
+                std::vector<int> nb;
+                for (int e : vcls[v]) for (int u : edges[e]) if (!seen[u]) { seen[u] = 1; nb.push_back(u); }
+                std::shuffle(nb.begin(), nb.end(), rng);
+                queue.insert(queue.end(), nb.begin(), nb.end());
+            }
+        }
+        const int min_side = std::max(1, (int)std::floor((0.5 - imbalance) * n));
+        std::vector<std::array<int, 2>> cnt(edges.size());
+        auto recount = [&]() {
+            for (size_t e = 0; e < edges.size(); ++e) { cnt[e] = {0, 0}; for (int v : edges[e]) cnt[e][side[v]]++; }
+        };
+        auto gain = [&](int v) {
+            const int s = side[v], t = 1 - s;
+            double g = 0;
+            for (int e : vcls[v]) {
+                if (cnt[e][s] == 1 && cnt[e][t] > 0) g += ew[e];        // edge leaves the cut
+                else if (cnt[e][t] == 0 && cnt[e][s] > 1) g -= ew[e];   // edge enters the cut
+            }
+            return g;
+        };
+        for (int pass = 0; pass < 6; ++pass) {                       // Fiduccia-Mattheyses passes
+            recount();
+            int n0 = 0;
+            for (int v = 0; v < n; ++v) n0 += side[v] == 0;
+            std::vector<char> locked(n, 0);
+            std::vector<int> moved;
+            double run = 0, best_run = 0; int best_len = 0;
+            for (int step = 0; step < n; ++step) {
+                int pick = -1; double pg = -1e300;
+                for (int v = 0; v < n; ++v) {
+                    if (locked[v]) continue;
+                    const int from = side[v];
+                    if ((from == 0 ? n0 : n - n0) - 1 < min_side) continue;
+                    const double g = gain(v);
+                    if (g > pg) { pg = g; pick = v; }
+                }
+                if (pick < 0) break;
+                const int s = side[pick];
+                for (int e : vcls[pick]) { cnt[e][s]--; cnt[e][1 - s]++; }
+                side[pick] = (char)(1 - s);
+                n0 += s == 0 ? -1 : 1;
+                locked[pick] = 1; moved.push_back(pick);
+                run += pg;
+                if (run > best_run + 1e-9) { best_run = run; best_len = (int)moved.size(); }
+                if ((int)moved.size() - best_len > 64) break;         // long unproductive tail
+            }
+            for (int i = (int)moved.size() - 1; i >= best_len; --i) side[moved[i]] = (char)(1 - side[moved[i]]);   // roll back
+            if (best_len == 0) break;
+        }
+        std::vector<int> a, b;
+        for (int v = 0; v < n; ++v) (side[v] == 0 ? a : b).push_back(leaves[v]);
+        if (a.empty() || b.empty()) return small_group(leaves);
+        const int ra = build(a), rb = build(b);
+        return T.add(ra, rb);
+    }
+};
+
+void bisect_build(Tree& T, double imbalance, std::mt19937_64& rng) {
+    T.init_leaves();
+    std::vector<int> all((int)T.net->leaf_ids.size());
+    for (size_t i = 0; i < all.size(); ++i) all[i] = (int)i;
+    Bisector bs(T, rng, imbalance);
+    T.root = bs.build(all);
 }
 
 // ------------------------------------------------------------------ subtree reconfiguration
@@ -437,6 +559,14 @@ double optimize_tree(const TreeNet& net, const TreeCostModel& cm, int restarts, 
         greedy_build(T, alpha, temp, rng);
         refine(T, 1, 8, rng);                                                          // one cheap sweep ranks candidates better
         add_pool(std::move(T));
+    }
+    if (cm.bisection_restarts > 0) {
+        for (int it = 0; it < cm.bisection_restarts; ++it) {
+            Tree T; T.net = &net; T.cm = &cm;
+            bisect_build(T, 0.02 + 0.3 * U(rng), rng);
+            refine(T, 1, 8, rng);
+            add_pool(std::move(T));
+        }
     }
     for (auto& pr : pool) {
         refine(pr.second, refine_rounds, L, rng);

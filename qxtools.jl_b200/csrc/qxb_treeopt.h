@@ -24,6 +24,7 @@ struct TreeCostModel {
     double flop_rate = 27e12;                   // flop/s of the GEMM kernels (c64 DMMA 27e12, c32 ~40e12)
     double launch_s = 0.0;
     bool shared_reread = false;                 // charge an operand shared by all bitstrings once per bitstring row (experiment)
+    int bisection_restarts = 0;                 // > 0: also seed the pool with recursive-bisection trees (Fiduccia-Mattheyses)
     double const_weight = 1.0;                  // share of a constant-folded node's cost that counts (1 = as if run once per step)
     double time(double a_bits, double b_bits, double c_bits, double union_bits) const;
 };

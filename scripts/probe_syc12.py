@@ -10,10 +10,10 @@ import bench
 from qxb200.executor import Graph, init
 init(0)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-NAME = "sycamore53_d12_c32_s2048"
+NAME = os.environ.get("PROBE_WORKLOAD", "sycamore53_d12_c32_s16")
 txt, data, w = bench.build_workload(NAME)
 bits = bench.synth_bits(1, 53)
-n_sl = int(os.environ.get("PROBE_SLICES", "4"))
+n_sl = min(int(os.environ.get("PROBE_SLICES", "4")), 16)
 res = {"workload": NAME}
 t = time.time()
 g = Graph.from_dsl(txt, data, "c32").compile(hbm_budget_bytes=int(150e9))

@@ -1,6 +1,11 @@
-"""Writes workloads/sycamore53_d12_c32_s2048.{qx,npz,yml}: BASELINE.json configs[4], a Sycamore-like 53-qubit
+"""Writes workloads/sycamore53_d12_c32_s16.{qx,npz,yml}: BASELINE.json configs[4], a Sycamore-like 53-qubit
 12-cycle fSim circuit, sliced by the LIBRARY's GPU-aware slicing (qxb_graph_replan_ex, n_free = -3) so that
 the largest tensor of one slice is 2^31 ComplexF32 elements (17 GB) -- "largest intermediate held in HBM".
+
+(workloads/sycamore53_d12_c32_s2048.* is the same circuit as sliced and planned by the first version of the tree
+search -- greedy + deterministic subtree reconfiguration only: 2^51 flops unsliced, 11 indices sliced; it is the
+file the measured numbers in profiles/r1p_summary.md refer to.  With the stochastic reconfiguration sweeps and
+the recursive-bisection seeds the search reaches 2^44.4 flops unsliced and needs 4 sliced indices.)
 
 The reference cannot produce this file (circuits.jl builds CZ grids only, contraction_scheme slices by
 treewidth alone, contraction_planning.jl:219-299).  Seeded and deterministic.  Run from the repo root:
@@ -19,7 +24,7 @@ import qxb200 as q                                # noqa: E402
 from qxb200.executor import Graph                 # noqa: E402
 from qxb200.simulation import output_params_dict, _plain  # noqa: E402
 
-NAME = "sycamore53_d12_c32_s2048"
+NAME = "sycamore53_d12_c32_s16"
 BUDGET = int(96e9)           # 3 x 8 B x 2^32 would be 103 GB: the slicer stops at 2^31-element tensors
 
 t = time.time()
@@ -32,6 +37,7 @@ g = Graph.from_dsl(txt, data, "c32")
 info = g.replan(128, 1, n_free=-3, budget_bytes=BUDGET)
 assert info["replanned"], info
 g2 = Graph.from_dsl(g.text, data, "c32")
+assert g2.n_slices == 16, g2.n_slices
 print(f"{NAME}: {g2.n_slices} slices {g2.slice_dims}, modelled {info['model_seconds_per_block']:.3f} s per slice, "
       f"{time.time() - t:.0f} s to plan")
 prefix = os.path.join(ROOT, "workloads", NAME)
