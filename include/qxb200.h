@@ -164,9 +164,73 @@ int  qxb_last_stats(const qxb_graph* g, qxb_stats* st);
 /* Per-op table (name, shape, flops, bytes, ms) of the last profiled call, as JSON. */
 int  qxb_profile_dump(qxb_graph* g, const char* json_path);
 
+/* ---- the file seam (B3): data files, parameter files, a whole triple --------------------------------
+ * JLD2 (HDF5-subset) reader/writer for the `.jld2` files of a simulation triple: one dataset per data label
+ * holding the N-d ComplexF64 array (tensor_cache.jl:90-106), and the results file bin/qxrun.jl -o names
+ * (docs/src/distributed.md:30-33).  Handles what JLD2.jl emits for numeric arrays (512-byte header, superblock
+ * v2, OHDR v2, link messages, contiguous/compact layout, committed compound {re, im}) and files of the HDF5 C
+ * library (superblock v0/v1, OHDR v1, symbol-table groups); chunked/compressed datasets are QXB_ERR_UNSUPP. */
+typedef struct qxb_jld2 qxb_jld2;
+#define QXB_JLD2_MAX_RANK 32
+#define QXB_ELEM_C64    0     /* {re: f64, im: f64} */
+#define QXB_ELEM_C32    1     /* {re: f32, im: f32} */
+#define QXB_ELEM_F64    2
+#define QXB_ELEM_F32    3
+#define QXB_ELEM_INT    4     /* elem_size bytes */
+#define QXB_ELEM_STRING 5     /* fixed length, elem_size bytes */
+#define QXB_ELEM_OTHER  6     /* present but not decoded (vlen strings, references, Julia structs) */
+int  qxb_jld2_open(const char* path, qxb_jld2** f);
+void qxb_jld2_close(qxb_jld2* f);
+/* datasets reachable from the root group (JLD2's `_types` group skipped); checksum_failures (may be NULL) counts
+ * version-2 structures whose lookup3 checksum did not match. */
+int  qxb_jld2_count(const qxb_jld2* f, int* n, int* checksum_failures);
+/* name is owned by the handle; dims (Julia / column-major order, room for QXB_JLD2_MAX_RANK) and the rest may be NULL */
+int  qxb_jld2_info(const qxb_jld2* f, int i, const char** name, int* elem_kind, int* elem_size, int* rank, int64_t* dims);
+/* as_c64 != 0: numeric elements converted to ComplexF64 (16 bytes each); 0: the stored bytes (elem_size each) */
+int  qxb_jld2_read(const qxb_jld2* f, int i, void* out, int as_c64);
+/* commit_types != 0 stores the complex datatypes under `_types/` and references them (JLD2.jl's layout);
+ * 0 writes them inline (any HDF5 tool reads it; JLD2.jl sees NamedTuple{(:re, :im)} elements). */
+int  qxb_jld2_write(const char* path, int n, const char* const* names, const int* elem_kinds, const int* elem_sizes,
+                    const int* ranks, const int64_t* const* dims, const void* const* data, int commit_types);
+/* qxb_graph_set_data for every numeric dataset of the file (dataset name = data label). */
+int  qxb_graph_load_jld2(qxb_graph* g, const char* path, int* n_set /*may be NULL*/);
+
+/* Parameter file (src/outputs.jl:47-78, docs/src/users_guide.md:22-35). */
+#define QXB_METHOD_LIST      0
+#define QXB_METHOD_UNIFORM   1
+#define QXB_METHOD_REJECTION 2
+typedef struct qxb_params {
+    int32_t method;
+    int32_t has_seed;
+    int64_t seed;
+    int64_t num_qubits;       /* List: length of the strings */
+    int64_t num_samples;
+    double  M;                /* Rejection (outputs.jl:57-62) */
+    int32_t fix_M;
+    int32_t reserved;
+    int64_t n_bitstrings;     /* List: strings in the file; Uniform: num_samples strings drawn WITH replacement
+                                 (simulation.jl:24-28) from the library's documented splitmix64 stream -- Julia's
+                                 MersenneTwister stream is not reproduced; Rejection: 0 */
+} qxb_params;
+/* bitstrings (may be NULL to query): n_bitstrings x (num_qubits + 1) bytes, each string NUL-terminated. */
+int  qxb_params_read(const char* yml_path, qxb_params* p, char* bitstrings, int64_t buflen);
+
+/* QXContexts.execute(dsl_file, input_file, param_file, output_file; max_amplitudes, max_slices) (bin/qxrun.jl:83-87)
+ * on this process' GPU.  input_file / param_file NULL = the DSL name with .jld2 / .yml (qxrun.jl:21,25);
+ * max_amplitudes / max_slices < 0 = all, else the FIRST n (qxrun.jl:32-39); replan_candidates > 0 runs
+ * qxb_graph_replan first.  Writes output_file (may be NULL) as JLD2 with datasets "bitstrings"
+ * (fixed-length strings) and "amplitudes" (complex of `dtype`).  seconds (may be NULL) receives the reference's
+ * timer sections: [0] parse input files, [1] create context, [2] simulation, [3] write results.
+ * List and Uniform methods; Rejection is QXB_ERR_UNSUPP here (Python harness). */
+int  qxb_execute_files(const char* dsl_file, const char* input_file, const char* param_file, const char* output_file,
+                       int dtype, int64_t max_amplitudes, int64_t max_slices, int replan_candidates,
+                       int64_t* n_amplitudes, double* seconds);
+
 /* test hook (not part of the drop-in surface): shared-memory offset contributed by tile-index bit `bit` in the
  * tensor-core GEMM kernels' staging layouts; tests/test_mma_layout.py replays the kernels' index arithmetic on the CPU */
 int  qxb_debug_mma_smem_bit(int dtype, int is_b, int tile_bits, int bit);
+/* test hook: the lookup3 checksum of HDF5 version-2 metadata, checked against Jenkins' published vectors */
+uint32_t qxb_debug_lookup3(const void* data, size_t n, uint32_t initval);
 
 #ifdef __cplusplus
 }

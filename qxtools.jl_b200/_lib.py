@@ -23,6 +23,8 @@ SYMBOLS = [
     "qxb_graph_describe", "qxb_graph_replan", "qxb_graph_replan_ex", "qxb_graph_program_text", "qxb_graph_configure", "qxb_graph_compile", "qxb_amplitudes", "qxb_amplitudes_device",
     "qxb_amplitudes_subspace", "qxb_partition_vars", "qxb_graph_describe_mask", "qxb_graph_cost_bytes",
     "qxb_last_stats", "qxb_profile_dump", "qxb_debug_mma_smem_bit",
+    "qxb_jld2_open", "qxb_jld2_close", "qxb_jld2_count", "qxb_jld2_info", "qxb_jld2_read", "qxb_jld2_write",
+    "qxb_graph_load_jld2", "qxb_params_read", "qxb_execute_files", "qxb_debug_lookup3",
 ]
 
 
@@ -37,6 +39,13 @@ class Options(C.Structure):
                 ("profile", C.c_int32), ("no_cuda_graph", C.c_int32),
                 ("sum_at_root", C.c_int32), ("no_smem_stage", C.c_int32),
                 ("no_gemm", C.c_int32), ("gemm_mode", C.c_int32)]
+
+
+class Params(C.Structure):
+    """qxb_params (include/qxb200.h): the parameter file of a triple, outputs.jl:47-78."""
+    _fields_ = [("method", C.c_int32), ("has_seed", C.c_int32), ("seed", C.c_int64), ("num_qubits", C.c_int64),
+                ("num_samples", C.c_int64), ("M", C.c_double), ("fix_M", C.c_int32), ("reserved", C.c_int32),
+                ("n_bitstrings", C.c_int64)]
 
 
 class Stats(C.Structure):
@@ -93,6 +102,18 @@ def load():
         "qxb_graph_cost_bytes": (i32, [p, C.c_uint64, i64, C.POINTER(C.c_double)]),
         "qxb_last_stats": (i32, [p, C.POINTER(Stats)]),
         "qxb_profile_dump": (i32, [p, cp]),
+        "qxb_debug_mma_smem_bit": (i32, [i32, i32, i32, i32]),
+        "qxb_jld2_open": (i32, [cp, C.POINTER(p)]),
+        "qxb_jld2_close": (None, [p]),
+        "qxb_jld2_count": (i32, [p, C.POINTER(i32), C.POINTER(i32)]),
+        "qxb_jld2_info": (i32, [p, i32, C.POINTER(cp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), pi64]),
+        "qxb_jld2_read": (i32, [p, i32, p, i32]),
+        "qxb_jld2_write": (i32, [cp, i32, C.POINTER(cp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
+                                 C.POINTER(pi64), C.POINTER(p), i32]),
+        "qxb_graph_load_jld2": (i32, [p, cp, C.POINTER(i32)]),
+        "qxb_params_read": (i32, [cp, C.POINTER(Params), p, i64]),
+        "qxb_debug_lookup3": (C.c_uint32, [p, C.c_size_t, C.c_uint32]),
+        "qxb_execute_files": (i32, [cp, cp, cp, cp, i32, i64, i64, i32, pi64, C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

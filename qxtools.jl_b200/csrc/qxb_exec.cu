@@ -924,6 +924,8 @@ int guard(F&& f) {
 
 }  // namespace
 
+void qxb::set_last_error(const std::string& msg) { g_err = msg; }
+
 // =============================================================== C ABI
 extern "C" {
 

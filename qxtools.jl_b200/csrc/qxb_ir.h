@@ -19,6 +19,9 @@ struct Error : std::runtime_error {
     Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
 };
 
+// message returned by qxb_last_error() on this thread (defined next to the C ABI, qxb_exec.cu)
+void set_last_error(const std::string& msg);
+
 // ----------------------------------------------------------------- DSL level
 enum CmdKind { CMD_LOAD, CMD_OUTPUT, CMD_VIEW, CMD_NCON, CMD_SAVE };
 

@@ -7,8 +7,10 @@
             max_amplitudes=None, max_slices=None, timings=False)
 
 * ``param_file`` defaults to the DSL name with ``.yml``, ``input_file`` to the DSL
-  name with the data suffix (qxrun.jl:21,25).  Data files are ``.npz`` in this
-  Python harness (no HDF5/JLD2 library in the image; the Julia shim reads ``.jld2``).
+  name with ``.jld2`` (qxrun.jl:21,25), read by the library's native JLD2 reader
+  (``csrc/qxb_jld2.cpp``); the harness' older ``.npz`` data files are used when no
+  ``.jld2`` sits next to the DSL file.  ``output_file``: ``.jld2`` (datasets
+  ``bitstrings`` and ``amplitudes``) unless the name ends in ``.npz``.
 * ``max_amplitudes`` / ``max_slices`` keep the FIRST N of the parameter file /
   slice space (qxrun.jl:32-39).
 * ``use_mpi`` -> torch.distributed (one process per GPU, launched by torchrun);
@@ -27,7 +29,21 @@ import numpy as np
 import yaml
 
 from .dist import Distribution
+from .jld2 import load_data_file, save_jld2
 from .simulation import amplitudes_uniform
+
+
+def write_results(output_file: str, bitstrings, amplitudes, **extra) -> None:
+    """The results file ``bin/qxrun.jl -o`` names (docs/src/distributed.md:30-33): JLD2 with the
+    datasets ``bitstrings`` (fixed-length strings) and ``amplitudes``; ``.npz`` on request."""
+    if output_file.endswith(".npz"):
+        np.savez(output_file, bitstrings=np.array(bitstrings), amplitudes=np.asarray(amplitudes), **extra)
+        return
+    n_q = max([len(b) for b in bitstrings], default=1)
+    arrays = {"bitstrings": np.array([b.encode() for b in bitstrings], dtype=f"S{max(1, n_q)}"),
+              "amplitudes": np.asarray(amplitudes)}
+    arrays.update({k: np.asarray(v, dtype=np.float64) for k, v in extra.items()})
+    save_jld2(output_file, arrays, commit_types=False)
 
 
 def _bitstrings_from_params(params: dict, max_amplitudes: Optional[int]):
@@ -57,11 +73,12 @@ def execute(dsl_file: str, input_file: Optional[str] = None, param_file: Optiona
     from .executor import Graph, init
     stem = os.path.splitext(dsl_file)[0]
     param_file = param_file or stem + ".yml"
-    input_file = input_file or stem + ".npz"
+    if input_file is None:
+        input_file = stem + ".jld2" if os.path.exists(stem + ".jld2") or not os.path.exists(stem + ".npz") else stem + ".npz"
     t = OrderedDict()
     t0 = time.perf_counter()
     text = open(dsl_file).read()
-    data = dict(np.load(input_file))
+    data = load_data_file(input_file)
     params = yaml.safe_load(open(param_file))
     t["Parse input files"] = time.perf_counter() - t0
 
@@ -100,8 +117,7 @@ def execute(dsl_file: str, input_file: Optional[str] = None, param_file: Optiona
             t["Simulation"] = time.perf_counter() - t0
             results = OrderedDict(zip(bs, amps))
             if output_file:
-                np.savez(output_file if output_file.endswith(".npz") else output_file + ".npz",
-                         bitstrings=np.array(bs), amplitudes=np.array(amps), M=info["M"], drawn=info["drawn"])
+                write_results(output_file, bs, np.array(amps), M=info["M"], drawn=info["drawn"])
             if timings:
                 for k, v in t.items():
                     print(f"  {k:<20s} {v * 1e3:10.3f} ms")
@@ -137,8 +153,7 @@ def execute(dsl_file: str, input_file: Optional[str] = None, param_file: Optiona
         t0 = time.perf_counter()
         results = OrderedDict((b, complex(a)) for b, a in zip(bitstrings, full))
         if output_file:
-            np.savez(output_file if output_file.endswith(".npz") else output_file + ".npz",
-                     bitstrings=np.array(bitstrings), amplitudes=full)
+            write_results(output_file, bitstrings, full)
         t["Write results"] = time.perf_counter() - t0
         if timings:
             for k, v in t.items():

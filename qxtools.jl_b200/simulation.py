@@ -82,15 +82,19 @@ def generate_parameter_file(filename_prefix: str, output_parameters) -> None:
         yaml.safe_dump({"output": _plain(output_parameters)}, f, sort_keys=False)
 
 
-def generate_dsl_files(compute_graph, prefix: str, force: bool = True, metadata=None) -> None:
+def generate_dsl_files(compute_graph, prefix: str, force: bool = True, metadata=None, npz: bool = False) -> None:
     """QXContexts.generate_dsl_files (call site simulation.jl:73): ``<prefix>.qx`` and
-    the tensor data file (``.npz`` here, ``.jld2`` through the Julia shim)."""
+    the tensor data file ``<prefix>.jld2`` (native writer, ``csrc/qxb_jld2.cpp``); ``npz=True`` also
+    keeps the ``.npz`` copy the benchmark caches use."""
     import os
-    if not force and (os.path.exists(prefix + ".qx") or os.path.exists(prefix + ".npz")):
+    from .jld2 import save_jld2
+    if not force and (os.path.exists(prefix + ".qx") or os.path.exists(prefix + ".jld2")):
         raise FileExistsError(prefix)
     with open(prefix + ".qx", "w") as f:
         f.write(write_dsl(compute_graph, metadata))
-    np.savez(prefix + ".npz", **{k: np.asfortranarray(v) for k, v in compute_graph.tensors.items()})
+    save_jld2(prefix + ".jld2", {k: np.asarray(v, dtype=np.complex128) for k, v in compute_graph.tensors.items()})
+    if npz:
+        np.savez(prefix + ".npz", **{k: np.asfortranarray(v) for k, v in compute_graph.tensors.items()})
 
 
 def generate_simulation_files(circ: Circuit, output_prefix: str = "simulation_input",

@@ -50,9 +50,13 @@ def test_tensor_cache_save(tmp_path):
     tc = TensorCache()
     a = np.arange(6.0).reshape(2, 3)
     sym = tc.push(a)
+    # test/test_compute_graph.jl:19-22: save_cache to tmp.jld2, load, compare every key
+    from qxb200.jld2 import load_jld2
+    save_cache(tc, str(tmp_path / "tmp.jld2"))
+    got = load_jld2(str(tmp_path / "tmp.jld2"))
+    assert list(got) == [sym] and np.array_equal(got[sym], a) and got[sym].dtype == np.complex128
     save_cache(tc, str(tmp_path / "t.npz"))
-    got = np.load(tmp_path / "t.npz")
-    assert np.array_equal(got[sym], a)
+    assert np.array_equal(np.load(tmp_path / "t.npz")[sym], a)
     with pytest.raises(ValueError):
         save_cache(tc, str(tmp_path / "t.jld"))
 
@@ -131,7 +135,7 @@ def test_generate_simulation_files(tmp_path):
     circ = q.create_rqc_circuit(3, 3, 8, 42)
     q.generate_simulation_files(circ, prefix, 2, seed=42, time=0,
                                 output_args=q.output_params_dict(9, 15, seed=1))
-    for ext in (".qx", ".npz", ".yml"):
+    for ext in (".qx", ".jld2", ".yml"):                       # test/test_bin.jl:18
         assert os.path.exists(prefix + ext)
     y = yaml.safe_load(open(prefix + ".yml"))
     assert y["output"]["method"] == "List"
