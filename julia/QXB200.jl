@@ -179,4 +179,24 @@ function execute(dsl_file::String, input_file::Union{String, Nothing}=nothing,
     results
 end
 
+"""
+    execute_native(dsl_file, input_file, param_file, output_file; max_amplitudes, max_slices, elt, replan)
+
+The whole file triple inside the library (`qxb_execute_files`): `.qx` parser, native JLD2 and YAML readers, compile,
+contraction, JLD2 results file.  Same defaults as `bin/qxrun.jl:21,25`.  Returns the number of amplitudes and the
+four timer sections of the reference's table (parse, context, simulation, write), in seconds.
+"""
+function execute_native(dsl_file::String, input_file::Union{String, Nothing}=nothing,
+                        param_file::Union{String, Nothing}=nothing, output_file::String="";
+                        max_amplitudes::Union{Int, Nothing}=nothing, max_slices::Union{Int, Nothing}=nothing,
+                        elt::Type=ComplexF32, replan::Int=0)
+    n, sec = Ref{Int64}(0), zeros(Cdouble, 4)
+    opt(x) = x === nothing ? C_NULL : x
+    check(ccall((:qxb_execute_files, LIB), Cint,
+                (Cstring, Cstring, Cstring, Cstring, Cint, Int64, Int64, Cint, Ref{Int64}, Ptr{Cdouble}),
+                dsl_file, opt(input_file), opt(param_file), output_file, elt == ComplexF32 ? C32 : C64,
+                max_amplitudes === nothing ? -1 : max_amplitudes, max_slices === nothing ? -1 : max_slices, replan, n, sec))
+    n[], sec
+end
+
 end # module

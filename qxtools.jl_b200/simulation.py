@@ -99,13 +99,13 @@ def generate_dsl_files(compute_graph, prefix: str, force: bool = True, metadata=
 
 def generate_simulation_files(circ: Circuit, output_prefix: str = "simulation_input",
                               number_bonds_to_slice: int = 2, decompose: bool = True,
-                              seed: Optional[int] = None, output_args=None, **kwargs) -> None:
-    """simulation.jl:52-77."""
+                              seed: Optional[int] = None, output_args=None, npz: bool = False, **kwargs) -> None:
+    """simulation.jl:52-77: writes ``<prefix>.qx``, ``<prefix>.jld2`` and ``<prefix>.yml``."""
     tnc = convert_to_tnc(circ, decompose=decompose)
     fc_seed = -1 if seed is None else seed
     bond_groups, plan, metadata = contraction_scheme(tnc, number_bonds_to_slice, seed=fc_seed, **kwargs)
     cg = build_compute_graph(tnc, plan, bond_groups)
-    generate_dsl_files(cg, output_prefix, force=True, metadata=metadata)
+    generate_dsl_files(cg, output_prefix, force=True, metadata=metadata, npz=npz)
     if output_args is None:
         output_args = output_params_dict(tnc.qubits)
     generate_parameter_file(output_prefix, output_args)

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_header_symbols_exported(lib_built):
     hdr = open(os.path.join(ROOT, "include", "qxb200.h")).read()
-    declared = set(re.findall(r"\b(qxb_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(qxb_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_lib.SYMBOLS)
     for s in declared:
         assert hasattr(lib_built, s), s

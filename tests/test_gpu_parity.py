@@ -153,9 +153,10 @@ def test_execute_file_triple(gpu, tmp_path):
     prefix = str(tmp_path / "rqc")
     circ = q.create_rqc_circuit(3, 3, 8, 42)
     q.generate_simulation_files(circ, prefix, 3, seed=42, time=0, output_args=q.output_params_dict(9, 6, seed=5))
+    from qxb200.jld2 import load_jld2
     res = execute(prefix + ".qx", output_file=prefix + "_out.npz", dtype="c64")
     txt = open(prefix + ".qx").read()
-    data = dict(np.load(prefix + ".npz"))
+    data = dict(load_jld2(prefix + ".jld2"))
     ref = orc.amplitudes(orc.parse_dsl(txt), data, list(res.keys()))
     assert rel_err(np.array(list(res.values())), ref, 9) < 1e-10
     res2 = execute(prefix + ".qx", max_amplitudes=2, max_slices=3, dtype="c64")

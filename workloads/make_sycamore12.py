@@ -1,4 +1,4 @@
-"""Writes workloads/sycamore53_d12_c32_s16.{qx,npz,yml}: BASELINE.json configs[4], a Sycamore-like 53-qubit
+"""Writes workloads/sycamore53_d12_c32_s16.{qx,jld2,npz,yml}: BASELINE.json configs[4], a Sycamore-like 53-qubit
 12-cycle fSim circuit, sliced by the LIBRARY's GPU-aware slicing (qxb_graph_replan_ex, n_free = -3) so that
 the largest tensor of one slice is 2^31 ComplexF32 elements (17 GB) -- "largest intermediate held in HBM".
 
@@ -48,6 +48,8 @@ body = "\n".join(ln for ln in g.text.splitlines() if not ln.startswith("#"))
 with open(prefix + ".qx", "w") as f:
     f.write(header + body + "\n")
 np.savez(prefix + ".npz", **data)
+from qxb200.jld2 import save_jld2  # noqa: E402
+save_jld2(prefix + ".jld2", {k: np.asarray(v, dtype=np.complex128) for k, v in data.items()})
 import yaml                                       # noqa: E402
 with open(prefix + ".yml", "w") as f:
     yaml.safe_dump({"output": _plain(output_params_dict(53, 16, seed=2020))}, f, sort_keys=False)

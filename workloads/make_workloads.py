@@ -1,4 +1,4 @@
-"""Writes the benchmark file triples (<name>.qx / .npz / .yml) that bench.py loads.
+"""Writes the benchmark file triples (<name>.qx / .jld2 / .yml, plus the .npz copy of the data) that bench.py loads.
 
 Seeded and deterministic: circuits from qxb200.circuits (numpy PCG64, seed 42), plan from
 contraction_scheme(time=0) = deterministic min-fill + greedy tree-trimming slicing -- the
@@ -24,5 +24,5 @@ for name, w in bench.WORKLOADS.items():
     n_q = circ.num_qubits
     prefix = os.path.join(ROOT, "workloads", name)
     q.generate_simulation_files(circ, prefix, w["n_slice"], seed=w["seed"], time=0,
-                                output_args=q.output_params_dict(n_q, 16, seed=2020))
+                                output_args=q.output_params_dict(n_q, 16, seed=2020), npz=True)
     print(name, os.path.getsize(prefix + ".qx"), "bytes of .qx")
