@@ -229,6 +229,9 @@ int  qxb_execute_files(const char* dsl_file, const char* input_file, const char*
 /* test hook (not part of the drop-in surface): shared-memory offset contributed by tile-index bit `bit` in the
  * tensor-core GEMM kernels' staging layouts; tests/test_mma_layout.py replays the kernels' index arithmetic on the CPU */
 int  qxb_debug_mma_smem_bit(int dtype, int is_b, int tile_bits, int bit);
+/* test hook: raw array of the per-contraction launch templates (struct OpParams of csrc/qxb_kernels.cuh, one per
+ * lowered op, pointers unset) for n_free batched variables; returns the bytes needed.  Host logic only. */
+int64_t qxb_debug_templates(qxb_graph* g, int n_free, void* buf, int64_t buflen);
 /* test hook: the lookup3 checksum of HDF5 version-2 metadata, checked against Jenkins' published vectors */
 uint32_t qxb_debug_lookup3(const void* data, size_t n, uint32_t initval);
 

@@ -24,7 +24,7 @@ SYMBOLS = [
     "qxb_amplitudes_subspace", "qxb_partition_vars", "qxb_graph_describe_mask", "qxb_graph_cost_bytes",
     "qxb_last_stats", "qxb_profile_dump", "qxb_debug_mma_smem_bit",
     "qxb_jld2_open", "qxb_jld2_close", "qxb_jld2_count", "qxb_jld2_info", "qxb_jld2_read", "qxb_jld2_write",
-    "qxb_graph_load_jld2", "qxb_params_read", "qxb_execute_files", "qxb_debug_lookup3",
+    "qxb_graph_load_jld2", "qxb_params_read", "qxb_execute_files", "qxb_debug_lookup3", "qxb_debug_templates",
 ]
 
 
@@ -112,6 +112,7 @@ def load():
                                  C.POINTER(pi64), C.POINTER(p), i32]),
         "qxb_graph_load_jld2": (i32, [p, cp, C.POINTER(i32)]),
         "qxb_params_read": (i32, [cp, C.POINTER(Params), p, i64]),
+        "qxb_debug_templates": (i64, [p, i32, p, i64]),
         "qxb_debug_lookup3": (C.c_uint32, [p, C.c_size_t, C.c_uint32]),
         "qxb_execute_files": (i32, [cp, cp, cp, cp, i32, i64, i64, i32, pi64, C.POINTER(C.c_double)]),
     }

@@ -200,6 +200,7 @@ void build_templates(Variant& v, int dtype) {
     // than 96 / 64 on the tree-searched 7x7 program (more loads in flight per thread; profiles/r1p_summary.md)
     const int kc_regs_multi = [] { const char* e = getenv("QXB_KC_REGS_MULTI"); return e ? atoi(e) : 128; }();
     const int kc_regs_one = [] { const char* e = getenv("QXB_KC_REGS_ONE"); return e ? atoi(e) : 96; }();
+    const int min_lob = [] { const char* e = getenv("QXB_MIN_LOB"); return e ? std::min(8, std::max(5, atoi(e))) : 8; }();
     v.tmpl.resize(v.L.ops.size());
     v.gtmpl.resize(v.L.ops.size());
     v.gemm_tmb.assign(v.L.ops.size(), 0); v.gemm_tnb.assign(v.L.ops.size(), 0);
@@ -215,13 +216,16 @@ void build_templates(Variant& v, int dtype) {
         p.nC = nC; p.nK = op.nK;
         // register tile: lowest M-only / N-only bits at C positions >= 5, so the 32 lanes of a warp
         // still cover C bits 0..4 (one contiguous 32-element store per warp and tile element)
+        // QXB_MIN_LOB (5..8, default 8) = thread bits that must remain: below 8 the 256 threads of a CTA span
+        // 2^(8 - lob) tiles (bitstring rows), which lets nodes with <= 2^8 elements per bitstring have a register
+        // tile at all (experiment for the L1-bound small nodes of the tree-searched plans, profiles/r1p_summary.md)
         std::vector<int> mbits, nbits;
-        if (nC > 8) {
+        if (nC > min_lob) {
             for (int b = 5; b < nC; ++b) {
                 if (mapA[b] >= 0 && mapB[b] < 0 && mbits.size() < 2) mbits.push_back(b);
                 else if (mapB[b] >= 0 && mapA[b] < 0 && nbits.size() < 2) nbits.push_back(b);
             }
-            while ((int)(mbits.size() + nbits.size()) > nC - 8) {      // keep 8 thread bits
+            while ((int)(mbits.size() + nbits.size()) > nC - min_lob) {      // keep min_lob thread bits
                 if (nbits.size() >= mbits.size() && !nbits.empty()) nbits.pop_back(); else mbits.pop_back();
             }
         }
@@ -1104,6 +1108,25 @@ int64_t qxb_graph_describe(qxb_graph* g, int n_free, char* buf, int64_t buflen) 
         std::string s = describe_json(g->prog, L);
         need = (int64_t)s.size() + 1;
         if (buf && buflen >= need) memcpy(buf, s.c_str(), need);
+    });
+    return rc == QXB_OK ? need : rc;
+}
+
+// test hook: the per-op launch templates (thread / register-tile / hi-bit split of every contraction, with the
+// address maps composed for the kernel) exactly as build_templates hands them to contract_kernel, so that
+// tests/template_emulator.py can replay the kernel's index arithmetic on the CPU.  Pure host logic.
+int64_t qxb_debug_templates(qxb_graph* g, int n_free, void* buf, int64_t buflen) {
+    int64_t need = 0;
+    int rc = guard([&] {
+        if (!g) throw Error(QXB_ERR_ARG, "null graph");
+        ensure_analysed(g);
+        const int k = (int)g->prog.vars.size();
+        Variant v;
+        v.L = lower(g->prog, low_mask(n_free < 0 || n_free > k ? k : n_free), !g->opts.sum_at_root);
+        plan_memory(v.L);
+        build_templates(v, g->dtype);
+        need = (int64_t)(v.tmpl.size() * sizeof(OpParams));
+        if (buf && buflen >= need && need) memcpy(buf, v.tmpl.data(), (size_t)need);
     });
     return rc == QXB_OK ? need : rc;
 }

@@ -25,7 +25,10 @@ if os.environ.get("PROBE_CONFIGS") == "smem":
                ("stage_more", {"QXB_SMEM_RATIO": "0.3", "QXB_SMEM_MINHB": "0"}),
                ("stage_more_shared", {"QXB_SMEM_RATIO": "0.3", "QXB_SMEM_MINHB": "0", "QXB_SMEM_SHARED": "1"}),
                ("shared_only", {"QXB_SMEM_SHARED": "1"})]
-KNOBS = ("QXB_SMEM_RATIO", "QXB_SMEM_MINHB", "QXB_SMEM_SHARED", "QXB_MINB", "QXB_KC_REGS_MULTI", "QXB_KC_REGS_ONE")
+if os.environ.get("PROBE_CONFIGS") == "lob":
+    # register tiles for nodes with <= 2^8..2^10 elements per bitstring: the CTA's 256 threads span several bitstring rows
+    CONFIGS = [("default", {}), ("lob7", {"QXB_MIN_LOB": "7"}), ("lob6", {"QXB_MIN_LOB": "6"}), ("lob5", {"QXB_MIN_LOB": "5"})]
+KNOBS = ("QXB_MIN_LOB", "QXB_SMEM_RATIO", "QXB_SMEM_MINHB", "QXB_SMEM_SHARED", "QXB_MINB", "QXB_KC_REGS_MULTI", "QXB_KC_REGS_ONE")
 results, ref = {}, None
 for tag, env in CONFIGS:
     for k in KNOBS:
