@@ -87,6 +87,11 @@ int  qxb_graph_set_data(qxb_graph* g, const char* data_label, const void* c64_co
 
 /* queries (pure host logic; usable without a GPU) */
 int  qxb_graph_num_outputs(const qxb_graph* g, int* n_outputs);
+/* Shape of the saved tensor: rank 0 for a closed network (one amplitude per bitstring).  An OPEN network -- built
+ * with convert_to_tnc(...; no_output=true), which is how the reference's own tests drive contract_tn!
+ * (test/test_contraction_planning.jl:50-61) -- saves a tensor: rank > 0 and dims (may be NULL) in Julia order;
+ * qxb_amplitudes* then write prod(dims) values per bitstring, column-major, bitstring-major. */
+int  qxb_graph_root_dims(const qxb_graph* g, int* rank, int64_t* dims);
 /* k slice symbols v1..vk and their extents; dims may be NULL to query k only. */
 int  qxb_graph_num_slice_vars(const qxb_graph* g, int* k, int64_t* dims);
 int  qxb_graph_num_slices(const qxb_graph* g, int64_t* n_slices);
@@ -122,7 +127,8 @@ int  qxb_graph_compile(qxb_graph* g, const qxb_options* opts);
 
 /* THE HOT PATH.  amplitude[a] = sum_{s in [slice_begin, slice_end)} root(bits[a], s).
  * bits: [n_amp][n_outputs] bytes, 0/1 (2 = '+', 3 = '-', basics.md:62), char i <-> qubit i.
- * out:  [n_amp] interleaved complex of the graph's dtype.
+ * out:  [n_amp] interleaved complex of the graph's dtype ([n_amp][prod(root dims)] for an open network,
+ *       see qxb_graph_root_dims).
  * Host-pointer form: H2D of bits, compute, D2H of out, synchronised on return
  * (replaces the "Simulation" section of QXContexts.execute and contract_tn!). */
 int  qxb_amplitudes(qxb_graph* g, const uint8_t* bits, int64_t n_amp,

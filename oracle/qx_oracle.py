@@ -150,10 +150,11 @@ def ncon_pair(A, a_l, B, b_l, c_l):
 
 
 def contract_instance(cmds: Sequence[Cmd], data: Dict[str, np.ndarray], bits: str,
-                      svals: Dict[str, int], dtype=np.complex128):
+                      svals: Dict[str, int], dtype=np.complex128, track_sliced: bool = False):
     """Run the whole program for ONE (bitstring, slice assignment) and return the
     ``save``d tensor (a scalar for closed networks)."""
     env: Dict[str, np.ndarray] = {}
+    sliced: Dict[str, set] = {}          # track_sliced: per tensor, the positions of modes a view has fixed
     result = None
     for c in cmds:
         if c.op == "load":
@@ -178,11 +179,18 @@ def contract_instance(cmds: Sequence[Cmd], data: Dict[str, np.ndarray], bits: st
             name, target, sym, pos, _dim = c.args
             # rank is preserved: the sliced mode keeps extent 1 (users_guide.md:85-88)
             env[name] = np.take(env[target], [svals[sym]], axis=pos - 1)
+            sliced[name] = sliced.get(target, set()) | {pos - 1}
         elif c.op == "ncon":
             out, c_l, a, a_l, b, b_l = c.args
             env[out] = ncon_pair(env[a], a_l, env[b], b_l, c_l)
+            if track_sliced:
+                lab = {a_l[i] for i in sliced.get(a, ())} | {b_l[i] for i in sliced.get(b, ())}
+                sliced[out] = {i for i, l in enumerate(c_l) if l in lab}
         elif c.op == "save":
             result = env[c.args[1]]
+            if track_sliced and sliced.get(c.args[1]):
+                # the slices would be different ELEMENTS of the result, not terms of a sum
+                raise ValueError("a mode of the saved tensor is sliced: open indices cannot be slice bonds")
     if result is None:
         raise ValueError("program has no save instruction")
     return result
@@ -198,6 +206,21 @@ def amplitude(cmds, data, bits: str, dtype=np.complex128, slice_begin=0, slice_e
     for s in range(slice_begin, slice_end):
         r = contract_instance(cmds, data, bits, slice_values(s, dims), dtype)
         acc = acc + np.asarray(r).reshape(-1)[0]
+    return acc
+
+
+def contract(cmds, data, bits: str = "", dtype=np.complex128, slice_begin=0, slice_end=None) -> np.ndarray:
+    """The saved TENSOR summed over slices: what ``contract_tn!`` returns for an open network
+    (/root/reference/test/test_contraction_planning.jl:58-61: ``reshape(output, 8)`` is the GHZ state vector).
+    For a closed network this is the amplitude as a 0-d array."""
+    dims = slice_dims(cmds)
+    total = int(np.prod([d for _, d in dims], dtype=np.int64)) if dims else 1
+    if slice_end is None:
+        slice_end = total
+    acc = None
+    for s in range(slice_begin, slice_end):
+        r = np.asarray(contract_instance(cmds, data, bits, slice_values(s, dims), dtype, track_sliced=True))
+        acc = r.copy() if acc is None else acc + r
     return acc
 
 

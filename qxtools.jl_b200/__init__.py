@@ -19,4 +19,12 @@ from .simulation import (single_amplitude, run_simulation, generate_simulation_f
                          generate_parameter_file, generate_dsl_files, amplitudes_all,
                          amplitudes_uniform, output_params_dict)
 
+
+
+def contract_tn(tnc, plan, dtype: str = "c64"):
+    """``QXTns.contract_tn!`` on the GPU, open networks included (see ``executor.contract_tn``)."""
+    from .executor import contract_tn as _impl
+    return _impl(tnc, plan, dtype)
+
+
 __version__ = "0.1.0"

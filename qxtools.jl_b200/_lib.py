@@ -19,7 +19,7 @@ SYMBOLS = [
     "qxb_version", "qxb_last_error", "qxb_init", "qxb_shutdown", "qxb_set_stream", "qxb_device_synchronize",
     "qxb_graph_create", "qxb_graph_destroy", "qxb_graph_load", "qxb_graph_output", "qxb_graph_view",
     "qxb_graph_ncon", "qxb_graph_save", "qxb_graph_parse_dsl", "qxb_graph_set_data",
-    "qxb_graph_num_outputs", "qxb_graph_num_slice_vars", "qxb_graph_num_slices", "qxb_slice_values",
+    "qxb_graph_num_outputs", "qxb_graph_root_dims", "qxb_graph_num_slice_vars", "qxb_graph_num_slices", "qxb_slice_values",
     "qxb_graph_describe", "qxb_graph_replan", "qxb_graph_replan_ex", "qxb_graph_program_text", "qxb_graph_configure", "qxb_graph_compile", "qxb_amplitudes", "qxb_amplitudes_device",
     "qxb_amplitudes_subspace", "qxb_partition_vars", "qxb_graph_describe_mask", "qxb_graph_cost_bytes",
     "qxb_last_stats", "qxb_profile_dump", "qxb_debug_mma_smem_bit",
@@ -84,6 +84,7 @@ def load():
         "qxb_graph_parse_dsl": (i32, [p, cp, C.c_size_t]),
         "qxb_graph_set_data": (i32, [p, cp, p, pi64, i32]),
         "qxb_graph_num_outputs": (i32, [p, C.POINTER(i32)]),
+        "qxb_graph_root_dims": (i32, [p, C.POINTER(i32), pi64]),
         "qxb_graph_num_slice_vars": (i32, [p, C.POINTER(i32), pi64]),
         "qxb_graph_num_slices": (i32, [p, pi64]),
         "qxb_slice_values": (i32, [p, i64, pi64]),

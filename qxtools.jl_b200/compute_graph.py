@@ -175,6 +175,7 @@ class ComputeGraph:
     def __init__(self, root: ComputeNode, tensors: Dict[str, np.ndarray]):
         self.root = root
         self.tensors = tensors
+        self.root_indices: List[int] = []
 
     def commands(self):
         return [n.op for n in self.root.post_order()]
@@ -270,6 +271,18 @@ def build_compute_graph(tnc: TensorNetworkCircuit, plan: Sequence[Tuple[str, str
         for i in ids:
             cnt[i] = cnt.get(i, 0) + 1
 
+    # open wires (no input / no output tensors attached) are held by the outside world: count one extra carrier so
+    # that an open index shared by the last two tensors of its hyper-edge stays a mode of the result instead of
+    # being summed (QXTns keeps a distinct open Index per wire end; ids are merged per hyper-edge here)
+    open_ids = set()
+    if not tnc.output_tensors_:
+        open_ids |= set(tnc.wire)
+    if not tnc.input_tensors:
+        open_ids |= set(tnc.wire_first)
+    for i in open_ids:
+        if i in cnt:
+            cnt[i] += 1
+
     def contract(a, b, c):
         c_l, a_l, b_l, c_ids = _contraction_labels(net, a, b, cnt)
         for i in net[a] + net[b]:
@@ -299,4 +312,8 @@ def build_compute_graph(tnc: TensorNetworkCircuit, plan: Sequence[Tuple[str, str
     node = ComputeNode(SaveCommand("output", root))            # :94
     node.children.append(nodes[root])
     nodes[root].parent = node
-    return ComputeGraph(node, tc.to_dict())
+    cg = ComputeGraph(node, tc.to_dict())
+    # index id behind each mode of the saved tensor (empty for a closed network); a hyper-edge is ONE id here, so
+    # several open wires of the circuit may map to the same mode (contract_tn expands them, executor.py)
+    cg.root_indices = list(net[root])
+    return cg

@@ -136,6 +136,14 @@ void ensure_analysed(qxb_graph* g) {
     if (!g->prog.analysed) analyse(g->prog);
 }
 
+// values per bitstring in the result: 1 for a closed network, prod of the saved tensor's extents for an open one
+int64_t root_elems(qxb_graph* g) {
+    ensure_analysed(g);
+    int64_t n = 1;
+    for (const Mode& m : g->prog.defs[g->prog.root].modes) n *= m.ext;
+    return n;
+}
+
 // ------------------------------------------------------------------ leaves
 void upload_leaves(qxb_graph* g) {
     for (const TensorDef& d : g->prog.defs) {
@@ -657,7 +665,7 @@ StepPlan prepare_step(qxb_graph* g, std::vector<Block> blocks, int64_t n_amp) {
                                                       block_bytes + (int64_t)v->const_arena.bytes);
     }
     sp.chunk = chunk;
-    bool moved = g->acc.reserve(sizeof(double) * 2 * n_amp);
+    bool moved = g->acc.reserve(sizeof(double) * 2 * n_amp * root_elems(g));
     moved |= g->block_arena.reserve(max_block);
     moved |= g->chunk_arena.reserve(max_per_amp * chunk);
     if (moved) g->drop_step_graphs();
@@ -670,7 +678,7 @@ StepPlan prepare_step(qxb_graph* g, std::vector<Block> blocks, int64_t n_amp) {
 std::vector<Node> build_step(qxb_graph* g, const StepPlan& sp, const uint8_t* d_bits, int64_t n_amp, void* d_out) {
     std::vector<Node> nodes;
     {
-        Node m; m.ms_ptr = g->acc.p; m.ms_bytes = sizeof(double) * 2 * n_amp;
+        Node m; m.ms_ptr = g->acc.p; m.ms_bytes = sizeof(double) * 2 * n_amp * root_elems(g);
         nodes.push_back(std::move(m));
     }
     int sink = 0;                                     // last node of the serial spine
@@ -719,11 +727,30 @@ std::vector<Node> build_step(qxb_graph* g, const StepPlan& sp, const uint8_t* d_
                 nodes.push_back(std::move(n));
             }
             Node r;
+            bool open_root = false;
+            for (const auto& rm : L.root_modes) open_root |= rm.nbits > 0;
+            if (open_root) {
+                // tensor-valued save (open network): gather the modes into Julia order, sum the open slice bits
+                RootDesc d{};
+                d.elems = L.root_elems; d.n_modes = (int)L.root_modes.size();
+                for (int m = 0; m < d.n_modes; ++m) { d.ext[m] = (int)L.root_modes[m].ext; d.pos[m] = (unsigned char)L.root_modes[m].pos; }
+                for (const LayEntry& e : R.lay) {
+                    if (e.key >= 0) continue;
+                    if (d.n_vseg == 16) throw Error(QXB_ERR_UNSUPP, "more than 16 batched slice variables open in a tensor-valued root");
+                    d.vpos[d.n_vseg] = (unsigned char)e.pos; d.vbits[d.n_vseg] = (unsigned char)e.nbits; d.vtotal += e.nbits; ++d.n_vseg;
+                }
+                r.func = reduce_root_open_func(g->dtype);
+                const long long rb = (c.n * d.elems + 255) / 256;
+                r.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(rb, 148 * 8))); r.block = dim3(256);
+                r.arg((const void*)tensor_ptr(c, R)); r.arg((long long)(R.amp ? (1ll << R.span_bits) : 0));
+                r.arg((long long)c.n); r.arg((double)L.root_scale); r.arg((double*)g->acc.p); r.arg((long long)a0); r.arg(d);
+            } else {
             r.func = reduce_root_func(g->dtype);
             long long rb = (c.n * 32 + 255) / 256;
             r.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(rb, 148 * 8))); r.block = dim3(256);
             r.arg((const void*)tensor_ptr(c, R)); r.arg((long long)(R.amp ? (1ll << R.span_bits) : 0)); r.arg((int)R.span_bits);
             r.arg((long long)c.n); r.arg((double)L.root_scale); r.arg((double*)g->acc.p); r.arg((long long)a0);
+            }
             r.deps.push_back(sink);
             if (start != sink) r.deps.push_back(start);
             if (root_op >= 0) {
@@ -738,8 +765,9 @@ std::vector<Node> build_step(qxb_graph* g, const StepPlan& sp, const uint8_t* d_
     }
     Node f;
     f.func = finalize_func(g->dtype);
-    f.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>((n_amp + 255) / 256, 1024))); f.block = dim3(256);
-    f.arg((const double*)g->acc.p); f.arg((void*)d_out); f.arg((long long)n_amp);
+    const long long n_vals = (long long)n_amp * root_elems(g);
+    f.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>((n_vals + 255) / 256, 1024))); f.block = dim3(256);
+    f.arg((const double*)g->acc.p); f.arg((void*)d_out); f.arg((long long)n_vals);
     f.deps.push_back(sink);
     nodes.push_back(std::move(f));
     return nodes;
@@ -1071,6 +1099,16 @@ int qxb_graph_num_outputs(const qxb_graph* g, int* n) {
     });
 }
 
+int qxb_graph_root_dims(const qxb_graph* g, int* rank, int64_t* dims) {
+    return guard([&] {
+        if (!g || !rank) throw Error(QXB_ERR_ARG, "null argument");
+        ensure_analysed(const_cast<qxb_graph*>(g));
+        const std::vector<Mode>& ms = g->prog.defs[g->prog.root].modes;
+        *rank = (int)ms.size();
+        if (dims) for (size_t i = 0; i < ms.size(); ++i) dims[i] = ms[i].ext;
+    });
+}
+
 int qxb_graph_num_slice_vars(const qxb_graph* g, int* k, int64_t* dims) {
     return guard([&] {
         if (!g || !k) throw Error(QXB_ERR_ARG, "null argument");
@@ -1229,11 +1267,11 @@ int qxb_amplitudes(qxb_graph* g, const uint8_t* bits, int64_t n_amp, int64_t s0,
         }
         cudaStream_t st = stream();
         g->d_bits.reserve(nb);
-        g->d_out.reserve((size_t)n_amp * g->es());
+        g->d_out.reserve((size_t)n_amp * (size_t)root_elems(g) * g->es());
         if (g->prog.n_outputs > 0)
             CUDA_OK(cudaMemcpyAsync(g->d_bits.p, bits, (size_t)n_amp * g->prog.n_outputs, cudaMemcpyHostToDevice, st));
         run_amplitudes(g, (const uint8_t*)g->d_bits.p, n_amp, s0, s1, g->d_out.p);
-        CUDA_OK(cudaMemcpyAsync(out, g->d_out.p, (size_t)n_amp * g->es(), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaMemcpyAsync(out, g->d_out.p, (size_t)n_amp * (size_t)root_elems(g) * g->es(), cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaStreamSynchronize(st));
         if (g->opts.profile) collect_profile(g);
     });
@@ -1262,11 +1300,11 @@ int qxb_amplitudes_subspace(qxb_graph* g, const uint8_t* bits, int64_t n_amp, co
             if (seen > 3) throw Error(QXB_ERR_ARG, "bitstring entries must be 0, 1, 2 ('+') or 3 ('-')");
         }
         g->d_bits.reserve((size_t)n_amp * std::max(1, g->prog.n_outputs));
-        g->d_out.reserve((size_t)n_amp * g->es());
+        g->d_out.reserve((size_t)n_amp * (size_t)root_elems(g) * g->es());
         if (g->prog.n_outputs > 0)
             CUDA_OK(cudaMemcpyAsync(g->d_bits.p, bits, (size_t)n_amp * g->prog.n_outputs, cudaMemcpyHostToDevice, st));
         run_subspace(g, (const uint8_t*)g->d_bits.p, n_amp, fixed_vars, fixed_vals, n_fixed, g->d_out.p);
-        CUDA_OK(cudaMemcpyAsync(out, g->d_out.p, (size_t)n_amp * g->es(), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaMemcpyAsync(out, g->d_out.p, (size_t)n_amp * (size_t)root_elems(g) * g->es(), cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaStreamSynchronize(st));
         if (g->opts.profile) collect_profile(g);
     });

@@ -435,8 +435,12 @@ int qxb_execute_files(const char* dsl_file, const char* input_file, const char* 
         std::vector<std::string>& bs = pr.bitstrings;
         if (max_amplitudes >= 0 && (int64_t)bs.size() > max_amplitudes) bs.resize((size_t)max_amplitudes);   // qxrun.jl:32-35
         const int64_t n_amp = (int64_t)bs.size();
-        int n_out = 0;
+        int n_out = 0, root_rank = 0;
         ok(qxb_graph_num_outputs(g, &n_out));
+        ok(qxb_graph_root_dims(g, &root_rank, nullptr));
+        if (root_rank != 0)
+            throw Error(QXB_ERR_UNSUPP, "the program saves a tensor (open network): the file runner writes one amplitude per "
+                                        "bitstring; use qxb_amplitudes with qxb_graph_root_dims for open networks");
         if (n_amp > 0 && n_out != (int)pr.p.num_qubits)
             throw Error(QXB_ERR_ARG, "the program has " + std::to_string(n_out) + " outputs but the parameter file gives " +
                                      std::to_string(pr.p.num_qubits) + "-qubit bitstrings");

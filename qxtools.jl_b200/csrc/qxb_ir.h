@@ -137,6 +137,11 @@ struct Lowered {
     std::vector<int> output_leaves;          // LTensor indices materialised from the bitstrings
     int root = -1;
     std::vector<int> root_vars;              // batched variables still open in the root (summed by reduce_root)
+    // open (tensor-valued) root: one entry per DSL mode of the saved tensor, in the order of its label list =
+    // Julia dimension order of the result; empty for a closed network (scalar root)
+    struct RootMode { int64_t ext; int nbits; int pos; };
+    std::vector<RootMode> root_modes;
+    int64_t root_elems = 1;                  // prod of the mode extents: values per bitstring in the result
     double root_scale = 1.0;                 // prod of extents of free vars the root does not depend on
     // arena sizes in elements: const, block, and chunk = per_amp * n_amp
     int64_t const_elems = 0, block_elems = 0, chunk_elems_per_amp = 0;

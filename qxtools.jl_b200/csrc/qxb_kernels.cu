@@ -969,6 +969,42 @@ const void* reduce_root_func(int dtype) {
     return dtype == 0 ? (const void*)&reduce_root_kernel<float2> : (const void*)&reduce_root_kernel<double2>;
 }
 
+// Tensor-valued root (open network): one thread per (bitstring, output element).  The output index runs over the
+// saved tensor's TRUE extents in Julia order; its modes sit at arbitrary bit positions of the (power-of-two padded)
+// lowered root, and the batched slice bits still open in the root are summed here, in double.
+template <typename R2>
+__global__ void reduce_root_open_kernel(const R2* __restrict__ root, long long sU, long long n, double scale,
+                                        double* __restrict__ acc, long long amp0, const __grid_constant__ RootDesc d) {
+    const long long total = n * d.elems;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long u = i / d.elems, o = i - u * d.elems;
+        long long rest = o, addr = 0;
+        for (int m = 0; m < d.n_modes; ++m) {
+            const long long idx = rest % d.ext[m];
+            rest /= d.ext[m];
+            addr |= idx << d.pos[m];
+        }
+        const R2* r = root + u * sU + addr;
+        double sx = 0, sy = 0;
+        for (long long v = 0; v < (1ll << d.vtotal); ++v) {
+            long long va = 0;
+            int sh = 0;
+            for (int s = 0; s < d.n_vseg; ++s) {
+                va |= ((v >> sh) & ((1ll << d.vbits[s]) - 1ll)) << d.vpos[s];
+                sh += d.vbits[s];
+            }
+            const R2 x = __ldg(r + va);
+            sx += (double)x.x; sy += (double)x.y;
+        }
+        acc[2 * ((amp0 + u) * d.elems + o)] += scale * sx;
+        acc[2 * ((amp0 + u) * d.elems + o) + 1] += scale * sy;
+    }
+}
+
+const void* reduce_root_open_func(int dtype) {
+    return dtype == 0 ? (const void*)&reduce_root_open_kernel<float2> : (const void*)&reduce_root_open_kernel<double2>;
+}
+
 template <typename R2>
 __global__ void finalize_kernel(const double* __restrict__ acc, R2* __restrict__ out, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;

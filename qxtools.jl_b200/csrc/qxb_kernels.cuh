@@ -94,6 +94,17 @@ const void* kreduce_split_func(int dtype);
 const void* outleaf_func(int dtype);
 // reduce:   (const R2* root, long long sU, int span_bits, long long n, double scale, double* acc, long long amp0)
 const void* reduce_root_func(int dtype);
+// open (tensor-valued) root: gather of the saved tensor's modes into Julia (column-major) order + sum over the
+// batched slice bits still open in it.  reduce_open: (const R2* root, long long sU, long long n, double scale,
+// double* acc, long long amp0, RootDesc d); acc holds n_amp x d.elems complex doubles
+struct RootDesc {
+    long long elems;                 // values per bitstring = prod ext
+    int n_modes, n_vseg, vtotal;     // vtotal = sum of vbits
+    int ext[32];                     // true extent of each mode, Julia order
+    unsigned char pos[32];           // address bit of each mode in the lowered root
+    unsigned char vpos[16], vbits[16];
+};
+const void* reduce_root_open_func(int dtype);
 // finalize: (const double* acc, R2* out, long long n)
 const void* finalize_func(int dtype);
 

@@ -434,10 +434,32 @@ Lowered lower(const Program& p, uint64_t free_mask, bool early_sum) {
     if (R.kind != T_NCON) throw Error(QXB_ERR_UNSUPP, "the saved tensor must be the result of a contraction");
     L.root = lt_of_def[p.root];
     L.tensors[L.root].persistent = true;
-    for (const LayEntry& e : L.tensors[L.root].lay) {
-        if (e.key >= 0) throw Error(QXB_ERR_UNSUPP, "the saved tensor must be a scalar (closed network)");
-        L.root_vars.push_back(~e.key);
+    // A closed network saves a scalar.  An open one (convert_to_tnc(...; no_output=true), the case the reference's own
+    // contract_tn! tests use, test/test_contraction_planning.jl:58-61) saves a tensor: its modes stay address bits
+    // of the root and are gathered into Julia order by reduce_root_open.
+    L.root_modes.assign(R.modes.size(), Lowered::RootMode{1, 0, 0});
+    for (size_t m = 0; m < R.modes.size(); ++m) {
+        // a sliced mode that stays open would make the slices different ELEMENTS of the result, not terms of a sum
+        if (R.modes[m].var >= 0)
+            throw Error(QXB_ERR_UNSUPP, "mode " + std::to_string(m + 1) + " of the saved tensor is sliced (" +
+                                        p.vars[R.modes[m].var].sym + "): open indices cannot be slice bonds");
+        L.root_modes[m].ext = R.modes[m].ext;
     }
+    for (const LayEntry& e : L.tensors[L.root].lay) {
+        if (e.key >= 0) {
+            if (e.key >= (int)R.modes.size()) throw Error(QXB_ERR_STATE, "root layout names a mode the saved tensor does not have");
+            L.root_modes[e.key].nbits = e.nbits;
+            L.root_modes[e.key].pos = e.pos;
+        } else {
+            L.root_vars.push_back(~e.key);
+        }
+    }
+    L.root_elems = 1;
+    for (const auto& rm : L.root_modes) {
+        if (rm.ext > (int64_t(1) << rm.nbits)) throw Error(QXB_ERR_STATE, "root mode wider than its address bits");
+        L.root_elems *= rm.ext;
+    }
+    if (L.root_modes.size() > 32) throw Error(QXB_ERR_UNSUPP, "the saved tensor has more than 32 modes");
     L.root_scale = 1.0;
     for (int v = 0; v < k; ++v)
         if (is_free(v) && !R.vars.count(v)) L.root_scale *= (double)p.vars[v].dim;
@@ -569,6 +591,9 @@ std::string describe_json(const Program& p, const Lowered& L) {
       << ",\"slice_vars\":[";
     for (size_t i = 0; i < p.vars.size(); ++i)
         o << (i ? "," : "") << "{\"sym\":\"" << p.vars[i].sym << "\",\"dim\":" << p.vars[i].dim << "}";
+    o << "],\"root_modes\":[";
+    for (size_t i = 0; i < L.root_modes.size(); ++i)
+        o << (i ? "," : "") << "[" << L.root_modes[i].ext << "," << L.root_modes[i].nbits << "," << L.root_modes[i].pos << "]";
     o << "],\"root_scale\":" << L.root_scale << ",\"root\":" << L.root << ",\"arena_elems\":{\"const\":" << L.const_elems
       << ",\"block\":" << L.block_elems << ",\"chunk_per_amp\":" << L.chunk_elems_per_amp << "},\"tensors\":[";
     static const char* ph[] = {"const", "block", "chunk"};

@@ -97,6 +97,9 @@ def execute(dsl_file: str, input_file: Optional[str] = None, param_file: Optiona
     bitstrings = _bitstrings_from_params(params, max_amplitudes)
     n_model = len(bitstrings) if bitstrings is not None else 1024
     g = Graph.from_dsl(text, data, dtype, replan=replan, replan_n_amp=max(1, n_model)).compile()
+    if g.root_dims:
+        raise ValueError("the program saves a tensor (open network); execute() writes one amplitude per bitstring -- "
+                         "use Graph.amplitudes / contract_tn for open networks")
     t["Create Context"] = time.perf_counter() - t0
 
     t0 = time.perf_counter()

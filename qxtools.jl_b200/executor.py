@@ -117,6 +117,25 @@ class Graph:
         return n.value
 
     @property
+    def root_dims(self) -> List[int]:
+        """Shape of the saved tensor in Julia order: ``[]`` for a closed network (qxb_graph_root_dims)."""
+        r = C.c_int()
+        check(self._lib.qxb_graph_root_dims(self._h, C.byref(r), None))
+        d = (C.c_int64 * max(r.value, 1))()
+        check(self._lib.qxb_graph_root_dims(self._h, C.byref(r), d))
+        return list(d[:r.value])
+
+    def _out_buffer(self, n: int):
+        """(flat buffer for the library, view to hand back): ``[n]`` amplitudes for a closed network, ``[n, *root_dims]``
+        (each tensor column-major, as Julia holds it) for an open one."""
+        dims = self.root_dims
+        per = int(np.prod(dims, dtype=np.int64)) if dims else 1
+        flat = np.zeros(n * per, dtype=self.np_dtype)
+        if not dims:
+            return flat, flat
+        return flat, flat.reshape([n] + dims[::-1]).transpose([0] + list(range(len(dims), 0, -1)))
+
+    @property
     def slice_dims(self) -> List[int]:
         k = C.c_int()
         check(self._lib.qxb_graph_num_slice_vars(self._h, C.byref(k), None))
@@ -242,10 +261,10 @@ class Graph:
         n = bits.shape[0]
         if slice_end is None:
             slice_end = self.n_slices
-        out = np.zeros(n, dtype=self.np_dtype)
+        out, view = self._out_buffer(n)
         check(self._lib.qxb_amplitudes(self._h, bits.ctypes.data_as(C.c_void_p), n, slice_begin, slice_end,
                                        out.ctypes.data_as(C.c_void_p)))
-        return out
+        return view
 
     def amplitudes_device(self, d_bits_ptr: int, n_amp: int, d_out_ptr: int, slice_begin: int = 0,
                           slice_end: Optional[int] = None) -> None:
@@ -261,12 +280,12 @@ class Graph:
         else:
             bits = np.ascontiguousarray(bits_from_strings(list(bitstrings), self.n_outputs))
         n = bits.shape[0]
-        out = np.zeros(n, dtype=self.np_dtype)
+        out, view = self._out_buffer(n)
         fv = (C.c_int32 * max(len(fixed_vars), 1))(*fixed_vars)
         fx = (C.c_int64 * max(len(fixed_vals), 1))(*fixed_vals)
         check(self._lib.qxb_amplitudes_subspace(self._h, bits.ctypes.data_as(C.c_void_p), n, fv, fx, len(fixed_vars),
                                                 out.ctypes.data_as(C.c_void_p), 0))
-        return out
+        return view
 
     def amplitudes_subspace_device(self, d_bits_ptr: int, n_amp: int, d_out_ptr: int, fixed_vars, fixed_vals) -> None:
         fv = (C.c_int32 * max(len(fixed_vars), 1))(*fixed_vars)
@@ -295,6 +314,42 @@ def set_stream(stream_ptr: int) -> None:
 
 def synchronize() -> None:
     check(_lib.load().qxb_device_synchronize())
+
+
+def expand_open_indices(reduced: np.ndarray, root_indices: Sequence[int], wires: Sequence[int]) -> np.ndarray:
+    """Saved tensor (one mode per distinct index id, hyper-edges merged) -> the full tensor over the open ``wires``:
+    wires that share an id are forced equal (the diagonal structure the reference keeps implicit in its hyper-index
+    groups and QXTns materialises in the result of ``contract_tn!``).  Pure index bookkeeping on the host."""
+    reduced = np.asarray(reduced)
+    if not wires:
+        return reduced
+    mode = {ix: m for m, ix in enumerate(root_indices)}
+    missing = [w for w in wires if w not in mode]
+    if missing:
+        raise ValueError(f"open wires {missing} are not modes of the saved tensor")
+    full = np.zeros([reduced.shape[mode[w]] for w in wires], dtype=reduced.dtype)
+    idx = np.indices(reduced.shape)
+    full[tuple(idx[mode[w]] for w in wires)] = reduced
+    return full
+
+
+def contract_tn(tnc, plan, dtype: str = "c64") -> np.ndarray:
+    """``QXTns.contract_tn!(tnc, plan)`` (call sites /root/reference/src/simulation.jl:89 and
+    /root/reference/test/test_contraction_planning.jl:58,111,126,142,158): contract the whole network along ``plan`` and
+    return the data of the remaining tensor -- a 1-element array for a closed network; for a network built with
+    ``no_output=True`` the tensor over the open output wires, qubit k on axis k (``out.reshape(-1, order="F")`` is the
+    reference's ``reshape(output, prod(size(output)))``), followed by the open input wires when ``no_input=True``.
+    The contraction itself runs on the GPU (tensor-valued ``save``, ``qxb_graph_root_dims``); the caller's network is
+    not modified."""
+    from .compute_graph import build_compute_graph
+    cg = build_compute_graph(tnc, plan)
+    g = Graph.from_compute_graph(cg, dtype).compile()
+    out = g.amplitudes(["0" * g.n_outputs])          # output tensors, if the network has any, are the |0> projectors
+    if not g.root_dims:
+        return np.asarray(out[:1])
+    open_ids = set(cg.root_indices)
+    wires = [w for w in tnc.wire if w in open_ids] + [w for w in tnc.wire_first if w in open_ids and w not in tnc.wire]
+    return expand_open_indices(out[0], cg.root_indices, wires)
 
 
 def amplitudes_for_network(tnc, plan, bitstrings: Sequence[str], dtype: str = "c64") -> np.ndarray:

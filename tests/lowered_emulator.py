@@ -130,6 +130,25 @@ def run_block(desc, data, bits, fixed_vals, dtype=np.complex128, shuffle_seed=No
                 Cb[c0 + u * sUC + c] = acc
     R = T[desc["root"]]
     buf, base, sU = locate(R)
+    modes = desc.get("root_modes", [])
+    if any(nbits > 0 for _ext, nbits, _pos in modes):
+        # tensor-valued root (reduce_root_open_kernel): output index over the true extents in Julia order, the
+        # remaining address bits (batched slice variables still open in the root) are summed
+        elems = int(np.prod([m[0] for m in modes], dtype=np.int64))
+        o = np.arange(elems, dtype=np.int64)
+        addr, rest, mode_mask = np.zeros_like(o), o.copy(), 0
+        for ext, nbits, pos in modes:
+            addr |= (rest % ext) << pos
+            rest //= ext
+            mode_mask |= ((1 << nbits) - 1) << pos
+        vbits = [b for b in range(R["span_bits"]) if not (mode_mask >> b) & 1]
+        out = np.zeros((n, elems), dtype=np.complex128)
+        for u in range(n):
+            row = buf[base + u * sU: base + u * sU + (1 << R["span_bits"])].astype(np.complex128)
+            for v in range(1 << len(vbits)):
+                va = sum(((v >> i) & 1) << b for i, b in enumerate(vbits))
+                out[u] += row[addr | va]
+        return desc["root_scale"] * out
     out = np.zeros(n, dtype=np.complex128)
     for u in range(n):
         out[u] = desc["root_scale"] * np.sum(buf[base + u * sU: base + u * sU + (1 << R["span_bits"])].astype(np.complex128))
@@ -141,12 +160,15 @@ def amplitudes(graph, data, bits, slice_begin=0, slice_end=None, dtype=np.comple
     dims = graph.slice_dims
     if slice_end is None:
         slice_end = graph.n_slices
-    total = np.zeros(bits.shape[0], dtype=np.complex128)
+    total = None
     cache = {}
     for n_free, vals in decompose(dims, slice_begin, slice_end):
         if n_free not in cache:
             cache[n_free] = graph.describe(n_free)
-        total += run_block(cache[n_free], data, bits, vals, dtype, shuffle_seed)
+        part = run_block(cache[n_free], data, bits, vals, dtype, shuffle_seed)
+        total = part if total is None else total + part
+    if total is None:
+        total = np.zeros(bits.shape[0], dtype=np.complex128)
     return total.astype(dtype)
 
 

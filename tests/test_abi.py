@@ -69,12 +69,21 @@ def test_malformed_programs(lib_built, bad, code):
     assert len(g._lib.qxb_last_error()) > 0
 
 
-def test_non_scalar_root_rejected(lib_built):
-    g = Graph.from_dsl("# version: 0.4.0\nload a d 2,2\nload b d 2,2\nncon c 1,3 a 1,2 b 2,3\nsave output c\n",
+def test_tensor_valued_root(lib_built):
+    """A non-scalar ``save`` (open network) is accepted: its shape is reported in Julia order and its modes are
+    located in the lowered root; slicing one of its modes is refused (tests/test_open_network.py has the values)."""
+    g = Graph.from_dsl("# version: 0.4.0\nload a d 2,2\nload b e 2,3\nncon c 1,3 a 1,2 b 2,3\nsave output c\n",
+                       {"d": np.eye(2), "e": np.ones((2, 3))})
+    assert g.root_dims == [2, 3] and g.n_outputs == 0
+    d = g.describe()
+    assert [m[0] for m in d["root_modes"]] == [2, 3] and [m[1] for m in d["root_modes"]] == [1, 2]
+    assert Graph.from_dsl("# version: 0.4.0\nload a d 2\nload b d 2\nncon c 0 a 1 b 1\nsave output c\n",
+                          {"d": np.ones(2)}).root_dims == []
+    g = Graph.from_dsl("# version: 0.4.0\nload a d 2,2\nview a_s a v1 1 2\nload b d 2,2\nncon c 1,3 a_s 1,2 b 2,3\nsave output c\n",
                        {"d": np.eye(2)})
     with pytest.raises(QxbError) as e:
         g.describe()
-    assert e.value.code == -4
+    assert e.value.code == -4 and "open indices cannot be slice bonds" in str(e.value)
 
 
 def test_compute_fails_loudly_without_gpu(lib_built):

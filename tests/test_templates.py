@@ -90,3 +90,23 @@ def test_min_lob_gives_small_nodes_a_register_tile(lib_built, monkeypatch):
     more = [n for n in base if tiled[n][7] > base[n][7]]
     assert fewer and not more
     assert all(tiled[n][3] >= 5 or tiled[n][1] < 5 + tiled[n][4] + tiled[n][5] for n in tiled)
+
+
+@pytest.mark.parametrize("min_lob", [None, "6"])
+@pytest.mark.parametrize("workload,replan", [("rqc_6x6_d16_c32_s64", 0), ("rqc_7x7_d20_c64_s4096", 16)])
+def test_templates_of_bench_workloads(lib_built, monkeypatch, workload, replan, min_lob):
+    """The committed benchmark triples have the nodes with > 2^8 elements per bitstring, i.e. the 2^ma x 2^nb
+    register tiles and multi-chunk K walks of the default split (the headline step's dominant contractions)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    if min_lob is None:
+        monkeypatch.delenv("QXB_MIN_LOB", raising=False)
+    else:
+        monkeypatch.setenv("QXB_MIN_LOB", min_lob)
+    txt, data, w = bench.build_workload(workload)
+    g = Graph.from_dsl(txt, data, w["dtype"], replan=replan, replan_n_amp=32768)
+    stats = check_graph(g)
+    tiles = {(s[4], s[5]) for s in stats}
+    assert len(tiles) >= 4 and any(m and n for m, n in tiles)
+    assert any(s[6] < s[2] for s in stats)                   # K walked in more than one register chunk somewhere
