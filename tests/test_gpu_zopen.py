@@ -64,7 +64,7 @@ def test_sliced_open_network(gpu):
         assert np.max(np.abs(total - ref)) < 1e-12
 
 
-@pytest.mark.parametrize("dtype,tol", [("c64", 1e-10), ("c32", 2e-5)])
+@pytest.mark.parametrize("dtype,tol", [("c64", 1e-10), ("c32", 2e-4)])      # as tests/test_fuzz.py: cancellations
 def test_random_programs_with_open_root(gpu, dtype, tol):
     """Tensor-valued save on random programs: padded (extent-3) modes, hyper-indices, slice variables still open in the
     root, several bitstrings per call."""
