@@ -127,5 +127,5 @@ def load():
 
 def check(rc):
     if rc < 0:
-        raise QxbError(rc, load().qxb_last_error().decode())
+        raise QxbError(rc, load().qxb_last_error().decode("utf-8", "replace"))
     return rc

@@ -168,6 +168,6 @@ std::string program_text(const Program& p);
 void plan_memory(Lowered& L);
 std::string describe_json(const Program& p, const Lowered& L);
 
-inline int ceil_log2(int64_t x) { int b = 0; while ((int64_t(1) << b) < x) ++b; return b; }
+inline int ceil_log2(int64_t x) { int b = 0; while (b < 62 && (int64_t(1) << b) < x) ++b; return b; }
 
 }  // namespace qxb

@@ -195,11 +195,14 @@ struct Reader {
         uint32_t bits = (uint32_t)rd(q + 1, 3);
         t.size = (int)rd(q + 4, 4);
         if ((cls == 0 || cls == 1) && (bits & 1)) unsupp(f.path, "big-endian numeric data");
-        if (cls == 0) { t.kind = EK_INT; t.is_signed = (bits & 8) != 0; t.len = 12; }
+        if (cls == 0) {
+            t.kind = (t.size == 1 || t.size == 2 || t.size == 4 || t.size == 8) ? EK_INT : EK_OTHER;
+            t.is_signed = (bits & 8) != 0; t.len = 12;
+        }
         else if (cls == 1) {
             t.len = 20;
             t.kind = t.size == 8 ? EK_F64 : t.size == 4 ? EK_F32 : EK_OTHER;
-        } else if (cls == 3) { t.kind = EK_STRING; t.len = 8; }
+        } else if (cls == 3) { t.kind = t.size > 0 ? EK_STRING : EK_OTHER; t.len = 8; }
         else if (cls == 7) { t.len = 8; }
         else if (cls == 6) {
             int nmemb = bits & 0xffff;
@@ -258,6 +261,7 @@ struct Reader {
         int sver = (int)rd(sp->off, 1), rank = (int)rd(sp->off + 1, 1);
         uint64_t dp = sp->off + (sver == 1 ? 8 : 4);
         bool null_space = sver >= 2 && rd(sp->off + 3, 1) == 2;
+        if (rank > 32) bad(f.path, sp->off, "dataset '" + name + "': rank above 32");
         std::vector<int64_t> h5dims(rank);
         for (int i = 0; i < rank; ++i) h5dims[i] = (int64_t)rd(dp + (uint64_t)i * sl, sl);
         d.dims.assign(h5dims.rbegin(), h5dims.rend());
@@ -266,7 +270,15 @@ struct Reader {
         DType t = resolve_datatype(*dt, d.committed_type);
         d.kind = t.kind; d.elem_size = t.size; d.is_signed = t.is_signed;
         if (d.kind == EK_OTHER) { f.datasets.push_back(d); return; }
-        uint64_t nbytes = (uint64_t)d.count() * (uint64_t)d.elem_size;
+        // extents come from the file: bound them by what the file can hold before any size arithmetic
+        uint64_t count = 1;
+        for (int64_t e : d.dims) {
+            if (e < 0 || (uint64_t)e > buf.size() || (e > 0 && count > buf.size() / (uint64_t)e + 1)) bad(f.path, sp->off, "dataset '" + name + "': extents exceed the file size");
+            count *= (uint64_t)e;
+        }
+        if (d.elem_size <= 0 || count > buf.size() / (uint64_t)d.elem_size + 1)
+            bad(f.path, sp->off, "dataset '" + name + "': extents exceed the file size");
+        uint64_t nbytes = count * (uint64_t)d.elem_size;
         // layout
         int lver = (int)rd(lay->off, 1);
         int cls;

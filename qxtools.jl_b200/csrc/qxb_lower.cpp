@@ -25,6 +25,11 @@
 
 namespace qxb {
 
+// sanity bounds on what a program may declare (a mode of 2^30 entries is already beyond any leaf or bond; without them
+// a corrupt extent reaches the bit arithmetic: found by tests/test_fuzz_inputs.py)
+static const int64_t kMaxExtent = int64_t(1) << 30;
+static const int64_t kMaxOutputs = 65536;
+
 // ---------------------------------------------------------------------- parse
 static std::vector<int64_t> parse_list(const std::string& tok, bool labels) {
     std::vector<int64_t> out;
@@ -120,7 +125,7 @@ void analyse(Program& p) {
         if (c.kind != CMD_VIEW) continue;
         int num = var_number(c.label);
         if (num < 0) throw Error(QXB_ERR_ARG, "slice symbol '" + c.label + "' is not of the form v<N>");
-        if (c.dim < 1) throw Error(QXB_ERR_ARG, "view " + c.name + ": bad bond dimension");
+        if (c.dim < 1 || c.dim > kMaxExtent) throw Error(QXB_ERR_ARG, "view " + c.name + ": bad bond dimension");
         auto it = found.find(num);
         if (it == found.end()) found[num] = {c.label, c.dim};
         else if (it->second.second != c.dim)
@@ -145,7 +150,7 @@ void analyse(Program& p) {
         case CMD_LOAD: {
             TensorDef d; d.kind = T_LOAD; d.name = c.name; d.data_label = c.label;
             for (int64_t e : c.dims) {
-                if (e < 1) throw Error(QXB_ERR_ARG, "load " + c.name + ": bad dimension");
+                if (e < 1 || e > kMaxExtent) throw Error(QXB_ERR_ARG, "load " + c.name + ": bad dimension");
                 d.modes.push_back(Mode{e, e, ceil_log2(e), -1});
             }
             d.leaf = (int)p.defs.size();
@@ -153,8 +158,8 @@ void analyse(Program& p) {
             break;
         }
         case CMD_OUTPUT: {
-            if (c.idx < 1) throw Error(QXB_ERR_ARG, "output " + c.name + ": index is 1-based");
-            if (c.dim < 2) throw Error(QXB_ERR_ARG, "output " + c.name + ": dimension must be >= 2");
+            if (c.idx < 1 || c.idx > kMaxOutputs) throw Error(QXB_ERR_ARG, "output " + c.name + ": index is 1-based (and at most 65536)");
+            if (c.dim < 2 || c.dim > kMaxExtent) throw Error(QXB_ERR_ARG, "output " + c.name + ": dimension must be >= 2");
             TensorDef d; d.kind = T_OUTPUT; d.name = c.name; d.out_idx = c.idx; d.amp = true;
             d.modes.push_back(Mode{c.dim, c.dim, ceil_log2(c.dim), -1});
             d.leaf = (int)p.defs.size();

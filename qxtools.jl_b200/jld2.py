@@ -40,7 +40,7 @@ def load_jld2(path: str, as_c64: bool = False, info: dict | None = None) -> "Ord
             dims = (C.c_int64 * 32)()
             check(lib.qxb_jld2_info(h, i, C.byref(name), C.byref(kind), C.byref(esize), C.byref(rank), dims))
             shape = tuple(dims[k] for k in range(rank.value))
-            key = name.value.decode()
+            key = name.value.decode("utf-8", "replace")
             if kind.value == OTHER:
                 skipped.append(key)
                 continue
