@@ -224,6 +224,11 @@ TreeCostModel cost_model_for(double elem_bytes) {
     cm.elem_bytes = elem_bytes;
     cm.bandwidth = 6.0e12;                                  // streaming kernels: 93 % of 6.45 TB/s (profiles/r1_summary.md)
     cm.flop_rate = elem_bytes <= 8 ? 40e12 : 27e12;         // GEMM kernels: c32 SIMT / 3xTF32 ~40, c64 DMMA 27 TFLOP/s
+    cm.gemm_min_k_bits = elem_bytes <= 8 ? 4 : 3;           // gemm_kcb(): K chunk of the tensor-core kernels
+    if (const char* e = getenv("QXB_MIN_LOB")) cm.thread_bits = std::min(8, std::max(5, atoi(e)));
+    // A/B knobs: QXB_PLAN_L1_BW (TB/s; 0 = the single-rate model of profiles/r1p), QXB_PLAN_FLOP_RATE (TFLOP/s)
+    if (const char* e = getenv("QXB_PLAN_FLOP_RATE")) if (atof(e) > 0) cm.flop_rate = atof(e) * 1e12;
+    if (const char* e = getenv("QXB_PLAN_L1_BW")) cm.l1_bandwidth = atof(e) * 1e12;
     cm.shared_reread = getenv("QXB_PLAN_SHARED_REREAD") && atoi(getenv("QXB_PLAN_SHARED_REREAD")) != 0;   // experiment, off
     return cm;
 }
@@ -237,7 +242,9 @@ double lowered_cost_seconds(const Lowered& L, double n_amp, const TreeCostModel&
         const double bytes = cm.elem_bytes * (op.elems_a * ((L.tensors[op.a].amp || rr) ? n_amp : 1) +
                                               op.elems_b * ((L.tensors[op.b].amp || rr) ? n_amp : 1) + op.elems_c * u);
         const double flops = 8.0 * op.macs_per_amp * u;
-        t += (op.phase == PH_CONST ? cm.const_weight : 1.0) * (std::max(bytes / cm.bandwidth, flops / cm.flop_rate) + cm.launch_s);
+        (void)flops;
+        const double compute = cm.compute_seconds(std::log2(std::max(1.0, op.macs_per_amp * u)), op.nC, op.n_m, op.n_n, op.nK);
+        t += (op.phase == PH_CONST ? cm.const_weight : 1.0) * (std::max(bytes / cm.bandwidth, compute) + cm.launch_s);
     }
     return t;
 }

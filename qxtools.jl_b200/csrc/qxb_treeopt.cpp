@@ -82,7 +82,7 @@ struct Tree {
         const double ab = net->amp >= 0 ? net->wbits[net->amp] : 0.0;
         const double ea = (cm->shared_reread && c.amp && !a.amp) ? a.bits + ab : a.bits;
         const double eb = (cm->shared_reread && c.amp && !b.amp) ? b.bits + ab : b.bits;
-        return w * cm->time(ea, eb, c.bits, union_bits);
+        return w * cm->time(ea, eb, c.bits, union_bits, a.amp ? ab : 0.0, b.amp ? ab : 0.0);
     }
     void recompute(int v) {
         TNode& c = n[v];
@@ -423,7 +423,7 @@ bool reconfigure_at(Tree& T, int top, int L, std::mt19937_64* rng) {
                 const double ub = wsum(u) + (ua ? amp_bits : 0.0);
                 const double e1 = (T.cm->shared_reread && s_amp[S] && !s_amp[S1]) ? s_bits[S1] + amp_bits : s_bits[S1];
                 const double e2 = (T.cm->shared_reread && s_amp[S] && !s_amp[S2]) ? s_bits[S2] + amp_bits : s_bits[S2];
-                c += ((s_amp[S] || s_var[S]) ? 1.0 : T.cm->const_weight) * T.cm->time(e1, e2, s_bits[S], ub);
+                c += ((s_amp[S] || s_var[S]) ? 1.0 : T.cm->const_weight) * T.cm->time(e1, e2, s_bits[S], ub, s_amp[S1] ? amp_bits : 0.0, s_amp[S2] ? amp_bits : 0.0);
             }
             if (bc < 0 || c < bc) { bc = c; bs = S1; }
         }
@@ -452,10 +452,28 @@ bool reconfigure_at(Tree& T, int top, int L, std::mt19937_64* rng) {
 
 }  // namespace
 
-double TreeCostModel::time(double a_bits, double b_bits, double c_bits, double union_bits) const {
+double TreeCostModel::compute_seconds(double macs_bits, double c_bits, double m_bits, double n_bits, double k_bits) const {
+    const double macs = std::exp2(macs_bits);
+    if (l1_bandwidth <= 0 || (m_bits >= gemm_min_mn_bits && n_bits >= gemm_min_mn_bits && k_bits >= gemm_min_k_bits))
+        return 8.0 * macs / flop_rate;
+    // register tile as build_templates picks it: up to 2 M-only and 2 N-only bits, thread_bits of C stay thread bits
+    int tm = (int)std::min(2.0, std::floor(m_bits + 1e-9)), tn = (int)std::min(2.0, std::floor(n_bits + 1e-9));
+    const int room = std::max(0, (int)std::floor(c_bits + 1e-9) - thread_bits);
+    while (tm + tn > room) { if (tn >= tm && tn > 0) --tn; else --tm; }
+    const double loads_per_mac = (double)((1 << tm) + (1 << tn)) / (double)(1 << (tm + tn));
+    return macs * loads_per_mac * elem_bytes / l1_bandwidth;
+}
+
+double TreeCostModel::time(double a_bits, double b_bits, double c_bits, double union_bits, double a_amp_bits, double b_amp_bits) const {
     const double bytes = elem_bytes * (std::exp2(a_bits) + std::exp2(b_bits) + std::exp2(c_bits));
-    const double flops = 8.0 * std::exp2(union_bits);
-    return std::max(bytes / bandwidth, flops / flop_rate) + launch_s;
+    // a = batch + M + K, b = batch + N + K, c = batch + M + N, union = batch + M + N + K; the bitstring axis is a batch
+    // axis when both operands carry it and otherwise rides with the operand that does -- it is never a tile axis, so
+    // it is taken out of the per-row M / N / C bit counts
+    const double c_amp = std::max(a_amp_bits, b_amp_bits);
+    const double m_bits = (union_bits - b_bits) - (a_amp_bits > 0 && b_amp_bits == 0 ? a_amp_bits : 0.0);
+    const double n_bits = (union_bits - a_bits) - (b_amp_bits > 0 && a_amp_bits == 0 ? b_amp_bits : 0.0);
+    const double compute = compute_seconds(union_bits, c_bits - c_amp, m_bits, n_bits, union_bits - c_bits);
+    return std::max(bytes / bandwidth, compute) + launch_s;
 }
 
 static void tree_to_plan(const Tree& T, std::vector<std::pair<int, int>>& plan, int& root) {

@@ -21,12 +21,24 @@ struct TreeNet {
 struct TreeCostModel {
     double elem_bytes = 16;                     // 8 for ComplexF32
     double bandwidth = 6.0e12;                  // B/s the streaming kernels reach on B200 (93 % of the measured peak)
-    double flop_rate = 27e12;                   // flop/s of the GEMM kernels (c64 DMMA 27e12, c32 ~40e12)
+    double flop_rate = 27e12;                   // flop/s of the tensor-core GEMM kernels on GEMM-shaped nodes (c64 DMMA 27e12, c32 ~40e12)
+    // Every other node runs on the register-tiled SIMT kernel, which is bound by operand loads through L1:
+    // (2^tm + 2^tn) / 2^(tm + tn) loads per complex MAC for a 2^tm x 2^tn register tile, at l1_bandwidth bytes/s --
+    // 19.9 TB/s is the median over the L1-bound nodes of the tree-searched 7x7 plan (profiles/r1p_ops.md, fitted by
+    // scripts/model_min_lob.py).  With one rate for all nodes (l1_bandwidth = 0: flops / flop_rate, the r1p model) the
+    // search bought a few per cent of bytes with long-K untiled nodes that ran at a tenth of the HBM peak.
+    double l1_bandwidth = 19.9e12;
+    int gemm_min_mn_bits = 6, gemm_min_k_bits = 3;   // shape the tensor-core kernels take (qxb_exec.cu: build_templates)
+    int thread_bits = 8;                        // C bits per bitstring row that stay thread bits (QXB_MIN_LOB)
+    // compute seconds of a node with 2^macs_bits complex MACs whose C has c_bits bits per bitstring row, of which
+    // m_bits come from A only and n_bits from B only; k_bits summed
+    double compute_seconds(double macs_bits, double c_bits, double m_bits, double n_bits, double k_bits) const;
     double launch_s = 0.0;
     bool shared_reread = false;                 // charge an operand shared by all bitstrings once per bitstring row (experiment)
     int bisection_restarts = 0;                 // > 0: also seed the pool with recursive-bisection trees (Fiduccia-Mattheyses)
     double const_weight = 1.0;                  // share of a constant-folded node's cost that counts (1 = as if run once per step)
-    double time(double a_bits, double b_bits, double c_bits, double union_bits) const;
+    // amp_bits: log2 of the bitstring batch when the operand / result carries that axis, else 0
+    double time(double a_bits, double b_bits, double c_bits, double union_bits, double a_amp_bits = 0, double b_amp_bits = 0) const;
 };
 
 struct TreeReport { double seconds = 0, flops = 0, bytes = 0, max_bits = 0; };
