@@ -445,16 +445,24 @@ def roofline(args, txt, data, w, bits_d, out_d, n_amp, s0, s1, assign=None, bits
     achieved = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
     # DRAM bytes per launch of the dominant kernels from the committed ncu --set full capture
     # (taken at 1024 bitstrings per step; the traffic of these launches is linear in the batch)
-    traffic = None
+    traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         t = json.load(open(tpath)).get(args.workload)
         if t:
-            traffic = t["bytes_per_launch_mean_dominant"] * n_amp / float(t["at_amps"])
+            # the capture belongs to ONE plan: use it only while the dominant launches still move the bytes it saw
+            # (the planner's time model changed after the r1p capture, so the tree -- and its dominant ops -- did too)
+            per_launch = t["bytes_per_launch_mean_dominant"] * n_amp / float(t["at_amps"])
+            alg = by / max(launches, 1)
+            if alg > 0 and abs(per_launch - alg) / alg < 0.10:
+                traffic = per_launch
+            else:
+                traffic_note = (f"no ncu capture of this plan yet: the committed one ({t['source']}) saw {per_launch / 1e9:.2f} GB per "
+                                f"dominant launch, this step moves {alg / 1e9:.2f} GB algorithmic")
     all_ms = sum(o["ms"] for o in ops)
     return {"bound": "hbm", "kernel": "contract_kernel (dominant contractions: top ops by FLOPs covering >=80%)",
             "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s",
-            "frac": achieved / peak if peak else None, "traffic": traffic,
+            "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_note": traffic_note,
             "bytes_per_launch": by / max(launches, 1), "ms_per_launch": ms / max(launches, 1),
             "dominant_ops": len(dom), "dominant_ms": ms, "all_contract_ms": all_ms,
             "dominant_gflops": fl / (ms * 1e-3) / 1e9 if ms > 0 else 0.0,

@@ -19,6 +19,7 @@ from qxb200.executor import Graph   # noqa: E402
 from template_emulator import templates   # noqa: E402
 
 N_AMP = 131072
+os.environ["QXB_PLAN_L1_BW"] = "0"     # the plan that was MEASURED (r1p): single-rate planner model; see scripts/model_plan_rate.py
 ES = 16
 BW_HBM = 6.0e12               # what the streaming nodes reach (93 % of the measured 6.55 TB/s copy rate)
 
