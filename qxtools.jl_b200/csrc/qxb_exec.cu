@@ -425,6 +425,7 @@ Node contract_node(const RunCtx& c, int i) {
     const long long blocks = (p.tiles + (1ll << sub_bits) - 1) >> sub_bits;
     const long long cap = (long long)g_num_sms * 8;
     Node n;
+    int tma_stages = 0;                    // > 0: the node runs contract_tma_kernel (second kernel argument)
     const double outputs = (double)p.U * std::ldexp(1.0, p.nC);
     if (!g->opts.no_gemm && c.v->gemm_tmb[i] > 0 && outputs >= 65536.0) {
         // GEMM-shaped node: shared-memory-tiled FMA GEMM
@@ -498,7 +499,32 @@ Node contract_node(const RunCtx& c, int i) {
             A.lay.size() && B.lay.size() && op.elems_c >= (one_shared ? 0.25 * amp_elems : smem_ratio * (op.elems_a + op.elems_b)) &&
             op.elems_a == std::ldexp(1.0, A.span_bits) && op.elems_b == std::ldexp(1.0, B.span_bits) && p.U >= g_num_sms)
             sf = contract_smem_func(g->dtype, p.kc, p.ma, p.nb, p.kc == p.nK);
-        if (sf) {
+        // EXPERIMENT QXB_SMEM_TMA=1 (never run on hardware yet, see contract_tma_kernel): operand rows through 1-D TMA
+        // bulk copies into a ring of stages; QXB_SMEM_TMA_RATIO = minimum |C| / (|A| + |B|)
+        const int smem_tma = [] { const char* e = getenv("QXB_SMEM_TMA"); return e ? atoi(e) : 0; }();
+        const void* tf = nullptr;
+        if (smem_tma && !g->opts.no_smem_stage && p.lob == 8 && p.ma + p.nb >= 1 && A.lay.size() && B.lay.size() &&
+            (A.amp || B.amp) && p.U >= g_num_sms &&
+            op.elems_a == std::ldexp(1.0, A.span_bits) && op.elems_b == std::ldexp(1.0, B.span_bits)) {
+            const double tma_ratio = [] { const char* e = getenv("QXB_SMEM_TMA_RATIO"); return e ? atof(e) : 0.3; }();
+            const size_t bytes_a = (size_t(1) << A.span_bits) * g->es(), bytes_b = (size_t(1) << B.span_bits) * g->es();
+            const bool aligned = bytes_a % 16 == 0 && bytes_b % 16 == 0 && (uintptr_t)p.A % 16 == 0 && (uintptr_t)p.B % 16 == 0;
+            const int fit = (int)std::min<size_t>(4, (200 * 1024 - 64) / stage);
+            if (aligned && fit >= 2 && op.elems_c >= tma_ratio * (op.elems_a + op.elems_b))
+                tf = contract_tma_func(g->dtype, p.kc, p.ma, p.nb, p.kc == p.nK);
+            if (tf) tma_stages = fit;
+        }
+        if (tf) {
+            p.aBits = A.span_bits; p.bBits = B.span_bits;
+            n.func = tf;
+            n.smem = stage * (size_t)tma_stages + 64;
+            n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(p.U, (long long)g_num_sms)));
+            static std::set<const void*> tma_configured;
+            if (!tma_configured.count(tf)) {
+                CUDA_OK(cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                tma_configured.insert(tf);
+            }
+        } else if (sf) {
             p.aBits = A.span_bits; p.bBits = B.span_bits;
             n.func = sf;
             n.smem = stage;
@@ -517,6 +543,7 @@ Node contract_node(const RunCtx& c, int i) {
     }
     n.block = dim3(kThreads);
     n.arg(p);      // p is final here (aBits/bBits set above)
+    if (tma_stages) n.arg(tma_stages);
     n.variant = c.variant_key; n.op = i;
     const double u = (double)p.U;
     n.flops = 8.0 * op.macs_per_amp * u;

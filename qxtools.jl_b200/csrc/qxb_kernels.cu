@@ -168,6 +168,133 @@ contract_smem_kernel(const __grid_constant__ OpParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Same node shape as contract_smem_kernel, but the operand rows arrive through the TMA engine:
+// one thread issues 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx) of A[u] and B[u]
+// into a ring of shared-memory stages, several bitstring rows ahead of the row being computed.
+// Why: the K = 8 - 32 nodes of the tree-searched plans run at 25 % occupancy with ~20 loads in
+// flight per thread -- about 5 - 10 KB in flight per SM where HBM needs ~35 KB (6.5 TB/s / 148 SMs
+// x ~800 ns); ncu: "no eligible warp" half of the cycles (profiles/r1p_summary.md).  Bulk copies
+// keep (stages - 1) x (|A[u]| + |B[u]|) bytes in flight per CTA without holding a register.
+// EXPERIMENT (QXB_SMEM_TMA=1): written without GPU access, never run; off by default.
+__device__ __forceinline__ unsigned tma_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_mbar_wait(unsigned bar, unsigned parity) {
+    for (unsigned spin = 0; spin < (1u << 27); ++spin) {
+        unsigned done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();                                  // a copy that never completes must fail the launch, not hang the GPU
+}
+
+constexpr int kTmaMaxStages = 4;
+
+template <typename R2, int KC, int MA, int NB, bool ONE>
+__global__ void __launch_bounds__(kThreads, 1)
+contract_tma_kernel(const __grid_constant__ OpParams p, const int stages) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const long long nA = 1ll << p.aBits, nB = 1ll << p.bBits;
+    const bool sharedA = p.sUA == 0, sharedB = p.sUB == 0;
+    // layout: [stage 0: A row | B row][stage 1] ... [mbarriers]; a shared operand lives once, in stage 0's slot
+    const long long stage_elems = nA + nB;
+    R2* ring = reinterpret_cast<R2*>(smem_raw);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + stage_elems * stages);
+    const R2* __restrict__ A = reinterpret_cast<const R2*>(p.A);
+    const R2* __restrict__ B = reinterpret_cast<const R2*>(p.B);
+    R2* __restrict__ C = reinterpret_cast<R2*>(p.C);
+    const int tid = threadIdx.x;
+    const unsigned lo = tid;
+    const long long aLo = segeval(p.sAlo, p.nsAlo, lo);
+    const long long bLo = segeval(p.sBlo, p.nsBlo, lo);
+    const long long cLo = segeval(p.sClo, p.nsClo, lo);
+    const long long tiles_u = 1ll << p.hb;
+    const unsigned row_bytes = (unsigned)(((sharedA ? 0 : nA) + (sharedB ? 0 : nB)) * (long long)sizeof(R2));
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tma_smem_u32(bars + s)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // operands shared by every bitstring row: plain loads, once per CTA
+    R2* shA = ring;                       // stage 0's A slot when A is shared
+    R2* shB = ring + nA;
+    if (sharedA) for (long long i = tid; i < nA; i += kThreads) shA[i] = __ldg(A + i);
+    if (sharedB) for (long long i = tid; i < nB; i += kThreads) shB[i] = __ldg(B + i);
+    __syncthreads();
+
+    // rows of this CTA: u_j = blockIdx.x + j * gridDim.x, j = 0 .. n_rows - 1; row j uses stage j % stages
+    const long long n_rows = p.U > (long long)blockIdx.x ? (p.U - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto issue = [&](long long j) {       // thread 0 only
+        const int s = (int)(j % stages);
+        const long long u = blockIdx.x + j * (long long)gridDim.x;
+        const unsigned bar = tma_smem_u32(bars + s);
+        R2* dstA = ring + (long long)s * stage_elems;
+        R2* dstB = dstA + nA;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(row_bytes), "r"(bar) : "memory");
+        if (!sharedA)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tma_smem_u32(dstA)), "l"(A + u * p.sUA), "r"((unsigned)(nA * sizeof(R2))), "r"(bar) : "memory");
+        if (!sharedB)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tma_smem_u32(dstB)), "l"(B + u * p.sUB), "r"((unsigned)(nB * sizeof(R2))), "r"(bar) : "memory");
+    };
+    if (tid == 0)
+        for (long long j = 0; j < n_rows && j < stages; ++j) issue(j);
+
+    for (long long j = 0; j < n_rows; ++j) {
+        const int s = (int)(j % stages);
+        const long long u = blockIdx.x + j * (long long)gridDim.x;
+        tma_mbar_wait(tma_smem_u32(bars + s), (unsigned)((j / stages) & 1));
+        const R2* rowA = sharedA ? shA : ring + (long long)s * stage_elems;
+        const R2* rowB = sharedB ? shB : ring + (long long)s * stage_elems + nA;
+        R2* Cu = C + u * p.sUC + cLo;
+        for (long long hh = 0; hh < tiles_u; ++hh) {
+            const R2* Ap = rowA + segeval(p.sAhi, p.nsAhi, (unsigned long long)hh) + aLo;
+            const R2* Bp = rowB + segeval(p.sBhi, p.nsBhi, (unsigned long long)hh) + bLo;
+            R2* Cp = Cu + segeval(p.sChi, p.nsChi, (unsigned long long)hh);
+            tile_compute<R2, KC, MA, NB, ONE, true>(Ap, Bp, Cp, p);
+        }
+        __syncthreads();                   // every thread is done reading stage s
+        if (tid == 0 && j + stages < n_rows) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before the async-proxy overwrite
+            issue(j + stages);
+        }
+    }
+}
+
+template <typename R2, int KC, int MA, int NB>
+static const void* pick_tma_one(bool one) {
+    return one ? (const void*)&contract_tma_kernel<R2, KC, MA, NB, true>
+               : (const void*)&contract_tma_kernel<R2, KC, MA, NB, false>;
+}
+template <typename R2, int KC>
+static const void* pick_tma_tile(int ma, int nb, bool one) {
+    if (ma == 1 && nb == 1) return pick_tma_one<R2, KC, 1, 1>(one);
+    if (ma == 1 && nb == 2) return pick_tma_one<R2, KC, 1, 2>(one);
+    if (ma == 2 && nb == 1) return pick_tma_one<R2, KC, 2, 1>(one);
+    if (ma == 2 && nb == 2) return pick_tma_one<R2, KC, 2, 2>(one);
+    if (ma == 0 && nb == 1) return pick_tma_one<R2, KC, 0, 1>(one);
+    if (ma == 0 && nb == 2) return pick_tma_one<R2, KC, 0, 2>(one);
+    if (ma == 1 && nb == 0) return pick_tma_one<R2, KC, 1, 0>(one);
+    if (ma == 2 && nb == 0) return pick_tma_one<R2, KC, 2, 0>(one);
+    return nullptr;
+}
+template <typename R2>
+static const void* pick_tma_kc(int kc, int ma, int nb, bool one) {
+    switch (kc) {
+    case 1: return pick_tma_tile<R2, 1>(ma, nb, one);
+    case 2: return pick_tma_tile<R2, 2>(ma, nb, one);
+    case 3: return pick_tma_tile<R2, 3>(ma, nb, one);
+    default: return nullptr;
+    }
+}
+// nullptr when there is no TMA-staged variant for this shape; second kernel argument = number of stages (2..4);
+// dynamic shared memory = stages * (2^aBits + 2^bBits) * sizeof(element) + 64
+const void* contract_tma_func(int dtype, int kc, int ma, int nb, bool single_chunk) {
+    return dtype == 0 ? pick_tma_kc<float2>(kc, ma, nb, single_chunk) : pick_tma_kc<double2>(kc, ma, nb, single_chunk);
+}
+
 template <typename R2, int KC, int MA, int NB>
 static const void* pick_smem_one(bool one) {
     return one ? (const void*)&contract_smem_kernel<R2, KC, MA, NB, true>

@@ -84,6 +84,9 @@ const void* contract_func(int dtype, int kc, int ma, int nb, bool single_chunk, 
 // shared-memory-staged variant for broadcast-type nodes (nullptr if the shape has none); dynamic
 // shared memory = (2^aBits + 2^bBits) * sizeof(element)
 const void* contract_smem_func(int dtype, int kc, int ma, int nb, bool single_chunk);
+// EXPERIMENT (QXB_SMEM_TMA=1): the same node shape with A[u], B[u] brought in by 1-D TMA bulk copies into a ring of
+// stages (nullptr if the shape has no instantiation); arguments (OpParams, int stages)
+const void* contract_tma_func(int dtype, int kc, int ma, int nb, bool single_chunk);
 // warp-per-output reduction variant for nC <= 8 and long K (same OpParams argument)
 const void* kreduce_func(int dtype);
 // block-per-output variant for very long K (>= 2^12) and few outputs

@@ -13,6 +13,8 @@ QXB_PLAN_L1_BW=0 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu > gp
 cp gpurun_out/op_profile_rqc_7x7_d20_c64_s4096.json gpurun_out/r2a_op_profile_r1pmodel.json 2>/dev/null
 # 3. register tiles for small nodes (QXB_MIN_LOB), per-op times and equality of the amplitudes
 PROBE_CONFIGS=lob timeout 500 python scripts/probe_variants.py > gpurun_out/r2a_probe_lob.log 2>&1; tail -12 gpurun_out/r2a_probe_lob.log
+# 3b. TMA-staged contraction kernel (QXB_SMEM_TMA=1): bounded waits trap instead of hanging; own timeout as well
+PROBE_CONFIGS=tma timeout 400 python scripts/probe_variants.py > gpurun_out/r2a_probe_tma.log 2>&1; tail -12 gpurun_out/r2a_probe_tma.log
 # 4. tcgen05 bring-up kernel: self-check against fp64, then the timed 4096 x 4096 x 512 case
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o /tmp/tc5_cgemm scripts/microbench/tc5_cgemm.cu \
   && timeout 60 /tmp/tc5_cgemm > gpurun_out/r2a_tc5.log 2>&1; cat gpurun_out/r2a_tc5.log

@@ -28,7 +28,11 @@ if os.environ.get("PROBE_CONFIGS") == "smem":
 if os.environ.get("PROBE_CONFIGS") == "lob":
     # register tiles for nodes with <= 2^8..2^10 elements per bitstring: the CTA's 256 threads span several bitstring rows
     CONFIGS = [("default", {}), ("lob7", {"QXB_MIN_LOB": "7"}), ("lob6", {"QXB_MIN_LOB": "6"}), ("lob5", {"QXB_MIN_LOB": "5"})]
-KNOBS = ("QXB_MIN_LOB", "QXB_SMEM_RATIO", "QXB_SMEM_MINHB", "QXB_SMEM_SHARED", "QXB_MINB", "QXB_KC_REGS_MULTI", "QXB_KC_REGS_ONE")
+if os.environ.get("PROBE_CONFIGS") == "tma":
+    # operand rows through 1-D TMA bulk copies into a ring of shared-memory stages (contract_tma_kernel, never run before r2)
+    CONFIGS = [("default", {}), ("tma", {"QXB_SMEM_TMA": "1"}), ("tma_all", {"QXB_SMEM_TMA": "1", "QXB_SMEM_TMA_RATIO": "0"}),
+               ("tma_lob6", {"QXB_SMEM_TMA": "1", "QXB_MIN_LOB": "6"})]
+KNOBS = ("QXB_SMEM_TMA", "QXB_SMEM_TMA_RATIO", "QXB_MIN_LOB", "QXB_SMEM_RATIO", "QXB_SMEM_MINHB", "QXB_SMEM_SHARED", "QXB_MINB", "QXB_KC_REGS_MULTI", "QXB_KC_REGS_ONE")
 results, ref = {}, None
 for tag, env in CONFIGS:
     for k in KNOBS:
