@@ -23,7 +23,7 @@ using namespace qxb;
 // ===================================================================== YAML subset
 // What YAML.jl writes for output_params_dict (outputs.jl:54-77): nested block mappings, block sequences of
 // scalars (possibly at the indentation of their key), plain / single- / double-quoted scalars, `~`/`null`,
-// flow sequences of scalars.  Anchors, tags, multi-line scalars and multi-document streams are rejected.
+// flow sequences / flow mappings of scalars.  Anchors, tags, multi-line scalars and multi-document streams are rejected.
 namespace {
 
 struct YNode {
@@ -120,7 +120,30 @@ struct YParser {
             }
             return n;
         }
-        if (t[0] == '{') yerr(path, no, "flow mappings are not supported");
+        if (t[0] == '{') {                                   // flow mapping of scalars: {a: 1, b: 'x'}
+            if (t.back() != '}') yerr(path, no, "flow mapping must close on the same line");
+            n.kind = YNode::MAP;
+            std::string cur;
+            char q = 0;
+            std::string inner = t.substr(1, t.size() - 2);
+            for (size_t i = 0; i <= inner.size(); ++i) {
+                char c = i < inner.size() ? inner[i] : ',';
+                if (q) { cur += c; if (c == q) q = 0; continue; }
+                if (c == '\'' || c == '"') { q = c; cur += c; continue; }
+                if (c == '[' || c == '{') yerr(path, no, "nested flow collections are not supported");
+                if (c == ',') {
+                    std::string item = trim(cur), k, v;
+                    cur.clear();
+                    if (item.empty()) { if (i < inner.size()) yerr(path, no, "empty entry in flow mapping"); continue; }
+                    if (!split_key(item, k, v)) yerr(path, no, "expected 'key: value' in flow mapping");
+                    if (n.get(k)) yerr(path, no, "duplicate key '" + k + "'");
+                    n.map.push_back({k, scalar(v, no)});
+                    continue;
+                }
+                cur += c;
+            }
+            return n;
+        }
         n.s = t;
         return n;
     }

@@ -44,5 +44,7 @@ def score(rate, min_lob=None):
     print("      top: " + "  ".join(f"{n}[{c},{k},{s},t{ma}{nb}] {ti * 1e3:.2f}" for ti, n, c, k, s, ma, nb in worst[:6]), flush=True)
 
 
-for rate in [None] + [float(x) for x in os.environ.get("MODEL_RATES", "0,30,14").split(",")]:
+for rate in [None] + [float(x) for x in os.environ.get("MODEL_RATES", "0,30,14").split(",") if x]:
     score(rate)
+for lob in [int(x) for x in os.environ.get("MODEL_LOBS", "").split(",") if x]:     # QXB_MIN_LOB on the default plan
+    score(None, lob)

@@ -179,6 +179,46 @@ def test_params_reader_schema(tmp_path):
         read_params(p)
 
 
+def test_params_reader_matches_pyyaml_on_styles(tmp_path):
+    """The same parameter dictionaries dumped by pyyaml in block style, with other indents, and with leaf collections
+    in flow style (`bitstrings: ['01', ...]`, `params: {num_qubits: 5, ...}`): same result as yaml.safe_load."""
+    import random
+    rng = random.Random(5)
+    p = str(tmp_path / "p.yml")
+    for trial in range(60):
+        nq = rng.randrange(1, 40)
+        method = rng.choice(["List", "Uniform", "Rejection"])
+        seed = rng.choice([None, 0, 7, 2 ** 40 + 3])
+        if method == "List":
+            bs = ["".join(rng.choice("01+-") for _ in range(nq)) for _ in range(rng.randrange(1, 12))]
+            params = {"num_samples": len(bs), "bitstrings": bs}
+        elif method == "Uniform":
+            params = {"num_qubits": nq, "num_samples": rng.randrange(0, 20), "seed": seed}
+        else:
+            params = {"num_qubits": nq, "M": rng.choice([0.0001, 2.5, 1e-3]), "fix_M": rng.choice([True, False]), "seed": seed,
+                      "num_samples": rng.randrange(0, 20)}
+        doc = {"output": {"method": method, "params": params}}
+        text = yaml.safe_dump(doc, sort_keys=rng.choice([True, False]), default_flow_style=rng.choice([False, None]),
+                              indent=rng.choice([2, 4, 6]), width=rng.choice([40, 80, 10 ** 6]), explicit_start=rng.choice([True, False]))
+        open(p, "w").write(text)
+        want = yaml.safe_load(text)["output"]
+        try:
+            got = read_params(p)
+        except QxbError as e:
+            # the one construct of these dumps outside the subset: a flow sequence folded over several lines
+            assert "same line" in str(e), (text, str(e))
+            continue
+        assert got["method"] == want["method"], text
+        wp = want["params"]
+        assert got["num_samples"] == wp["num_samples"], text
+        if method == "List":
+            assert got["bitstrings"] == [str(b) for b in wp["bitstrings"]] and got["num_qubits"] == nq, text
+        else:
+            assert got["num_qubits"] == nq and got["seed"] == wp["seed"], text
+        if method == "Rejection":
+            assert got["M"] == wp["M"] and got["fix_M"] == wp["fix_M"], text
+
+
 def _triple(tmp_path):
     prefix = str(tmp_path / "rqc_3_3_8")
     q.generate_simulation_files(q.create_rqc_circuit(3, 3, 8, 42), prefix, 2, seed=42, time=0,
