@@ -227,7 +227,8 @@ int  qxb_params_read(const char* yml_path, qxb_params* p, char* bitstrings, int6
  * qxb_graph_replan first.  Writes output_file (may be NULL) as JLD2 with datasets "bitstrings"
  * (fixed-length strings) and "amplitudes" (complex of `dtype`).  seconds (may be NULL) receives the reference's
  * timer sections: [0] parse input files, [1] create context, [2] simulation, [3] write results.
- * List and Uniform methods; Rejection is QXB_ERR_UNSUPP here (Python harness). */
+ * All three methods of outputs.jl:54-77: List, Uniform, and Rejection (empirical-supremum rejection sampling,
+ * docs/src/features.md:68-84, candidates in batches of 1024; the file then also holds the scalars "M" and "drawn"). */
 int  qxb_execute_files(const char* dsl_file, const char* input_file, const char* param_file, const char* output_file,
                        int dtype, int64_t max_amplitudes, int64_t max_slices, int replan_candidates,
                        int64_t* n_amplitudes, double* seconds);

@@ -8,6 +8,7 @@
 // qxb_graph_* / qxb_amplitudes entry points a Julia `ccall` binding uses, so the file path cannot drift
 // from the in-process one.  Pure host code; the compute calls fail with QXB_ERR_CUDA without a GPU.
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -447,9 +448,6 @@ int qxb_execute_files(const char* dsl_file, const char* input_file, const char* 
         double t0 = now();
         std::string text = read_text(dsl_file);
         Params pr = read_params(param);
-        if (pr.p.method == QXB_METHOD_REJECTION)
-            throw Error(QXB_ERR_UNSUPP, "the native runner executes List and Uniform parameter files; Rejection sampling is "
-                                        "in the Python harness (qxtools.jl_b200/samplers.py)");
         ok(qxb_graph_create(&g, dtype));
         ok(qxb_graph_parse_dsl(g, text.data(), text.size()));
         ok(qxb_graph_load_jld2(g, input.c_str(), nullptr));
@@ -473,7 +471,8 @@ int qxb_execute_files(const char* dsl_file, const char* input_file, const char* 
                 char c = bs[(size_t)a][(size_t)q];
                 bits[(size_t)(a * n_out + q)] = c == '0' ? 0 : c == '1' ? 1 : c == '+' ? 2 : 3;
             }
-        if (replan_candidates > 0) ok(qxb_graph_replan(g, replan_candidates, n_amp > 0 ? n_amp : 1, nullptr, nullptr));
+        if (replan_candidates > 0)      // plan for the batch the run will use (Rejection: candidate batches of 1024)
+            ok(qxb_graph_replan(g, replan_candidates, pr.p.method == QXB_METHOD_REJECTION ? 1024 : (n_amp > 0 ? n_amp : 1), nullptr, nullptr));
         ok(qxb_graph_compile(g, nullptr));
         int64_t n_slices = 0;
         ok(qxb_graph_num_slices(g, &n_slices));
@@ -482,21 +481,70 @@ int qxb_execute_files(const char* dsl_file, const char* input_file, const char* 
 
         const size_t es = dtype == QXB_C32 ? 8 : 16;
         std::vector<uint8_t> amps((size_t)n_amp * es);
-        if (n_amp > 0) ok(qxb_amplitudes(g, bits.data(), n_amp, 0, n_slices, amps.data()));
+        double final_M = pr.p.M;
+        int64_t drawn = 0;
+        if (pr.p.method == QXB_METHOD_REJECTION) {
+            // Rejection sampling from the circuit's output distribution (docs/src/features.md:68-84, outputs.jl:57-62):
+            // draw a uniform bitstring, accept with probability p 2^n / M; unless fix_M, a larger ratio raises M
+            // ("empirical supremum" sampling).  Candidates go down in batches of 1024 -- one qxb_amplitudes call each.
+            // Stream: the library's splitmix64 (the reference: Julia's MersenneTwister, not reproducible elsewhere).
+            if (n_out != (int)pr.p.num_qubits)
+                throw Error(QXB_ERR_ARG, "the program has " + std::to_string(n_out) + " outputs but the parameter file says num_qubits = " +
+                                         std::to_string(pr.p.num_qubits));
+            int64_t want = pr.p.num_samples;
+            if (max_amplitudes >= 0 && want > max_amplitudes) want = max_amplitudes;
+            uint64_t rs = pr.p.has_seed ? (uint64_t)pr.p.seed : 0x5851f42d4c957f2dull;
+            const int64_t batch = 1024;
+            const double N = std::ldexp(1.0, n_out);
+            std::vector<uint8_t> cand((size_t)(batch * std::max(n_out, 1))), camp((size_t)batch * es);
+            bs.clear(); amps.clear();
+            for (int b = 0; b < 10000 && (int64_t)bs.size() < want; ++b) {
+                uint64_t word = 0;
+                for (int64_t i = 0; i < batch * n_out; ++i) {
+                    if (i % 64 == 0) word = splitmix64(rs);
+                    cand[(size_t)i] = (uint8_t)((word >> (i % 64)) & 1);
+                }
+                ok(qxb_amplitudes(g, cand.data(), batch, 0, n_slices, camp.data()));
+                for (int64_t i = 0; i < batch && (int64_t)bs.size() < want; ++i) {
+                    double re, im;
+                    if (dtype == QXB_C32) { float v[2]; memcpy(v, &camp[(size_t)i * 8], 8); re = v[0]; im = v[1]; }
+                    else { double v[2]; memcpy(v, &camp[(size_t)i * 16], 16); re = v[0]; im = v[1]; }
+                    const double ratio = (re * re + im * im) * N;
+                    const double u = (double)(splitmix64(rs) >> 11) / 9007199254740992.0;
+                    ++drawn;
+                    if (!pr.p.fix_M && ratio > final_M) final_M = ratio;
+                    if (u < ratio / final_M) {
+                        std::string str((size_t)n_out, '0');
+                        for (int q = 0; q < n_out; ++q) str[(size_t)q] = (char)('0' + cand[(size_t)(i * n_out + q)]);
+                        bs.push_back(str);
+                        amps.insert(amps.end(), camp.begin() + (size_t)i * es, camp.begin() + (size_t)(i + 1) * es);
+                    }
+                }
+            }
+        } else if (n_amp > 0) {
+            ok(qxb_amplitudes(g, bits.data(), n_amp, 0, n_slices, amps.data()));
+        }
+        const int64_t n_res = (int64_t)bs.size();
         double t3 = now();
 
         if (output_file && *output_file) {
-            std::vector<char> names((size_t)(n_amp * (n_out > 0 ? n_out : 1)));
-            for (int64_t a = 0; a < n_amp; ++a) memcpy(&names[(size_t)(a * n_out)], bs[(size_t)a].data(), (size_t)n_out);
+            std::vector<char> names((size_t)(n_res * (n_out > 0 ? n_out : 1)));
+            for (int64_t a = 0; a < n_res; ++a) memcpy(&names[(size_t)(a * n_out)], bs[(size_t)a].data(), (size_t)n_out);
             std::vector<jld2::WriteArray> arrays(2);
             arrays[0].name = "bitstrings"; arrays[0].kind = jld2::EK_STRING; arrays[0].elem_size = n_out > 0 ? n_out : 1;
-            arrays[0].dims = {n_amp}; arrays[0].data = names.data();
+            arrays[0].dims = {n_res}; arrays[0].data = names.data();
             arrays[1].name = "amplitudes"; arrays[1].kind = dtype == QXB_C32 ? jld2::EK_C32 : jld2::EK_C64;
-            arrays[1].elem_size = (int)es; arrays[1].dims = {n_amp}; arrays[1].data = amps.data();
+            arrays[1].elem_size = (int)es; arrays[1].dims = {n_res}; arrays[1].data = amps.data();
+            const double drawn_d = (double)drawn;
+            if (pr.p.method == QXB_METHOD_REJECTION) {       // what the sampler ended with (the Python harness writes the same)
+                jld2::WriteArray m; m.name = "M"; m.kind = jld2::EK_F64; m.elem_size = 8; m.data = &final_M;
+                jld2::WriteArray d; d.name = "drawn"; d.kind = jld2::EK_F64; d.elem_size = 8; d.data = &drawn_d;
+                arrays.push_back(m); arrays.push_back(d);
+            }
             jld2::write_file(output_file, arrays, false);
         }
         double t4 = now();
-        if (n_amplitudes) *n_amplitudes = n_amp;
+        if (n_amplitudes) *n_amplitudes = n_res;
         if (seconds) { seconds[0] = t1 - t0; seconds[1] = t2 - t1; seconds[2] = t3 - t2; seconds[3] = t4 - t3; }
     });
     if (g) qxb_graph_destroy(g);

@@ -91,3 +91,27 @@ def test_python_execute_reads_and_writes_jld2(gpu, triple):
     assert [b.decode() for b in back["bitstrings"]] == list(res.keys()) == bitstrings
     assert np.array_equal(back["amplitudes"], np.array(list(res.values())))
     assert rel_err(back["amplitudes"], orc.amplitudes(cmds, data, bitstrings), 9) < 1e-10
+
+
+def test_native_rejection_sampler(gpu, tmp_path):
+    """A Rejection parameter file (outputs.jl:57-62) through the native runner: GHZ-5 yields only its two outcomes, each
+    with |amplitude| = 1/sqrt2; fix_M keeps M; the file also records M and the number of candidates drawn."""
+    prefix = str(tmp_path / "ghz5")
+    q.generate_simulation_files(q.create_ghz_circuit(5), prefix, 1, time=0,
+                                output_args=q.output_params_dict(5, 12, output_method="Rejection", M=16.0, fix_M=True, seed=4))
+    lib = load()
+    n = C.c_int64()
+    out = prefix + "_out.jld2"
+    rc = lib.qxb_execute_files((prefix + ".qx").encode(), None, None, out.encode(), 1, -1, -1, 0, C.byref(n), None)
+    assert rc == 0, lib.qxb_last_error()
+    res = load_jld2(out)
+    assert n.value == 12 and len(res["bitstrings"]) == 12
+    assert set(b.decode() for b in res["bitstrings"]) <= {"00000", "11111"}
+    assert np.allclose(np.abs(res["amplitudes"]), 1 / np.sqrt(2), atol=1e-12)
+    assert float(res["M"]) == 16.0 and float(res["drawn"]) >= 12
+    # frugal mode: M rises to the largest p 2^n seen (16 for GHZ-5), -a truncates the number of samples
+    q.generate_parameter_file(prefix, q.output_params_dict(5, 12, output_method="Rejection", M=0.0001, fix_M=False, seed=5))
+    rc = lib.qxb_execute_files((prefix + ".qx").encode(), None, None, out.encode(), 0, 5, -1, 0, C.byref(n), None)
+    assert rc == 0, lib.qxb_last_error()
+    res = load_jld2(out)
+    assert n.value == 5 and abs(float(res["M"]) - 16.0) < 1e-4 and res["amplitudes"].dtype == np.complex64

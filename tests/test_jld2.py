@@ -261,6 +261,10 @@ def test_execute_files_host_part_and_no_cpu_fallback(tmp_path):
     rc = lib.qxb_execute_files((prefix + ".qx").encode(), None, None, (prefix + "_out.jld2").encode(), 1, -1, -1, 0, C.byref(n), None)
     assert rc == -3, lib.qxb_last_error()
     assert not os.path.exists(prefix + "_out.jld2")
+    # a Rejection parameter file takes the same route (sampling loop = GPU calls)
+    q.generate_parameter_file(prefix + "_rej", q.output_params_dict(9, 4, output_method="Rejection", M=8.0, fix_M=True, seed=3))
+    rc = lib.qxb_execute_files((prefix + ".qx").encode(), None, (prefix + "_rej.yml").encode(), None, 1, -1, -1, 0, C.byref(n), None)
+    assert rc == -3, lib.qxb_last_error()
     os.remove(prefix + ".jld2")
     rc = lib.qxb_execute_files((prefix + ".qx").encode(), None, None, None, 1, -1, -1, 0, None, None)
     assert rc == -1 and b".jld2" in lib.qxb_last_error()
