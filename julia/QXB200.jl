@@ -153,7 +153,14 @@ function execute(dsl_file::String, input_file::Union{String, Nothing}=nothing,
     param_file === nothing && (param_file = splitext(dsl_file)[1] * ".yml")
     tensors = load(input_file)                          # JLD2: label => N-d ComplexF64 array
     params = YAML.load_file(param_file)["output"]
-    params["method"] == "List" || error("only the List output method is wired (Rejection/Uniform: QXContexts samplers)")
+    if params["method"] != "List"
+        # Uniform / Rejection (src/outputs.jl:57-72): the library's own samplers, through the whole-triple entry point
+        output_file == "" && (output_file = tempname() * ".jld2")
+        execute_native(dsl_file, input_file, param_file, output_file; max_amplitudes=max_amplitudes, max_slices=max_slices, elt=elt)
+        res = load(output_file)            # amplitudes: compound {re, im} -> NamedTuple elements (INTEGRATION.md)
+        amps = [Complex(a.re, a.im) for a in res["amplitudes"]]
+        return OrderedDict(zip(String.(res["bitstrings"]), amps))
+    end
     bs = Vector{String}(params["params"]["bitstrings"])
     max_amplitudes === nothing || (bs = bs[1:min(end, max_amplitudes)])
     g = Graph(read(dsl_file, String), tensors; dtype=(elt == ComplexF32 ? C32 : C64))
