@@ -73,6 +73,10 @@ def test_qxrun_binary(gpu, triple):
     prefix, cmds, data, bitstrings = triple
     if not os.path.exists(QXRUN):                            # normally built by __graft_entry__.build() (csrc/Makefile)
         subprocess.run(["make", "-C", os.path.join(ROOT, "qxtools.jl_b200", "csrc"), "../bin/qxrun"], check=True)
+    try:
+        os.chmod(QXRUN, 0o755)                               # the snapshot that reaches the GPU box may drop the mode bits
+    except OSError:
+        pass
     out = prefix + "_cli.jld2"
     r = subprocess.run([QXRUN, "-d", prefix + ".qx", "-o", out, "--dtype", "c64", "-t", "-g", "-b", "1"],
                        capture_output=True, text=True, timeout=600)
