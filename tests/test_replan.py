@@ -164,3 +164,30 @@ def test_replan_is_deterministic_and_tree_search_beats_orders(lib_built):
     assert a.text == b.text and ia["bytes"] == ib["bytes"]
     _, info = replan_dsl(txt, n_amp=1024, candidates=8)
     assert ia["bytes"] <= info["bytes"] * 1.0001
+
+
+def test_l1_aware_model_avoids_long_k_untiled_nodes(lib_built, monkeypatch):
+    """The planner's time model charges the SIMT kernel's operand loads (qxb_treeopt.h: l1_bandwidth).  On the headline
+    workload the plan it finds must have clearly fewer MACs than the single-rate model of r1p (QXB_PLAN_L1_BW=0) at about
+    the same bytes, and no node with K >= 32 and no register tile (the 552 GB/s node of profiles/r1p_ops.md)."""
+    import bench
+    from template_emulator import templates
+    txt, data, w = bench.build_workload("rqc_7x7_d20_c64_s4096")
+    n_amp = 131072
+
+    def plan(l1):
+        if l1 is None:
+            monkeypatch.delenv("QXB_PLAN_L1_BW", raising=False)
+        else:
+            monkeypatch.setenv("QXB_PLAN_L1_BW", l1)
+        g = Graph.from_dsl(txt, data, "c64", replan=48, replan_n_amp=n_amp)
+        ops = [(p, o) for p, o in zip(templates(g), g.describe()["ops"]) if o["phase"] == "chunk"]
+        macs = sum(2.0 ** (p.nC + p.nK) for p, _ in ops)
+        untiled_long_k = [o["name"] for p, o in ops if p.nK >= 5 and p.ma + p.nb == 0 and p.nC >= 8]
+        return g.replan_info["bytes"], macs, untiled_long_k
+
+    b_new, m_new, bad_new = plan(None)
+    b_old, m_old, _ = plan("0")
+    assert m_new < 0.9 * m_old                      # measured here: 0.78
+    assert b_new < 1.15 * b_old                     # measured here: 1.06
+    assert not bad_new
