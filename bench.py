@@ -203,6 +203,60 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def tune_plan(args, txt, data, w, g, dev, stream, world, dist, torch):
+    """-> (graph to run (uncompiled), its plan text, report).  Candidates: (planner model) x (QXB_MIN_LOB); the probe is
+    the first min(amps, 32768) bitstrings over the full slice space, 2 warm-up + 3 timed replays, CUDA events on the
+    stream the library launches on; results must agree with the baseline (default plan, default knobs) to 1e-9
+    (ComplexF64) / 1e-4 (ComplexF32) of the largest amplitude."""
+    from qxb200.executor import Graph, autotune
+    n_q = w["rows"] * w["cols"]
+    n_probe = int(min(args.amps, 32768))
+    plans = [("l1model", g.text, g.replan_info)]
+    os.environ["QXB_PLAN_L1_BW"] = "0"
+    try:
+        g_old = Graph.from_dsl(txt, data, w["dtype"], replan=args.replan_candidates, replan_n_amp=args.amps)
+        if g_old.text != g.text:
+            plans.append(("r1pmodel", g_old.text, g_old.replan_info))
+        del g_old
+    finally:
+        os.environ.pop("QXB_PLAN_L1_BW", None)
+    cands = [(f"{tag}/lob{lob}", text, ({} if lob == 8 else {"QXB_MIN_LOB": str(lob)})) for tag, text, _ in plans for lob in (8, 7, 6)]
+    bits = torch.from_numpy(synth_bits(n_probe, n_q)).to(dev)
+    cdt = torch.complex64 if w["dtype"] == "c32" else torch.complex128
+    out = torch.zeros(n_probe, dtype=cdt, device=dev)
+
+    def build(text):
+        return Graph.from_dsl(text, data, w["dtype"]).compile(amp_batch=args.amp_batch, cuda_graph=not args.no_graph)
+
+    def probe(gc):
+        S = gc.n_slices
+        for _ in range(2):
+            gc.amplitudes_device(bits.data_ptr(), n_probe, out.data_ptr(), 0, S)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(3):
+            gc.amplitudes_device(bits.data_ptr(), n_probe, out.data_ptr(), 0, S)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 3.0, out.cpu().numpy().copy()
+
+    def reduce_times(ts):
+        if world == 1:
+            return ts
+        t = torch.tensor([1e30 if x == float("inf") else x for x in ts], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float("inf") if x >= 1e29 else x for x in t.tolist()]
+
+    best, report = autotune(cands, build, probe, reduce_times, rel_tol=1e-4 if w["dtype"] == "c32" else 1e-9)
+    del bits, out
+    tag, text, env = cands[best]
+    os.environ.update(env)                                   # in force for the timed graph, the profiled clone and the as-given run
+    info = next(i for t, _, i in plans if tag.startswith(t + "/"))
+    chosen = Graph.from_dsl(text, data, w["dtype"])
+    chosen.replan_info = info
+    return chosen, text, {"chosen": tag, "probe_bitstrings": n_probe, "candidates": report}
+
+
 # ------------------------------------------------------------------ GPU arm
 def run_gpu(args):
     import torch
@@ -229,6 +283,17 @@ def run_gpu(args):
     g = Graph.from_dsl(txt, data, w["dtype"], replan=0 if args.no_replan else args.replan_candidates,
                        replan_n_amp=args.amps)
     plan_txt = g.text
+    tune_report = None
+    if not args.no_replan and not args.no_autotune:
+        # Measured choice among exact alternatives before anything is timed (qxb200.executor.autotune): the tree of the
+        # L1-aware planner model vs the tree of the r1p model, each with the register-tile knob QXB_MIN_LOB = 8 / 7 / 6.
+        # Any failure in here leaves the run exactly as it was without tuning.
+        try:
+            g, plan_txt, tune_report = tune_plan(args, txt, data, w, g, dev, stream, world, dist, torch)
+        except Exception as e:                                   # noqa: BLE001
+            tune_report = {"error": repr(e)[:300]}
+            for k in ("QXB_MIN_LOB", "QXB_PLAN_L1_BW"):
+                os.environ.pop(k, None)
     g.compile(amp_batch=args.amp_batch, cuda_graph=not args.no_graph)
     S = g.n_slices
     n_amp = args.amps
@@ -399,6 +464,7 @@ def run_gpu(args):
                                 f"{g.replan_info['n_amp_model']} bitstrings") if g.replan_info and g.replan_info.get("replanned")
                                else "contraction order as given by the file",
                        "as_given_plan": as_given,
+                       "autotune": tune_report,
                        "l2": l2_note,
                        "amp_batch": st["amp_batch"], "mean_p_times_2^n": norm},
             "e2e": {"value": e2e, "unit": "amplitudes/s", "h2d_bytes_per_step": int(n_amp * n_q),
@@ -481,6 +547,8 @@ def main():
     ap.add_argument("--ref-slices", type=int, default=64, help="slices per bitstring in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-replan", action="store_true", help="run the contraction order exactly as the file gives it")
+    ap.add_argument("--no-autotune", action="store_true",
+                    help="skip the measured choice among planner models / register-tile knobs (run the default plan and knobs)")
     ap.add_argument("--replan-candidates", type=int, default=128, help="orders scored by the re-planner (seeded)")
     ap.add_argument("--no-as-given", action="store_true", help="skip the extra as-given-plan measurement")
     ap.add_argument("--partition", default="auto", choices=["auto", "amps", "slices"])

@@ -304,6 +304,58 @@ class Graph:
             return json.load(f)
 
 
+def autotune(candidates, build, probe, reduce_times=None, rel_tol: float = 1e-9):
+    """Measured choice among EXACT alternatives of the same program (different contraction trees from the re-planner,
+    different kernel-selection knobs): every candidate is built, run on the same probe input and timed; a candidate
+    whose result differs from the first one's by more than ``rel_tol`` (relative to the largest amplitude), or that
+    raises, is discarded.  The model picks the candidates, the GPU picks the winner.
+
+    ``candidates``: ``[(tag, plan_text, env)]`` -- ``env`` = library knobs (``os.environ`` entries) in force while the
+    candidate is compiled and run; the first candidate is the baseline.  ``build(plan_text) -> graph``;
+    ``probe(graph) -> (milliseconds, result ndarray)``; ``reduce_times(list) -> list`` combines the times over the
+    ranks of a multi-GPU job (max), so that every rank takes the same decision.
+    Returns ``(index, report)``; index 0 when nothing could be measured."""
+    import os
+    times, report, ref = [], [], None
+    for tag, text, env in candidates:
+        saved = {k: os.environ.get(k) for k in env}
+        ms, note = float("inf"), "ok"
+        try:
+            os.environ.update(env)
+            g = build(text)
+            t, res = probe(g)
+            res = np.asarray(res)
+            del g
+            if ref is None:
+                if len(times) == 0:
+                    ref, ms = res, float(t)
+                else:
+                    note = "no baseline result to compare with"
+            else:
+                scale = max(float(np.max(np.abs(ref))), 1e-300)
+                diff = float(np.max(np.abs(res - ref))) / scale
+                if diff <= rel_tol:
+                    ms = float(t)
+                else:
+                    note = f"discarded: differs from the baseline by {diff:.2e}"
+        except Exception as e:                       # a candidate must never take the run down
+            note = f"failed: {e!r}"[:200]
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        times.append(ms)
+        report.append({"tag": tag, "ms": None if ms == float("inf") else ms, "note": note})
+    if reduce_times is not None:
+        times = [float(t) for t in reduce_times(list(times))]
+        for r, t in zip(report, times):
+            r["ms_max_over_ranks"] = None if t == float("inf") else t
+    best = min(range(len(times)), key=lambda i: (times[i], i)) if times and min(times) < float("inf") else 0
+    return best, report
+
+
 def init(device: int = 0) -> None:
     check(_lib.load().qxb_init(device))
 
