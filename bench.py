@@ -204,7 +204,7 @@ class ClockSampler:
 
 
 def tune_plan(args, txt, data, w, g, dev, stream, world, dist, torch):
-    """-> (graph to run (uncompiled), its plan text, report).  Candidates: (planner model) x (QXB_MIN_LOB); the probe is
+    """-> (graph to run (uncompiled), its plan text, report).  Candidates: (planner model setting) x (QXB_MIN_LOB); the probe is
     the first min(amps, 32768) bitstrings over the full slice space, 2 warm-up + 3 timed replays, CUDA events on the
     stream the library launches on; results must agree with the baseline (default plan, default knobs) to 1e-9
     (ComplexF64) / 1e-4 (ComplexF32) of the largest amplitude."""
@@ -212,14 +212,19 @@ def tune_plan(args, txt, data, w, g, dev, stream, world, dist, torch):
     n_q = w["rows"] * w["cols"]
     n_probe = int(min(args.amps, 32768))
     plans = [("l1model", g.text, g.replan_info)]
-    os.environ["QXB_PLAN_L1_BW"] = "0"
-    try:
-        g_old = Graph.from_dsl(txt, data, w["dtype"], replan=args.replan_candidates, replan_n_amp=args.amps)
-        if g_old.text != g.text:
-            plans.append(("r1pmodel", g_old.text, g_old.replan_info))
-        del g_old
-    finally:
-        os.environ.pop("QXB_PLAN_L1_BW", None)
+    # other trees: the single-rate model of r1p (L1 term off) and the L1 term at 14 / 30 TB/s -- the search is noisy at
+    # the +-5 % level between such settings (profiles/r1q_summary.md), so let the probe pick
+    for tag, bw in (("r1pmodel", "0"), ("l1bw14", "14"), ("l1bw30", "30")):
+        os.environ["QXB_PLAN_L1_BW"] = bw
+        try:
+            g_alt = Graph.from_dsl(txt, data, w["dtype"], replan=args.replan_candidates, replan_n_amp=args.amps)
+            if all(g_alt.text != t for _, t, _ in plans):
+                plans.append((tag, g_alt.text, g_alt.replan_info))
+            del g_alt
+        except Exception:                                    # noqa: BLE001  (one plan less to choose from)
+            pass
+        finally:
+            os.environ.pop("QXB_PLAN_L1_BW", None)
     cands = [(f"{tag}/lob{lob}", text, ({} if lob == 8 else {"QXB_MIN_LOB": str(lob)})) for tag, text, _ in plans for lob in (8, 7, 6)]
     bits = torch.from_numpy(synth_bits(n_probe, n_q)).to(dev)
     cdt = torch.complex64 if w["dtype"] == "c32" else torch.complex128
