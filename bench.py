@@ -211,21 +211,11 @@ def tune_plan(args, txt, data, w, g, dev, stream, world, dist, torch):
     from qxb200.executor import Graph, autotune
     n_q = w["rows"] * w["cols"]
     n_probe = int(min(args.amps, 32768))
-    plans = [("l1model", g.text, g.replan_info)]
-    # other trees: the single-rate model of r1p (L1 term off) and the L1 term at 14 / 30 TB/s -- the search is noisy at
-    # the +-5 % level between such settings (profiles/r1q_summary.md), so let the probe pick
-    for tag, bw in (("r1pmodel", "0"), ("l1bw14", "14"), ("l1bw30", "30")):
-        os.environ["QXB_PLAN_L1_BW"] = bw
-        try:
-            g_alt = Graph.from_dsl(txt, data, w["dtype"], replan=args.replan_candidates, replan_n_amp=args.amps)
-            if all(g_alt.text != t for _, t, _ in plans):
-                plans.append((tag, g_alt.text, g_alt.replan_info))
-            del g_alt
-        except Exception:                                    # noqa: BLE001  (one plan less to choose from)
-            pass
-        finally:
-            os.environ.pop("QXB_PLAN_L1_BW", None)
-    cands = [(f"{tag}/lob{lob}", text, ({} if lob == 8 else {"QXB_MIN_LOB": str(lob)})) for tag, text, _ in plans for lob in (8, 7, 6)]
+    from qxb200.tuning import candidates_of, plan_candidates
+    # trees of the planner under four settings of its L1 term (the first one is the graph already re-planned above) x
+    # QXB_MIN_LOB 8 / 7 / 6: the search is noisy at the +-5 % level between such settings (profiles/r1q_summary.md)
+    plans = plan_candidates(txt, data, w["dtype"], args.replan_candidates, args.amps, first=g)
+    cands = candidates_of(plans)
     bits = torch.from_numpy(synth_bits(n_probe, n_q)).to(dev)
     cdt = torch.complex64 if w["dtype"] == "c32" else torch.complex128
     out = torch.zeros(n_probe, dtype=cdt, device=dev)

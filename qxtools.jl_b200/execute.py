@@ -66,8 +66,10 @@ def _bitstrings_from_params(params: dict, max_amplitudes: Optional[int]):
 def execute(dsl_file: str, input_file: Optional[str] = None, param_file: Optional[str] = None,
             output_file: Optional[str] = None, use_mpi: bool = False, sub_comm_size: int = 1,
             use_gpu: bool = True, max_amplitudes: Optional[int] = None, max_slices: Optional[int] = None,
-            timings: bool = False, dtype: str = "c32", replan: int = -1):
-    """Returns ``OrderedDict{bitstring => amplitude}`` on rank 0 (None elsewhere)."""
+            timings: bool = False, dtype: str = "c32", replan: int = -1, autotune: bool = False):
+    """Returns ``OrderedDict{bitstring => amplitude}`` on rank 0 (None elsewhere).
+    ``autotune=True`` (single process, List / Uniform): measured choice among the re-planner's trees and the
+    register-tile knob on the first bitstrings before the run (``qxb200.tuning.tune``)."""
     if not use_gpu:
         raise RuntimeError("qxb200 has no CPU path: use_gpu must be True")
     from .executor import Graph, init
@@ -96,7 +98,17 @@ def execute(dsl_file: str, input_file: Optional[str] = None, param_file: Optiona
     init(int(os.environ.get("LOCAL_RANK", "0")))
     bitstrings = _bitstrings_from_params(params, max_amplitudes)
     n_model = len(bitstrings) if bitstrings is not None else 1024
-    g = Graph.from_dsl(text, data, dtype, replan=replan, replan_n_amp=max(1, n_model)).compile()
+    tune_report = None
+    if autotune and not use_mpi and bitstrings:
+        from .executor import bits_from_strings
+        from .tuning import tune
+        g0 = Graph.from_dsl(text, data, dtype)
+        probe = bits_from_strings(bitstrings[:min(len(bitstrings), 32768)], g0.n_outputs)
+        del g0
+        g, tune_report = tune(text, data, dtype, np.ascontiguousarray(probe), replan_candidates=32 if replan < 0 else max(1, replan))
+        g.compile()
+    else:
+        g = Graph.from_dsl(text, data, dtype, replan=replan, replan_n_amp=max(1, n_model)).compile()
     if g.root_dims:
         raise ValueError("the program saves a tensor (open network); execute() writes one amplitude per bitstring -- "
                          "use Graph.amplitudes / contract_tn for open networks")
@@ -179,9 +191,10 @@ def main(argv=None):
     ap.add_argument("--timings", "-t", action="store_true")
     ap.add_argument("--blas-threads", "-b", type=int, default=8, help="ignored (no BLAS on the path)")
     ap.add_argument("--dtype", default="c32", choices=["c32", "c64"])
+    ap.add_argument("--autotune", action="store_true", help="measured choice among re-planned trees / register-tile knobs first")
     a = ap.parse_args(argv)
     kw = dict(use_mpi=a.mpi, sub_comm_size=a.sub_comm_size, use_gpu=True, max_amplitudes=a.number_amplitudes,
-              max_slices=a.number_slices, timings=a.timings, dtype=a.dtype)
+              max_slices=a.number_slices, timings=a.timings, dtype=a.dtype, autotune=a.autotune)
     res = execute(a.dsl, a.input_file, a.parameter_file, a.output_file, **kw)
     if a.timings:                 # qxrun.jl:89-96 runs twice so the second table excludes warm-up
         res = execute(a.dsl, a.input_file, a.parameter_file, a.output_file, **kw)

@@ -119,3 +119,16 @@ def test_native_rejection_sampler(gpu, tmp_path):
     assert rc == 0, lib.qxb_last_error()
     res = load_jld2(out)
     assert n.value == 5 and abs(float(res["M"]) - 16.0) < 1e-4 and res["amplitudes"].dtype == np.complex64
+
+
+def test_execute_with_autotune(gpu, triple):
+    """execute(..., autotune=True): the measured choice among re-planned trees / register-tile knobs must not change
+    a single amplitude beyond rounding (every candidate is an exact re-association run by the same kernels)."""
+    from qxb200.execute import execute
+    prefix, cmds, data, bitstrings = triple
+    try:
+        res = execute(prefix + ".qx", dtype="c64", autotune=True)
+    finally:
+        os.environ.pop("QXB_MIN_LOB", None)
+    assert list(res.keys()) == bitstrings
+    assert rel_err(np.array(list(res.values())), orc.amplitudes(cmds, data, bitstrings), 9) < 1e-10
