@@ -7,9 +7,10 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.acti
 # 1. parity: the new GPU test files first (never run on hardware), then the whole suite
 timeout 600 python -m pytest tests/test_gpu_zfiles.py tests/test_gpu_zopen.py -q -m gpu -x > gpurun_out/r2a_pytest_new.log 2>&1; tail -5 gpurun_out/r2a_pytest_new.log
 timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/r2a_pytest_all.log 2>&1; tail -5 gpurun_out/r2a_pytest_all.log
-# 2. headline step: plan of the L1-aware planner model (default) against the r1p plan
-timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/r2a_bench_l1model.jsonl 2> gpurun_out/r2a_bench_l1model.err
-QXB_PLAN_L1_BW=0 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/r2a_bench_r1pmodel.jsonl 2> gpurun_out/r2a_bench_r1pmodel.err
+# 2. headline step: the bench's own measured choice (config.autotune lists all twelve candidates), then the two plans untuned
+timeout 500 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/r2a_bench_autotune.jsonl 2> gpurun_out/r2a_bench_autotune.err
+timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu --no-autotune > gpurun_out/r2a_bench_l1model.jsonl 2> gpurun_out/r2a_bench_l1model.err
+QXB_PLAN_L1_BW=0 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu --no-autotune > gpurun_out/r2a_bench_r1pmodel.jsonl 2> gpurun_out/r2a_bench_r1pmodel.err
 cp gpurun_out/op_profile_rqc_7x7_d20_c64_s4096.json gpurun_out/r2a_op_profile_r1pmodel.json 2>/dev/null
 # 3. register tiles for small nodes (QXB_MIN_LOB), per-op times and equality of the amplitudes
 PROBE_CONFIGS=lob timeout 500 python scripts/probe_variants.py > gpurun_out/r2a_probe_lob.log 2>&1; tail -12 gpurun_out/r2a_probe_lob.log
