@@ -242,9 +242,21 @@ def tune_plan(args, txt, data, w, g, dev, stream, world, dist, torch):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return [float("inf") if x >= 1e29 else x for x in t.tolist()]
 
-    best, report = autotune(cands, build, probe, reduce_times, rel_tol=1e-4 if w["dtype"] == "c32" else 1e-9)
-    del bits, out
+    tol = 1e-4 if w["dtype"] == "c32" else 1e-9
+    best, report = autotune(cands, build, probe, reduce_times, rel_tol=tol)
     tag, text, env = cands[best]
+    # second stage, on the winner only: the register budget of the K chunk (loads in flight per thread vs registers);
+    # 128 / 96 was 4.6 % faster than 96 / 64 on the r1p plan (profiles/r1p_summary.md) -- other plans may differ
+    stage2 = [(tag, text, env)] + [(f"{tag}/kc{m}", text, dict(env, QXB_KC_REGS_MULTI=str(m), QXB_KC_REGS_ONE=str(o)))
+                                   for m, o in ((96, 64), (160, 128))]
+    try:
+        best2, report2 = autotune(stage2, build, probe, reduce_times, rel_tol=tol)
+        if best2 > 0 and report2[best2].get("ms") is not None:
+            tag, text, env = stage2[best2]
+        report = report + report2[1:]
+    except Exception:                                        # noqa: BLE001  (keep the first-stage winner)
+        pass
+    del bits, out
     os.environ.update(env)                                   # in force for the timed graph, the profiled clone and the as-given run
     info = next(i for t, _, i in plans if tag.startswith(t + "/"))
     chosen = Graph.from_dsl(text, data, w["dtype"])
