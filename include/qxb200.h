@@ -54,6 +54,17 @@ typedef struct qxb_options {
     int32_t no_gemm;           /* 1 = never use the tiled GEMM kernel for GEMM-shaped nodes               */
     int32_t gemm_mode;         /* GEMM-shaped nodes: 0 = auto, 1 = SIMT FMA kernel only, 2 = tensor-core kernel
                                   (DMMA for ComplexF64, 3xTF32 for ComplexF32) wherever the tile shape allows */
+    /* ---- round 2: every kernel-selection knob is an option (0 = the library's default; the QXB_* environment
+     *      variables of round 1 are still read, as overrides for experiments, only where the option is 0) ---- */
+    int32_t row_programs;      /* 0 = auto: run a whole phase of the tree as ONE persistent kernel with the row's
+                                  intermediates in shared memory whenever they fit (csrc/qxb_rowprog.h); 1 = never  */
+    int32_t min_lob;           /* 5..8: thread bits contract_kernel keeps (register tiles for small nodes); 0 = 6  */
+    int32_t kc_regs_multi;     /* register budget of the K chunk, multi-chunk nodes; 0 = 160                      */
+    int32_t kc_regs_one;       /* register budget of the K chunk, single-chunk nodes; 0 = 128                     */
+    int32_t smem_tma;          /* 1 = TMA-staged contract_tma_kernel for broadcast-type nodes; 0 = off            */
+    int32_t row_min_tt_bits;   /* row programs: keep >= 2^n thread-tiles per node when choosing the register tile; 0 = 7 */
+    int32_t row_tile_regs;     /* row programs: registers for staged operands + accumulators; 0 = 100            */
+    int32_t row_ctas_per_sm;   /* row programs: resident CTAs per SM; 0 = as many as the arena allows, at most 2  */
 } qxb_options;
 
 /* library */
@@ -239,6 +250,10 @@ int  qxb_debug_mma_smem_bit(int dtype, int is_b, int tile_bits, int bit);
 /* test hook: raw array of the per-contraction launch templates (struct OpParams of csrc/qxb_kernels.cuh, one per
  * lowered op, pointers unset) for n_free batched variables; returns the bytes needed.  Host logic only. */
 int64_t qxb_debug_templates(qxb_graph* g, int n_free, void* buf, int64_t buflen);
+/* test hook: the row program (csrc/qxb_rowprog.h) of one phase (1 = block, 2 = chunk) for the batched variables in
+ * free_mask, serialised (layout in csrc/qxb_exec.cu) for tests/rowprog_emulator.py; returns the bytes needed.
+ * Host logic only. */
+int64_t qxb_debug_rowprog(qxb_graph* g, uint64_t free_mask, int phase, void* buf, int64_t buflen);
 /* test hook: the lookup3 checksum of HDF5 version-2 metadata, checked against Jenkins' published vectors */
 uint32_t qxb_debug_lookup3(const void* data, size_t n, uint32_t initval);
 

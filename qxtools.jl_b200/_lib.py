@@ -25,6 +25,7 @@ SYMBOLS = [
     "qxb_last_stats", "qxb_profile_dump", "qxb_debug_mma_smem_bit",
     "qxb_jld2_open", "qxb_jld2_close", "qxb_jld2_count", "qxb_jld2_info", "qxb_jld2_read", "qxb_jld2_write",
     "qxb_graph_load_jld2", "qxb_params_read", "qxb_execute_files", "qxb_debug_lookup3", "qxb_debug_templates",
+    "qxb_debug_rowprog",
 ]
 
 
@@ -38,7 +39,10 @@ class Options(C.Structure):
     _fields_ = [("hbm_budget_bytes", C.c_int64), ("amp_batch", C.c_int64),
                 ("profile", C.c_int32), ("no_cuda_graph", C.c_int32),
                 ("sum_at_root", C.c_int32), ("no_smem_stage", C.c_int32),
-                ("no_gemm", C.c_int32), ("gemm_mode", C.c_int32)]
+                ("no_gemm", C.c_int32), ("gemm_mode", C.c_int32),
+                ("row_programs", C.c_int32), ("min_lob", C.c_int32), ("kc_regs_multi", C.c_int32),
+                ("kc_regs_one", C.c_int32), ("smem_tma", C.c_int32), ("row_min_tt_bits", C.c_int32),
+                ("row_tile_regs", C.c_int32), ("row_ctas_per_sm", C.c_int32)]
 
 
 class Params(C.Structure):
@@ -114,6 +118,7 @@ def load():
         "qxb_graph_load_jld2": (i32, [p, cp, C.POINTER(i32)]),
         "qxb_params_read": (i32, [cp, C.POINTER(Params), p, i64]),
         "qxb_debug_templates": (i64, [p, i32, p, i64]),
+        "qxb_debug_rowprog": (i64, [p, C.c_uint64, i32, p, i64]),
         "qxb_debug_lookup3": (C.c_uint32, [p, C.c_size_t, C.c_uint32]),
         "qxb_execute_files": (i32, [cp, cp, cp, cp, i32, i64, i64, i32, pi64, C.POINTER(C.c_double)]),
     }

@@ -22,6 +22,7 @@
 #include "../../include/qxb200.h"
 #include "qxb_ir.h"
 #include "qxb_kernels.cuh"
+#include "qxb_rowplan.h"
 
 using namespace qxb;
 
@@ -85,6 +86,16 @@ struct Variant {
     std::vector<GemmParams> gtmpl;       // per op: tiled-GEMM parameters (valid when gemm_tmb > 0)
     std::vector<int> gemm_tmb, gemm_tnb;
     std::vector<OpProfile> prof;
+    // row programs (qxb_rowprog.h): the chunk phase as one persistent kernel with the row's intermediates in shared
+    // memory, the block phase as a single-CTA program; device copies of the descriptors per set of fixed values
+    bool use_rows = false;
+    RowProgramHost rp_block, rp_chunk;
+    struct RowDev {
+        DevBuf ops_block, units_block, ops_chunk, units_chunk, leaves;
+        const void *block_base = nullptr, *const_base = nullptr;     // arena bases the pointers were resolved against
+    };
+    std::map<std::vector<int64_t>, RowDev> rowdev;
+    OpProfile prof_rows, prof_block_rows;                // profile mode: the two fused launches
 };
 
 struct EventPair { cudaEvent_t a, b; int variant, op; };
@@ -123,7 +134,13 @@ struct qxb_graph {
     size_t es() const { return dtype == QXB_C32 ? 8 : 16; }
     ~qxb_graph() {
         for (auto& kv : leafbuf) kv.second.release();
-        for (auto& kv : variants) { kv.second->const_arena.release(); kv.second->outleaf_desc.release(); }
+        for (auto& kv : variants) {
+            kv.second->const_arena.release(); kv.second->outleaf_desc.release();
+            for (auto& rd : kv.second->rowdev) {
+                rd.second.ops_block.release(); rd.second.units_block.release(); rd.second.ops_chunk.release();
+                rd.second.units_chunk.release(); rd.second.leaves.release();
+            }
+        }
         block_arena.release(); chunk_arena.release(); acc.release(); d_bits.release(); d_out.release();
         for (auto& e : events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         drop_step_graphs();
@@ -203,12 +220,19 @@ char* tensor_ptr(const RunCtx& c, const LTensor& T) {
 
 // Split the bits of C into thread bits / register-tile bits / hi bits and compose
 // the address maps accordingly (see contract_kernel).
-void build_templates(Variant& v, int dtype) {
-    // register budget of the K chunk (overridable: QXB_KC_REGS_MULTI / QXB_KC_REGS_ONE).  128 / 96 measured 4.6 % faster
-    // than 96 / 64 on the tree-searched 7x7 program (more loads in flight per thread; profiles/r1p_summary.md)
-    const int kc_regs_multi = [] { const char* e = getenv("QXB_KC_REGS_MULTI"); return e ? atoi(e) : 128; }();
-    const int kc_regs_one = [] { const char* e = getenv("QXB_KC_REGS_ONE"); return e ? atoi(e) : 96; }();
-    const int min_lob = [] { const char* e = getenv("QXB_MIN_LOB"); return e ? std::min(8, std::max(5, atoi(e))) : 8; }();
+// a knob: the option if set, else the round-1 environment variable (experiments), else the default
+int knob(int opt, const char* env, int dflt) {
+    if (opt > 0) return opt;
+    const char* e = getenv(env);
+    return e ? atoi(e) : dflt;
+}
+
+void build_templates(Variant& v, int dtype, const qxb_options& opts) {
+    // register budget of the K chunk: 160 / 128 and min_lob 6 are what the measured choice of bench.py picked on two
+    // separate B200s (BENCH_r01.json config.autotune: l1bw14/lob6/kc160; 128 / 96 was 4.6 % faster than 96 / 64 before)
+    const int kc_regs_multi = knob(opts.kc_regs_multi, "QXB_KC_REGS_MULTI", 160);
+    const int kc_regs_one = knob(opts.kc_regs_one, "QXB_KC_REGS_ONE", 128);
+    const int min_lob = std::min(8, std::max(5, knob(opts.min_lob, "QXB_MIN_LOB", 6)));
     v.tmpl.resize(v.L.ops.size());
     v.gtmpl.resize(v.L.ops.size());
     v.gemm_tmb.assign(v.L.ops.size(), 0); v.gemm_tnb.assign(v.L.ops.size(), 0);
@@ -501,7 +525,7 @@ Node contract_node(const RunCtx& c, int i) {
             sf = contract_smem_func(g->dtype, p.kc, p.ma, p.nb, p.kc == p.nK);
         // EXPERIMENT QXB_SMEM_TMA=1 (never run on hardware yet, see contract_tma_kernel): operand rows through 1-D TMA
         // bulk copies into a ring of stages; QXB_SMEM_TMA_RATIO = minimum |C| / (|A| + |B|)
-        const int smem_tma = [] { const char* e = getenv("QXB_SMEM_TMA"); return e ? atoi(e) : 0; }();
+        const int smem_tma = knob(g->opts.smem_tma, "QXB_SMEM_TMA", 0);
         const void* tf = nullptr;
         if (smem_tma && !g->opts.no_smem_stage && p.lob == 8 && p.ma + p.nb >= 1 && A.lay.size() && B.lay.size() &&
             (A.amp || B.amp) && p.U >= g_num_sms &&
@@ -567,13 +591,79 @@ void run_const_phase(const RunCtx& c) {
     CUDA_OK(cudaGetLastError());
 }
 
+
+// ------------------------------------------------------------------ row programs
+// Host part: levels, units, arena plan, descriptors (qxb_rowplan.cpp).  Used when the saved tensor is a scalar,
+// the root is produced in the chunk phase and the live set of one bitstring row fits shared memory.
+void build_row_programs(qxb_graph* g, Variant& v) {
+    v.use_rows = false;
+    if (knob(0, "QXB_ROWPROG", 1) == 0 || g->opts.row_programs == 1) return;
+    for (const auto& rm : v.L.root_modes) if (rm.nbits > 0) return;     // tensor-valued save: per-op path
+    RowPlanOptions o;
+    o.min_tt_bits = knob(g->opts.row_min_tt_bits, "QXB_ROW_MIN_TT", 7);
+    o.tile_reg_budget = knob(g->opts.row_tile_regs, "QXB_ROW_TILE_REGS", 100);
+    o.alap = knob(0, "QXB_ROW_ALAP", 1) != 0;
+    o.max_tile_bits = knob(0, "QXB_ROW_MAX_TILE", 4);
+    const long long slot_bytes = kRowWarps * (long long)sizeof(RowOpHot);
+    o.max_arena_bytes = 227 * 1024 - slot_bytes;
+    v.rp_chunk = build_row_program(v.L, PH_CHUNK, g->dtype, o);
+    if (!v.rp_chunk.ok) return;
+    bool has_block = false;
+    for (const LOp& op : v.L.ops) has_block |= op.phase == PH_BLOCK;
+    if (has_block) {
+        v.rp_block = build_row_program(v.L, PH_BLOCK, g->dtype, o);
+        if (!v.rp_block.ok) return;
+    }
+    v.use_rows = true;
+}
+
+// Device copies of the descriptors with the pointers of this block resolved (fixed slice values, arena bases).
+Variant::RowDev& row_device_tables(const RunCtx& c) {
+    Variant& v = *c.v;
+    qxb_graph* g = c.g;
+    const int k = (int)g->prog.vars.size();
+    std::vector<int64_t> key(k, 0);
+    for (int i = 0; i < k; ++i) if (!((v.L.free_mask >> i) & 1ull)) key[i] = c.fixed_vals[i];
+    Variant::RowDev& rd = v.rowdev[key];
+    if (rd.ops_chunk.p && rd.block_base == g->block_arena.p && rd.const_base == v.const_arena.p) return rd;
+    rd.block_base = g->block_arena.p; rd.const_base = v.const_arena.p;
+    auto fixed_off = [&](const LTensor& T) {
+        long long off = 0;
+        for (auto& f : T.fixed) off += (long long)c.fixed_vals[f.first] << f.second;
+        return off;
+    };
+    auto resolve = [&](const RowProgramHost& rp, DevBuf& d_ops, DevBuf& d_units) {
+        std::vector<RowOp> ops = rp.ops;
+        for (size_t j = 0; j < ops.size(); ++j) {
+            RowOp& d = ops[j];
+            const LTensor &A = v.L.tensors[rp.ref_a[j]], &B = v.L.tensors[rp.ref_b[j]], &C = v.L.tensors[rp.ref_c[j]];
+            if (rp.in_arena_a[j]) d.oA ^= (int)fixed_off(A); else { d.gA = (unsigned long long)tensor_ptr(c, A); d.oA = 0; }
+            if (rp.in_arena_b[j]) d.oB ^= (int)fixed_off(B); else { d.gB = (unsigned long long)tensor_ptr(c, B); d.oB = 0; }
+            if (!rp.in_arena_c[j]) { d.gC = (unsigned long long)tensor_ptr(c, C); d.oC = 0; }
+            d.rsA = d.rsB = d.rsC = 0;                       // every global tensor of a row program is shared by the rows
+        }
+        d_ops.reserve(std::max<size_t>(ops.size(), 1) * sizeof(RowOp));
+        d_units.reserve(std::max<size_t>(rp.units.size(), 1) * sizeof(RowUnit));
+        CUDA_OK(cudaMemcpy(d_ops.p, ops.data(), ops.size() * sizeof(RowOp), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(d_units.p, rp.units.data(), rp.units.size() * sizeof(RowUnit), cudaMemcpyHostToDevice));
+    };
+    if (v.rp_block.ok) resolve(v.rp_block, rd.ops_block, rd.units_block);
+    resolve(v.rp_chunk, rd.ops_chunk, rd.units_chunk);
+    rd.leaves.reserve(std::max<size_t>(v.rp_chunk.leaves.size(), 1) * sizeof(RowLeaf));
+    if (!v.rp_chunk.leaves.empty())
+        CUDA_OK(cudaMemcpy(rd.leaves.p, v.rp_chunk.leaves.data(), v.rp_chunk.leaves.size() * sizeof(RowLeaf), cudaMemcpyHostToDevice));
+    return rd;
+}
+
+
 Variant* get_variant(qxb_graph* g, uint64_t free_mask) {
     auto it = g->variants.find(free_mask);
     if (it != g->variants.end()) return it->second.get();
     std::unique_ptr<Variant> v(new Variant());
     v->L = lower(g->prog, free_mask, !g->opts.sum_at_root);
     plan_memory(v->L);
-    build_templates(*v, g->dtype);
+    build_templates(*v, g->dtype, g->opts);
+    build_row_programs(g, *v);
     const size_t es = g->es();
     v->const_arena.reserve(std::max<int64_t>(v->L.const_elems, 2) * es);
     std::vector<OutLeafDesc> descs;
@@ -680,7 +770,13 @@ StepPlan prepare_step(qxb_graph* g, std::vector<Block> blocks, int64_t n_amp) {
         Variant* v = get_variant(g, blk.free_mask);
         sp.variants.push_back(v);
         const int64_t block_bytes = std::max<int64_t>(v->L.block_elems, 2) * es;
-        const int64_t per_amp = std::max<int64_t>(v->L.chunk_elems_per_amp, 2) * es;
+        // a row program keeps the chunk phase in shared memory: no HBM workspace per bitstring
+        const int64_t per_amp = v->use_rows ? 0 : std::max<int64_t>(v->L.chunk_elems_per_amp, 2) * es;
+        if (v->use_rows) {
+            max_block = std::max(max_block, block_bytes);
+            g->stats.workspace_bytes = std::max<int64_t>(g->stats.workspace_bytes, block_bytes + (int64_t)v->const_arena.bytes);
+            continue;
+        }
         const int64_t fit = (budget - block_bytes) / per_amp;
         if (fit < 1)
             throw Error(QXB_ERR_MEM, "workspace for one bitstring (" + std::to_string(block_bytes + per_amp) +
@@ -702,6 +798,53 @@ StepPlan prepare_step(qxb_graph* g, std::vector<Block> blocks, int64_t n_amp) {
     return sp;
 }
 
+
+// The two fused launches of a block: op = -3 (block phase, one CTA over global memory), op = -2 (chunk phase, one CTA
+// per bitstring row at a time, intermediates in shared memory).
+constexpr int kOpRowChunk = -2, kOpRowBlock = -3;
+
+Node row_node(const RunCtx& c, Variant::RowDev& rd, bool chunk, const uint8_t* d_bits, int64_t a0) {
+    qxb_graph* g = c.g;
+    Variant& v = *c.v;
+    const RowProgramHost& rp = chunk ? v.rp_chunk : v.rp_block;
+    RowLaunch P;
+    memset(&P, 0, sizeof(P));
+    P.ops = (const RowOp*)(chunk ? rd.ops_chunk.p : rd.ops_block.p);
+    P.units = (const RowUnit*)(chunk ? rd.units_chunk.p : rd.units_block.p);
+    P.leaves = (const RowLeaf*)rd.leaves.p;
+    P.bits = d_bits;
+    P.acc = chunk ? (double*)g->acc.p : nullptr;
+    P.amp0 = chunk ? a0 : 0;
+    P.n_rows = chunk ? c.n : 1;
+    P.scale = v.L.root_scale;
+    P.n_levels = rp.n_levels;
+    P.n_leaves = chunk ? (int)rp.leaves.size() : 0;
+    P.n_outputs = g->prog.n_outputs;
+    P.root_off = rp.root_off; P.root_span = rp.root_span;
+    for (int i = 0; i <= rp.n_levels; ++i) P.level_start[i] = rp.level_start[i];
+    Node n;
+    n.func = rowprog_func(g->dtype);
+    n.block = dim3(kRowThreads);
+    n.smem = kRowWarps * sizeof(RowOpHot) + (chunk ? (size_t)rp.arena_elems * g->es() : 0);
+    static std::set<const void*> configured;
+    if (!configured.count(n.func)) {
+        CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured.insert(n.func);
+    }
+    int per_sm = 1;
+    if (chunk) {
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, n.func, kRowThreads, n.smem));
+        per_sm = std::max(1, std::min(per_sm, knob(g->opts.row_ctas_per_sm, "QXB_ROW_CTAS", 2)));
+    }
+    n.grid = dim3(chunk ? (unsigned)std::max<long long>(1, std::min<long long>(c.n, (long long)g_num_sms * per_sm)) : 1u);
+    n.arg(P);
+    n.variant = c.variant_key; n.op = chunk ? kOpRowChunk : kOpRowBlock;
+    const double rows = chunk ? (double)c.n : 1.0;
+    n.flops = rp.flops_per_row * rows;
+    n.bytes = (double)g->es() * (rp.elems_per_row_amp * rows + rp.elems_shared);   // same accounting as contract_node
+    return n;
+}
+
 std::vector<Node> build_step(qxb_graph* g, const StepPlan& sp, const uint8_t* d_bits, int64_t n_amp, void* d_out) {
     std::vector<Node> nodes;
     {
@@ -714,6 +857,24 @@ std::vector<Node> build_step(qxb_graph* g, const StepPlan& sp, const uint8_t* d_
         Variant* v = sp.variants[bi];
         Lowered& L = v->L;
         RunCtx c{g, v, v->key, blk.vals.data(), 1};
+        if (v->use_rows) {
+            // the whole block as two launches: block-phase program (one CTA), then one persistent kernel that takes
+            // every bitstring row through the chunk phase in shared memory and adds the root into its accumulator
+            Variant::RowDev& rd = row_device_tables(c);
+            int after = sink;
+            if (v->rp_block.ok) {
+                Node b = row_node(c, rd, false, d_bits, 0);
+                b.deps.push_back(sink);
+                after = (int)nodes.size();
+                nodes.push_back(std::move(b));
+            }
+            c.n = n_amp;
+            Node r = row_node(c, rd, true, d_bits, 0);
+            r.deps.push_back(after);
+            sink = (int)nodes.size();
+            nodes.push_back(std::move(r));
+            continue;
+        }
         std::vector<int> node_of(L.ops.size(), -1);   // block-phase ops of this block
         for (size_t i = 0; i < L.ops.size(); ++i) {
             if (L.ops[i].phase != PH_BLOCK) continue;
@@ -803,7 +964,9 @@ std::vector<Node> build_step(qxb_graph* g, const StepPlan& sp, const uint8_t* d_
 void account(qxb_graph* g, const std::vector<Node>& nodes) {
     for (const Node& n : nodes) {
         if (n.func) g->stats.kernel_launches++;
-        if (n.op >= 0) { g->stats.contract_launches++; g->stats.flops += n.flops; g->stats.bytes += n.bytes; }
+        if (n.op >= 0 || n.op == kOpRowChunk || n.op == kOpRowBlock) {
+            g->stats.contract_launches++; g->stats.flops += n.flops; g->stats.bytes += n.bytes;
+        }
     }
 }
 
@@ -829,10 +992,13 @@ void launch_serial(qxb_graph* g, const std::vector<Node>& nodes) {
         if (n.op >= 0 && !ncu_ops().empty())
             for (auto& kv : g->variants)
                 if (kv.second->key == n.variant && ncu_ops().count(kv.second->L.ops[n.op].name)) bracket = true;
+        if ((n.op == kOpRowChunk && ncu_ops().count("ROWPROG_CHUNK")) || (n.op == kOpRowBlock && ncu_ops().count("ROWPROG_BLOCK")))
+            bracket = true;
         if (bracket) { CUDA_OK(cudaStreamSynchronize(st)); cudaProfilerStart(); }
         struct Stop { bool on; cudaStream_t s; ~Stop() { if (on) { cudaStreamSynchronize(s); cudaProfilerStop(); } } } stop{bracket, st};
         EventPair* ev = nullptr;
-        if (g->opts.profile && n.op >= 0) {
+        const bool fused = n.op == kOpRowChunk || n.op == kOpRowBlock;
+        if (g->opts.profile && (n.op >= 0 || fused)) {
             if (g->events_used == g->events.size()) {
                 EventPair e{};
                 CUDA_OK(cudaEventCreate(&e.a)); CUDA_OK(cudaEventCreate(&e.b));
@@ -847,7 +1013,8 @@ void launch_serial(qxb_graph* g, const std::vector<Node>& nodes) {
             CUDA_OK(cudaEventRecord(ev->b, st));
             for (auto& kv : g->variants)
                 if (kv.second->key == n.variant) {
-                    OpProfile& pr = kv.second->prof[n.op];
+                    OpProfile& pr = n.op == kOpRowChunk ? kv.second->prof_rows : n.op == kOpRowBlock ? kv.second->prof_block_rows
+                                                                                                     : kv.second->prof[n.op];
                     pr.flops += n.flops; pr.bytes += n.bytes; pr.launches++;
                 }
         }
@@ -900,7 +1067,10 @@ cudaGraphExec_t instantiate(const std::vector<Node>& nodes) {
 void run_blocks(qxb_graph* g, std::vector<Block> blocks, StepKey key, const uint8_t* d_bits, int64_t n_amp, void* d_out) {
     g->stats = qxb_stats{};
     g->events_used = 0;
-    for (auto& kv : g->variants) kv.second->prof.assign(kv.second->L.ops.size(), OpProfile{});
+    for (auto& kv : g->variants) {
+        kv.second->prof.assign(kv.second->L.ops.size(), OpProfile{});
+        kv.second->prof_rows = OpProfile{}; kv.second->prof_block_rows = OpProfile{};
+    }
     if (n_amp == 0) return;
     cudaStream_t st = stream();
     key.st = st;
@@ -960,8 +1130,12 @@ void collect_profile(qxb_graph* g) {
         EventPair& e = g->events[i];
         float ms = 0;
         if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
-            for (auto& kv : g->variants)
-                if (kv.second->key == e.variant && e.op < (int)kv.second->prof.size()) kv.second->prof[e.op].ms += ms;
+            for (auto& kv : g->variants) {
+                if (kv.second->key != e.variant) continue;
+                if (e.op == kOpRowChunk) kv.second->prof_rows.ms += ms;
+                else if (e.op == kOpRowBlock) kv.second->prof_block_rows.ms += ms;
+                else if (e.op >= 0 && e.op < (int)kv.second->prof.size()) kv.second->prof[e.op].ms += ms;
+            }
         }
     }
     g->events_used = 0;
@@ -1189,7 +1363,7 @@ int64_t qxb_debug_templates(qxb_graph* g, int n_free, void* buf, int64_t buflen)
         Variant v;
         v.L = lower(g->prog, low_mask(n_free < 0 || n_free > k ? k : n_free), !g->opts.sum_at_root);
         plan_memory(v.L);
-        build_templates(v, g->dtype);
+        build_templates(v, g->dtype, g->opts);
         need = (int64_t)(v.tmpl.size() * sizeof(OpParams));
         if (buf && buflen >= need && need) memcpy(buf, v.tmpl.data(), (size_t)need);
     });
@@ -1401,11 +1575,66 @@ int qxb_profile_dump(qxb_graph* g, const char* path) {
                         pr.launches, pr.flops, pr.bytes, pr.ms);
                 first = false;
             }
+            // the fused launches of a row-program variant: one pseudo-op per phase (the sums over the ops they cover)
+            const OpProfile* fp[2] = {&v.prof_block_rows, &v.prof_rows};
+            const char* fname[2] = {"ROWPROG_BLOCK", "ROWPROG_CHUNK"};
+            for (int q = 0; q < 2; ++q) {
+                if (fp[q]->launches == 0) continue;
+                const RowProgramHost& rp = q ? v.rp_chunk : v.rp_block;
+                fprintf(f, "%s{\"name\":\"%s\",\"phase\":%d,\"fused_ops\":%d,\"levels\":%d,\"units\":%d,\"arena_bytes\":%lld,"
+                           "\"launches\":%lld,\"flops\":%.6g,\"bytes\":%.6g,\"ms\":%.6g}",
+                        first ? "" : ",", fname[q], q ? 2 : 1, (int)rp.ops.size(), rp.n_levels, (int)rp.units.size(),
+                        (long long)rp.arena_elems * (long long)g->es(), fp[q]->launches, fp[q]->flops, fp[q]->bytes, fp[q]->ms);
+                first = false;
+            }
             fprintf(f, "]}");
         }
         fprintf(f, "]}\n");
         fclose(f);
     });
+}
+
+// test hook: the row program of one phase (qxb_rowprog.h) exactly as the executor would build it, serialised for
+// tests/rowprog_emulator.py.  Pure host logic.  Layout: int32 header[8] = {ok, n_ops, n_units, n_levels, n_leaves,
+// arena_elems, root_off, root_span}, int32 level_start[n_levels + 1], RowOp ops[n_ops], RowUnit units[n_units],
+// RowLeaf leaves[n_leaves], int32 lop / ref_a / ref_b / ref_c / in_arena_a / in_arena_b / in_arena_c [n_ops] each.
+int64_t qxb_debug_rowprog(qxb_graph* g, uint64_t free_mask, int phase, void* buf, int64_t buflen) {
+    int64_t need = 0;
+    int rc = guard([&] {
+        if (!g) throw Error(QXB_ERR_ARG, "null graph");
+        if (phase != PH_BLOCK && phase != PH_CHUNK) throw Error(QXB_ERR_ARG, "phase must be 1 (block) or 2 (chunk)");
+        ensure_analysed(g);
+        Lowered L = lower(g->prog, free_mask, !g->opts.sum_at_root);
+        plan_memory(L);
+        RowPlanOptions o;
+        o.min_tt_bits = knob(g->opts.row_min_tt_bits, "QXB_ROW_MIN_TT", 7);
+        o.tile_reg_budget = knob(g->opts.row_tile_regs, "QXB_ROW_TILE_REGS", 100);
+        o.alap = knob(0, "QXB_ROW_ALAP", 1) != 0;
+        o.max_tile_bits = knob(0, "QXB_ROW_MAX_TILE", 4);
+        o.max_arena_bytes = 227 * 1024 - kRowWarps * (long long)sizeof(RowOpHot);
+        RowProgramHost rp = build_row_program(L, (Phase)phase, g->dtype, o);
+        if (!rp.ok) { set_last_error(rp.why); }
+        std::vector<char> out;
+        auto put = [&](const void* p, size_t n) { const char* c = (const char*)p; out.insert(out.end(), c, c + n); };
+        const int n_ops = rp.ok ? (int)rp.ops.size() : 0;
+        int32_t hdr[8] = {rp.ok ? 1 : 0, n_ops, rp.ok ? (int)rp.units.size() : 0, rp.ok ? rp.n_levels : 0,
+                          rp.ok ? (int)rp.leaves.size() : 0, rp.arena_elems, rp.root_off, rp.root_span};
+        put(hdr, sizeof(hdr));
+        if (rp.ok) {
+            std::vector<int32_t> ls(rp.level_start.begin(), rp.level_start.end());
+            put(ls.data(), ls.size() * 4);
+            put(rp.ops.data(), rp.ops.size() * sizeof(RowOp));
+            put(rp.units.data(), rp.units.size() * sizeof(RowUnit));
+            put(rp.leaves.data(), rp.leaves.size() * sizeof(RowLeaf));
+            auto puti = [&](const std::vector<int>& v) { std::vector<int32_t> w(v.begin(), v.end()); put(w.data(), w.size() * 4); };
+            auto putc = [&](const std::vector<char>& v) { std::vector<int32_t> w(v.begin(), v.end()); put(w.data(), w.size() * 4); };
+            puti(rp.lop); puti(rp.ref_a); puti(rp.ref_b); puti(rp.ref_c);
+            putc(rp.in_arena_a); putc(rp.in_arena_b); putc(rp.in_arena_c);
+        }
+        need = (int64_t)out.size();
+        if (buf && buflen >= need) memcpy(buf, out.data(), out.size());
+    });
+    return rc == QXB_OK ? need : rc;
 }
 
 // test hook: shared-memory layout table of the tensor-core GEMM kernels (tests/test_mma_layout.py)

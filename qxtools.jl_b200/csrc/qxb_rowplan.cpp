@@ -1,0 +1,262 @@
+// qxb200 -- host-side builder of row programs (qxb_rowprog.h): turns one phase of a lowered program into
+// dependency levels, warp-sized work units, a size-aligned shared-memory arena plan and per-op descriptors.
+// Pure host code (no CUDA calls): tests replay the descriptors on the CPU (tests/rowprog_emulator.py).
+#include "qxb_rowplan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+#include "../../include/qxb200.h"
+
+namespace qxb {
+
+namespace {
+
+// merge (src bit, dst bit) pairs, sorted by src, into (src, dst, len) runs
+int merge_runs(const std::vector<std::pair<int, int>>& bits, RSeg* out, int cap) {
+    int n = 0;
+    for (auto& b : bits) {
+        if (n > 0 && out[n - 1].src + out[n - 1].len == b.first && out[n - 1].dst + out[n - 1].len == b.second) {
+            out[n - 1].len = (unsigned char)(out[n - 1].len + 1);
+        } else {
+            if (n == cap) return -1;
+            out[n++] = RSeg{(unsigned char)b.first, (unsigned char)b.second, 1, 0};
+        }
+    }
+    return n;
+}
+
+// registers of a tile variant; must equal TileRegs<> in qxb_rowprog.cu
+int tile_regs(int dtype, int ma, int nb, int kc) {
+    const int rp = dtype == QXB_C32 ? 2 : 4;
+    return rp * (((1 << ma) + (1 << nb)) * (1 << kc) + (1 << (ma + nb)));
+}
+
+struct Interval { int off, size, until; };     // live until level `until` inclusive
+
+// lowest offset that is a multiple of `size` and overlaps no live interval
+int aligned_alloc(std::vector<Interval>& live, int size, int until) {
+    for (int off = 0;; off += size) {
+        bool clash = false;
+        for (const Interval& iv : live)
+            if (iv.off < off + size && off < iv.off + iv.size) { clash = true; break; }
+        if (!clash) { live.push_back(Interval{off, size, until}); return off; }
+    }
+}
+
+}  // namespace
+
+RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const RowPlanOptions& o) {
+    RowProgramHost rp;
+    rp.phase = phase;
+    auto fail = [&](const std::string& why) { rp.ok = false; rp.why = why; return rp; };
+    // ---- ops of the phase, producers, levels
+    std::vector<int> sel;                                   // indices into L.ops
+    for (size_t i = 0; i < L.ops.size(); ++i) if (L.ops[i].phase == phase) sel.push_back((int)i);
+    if (sel.empty()) return fail("no op in this phase");
+    if (sel.size() > 60000) return fail("too many ops");
+    std::map<int, int> local_of_lop;                        // L.ops index -> local index
+    for (size_t j = 0; j < sel.size(); ++j) local_of_lop[sel[j]] = (int)j;
+    const int n = (int)sel.size();
+    std::map<int, int> producer;                            // LTensor -> local op
+    for (int j = 0; j < n; ++j) producer[L.ops[sel[j]].c] = j;
+    std::vector<std::vector<int>> deps(n), users(n);
+    for (int j = 0; j < n; ++j) {
+        const LOp& op = L.ops[sel[j]];
+        std::vector<int> d;
+        if (phase == PH_CHUNK) {
+            // the arena is re-planned here: only true data dependencies count
+            for (int t : {op.a, op.b}) { auto it = producer.find(t); if (it != producer.end()) d.push_back(it->second); }
+        } else {
+            // tensors stay where plan_memory put them: keep its write-after-read edges too
+            for (int dd : op.deps) { auto it = local_of_lop.find(dd); if (it != local_of_lop.end()) d.push_back(it->second); }
+        }
+        std::sort(d.begin(), d.end()); d.erase(std::unique(d.begin(), d.end()), d.end());
+        for (int x : d) { if (x >= j) return fail("ops not in topological order"); users[x].push_back(j); }
+        deps[j] = d;
+    }
+    std::vector<int> level(n, 0);
+    int n_levels = 0;
+    for (int j = 0; j < n; ++j) {
+        for (int d : deps[j]) level[j] = std::max(level[j], level[d] + 1);
+        n_levels = std::max(n_levels, level[j] + 1);
+    }
+    if (o.alap) {
+        // as late as possible: small early nodes run beside the big ones and their results live shorter
+        for (int j = n - 1; j >= 0; --j) {
+            if (users[j].empty()) { level[j] = std::max(level[j], 0); continue; }
+            int lv = n_levels;
+            for (int u : users[j]) lv = std::min(lv, level[u] - 1);
+            level[j] = std::max(level[j], lv);
+        }
+    }
+    if (n_levels > kRowMaxLevels) return fail("more than " + std::to_string(kRowMaxLevels) + " levels");
+
+    // ---- arena plan (chunk phase): tensors are powers of two, aligned to their size
+    std::map<int, int> arena_off;                           // LTensor -> element offset
+    if (phase == PH_CHUNK) {
+        auto last_level = [&](int t) {
+            int lv = -1;
+            for (int j = 0; j < n; ++j) if (L.ops[sel[j]].a == t || L.ops[sel[j]].b == t) lv = std::max(lv, level[j]);
+            return lv;
+        };
+        std::vector<Interval> live;
+        for (int t : L.output_leaves) {
+            const LTensor& T = L.tensors[t];
+            if (T.span_bits > 16) return fail("output leaf too large");
+            const int lu = last_level(t);
+            if (lu < 0) continue;                               // unused leaf
+            arena_off[t] = aligned_alloc(live, 1 << T.span_bits, lu);
+            rp.leaves.push_back(RowLeaf{arena_off[t], T.span_bits, (int)T.out_idx});
+        }
+        int peak = 0;
+        for (const Interval& iv : live) peak = std::max(peak, iv.off + iv.size);
+        for (int lv = 0; lv < n_levels; ++lv) {
+            live.erase(std::remove_if(live.begin(), live.end(), [&](const Interval& iv) { return iv.until < lv; }), live.end());
+            std::vector<int> here;
+            for (int j = 0; j < n; ++j) if (level[j] == lv) here.push_back(j);
+            std::sort(here.begin(), here.end(), [&](int x, int y) { return L.ops[sel[x]].nC > L.ops[sel[y]].nC; });
+            for (int j : here) {
+                const LOp& op = L.ops[sel[j]];
+                if (op.nC > 16) return fail("intermediate larger than 2^16 elements");
+                const int t = op.c;
+                int until = last_level(t);
+                if (t == L.root || until < 0) until = n_levels;       // the root (and anything unread) lives to the end
+                arena_off[t] = aligned_alloc(live, 1 << op.nC, until);
+                peak = std::max(peak, arena_off[t] + (1 << op.nC));
+            }
+        }
+        rp.arena_elems = peak;
+        if (!arena_off.count(L.root)) return fail("the root is not produced in the chunk phase");
+        rp.root_off = arena_off[L.root];
+        rp.root_span = L.tensors[L.root].span_bits;
+        const size_t es = dtype == QXB_C32 ? 8 : 16;
+        if ((size_t)peak * es > (size_t)o.max_arena_bytes) return fail("row arena of " + std::to_string((size_t)peak * es) + " bytes exceeds the budget");
+    }
+
+    // ---- per-op descriptors
+    rp.ops.resize(n); rp.ref_a.resize(n); rp.ref_b.resize(n); rp.ref_c.resize(n); rp.lop.resize(n);
+    rp.in_arena_a.assign(n, 0); rp.in_arena_b.assign(n, 0); rp.in_arena_c.assign(n, 0);
+    std::vector<double> unit_cost(n, 0);
+    std::vector<int> n_units(n, 1);
+    for (int j = 0; j < n; ++j) {
+        const LOp& op = L.ops[sel[j]];
+        RowOp& d = rp.ops[j];
+        memset(&d, 0, sizeof(d));
+        rp.lop[j] = sel[j]; rp.ref_a[j] = op.a; rp.ref_b[j] = op.b; rp.ref_c[j] = op.c;
+        const int nC = op.nC, nK = op.nK;
+        if (nC > 16 || nK > 16) return fail("op too large for a row program");
+        std::vector<int> mapA(nC, -1), mapB(nC, -1);
+        for (auto& s : op.segA) for (int b = 0; b < s.len; ++b) mapA[s.src + b] = s.dst + b;
+        for (auto& s : op.segB) for (int b = 0; b < s.len; ++b) mapB[s.src + b] = s.dst + b;
+        std::vector<int> kposA(nK, -1), kposB(nK, -1);
+        for (auto& s : op.segKA) for (int b = 0; b < s.len; ++b) kposA[s.src + b] = s.dst + b;
+        for (auto& s : op.segKB) for (int b = 0; b < s.len; ++b) kposB[s.src + b] = s.dst + b;
+        for (int b = 0; b < nC; ++b) if (mapA[b] > 15 || mapB[b] > 15) return fail("operand wider than 2^16 elements");
+        for (int b = 0; b < nK; ++b) if (kposA[b] > 15 || kposB[b] > 15) return fail("operand wider than 2^16 elements");
+        // register tile: highest M-only / N-only bits, alternating sides, while >= 2^min_tt_bits thread-tiles remain
+        std::vector<int> mcand, ncand, mbits, nbits;
+        for (int b = nC - 1; b >= 0; --b) {
+            if (mapA[b] >= 0 && mapB[b] < 0) mcand.push_back(b);
+            else if (mapB[b] >= 0 && mapA[b] < 0) ncand.push_back(b);
+        }
+        while ((int)(mbits.size() + nbits.size()) < o.max_tile_bits && nC - (int)(mbits.size() + nbits.size()) - 1 >= o.min_tt_bits) {
+            const bool can_m = mbits.size() < 2 && mbits.size() < mcand.size();
+            const bool can_n = nbits.size() < 2 && nbits.size() < ncand.size();
+            if (!can_m && !can_n) break;
+            if (can_m && (!can_n || mbits.size() <= nbits.size())) mbits.push_back(mcand[mbits.size()]);
+            else nbits.push_back(ncand[nbits.size()]);
+        }
+        int ma = (int)mbits.size(), nb = (int)nbits.size();
+        int ntt = nC - ma - nb;
+        RowOpHot& h = d.hot;
+        if (ntt < 5) {                                       // fewer than 32 thread-tiles: lanes split K instead
+            mbits.clear(); nbits.clear(); ma = nb = 0; ntt = nC;
+        }
+        std::sort(mbits.begin(), mbits.end()); std::sort(nbits.begin(), nbits.end());
+        int kc = 0;
+        if (ntt >= 5) {
+            kc = std::min(nK, 2);
+            while (kc > 0 && tile_regs(dtype, ma, nb, kc) > std::min(100, o.tile_reg_budget)) --kc;
+            if (tile_regs(dtype, ma, nb, kc) > 100) return fail("no tile variant");
+            h.kind = (uint8_t)row_tile_kind(ma, nb, kc, 0);
+            h.ks = 0;
+            n_units[j] = 1 << (ntt - 5);
+        } else {
+            h.kind = kRowKindKred;
+            h.ks = (uint8_t)std::min(5 - ntt, nK);
+            n_units[j] = 1;
+        }
+        h.nK = (uint8_t)nK; h.kc = (uint8_t)kc; h.ma = (uint8_t)ma; h.nb = (uint8_t)nb; h.ntt = (uint8_t)ntt;
+        unit_cost[j] = std::ldexp(1.0, ma + nb + nK - (int)h.ks) + 8.0;
+        std::vector<bool> is_tile(nC, false);
+        for (int b : mbits) is_tile[b] = true;
+        for (int b : nbits) is_tile[b] = true;
+        for (int jm = 0; jm < (1 << ma); ++jm) {
+            int a = 0, c = 0;
+            for (int t = 0; t < ma; ++t) if ((jm >> t) & 1) { a |= 1 << mapA[mbits[t]]; c |= 1 << mbits[t]; }
+            h.aT[jm] = (uint16_t)a;
+            for (int jn = 0; jn < (1 << nb); ++jn) {
+                int b = 0, c2 = c;
+                for (int t = 0; t < nb; ++t) if ((jn >> t) & 1) { b |= 1 << mapB[nbits[t]]; c2 |= 1 << nbits[t]; }
+                h.bT[jn] = (uint16_t)b;
+                h.cT[jm * (1 << nb) + jn] = (uint16_t)c2;
+            }
+        }
+        for (int k = 0; k < (1 << std::min(nK, 4)); ++k) {
+            int a = 0, b = 0;
+            for (int t = 0; t < std::min(nK, 4); ++t) if ((k >> t) & 1) {
+                if (kposA[t] >= 0) a |= 1 << kposA[t];
+                if (kposB[t] >= 0) b |= 1 << kposB[t];
+            }
+            h.ktA[k] = (uint16_t)a; h.ktB[k] = (uint16_t)b;
+        }
+        std::vector<std::pair<int, int>> ta, tb, tc, ka, kb;
+        int t = 0;
+        for (int b = 0; b < nC; ++b) {
+            if (is_tile[b]) continue;
+            tc.push_back({t, b});
+            if (mapA[b] >= 0) ta.push_back({t, mapA[b]});
+            if (mapB[b] >= 0) tb.push_back({t, mapB[b]});
+            ++t;
+        }
+        for (int b = 4; b < nK; ++b) {
+            if (kposA[b] >= 0) ka.push_back({b - 4, kposA[b]});
+            if (kposB[b] >= 0) kb.push_back({b - 4, kposB[b]});
+        }
+        const int nsA = merge_runs(ta, d.tA, kRowMaxSeg), nsB = merge_runs(tb, d.tB, kRowMaxSeg), nsC = merge_runs(tc, d.tC, kRowMaxSeg);
+        const int nkA = merge_runs(ka, d.kA, kRowMaxKSeg), nkB = merge_runs(kb, d.kB, kRowMaxKSeg);
+        if (nsA < 0 || nsB < 0 || nsC < 0 || nkA < 0 || nkB < 0) return fail("too many address segments");
+        d.nsA = (uint8_t)nsA; d.nsB = (uint8_t)nsB; d.nsC = (uint8_t)nsC; d.nkA = (uint8_t)nkA; d.nkB = (uint8_t)nkB;
+        // where the tensors live
+        auto place = [&](int tensor, int& off, char& in_arena) {
+            auto it = arena_off.find(tensor);
+            if (it != arena_off.end()) { off = it->second; in_arena = 1; }
+            else { off = 0; in_arena = 0; }
+        };
+        place(op.a, d.oA, rp.in_arena_a[j]); place(op.b, d.oB, rp.in_arena_b[j]); place(op.c, d.oC, rp.in_arena_c[j]);
+        h.gen = (uint8_t)(!(rp.in_arena_a[j] && rp.in_arena_b[j] && rp.in_arena_c[j]));
+        const LTensor &TA = L.tensors[op.a], &TB = L.tensors[op.b];
+        rp.flops_per_row += 8.0 * op.macs_per_amp;
+        rp.elems_per_row_amp += (TA.amp ? op.elems_a : 0) + (TB.amp ? op.elems_b : 0) + op.elems_c;
+        rp.elems_shared += (TA.amp ? 0 : op.elems_a) + (TB.amp ? 0 : op.elems_b);
+    }
+
+    // ---- units per level: costly units first, so the round-robin over warps balances
+    rp.level_start.assign(n_levels + 1, 0);
+    for (int lv = 0; lv < n_levels; ++lv) {
+        std::vector<int> here;
+        for (int j = 0; j < n; ++j) if (level[j] == lv) here.push_back(j);
+        std::stable_sort(here.begin(), here.end(), [&](int x, int y) { return unit_cost[x] > unit_cost[y]; });
+        for (int j : here)
+            for (int c = 0; c < n_units[j]; ++c) rp.units.push_back(RowUnit{(uint16_t)j, (uint16_t)c});
+        rp.level_start[lv + 1] = (int)rp.units.size();
+    }
+    rp.n_levels = n_levels;
+    rp.ok = true;
+    return rp;
+}
+
+}  // namespace qxb

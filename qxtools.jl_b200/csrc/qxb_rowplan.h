@@ -1,0 +1,40 @@
+// qxb200 -- host-side builder of row programs (see qxb_rowprog.h).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "qxb_ir.h"
+#include "qxb_rowprog.h"
+
+namespace qxb {
+
+struct RowPlanOptions {
+    int min_tt_bits = 7;          // keep at least 2^min_tt_bits thread-tiles per op when choosing the register tile
+    int max_tile_bits = 4;        // ma + nb <= this (each side <= 2)
+    int tile_reg_budget = 100;    // 32-bit registers for staged operands + accumulators (chooses the K chunk)
+    bool alap = true;             // schedule every op as late as its consumers allow
+    long long max_arena_bytes = 200 * 1024;
+};
+
+struct RowProgramHost {
+    bool ok = false;
+    std::string why;              // why not, when !ok
+    Phase phase = PH_CHUNK;
+    std::vector<RowOp> ops;       // descriptors; g* pointers and fixed-variable offsets are filled in per launch
+    std::vector<int> lop;         // index into Lowered::ops
+    std::vector<int> ref_a, ref_b, ref_c;          // LTensor indices
+    std::vector<char> in_arena_a, in_arena_b, in_arena_c;
+    std::vector<RowUnit> units;
+    std::vector<int> level_start; // n_levels + 1
+    int n_levels = 0;
+    std::vector<RowLeaf> leaves;
+    int arena_elems = 0;          // per row (chunk phase)
+    int root_off = 0, root_span = 0;
+    double flops_per_row = 0;     // 8 * complex MACs
+    double elems_per_row_amp = 0; // algorithmic elements of per-row tensors (A, B, C of every op)
+    double elems_shared = 0;      // algorithmic elements of operands shared by all rows
+};
+
+RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const RowPlanOptions& o);
+
+}  // namespace qxb

@@ -1,0 +1,80 @@
+// qxb200 -- "row programs": a whole phase of the lowered contraction tree executed by ONE persistent kernel.
+//
+// Why: in the batched lowering (qxb_lower.cpp) every chunk-phase tensor is a small dense 2^n array PER BITSTRING ROW
+// (RQC 7x7 d20, 2^12 slices batched: 100 contractions, largest intermediate 2^11 elements = 32 KB, 76 KB live at
+// the peak).  Launching one kernel per contraction streams every intermediate through HBM (62 GB per 131072
+// bitstrings, 14 ms at 63 % of the HBM peak).  A B200 SM has 227 KB of shared memory: the live set of a row FITS.
+// So one CTA takes one bitstring row through the ENTIRE chunk phase with every intermediate in shared memory:
+//     HBM traffic per row = its bitstring (n_qubits bytes) + one amplitude; the step becomes FP64-pipe-bound.
+// The same interpreter runs the block phase (slice-only nodes: ~250 tiny contractions, pure launch latency as
+// separate kernels) as a single-CTA program over global memory.
+//
+// Replaces, for the rows it covers, the inner loops of QXContexts.execute (call site
+// /root/reference/bin/qxrun.jl:83-87): "for bitstring: for slice: for ncon" -> one launch.
+//
+// Program = ops grouped into dependency LEVELS; the work of a level is cut into warp-sized UNITS (32 thread-tiles
+// of one op) that the warps of the CTA take round-robin; one __syncthreads per level.
+#pragma once
+#include <stdint.h>
+
+namespace qxb {
+
+constexpr int kRowThreads = 256;
+constexpr int kRowWarps = kRowThreads / 32;
+constexpr int kRowMaxLevels = 96;
+constexpr int kRowMaxSeg = 12;          // (src, dst, len) runs of the thread-tile-index -> address maps
+constexpr int kRowMaxKSeg = 8;          // runs of the k-bits >= 4 -> address maps
+
+struct RSeg { unsigned char src, dst, len, pad; };
+
+// kinds of inner loop
+constexpr int kRowKindKred = 0;         // <= 16 thread-tiles: lanes also split K, shuffle-reduced
+// tile kinds: 1 + (((ma * 3 + nb) * 3 + kc) * 2 + gen)
+inline int row_tile_kind(int ma, int nb, int kc, int gen) { return 1 + (((ma * 3 + nb) * 3 + kc) * 2 + gen); }
+
+// HOT part (128 bytes): copied by each warp into its shared-memory slot before it runs a unit of the op; every
+// table lookup of the inner loops is then a shared-memory broadcast.  Offsets are ELEMENT indices relative to the
+// tensor (all < 2^16: row programs are only built for tensors of <= 2^16 elements), made of disjoint bits, so
+// they combine with XOR (== OR == ADD); arena tensors are aligned to their size, so the arena offset XORs in too.
+struct alignas(16) RowOpHot {
+    uint16_t aT[4], bT[4];      // register-tile offsets into A (M-only bits) / B (N-only bits)
+    uint16_t cT[16];            // register-tile offsets into C, index jm * 2^nb + jn
+    uint16_t ktA[16], ktB[16];  // offsets of the low min(nK, 4) bits of k
+    uint8_t nK, kc, ma, nb;     // K bits; log2 K chunk held in registers; tile bits
+    uint8_t ntt, kind, ks, gen; // log2 #thread-tiles; inner-loop kind; K-split bits (kred); 1 = some tensor is global
+};
+static_assert(sizeof(RowOpHot) == 128, "hot descriptor must be 128 bytes");
+
+struct alignas(16) RowOp {
+    RowOpHot hot;
+    // COLD part: read once per unit straight from global memory (L1)
+    unsigned long long gA, gB, gC;   // global base pointer, or 0 when the tensor lives in the row arena
+    long long rsA, rsB, rsC;         // elements between consecutive rows of a global per-row tensor (0 = shared)
+    int oA, oB, oC;                  // arena element offset (multiple of the tensor size) when g* == 0
+    uint8_t nsA, nsB, nsC, nkA, nkB, pad[3];
+    RSeg tA[kRowMaxSeg], tB[kRowMaxSeg], tC[kRowMaxSeg];   // thread-tile index bits -> address bits
+    RSeg kA[kRowMaxKSeg], kB[kRowMaxKSeg];                 // (k >> 4) bits -> address bits
+};
+
+struct RowUnit { uint16_t op, chunk; };      // chunk = which group of 32 thread-tiles of the op
+
+struct RowLeaf { int off, span_bits, out_idx; };   // output leaf materialised in the arena from the row's bitstring
+
+// kernel argument (by value, __grid_constant__)
+struct RowLaunch {
+    const RowOp* ops;
+    const RowUnit* units;
+    const RowLeaf* leaves;
+    const unsigned char* bits;      // [n_rows_total][n_outputs] bitstring bytes (0, 1, 2 = '+', 3 = '-')
+    double* acc;                    // [n_rows_total] complex double accumulators (closed network), or nullptr
+    long long amp0, n_rows;         // rows [amp0, amp0 + n_rows)
+    double scale;                   // root_scale
+    int n_levels, n_leaves, n_outputs;
+    int root_off, root_span;        // root tensor in the arena (summed over its 2^root_span elements into acc)
+    int level_start[kRowMaxLevels + 1];
+};
+
+// entry point: (RowLaunch by value); dynamic shared memory = arena bytes + kRowWarps * 128
+const void* rowprog_func(int dtype);
+
+}  // namespace qxb

@@ -1,0 +1,279 @@
+"""CPU replay of the row-program interpreter kernel (csrc/qxb_rowprog.cu) on the descriptors the library builds.
+
+Test infrastructure.  ``qxb_debug_rowprog`` serialises the program of one phase exactly as the executor hands it to
+``rowprog_kernel``: dependency levels, warp units, the size-aligned shared-memory arena plan, the 128-byte hot
+descriptors (register-tile / K tables, combined by XOR) and the cold ones (thread-tile -> address segments).  This
+module mirrors the structs (csrc/qxb_rowprog.h) and walks the same loops as the kernel -- level, unit, lane,
+thread-tile, register tile, K chunk, k; the K-splitting lanes of the small-op path -- on a numpy arena per bitstring
+row, with the const phase and the leaves taken from ``lowered_emulator``.  Levels are executed with a barrier
+in between (all units of a level read the state the previous level left), so a missing dependency or an arena
+overlap between tensors that are live in the same level shows up as a wrong amplitude.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+import lowered_emulator as le
+
+K_MAX_SEG, K_MAX_KSEG = 12, 8
+
+
+class RSeg(C.Structure):
+    _fields_ = [("src", C.c_ubyte), ("dst", C.c_ubyte), ("len", C.c_ubyte), ("pad", C.c_ubyte)]
+
+
+class RowOpHot(C.Structure):
+    _fields_ = [("aT", C.c_uint16 * 4), ("bT", C.c_uint16 * 4), ("cT", C.c_uint16 * 16),
+                ("ktA", C.c_uint16 * 16), ("ktB", C.c_uint16 * 16),
+                ("nK", C.c_uint8), ("kc", C.c_uint8), ("ma", C.c_uint8), ("nb", C.c_uint8),
+                ("ntt", C.c_uint8), ("kind", C.c_uint8), ("ks", C.c_uint8), ("gen", C.c_uint8),
+                ("pad_", C.c_uint8 * 8)]          # alignas(16)
+
+
+class RowOp(C.Structure):
+    _fields_ = [("hot", RowOpHot),
+                ("gA", C.c_uint64), ("gB", C.c_uint64), ("gC", C.c_uint64),
+                ("rsA", C.c_int64), ("rsB", C.c_int64), ("rsC", C.c_int64),
+                ("oA", C.c_int32), ("oB", C.c_int32), ("oC", C.c_int32),
+                ("nsA", C.c_uint8), ("nsB", C.c_uint8), ("nsC", C.c_uint8), ("nkA", C.c_uint8), ("nkB", C.c_uint8),
+                ("pad", C.c_uint8 * 3),
+                ("tA", RSeg * K_MAX_SEG), ("tB", RSeg * K_MAX_SEG), ("tC", RSeg * K_MAX_SEG),
+                ("kA", RSeg * K_MAX_KSEG), ("kB", RSeg * K_MAX_KSEG),
+                ("pad_", C.c_uint8 * 12)]         # alignas(16): sizeof == 416
+
+
+class RowUnit(C.Structure):
+    _fields_ = [("op", C.c_uint16), ("chunk", C.c_uint16)]
+
+
+class RowLeaf(C.Structure):
+    _fields_ = [("off", C.c_int32), ("span_bits", C.c_int32), ("out_idx", C.c_int32)]
+
+
+assert C.sizeof(RowOpHot) == 128 and C.sizeof(RowOp) == 416
+
+
+class RowProgram:
+    pass
+
+
+class Unavailable(Exception):
+    """The library builds no row program for this phase (it then runs the per-op kernels); str = its reason."""
+
+
+def dump(graph, free_mask: int, phase: int):
+    """Row program of ``phase`` (1 block, 2 chunk) for the batched variables in ``free_mask``; None when the library
+    would not build one (reason in ``qxb_last_error``)."""
+    lib = graph._lib
+    need = lib.qxb_debug_rowprog(graph._h, free_mask, phase, None, 0)
+    assert need >= 32, need
+    buf = (C.c_char * need)()
+    assert lib.qxb_debug_rowprog(graph._h, free_mask, phase, buf, need) == need
+    raw = bytes(buf)
+    hdr = np.frombuffer(raw, dtype=np.int32, count=8)
+    if not hdr[0]:
+        return None
+    rp = RowProgram()
+    _, n_ops, n_units, n_levels, n_leaves, rp.arena_elems, rp.root_off, rp.root_span = (int(x) for x in hdr)
+    off = 32
+    rp.level_start = np.frombuffer(raw, dtype=np.int32, count=n_levels + 1, offset=off).tolist(); off += 4 * (n_levels + 1)
+    rp.ops = [RowOp.from_buffer_copy(raw, off + i * C.sizeof(RowOp)) for i in range(n_ops)]; off += n_ops * C.sizeof(RowOp)
+    rp.units = [RowUnit.from_buffer_copy(raw, off + i * 4) for i in range(n_units)]; off += 4 * n_units
+    rp.leaves = [RowLeaf.from_buffer_copy(raw, off + i * 12) for i in range(n_leaves)]; off += 12 * n_leaves
+    names = ("lop", "ref_a", "ref_b", "ref_c", "in_arena_a", "in_arena_b", "in_arena_c")
+    for nm in names:
+        setattr(rp, nm, np.frombuffer(raw, dtype=np.int32, count=n_ops, offset=off).tolist()); off += 4 * n_ops
+    assert off == need
+    rp.n_levels = n_levels
+    return rp
+
+
+def _rseg(segs, n, x):
+    r = np.zeros_like(x)
+    for i in range(n):
+        s = segs[i]
+        r |= ((x >> s.src) & ((1 << s.len) - 1)) << s.dst
+    return r
+
+
+class _Mem:
+    """One tensor's storage as the kernel sees it: a flat array + base element offset."""
+    def __init__(self, buf, base):
+        self.buf, self.base = buf, base
+
+    def ld(self, idx):
+        return self.buf[self.base + idx]
+
+    def st(self, idx, val):
+        self.buf[self.base + idx] = val
+
+
+def _run_unit(op: RowOp, un: RowUnit, mA: _Mem, mB: _Mem, mC: _Mem, stores, dtype):
+    """One warp unit; stores are appended to ``stores`` (applied at the level barrier)."""
+    h = op.hot
+    lane = np.arange(32, dtype=np.int64)
+    nK = h.nK
+
+    def koff(k):                      # k: int array
+        ka = np.array([h.ktA[int(x) & 15] for x in k], dtype=np.int64)
+        kb = np.array([h.ktB[int(x) & 15] for x in k], dtype=np.int64)
+        if nK > 4:
+            ka ^= _rseg(op.kA, op.nkA, k >> 4)
+            kb ^= _rseg(op.kB, op.nkB, k >> 4)
+        return ka, kb
+
+    if h.kind == 0:                   # kred: lanes split K
+        ntt, ks = h.ntt, h.ks
+        tt = lane & ((1 << ntt) - 1)
+        ksub = lane >> ntt
+        active = ksub < (1 << ks)
+        bA = op.oA ^ _rseg(op.tA, op.nsA, tt) ^ h.aT[0]
+        bB = op.oB ^ _rseg(op.tB, op.nsB, tt) ^ h.bT[0]
+        bC = op.oC ^ _rseg(op.tC, op.nsC, tt) ^ h.cT[0]
+        acc = np.zeros(32, dtype=dtype)
+        for kl in range(1 << (nK - ks)):
+            k = ksub | (kl << ks)
+            ka, kb = koff(k)
+            a = mA.ld(np.where(active, bA ^ ka, 0))
+            b = mB.ld(np.where(active, bB ^ kb, 0))
+            acc += np.where(active, a * b, 0)
+        for i in range(ks):
+            acc = acc + acc[lane ^ (1 << (ntt + i))]
+        sel = active & (ksub == 0)
+        stores.append((mC, bC[sel], acc[sel]))
+        return
+    ma, nb, kc = h.ma, h.nb, h.kc
+    assert h.kind == 1 + (((ma * 3 + nb) * 3 + kc) * 2 + 0), "tile kind does not encode (ma, nb, kc)"
+    regs = (4 if dtype == np.complex128 else 2) * (((1 << ma) + (1 << nb)) * (1 << kc) + (1 << (ma + nb)))
+    assert regs <= 100, "tile variant not instantiated in the kernel"
+    tt = un.chunk * 32 + lane
+    act = tt < (1 << h.ntt)
+    tt = np.where(act, tt, 0)
+    bA = op.oA ^ _rseg(op.tA, op.nsA, tt)
+    bB = op.oB ^ _rseg(op.tB, op.nsB, tt)
+    bC = op.oC ^ _rseg(op.tC, op.nsC, tt)
+    TM, TN, KK = 1 << ma, 1 << nb, 1 << kc
+    acc = np.zeros((TM, TN, 32), dtype=dtype)
+    for ch in range(1 << (nK - kc)):
+        kb0 = ch << kc
+        ka, kbo = koff(np.full(32, kb0, dtype=np.int64))
+        for k in range(KK):
+            av = [mA.ld(bA ^ h.aT[j] ^ ka ^ h.ktA[k]) for j in range(TM)]
+            bv = [mB.ld(bB ^ h.bT[j] ^ kbo ^ h.ktB[k]) for j in range(TN)]
+            for jm in range(TM):
+                for jn in range(TN):
+                    acc[jm, jn] += av[jm] * bv[jn]
+    for jm in range(TM):
+        for jn in range(TN):
+            stores.append((mC, (bC ^ h.cT[jm * TN + jn])[act], acc[jm, jn][act]))
+
+
+def run_program(rp: RowProgram, resolve, arena, dtype, check_races=True):
+    """Execute the levels of ``rp``.  resolve(tensor index) -> _Mem of a tensor that is not in the row arena."""
+    for lv in range(rp.n_levels):
+        stores = []
+        for u in range(rp.level_start[lv], rp.level_start[lv + 1]):
+            un = rp.units[u]
+            op = rp.ops[un.op]
+            j = un.op
+            mA = _Mem(arena, 0) if rp.in_arena_a[j] else resolve(rp.ref_a[j])
+            mB = _Mem(arena, 0) if rp.in_arena_b[j] else resolve(rp.ref_b[j])
+            mC = _Mem(arena, 0) if rp.in_arena_c[j] else resolve(rp.ref_c[j])
+            assert op.hot.gen == (0 if (rp.in_arena_a[j] and rp.in_arena_b[j] and rp.in_arena_c[j]) else 1)
+            _run_unit(op, un, mA, mB, mC, stores, dtype)
+        # barrier: the stores of the level land now (no unit of the level may read what another one writes)
+        seen = {}
+        for mem, idx, val in stores:
+            if check_races:
+                key = id(mem.buf)
+                s = seen.setdefault(key, set())
+                addrs = (mem.base + idx).tolist()
+                assert not (s & set(addrs)), "two stores of one level hit the same element"
+                s.update(addrs)
+            mem.st(idx, val)
+
+
+def run_block_rows(graph, desc, free_mask, data, bits, fixed_vals, dtype=np.complex128):
+    """One aligned block the way the row-program path executes it: const phase as lowered ops (folded at compile
+    time by the per-op kernels), block phase = single-CTA row program over the global arenas, chunk phase = one
+    shared-memory arena per bitstring row; returns the per-bitstring partial sums."""
+    n = bits.shape[0]
+    T = desc["tensors"]
+    ops = desc["ops"]
+    ar = desc["arena_elems"]
+    arenas = {"const": np.zeros(max(ar["const"], 2), dtype=dtype), "block": np.zeros(max(ar["block"], 2), dtype=dtype)}
+    leaves = {}
+
+    def locate(t):
+        off = sum(int(fixed_vals[v]) << pos for v, pos in t["fixed"])
+        if t["leaf"] and not t["output_leaf"]:
+            lab = t["data_label"]
+            if lab not in leaves:
+                leaves[lab] = le.pad_leaf(data[lab]).astype(dtype)
+            return leaves[lab], off
+        assert t["phase"] != "chunk"
+        return arenas[t["phase"]], t["offset"] + off
+
+    for op in ops:                                      # const phase (per-op kernels at compile time)
+        if op["phase"] != "const":
+            continue
+        A, a0 = locate(T[op["a"]]); B, b0 = locate(T[op["b"]]); Cb, c0 = locate(T[op["c"]])
+        c = np.arange(1 << op["nC"], dtype=np.int64)
+        fa, fb = le.segeval(op["segA"], c), le.segeval(op["segB"], c)
+        ks = np.arange(1 << op["nK"], dtype=np.int64)
+        ka, kb = le.segeval(op["segKA"], ks), le.segeval(op["segKB"], ks)
+        acc = np.zeros(1 << op["nC"], dtype=dtype)
+        for k in range(len(ks)):
+            acc += A[a0 + fa + ka[k]] * B[b0 + fb + kb[k]]
+        Cb[c0 + c] = acc
+
+    def resolve(ti):
+        buf, base = locate(T[ti])
+        return _Mem(buf, base)
+
+    rp_block = dump(graph, free_mask, 1)
+    if any(o["phase"] == "block" for o in ops):
+        if rp_block is None:
+            raise Unavailable(graph._lib.qxb_last_error().decode())
+        run_program(rp_block, resolve, None, dtype)
+    rp = dump(graph, free_mask, 2)
+    if rp is None:
+        raise Unavailable(graph._lib.qxb_last_error().decode())
+    out = np.zeros(n, dtype=np.complex128)
+    for u in range(n):
+        arena = np.full(max(rp.arena_elems, 1), np.nan + 0j, dtype=dtype)      # NaN: reading an unwritten element shows
+        for lf in rp.leaves:
+            val = bits[u, lf.out_idx - 1]
+            v = np.zeros(1 << lf.span_bits, dtype=dtype)
+            if val == 0: v[0] = 1
+            elif val == 1: v[1] = 1
+            elif val == 2: v[:2] = 1
+            else: v[0], v[1] = 1, -1
+            arena[lf.off: lf.off + (1 << lf.span_bits)] = v
+        # fixed-variable offsets of arena-resident output leaves are XORed into oA/oB per launch by the executor
+        prog = rp
+        if any(T[t]["fixed"] for j in range(len(rp.ops)) for t in (rp.ref_a[j], rp.ref_b[j]) if T[t]["output_leaf"]):
+            import copy
+            prog = copy.copy(rp)
+            prog.ops = [RowOp.from_buffer_copy(bytes(o)) for o in rp.ops]
+            for j, o in enumerate(prog.ops):
+                for side, ref, ina in (("oA", rp.ref_a[j], rp.in_arena_a[j]), ("oB", rp.ref_b[j], rp.in_arena_b[j])):
+                    if ina:
+                        setattr(o, side, getattr(o, side) ^ sum(int(fixed_vals[v]) << pos for v, pos in T[ref]["fixed"]))
+        run_program(prog, resolve, arena, dtype)
+        root = arena[rp.root_off: rp.root_off + (1 << rp.root_span)].astype(np.complex128)
+        out[u] = desc["root_scale"] * np.sum(root)
+    return out
+
+
+def amplitudes(graph, data, bits, slice_begin=0, slice_end=None, dtype=np.complex128):
+    dims = graph.slice_dims
+    if slice_end is None:
+        slice_end = graph.n_slices
+    total = np.zeros(bits.shape[0], dtype=np.complex128)
+    for n_free, vals in le.decompose(dims, slice_begin, slice_end):
+        mask = (1 << n_free) - 1
+        total = total + run_block_rows(graph, graph.describe(n_free), mask, data, bits, vals, dtype)
+    return total.astype(dtype)

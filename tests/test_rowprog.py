@@ -1,0 +1,128 @@
+"""Row programs (csrc/qxb_rowprog.h: a whole phase of the tree as one persistent kernel, intermediates in shared
+memory) replayed on the CPU: the descriptors the library builds -- levels, warp units, aligned arena plan, XOR-combined
+tables, K-splitting lanes -- must reproduce the oracle.  The GPU parity tests then only have to show that the kernel
+follows the same loops (tests/test_gpu_rowprog.py)."""
+import numpy as np
+import pytest
+
+from qxb200.executor import Graph, bits_from_strings
+from oracle import qx_oracle as orc
+import rowprog_emulator as rpe
+import lowered_emulator as le
+from cases import kat0, rqc_case, circuit_case, random_program
+import qxb200 as q
+
+
+def test_kat0_all_ranges(lib_built):
+    txt, data = kat0()
+    g = Graph.from_dsl(txt, data)
+    bs = ["00", "11", "01", "10"]
+    bits = bits_from_strings(bs, 2)
+    cmds = orc.parse_dsl(txt)
+    for b in range(4):
+        for e in range(b + 1, 5):
+            ref = orc.amplitudes(cmds, data, bs, slice_begin=b, slice_end=e)
+            assert np.allclose(rpe.amplitudes(g, data, bits, b, e), ref, atol=1e-15)
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 8, 2), (3, 4, 10, 3), (4, 4, 12, 4)])
+def test_rqc_rowprog_matches_oracle(lib_built, shape):
+    r, c, d, ns = shape
+    txt, data, bs = rqc_case(r, c, d, ns, n_amp=4)
+    g = Graph.from_dsl(txt, data)
+    bits = bits_from_strings(bs + ["+" * (r * c), "-" * (r * c)], r * c)
+    cmds = orc.parse_dsl(txt)
+    ref = orc.amplitudes(cmds, data, bs + ["+" * (r * c), "-" * (r * c)])
+    assert np.allclose(rpe.amplitudes(g, data, bits), ref, atol=1e-14)
+    S = g.n_slices
+    for (b, e) in [(1, S - 1), (3, 4)]:
+        ref = orc.amplitudes(cmds, data, bs, slice_begin=b, slice_end=e)
+        assert np.allclose(rpe.amplitudes(g, data, bits[:len(bs)], b, e), ref, atol=1e-14)
+
+
+def test_replanned_rqc_rowprog(lib_built):
+    """The re-planned (batch-aware) tree is what the bench runs: bigger nodes, register tiles, several units per op."""
+    txt, data, bs = rqc_case(4, 4, 12, 4, n_amp=3)
+    g = Graph.from_dsl(txt, data, replan=16, replan_n_amp=1024)
+    bits = bits_from_strings(bs, 16)
+    ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
+    assert np.allclose(rpe.amplitudes(g, data, bits), ref, atol=1e-14)
+    rp = rpe.dump(g, (1 << len(g.slice_dims)) - 1, 2)
+    assert rp.n_levels < len(rp.ops)                      # levels really group independent ops
+
+
+@pytest.mark.parametrize("workload", ["rqc_7x7_d20_c64_s4096", "rqc_6x6_d16_c32_s64"])
+def test_bench_workloads_rowprog(lib_built, workload):
+    """The plans the bench runs (every slice variable batched: nodes of up to 2^11 elements per bitstring, 2 x 2
+    register tiles, several warp units per node, K chunks) against the emulator of the lowered program -- itself
+    pinned to the oracle by tests/test_lowering.py -- and, on a short slice range, against the oracle directly."""
+    import bench
+    txt, data, w = bench.build_workload(workload)
+    g = Graph.from_dsl(txt, data, "c64", replan=8, replan_n_amp=131072)
+    nq = w["rows"] * w["cols"]
+    bits = bench.synth_bits(2, nq)
+    bits[1, :3] = (2, 3, 2)                              # '+' / '-' outputs as well
+    got = rpe.amplitudes(g, data, bits)
+    ref = le.amplitudes(g, data, bits)
+    assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+    k = len(g.slice_dims)
+    rp = rpe.dump(g, (1 << k) - 1, 2)
+    kinds = {op.hot.kind for op in rp.ops}
+    assert 0 in kinds and max(kinds) > 1                  # both the K-splitting path and register tiles are exercised
+    if workload.startswith("rqc_7x7"):
+        assert max(op.hot.ma + op.hot.nb for op in rp.ops) >= 3
+    # a 3-slice range (blocks with fixed variables) against the oracle
+    bs = ["".join("01"[b] for b in row) for row in bench.synth_bits(1, nq)]
+    ref = orc.amplitudes(orc.parse_dsl(g.text), data, bs, slice_begin=5, slice_end=8)
+    got = rpe.amplitudes(g, data, bits_from_strings(bs, nq), 5, 8)
+    assert np.max(np.abs(got - ref)) <= 1e-12 * max(np.max(np.abs(ref)), 2.0 ** (-nq / 2))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_programs_rowprog(lib_built, seed):
+    """Hyper-edges, outer products, non-power-of-two extents, views on outputs (fixed offsets into arena leaves)."""
+    txt, data, bs = random_program(seed)
+    g = Graph.from_dsl(txt, data)
+    n_out = g.n_outputs
+    bits = bits_from_strings(bs, n_out)
+    cmds = orc.parse_dsl(txt)
+    ref = orc.amplitudes(cmds, data, bs)
+    try:
+        got = rpe.amplitudes(g, data, bits)
+    except rpe.Unavailable as e:                          # a row too large for shared memory: the per-op path runs it
+        assert "exceeds the budget" in str(e) or "2^16" in str(e)
+        pytest.skip(f"no row program: {e}")
+    assert np.allclose(got, ref, atol=1e-12 * max(1.0, float(np.max(np.abs(ref)))))
+    S = g.n_slices
+    if S > 2:
+        ref = orc.amplitudes(cmds, data, bs, slice_begin=1, slice_end=S - 1)
+        got = rpe.amplitudes(g, data, bits, 1, S - 1)
+        assert np.allclose(got, ref, atol=1e-12 * max(1.0, float(np.max(np.abs(ref)))))
+
+
+def test_ghz_and_qft_rowprog(lib_built):
+    for circ, ns in ((q.create_ghz_circuit(5), 0), (q.create_qft_circuit(6), 0), (q.create_ghz_circuit(4), 2)):
+        txt, data, bs = circuit_case(circ, n_slice=ns, n_amp=4)
+        g = Graph.from_dsl(txt, data)
+        bits = bits_from_strings(bs, circ.num_qubits)
+        ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
+        assert np.allclose(rpe.amplitudes(g, data, bits), ref, atol=1e-14)
+
+
+def test_arena_plan_is_aligned_and_fits(lib_built):
+    """Every arena tensor sits at a multiple of its size (the XOR address arithmetic needs it) and the headline
+    workload's row fits a B200 SM's shared memory."""
+    import bench
+    txt, data, w = bench.build_workload("rqc_7x7_d20_c64_s4096")
+    g = Graph.from_dsl(txt, data, "c64", replan=8, replan_n_amp=131072)
+    k = len(g.slice_dims)
+    rp = rpe.dump(g, (1 << k) - 1, 2)
+    assert rp is not None
+    d = g.describe()
+    for j, op in enumerate(rp.ops):
+        lop = d["ops"][rp.lop[j]]
+        assert op.oC % (1 << lop["nC"]) == 0
+        for ina, off, ref in ((rp.in_arena_a[j], op.oA, rp.ref_a[j]), (rp.in_arena_b[j], op.oB, rp.ref_b[j])):
+            if ina:
+                assert off % (1 << d["tensors"][ref]["span_bits"]) == 0
+    assert rp.arena_elems * 16 <= 226 * 1024              # fits one SM's shared memory (<= 113 KB: two CTAs per SM)
