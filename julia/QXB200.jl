@@ -6,10 +6,12 @@
 # Everything else (convert_to_tnc, flow_cutter_contraction_plan, contraction_scheme,
 # build_compute_graph, generate_simulation_files) stays QXTools' own Julia code.
 #
-# NOTE: written against the ABI but NOT runnable in the build container (no Julia there).
+# NOTE: written against the ABI but NOT runnable in the build container (no Julia there): UNTESTED until it runs
+# under a CI with Julia + the QX packages (INTEGRATION.md says the same).
 module QXB200
 
 using QXTools, QXContexts, JLD2, YAML
+using AbstractTrees                       # PostOrderDFS, as compute_graph.jl:3 of the reference
 using DataStructures: OrderedDict
 
 const LIB = get(ENV, "QXB200_LIB", "libqxb200.so")
@@ -163,19 +165,32 @@ function execute(dsl_file::String, input_file::Union{String, Nothing}=nothing,
     end
     bs = Vector{String}(params["params"]["bitstrings"])
     max_amplitudes === nothing || (bs = bs[1:min(end, max_amplitudes)])
-    g = Graph(read(dsl_file, String), tensors; dtype=(elt == ComplexF32 ? C32 : C64))
-    S = max_slices === nothing ? num_slices(g) : min(max_slices, num_slices(g))
     rank, nranks = 0, 1
+    MPI = nothing
     if use_mpi
-        # one process per GPU: bitstrings across sub-communicators, slices inside (users_guide.md:11-20)
+        # one process per GPU.  The device is chosen BEFORE the graph is built: compile uploads the leaves and folds
+        # constants on the current device.  Local rank = rank modulo the GPUs of the node (QXB200_GPUS_PER_NODE, 8).
         MPI = Base.require(Base.PkgId(Base.UUID("da04e1cc-30fd-572f-bb4f-1f8673147195"), "MPI"))
         MPI.Initialized() || MPI.Init()
         rank, nranks = MPI.Comm_rank(MPI.COMM_WORLD), MPI.Comm_size(MPI.COMM_WORLD)
-        check(ccall((:qxb_init, LIB), Cint, (Cint,), rank % sub_comm_size))
+        nranks % sub_comm_size == 0 || error("sub_comm_size must divide the number of ranks")
+        check(ccall((:qxb_init, LIB), Cint, (Cint,), rank % parse(Int, get(ENV, "QXB200_GPUS_PER_NODE", "8"))))
+    else
+        sub_comm_size = 1
     end
-    r = rank % sub_comm_size
-    amps = amplitudes(g, bs; slice_begin=(S * r) ÷ sub_comm_size, slice_end=(S * (r + 1)) ÷ sub_comm_size)
-    use_mpi && (amps = MPI.Allreduce(amps, +, MPI.COMM_WORLD))     # sub_comm_size == nranks case
+    g = Graph(read(dsl_file, String), tensors; dtype=(elt == ComplexF32 ? C32 : C64))
+    S = max_slices === nothing ? num_slices(g) : min(max_slices, num_slices(g))
+    # two levels, as docs/src/users_guide.md:11-20: the bitstrings are split across the nranks / sub_comm_size
+    # sub-communicators, the slices across the ranks inside one (qxtools.jl_b200/dist.py is the tested mirror)
+    n_groups = nranks ÷ sub_comm_size
+    group, r = rank ÷ sub_comm_size, rank % sub_comm_size
+    a0, a1 = (length(bs) * group) ÷ n_groups, (length(bs) * (group + 1)) ÷ n_groups
+    amps = zeros(elt == ComplexF32 ? ComplexF32 : ComplexF64, length(bs))
+    if a1 > a0
+        amps[a0+1:a1] = amplitudes(g, bs[a0+1:a1]; slice_begin=(S * r) ÷ sub_comm_size, slice_end=(S * (r + 1)) ÷ sub_comm_size)
+    end
+    # groups own disjoint bitstrings (zeros elsewhere), ranks of a group hold partial sums over slices: one sum does both
+    use_mpi && (amps = MPI.Allreduce(amps, +, MPI.COMM_WORLD))
     results = OrderedDict(zip(bs, amps))
     if rank == 0 && output_file != ""
         jldopen(output_file, "w") do io

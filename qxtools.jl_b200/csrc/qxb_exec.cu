@@ -91,11 +91,13 @@ struct Variant {
     bool use_rows = false;
     RowProgramHost rp_block, rp_chunk;
     struct RowDev {
-        DevBuf ops_block, units_block, ops_chunk, units_chunk, leaves;
+        DevBuf descs_block, slots_block, descs_chunk, slots_chunk, leaves;
+        std::vector<int> level_start_block, level_start_chunk;      // in slots
         const void *block_base = nullptr, *const_base = nullptr;     // arena bases the pointers were resolved against
     };
     std::map<std::vector<int64_t>, RowDev> rowdev;
     OpProfile prof_rows, prof_block_rows;                // profile mode: the two fused launches
+    DevBuf row_timing;                                   // profile mode: per-level clock cycles of CTA 0 (chunk program)
 };
 
 struct EventPair { cudaEvent_t a, b; int variant, op; };
@@ -135,10 +137,10 @@ struct qxb_graph {
     ~qxb_graph() {
         for (auto& kv : leafbuf) kv.second.release();
         for (auto& kv : variants) {
-            kv.second->const_arena.release(); kv.second->outleaf_desc.release();
+            kv.second->const_arena.release(); kv.second->outleaf_desc.release(); kv.second->row_timing.release();
             for (auto& rd : kv.second->rowdev) {
-                rd.second.ops_block.release(); rd.second.units_block.release(); rd.second.ops_chunk.release();
-                rd.second.units_chunk.release(); rd.second.leaves.release();
+                rd.second.descs_block.release(); rd.second.slots_block.release(); rd.second.descs_chunk.release();
+                rd.second.slots_chunk.release(); rd.second.leaves.release();
             }
         }
         block_arena.release(); chunk_arena.release(); acc.release(); d_bits.release(); d_out.release();
@@ -604,8 +606,7 @@ void build_row_programs(qxb_graph* g, Variant& v) {
     o.tile_reg_budget = knob(g->opts.row_tile_regs, "QXB_ROW_TILE_REGS", 100);
     o.alap = knob(0, "QXB_ROW_ALAP", 1) != 0;
     o.max_tile_bits = knob(0, "QXB_ROW_MAX_TILE", 4);
-    const long long slot_bytes = kRowWarps * (long long)sizeof(RowOpHot);
-    o.max_arena_bytes = 227 * 1024 - slot_bytes;
+    o.max_arena_bytes = 227 * 1024 - (long long)row_fixed_smem_bytes(2048 + kRowWarps * kRowMaxLevels);   // descriptor buffers + slot table
     v.rp_chunk = build_row_program(v.L, PH_CHUNK, g->dtype, o);
     if (!v.rp_chunk.ok) return;
     bool has_block = false;
@@ -625,14 +626,14 @@ Variant::RowDev& row_device_tables(const RunCtx& c) {
     std::vector<int64_t> key(k, 0);
     for (int i = 0; i < k; ++i) if (!((v.L.free_mask >> i) & 1ull)) key[i] = c.fixed_vals[i];
     Variant::RowDev& rd = v.rowdev[key];
-    if (rd.ops_chunk.p && rd.block_base == g->block_arena.p && rd.const_base == v.const_arena.p) return rd;
+    if (rd.descs_chunk.p && rd.block_base == g->block_arena.p && rd.const_base == v.const_arena.p) return rd;
     rd.block_base = g->block_arena.p; rd.const_base = v.const_arena.p;
     auto fixed_off = [&](const LTensor& T) {
         long long off = 0;
         for (auto& f : T.fixed) off += (long long)c.fixed_vals[f.first] << f.second;
         return off;
     };
-    auto resolve = [&](const RowProgramHost& rp, DevBuf& d_ops, DevBuf& d_units) {
+    auto resolve = [&](const RowProgramHost& rp, DevBuf& d_descs, DevBuf& d_slots, std::vector<int>& level_start) {
         std::vector<RowOp> ops = rp.ops;
         for (size_t j = 0; j < ops.size(); ++j) {
             RowOp& d = ops[j];
@@ -640,21 +641,21 @@ Variant::RowDev& row_device_tables(const RunCtx& c) {
             if (rp.in_arena_a[j]) d.oA ^= (int)fixed_off(A); else { d.gA = (unsigned long long)tensor_ptr(c, A); d.oA = 0; }
             if (rp.in_arena_b[j]) d.oB ^= (int)fixed_off(B); else { d.gB = (unsigned long long)tensor_ptr(c, B); d.oB = 0; }
             if (!rp.in_arena_c[j]) { d.gC = (unsigned long long)tensor_ptr(c, C); d.oC = 0; }
-            d.rsA = d.rsB = d.rsC = 0;                       // every global tensor of a row program is shared by the rows
         }
-        d_ops.reserve(std::max<size_t>(ops.size(), 1) * sizeof(RowOp));
-        d_units.reserve(std::max<size_t>(rp.units.size(), 1) * sizeof(RowUnit));
-        CUDA_OK(cudaMemcpy(d_ops.p, ops.data(), ops.size() * sizeof(RowOp), cudaMemcpyHostToDevice));
-        CUDA_OK(cudaMemcpy(d_units.p, rp.units.data(), rp.units.size() * sizeof(RowUnit), cudaMemcpyHostToDevice));
+        RowDeviceTables t = build_row_tables(rp, ops);
+        level_start = t.level_start;
+        d_descs.reserve(std::max<size_t>(t.descs.size(), 1) * sizeof(RowUnitDesc));
+        d_slots.reserve(std::max<size_t>(t.slots.size(), 1) * sizeof(uint16_t));
+        CUDA_OK(cudaMemcpy(d_descs.p, t.descs.data(), t.descs.size() * sizeof(RowUnitDesc), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(d_slots.p, t.slots.data(), t.slots.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     };
-    if (v.rp_block.ok) resolve(v.rp_block, rd.ops_block, rd.units_block);
-    resolve(v.rp_chunk, rd.ops_chunk, rd.units_chunk);
+    if (v.rp_block.ok) resolve(v.rp_block, rd.descs_block, rd.slots_block, rd.level_start_block);
+    resolve(v.rp_chunk, rd.descs_chunk, rd.slots_chunk, rd.level_start_chunk);
     rd.leaves.reserve(std::max<size_t>(v.rp_chunk.leaves.size(), 1) * sizeof(RowLeaf));
     if (!v.rp_chunk.leaves.empty())
         CUDA_OK(cudaMemcpy(rd.leaves.p, v.rp_chunk.leaves.data(), v.rp_chunk.leaves.size() * sizeof(RowLeaf), cudaMemcpyHostToDevice));
     return rd;
 }
-
 
 Variant* get_variant(qxb_graph* g, uint64_t free_mask) {
     auto it = g->variants.find(free_mask);
@@ -809,8 +810,8 @@ Node row_node(const RunCtx& c, Variant::RowDev& rd, bool chunk, const uint8_t* d
     const RowProgramHost& rp = chunk ? v.rp_chunk : v.rp_block;
     RowLaunch P;
     memset(&P, 0, sizeof(P));
-    P.ops = (const RowOp*)(chunk ? rd.ops_chunk.p : rd.ops_block.p);
-    P.units = (const RowUnit*)(chunk ? rd.units_chunk.p : rd.units_block.p);
+    P.descs = (const RowUnitDesc*)(chunk ? rd.descs_chunk.p : rd.descs_block.p);
+    P.slots = (const uint16_t*)(chunk ? rd.slots_chunk.p : rd.slots_block.p);
     P.leaves = (const RowLeaf*)rd.leaves.p;
     P.bits = d_bits;
     P.acc = chunk ? (double*)g->acc.p : nullptr;
@@ -821,11 +822,20 @@ Node row_node(const RunCtx& c, Variant::RowDev& rd, bool chunk, const uint8_t* d
     P.n_leaves = chunk ? (int)rp.leaves.size() : 0;
     P.n_outputs = g->prog.n_outputs;
     P.root_off = rp.root_off; P.root_span = rp.root_span;
-    for (int i = 0; i <= rp.n_levels; ++i) P.level_start[i] = rp.level_start[i];
+    const std::vector<int>& ls = chunk ? rd.level_start_chunk : rd.level_start_block;
+    for (int i = 0; i <= rp.n_levels; ++i) P.level_start[i] = ls[i];
+    const size_t n_slots = (size_t)ls[rp.n_levels];
     Node n;
     n.func = rowprog_func(g->dtype);
     n.block = dim3(kRowThreads);
-    n.smem = kRowWarps * sizeof(RowOpHot) + (chunk ? (size_t)rp.arena_elems * g->es() : 0);
+    P.slots_bytes = (int)row_slots_bytes(n_slots);
+    P.timing = nullptr;
+    if (chunk && g->opts.profile) {
+        if (v.row_timing.reserve(sizeof(long long) * (kRowMaxLevels + 1)))
+            CUDA_OK(cudaMemset(v.row_timing.p, 0, v.row_timing.bytes));
+        P.timing = (long long*)v.row_timing.p;
+    }
+    n.smem = row_fixed_smem_bytes(n_slots) + (chunk ? (size_t)rp.arena_elems * g->es() : 0);
     static std::set<const void*> configured;
     if (!configured.count(n.func)) {
         CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1581,10 +1591,21 @@ int qxb_profile_dump(qxb_graph* g, const char* path) {
             for (int q = 0; q < 2; ++q) {
                 if (fp[q]->launches == 0) continue;
                 const RowProgramHost& rp = q ? v.rp_chunk : v.rp_block;
+                std::string lc = "[]";
+                if (q == 1 && v.row_timing.p) {
+                    // cycles CTA 0 spent in each level, summed over every row it took since the graph was compiled
+                    std::vector<long long> cyc(rp.n_levels, 0);
+                    if (cudaMemcpy(cyc.data(), v.row_timing.p, sizeof(long long) * rp.n_levels, cudaMemcpyDeviceToHost) == cudaSuccess) {
+                        lc = "[";
+                        for (int l = 0; l < rp.n_levels; ++l) lc += (l ? "," : "") + std::to_string(cyc[l]);
+                        lc += "]";
+                    }
+                }
                 fprintf(f, "%s{\"name\":\"%s\",\"phase\":%d,\"fused_ops\":%d,\"levels\":%d,\"units\":%d,\"arena_bytes\":%lld,"
+                           "\"level_cycles_cta0\":%s,"
                            "\"launches\":%lld,\"flops\":%.6g,\"bytes\":%.6g,\"ms\":%.6g}",
                         first ? "" : ",", fname[q], q ? 2 : 1, (int)rp.ops.size(), rp.n_levels, (int)rp.units.size(),
-                        (long long)rp.arena_elems * (long long)g->es(), fp[q]->launches, fp[q]->flops, fp[q]->bytes, fp[q]->ms);
+                        (long long)rp.arena_elems * (long long)g->es(), lc.c_str(), fp[q]->launches, fp[q]->flops, fp[q]->bytes, fp[q]->ms);
                 first = false;
             }
             fprintf(f, "]}");
@@ -1594,10 +1615,13 @@ int qxb_profile_dump(qxb_graph* g, const char* path) {
     });
 }
 
-// test hook: the row program of one phase (qxb_rowprog.h) exactly as the executor would build it, serialised for
-// tests/rowprog_emulator.py.  Pure host logic.  Layout: int32 header[8] = {ok, n_ops, n_units, n_levels, n_leaves,
-// arena_elems, root_off, root_span}, int32 level_start[n_levels + 1], RowOp ops[n_ops], RowUnit units[n_units],
-// RowLeaf leaves[n_leaves], int32 lop / ref_a / ref_b / ref_c / in_arena_a / in_arena_b / in_arena_c [n_ops] each.
+// test hook: the row program of one phase (qxb_rowprog.h) exactly as the executor would hand it to rowprog_kernel
+// (unit descriptors and slot table of build_row_tables; tensors outside the arena keep a null pointer and are named
+// by the reference arrays), serialised for tests/rowprog_emulator.py.  Pure host logic.  Layout: int32 header[8] =
+// {ok, n_ops, n_descs, n_levels, n_leaves, arena_elems, root_off, root_span}, int32 n_slots, int32
+// level_start[n_levels + 1] (in slots), uint16 slots[n_slots] (+ pad to 4 bytes), RowUnitDesc descs[n_descs],
+// int32 desc_op[n_descs], RowLeaf leaves[n_leaves], int32 lop / ref_a / ref_b / ref_c / in_arena_a / in_arena_b /
+// in_arena_c [n_ops] each.
 int64_t qxb_debug_rowprog(qxb_graph* g, uint64_t free_mask, int phase, void* buf, int64_t buflen) {
     int64_t need = 0;
     int rc = guard([&] {
@@ -1611,23 +1635,37 @@ int64_t qxb_debug_rowprog(qxb_graph* g, uint64_t free_mask, int phase, void* buf
         o.tile_reg_budget = knob(g->opts.row_tile_regs, "QXB_ROW_TILE_REGS", 100);
         o.alap = knob(0, "QXB_ROW_ALAP", 1) != 0;
         o.max_tile_bits = knob(0, "QXB_ROW_MAX_TILE", 4);
-        o.max_arena_bytes = 227 * 1024 - kRowWarps * (long long)sizeof(RowOpHot);
+        o.max_arena_bytes = 227 * 1024 - (long long)row_fixed_smem_bytes(2048 + kRowWarps * kRowMaxLevels);
         RowProgramHost rp = build_row_program(L, (Phase)phase, g->dtype, o);
         if (!rp.ok) { set_last_error(rp.why); }
         std::vector<char> out;
         auto put = [&](const void* p, size_t n) { const char* c = (const char*)p; out.insert(out.end(), c, c + n); };
-        const int n_ops = rp.ok ? (int)rp.ops.size() : 0;
-        int32_t hdr[8] = {rp.ok ? 1 : 0, n_ops, rp.ok ? (int)rp.units.size() : 0, rp.ok ? rp.n_levels : 0,
-                          rp.ok ? (int)rp.leaves.size() : 0, rp.arena_elems, rp.root_off, rp.root_span};
-        put(hdr, sizeof(hdr));
-        if (rp.ok) {
-            std::vector<int32_t> ls(rp.level_start.begin(), rp.level_start.end());
+        if (!rp.ok) {
+            int32_t hdr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            put(hdr, sizeof(hdr));
+        } else {
+            std::vector<RowOp> ops = rp.ops;
+            for (size_t j = 0; j < ops.size(); ++j) {       // tensors outside the arena: base offset 0, pointer unresolved
+                if (!rp.in_arena_a[j]) ops[j].oA = 0;
+                if (!rp.in_arena_b[j]) ops[j].oB = 0;
+                if (!rp.in_arena_c[j]) ops[j].oC = 0;
+            }
+            RowDeviceTables t = build_row_tables(rp, ops);
+            int32_t hdr[8] = {1, (int)rp.ops.size(), (int)t.descs.size(), rp.n_levels, (int)rp.leaves.size(), rp.arena_elems,
+                              rp.root_off, rp.root_span};
+            put(hdr, sizeof(hdr));
+            int32_t n_slots = (int32_t)t.slots.size();
+            put(&n_slots, 4);
+            std::vector<int32_t> ls(t.level_start.begin(), t.level_start.end());
             put(ls.data(), ls.size() * 4);
-            put(rp.ops.data(), rp.ops.size() * sizeof(RowOp));
-            put(rp.units.data(), rp.units.size() * sizeof(RowUnit));
-            put(rp.leaves.data(), rp.leaves.size() * sizeof(RowLeaf));
+            std::vector<uint16_t> sl = t.slots;
+            if (sl.size() % 2) sl.push_back(0);
+            put(sl.data(), sl.size() * 2);
+            put(t.descs.data(), t.descs.size() * sizeof(RowUnitDesc));
             auto puti = [&](const std::vector<int>& v) { std::vector<int32_t> w(v.begin(), v.end()); put(w.data(), w.size() * 4); };
             auto putc = [&](const std::vector<char>& v) { std::vector<int32_t> w(v.begin(), v.end()); put(w.data(), w.size() * 4); };
+            puti(t.desc_op);
+            put(rp.leaves.data(), rp.leaves.size() * sizeof(RowLeaf));
             puti(rp.lop); puti(rp.ref_a); puti(rp.ref_b); puti(rp.ref_c);
             putc(rp.in_arena_a); putc(rp.in_arena_b); putc(rp.in_arena_c);
         }

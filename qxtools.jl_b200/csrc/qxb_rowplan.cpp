@@ -254,9 +254,52 @@ RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const
             for (int c = 0; c < n_units[j]; ++c) rp.units.push_back(RowUnit{(uint16_t)j, (uint16_t)c});
         rp.level_start[lv + 1] = (int)rp.units.size();
     }
+    if (rp.units.size() > 2048 && phase == PH_CHUNK) return fail("more than 2048 units");
+    if (rp.units.size() > 40000) return fail("too many units");     // descriptor indices are 16 bits, 0xFFFF = none
     rp.n_levels = n_levels;
     rp.ok = true;
     return rp;
+}
+
+
+static int eval_segs(const RSeg* s, int n, unsigned x) {
+    int r = 0;
+    for (int i = 0; i < n; ++i) r |= (int)(((x >> s[i].src) & ((1u << s[i].len) - 1u)) << s[i].dst);
+    return r;
+}
+
+RowDeviceTables build_row_tables(const RowProgramHost& rp, const std::vector<RowOp>& ops) {
+    RowDeviceTables t;
+    t.level_start.assign(rp.n_levels + 1, 0);
+    for (int lv = 0; lv < rp.n_levels; ++lv) {
+        for (int u = rp.level_start[lv]; u < rp.level_start[lv + 1]; ++u) {
+            const RowUnit un = rp.units[u];
+            const RowOp& op = ops[un.op];
+            RowUnitDesc d;
+            memset(&d, 0, sizeof(d));
+            d.hot = op.hot;
+            d.gA = op.gA; d.gB = op.gB; d.gC = op.gC;
+            memcpy(d.kA, op.kA, sizeof(d.kA)); memcpy(d.kB, op.kB, sizeof(d.kB));
+            d.nkA = op.nkA; d.nkB = op.nkB;
+            const int ntt = op.hot.ntt;
+            for (int lane = 0; lane < 32; ++lane) {
+                int tt; bool active;
+                if (op.hot.kind == kRowKindKred) { tt = lane & ((1 << ntt) - 1); active = (lane >> ntt) < (1 << op.hot.ks); }
+                else { tt = un.chunk * 32 + lane; active = tt < (1 << ntt); }
+                if (!active) { d.lA[lane] = d.lB[lane] = 0; d.lC[lane] = kRowNull; continue; }
+                d.lA[lane] = (uint16_t)(op.oA ^ eval_segs(op.tA, op.nsA, (unsigned)tt));
+                d.lB[lane] = (uint16_t)(op.oB ^ eval_segs(op.tB, op.nsB, (unsigned)tt));
+                d.lC[lane] = (uint16_t)(op.oC ^ eval_segs(op.tC, op.nsC, (unsigned)tt));
+            }
+            t.slots.push_back((uint16_t)t.descs.size());
+            t.descs.push_back(d);
+            t.desc_op.push_back(un.op);
+        }
+        while (t.slots.size() % kRowWarps) t.slots.push_back(kRowNull);      // every warp has a slot in every round
+        if ((int)t.slots.size() == t.level_start[lv]) for (int w = 0; w < kRowWarps; ++w) t.slots.push_back(kRowNull);
+        t.level_start[lv + 1] = (int)t.slots.size();
+    }
+    return t;
 }
 
 }  // namespace qxb

@@ -37,4 +37,15 @@ struct RowProgramHost {
 
 RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const RowPlanOptions& o);
 
+// What the kernel reads: one resolved descriptor per unit and the slot table (levels padded to a multiple of
+// kRowWarps slots).  `ops` = rp.ops with oA/oB/oC final (fixed-variable offsets XORed in, 0 for global tensors) and
+// gA/gB/gC set for tensors outside the arena.
+struct RowDeviceTables {
+    std::vector<RowUnitDesc> descs;
+    std::vector<uint16_t> slots;
+    std::vector<int> level_start;     // in slots, n_levels + 1
+    std::vector<int> desc_op;         // op index (into rp.ops) of each descriptor
+};
+RowDeviceTables build_row_tables(const RowProgramHost& rp, const std::vector<RowOp>& ops);
+
 }  // namespace qxb

@@ -38,7 +38,7 @@ struct TileRegs {
 
 // One thread-tile.  pA / pB / pC: the arena (shared memory, known to the compiler when !GEN) or generic pointers.
 template <typename R2, int MA, int NB, int KC, bool GEN>
-__device__ __forceinline__ void row_tile(const RowOpHot* __restrict__ h, const RowOp* __restrict__ op,
+__device__ __forceinline__ void row_tile(const RowOpHot* __restrict__ h, const RowUnitDesc* __restrict__ op,
                                          const R2* pA, const R2* pB, R2* pC, int bA, int bB, int bC) {
     constexpr int TM = 1 << MA, TN = 1 << NB, KK = 1 << KC;
     const int nK = h->nK;
@@ -83,17 +83,13 @@ __device__ __forceinline__ void row_tile(const RowOpHot* __restrict__ h, const R
 
 // Ops with < 32 thread-tiles: the spare lane bits split K (interleaved), partial sums meet by xor-shuffles.
 template <typename R2>
-__device__ __forceinline__ void row_kred(const RowOpHot* __restrict__ h, const RowOp* __restrict__ op, const R2* pA,
-                                         const R2* pB, R2* pC, int oA, int oB, int oC, int lane) {
+__device__ __forceinline__ void row_kred(const RowOpHot* __restrict__ h, const RowUnitDesc* __restrict__ op, const R2* pA,
+                                         const R2* pB, R2* pC, int bA, int bB, int bC, int lane) {
     const int ntt = h->ntt, ks = h->ks, nK = h->nK;
-    const int tt = lane & ((1 << ntt) - 1), ksub = lane >> ntt;
-    const bool active = ksub < (1 << ks);
+    const int ksub = lane >> ntt;
+    const bool active = bC != kRowNull;
     R2 acc; acc.x = 0; acc.y = 0;
-    int bC = 0;
     if (active) {
-        const int bA = oA ^ rseg(op->tA, op->nsA, (unsigned)tt) ^ h->aT[0];
-        const int bB = oB ^ rseg(op->tB, op->nsB, (unsigned)tt) ^ h->bT[0];
-        bC = oC ^ rseg(op->tC, op->nsC, (unsigned)tt) ^ h->cT[0];
         const int nl = 1 << (nK - ks);
         for (int kl = 0; kl < nl; ++kl) {
             const int k = ksub | (kl << ks);
@@ -110,7 +106,7 @@ __device__ __forceinline__ void row_kred(const RowOpHot* __restrict__ h, const R
 }
 
 template <typename R2, int MA, int NB, int KC>
-__device__ __forceinline__ void row_tile_pick(const RowOpHot* __restrict__ h, const RowOp* __restrict__ op, R2* arena,
+__device__ __forceinline__ void row_tile_pick(const RowOpHot* __restrict__ h, const RowUnitDesc* __restrict__ op, R2* arena,
                                               const R2* pA, const R2* pB, R2* pC, int bA, int bB, int bC) {
     if constexpr (TileRegs<R2, MA, NB, KC>::value <= 100) {
         if (h->gen) row_tile<R2, MA, NB, KC, true>(h, op, pA, pB, pC, bA, bB, bC);
@@ -119,7 +115,7 @@ __device__ __forceinline__ void row_tile_pick(const RowOpHot* __restrict__ h, co
 }
 
 template <typename R2, int MA, int NB>
-__device__ __forceinline__ void row_tile_kc(const RowOpHot* __restrict__ h, const RowOp* __restrict__ op, R2* arena,
+__device__ __forceinline__ void row_tile_kc(const RowOpHot* __restrict__ h, const RowUnitDesc* __restrict__ op, R2* arena,
                                             const R2* pA, const R2* pB, R2* pC, int bA, int bB, int bC) {
     switch (h->kc) {
     case 0: row_tile_pick<R2, MA, NB, 0>(h, op, arena, pA, pB, pC, bA, bB, bC); break;
@@ -130,13 +126,38 @@ __device__ __forceinline__ void row_tile_kc(const RowOpHot* __restrict__ h, cons
 
 }  // namespace
 
+// 16-byte asynchronous global -> shared copy (LDGSTS): descriptor prefetch without touching registers
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Shared memory: [2 descriptor buffers per warp][slot table][arena].  The descriptor of a warp's next unit is in
+// flight (cp.async) while it computes the current one; nothing on the unit path reads global memory synchronously.
 template <typename R2>
 __global__ void __launch_bounds__(kRowThreads, 2) rowprog_kernel(const __grid_constant__ RowLaunch P) {
     extern __shared__ __align__(16) unsigned char row_smem[];
-    RowOpHot* slots = reinterpret_cast<RowOpHot*>(row_smem);
-    R2* arena = reinterpret_cast<R2*>(row_smem + kRowWarps * sizeof(RowOpHot));
+    RowUnitDesc* bufs = reinterpret_cast<RowUnitDesc*>(row_smem);
+    uint16_t* slots = reinterpret_cast<uint16_t*>(row_smem + 2 * kRowWarps * sizeof(RowUnitDesc));
+    R2* arena = reinterpret_cast<R2*>(row_smem + 2 * kRowWarps * sizeof(RowUnitDesc) + P.slots_bytes);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    RowOpHot* h = slots + warp;
+    const int n_slots = P.level_start[P.n_levels];
+    for (int i = tid; i < n_slots; i += kRowThreads) slots[i] = P.slots[i];
+    __syncthreads();
+    auto prefetch = [&](int s, int par) {           // descriptor of slot s -> buffer par of this warp (26 x 16 bytes)
+        if (s >= 0) {
+            const unsigned di = slots[s];
+            if (di != kRowNull && lane < (int)(sizeof(RowUnitDesc) / 16))
+                cp_async16(reinterpret_cast<char*>(bufs + warp * 2 + par) + lane * 16,
+                           reinterpret_cast<const char*>(P.descs + di) + lane * 16);
+        }
+        cp_async_commit();
+    };
+    long long t_prev = 0;
+    int par = 0;
+    prefetch(P.level_start[0] + warp, par);
     for (long long row = blockIdx.x; row < P.n_rows; row += gridDim.x) {
         // output leaves of this row: one-hot (or +/-) vectors from the bitstring bytes
         // (docs/src/users_guide.md:149-158, docs/src/basics.md:55-63 of the reference)
@@ -157,32 +178,34 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowprog_kernel(const __grid_co
             }
         }
         __syncthreads();
+        if (P.timing && blockIdx.x == 0 && tid == 0) t_prev = clock64();
         for (int lv = 0; lv < P.n_levels; ++lv) {
-            const int u1 = P.level_start[lv + 1];
-            for (int u = P.level_start[lv] + warp; u < u1; u += kRowWarps) {
-                const RowUnit un = P.units[u];
-                const RowOp* __restrict__ op = P.ops + un.op;
-                // stage the hot descriptor (128 bytes) in this warp's slot
+            const int s1 = P.level_start[lv + 1];
+            for (int s = P.level_start[lv] + warp; s < s1; s += kRowWarps) {
+                cp_async_wait_all();                 // the descriptor of slot s has landed in buffer `par`
                 __syncwarp();
-                reinterpret_cast<unsigned*>(h)[lane] = reinterpret_cast<const unsigned*>(&op->hot)[lane];
-                __syncwarp();
-                const int oA = op->oA, oB = op->oB, oC = op->oC;
+                const RowUnitDesc* __restrict__ op = bufs + warp * 2 + par;
+                const unsigned di = slots[s];
+                // next slot of this warp: same level, next level, or the first slot of the next row
+                int ns = s + kRowWarps;
+                if (ns >= s1) ns = lv + 1 < P.n_levels ? s1 + warp : (row + gridDim.x < P.n_rows ? P.level_start[0] + warp : -1);
+                par ^= 1;
+                prefetch(ns, par);
+                if (di == kRowNull) continue;
+                const RowOpHot* __restrict__ h = &op->hot;
+                const int bA = op->lA[lane], bB = op->lB[lane], bC = op->lC[lane];
                 const R2 *pA = arena, *pB = arena;
                 R2* pC = arena;
                 if (h->gen) {
-                    if (op->gA) pA = reinterpret_cast<const R2*>(op->gA) + (P.amp0 + row) * op->rsA;
-                    if (op->gB) pB = reinterpret_cast<const R2*>(op->gB) + (P.amp0 + row) * op->rsB;
-                    if (op->gC) pC = reinterpret_cast<R2*>(op->gC) + (P.amp0 + row) * op->rsC;
+                    if (op->gA) pA = reinterpret_cast<const R2*>(op->gA);
+                    if (op->gB) pB = reinterpret_cast<const R2*>(op->gB);
+                    if (op->gC) pC = reinterpret_cast<R2*>(op->gC);
                 }
                 if (h->kind == kRowKindKred) {
-                    row_kred<R2>(h, op, pA, pB, pC, oA, oB, oC, lane);
+                    row_kred<R2>(h, op, pA, pB, pC, bA, bB, bC, lane);
                     continue;
                 }
-                const int tt = un.chunk * 32 + lane;
-                if (tt >= (1 << h->ntt)) continue;
-                const int bA = oA ^ rseg(op->tA, op->nsA, (unsigned)tt);
-                const int bB = oB ^ rseg(op->tB, op->nsB, (unsigned)tt);
-                const int bC = oC ^ rseg(op->tC, op->nsC, (unsigned)tt);
+                if (bC == kRowNull) continue;
                 switch (h->ma * 3 + h->nb) {
                 case 0: row_tile_kc<R2, 0, 0>(h, op, arena, pA, pB, pC, bA, bB, bC); break;
                 case 1: row_tile_kc<R2, 0, 1>(h, op, arena, pA, pB, pC, bA, bB, bC); break;
@@ -196,6 +219,11 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowprog_kernel(const __grid_co
                 }
             }
             __syncthreads();
+            if (P.timing && blockIdx.x == 0 && tid == 0) {     // per-level cycles of CTA 0 (diagnostics)
+                const long long t = clock64();
+                P.timing[lv] += t - t_prev;
+                t_prev = t;
+            }
         }
         // root: sum over the batched slice bits still open in it, in double (what reduce_root_kernel does)
         if (P.acc && warp == 0) {
@@ -217,6 +245,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowprog_kernel(const __grid_co
         }
         __syncthreads();                       // the arena is rewritten by the next row
     }
+    cp_async_wait_all();
 }
 
 const void* rowprog_func(int dtype) {

@@ -32,8 +32,7 @@ constexpr int kRowKindKred = 0;         // <= 16 thread-tiles: lanes also split 
 // tile kinds: 1 + (((ma * 3 + nb) * 3 + kc) * 2 + gen)
 inline int row_tile_kind(int ma, int nb, int kc, int gen) { return 1 + (((ma * 3 + nb) * 3 + kc) * 2 + gen); }
 
-// HOT part (128 bytes): copied by each warp into its shared-memory slot before it runs a unit of the op; every
-// table lookup of the inner loops is then a shared-memory broadcast.  Offsets are ELEMENT indices relative to the
+// HOT part (128 bytes): the tables the inner loops index; read from the warp's shared-memory slot (broadcasts).  Offsets are ELEMENT indices relative to the
 // tensor (all < 2^16: row programs are only built for tensors of <= 2^16 elements), made of disjoint bits, so
 // they combine with XOR (== OR == ADD); arena tensors are aligned to their size, so the arena offset XORs in too.
 struct alignas(16) RowOpHot {
@@ -47,7 +46,7 @@ static_assert(sizeof(RowOpHot) == 128, "hot descriptor must be 128 bytes");
 
 struct alignas(16) RowOp {
     RowOpHot hot;
-    // COLD part: read once per unit straight from global memory (L1)
+    // COLD part (host side only since the unit descriptors exist): address maps and tensor locations
     unsigned long long gA, gB, gC;   // global base pointer, or 0 when the tensor lives in the row arena
     long long rsA, rsB, rsC;         // elements between consecutive rows of a global per-row tensor (0 = shared)
     int oA, oB, oC;                  // arena element offset (multiple of the tensor size) when g* == 0
@@ -56,25 +55,45 @@ struct alignas(16) RowOp {
     RSeg kA[kRowMaxKSeg], kB[kRowMaxKSeg];                 // (k >> 4) bits -> address bits
 };
 
-struct RowUnit { uint16_t op, chunk; };      // chunk = which group of 32 thread-tiles of the op
+struct RowUnit { uint16_t op, chunk; };      // host side: chunk = which group of 32 thread-tiles of the op
+
+// What the kernel executes: one descriptor PER UNIT (32 thread-tiles of one op), fully resolved on the host -- the
+// per-lane base offsets replace the segment evaluation the first version did per lane and unit (3 x ~8 segments x
+// ~12 instructions: half of the 80 000 warp instructions per row that version executed, profiles/r2d_summary.md).
+// 416 bytes = 26 cp.async of 16 bytes into the warp's shared-memory slot, one unit ahead of the compute.
+struct alignas(16) RowUnitDesc {
+    RowOpHot hot;
+    unsigned long long gA, gB, gC;           // global base pointers (0: the tensor lives in the row arena)
+    RSeg kA[kRowMaxKSeg], kB[kRowMaxKSeg];   // (k >> 4) bits -> address bits (only read when nK > 4)
+    uint8_t nkA, nkB, pad[6];
+    uint16_t lA[32], lB[32], lC[32];         // per lane: base element offsets of its thread-tile (arena offset folded
+                                             // in); lC == 0xFFFF: the lane has no thread-tile in this unit
+};
+static_assert(sizeof(RowUnitDesc) == 416, "unit descriptor must be 26 x 16 bytes");
+constexpr uint16_t kRowNull = 0xFFFF;        // slot table: no unit for this warp in this round
 
 struct RowLeaf { int off, span_bits, out_idx; };   // output leaf materialised in the arena from the row's bitstring
 
 // kernel argument (by value, __grid_constant__)
 struct RowLaunch {
-    const RowOp* ops;
-    const RowUnit* units;
+    const RowUnitDesc* descs;       // unit descriptors
+    const uint16_t* slots;          // slot table: per level a multiple of kRowWarps entries; warp w takes entries
+                                    // level_start[lv] + w, + kRowWarps, ...; value = descriptor index or kRowNull
     const RowLeaf* leaves;
     const unsigned char* bits;      // [n_rows_total][n_outputs] bitstring bytes (0, 1, 2 = '+', 3 = '-')
     double* acc;                    // [n_rows_total] complex double accumulators (closed network), or nullptr
     long long amp0, n_rows;         // rows [amp0, amp0 + n_rows)
     double scale;                   // root_scale
+    long long* timing;              // diagnostics: per-level clock cycles of CTA 0, summed over its rows (or nullptr)
+    int slots_bytes;                // bytes reserved for the slot table in shared memory (multiple of 128)
     int n_levels, n_leaves, n_outputs;
     int root_off, root_span;        // root tensor in the arena (summed over its 2^root_span elements into acc)
-    int level_start[kRowMaxLevels + 1];
+    int level_start[kRowMaxLevels + 1];     // in slots
 };
 
-// entry point: (RowLaunch by value); dynamic shared memory = arena bytes + kRowWarps * 128
+// entry point: (RowLaunch by value); dynamic shared memory = row_smem_bytes(...)
 const void* rowprog_func(int dtype);
+inline size_t row_slots_bytes(size_t n_slots) { return (n_slots * sizeof(uint16_t) + 127) / 128 * 128; }
+inline size_t row_fixed_smem_bytes(size_t n_slots) { return 2 * kRowWarps * sizeof(RowUnitDesc) + row_slots_bytes(n_slots); }
 
 }  // namespace qxb

@@ -27,7 +27,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .planning import min_fill
+from qxb200.planning import min_fill
 
 AMP = -1     # pseudo index: the bitstring axis carried by every output leaf
 
@@ -262,10 +262,10 @@ def _emit(header, leaf_lines, leaves, plan, root) -> str:
 
 def _cost(text: str, data_dims: Dict[str, Tuple[int, ...]], n_amp: int, dtype: str) -> float:
     """Bytes moved by the lowered program (the executor's own model, host-only call)."""
-    from .executor import Graph
+    from qxb200.executor import Graph
     g = Graph(dtype)
     b = text.encode()
-    from ._lib import check
+    from qxb200._lib import check
     check(g._lib.qxb_graph_parse_dsl(g._h, b, len(b)))
     d = g.describe()
     es = 8 if g.dtype == 0 else 16

@@ -2,7 +2,8 @@
 
 Test infrastructure.  ``qxb_debug_rowprog`` serialises the program of one phase exactly as the executor hands it to
 ``rowprog_kernel``: dependency levels, warp units, the size-aligned shared-memory arena plan, the 128-byte hot
-descriptors (register-tile / K tables, combined by XOR) and the cold ones (thread-tile -> address segments).  This
+descriptors (register-tile / K tables, combined by XOR) and the per-unit lane tables (base offsets of each lane's
+thread-tile, evaluated on the host from the thread-tile -> address segments).  This
 module mirrors the structs (csrc/qxb_rowprog.h) and walks the same loops as the kernel -- level, unit, lane,
 thread-tile, register tile, K chunk, k; the K-splitting lanes of the small-op path -- on a numpy arena per bitstring
 row, with the const phase and the leaves taken from ``lowered_emulator``.  Levels are executed with a barrier
@@ -32,27 +33,20 @@ class RowOpHot(C.Structure):
                 ("pad_", C.c_uint8 * 8)]          # alignas(16)
 
 
-class RowOp(C.Structure):
+class RowUnitDesc(C.Structure):
     _fields_ = [("hot", RowOpHot),
                 ("gA", C.c_uint64), ("gB", C.c_uint64), ("gC", C.c_uint64),
-                ("rsA", C.c_int64), ("rsB", C.c_int64), ("rsC", C.c_int64),
-                ("oA", C.c_int32), ("oB", C.c_int32), ("oC", C.c_int32),
-                ("nsA", C.c_uint8), ("nsB", C.c_uint8), ("nsC", C.c_uint8), ("nkA", C.c_uint8), ("nkB", C.c_uint8),
-                ("pad", C.c_uint8 * 3),
-                ("tA", RSeg * K_MAX_SEG), ("tB", RSeg * K_MAX_SEG), ("tC", RSeg * K_MAX_SEG),
                 ("kA", RSeg * K_MAX_KSEG), ("kB", RSeg * K_MAX_KSEG),
-                ("pad_", C.c_uint8 * 12)]         # alignas(16): sizeof == 416
-
-
-class RowUnit(C.Structure):
-    _fields_ = [("op", C.c_uint16), ("chunk", C.c_uint16)]
+                ("nkA", C.c_uint8), ("nkB", C.c_uint8), ("pad", C.c_uint8 * 6),
+                ("lA", C.c_uint16 * 32), ("lB", C.c_uint16 * 32), ("lC", C.c_uint16 * 32)]
 
 
 class RowLeaf(C.Structure):
     _fields_ = [("off", C.c_int32), ("span_bits", C.c_int32), ("out_idx", C.c_int32)]
 
 
-assert C.sizeof(RowOpHot) == 128 and C.sizeof(RowOp) == 416
+assert C.sizeof(RowOpHot) == 128 and C.sizeof(RowUnitDesc) == 416
+K_NULL, K_WARPS = 0xFFFF, 8
 
 
 class RowProgram:
@@ -76,17 +70,21 @@ def dump(graph, free_mask: int, phase: int):
     if not hdr[0]:
         return None
     rp = RowProgram()
-    _, n_ops, n_units, n_levels, n_leaves, rp.arena_elems, rp.root_off, rp.root_span = (int(x) for x in hdr)
+    _, n_ops, n_descs, n_levels, n_leaves, rp.arena_elems, rp.root_off, rp.root_span = (int(x) for x in hdr)
     off = 32
+    n_slots = int(np.frombuffer(raw, dtype=np.int32, count=1, offset=off)[0]); off += 4
     rp.level_start = np.frombuffer(raw, dtype=np.int32, count=n_levels + 1, offset=off).tolist(); off += 4 * (n_levels + 1)
-    rp.ops = [RowOp.from_buffer_copy(raw, off + i * C.sizeof(RowOp)) for i in range(n_ops)]; off += n_ops * C.sizeof(RowOp)
-    rp.units = [RowUnit.from_buffer_copy(raw, off + i * 4) for i in range(n_units)]; off += 4 * n_units
+    rp.slots = np.frombuffer(raw, dtype=np.uint16, count=n_slots, offset=off).tolist(); off += 2 * (n_slots + n_slots % 2)
+    rp.descs = [RowUnitDesc.from_buffer_copy(raw, off + i * C.sizeof(RowUnitDesc)) for i in range(n_descs)]
+    off += n_descs * C.sizeof(RowUnitDesc)
+    rp.desc_op = np.frombuffer(raw, dtype=np.int32, count=n_descs, offset=off).tolist(); off += 4 * n_descs
     rp.leaves = [RowLeaf.from_buffer_copy(raw, off + i * 12) for i in range(n_leaves)]; off += 12 * n_leaves
     names = ("lop", "ref_a", "ref_b", "ref_c", "in_arena_a", "in_arena_b", "in_arena_c")
     for nm in names:
         setattr(rp, nm, np.frombuffer(raw, dtype=np.int32, count=n_ops, offset=off).tolist()); off += 4 * n_ops
     assert off == need
     rp.n_levels = n_levels
+    assert rp.level_start[-1] == n_slots and all(x % K_WARPS == 0 for x in rp.level_start)
     return rp
 
 
@@ -110,11 +108,16 @@ class _Mem:
         self.buf[self.base + idx] = val
 
 
-def _run_unit(op: RowOp, un: RowUnit, mA: _Mem, mB: _Mem, mC: _Mem, stores, dtype):
-    """One warp unit; stores are appended to ``stores`` (applied at the level barrier)."""
+def _run_unit(op: RowUnitDesc, mA: _Mem, mB: _Mem, mC: _Mem, fixA, fixB, stores, dtype):
+    """One warp unit as rowprog_kernel runs it from its descriptor; stores are appended to ``stores`` (applied at the
+    level barrier).  fixA / fixB: what the executor XORs into the lane bases of arena leaves with fixed variables."""
     h = op.hot
     lane = np.arange(32, dtype=np.int64)
     nK = h.nK
+    bA = np.array(op.lA[:], dtype=np.int64) ^ fixA
+    bB = np.array(op.lB[:], dtype=np.int64) ^ fixB
+    bC = np.array(op.lC[:], dtype=np.int64)
+    act = bC != K_NULL
 
     def koff(k):                      # k: int array
         ka = np.array([h.ktA[int(x) & 15] for x in k], dtype=np.int64)
@@ -126,34 +129,25 @@ def _run_unit(op: RowOp, un: RowUnit, mA: _Mem, mB: _Mem, mC: _Mem, stores, dtyp
 
     if h.kind == 0:                   # kred: lanes split K
         ntt, ks = h.ntt, h.ks
-        tt = lane & ((1 << ntt) - 1)
         ksub = lane >> ntt
-        active = ksub < (1 << ks)
-        bA = op.oA ^ _rseg(op.tA, op.nsA, tt) ^ h.aT[0]
-        bB = op.oB ^ _rseg(op.tB, op.nsB, tt) ^ h.bT[0]
-        bC = op.oC ^ _rseg(op.tC, op.nsC, tt) ^ h.cT[0]
+        assert np.array_equal(act, ksub < (1 << ks)), "kred lane mask"
         acc = np.zeros(32, dtype=dtype)
         for kl in range(1 << (nK - ks)):
             k = ksub | (kl << ks)
             ka, kb = koff(k)
-            a = mA.ld(np.where(active, bA ^ ka, 0))
-            b = mB.ld(np.where(active, bB ^ kb, 0))
-            acc += np.where(active, a * b, 0)
+            a = mA.ld(np.where(act, bA ^ ka, 0))
+            b = mB.ld(np.where(act, bB ^ kb, 0))
+            acc += np.where(act, a * b, 0)
         for i in range(ks):
             acc = acc + acc[lane ^ (1 << (ntt + i))]
-        sel = active & (ksub == 0)
+        sel = act & (ksub == 0)
         stores.append((mC, bC[sel], acc[sel]))
         return
     ma, nb, kc = h.ma, h.nb, h.kc
     assert h.kind == 1 + (((ma * 3 + nb) * 3 + kc) * 2 + 0), "tile kind does not encode (ma, nb, kc)"
     regs = (4 if dtype == np.complex128 else 2) * (((1 << ma) + (1 << nb)) * (1 << kc) + (1 << (ma + nb)))
     assert regs <= 100, "tile variant not instantiated in the kernel"
-    tt = un.chunk * 32 + lane
-    act = tt < (1 << h.ntt)
-    tt = np.where(act, tt, 0)
-    bA = op.oA ^ _rseg(op.tA, op.nsA, tt)
-    bB = op.oB ^ _rseg(op.tB, op.nsB, tt)
-    bC = op.oC ^ _rseg(op.tC, op.nsC, tt)
+    bA = np.where(act, bA, 0); bB = np.where(act, bB, 0)
     TM, TN, KK = 1 << ma, 1 << nb, 1 << kc
     acc = np.zeros((TM, TN, 32), dtype=dtype)
     for ch in range(1 << (nK - kc)):
@@ -170,19 +164,28 @@ def _run_unit(op: RowOp, un: RowUnit, mA: _Mem, mB: _Mem, mC: _Mem, stores, dtyp
             stores.append((mC, (bC ^ h.cT[jm * TN + jn])[act], acc[jm, jn][act]))
 
 
-def run_program(rp: RowProgram, resolve, arena, dtype, check_races=True):
-    """Execute the levels of ``rp``.  resolve(tensor index) -> _Mem of a tensor that is not in the row arena."""
+def run_program(rp: RowProgram, resolve, arena, dtype, fix=None, check_races=True):
+    """Execute the levels of ``rp`` the way the kernel walks them: per level, warp w takes slots level_start + w,
+    + 8, ...; a barrier after each level.  resolve(tensor index) -> _Mem of a tensor that is not in the row arena.
+    fix: {op index: (xorA, xorB)} for arena leaves whose fixed-variable offsets the executor folds in per launch."""
+    fix = fix or {}
     for lv in range(rp.n_levels):
         stores = []
-        for u in range(rp.level_start[lv], rp.level_start[lv + 1]):
-            un = rp.units[u]
-            op = rp.ops[un.op]
-            j = un.op
+        s0, s1 = rp.level_start[lv], rp.level_start[lv + 1]
+        order = [s for w in range(K_WARPS) for s in range(s0 + w, s1, K_WARPS)]
+        assert sorted(order) == list(range(s0, s1))
+        for sl in order:
+            di = rp.slots[sl]
+            if di == K_NULL:
+                continue
+            op = rp.descs[di]
+            j = rp.desc_op[di]
             mA = _Mem(arena, 0) if rp.in_arena_a[j] else resolve(rp.ref_a[j])
             mB = _Mem(arena, 0) if rp.in_arena_b[j] else resolve(rp.ref_b[j])
             mC = _Mem(arena, 0) if rp.in_arena_c[j] else resolve(rp.ref_c[j])
             assert op.hot.gen == (0 if (rp.in_arena_a[j] and rp.in_arena_b[j] and rp.in_arena_c[j]) else 1)
-            _run_unit(op, un, mA, mB, mC, stores, dtype)
+            fa, fb = fix.get(j, (0, 0))
+            _run_unit(op, mA, mB, mC, fa, fb, stores, dtype)
         # barrier: the stores of the level land now (no unit of the level may read what another one writes)
         seen = {}
         for mem, idx, val in stores:
@@ -252,17 +255,14 @@ def run_block_rows(graph, desc, free_mask, data, bits, fixed_vals, dtype=np.comp
             elif val == 2: v[:2] = 1
             else: v[0], v[1] = 1, -1
             arena[lf.off: lf.off + (1 << lf.span_bits)] = v
-        # fixed-variable offsets of arena-resident output leaves are XORed into oA/oB per launch by the executor
-        prog = rp
-        if any(T[t]["fixed"] for j in range(len(rp.ops)) for t in (rp.ref_a[j], rp.ref_b[j]) if T[t]["output_leaf"]):
-            import copy
-            prog = copy.copy(rp)
-            prog.ops = [RowOp.from_buffer_copy(bytes(o)) for o in rp.ops]
-            for j, o in enumerate(prog.ops):
-                for side, ref, ina in (("oA", rp.ref_a[j], rp.in_arena_a[j]), ("oB", rp.ref_b[j], rp.in_arena_b[j])):
-                    if ina:
-                        setattr(o, side, getattr(o, side) ^ sum(int(fixed_vals[v]) << pos for v, pos in T[ref]["fixed"]))
-        run_program(prog, resolve, arena, dtype)
+        # fixed-variable offsets of arena-resident output leaves are XORed into the lane bases per launch by the executor
+        fix = {}
+        for j in range(len(rp.ref_a)):
+            fa = sum(int(fixed_vals[v]) << pos for v, pos in T[rp.ref_a[j]]["fixed"]) if rp.in_arena_a[j] else 0
+            fb = sum(int(fixed_vals[v]) << pos for v, pos in T[rp.ref_b[j]]["fixed"]) if rp.in_arena_b[j] else 0
+            if fa or fb:
+                fix[j] = (fa, fb)
+        run_program(rp, resolve, arena, dtype, fix)
         root = arena[rp.root_off: rp.root_off + (1 << rp.root_span)].astype(np.complex128)
         out[u] = desc["root_scale"] * np.sum(root)
     return out

@@ -5,7 +5,7 @@ import pytest
 
 import qxb200 as q
 from qxb200.executor import Graph, bits_from_strings
-from qxb200.replan import replan_dsl, recover_network
+from replan_prototype import replan_dsl, recover_network
 from oracle import qx_oracle as orc
 import lowered_emulator as em
 from cases import kat0, rqc_case, circuit_case

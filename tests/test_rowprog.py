@@ -48,7 +48,7 @@ def test_replanned_rqc_rowprog(lib_built):
     ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
     assert np.allclose(rpe.amplitudes(g, data, bits), ref, atol=1e-14)
     rp = rpe.dump(g, (1 << len(g.slice_dims)) - 1, 2)
-    assert rp.n_levels < len(rp.ops)                      # levels really group independent ops
+    assert rp.n_levels < len(rp.lop)                      # levels really group independent ops
 
 
 @pytest.mark.parametrize("workload", ["rqc_7x7_d20_c64_s4096", "rqc_6x6_d16_c32_s64"])
@@ -67,10 +67,10 @@ def test_bench_workloads_rowprog(lib_built, workload):
     assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
     k = len(g.slice_dims)
     rp = rpe.dump(g, (1 << k) - 1, 2)
-    kinds = {op.hot.kind for op in rp.ops}
+    kinds = {op.hot.kind for op in rp.descs}
     assert 0 in kinds and max(kinds) > 1                  # both the K-splitting path and register tiles are exercised
     if workload.startswith("rqc_7x7"):
-        assert max(op.hot.ma + op.hot.nb for op in rp.ops) >= 3
+        assert max(op.hot.ma + op.hot.nb for op in rp.descs) >= 3
     # a 3-slice range (blocks with fixed variables) against the oracle
     bs = ["".join("01"[b] for b in row) for row in bench.synth_bits(1, nq)]
     ref = orc.amplitudes(orc.parse_dsl(g.text), data, bs, slice_begin=5, slice_end=8)
@@ -119,10 +119,14 @@ def test_arena_plan_is_aligned_and_fits(lib_built):
     rp = rpe.dump(g, (1 << k) - 1, 2)
     assert rp is not None
     d = g.describe()
-    for j, op in enumerate(rp.ops):
+    for di, op in enumerate(rp.descs):
+        j = rp.desc_op[di]
         lop = d["ops"][rp.lop[j]]
-        assert op.oC % (1 << lop["nC"]) == 0
-        for ina, off, ref in ((rp.in_arena_a[j], op.oA, rp.ref_a[j]), (rp.in_arena_b[j], op.oB, rp.ref_b[j])):
+        act = [l for l in range(32) if op.lC[l] != 0xFFFF]
+        assert act
+        # all lanes of a unit address ONE size-aligned block per arena tensor (the arena offset is XORed, not added)
+        assert len({op.lC[l] >> lop["nC"] for l in act}) == 1
+        for ina, lanes, ref in ((rp.in_arena_a[j], op.lA, rp.ref_a[j]), (rp.in_arena_b[j], op.lB, rp.ref_b[j])):
             if ina:
-                assert off % (1 << d["tensors"][ref]["span_bits"]) == 0
+                assert len({lanes[l] >> d["tensors"][ref]["span_bits"] for l in act}) == 1
     assert rp.arena_elems * 16 <= 226 * 1024              # fits one SM's shared memory (<= 113 KB: two CTAs per SM)
