@@ -606,6 +606,7 @@ void build_row_programs(qxb_graph* g, Variant& v) {
     o.tile_reg_budget = knob(g->opts.row_tile_regs, "QXB_ROW_TILE_REGS", 100);
     o.alap = knob(0, "QXB_ROW_ALAP", 1) != 0;
     o.max_tile_bits = knob(0, "QXB_ROW_MAX_TILE", 4);
+    o.stage_shared = knob(0, "QXB_ROW_STAGE", 1) != 0;
     o.max_arena_bytes = 227 * 1024 - (long long)row_fixed_smem_bytes(2048 + kRowWarps * kRowMaxLevels);   // descriptor buffers + slot table
     v.rp_chunk = build_row_program(v.L, PH_CHUNK, g->dtype, o);
     if (!v.rp_chunk.ok) return;
@@ -637,9 +638,15 @@ Variant::RowDev& row_device_tables(const RunCtx& c) {
         std::vector<RowOp> ops = rp.ops;
         for (size_t j = 0; j < ops.size(); ++j) {
             RowOp& d = ops[j];
+            if (rp.lop[j] < 0) {
+                // copy pseudo-op of a staged operand: the whole tensor from its base (the consumers add the fixed offsets)
+                const LTensor& A = v.L.tensors[rp.ref_a[j]];
+                d.gA = (unsigned long long)(tensor_ptr(c, A) - fixed_off(A) * (long long)g->es());
+                continue;
+            }
             const LTensor &A = v.L.tensors[rp.ref_a[j]], &B = v.L.tensors[rp.ref_b[j]], &C = v.L.tensors[rp.ref_c[j]];
-            if (rp.in_arena_a[j]) d.oA ^= (int)fixed_off(A); else { d.gA = (unsigned long long)tensor_ptr(c, A); d.oA = 0; }
-            if (rp.in_arena_b[j]) d.oB ^= (int)fixed_off(B); else { d.gB = (unsigned long long)tensor_ptr(c, B); d.oB = 0; }
+            if (rp.in_arena_a[j]) d.oA += (int)fixed_off(A); else { d.gA = (unsigned long long)tensor_ptr(c, A); d.oA = 0; }
+            if (rp.in_arena_b[j]) d.oB += (int)fixed_off(B); else { d.gB = (unsigned long long)tensor_ptr(c, B); d.oB = 0; }
             if (!rp.in_arena_c[j]) { d.gC = (unsigned long long)tensor_ptr(c, C); d.oC = 0; }
         }
         RowDeviceTables t = build_row_tables(rp, ops);
@@ -1635,6 +1642,7 @@ int64_t qxb_debug_rowprog(qxb_graph* g, uint64_t free_mask, int phase, void* buf
         o.tile_reg_budget = knob(g->opts.row_tile_regs, "QXB_ROW_TILE_REGS", 100);
         o.alap = knob(0, "QXB_ROW_ALAP", 1) != 0;
         o.max_tile_bits = knob(0, "QXB_ROW_MAX_TILE", 4);
+        o.stage_shared = knob(0, "QXB_ROW_STAGE", 1) != 0;
         o.max_arena_bytes = 227 * 1024 - (long long)row_fixed_smem_bytes(2048 + kRowWarps * kRowMaxLevels);
         RowProgramHost rp = build_row_program(L, (Phase)phase, g->dtype, o);
         if (!rp.ok) { set_last_error(rp.why); }

@@ -36,14 +36,18 @@ int tile_regs(int dtype, int ma, int nb, int kc) {
 
 struct Interval { int off, size, until; };     // live until level `until` inclusive
 
-// lowest offset that is a multiple of `size` and overlaps no live interval
-int aligned_alloc(std::vector<Interval>& live, int size, int until) {
-    for (int off = 0;; off += size) {
-        bool clash = false;
-        for (const Interval& iv : live)
-            if (iv.off < off + size && off < iv.off + iv.size) { clash = true; break; }
-        if (!clash) { live.push_back(Interval{off, size, until}); return off; }
+// lowest offset (multiple of `align`) where `size` elements overlap no live interval: first fit
+int arena_alloc(std::vector<Interval>& live, int size, int until, int align = 1) {
+    std::vector<std::pair<int, int>> iv;
+    for (const Interval& x : live) iv.push_back({x.off, x.off + x.size});
+    std::sort(iv.begin(), iv.end());
+    int off = 0;
+    for (auto& x : iv) {
+        if (x.first - off >= size) break;
+        off = std::max(off, (x.second + align - 1) / align * align);
     }
+    live.push_back(Interval{off, size, until});
+    return off;
 }
 
 }  // namespace
@@ -51,6 +55,7 @@ int aligned_alloc(std::vector<Interval>& live, int size, int until) {
 RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const RowPlanOptions& o) {
     RowProgramHost rp;
     rp.phase = phase;
+    rp.elem_bytes = dtype == QXB_C32 ? 8 : 16;
     auto fail = [&](const std::string& why) { rp.ok = false; rp.why = why; return rp; };
     // ---- ops of the phase, producers, levels
     std::vector<int> sel;                                   // indices into L.ops
@@ -92,9 +97,30 @@ RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const
             level[j] = std::max(level[j], lv);
         }
     }
+    // operands that live outside the chunk phase (leaves, const- and block-phase results): stage the small ones
+    struct Staged { int tensor, copy_level, until, off; };
+    std::vector<Staged> staged;
+    if (phase == PH_CHUNK && o.stage_shared) {
+        std::map<int, std::pair<int, int>> use;             // tensor -> (first, last) level of use
+        for (int j = 0; j < n; ++j)
+            for (int t : {L.ops[sel[j]].a, L.ops[sel[j]].b}) {
+                const LTensor& T = L.tensors[t];
+                if (producer.count(t) || T.is_output_leaf || T.span_bits > o.stage_max_bits) continue;
+                auto it = use.find(t);
+                if (it == use.end()) use[t] = {level[j], level[j]};
+                else { it->second.first = std::min(it->second.first, level[j]); it->second.second = std::max(it->second.second, level[j]); }
+            }
+        if (!use.empty()) {
+            for (int j = 0; j < n; ++j) ++level[j];          // level 0 = the copies the first ops need
+            ++n_levels;
+            for (auto& kv : use) staged.push_back(Staged{kv.first, kv.second.first, kv.second.second + 1, -1});
+        }
+    }
     if (n_levels > kRowMaxLevels) return fail("more than " + std::to_string(kRowMaxLevels) + " levels");
 
-    // ---- arena plan (chunk phase): tensors are powers of two, aligned to their size
+    // ---- arena plan (chunk phase): first fit over level-granular live ranges (addresses are base + offsets, so a
+    //      tensor may sit anywhere); operands shared by all rows are STAGED: copied into the arena by cp.async one
+    //      level before their first use (a global load at use time is an L2 round trip on the critical path)
     std::map<int, int> arena_off;                           // LTensor -> element offset
     if (phase == PH_CHUNK) {
         auto last_level = [&](int t) {
@@ -108,13 +134,19 @@ RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const
             if (T.span_bits > 16) return fail("output leaf too large");
             const int lu = last_level(t);
             if (lu < 0) continue;                               // unused leaf
-            arena_off[t] = aligned_alloc(live, 1 << T.span_bits, lu);
+            arena_off[t] = arena_alloc(live, 1 << T.span_bits, lu);
             rp.leaves.push_back(RowLeaf{arena_off[t], T.span_bits, (int)T.out_idx});
         }
         int peak = 0;
         for (const Interval& iv : live) peak = std::max(peak, iv.off + iv.size);
         for (int lv = 0; lv < n_levels; ++lv) {
             live.erase(std::remove_if(live.begin(), live.end(), [&](const Interval& iv) { return iv.until < lv; }), live.end());
+            for (Staged& st : staged)
+                if (st.copy_level == lv) {
+                    st.off = arena_alloc(live, 1 << L.tensors[st.tensor].span_bits, st.until);
+                    arena_off[st.tensor] = st.off;
+                    peak = std::max(peak, st.off + (1 << L.tensors[st.tensor].span_bits));
+                }
             std::vector<int> here;
             for (int j = 0; j < n; ++j) if (level[j] == lv) here.push_back(j);
             std::sort(here.begin(), here.end(), [&](int x, int y) { return L.ops[sel[x]].nC > L.ops[sel[y]].nC; });
@@ -124,7 +156,7 @@ RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const
                 const int t = op.c;
                 int until = last_level(t);
                 if (t == L.root || until < 0) until = n_levels;       // the root (and anything unread) lives to the end
-                arena_off[t] = aligned_alloc(live, 1 << op.nC, until);
+                arena_off[t] = arena_alloc(live, 1 << op.nC, until);
                 peak = std::max(peak, arena_off[t] + (1 << op.nC));
             }
         }
@@ -244,11 +276,29 @@ RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const
         rp.elems_shared += (TA.amp ? 0 : op.elems_a) + (TB.amp ? 0 : op.elems_b);
     }
 
+    // ---- copy pseudo-ops of the staged operands: 256 elements per unit
+    for (const Staged& st : staged) {
+        RowOp d;
+        memset(&d, 0, sizeof(d));
+        const int span = L.tensors[st.tensor].span_bits;
+        d.hot.kind = kRowKindCopy;
+        d.hot.ntt = (uint8_t)std::min(span, 8);              // log2 elements per unit
+        d.hot.gen = 1;
+        d.oC = st.off;
+        rp.ops.push_back(d);
+        rp.lop.push_back(-1); rp.ref_a.push_back(st.tensor); rp.ref_b.push_back(-1); rp.ref_c.push_back(-1);
+        rp.in_arena_a.push_back(0); rp.in_arena_b.push_back(1); rp.in_arena_c.push_back(1);
+        level.push_back(st.copy_level);
+        unit_cost.push_back(4.0);
+        n_units.push_back(1 << std::max(0, span - 8));
+    }
+    const int n_all = (int)rp.ops.size();
+
     // ---- units per level: costly units first, so the round-robin over warps balances
     rp.level_start.assign(n_levels + 1, 0);
     for (int lv = 0; lv < n_levels; ++lv) {
         std::vector<int> here;
-        for (int j = 0; j < n; ++j) if (level[j] == lv) here.push_back(j);
+        for (int j = 0; j < n_all; ++j) if (level[j] == lv) here.push_back(j);
         std::stable_sort(here.begin(), here.end(), [&](int x, int y) { return unit_cost[x] > unit_cost[y]; });
         for (int j : here)
             for (int c = 0; c < n_units[j]; ++c) rp.units.push_back(RowUnit{(uint16_t)j, (uint16_t)c});
@@ -282,14 +332,26 @@ RowDeviceTables build_row_tables(const RowProgramHost& rp, const std::vector<Row
             memcpy(d.kA, op.kA, sizeof(d.kA)); memcpy(d.kB, op.kB, sizeof(d.kB));
             d.nkA = op.nkA; d.nkB = op.nkB;
             const int ntt = op.hot.ntt;
+            if (op.hot.kind == kRowKindCopy) {
+                // gA = first source element of this unit (set by the caller per op; advanced here per chunk), lC[0..1] =
+                // destination element offset (32 bits), 2^ntt elements
+                const long long first = (long long)un.chunk << 8;
+                d.gA = op.gA + (unsigned long long)first * (unsigned long long)rp.elem_bytes;
+                const unsigned dst = (unsigned)(op.oC + first);
+                d.lC[0] = (uint16_t)(dst & 0xFFFF); d.lC[1] = (uint16_t)(dst >> 16);
+                t.slots.push_back((uint16_t)t.descs.size());
+                t.descs.push_back(d);
+                t.desc_op.push_back(un.op);
+                continue;
+            }
             for (int lane = 0; lane < 32; ++lane) {
                 int tt; bool active;
                 if (op.hot.kind == kRowKindKred) { tt = lane & ((1 << ntt) - 1); active = (lane >> ntt) < (1 << op.hot.ks); }
                 else { tt = un.chunk * 32 + lane; active = tt < (1 << ntt); }
                 if (!active) { d.lA[lane] = d.lB[lane] = 0; d.lC[lane] = kRowNull; continue; }
-                d.lA[lane] = (uint16_t)(op.oA ^ eval_segs(op.tA, op.nsA, (unsigned)tt));
-                d.lB[lane] = (uint16_t)(op.oB ^ eval_segs(op.tB, op.nsB, (unsigned)tt));
-                d.lC[lane] = (uint16_t)(op.oC ^ eval_segs(op.tC, op.nsC, (unsigned)tt));
+                d.lA[lane] = (uint16_t)(op.oA + eval_segs(op.tA, op.nsA, (unsigned)tt));
+                d.lB[lane] = (uint16_t)(op.oB + eval_segs(op.tB, op.nsB, (unsigned)tt));
+                d.lC[lane] = (uint16_t)(op.oC + eval_segs(op.tC, op.nsC, (unsigned)tt));
             }
             t.slots.push_back((uint16_t)t.descs.size());
             t.descs.push_back(d);

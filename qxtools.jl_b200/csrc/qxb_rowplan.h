@@ -13,6 +13,8 @@ struct RowPlanOptions {
     int max_tile_bits = 4;        // ma + nb <= this (each side <= 2)
     int tile_reg_budget = 100;    // 32-bit registers for staged operands + accumulators (chooses the K chunk)
     bool alap = true;             // schedule every op as late as its consumers allow
+    bool stage_shared = true;     // copy operands shared by all rows into the arena one level before their first use
+    int stage_max_bits = 12;      // ... when they span at most 2^n elements
     long long max_arena_bytes = 200 * 1024;
 };
 
@@ -21,7 +23,7 @@ struct RowProgramHost {
     std::string why;              // why not, when !ok
     Phase phase = PH_CHUNK;
     std::vector<RowOp> ops;       // descriptors; g* pointers and fixed-variable offsets are filled in per launch
-    std::vector<int> lop;         // index into Lowered::ops
+    std::vector<int> lop;         // index into Lowered::ops (-1: copy pseudo-op of a staged operand, source = ref_a)
     std::vector<int> ref_a, ref_b, ref_c;          // LTensor indices
     std::vector<char> in_arena_a, in_arena_b, in_arena_c;
     std::vector<RowUnit> units;
@@ -29,6 +31,7 @@ struct RowProgramHost {
     int n_levels = 0;
     std::vector<RowLeaf> leaves;
     int arena_elems = 0;          // per row (chunk phase)
+    int elem_bytes = 16;
     int root_off = 0, root_span = 0;
     double flops_per_row = 0;     // 8 * complex MACs
     double elems_per_row_amp = 0; // algorithmic elements of per-row tensors (A, B, C of every op)

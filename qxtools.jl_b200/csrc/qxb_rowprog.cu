@@ -44,9 +44,9 @@ __device__ __forceinline__ void row_tile(const RowOpHot* __restrict__ h, const R
     const int nK = h->nK;
     int xa[TM], xb[TN], kta[KK], ktb[KK];
 #pragma unroll
-    for (int j = 0; j < TM; ++j) xa[j] = bA ^ h->aT[j];
+    for (int j = 0; j < TM; ++j) xa[j] = bA + h->aT[j];
 #pragma unroll
-    for (int j = 0; j < TN; ++j) xb[j] = bB ^ h->bT[j];
+    for (int j = 0; j < TN; ++j) xb[j] = bB + h->bT[j];
 #pragma unroll
     for (int k = 0; k < KK; ++k) { kta[k] = h->ktA[k]; ktb[k] = h->ktB[k]; }
     R2 acc[TM][TN];
@@ -58,16 +58,16 @@ __device__ __forceinline__ void row_tile(const RowOpHot* __restrict__ h, const R
     for (int ch = 0; ch < nch; ++ch) {
         const int kb = ch << KC;
         int ka = h->ktA[kb & 15], kbo = h->ktB[kb & 15];
-        if (nK > 4) { ka ^= rseg(op->kA, op->nkA, (unsigned)kb >> 4); kbo ^= rseg(op->kB, op->nkB, (unsigned)kb >> 4); }
+        if (nK > 4) { ka += rseg(op->kA, op->nkA, (unsigned)kb >> 4); kbo += rseg(op->kB, op->nkB, (unsigned)kb >> 4); }
         R2 av[TM][KK], bv[TN][KK];
 #pragma unroll
         for (int j = 0; j < TM; ++j)
 #pragma unroll
-            for (int k = 0; k < KK; ++k) av[j][k] = pA[xa[j] ^ ka ^ kta[k]];
+            for (int k = 0; k < KK; ++k) av[j][k] = pA[xa[j] + ka + kta[k]];
 #pragma unroll
         for (int j = 0; j < TN; ++j)
 #pragma unroll
-            for (int k = 0; k < KK; ++k) bv[j][k] = pB[xb[j] ^ kbo ^ ktb[k]];
+            for (int k = 0; k < KK; ++k) bv[j][k] = pB[xb[j] + kbo + ktb[k]];
 #pragma unroll
         for (int jm = 0; jm < TM; ++jm)
 #pragma unroll
@@ -78,7 +78,7 @@ __device__ __forceinline__ void row_tile(const RowOpHot* __restrict__ h, const R
 #pragma unroll
     for (int jm = 0; jm < TM; ++jm)
 #pragma unroll
-        for (int jn = 0; jn < TN; ++jn) pC[bC ^ h->cT[jm * TN + jn]] = acc[jm][jn];
+        for (int jn = 0; jn < TN; ++jn) pC[bC + h->cT[jm * TN + jn]] = acc[jm][jn];
 }
 
 // Ops with < 32 thread-tiles: the spare lane bits split K (interleaved), partial sums meet by xor-shuffles.
@@ -91,11 +91,26 @@ __device__ __forceinline__ void row_kred(const RowOpHot* __restrict__ h, const R
     R2 acc; acc.x = 0; acc.y = 0;
     if (active) {
         const int nl = 1 << (nK - ks);
-        for (int kl = 0; kl < nl; ++kl) {
-            const int k = ksub | (kl << ks);
-            int ka = h->ktA[k & 15], kbo = h->ktB[k & 15];
-            if (nK > 4) { ka ^= rseg(op->kA, op->nkA, (unsigned)k >> 4); kbo ^= rseg(op->kB, op->nkB, (unsigned)k >> 4); }
-            rcmac(acc, pA[bA ^ ka], pB[bB ^ kbo]);
+        auto koffs = [&](int k, int& ka, int& kbo) {
+            ka = h->ktA[k & 15]; kbo = h->ktB[k & 15];
+            if (nK > 4) { ka += rseg(op->kA, op->nkA, (unsigned)k >> 4); kbo += rseg(op->kB, op->nkB, (unsigned)k >> 4); }
+        };
+        int kl = 0;
+        for (; kl + 4 <= nl; kl += 4) {                      // four k per round: the loads of a round are independent
+            R2 a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int ka, kbo;
+                koffs(ksub | ((kl + q) << ks), ka, kbo);
+                a[q] = pA[bA + ka]; b[q] = pB[bB + kbo];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rcmac(acc, a[q], b[q]);
+        }
+        for (; kl < nl; ++kl) {
+            int ka, kbo;
+            koffs(ksub | (kl << ks), ka, kbo);
+            rcmac(acc, pA[bA + ka], pB[bB + kbo]);
         }
     }
     for (int i = 0; i < ks; ++i) {
@@ -131,6 +146,13 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+template <typename R2>
+__device__ __forceinline__ void cp_async_elem(R2* smem_dst, const R2* gsrc) {      // one element: 8 or 16 bytes
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (sizeof(R2) == 16) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_but_newest() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -189,10 +211,19 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowprog_kernel(const __grid_co
                 // next slot of this warp: same level, next level, or the first slot of the next row
                 int ns = s + kRowWarps;
                 if (ns >= s1) ns = lv + 1 < P.n_levels ? s1 + warp : (row + gridDim.x < P.n_rows ? P.level_start[0] + warp : -1);
+                const RowOpHot* __restrict__ h = &op->hot;
+                if (di != kRowNull && h->kind == kRowKindCopy) {
+                    // staged operand: 2^ntt elements global -> arena; committed BEFORE the descriptor prefetch so that
+                    // "all groups but the newest" at the level barrier means "every copy has landed"
+                    const int n = 1 << h->ntt;
+                    const unsigned dst = (unsigned)op->lC[0] | ((unsigned)op->lC[1] << 16);
+                    const R2* src = reinterpret_cast<const R2*>(op->gA);
+                    for (int i = lane; i < n; i += 32) cp_async_elem<R2>(arena + dst + i, src + i);
+                    cp_async_commit();
+                }
                 par ^= 1;
                 prefetch(ns, par);
-                if (di == kRowNull) continue;
-                const RowOpHot* __restrict__ h = &op->hot;
+                if (di == kRowNull || h->kind == kRowKindCopy) continue;
                 const int bA = op->lA[lane], bB = op->lB[lane], bC = op->lC[lane];
                 const R2 *pA = arena, *pB = arena;
                 R2* pC = arena;
@@ -218,6 +249,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowprog_kernel(const __grid_co
                 default: row_tile_kc<R2, 2, 2>(h, op, arena, pA, pB, pC, bA, bB, bC); break;
                 }
             }
+            cp_async_wait_but_newest();              // staged copies of this level (the descriptor prefetch may stay in flight)
             __syncthreads();
             if (P.timing && blockIdx.x == 0 && tid == 0) {     // per-level cycles of CTA 0 (diagnostics)
                 const long long t = clock64();

@@ -29,12 +29,13 @@ struct RSeg { unsigned char src, dst, len, pad; };
 
 // kinds of inner loop
 constexpr int kRowKindKred = 0;         // <= 16 thread-tiles: lanes also split K, shuffle-reduced
+constexpr int kRowKindCopy = 255;       // staging: 2^ntt elements from global memory (gA) into the arena at lC[0] | lC[1] << 16
 // tile kinds: 1 + (((ma * 3 + nb) * 3 + kc) * 2 + gen)
 inline int row_tile_kind(int ma, int nb, int kc, int gen) { return 1 + (((ma * 3 + nb) * 3 + kc) * 2 + gen); }
 
 // HOT part (128 bytes): the tables the inner loops index; read from the warp's shared-memory slot (broadcasts).  Offsets are ELEMENT indices relative to the
 // tensor (all < 2^16: row programs are only built for tensors of <= 2^16 elements), made of disjoint bits, so
-// they combine with XOR (== OR == ADD); arena tensors are aligned to their size, so the arena offset XORs in too.
+// they simply ADD; the per-lane bases (RowUnitDesc) carry the arena offset, so a tensor may sit anywhere in the arena.
 struct alignas(16) RowOpHot {
     uint16_t aT[4], bT[4];      // register-tile offsets into A (M-only bits) / B (N-only bits)
     uint16_t cT[16];            // register-tile offsets into C, index jm * 2^nb + jn

@@ -2,7 +2,7 @@
 
 Test infrastructure.  ``qxb_debug_rowprog`` serialises the program of one phase exactly as the executor hands it to
 ``rowprog_kernel``: dependency levels, warp units, the size-aligned shared-memory arena plan, the 128-byte hot
-descriptors (register-tile / K tables, combined by XOR) and the per-unit lane tables (base offsets of each lane's
+descriptors (register-tile / K tables, added to the lane bases) and the per-unit lane tables (base offsets of each lane's
 thread-tile, evaluated on the host from the thread-tile -> address segments).  This
 module mirrors the structs (csrc/qxb_rowprog.h) and walks the same loops as the kernel -- level, unit, lane,
 thread-tile, register tile, K chunk, k; the K-splitting lanes of the small-op path -- on a numpy arena per bitstring
@@ -114,8 +114,16 @@ def _run_unit(op: RowUnitDesc, mA: _Mem, mB: _Mem, mC: _Mem, fixA, fixB, stores,
     h = op.hot
     lane = np.arange(32, dtype=np.int64)
     nK = h.nK
-    bA = np.array(op.lA[:], dtype=np.int64) ^ fixA
-    bB = np.array(op.lB[:], dtype=np.int64) ^ fixB
+    if h.kind == 255:                 # staged operand: 2^ntt elements from the tensor's base (+ chunk offset) into the arena
+        n = 1 << h.ntt
+        es = 16 if dtype == np.complex128 else 8
+        first = op.gA // es           # the dump leaves the pointer null: gA = byte offset of this unit's first element
+        dst = op.lC[0] | (op.lC[1] << 16)
+        i = np.arange(n, dtype=np.int64)
+        stores.append((mC, dst + i, mA.ld(first + i)))
+        return
+    bA = np.array(op.lA[:], dtype=np.int64) + fixA
+    bB = np.array(op.lB[:], dtype=np.int64) + fixB
     bC = np.array(op.lC[:], dtype=np.int64)
     act = bC != K_NULL
 
@@ -123,8 +131,8 @@ def _run_unit(op: RowUnitDesc, mA: _Mem, mB: _Mem, mC: _Mem, fixA, fixB, stores,
         ka = np.array([h.ktA[int(x) & 15] for x in k], dtype=np.int64)
         kb = np.array([h.ktB[int(x) & 15] for x in k], dtype=np.int64)
         if nK > 4:
-            ka ^= _rseg(op.kA, op.nkA, k >> 4)
-            kb ^= _rseg(op.kB, op.nkB, k >> 4)
+            ka += _rseg(op.kA, op.nkA, k >> 4)
+            kb += _rseg(op.kB, op.nkB, k >> 4)
         return ka, kb
 
     if h.kind == 0:                   # kred: lanes split K
@@ -135,8 +143,8 @@ def _run_unit(op: RowUnitDesc, mA: _Mem, mB: _Mem, mC: _Mem, fixA, fixB, stores,
         for kl in range(1 << (nK - ks)):
             k = ksub | (kl << ks)
             ka, kb = koff(k)
-            a = mA.ld(np.where(act, bA ^ ka, 0))
-            b = mB.ld(np.where(act, bB ^ kb, 0))
+            a = mA.ld(np.where(act, bA + ka, 0))
+            b = mB.ld(np.where(act, bB + kb, 0))
             acc += np.where(act, a * b, 0)
         for i in range(ks):
             acc = acc + acc[lane ^ (1 << (ntt + i))]
@@ -154,14 +162,14 @@ def _run_unit(op: RowUnitDesc, mA: _Mem, mB: _Mem, mC: _Mem, fixA, fixB, stores,
         kb0 = ch << kc
         ka, kbo = koff(np.full(32, kb0, dtype=np.int64))
         for k in range(KK):
-            av = [mA.ld(bA ^ h.aT[j] ^ ka ^ h.ktA[k]) for j in range(TM)]
-            bv = [mB.ld(bB ^ h.bT[j] ^ kbo ^ h.ktB[k]) for j in range(TN)]
+            av = [mA.ld(bA + h.aT[j] + ka + h.ktA[k]) for j in range(TM)]
+            bv = [mB.ld(bB + h.bT[j] + kbo + h.ktB[k]) for j in range(TN)]
             for jm in range(TM):
                 for jn in range(TN):
                     acc[jm, jn] += av[jm] * bv[jn]
     for jm in range(TM):
         for jn in range(TN):
-            stores.append((mC, (bC ^ h.cT[jm * TN + jn])[act], acc[jm, jn][act]))
+            stores.append((mC, (bC + h.cT[jm * TN + jn])[act], acc[jm, jn][act]))
 
 
 def run_program(rp: RowProgram, resolve, arena, dtype, fix=None, check_races=True):
@@ -180,9 +188,12 @@ def run_program(rp: RowProgram, resolve, arena, dtype, fix=None, check_races=Tru
                 continue
             op = rp.descs[di]
             j = rp.desc_op[di]
-            mA = _Mem(arena, 0) if rp.in_arena_a[j] else resolve(rp.ref_a[j])
-            mB = _Mem(arena, 0) if rp.in_arena_b[j] else resolve(rp.ref_b[j])
-            mC = _Mem(arena, 0) if rp.in_arena_c[j] else resolve(rp.ref_c[j])
+            if rp.lop[j] < 0:             # copy pseudo-op: source = the whole tensor from its base
+                mA, mB, mC = resolve(rp.ref_a[j], base=True), None, _Mem(arena, 0)
+            else:
+                mA = _Mem(arena, 0) if rp.in_arena_a[j] else resolve(rp.ref_a[j])
+                mB = _Mem(arena, 0) if rp.in_arena_b[j] else resolve(rp.ref_b[j])
+                mC = _Mem(arena, 0) if rp.in_arena_c[j] else resolve(rp.ref_c[j])
             assert op.hot.gen == (0 if (rp.in_arena_a[j] and rp.in_arena_b[j] and rp.in_arena_c[j]) else 1)
             fa, fb = fix.get(j, (0, 0))
             _run_unit(op, mA, mB, mC, fa, fb, stores, dtype)
@@ -232,9 +243,9 @@ def run_block_rows(graph, desc, free_mask, data, bits, fixed_vals, dtype=np.comp
             acc += A[a0 + fa + ka[k]] * B[b0 + fb + kb[k]]
         Cb[c0 + c] = acc
 
-    def resolve(ti):
-        buf, base = locate(T[ti])
-        return _Mem(buf, base)
+    def resolve(ti, base=False):
+        buf, off = locate({**T[ti], "fixed": []} if base else T[ti])
+        return _Mem(buf, off)
 
     rp_block = dump(graph, free_mask, 1)
     if any(o["phase"] == "block" for o in ops):
@@ -258,6 +269,8 @@ def run_block_rows(graph, desc, free_mask, data, bits, fixed_vals, dtype=np.comp
         # fixed-variable offsets of arena-resident output leaves are XORed into the lane bases per launch by the executor
         fix = {}
         for j in range(len(rp.ref_a)):
+            if rp.lop[j] < 0:
+                continue
             fa = sum(int(fixed_vals[v]) << pos for v, pos in T[rp.ref_a[j]]["fixed"]) if rp.in_arena_a[j] else 0
             fb = sum(int(fixed_vals[v]) << pos for v, pos in T[rp.ref_b[j]]["fixed"]) if rp.in_arena_b[j] else 0
             if fa or fb:
