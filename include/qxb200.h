@@ -56,15 +56,18 @@ typedef struct qxb_options {
                                   (DMMA for ComplexF64, 3xTF32 for ComplexF32) wherever the tile shape allows */
     /* ---- round 2: every kernel-selection knob is an option (0 = the library's default; the QXB_* environment
      *      variables of round 1 are still read, as overrides for experiments, only where the option is 0) ---- */
-    int32_t row_programs;      /* 0 = auto: run a whole phase of the tree as ONE persistent kernel with the row's
-                                  intermediates in shared memory whenever they fit (csrc/qxb_rowprog.h); 1 = never  */
+    int32_t row_programs;      /* row programs (csrc/qxb_rowprog.h: a whole phase of the tree as ONE persistent kernel).
+                                  0 = auto: the block phase always, the chunk phase (a bitstring row's intermediates
+                                  in shared memory) for calls of <= row_chunk_max_amps bitstrings; 1 = never;
+                                  2 = both phases whenever the row fits; 3 = block phase only                      */
     int32_t min_lob;           /* 5..8: thread bits contract_kernel keeps (register tiles for small nodes); 0 = 6  */
     int32_t kc_regs_multi;     /* register budget of the K chunk, multi-chunk nodes; 0 = 160                      */
     int32_t kc_regs_one;       /* register budget of the K chunk, single-chunk nodes; 0 = 128                     */
     int32_t smem_tma;          /* 1 = TMA-staged contract_tma_kernel for broadcast-type nodes; 0 = off            */
-    int32_t row_min_tt_bits;   /* row programs: keep >= 2^n thread-tiles per node when choosing the register tile; 0 = 7 */
+    int32_t row_min_tt_bits;   /* row programs: keep >= 2^n thread-tiles per node when choosing the register tile; 0 = 6 */
     int32_t row_tile_regs;     /* row programs: registers for staged operands + accumulators; 0 = 100            */
     int32_t row_ctas_per_sm;   /* row programs: resident CTAs per SM; 0 = as many as the arena allows, at most 2  */
+    int32_t row_chunk_max_amps;/* auto mode: largest call (bitstrings) whose chunk phase runs as a row program; 0 = 8192 */
 } qxb_options;
 
 /* library */

@@ -88,7 +88,7 @@ struct Variant {
     std::vector<OpProfile> prof;
     // row programs (qxb_rowprog.h): the chunk phase as one persistent kernel with the row's intermediates in shared
     // memory, the block phase as a single-CTA program; device copies of the descriptors per set of fixed values
-    bool use_rows = false;
+    bool rows_block = false, rows_chunk = false;         // which phases have a row program
     RowProgramHost rp_block, rp_chunk;
     struct RowDev {
         DevBuf descs_block, slots_block, descs_chunk, slots_chunk, leaves;
@@ -598,25 +598,35 @@ void run_const_phase(const RunCtx& c) {
 // Host part: levels, units, arena plan, descriptors (qxb_rowplan.cpp).  Used when the saved tensor is a scalar,
 // the root is produced in the chunk phase and the live set of one bitstring row fits shared memory.
 void build_row_programs(qxb_graph* g, Variant& v) {
-    v.use_rows = false;
+    v.rows_block = v.rows_chunk = false;
     if (knob(0, "QXB_ROWPROG", 1) == 0 || g->opts.row_programs == 1) return;
-    for (const auto& rm : v.L.root_modes) if (rm.nbits > 0) return;     // tensor-valued save: per-op path
     RowPlanOptions o;
-    o.min_tt_bits = knob(g->opts.row_min_tt_bits, "QXB_ROW_MIN_TT", 7);
+    o.min_tt_bits = knob(g->opts.row_min_tt_bits, "QXB_ROW_MIN_TT", 6);
     o.tile_reg_budget = knob(g->opts.row_tile_regs, "QXB_ROW_TILE_REGS", 100);
     o.alap = knob(0, "QXB_ROW_ALAP", 1) != 0;
     o.max_tile_bits = knob(0, "QXB_ROW_MAX_TILE", 4);
     o.stage_shared = knob(0, "QXB_ROW_STAGE", 1) != 0;
     o.max_arena_bytes = 227 * 1024 - (long long)row_fixed_smem_bytes(2048 + kRowWarps * kRowMaxLevels);   // descriptor buffers + slot table
+    // block phase (slice-only nodes: hundreds of tiny contractions, pure launch latency as separate kernels)
+    v.rp_block = build_row_program(v.L, PH_BLOCK, g->dtype, o);
+    v.rows_block = v.rp_block.ok;
+    // chunk phase: needs a scalar root produced in the chunk phase and a row that fits shared memory
+    for (const auto& rm : v.L.root_modes) if (rm.nbits > 0) return;     // tensor-valued save: per-op path
     v.rp_chunk = build_row_program(v.L, PH_CHUNK, g->dtype, o);
-    if (!v.rp_chunk.ok) return;
-    bool has_block = false;
-    for (const LOp& op : v.L.ops) has_block |= op.phase == PH_BLOCK;
-    if (has_block) {
-        v.rp_block = build_row_program(v.L, PH_BLOCK, g->dtype, o);
-        if (!v.rp_block.ok) return;
-    }
-    v.use_rows = true;
+    v.rows_chunk = v.rp_chunk.ok;
+}
+
+// Which phases of this call run as row programs.  The block program always (one 35 us launch instead of ~250
+// kernels).  The chunk program wins while the step is launch-latency-bound (3 launches instead of ~350: 20 x faster
+// at 10 bitstrings); with only two rows in flight per SM it is latency-bound itself, and above ~10^4 bitstrings
+// the per-op kernels (HBM-bound, every SM streaming) are faster on a B200 (profiles/r2_summary.md).
+bool chunk_as_rows(const qxb_graph* g, const Variant& v, int64_t n_amp) {
+    if (!v.rows_chunk) return false;
+    if (g->opts.row_programs == 2) return true;
+    if (g->opts.row_programs == 3) return false;
+    const bool has_block = std::any_of(v.L.ops.begin(), v.L.ops.end(), [](const LOp& op) { return op.phase == PH_BLOCK; });
+    if (has_block && !v.rows_block) return false;
+    return n_amp <= (int64_t)knob(g->opts.row_chunk_max_amps, "QXB_ROW_CHUNK_MAX_AMPS", 8192);
 }
 
 // Device copies of the descriptors with the pointers of this block resolved (fixed slice values, arena bases).
@@ -627,7 +637,7 @@ Variant::RowDev& row_device_tables(const RunCtx& c) {
     std::vector<int64_t> key(k, 0);
     for (int i = 0; i < k; ++i) if (!((v.L.free_mask >> i) & 1ull)) key[i] = c.fixed_vals[i];
     Variant::RowDev& rd = v.rowdev[key];
-    if (rd.descs_chunk.p && rd.block_base == g->block_arena.p && rd.const_base == v.const_arena.p) return rd;
+    if ((rd.descs_chunk.p || rd.descs_block.p) && rd.block_base == g->block_arena.p && rd.const_base == v.const_arena.p) return rd;
     rd.block_base = g->block_arena.p; rd.const_base = v.const_arena.p;
     auto fixed_off = [&](const LTensor& T) {
         long long off = 0;
@@ -656,10 +666,10 @@ Variant::RowDev& row_device_tables(const RunCtx& c) {
         CUDA_OK(cudaMemcpy(d_descs.p, t.descs.data(), t.descs.size() * sizeof(RowUnitDesc), cudaMemcpyHostToDevice));
         CUDA_OK(cudaMemcpy(d_slots.p, t.slots.data(), t.slots.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     };
-    if (v.rp_block.ok) resolve(v.rp_block, rd.descs_block, rd.slots_block, rd.level_start_block);
-    resolve(v.rp_chunk, rd.descs_chunk, rd.slots_chunk, rd.level_start_chunk);
+    if (v.rows_block) resolve(v.rp_block, rd.descs_block, rd.slots_block, rd.level_start_block);
+    if (v.rows_chunk) resolve(v.rp_chunk, rd.descs_chunk, rd.slots_chunk, rd.level_start_chunk);
     rd.leaves.reserve(std::max<size_t>(v.rp_chunk.leaves.size(), 1) * sizeof(RowLeaf));
-    if (!v.rp_chunk.leaves.empty())
+    if (v.rows_chunk && !v.rp_chunk.leaves.empty())
         CUDA_OK(cudaMemcpy(rd.leaves.p, v.rp_chunk.leaves.data(), v.rp_chunk.leaves.size() * sizeof(RowLeaf), cudaMemcpyHostToDevice));
     return rd;
 }
@@ -779,8 +789,9 @@ StepPlan prepare_step(qxb_graph* g, std::vector<Block> blocks, int64_t n_amp) {
         sp.variants.push_back(v);
         const int64_t block_bytes = std::max<int64_t>(v->L.block_elems, 2) * es;
         // a row program keeps the chunk phase in shared memory: no HBM workspace per bitstring
-        const int64_t per_amp = v->use_rows ? 0 : std::max<int64_t>(v->L.chunk_elems_per_amp, 2) * es;
-        if (v->use_rows) {
+        const bool rows = chunk_as_rows(g, *v, n_amp);
+        const int64_t per_amp = rows ? 0 : std::max<int64_t>(v->L.chunk_elems_per_amp, 2) * es;
+        if (rows) {
             max_block = std::max(max_block, block_bytes);
             g->stats.workspace_bytes = std::max<int64_t>(g->stats.workspace_bytes, block_bytes + (int64_t)v->const_arena.bytes);
             continue;
@@ -874,20 +885,24 @@ std::vector<Node> build_step(qxb_graph* g, const StepPlan& sp, const uint8_t* d_
         Variant* v = sp.variants[bi];
         Lowered& L = v->L;
         RunCtx c{g, v, v->key, blk.vals.data(), 1};
-        if (v->use_rows) {
+        const bool has_block = std::any_of(L.ops.begin(), L.ops.end(), [](const LOp& op) { return op.phase == PH_BLOCK; });
+        const bool rows_chunk = chunk_as_rows(g, *v, n_amp);
+        const bool rows_block = v->rows_block && has_block && g->opts.row_programs != 1;
+        int block_node = -1;                          // the single-CTA block program, when the block phase runs as one
+        if (rows_block) {
+            Variant::RowDev& rd = row_device_tables(c);
+            Node b = row_node(c, rd, false, d_bits, 0);
+            b.deps.push_back(sink);
+            block_node = (int)nodes.size();
+            nodes.push_back(std::move(b));
+        }
+        if (rows_chunk) {
             // the whole block as two launches: block-phase program (one CTA), then one persistent kernel that takes
             // every bitstring row through the chunk phase in shared memory and adds the root into its accumulator
             Variant::RowDev& rd = row_device_tables(c);
-            int after = sink;
-            if (v->rp_block.ok) {
-                Node b = row_node(c, rd, false, d_bits, 0);
-                b.deps.push_back(sink);
-                after = (int)nodes.size();
-                nodes.push_back(std::move(b));
-            }
             c.n = n_amp;
             Node r = row_node(c, rd, true, d_bits, 0);
-            r.deps.push_back(after);
+            r.deps.push_back(block_node >= 0 ? block_node : sink);
             sink = (int)nodes.size();
             nodes.push_back(std::move(r));
             continue;
@@ -895,6 +910,7 @@ std::vector<Node> build_step(qxb_graph* g, const StepPlan& sp, const uint8_t* d_
         std::vector<int> node_of(L.ops.size(), -1);   // block-phase ops of this block
         for (size_t i = 0; i < L.ops.size(); ++i) {
             if (L.ops[i].phase != PH_BLOCK) continue;
+            if (block_node >= 0) { node_of[i] = block_node; continue; }       // produced by the block program
             Node n = contract_node(c, (int)i);
             for (int d : L.ops[i].deps) if (node_of[d] >= 0) n.deps.push_back(node_of[d]);
             if (n.deps.empty()) n.deps.push_back(sink);
@@ -1638,7 +1654,7 @@ int64_t qxb_debug_rowprog(qxb_graph* g, uint64_t free_mask, int phase, void* buf
         Lowered L = lower(g->prog, free_mask, !g->opts.sum_at_root);
         plan_memory(L);
         RowPlanOptions o;
-        o.min_tt_bits = knob(g->opts.row_min_tt_bits, "QXB_ROW_MIN_TT", 7);
+        o.min_tt_bits = knob(g->opts.row_min_tt_bits, "QXB_ROW_MIN_TT", 6);
         o.tile_reg_budget = knob(g->opts.row_tile_regs, "QXB_ROW_TILE_REGS", 100);
         o.alap = knob(0, "QXB_ROW_ALAP", 1) != 0;
         o.max_tile_bits = knob(0, "QXB_ROW_MAX_TILE", 4);

@@ -9,7 +9,7 @@
 namespace qxb {
 
 struct RowPlanOptions {
-    int min_tt_bits = 7;          // keep at least 2^min_tt_bits thread-tiles per op when choosing the register tile
+    int min_tt_bits = 6;          // keep at least 2^min_tt_bits thread-tiles per op when choosing the register tile
     int max_tile_bits = 4;        // ma + nb <= this (each side <= 2)
     int tile_reg_budget = 100;    // 32-bit registers for staged operands + accumulators (chooses the K chunk)
     bool alap = true;             // schedule every op as late as its consumers allow
