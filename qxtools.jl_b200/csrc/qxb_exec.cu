@@ -626,7 +626,7 @@ bool chunk_as_rows(const qxb_graph* g, const Variant& v, int64_t n_amp) {
     if (g->opts.row_programs == 3) return false;
     const bool has_block = std::any_of(v.L.ops.begin(), v.L.ops.end(), [](const LOp& op) { return op.phase == PH_BLOCK; });
     if (has_block && !v.rows_block) return false;
-    return n_amp <= (int64_t)knob(g->opts.row_chunk_max_amps, "QXB_ROW_CHUNK_MAX_AMPS", 8192);
+    return n_amp <= (int64_t)knob(g->opts.row_chunk_max_amps, "QXB_ROW_CHUNK_MAX_AMPS", 512);
 }
 
 // Device copies of the descriptors with the pointers of this block resolved (fixed slice values, arena bases).

@@ -221,14 +221,18 @@ def test_edge_cases_and_errors(gpu):
     with pytest.raises(QxbError) as e:
         g.compile()                              # already compiled
     assert e.value.code == -2
-    # a budget that cannot hold one bitstring row is a memory error, and a tight one forces batching
+    # per-op kernels (the intermediates of a bitstring row live in HBM): a budget that cannot hold one row is a memory
+    # error, and a tight one forces batching
     with pytest.raises(QxbError) as e:
-        Graph.from_dsl(txt, data, "c64").compile(hbm_budget_bytes=64).amplitudes(bs)
+        Graph.from_dsl(txt, data, "c64").compile(hbm_budget_bytes=64, row_programs=False).amplitudes(bs)
     assert e.value.code == -5
-    gt = Graph.from_dsl(txt, data, "c64").compile(hbm_budget_bytes=40_000)
+    gt = Graph.from_dsl(txt, data, "c64").compile(hbm_budget_bytes=40_000, row_programs=False)
     out = gt.amplitudes(bs)
     assert gt.stats()["amp_batch"] < len(bs)
     assert rel_err(out, orc.amplitudes(cmds, data, bs), 12) < 1e-10
+    # row programs keep a row's intermediates in shared memory: the same tiny budget is enough
+    gr = Graph.from_dsl(txt, data, "c64").compile(hbm_budget_bytes=40_000, row_programs="all")
+    assert rel_err(gr.amplitudes(bs), orc.amplitudes(cmds, data, bs), 12) < 1e-10
     # missing leaf data
     with pytest.raises(QxbError) as e:
         Graph.from_dsl(txt, {k: v for k, v in list(data.items())[1:]}, "c64").compile()

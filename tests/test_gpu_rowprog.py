@@ -19,6 +19,15 @@ def fused(g):
     return st["kernel_launches"] <= 2 + 2 * st["n_blocks"]
 
 
+def fused_block(g):
+    """True when the block phase of the last (single-block) call ran as ONE program: launches = 1 + the chunk-phase
+    contractions + output leaves, root reduction, finalize."""
+    ops = g.describe()["ops"]
+    n_block = sum(1 for o in ops if o["phase"] == "block")
+    n_chunk = sum(1 for o in ops if o["phase"] == "chunk")
+    return n_block < 2 or g.stats()["kernel_launches"] <= n_chunk + 4
+
+
 @pytest.mark.parametrize("dtype", ["c64", "c32"])
 @pytest.mark.parametrize("shape", [(3, 3, 8, 2), (3, 4, 10, 3), (4, 4, 12, 4)])
 def test_rows_vs_oracle_and_per_op(gpu, dtype, shape):
@@ -81,11 +90,15 @@ def test_many_rows_per_cta(gpu):
     txt, data, _ = rqc_case(3, 4, 10, 3)
     n = 148 * 2 * 3 + 5
     bits = np.random.default_rng(3).integers(0, 2, (n, 12)).astype(np.uint8)
-    g = Graph.from_dsl(txt, data, "c64").compile()
+    g = Graph.from_dsl(txt, data, "c64").compile(row_programs="all")
     got = g.amplitudes(bits)
     assert fused(g)
+    ga = Graph.from_dsl(txt, data, "c64").compile()          # auto: above row_chunk_max_amps the chunk phase runs per op
+    got_auto = ga.amplitudes(bits)
+    assert not fused(ga) and fused_block(ga)
     g0 = Graph.from_dsl(txt, data, "c64").compile(row_programs=False)
     ref = g0.amplitudes(bits)
+    assert np.max(np.abs(got_auto - ref)) < 1e-12 * np.max(np.abs(ref))
     assert np.max(np.abs(got - ref)) < 1e-12 * np.max(np.abs(ref))
     idx = [0, 1, 295, 296, 297, n - 1]
     bs = ["".join("01"[b] for b in bits[i]) for i in idx]
