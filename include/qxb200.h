@@ -67,6 +67,8 @@ typedef struct qxb_options {
     int32_t row_min_tt_bits;   /* row programs: keep >= 2^n thread-tiles per node when choosing the register tile; 0 = 6 */
     int32_t row_tile_regs;     /* row programs: registers for staged operands + accumulators; 0 = 100            */
     int32_t row_ctas_per_sm;   /* row programs: resident CTAs per SM; 0 = as many as the arena allows, at most 2  */
+    int32_t ring;              /* 0 = auto: nodes whose operand and result rows are small dense per-bitstring rows run on
+                                  the TMA ring kernel (bulk copies in, bulk store out, csrc/qxb_rowprog.h); 1 = never  */
     int32_t row_chunk_max_amps;/* auto mode: largest call (bitstrings) whose chunk phase runs as a row program; 0 = 512 */
 } qxb_options;
 

@@ -75,7 +75,7 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
 
-struct OpProfile { double ms = 0; double flops = 0; double bytes = 0; long long launches = 0; };
+struct OpProfile { double ms = 0; double flops = 0; double bytes = 0; long long launches = 0; const char* kernel = ""; };
 
 struct Variant {
     Lowered L;
@@ -98,6 +98,8 @@ struct Variant {
     std::map<std::vector<int64_t>, RowDev> rowdev;
     OpProfile prof_rows, prof_block_rows;                // profile mode: the two fused launches
     DevBuf row_timing;                                   // profile mode: per-level clock cycles of CTA 0 (chunk program)
+    struct RingDescs { DevBuf buf; int n_units = 0; bool tried = false; };
+    std::map<int, RingDescs> ring;                       // per op: unit descriptors of the TMA ring kernel
 };
 
 struct EventPair { cudaEvent_t a, b; int variant, op; };
@@ -138,6 +140,7 @@ struct qxb_graph {
         for (auto& kv : leafbuf) kv.second.release();
         for (auto& kv : variants) {
             kv.second->const_arena.release(); kv.second->outleaf_desc.release(); kv.second->row_timing.release();
+            for (auto& r : kv.second->ring) r.second.buf.release();
             for (auto& rd : kv.second->rowdev) {
                 rd.second.descs_block.release(); rd.second.slots_block.release(); rd.second.descs_chunk.release();
                 rd.second.slots_chunk.release(); rd.second.leaves.release();
@@ -416,6 +419,7 @@ struct Node {
     void* ms_ptr = nullptr; size_t ms_bytes = 0;
     void* pre_zero_ptr = nullptr; size_t pre_zero_bytes = 0;   // kernel nodes: region to clear first (split-K partial sums)
     int variant = -1, op = -1;           // contraction nodes: where to book profile time
+    const char* kname = "";              // which kernel family runs the node (profile dump)
     double flops = 0, bytes = 0;
     size_t smem = 0;
     template <typename T> void arg(const T& v) {
@@ -462,7 +466,7 @@ Node contract_node(const RunCtx& c, int i) {
         const void* tc = gemm_mode(g) == 2 ? gemm_mma_func(g->dtype, tmb, tnb) : nullptr;
         if (tc) {
             // tensor-core variant (DMMA / 3xTF32 mma.sync); persistent grid = SMs x resident CTAs
-            n.func = tc;
+            n.func = tc; n.kname = "gemm_tc";
             n.block = dim3((unsigned)gemm_mma_threads(g->dtype));
             n.smem = gemm_mma_smem_bytes(g->dtype);
             static std::map<const void*, int> resident;
@@ -476,7 +480,7 @@ Node contract_node(const RunCtx& c, int i) {
             }
             n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(q.tiles, (long long)g_num_sms * it->second)));
         } else {
-            n.func = gemm_func(g->dtype, tmb, tnb);
+            n.func = gemm_func(g->dtype, tmb, tnb); n.kname = "gemm_simt";
             n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(q.tiles, (long long)g_num_sms * 2)));
             n.block = dim3(1u << (tmb + tnb - 4));
         }
@@ -494,15 +498,15 @@ Node contract_node(const RunCtx& c, int i) {
             int sb = 0;
             while (outputs * std::ldexp(1.0, sb) < (double)cap && p.nK - sb > 13) ++sb;
             p.kc = sb;
-            n.func = kreduce_split_func(g->dtype);
+            n.func = kreduce_split_func(g->dtype); n.kname = "kreduce_split";
             n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>((long long)std::ldexp(outputs, sb), cap)));
             n.pre_zero_ptr = p.C;                                // partial sums are combined with atomicAdd
             n.pre_zero_bytes = (size_t)((C.amp ? c.n : 1) << C.span_bits) * g->es();
         } else if (p.nK >= 12 && outputs <= 8192.0) {
-            n.func = kreduce_block_func(g->dtype);           // very long K, few outputs: a block per output
+            n.func = kreduce_block_func(g->dtype); n.kname = "kreduce_block";          // very long K, few outputs: a block per output
             n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>((long long)outputs, cap)));
         } else {
-            n.func = kreduce_func(g->dtype);
+            n.func = kreduce_func(g->dtype); n.kname = "kreduce";
             const long long warps = (long long)outputs;
             n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>((warps * 32 + kThreads - 1) / kThreads, cap)));
         }
@@ -540,9 +544,62 @@ Node contract_node(const RunCtx& c, int i) {
                 tf = contract_tma_func(g->dtype, p.kc, p.ma, p.nb, p.kc == p.nK);
             if (tf) tma_stages = fit;
         }
+        // TMA ring kernel (qxb_rowprog.h): operand rows in by bulk copies, result row out by a bulk store, compute
+        // from shared memory into shared memory with a free thread <-> element mapping
+        if (knob(0, "QXB_RING", 1) != 0 && g->opts.ring != 1 && C.amp && (A.amp || B.amp) && p.U >= g_num_sms && p.nC >= 8 &&
+            A.lay.size() && B.lay.size() && op.elems_a == std::ldexp(1.0, A.span_bits) && op.elems_b == std::ldexp(1.0, B.span_bits) &&
+            A.span_bits <= 15 && B.span_bits <= 15 && p.nC <= 15) {
+            const size_t es = g->es();
+            const int nA = 1 << A.span_bits, nB = 1 << B.span_bits, nCe = 1 << p.nC;
+            const bool shA = !A.amp, shB = !B.amp;
+            const bool aligned = (nA * es) % 16 == 0 && (nB * es) % 16 == 0 && (nCe * es) % 16 == 0 &&
+                                 (uintptr_t)p.A % 16 == 0 && (uintptr_t)p.B % 16 == 0 && (uintptr_t)p.C % 16 == 0;
+            Variant::RingDescs& rd = c.v->ring[i];
+            if (aligned && !rd.tried) {
+                rd.tried = true;
+                RowPlanOptions ro;
+                ro.min_tt_bits = knob(0, "QXB_RING_MIN_TT", 7);
+                ro.tile_reg_budget = knob(0, "QXB_RING_TILE_REGS", 100);
+                std::string why;
+                std::vector<RowUnitDesc> descs = build_ring_descs(op, g->dtype, ro, why);
+                if (!descs.empty()) {
+                    rd.buf.reserve(descs.size() * sizeof(RowUnitDesc));
+                    CUDA_OK(cudaMemcpy(rd.buf.p, descs.data(), descs.size() * sizeof(RowUnitDesc), cudaMemcpyHostToDevice));
+                    rd.n_units = (int)descs.size();
+                }
+            }
+            int stages = 0;
+            if (aligned && rd.n_units > 0) {
+                const size_t budget = 220 * 1024;
+                for (int st = kRingMaxStages; st >= 2; --st)
+                    if (ring_smem_bytes(rd.n_units, nA, nB, nCe, shA, shB, st, es) <= budget) { stages = st; break; }
+            }
+            if (stages >= 2) {
+                RingLaunch R;
+                memset(&R, 0, sizeof(R));
+                R.descs = (const RowUnitDesc*)rd.buf.p; R.n_units = rd.n_units;
+                R.A = p.A; R.B = p.B; R.C = p.C; R.sUA = p.sUA; R.sUB = p.sUB; R.sUC = p.sUC; R.U = p.U;
+                R.nA = nA; R.nB = nB; R.nC = nCe; R.stages = stages;
+                n.func = ring_func(g->dtype); n.kname = "ring";
+                n.smem = ring_smem_bytes(rd.n_units, nA, nB, nCe, shA, shB, stages, es);
+                n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(p.U, (long long)g_num_sms)));
+                n.block = dim3(kRowThreads);
+                static std::set<const void*> ring_configured;
+                if (!ring_configured.count(n.func)) {
+                    CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                    ring_configured.insert(n.func);
+                }
+                n.arg(R);
+                n.variant = c.variant_key; n.op = i;
+                const double u = (double)p.U;
+                n.flops = 8.0 * op.macs_per_amp * u;
+                n.bytes = (double)g->es() * (op.elems_a * (A.amp ? c.n : 1) + op.elems_b * (B.amp ? c.n : 1) + op.elems_c * u);
+                return n;
+            }
+        }
         if (tf) {
             p.aBits = A.span_bits; p.bBits = B.span_bits;
-            n.func = tf;
+            n.func = tf; n.kname = "tma";
             n.smem = stage * (size_t)tma_stages + 64;
             n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(p.U, (long long)g_num_sms)));
             static std::set<const void*> tma_configured;
@@ -552,7 +609,7 @@ Node contract_node(const RunCtx& c, int i) {
             }
         } else if (sf) {
             p.aBits = A.span_bits; p.bBits = B.span_bits;
-            n.func = sf;
+            n.func = sf; n.kname = "smem";
             n.smem = stage;
             n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(p.U, (long long)g_num_sms * 2)));
             static std::set<const void*> configured;
@@ -563,7 +620,7 @@ Node contract_node(const RunCtx& c, int i) {
         } else {
             // QXB_MINB=3 (experiment): the register allocation bounded for three resident CTAs per SM where it does not spill
             const int minb = [] { const char* e = getenv("QXB_MINB"); return e ? atoi(e) : 2; }();
-            n.func = contract_func(g->dtype, p.kc, p.ma, p.nb, p.kc == p.nK, minb);
+            n.func = contract_func(g->dtype, p.kc, p.ma, p.nb, p.kc == p.nK, minb); n.kname = "contract";
             n.grid = dim3((unsigned)std::max<long long>(1, std::min(blocks, cap)));
         }
     }
@@ -1048,7 +1105,7 @@ void launch_serial(qxb_graph* g, const std::vector<Node>& nodes) {
                 if (kv.second->key == n.variant) {
                     OpProfile& pr = n.op == kOpRowChunk ? kv.second->prof_rows : n.op == kOpRowBlock ? kv.second->prof_block_rows
                                                                                                      : kv.second->prof[n.op];
-                    pr.flops += n.flops; pr.bytes += n.bytes; pr.launches++;
+                    pr.flops += n.flops; pr.bytes += n.bytes; pr.launches++; pr.kernel = n.kname;
                 }
         }
     }
@@ -1603,9 +1660,9 @@ int qxb_profile_dump(qxb_graph* g, const char* path) {
                 const OpProfile& pr = v.prof[i];
                 if (pr.launches == 0) continue;
                 fprintf(f, "%s{\"name\":\"%s\",\"phase\":%d,\"nC\":%d,\"nK\":%d,\"batch_bits\":%d,\"m_bits\":%d,\"n_bits\":%d,"
-                           "\"launches\":%lld,\"flops\":%.6g,\"bytes\":%.6g,\"ms\":%.6g}",
+                           "\"kernel\":\"%s\",\"launches\":%lld,\"flops\":%.6g,\"bytes\":%.6g,\"ms\":%.6g}",
                         first ? "" : ",", op.name.c_str(), (int)op.phase, op.nC, op.nK, op.n_batch, op.n_m, op.n_n,
-                        pr.launches, pr.flops, pr.bytes, pr.ms);
+                        pr.kernel, pr.launches, pr.flops, pr.bytes, pr.ms);
                 first = false;
             }
             // the fused launches of a row-program variant: one pseudo-op per phase (the sums over the ops they cover)

@@ -52,6 +52,99 @@ int arena_alloc(std::vector<Interval>& live, int size, int until, int align = 1)
 
 }  // namespace
 
+// The descriptor of one contraction for the unit interpreter: register tile, K chunk, tables, thread-tile maps.
+// Tensor locations (oA / oB / oC, g*) are left to the caller.
+bool describe_row_op(const LOp& op, int dtype, const RowPlanOptions& o, RowOp& d, int& n_units, double& unit_cost,
+                     std::string& why) {
+    auto bad = [&](const std::string& w) { why = w; return false; };
+    memset(&d, 0, sizeof(d));
+    const int nC = op.nC, nK = op.nK;
+    if (nC > 16 || nK > 16) return bad("op too large for a row program");
+    std::vector<int> mapA(nC, -1), mapB(nC, -1);
+    for (auto& s : op.segA) for (int b = 0; b < s.len; ++b) mapA[s.src + b] = s.dst + b;
+    for (auto& s : op.segB) for (int b = 0; b < s.len; ++b) mapB[s.src + b] = s.dst + b;
+    std::vector<int> kposA(nK, -1), kposB(nK, -1);
+    for (auto& s : op.segKA) for (int b = 0; b < s.len; ++b) kposA[s.src + b] = s.dst + b;
+    for (auto& s : op.segKB) for (int b = 0; b < s.len; ++b) kposB[s.src + b] = s.dst + b;
+    for (int b = 0; b < nC; ++b) if (mapA[b] > 15 || mapB[b] > 15) return bad("operand wider than 2^16 elements");
+    for (int b = 0; b < nK; ++b) if (kposA[b] > 15 || kposB[b] > 15) return bad("operand wider than 2^16 elements");
+    // register tile: highest M-only / N-only bits, alternating sides, while >= 2^min_tt_bits thread-tiles remain
+    std::vector<int> mcand, ncand, mbits, nbits;
+    for (int b = nC - 1; b >= 0; --b) {
+        if (mapA[b] >= 0 && mapB[b] < 0) mcand.push_back(b);
+        else if (mapB[b] >= 0 && mapA[b] < 0) ncand.push_back(b);
+    }
+    while ((int)(mbits.size() + nbits.size()) < o.max_tile_bits && nC - (int)(mbits.size() + nbits.size()) - 1 >= o.min_tt_bits) {
+        const bool can_m = mbits.size() < 2 && mbits.size() < mcand.size();
+        const bool can_n = nbits.size() < 2 && nbits.size() < ncand.size();
+        if (!can_m && !can_n) break;
+        if (can_m && (!can_n || mbits.size() <= nbits.size())) mbits.push_back(mcand[mbits.size()]);
+        else nbits.push_back(ncand[nbits.size()]);
+    }
+    int ma = (int)mbits.size(), nb = (int)nbits.size();
+    int ntt = nC - ma - nb;
+    RowOpHot& h = d.hot;
+    if (ntt < 5) {                                       // fewer than 32 thread-tiles: lanes split K instead
+        mbits.clear(); nbits.clear(); ma = nb = 0; ntt = nC;
+    }
+    std::sort(mbits.begin(), mbits.end()); std::sort(nbits.begin(), nbits.end());
+    int kc = 0;
+    if (ntt >= 5) {
+        kc = std::min(nK, 2);
+        while (kc > 0 && tile_regs(dtype, ma, nb, kc) > std::min(100, o.tile_reg_budget)) --kc;
+        if (tile_regs(dtype, ma, nb, kc) > 100) return bad("no tile variant");
+        h.kind = (uint8_t)row_tile_kind(ma, nb, kc, 0);
+        h.ks = 0;
+        n_units = 1 << (ntt - 5);
+    } else {
+        h.kind = kRowKindKred;
+        h.ks = (uint8_t)std::min(5 - ntt, nK);
+        n_units = 1;
+    }
+    h.nK = (uint8_t)nK; h.kc = (uint8_t)kc; h.ma = (uint8_t)ma; h.nb = (uint8_t)nb; h.ntt = (uint8_t)ntt;
+    unit_cost = std::ldexp(1.0, ma + nb + nK - (int)h.ks) + 8.0;
+    std::vector<bool> is_tile(nC, false);
+    for (int b : mbits) is_tile[b] = true;
+    for (int b : nbits) is_tile[b] = true;
+    for (int jm = 0; jm < (1 << ma); ++jm) {
+        int a = 0, c = 0;
+        for (int t = 0; t < ma; ++t) if ((jm >> t) & 1) { a |= 1 << mapA[mbits[t]]; c |= 1 << mbits[t]; }
+        h.aT[jm] = (uint16_t)a;
+        for (int jn = 0; jn < (1 << nb); ++jn) {
+            int b = 0, c2 = c;
+            for (int t = 0; t < nb; ++t) if ((jn >> t) & 1) { b |= 1 << mapB[nbits[t]]; c2 |= 1 << nbits[t]; }
+            h.bT[jn] = (uint16_t)b;
+            h.cT[jm * (1 << nb) + jn] = (uint16_t)c2;
+        }
+    }
+    for (int k = 0; k < (1 << std::min(nK, 4)); ++k) {
+        int a = 0, b = 0;
+        for (int t = 0; t < std::min(nK, 4); ++t) if ((k >> t) & 1) {
+            if (kposA[t] >= 0) a |= 1 << kposA[t];
+            if (kposB[t] >= 0) b |= 1 << kposB[t];
+        }
+        h.ktA[k] = (uint16_t)a; h.ktB[k] = (uint16_t)b;
+    }
+    std::vector<std::pair<int, int>> ta, tb, tc, ka, kb;
+    int t = 0;
+    for (int b = 0; b < nC; ++b) {
+        if (is_tile[b]) continue;
+        tc.push_back({t, b});
+        if (mapA[b] >= 0) ta.push_back({t, mapA[b]});
+        if (mapB[b] >= 0) tb.push_back({t, mapB[b]});
+        ++t;
+    }
+    for (int b = 4; b < nK; ++b) {
+        if (kposA[b] >= 0) ka.push_back({b - 4, kposA[b]});
+        if (kposB[b] >= 0) kb.push_back({b - 4, kposB[b]});
+    }
+    const int nsA = merge_runs(ta, d.tA, kRowMaxSeg), nsB = merge_runs(tb, d.tB, kRowMaxSeg), nsC = merge_runs(tc, d.tC, kRowMaxSeg);
+    const int nkA = merge_runs(ka, d.kA, kRowMaxKSeg), nkB = merge_runs(kb, d.kB, kRowMaxKSeg);
+    if (nsA < 0 || nsB < 0 || nsC < 0 || nkA < 0 || nkB < 0) return bad("too many address segments");
+    d.nsA = (uint8_t)nsA; d.nsB = (uint8_t)nsB; d.nsC = (uint8_t)nsC; d.nkA = (uint8_t)nkA; d.nkB = (uint8_t)nkB;
+    return true;
+}
+
 RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const RowPlanOptions& o) {
     RowProgramHost rp;
     rp.phase = phase;
@@ -178,90 +271,8 @@ RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const
         RowOp& d = rp.ops[j];
         memset(&d, 0, sizeof(d));
         rp.lop[j] = sel[j]; rp.ref_a[j] = op.a; rp.ref_b[j] = op.b; rp.ref_c[j] = op.c;
-        const int nC = op.nC, nK = op.nK;
-        if (nC > 16 || nK > 16) return fail("op too large for a row program");
-        std::vector<int> mapA(nC, -1), mapB(nC, -1);
-        for (auto& s : op.segA) for (int b = 0; b < s.len; ++b) mapA[s.src + b] = s.dst + b;
-        for (auto& s : op.segB) for (int b = 0; b < s.len; ++b) mapB[s.src + b] = s.dst + b;
-        std::vector<int> kposA(nK, -1), kposB(nK, -1);
-        for (auto& s : op.segKA) for (int b = 0; b < s.len; ++b) kposA[s.src + b] = s.dst + b;
-        for (auto& s : op.segKB) for (int b = 0; b < s.len; ++b) kposB[s.src + b] = s.dst + b;
-        for (int b = 0; b < nC; ++b) if (mapA[b] > 15 || mapB[b] > 15) return fail("operand wider than 2^16 elements");
-        for (int b = 0; b < nK; ++b) if (kposA[b] > 15 || kposB[b] > 15) return fail("operand wider than 2^16 elements");
-        // register tile: highest M-only / N-only bits, alternating sides, while >= 2^min_tt_bits thread-tiles remain
-        std::vector<int> mcand, ncand, mbits, nbits;
-        for (int b = nC - 1; b >= 0; --b) {
-            if (mapA[b] >= 0 && mapB[b] < 0) mcand.push_back(b);
-            else if (mapB[b] >= 0 && mapA[b] < 0) ncand.push_back(b);
-        }
-        while ((int)(mbits.size() + nbits.size()) < o.max_tile_bits && nC - (int)(mbits.size() + nbits.size()) - 1 >= o.min_tt_bits) {
-            const bool can_m = mbits.size() < 2 && mbits.size() < mcand.size();
-            const bool can_n = nbits.size() < 2 && nbits.size() < ncand.size();
-            if (!can_m && !can_n) break;
-            if (can_m && (!can_n || mbits.size() <= nbits.size())) mbits.push_back(mcand[mbits.size()]);
-            else nbits.push_back(ncand[nbits.size()]);
-        }
-        int ma = (int)mbits.size(), nb = (int)nbits.size();
-        int ntt = nC - ma - nb;
+        if (!describe_row_op(op, dtype, o, d, n_units[j], unit_cost[j], rp.why)) { rp.ok = false; return rp; }
         RowOpHot& h = d.hot;
-        if (ntt < 5) {                                       // fewer than 32 thread-tiles: lanes split K instead
-            mbits.clear(); nbits.clear(); ma = nb = 0; ntt = nC;
-        }
-        std::sort(mbits.begin(), mbits.end()); std::sort(nbits.begin(), nbits.end());
-        int kc = 0;
-        if (ntt >= 5) {
-            kc = std::min(nK, 2);
-            while (kc > 0 && tile_regs(dtype, ma, nb, kc) > std::min(100, o.tile_reg_budget)) --kc;
-            if (tile_regs(dtype, ma, nb, kc) > 100) return fail("no tile variant");
-            h.kind = (uint8_t)row_tile_kind(ma, nb, kc, 0);
-            h.ks = 0;
-            n_units[j] = 1 << (ntt - 5);
-        } else {
-            h.kind = kRowKindKred;
-            h.ks = (uint8_t)std::min(5 - ntt, nK);
-            n_units[j] = 1;
-        }
-        h.nK = (uint8_t)nK; h.kc = (uint8_t)kc; h.ma = (uint8_t)ma; h.nb = (uint8_t)nb; h.ntt = (uint8_t)ntt;
-        unit_cost[j] = std::ldexp(1.0, ma + nb + nK - (int)h.ks) + 8.0;
-        std::vector<bool> is_tile(nC, false);
-        for (int b : mbits) is_tile[b] = true;
-        for (int b : nbits) is_tile[b] = true;
-        for (int jm = 0; jm < (1 << ma); ++jm) {
-            int a = 0, c = 0;
-            for (int t = 0; t < ma; ++t) if ((jm >> t) & 1) { a |= 1 << mapA[mbits[t]]; c |= 1 << mbits[t]; }
-            h.aT[jm] = (uint16_t)a;
-            for (int jn = 0; jn < (1 << nb); ++jn) {
-                int b = 0, c2 = c;
-                for (int t = 0; t < nb; ++t) if ((jn >> t) & 1) { b |= 1 << mapB[nbits[t]]; c2 |= 1 << nbits[t]; }
-                h.bT[jn] = (uint16_t)b;
-                h.cT[jm * (1 << nb) + jn] = (uint16_t)c2;
-            }
-        }
-        for (int k = 0; k < (1 << std::min(nK, 4)); ++k) {
-            int a = 0, b = 0;
-            for (int t = 0; t < std::min(nK, 4); ++t) if ((k >> t) & 1) {
-                if (kposA[t] >= 0) a |= 1 << kposA[t];
-                if (kposB[t] >= 0) b |= 1 << kposB[t];
-            }
-            h.ktA[k] = (uint16_t)a; h.ktB[k] = (uint16_t)b;
-        }
-        std::vector<std::pair<int, int>> ta, tb, tc, ka, kb;
-        int t = 0;
-        for (int b = 0; b < nC; ++b) {
-            if (is_tile[b]) continue;
-            tc.push_back({t, b});
-            if (mapA[b] >= 0) ta.push_back({t, mapA[b]});
-            if (mapB[b] >= 0) tb.push_back({t, mapB[b]});
-            ++t;
-        }
-        for (int b = 4; b < nK; ++b) {
-            if (kposA[b] >= 0) ka.push_back({b - 4, kposA[b]});
-            if (kposB[b] >= 0) kb.push_back({b - 4, kposB[b]});
-        }
-        const int nsA = merge_runs(ta, d.tA, kRowMaxSeg), nsB = merge_runs(tb, d.tB, kRowMaxSeg), nsC = merge_runs(tc, d.tC, kRowMaxSeg);
-        const int nkA = merge_runs(ka, d.kA, kRowMaxKSeg), nkB = merge_runs(kb, d.kB, kRowMaxKSeg);
-        if (nsA < 0 || nsB < 0 || nsC < 0 || nkA < 0 || nkB < 0) return fail("too many address segments");
-        d.nsA = (uint8_t)nsA; d.nsB = (uint8_t)nsB; d.nsC = (uint8_t)nsC; d.nkA = (uint8_t)nkA; d.nkB = (uint8_t)nkB;
         // where the tensors live
         auto place = [&](int tensor, int& off, char& in_arena) {
             auto it = arena_off.find(tensor);
@@ -362,6 +373,23 @@ RowDeviceTables build_row_tables(const RowProgramHost& rp, const std::vector<Row
         t.level_start[lv + 1] = (int)t.slots.size();
     }
     return t;
+}
+
+
+std::vector<RowUnitDesc> build_ring_descs(const LOp& op, int dtype, const RowPlanOptions& o, std::string& why) {
+    std::vector<RowUnitDesc> out;
+    RowOp d;
+    int n_units = 0;
+    double cost = 0;
+    if (!describe_row_op(op, dtype, o, d, n_units, cost, why)) return out;
+    if (d.hot.kind == kRowKindKred) { why = "fewer than 32 thread-tiles"; return out; }
+    RowProgramHost rp;
+    rp.n_levels = 1;
+    rp.level_start = {0, n_units};
+    for (int c = 0; c < n_units; ++c) rp.units.push_back(RowUnit{0, (uint16_t)c});
+    rp.elem_bytes = dtype == QXB_C32 ? 8 : 16;
+    RowDeviceTables t = build_row_tables(rp, std::vector<RowOp>{d});
+    return t.descs;
 }
 
 }  // namespace qxb

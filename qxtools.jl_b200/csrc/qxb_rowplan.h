@@ -51,4 +51,8 @@ struct RowDeviceTables {
 };
 RowDeviceTables build_row_tables(const RowProgramHost& rp, const std::vector<RowOp>& ops);
 
+// Unit descriptors of ONE contraction for the ring kernel (lane bases relative to each operand's own region);
+// empty when the op has no tile variant / fewer than 32 thread-tiles.
+std::vector<RowUnitDesc> build_ring_descs(const LOp& op, int dtype, const RowPlanOptions& o, std::string& why);
+
 }  // namespace qxb

@@ -280,6 +280,131 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowprog_kernel(const __grid_co
     cp_async_wait_all();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Ring kernel (see RingLaunch in qxb_rowprog.h).
+namespace {
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a copy that never completes must fail the launch, not hang the GPU
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    for (unsigned spin = 0; spin < (1u << 28); ++spin) {
+        unsigned done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+}  // namespace
+
+template <typename R2>
+__global__ void __launch_bounds__(kRowThreads, 1) ring_kernel(const __grid_constant__ RingLaunch P) {
+    extern __shared__ __align__(128) unsigned char ring_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool sharedA = P.sUA == 0, sharedB = P.sUB == 0;
+    const int S = P.stages;
+    RowUnitDesc* descs = reinterpret_cast<RowUnitDesc*>(ring_smem);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring_smem + (size_t)P.n_units * sizeof(RowUnitDesc));
+    const size_t head = ((size_t)P.n_units * sizeof(RowUnitDesc) + 8 * kRingMaxStages + 127) / 128 * 128;
+    R2* data = reinterpret_cast<R2*>(ring_smem + head);
+    // element offsets inside `data`: [A if shared][B if shared][stage 0: A? B? C][stage 1] ...
+    const int shA = 0, shB = sharedA ? P.nA : 0;
+    const int ring0 = (sharedA ? P.nA : 0) + (sharedB ? P.nB : 0);
+    const int stA = 0, stB = sharedA ? 0 : P.nA, stC = stB + (sharedB ? 0 : P.nB);
+    const int stage_elems = stC + P.nC;
+    const R2* __restrict__ A = reinterpret_cast<const R2*>(P.A);
+    const R2* __restrict__ B = reinterpret_cast<const R2*>(P.B);
+    R2* __restrict__ C = reinterpret_cast<R2*>(P.C);
+
+    // descriptors (once per CTA) and operands shared by every row
+    for (int i = tid; i < P.n_units * (int)(sizeof(RowUnitDesc) / 16); i += kRowThreads)
+        reinterpret_cast<uint4*>(descs)[i] = reinterpret_cast<const uint4*>(P.descs)[i];
+    if (sharedA) for (int i = tid; i < P.nA; i += kRowThreads) data[shA + i] = A[i];
+    if (sharedB) for (int i = tid; i < P.nB; i += kRowThreads) data[shB + i] = B[i];
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(smem_u32(bars + s), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long n_rows = P.U > (long long)blockIdx.x ? (P.U - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const unsigned row_bytes = (unsigned)(((sharedA ? 0 : P.nA) + (sharedB ? 0 : P.nB)) * (int)sizeof(R2));
+    auto issue = [&](long long j) {       // thread 0: operand rows of this CTA's j-th row -> stage j % S
+        const int s = (int)(j % S);
+        const long long u = blockIdx.x + j * (long long)gridDim.x;
+        const unsigned bar = smem_u32(bars + s);
+        R2* st = data + ring0 + (long long)s * stage_elems;
+        mbar_expect_tx(bar, row_bytes);
+        if (!sharedA) bulk_g2s(smem_u32(st + stA), A + u * P.sUA, (unsigned)(P.nA * sizeof(R2)), bar);
+        if (!sharedB) bulk_g2s(smem_u32(st + stB), B + u * P.sUB, (unsigned)(P.nB * sizeof(R2)), bar);
+    };
+    if (tid == 0) for (long long j = 0; j < n_rows && j < S - 1; ++j) issue(j);
+
+    for (long long j = 0; j < n_rows; ++j) {
+        const int s = (int)(j % S);
+        if (tid == 0 && j + S - 1 < n_rows) {
+            // stage (j + S - 1) % S was read by the compute of row j - 1 (all threads passed the barrier that ended it)
+            fence_async_smem();
+            issue(j + S - 1);
+        }
+        mbar_wait(smem_u32(bars + s), (unsigned)((j / S) & 1));
+        const int base = ring0 + s * stage_elems;
+        const int offA = sharedA ? shA : base + stA, offB = sharedB ? shB : base + stB, offC = base + stC;
+        for (int u = warp; u < P.n_units; u += kRowWarps) {
+            const RowUnitDesc* __restrict__ op = descs + u;
+            const RowOpHot* __restrict__ h = &op->hot;
+            const int lc = op->lC[lane];
+            if (lc == kRowNull) continue;
+            const int bA = op->lA[lane] + offA, bB = op->lB[lane] + offB, bC = lc + offC;
+            switch (h->ma * 3 + h->nb) {
+            case 0: row_tile_kc<R2, 0, 0>(h, op, data, data, data, data, bA, bB, bC); break;
+            case 1: row_tile_kc<R2, 0, 1>(h, op, data, data, data, data, bA, bB, bC); break;
+            case 2: row_tile_kc<R2, 0, 2>(h, op, data, data, data, data, bA, bB, bC); break;
+            case 3: row_tile_kc<R2, 1, 0>(h, op, data, data, data, data, bA, bB, bC); break;
+            case 4: row_tile_kc<R2, 1, 1>(h, op, data, data, data, data, bA, bB, bC); break;
+            case 5: row_tile_kc<R2, 1, 2>(h, op, data, data, data, data, bA, bB, bC); break;
+            case 6: row_tile_kc<R2, 2, 0>(h, op, data, data, data, data, bA, bB, bC); break;
+            case 7: row_tile_kc<R2, 2, 1>(h, op, data, data, data, data, bA, bB, bC); break;
+            default: row_tile_kc<R2, 2, 2>(h, op, data, data, data, data, bA, bB, bC); break;
+            }
+        }
+        fence_async_smem();                    // this thread's writes to the C stage -> visible to the bulk store
+        if (tid == 0) {
+            // the C region of the NEXT row's stage was last read by the bulk store of row j + 1 - S: it must be done
+            // before anyone passes the barrier below and starts writing that region
+            if (S == 2) bulk_wait_read<0>(); else if (S == 3) bulk_wait_read<1>(); else bulk_wait_read<2>();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const long long u = blockIdx.x + j * (long long)gridDim.x;
+            bulk_s2g(C + u * P.sUC, smem_u32(data + offC), (unsigned)(P.nC * sizeof(R2)));
+            bulk_commit();
+        }
+    }
+    if (tid == 0) bulk_wait_all();             // shared memory must outlive the last stores
+}
+
+const void* ring_func(int dtype) {
+    return dtype == 0 ? (const void*)&ring_kernel<float2> : (const void*)&ring_kernel<double2>;
+}
+
 const void* rowprog_func(int dtype) {
     return dtype == 0 ? (const void*)&rowprog_kernel<float2> : (const void*)&rowprog_kernel<double2>;
 }

@@ -92,6 +92,34 @@ struct RowLaunch {
     int level_start[kRowMaxLevels + 1];     // in slots
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Ring kernel: ONE contraction whose operand rows A[u], B[u] and result row C[u] are small dense per-bitstring rows
+// (the dominant nodes of the batched RQC plans: 32 KB + 8 KB -> 32 KB per row, K = 8).  Persistent CTA per SM;
+// the rows travel by 1-D TMA bulk copies: cp.async.bulk global -> shared into a ring of stages (mbarrier
+// complete_tx), the same unit interpreter computes the row from shared memory INTO shared memory, and the result
+// row leaves by cp.async.bulk shared -> global (bulk_group).  No thread ever touches global memory, so the
+// thread <-> element mapping is free (2 x 2-bit register tiles on any M / N bits) and the bytes in flight cost no
+// registers -- what limited contract_kernel to 55-63 % of the HBM peak on these nodes (profiles/r1p_summary.md).
+struct RingLaunch {
+    const RowUnitDesc* descs;       // n_units descriptors; lane bases relative to the operand's own region
+    const void* A;
+    const void* B;
+    void* C;
+    long long sUA, sUB, sUC;        // elements between consecutive rows (0 = operand shared by all rows)
+    long long U;                    // rows
+    int n_units;
+    int nA, nB, nC;                 // elements per row
+    int stages;                     // 2..4
+};
+const void* ring_func(int dtype);
+constexpr int kRingMaxStages = 4;
+// dynamic shared memory of the ring kernel
+inline size_t ring_smem_bytes(int n_units, int nA, int nB, int nC, bool sharedA, bool sharedB, int stages, size_t es) {
+    const size_t head = ((size_t)n_units * sizeof(RowUnitDesc) + 8 * kRingMaxStages + 127) / 128 * 128;
+    const size_t stage = ((sharedA ? 0 : (size_t)nA) + (sharedB ? 0 : (size_t)nB) + (size_t)nC) * es;
+    return head + ((sharedA ? (size_t)nA : 0) + (sharedB ? (size_t)nB : 0)) * es + (size_t)stages * stage;
+}
+
 // entry point: (RowLaunch by value); dynamic shared memory = row_smem_bytes(...)
 const void* rowprog_func(int dtype);
 inline size_t row_slots_bytes(size_t n_slots) { return (n_slots * sizeof(uint16_t) + 127) / 128 * 128; }

@@ -143,3 +143,32 @@ def test_ghz_qft_rows(gpu):
         ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
         g = Graph.from_dsl(txt, data, "c64").compile()
         assert rel_err(g.amplitudes(bs), ref, circ.num_qubits) < 1e-10
+
+
+@pytest.mark.parametrize("workload,dtype,tol", [("rqc_7x7_d20_c64_s4096", "c64", 1e-12), ("rqc_7x7_d20_c64_s4096", "c32", 1e-5),
+                                                ("rqc_6x6_d16_c32_s64", "c64", 1e-12)])
+def test_ring_kernel_equals_streaming_kernels(gpu, workload, dtype, tol):
+    """The TMA ring kernel (bulk copies in, bulk store out) on the dominant nodes of the bench plans against the
+    streaming kernels (ring=False) on the same plan, enough bitstrings that every CTA walks several rows; a short
+    slice range against the oracle."""
+    import bench
+    txt, data, w = bench.build_workload(workload)
+    nq = w["rows"] * w["cols"]
+    n = 148 * 5 + 3
+    bits = bench.synth_bits(n, nq)
+    g = Graph.from_dsl(txt, data, dtype, replan=32, replan_n_amp=131072)
+    plan = g.text
+    g.compile(row_programs="block")
+    got = g.amplitudes(bits)
+    ref = Graph.from_dsl(plan, data, "c64").compile(row_programs=False, ring=False).amplitudes(bits)
+    assert np.max(np.abs(got - ref)) < tol * max(np.max(np.abs(ref)), 2.0 ** (-nq / 2))
+    prof = Graph.from_dsl(plan, data, dtype).compile(row_programs="block", profile=True)
+    prof.amplitudes(bits)
+    import json, tempfile, os
+    path = os.path.join(tempfile.mkdtemp(), "p.json")
+    ops = [o for v in prof.profile_dump(path)["variants"] for o in v["ops"]]
+    assert any(o.get("kernel") == "ring" for o in ops), "no node ran on the ring kernel"
+    bs = ["".join("01"[b] for b in row) for row in bits[:2]]
+    o = orc.amplitudes(orc.parse_dsl(plan), data, bs, slice_begin=5, slice_end=8)
+    big = np.tile(bits[:2], (148, 1))                    # >= 148 rows so that the ring kernel is eligible
+    assert rel_err(g.amplitudes(big, 5, 8)[:2], o, nq) < max(tol, 1e-10)
