@@ -63,7 +63,7 @@ typedef struct qxb_options {
     int32_t min_lob;           /* 5..8: thread bits contract_kernel keeps (register tiles for small nodes); 0 = 6  */
     int32_t kc_regs_multi;     /* register budget of the K chunk, multi-chunk nodes; 0 = 160                      */
     int32_t kc_regs_one;       /* register budget of the K chunk, single-chunk nodes; 0 = 128                     */
-    int32_t smem_tma;          /* 1 = TMA-staged contract_tma_kernel for broadcast-type nodes; 0 = off            */
+    int32_t smem_tma;          /* TMA-staged contract_tma_kernel for broadcast-type nodes: 0 = auto (on), 1 = on, 2 = off */
     int32_t row_min_tt_bits;   /* row programs: keep >= 2^n thread-tiles per node when choosing the register tile; 0 = 6 */
     int32_t row_tile_regs;     /* row programs: registers for staged operands + accumulators; 0 = 100            */
     int32_t row_ctas_per_sm;   /* row programs: resident CTAs per SM; 0 = as many as the arena allows, at most 2  */

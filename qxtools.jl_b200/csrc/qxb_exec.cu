@@ -531,7 +531,7 @@ Node contract_node(const RunCtx& c, int i) {
             sf = contract_smem_func(g->dtype, p.kc, p.ma, p.nb, p.kc == p.nK);
         // EXPERIMENT QXB_SMEM_TMA=1 (never run on hardware yet, see contract_tma_kernel): operand rows through 1-D TMA
         // bulk copies into a ring of stages; QXB_SMEM_TMA_RATIO = minimum |C| / (|A| + |B|)
-        const int smem_tma = knob(g->opts.smem_tma, "QXB_SMEM_TMA", 0);
+        const int smem_tma = g->opts.smem_tma == 2 ? 0 : knob(g->opts.smem_tma, "QXB_SMEM_TMA", 1);   // default on since r2 (measured 13.1 vs 14.2 ms)
         const void* tf = nullptr;
         if (smem_tma && !g->opts.no_smem_stage && p.lob == 8 && p.ma + p.nb >= 1 && A.lay.size() && B.lay.size() &&
             (A.amp || B.amp) && p.U >= g_num_sms &&
@@ -548,7 +548,12 @@ Node contract_node(const RunCtx& c, int i) {
         // from shared memory into shared memory with a free thread <-> element mapping
         if (knob(0, "QXB_RING", 1) != 0 && g->opts.ring != 1 && C.amp && (A.amp || B.amp) && p.U >= g_num_sms && p.nC >= 8 &&
             A.lay.size() && B.lay.size() && op.elems_a == std::ldexp(1.0, A.span_bits) && op.elems_b == std::ldexp(1.0, B.span_bits) &&
-            A.span_bits <= 15 && B.span_bits <= 15 && p.nC <= 15) {
+            A.span_bits <= 15 && B.span_bits <= 15 && p.nC <= 15 &&
+            // measured (scripts/probe_ring.py, profiles/r2_summary.md): the ring wins on the big rows (68-72 KB per row:
+            // 80-84 % of the HBM peak against 51-62 % for contract_kernel) and loses below ~48 KB per row, where its
+            // per-row hand-shake (~3000 cycles with one CTA per SM) is longer than the row's HBM time
+            ((double)(1ll << A.span_bits) + (double)(1ll << B.span_bits) + std::ldexp(1.0, p.nC)) * (double)g->es() >=
+                (double)knob(0, "QXB_RING_MIN_ROW_BYTES", 48 * 1024)) {
             const size_t es = g->es();
             const int nA = 1 << A.span_bits, nB = 1 << B.span_bits, nCe = 1 << p.nC;
             const bool shA = !A.amp, shB = !B.amp;
@@ -558,7 +563,7 @@ Node contract_node(const RunCtx& c, int i) {
             if (aligned && !rd.tried) {
                 rd.tried = true;
                 RowPlanOptions ro;
-                ro.min_tt_bits = knob(0, "QXB_RING_MIN_TT", 7);
+                ro.min_tt_bits = knob(0, "QXB_RING_MIN_TT", 8);
                 ro.tile_reg_budget = knob(0, "QXB_RING_TILE_REGS", 100);
                 std::string why;
                 std::vector<RowUnitDesc> descs = build_ring_descs(op, g->dtype, ro, why);

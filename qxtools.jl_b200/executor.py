@@ -239,7 +239,7 @@ class Graph:
     def _options(hbm_budget_bytes: int = 0, amp_batch: int = 0, profile: bool = False,
                  cuda_graph: bool = True, sum_at_root: bool = False, smem_stage: bool = True,
                  gemm: bool = True, gemm_mode: int = 0, row_programs=True, min_lob: int = 0,
-                 kc_regs_multi: int = 0, kc_regs_one: int = 0, smem_tma: bool = False, row_min_tt_bits: int = 0,
+                 kc_regs_multi: int = 0, kc_regs_one: int = 0, smem_tma: bool = True, row_min_tt_bits: int = 0,
                  row_tile_regs: int = 0, row_ctas_per_sm: int = 0, row_chunk_max_amps: int = 0, ring: bool = True) -> Options:
         """``qxb_options`` (include/qxb200.h); 0 / default = the library's own choice.
         ``row_programs``: True = auto (block phase always, chunk phase for small calls), False = never,
@@ -247,7 +247,7 @@ class Graph:
         rp = {True: 0, False: 1, "auto": 0, "never": 1, "all": 2, "block": 3}[row_programs]
         return Options(hbm_budget_bytes, amp_batch, 1 if profile else 0, 0 if cuda_graph else 1,
                        1 if sum_at_root else 0, 0 if smem_stage else 1, 0 if gemm else 1, gemm_mode,
-                       rp, min_lob, kc_regs_multi, kc_regs_one, 1 if smem_tma else 0,
+                       rp, min_lob, kc_regs_multi, kc_regs_one, 0 if smem_tma else 2,
                        row_min_tt_bits, row_tile_regs, row_ctas_per_sm, 0 if ring else 1, row_chunk_max_amps)
 
     def configure(self, **kw) -> "Graph":

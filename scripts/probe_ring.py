@@ -16,14 +16,14 @@ bits = torch.from_numpy(bench.synth_bits(n_amp, nq)).cuda()
 cdt = torch.complex64 if w["dtype"] == "c32" else torch.complex128
 out = torch.zeros(n_amp, dtype=cdt, device="cuda")
 plan_txt = Graph.from_dsl(txt, data, w["dtype"], replan=128, replan_n_amp=n_amp).text
-CONFIGS = [("noring", dict(ring=False), {}), ("ring_tt7", {}, {}), ("ring_tt8", {}, {"QXB_RING_MIN_TT": "8"}), ("ring_tt6", {}, {"QXB_RING_MIN_TT": "6"}),
-           ("noring_tma", dict(ring=False, smem_tma=True), {})]
+CONFIGS = [("noring_notma", dict(ring=False, smem_tma=False), {}), ("noring_tma", dict(ring=False), {}), ("default", {}, {}),
+           ("ring_tt7", {}, {"QXB_RING_MIN_TT": "7"}), ("ring_all_rows", {}, {"QXB_RING_MIN_ROW_BYTES": "16384"})]
 only = os.environ.get("PROBE_ONLY")
 if only:
     CONFIGS = [c for c in CONFIGS if c[0] in only.split(",")]
 ref, results = None, {}
 for tag, kw, env in CONFIGS:
-    for k in ("QXB_RING_MIN_TT",):
+    for k in ("QXB_RING_MIN_TT", "QXB_RING_MIN_ROW_BYTES"):
         os.environ.pop(k, None)
     os.environ.update(env)
     g = Graph.from_dsl(plan_txt, data, w["dtype"]).compile(**kw)
@@ -57,8 +57,8 @@ for tag, kw, env in CONFIGS:
     dby, dms = sum(o["bytes"] for o in dom), sum(o["ms"] for o in dom)
     print(f"[{tag}] {ms:.3f} ms per {n_amp} -> {n_amp / ms * 1e3:.3e} amp/s, {st['bytes'] / ms / 1e6:.0f} GB/s alg; dominant {dby / dms / 1e6:.0f} GB/s "
           f"({dby / dms / 1e6 / 6451.5:.3f} of HBM peak); diff vs first {err:.1e}", flush=True)
-    print("    " + "  ".join(f"{o['name']}[{o['nC']},{o['nK']}]{o['kernel']} {o['ms']:.2f}ms {o['bytes'] / o['ms'] / 1e6:.0f}" for o in dom), flush=True)
-    nring = sum(1 for o in ops if o["kernel"] == "ring")
+    print("    " + "  ".join(f"{o['name']}[{o['nC']},{o['nK']}]{o.get('kernel', '')} {o['ms']:.2f}ms {o['bytes'] / o['ms'] / 1e6:.0f}" for o in dom), flush=True)
+    nring = sum(1 for o in ops if o.get("kernel") == "ring")
     print(f"    ring nodes: {nring} of {len(ops)}; sum of op ms {sum(o['ms'] for o in ops):.2f}", flush=True)
     results[tag] = {"ms": ms, "dominant_gbs": dby / dms / 1e6, "rel_diff": err, "ring_nodes": nring}
 json.dump(results, open(os.path.join(ROOT, "gpurun_out", f"probe_ring_{wl}.json"), "w"), indent=1)
