@@ -52,8 +52,10 @@ typedef struct qxb_options {
                                   0 (default) = sum each one at the lowest node covering all its leaves   */
     int32_t no_smem_stage;     /* 1 = never use the shared-memory-staged kernel for broadcast-type nodes */
     int32_t no_gemm;           /* 1 = never use the tiled GEMM kernel for GEMM-shaped nodes               */
-    int32_t gemm_mode;         /* GEMM-shaped nodes: 0 = auto, 1 = SIMT FMA kernel only, 2 = tensor-core kernel
-                                  (DMMA for ComplexF64, 3xTF32 for ComplexF32) wherever the tile shape allows */
+    int32_t gemm_mode;         /* GEMM-shaped nodes: 0 = auto (= 2), 1 = SIMT FMA kernel only, 2 = tensor cores wherever the
+                                  tile shape allows: ComplexF32 -> tcgen05 / TMEM 3xTF32 kernel (2^7 x 2^6 x 2^4 tiles),
+                                  else the mma.sync 3xTF32 kernel; ComplexF64 -> DMMA (tcgen05 has no FP64 kind);
+                                  4 = mma.sync kernels only (no tcgen05) */
     /* ---- round 2: every kernel-selection knob is an option (0 = the library's default; the QXB_* environment
      *      variables of round 1 are still read, as overrides for experiments, only where the option is 0) ---- */
     int32_t row_programs;      /* row programs (csrc/qxb_rowprog.h: a whole phase of the tree as ONE persistent kernel).
@@ -252,6 +254,9 @@ int  qxb_execute_files(const char* dsl_file, const char* input_file, const char*
 /* test hook (not part of the drop-in surface): shared-memory offset contributed by tile-index bit `bit` in the
  * tensor-core GEMM kernels' staging layouts; tests/test_mma_layout.py replays the kernels' index arithmetic on the CPU */
 int  qxb_debug_mma_smem_bit(int dtype, int is_b, int tile_bits, int bit);
+/* test hook: the same for the tcgen05 / TMEM kernel (csrc/qxb_gemm_tc5.cu): BYTE offset in the canonical K-major
+ * no-swizzle core-matrix layout (8 rows x 16 bytes contiguous, 128 B between 16-byte K chunks, 1024 B between 8-row groups) */
+int  qxb_debug_tc5_smem_bit(int tile_bits, int bit);
 /* test hook: raw array of the per-contraction launch templates (struct OpParams of csrc/qxb_kernels.cuh, one per
  * lowered op, pointers unset) for n_free batched variables; returns the bytes needed.  Host logic only. */
 int64_t qxb_debug_templates(qxb_graph* g, int n_free, void* buf, int64_t buflen);

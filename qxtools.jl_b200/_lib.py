@@ -25,7 +25,7 @@ SYMBOLS = [
     "qxb_last_stats", "qxb_profile_dump", "qxb_debug_mma_smem_bit",
     "qxb_jld2_open", "qxb_jld2_close", "qxb_jld2_count", "qxb_jld2_info", "qxb_jld2_read", "qxb_jld2_write",
     "qxb_graph_load_jld2", "qxb_params_read", "qxb_execute_files", "qxb_debug_lookup3", "qxb_debug_templates",
-    "qxb_debug_rowprog",
+    "qxb_debug_rowprog", "qxb_debug_tc5_smem_bit",
 ]
 
 
@@ -109,6 +109,7 @@ def load():
         "qxb_last_stats": (i32, [p, C.POINTER(Stats)]),
         "qxb_profile_dump": (i32, [p, cp]),
         "qxb_debug_mma_smem_bit": (i32, [i32, i32, i32, i32]),
+        "qxb_debug_tc5_smem_bit": (i32, [i32, i32]),
         "qxb_jld2_open": (i32, [cp, C.POINTER(p)]),
         "qxb_jld2_close": (None, [p]),
         "qxb_jld2_count": (i32, [p, C.POINTER(i32), C.POINTER(i32)]),

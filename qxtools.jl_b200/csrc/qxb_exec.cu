@@ -85,6 +85,8 @@ struct Variant {
     std::vector<OpParams> tmpl;          // per op, pointers unset
     std::vector<GemmParams> gtmpl;       // per op: tiled-GEMM parameters (valid when gemm_tmb > 0)
     std::vector<int> gemm_tmb, gemm_tnb;
+    std::vector<GemmParams> gtmpl5;      // per op: parameters of the tcgen05 kernel (valid when gemm5[i])
+    std::vector<char> gemm5;
     std::vector<OpProfile> prof;
     // row programs (qxb_rowprog.h): the chunk phase as one persistent kernel with the row's intermediates in shared
     // memory, the block phase as a single-CTA program; device copies of the descriptors per set of fixed values
@@ -241,6 +243,7 @@ void build_templates(Variant& v, int dtype, const qxb_options& opts) {
     v.tmpl.resize(v.L.ops.size());
     v.gtmpl.resize(v.L.ops.size());
     v.gemm_tmb.assign(v.L.ops.size(), 0); v.gemm_tnb.assign(v.L.ops.size(), 0);
+    v.gtmpl5.resize(v.L.ops.size()); v.gemm5.assign(v.L.ops.size(), 0);
     v.prof.assign(v.L.ops.size(), OpProfile{});
     for (size_t i = 0; i < v.L.ops.size(); ++i) {
         const LOp& op = v.L.ops[i];
@@ -353,31 +356,29 @@ void build_templates(Variant& v, int dtype, const qxb_options& opts) {
             else if (mapB[b] >= 0 && mapA[b] < 0) nall.push_back(b);
         }
         const LTensor &TA = v.L.tensors[op.a], &TB = v.L.tensors[op.b];
-        if (op.nK >= kcb && mall.size() >= 5 && nall.size() >= 5 && nC <= 31 && TA.span_bits <= 31 && TB.span_bits <= 31) {
-            GemmParams& q = v.gtmpl[i];
+        // tile bits: the M-only (N-only) bits that sit lowest in A (B): ascending operand addresses per load
+        std::sort(mall.begin(), mall.end(), [&](int x, int y) { return mapA[x] < mapA[y]; });
+        std::sort(nall.begin(), nall.end(), [&](int x, int y) { return mapB[x] < mapB[y]; });
+        // one GemmParams for a (tmb, tnb, kcb) block tile; smem_bit(is_b, bit) = layout of the kernel that will read it
+        auto make_gemm = [&](GemmParams& q, int tmb, int tnb, int kcb_, auto smem_bit) {
             memset(&q, 0, sizeof(q));
-            const int tmb = (int)std::min<size_t>(6, mall.size()), tnb = (int)std::min<size_t>(6, nall.size());
-            // tile bits: the M-only (N-only) bits that sit lowest in A (B): ascending operand addresses per load
-            std::sort(mall.begin(), mall.end(), [&](int x, int y) { return mapA[x] < mapA[y]; });
-            std::sort(nall.begin(), nall.end(), [&](int x, int y) { return mapB[x] < mapB[y]; });
             std::vector<int> mt(mall.begin(), mall.begin() + tmb), nt(nall.begin(), nall.begin() + tnb);
             std::vector<long long> kposA(op.nK, 0), kposB(op.nK, 0);
             for (auto& s : op.segKA) for (int b = 0; b < s.len; ++b) kposA[s.src + b] = 1ll << (s.dst + b);
             for (auto& s : op.segKB) for (int b = 0; b < s.len; ++b) kposB[s.src + b] = 1ll << (s.dst + b);
-            std::vector<std::pair<long long, int>> la, lb;        // (global offset, smem contribution)
-            for (int t = 0; t < tmb; ++t) la.push_back({1ll << mapA[mt[t]], 1 << t});
-            for (int c = 0; c < kcb; ++c) la.push_back({kposA[c], (1 << c) << tmb});
-            for (int t = 0; t < tnb; ++t) lb.push_back({1ll << mapB[nt[t]], 1 << t});
-            for (int c = 0; c < kcb; ++c) lb.push_back({kposB[c], (1 << c) << tnb});
+            std::vector<std::pair<long long, int>> la, lb;        // (global offset, tile-index bit)
+            for (int t = 0; t < tmb; ++t) la.push_back({1ll << mapA[mt[t]], t});
+            for (int c = 0; c < kcb_; ++c) la.push_back({kposA[c], tmb + c});
+            for (int t = 0; t < tnb; ++t) lb.push_back({1ll << mapB[nt[t]], t});
+            for (int c = 0; c < kcb_; ++c) lb.push_back({kposB[c], tnb + c});
             std::sort(la.begin(), la.end()); std::sort(lb.begin(), lb.end());
-            auto bitpos = [](int mask) { int b = 0; while ((1 << b) < mask) ++b; return b; };
             for (size_t j = 0; j < la.size(); ++j) {
-                q.aLoadOff[j] = la[j].first; q.aLoadSm[j] = la[j].second;
-                q.aLoadSmT[j] = gemm_mma_smem_bit(dtype, false, tmb, bitpos(la[j].second));
+                q.aLoadOff[j] = la[j].first; q.aLoadSm[j] = 1 << la[j].second;
+                q.aLoadSmT[j] = smem_bit(false, la[j].second);
             }
             for (size_t j = 0; j < lb.size(); ++j) {
-                q.bLoadOff[j] = lb[j].first; q.bLoadSm[j] = lb[j].second;
-                q.bLoadSmT[j] = gemm_mma_smem_bit(dtype, true, tnb, bitpos(lb[j].second));
+                q.bLoadOff[j] = lb[j].first; q.bLoadSm[j] = 1 << lb[j].second;
+                q.bLoadSmT[j] = smem_bit(true, lb[j].second);
             }
             for (int t = 0; t < tmb; ++t) q.cM[t] = 1ll << mt[t];
             for (int t = 0; t < tnb; ++t) q.cN[t] = 1ll << nt[t];
@@ -398,7 +399,16 @@ void build_templates(Variant& v, int dtype, const qxb_options& opts) {
             q.nsChi = merge(gch, q.sChi, kMaxSeg, op.name);
             q.nkA = p.nkA; q.nkB = p.nkB;
             memcpy(q.kA, p.kA, sizeof(q.kA)); memcpy(q.kB, p.kB, sizeof(q.kB));
+        };
+        if (op.nK >= kcb && mall.size() >= 5 && nall.size() >= 5 && nC <= 31 && TA.span_bits <= 31 && TB.span_bits <= 31) {
+            const int tmb = (int)std::min<size_t>(6, mall.size()), tnb = (int)std::min<size_t>(6, nall.size());
+            make_gemm(v.gtmpl[i], tmb, tnb, kcb, [&](bool is_b, int bit) { return gemm_mma_smem_bit(dtype, is_b, is_b ? tnb : tmb, bit); });
             if (gemm_func(dtype, tmb, tnb)) { v.gemm_tmb[i] = tmb; v.gemm_tnb[i] = tnb; }
+        }
+        // tcgen05 / TMEM kernel (ComplexF32): 2^7 x 2^6 x 2^4 block tile
+        if (dtype == QXB_C32 && op.nK >= 4 && mall.size() >= 7 && nall.size() >= 6 && nC <= 31 && TA.span_bits <= 31 && TB.span_bits <= 31) {
+            make_gemm(v.gtmpl5[i], 7, 6, 4, [&](bool is_b, int bit) { return gemm_tc5_smem_bit(is_b ? 6 : 7, bit); });
+            v.gemm5[i] = 1;
         }
     }
 }
@@ -457,13 +467,36 @@ Node contract_node(const RunCtx& c, int i) {
     Node n;
     int tma_stages = 0;                    // > 0: the node runs contract_tma_kernel (second kernel argument)
     const double outputs = (double)p.U * std::ldexp(1.0, p.nC);
+    // tcgen05 / TMEM 3xTF32 kernel (ComplexF32): auto prefers it wherever the shape has 2^7 M-only x 2^6 N-only bits
+    // (81 TFLOP/s complex-equivalent stand-alone against 49 for the mma.sync kernel); gemm_mode 1 / 2 keep the others
+    const int gm = gemm_mode(g);
+    if (!g->opts.no_gemm && g->dtype == QXB_C32 && c.v->gemm5[i] && outputs >= 65536.0 && gm == 2) {
+        GemmParams q = c.v->gtmpl5[i];
+        q.A = p.A; q.B = p.B; q.C = p.C; q.sUA = p.sUA; q.sUB = p.sUB; q.sUC = p.sUC; q.U = p.U;
+        q.tiles = (long long)p.U << q.hb;
+        n.func = gemm_tc5_func(); n.kname = "gemm_tc5";
+        n.block = dim3((unsigned)gemm_tc5_threads());
+        n.smem = gemm_tc5_smem_bytes();
+        static bool tc5_configured = false;
+        if (!tc5_configured) {
+            CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n.smem));
+            tc5_configured = true;
+        }
+        n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(q.tiles, (long long)g_num_sms)));
+        n.arg(q);
+        n.variant = c.variant_key; n.op = i;
+        const double u = (double)p.U;
+        n.flops = 8.0 * op.macs_per_amp * u;
+        n.bytes = (double)g->es() * (op.elems_a * (A.amp ? c.n : 1) + op.elems_b * (B.amp ? c.n : 1) + op.elems_c * u);
+        return n;
+    }
     if (!g->opts.no_gemm && c.v->gemm_tmb[i] > 0 && outputs >= 65536.0) {
         // GEMM-shaped node: shared-memory-tiled FMA GEMM
         GemmParams q = c.v->gtmpl[i];
         q.A = p.A; q.B = p.B; q.C = p.C; q.sUA = p.sUA; q.sUB = p.sUB; q.sUC = p.sUC; q.U = p.U;
         q.tiles = (long long)p.U << q.hb;
         const int tmb = c.v->gemm_tmb[i], tnb = c.v->gemm_tnb[i];
-        const void* tc = gemm_mode(g) == 2 ? gemm_mma_func(g->dtype, tmb, tnb) : nullptr;
+        const void* tc = gm >= 2 ? gemm_mma_func(g->dtype, tmb, tnb) : nullptr;
         if (tc) {
             // tensor-core variant (DMMA / 3xTF32 mma.sync); persistent grid = SMs x resident CTAs
             n.func = tc; n.kname = "gemm_tc";
@@ -1760,6 +1793,9 @@ int64_t qxb_debug_rowprog(qxb_graph* g, uint64_t free_mask, int phase, void* buf
     });
     return rc == QXB_OK ? need : rc;
 }
+
+// test hook: byte offset a tile-index bit contributes in the tcgen05 kernel's canonical K-major staging layout
+int qxb_debug_tc5_smem_bit(int tile_bits, int bit) { return qxb::gemm_tc5_smem_bit(tile_bits, bit); }
 
 // test hook: shared-memory layout table of the tensor-core GEMM kernels (tests/test_mma_layout.py)
 int qxb_debug_mma_smem_bit(int dtype, int is_b, int tile_bits, int bit) {

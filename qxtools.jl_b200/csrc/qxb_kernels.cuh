@@ -58,10 +58,10 @@ struct GemmParams {
     int nsAhi, nsBhi, nsChi, nkA, nkB;
     // operand tile loads: load-index bit j -> global offset / shared-memory index contribution
     // (bits sorted by ascending global offset so consecutive threads read ascending addresses)
-    long long aLoadOff[10], bLoadOff[10];
-    int aLoadSm[10], bLoadSm[10];
-    int aLoadSmT[10], bLoadSmT[10];  // same for the tensor-core kernels' shared-memory layouts (gemm_mma_smem_bit)
-    long long cM[6], cN[6];          // C offset of each M-tile / N-tile bit
+    long long aLoadOff[12], bLoadOff[12];
+    int aLoadSm[12], bLoadSm[12];
+    int aLoadSmT[12], bLoadSmT[12];  // same for the tensor-core kernels' shared-memory layouts (gemm_mma_smem_bit / gemm_tc5_smem_bit)
+    long long cM[8], cN[8];          // C offset of each M-tile / N-tile bit
     DSeg sAhi[kMaxSeg], sBhi[kMaxSeg], sChi[kMaxSeg];
     DSeg kA[kMaxKSeg], kB[kMaxKSeg]; // k index (all nK bits) -> offsets; chunk c covers k = c << kcb ...
 };
@@ -75,6 +75,13 @@ const void* gemm_mma_func(int dtype, int tmb, int tnb);
 int gemm_mma_threads(int dtype);
 size_t gemm_mma_smem_bytes(int dtype);
 int gemm_mma_smem_bit(int dtype, bool is_b, int tb, int bit);
+// tcgen05 / TMEM ComplexF32 GEMM (qxb_gemm_tc5.cu): block tile 2^7 M-only bits x 2^6 N-only bits x 2^4 K bits,
+// 3xTF32 through kind::tf32 UMMAs with TMEM accumulators; same GemmParams, aLoadSmT / bLoadSmT = BYTE offsets of the
+// canonical K-major core-matrix layout (gemm_tc5_smem_bit)
+const void* gemm_tc5_func();
+size_t gemm_tc5_smem_bytes();
+int gemm_tc5_threads();
+int gemm_tc5_smem_bit(int tile_bits, int bit);
 
 struct OutLeafDesc { long long offset_per_amp; int span_bits; int out_idx; };
 

@@ -135,8 +135,10 @@ def test_tensor_core_gemm_on_sycamore_like(gpu):
     ref = Graph.from_dsl(txt, data, "c64", replan=32, replan_n_amp=64).compile(gemm_mode=1).amplitudes(bits)
     t64 = Graph.from_dsl(txt, data, "c64", replan=32, replan_n_amp=64).compile(gemm_mode=2)
     assert rel_err(t64.amplitudes(bits), ref, 53) < 1e-12
-    t32 = Graph.from_dsl(txt, data, "c32", replan=32, replan_n_amp=64).compile(gemm_mode=2)
+    t32 = Graph.from_dsl(txt, data, "c32", replan=32, replan_n_amp=64).compile(gemm_mode=2)      # tcgen05 where 2^7 x 2^6 tiles fit
     assert rel_err(t32.amplitudes(bits), ref, 53) < 1e-5
+    m32 = Graph.from_dsl(txt, data, "c32", replan=32, replan_n_amp=64).compile(gemm_mode=4)      # mma.sync 3xTF32 only
+    assert rel_err(m32.amplitudes(bits), ref, 53) < 1e-5
     cmds = orc.parse_dsl(txt)
     bss = ["".join("01"[x] for x in row) for row in bits[:1]]
     refs = orc.amplitudes(cmds, data, bss, slice_begin=17, slice_end=18)

@@ -185,6 +185,14 @@ def test_reduction_shaped_nodes(gpu, dtype):
     g = Graph.from_dsl(txt, data, dtype).compile()
     got = g.amplitudes(bs)
     assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 2e-5)
+    # which kernel ran the node
+    import os, tempfile
+    gp = Graph.from_dsl(txt, data, dtype).compile(gemm_mode=gemm_mode, profile=True)
+    gp.amplitudes(bs)
+    prof = gp.profile_dump(os.path.join(tempfile.mkdtemp(), "p.json"))
+    kern = [o["kernel"] for v in prof["variants"] for o in v["ops"] if o["name"] == "c"][0]
+    want = {1: "gemm_simt", 2: "gemm_tc5" if dtype == "c32" else "gemm_tc", 4: "gemm_tc"}[gemm_mode]
+    assert kern == want, (kern, want)
 
 
 @pytest.mark.parametrize("dtype", ["c64", "c32"])
@@ -330,12 +338,12 @@ def test_long_k_block_reduction(gpu, dtype):
 
 
 @pytest.mark.parametrize("dtype", ["c64", "c32"])
-@pytest.mark.parametrize("gemm_mode", [1, 2])
+@pytest.mark.parametrize("gemm_mode", [1, 2, 4])
 @pytest.mark.parametrize("seed", [0, 1])
 def test_gemm_shaped_node_random(gpu, dtype, gemm_mode, seed):
     """One GEMM-shaped node on random data with shuffled mode orders: M = 2^8, N = 2^8, K = 2^6 per
-    bitstring, through the SIMT tile kernel (gemm_mode 1) and the tensor-core kernel (gemm_mode 2:
-    DMMA for ComplexF64, 3xTF32 for ComplexF32)."""
+    bitstring, through the SIMT tile kernel (gemm_mode 1), the tensor-core kernels of the auto choice (gemm_mode 2:
+    DMMA for ComplexF64, tcgen05 / TMEM 3xTF32 for ComplexF32) and the mma.sync kernels (gemm_mode 4)."""
     rng = np.random.default_rng(100 + seed)
     nm, nn, nk = 8, 8, 6
     M = list(range(1, nm + 1)); N = list(range(nm + 1, nm + nn + 1)); K = list(range(nm + nn + 1, nm + nn + nk + 1))

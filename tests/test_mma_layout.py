@@ -44,3 +44,21 @@ def test_tile_product(dtype, seed):
     want = A.astype(np.complex128) @ B.astype(np.complex128).T
     tol = 2e-6 if dtype == 0 else 1e-13       # 3xTF32: dropped lo*lo terms ~ 2^-22 per product
     assert np.max(np.abs(got - want)) / np.max(np.abs(want)) < tol
+
+
+def test_tc5_staging_layout(lib_built):
+    """tcgen05 kernel (csrc/qxb_gemm_tc5.cu): the per-bit byte offsets the gather adds up must reproduce the canonical
+    K-major no-swizzle core-matrix layout the UMMA descriptors announce (LBO 128 B, SBO 1024 B): element (row r,
+    complex k c) of a 2^tb-row tile at (r >> 3) * 1024 + (c >> 1) * 128 + (r & 7) * 16 + (c & 1) * 8."""
+    lib = lib_built
+    for tb in (7, 6):
+        seen = set()
+        for r in range(1 << tb):
+            for c in range(16):
+                idx = r | (c << tb)
+                off = sum(lib.qxb_debug_tc5_smem_bit(tb, b) for b in range(tb + 4) if (idx >> b) & 1)
+                assert off == (r >> 3) * 1024 + (c >> 1) * 128 + (r & 7) * 16 + (c & 1) * 8
+                seen.add(off)
+        assert len(seen) == (1 << tb) * 16 and max(seen) + 8 <= 128 * 32 * 4      # distinct, inside one 16 KB plane
+    # B: rows n and 64 + n of the 128-row real operand; 64 rows further = 8 groups of 8 rows = 8 * 1024 bytes
+    assert lib.qxb_debug_tc5_smem_bit(7, 6) == 8 * 1024
