@@ -13,9 +13,14 @@ value : whole-job amplitudes/s, bitstrings already resident in HBM, timed with C
         events on the launching stream (max over ranks)
 e2e   : the same through the host-buffer C-ABI call qxb_amplitudes (pinned host
         bitstrings -> H2D -> contraction -> D2H of the amplitudes inside the timed region)
-N > 1 : the linear slice-id space is split into N contiguous ranges, one process
-        per GPU (torchrun), partial amplitudes combined by ONE NCCL all-reduce of
-        [n_amp] complex numbers -> "scaling": "strong".
+N > 1 : one process per GPU (torchrun).  Default partition: every rank takes a contiguous share of the
+        BITSTRINGS over all slices (the dependency-tracked lowering makes a rank's work proportional to its
+        bitstrings; fixing slice variables per rank instead -- `--partition slices`, what north_star names --
+        leaves the slice-independent part of every node replicated and measured 0.44 efficiency at N = 8,
+        profiles/r1_scaling.md); the shards meet in ONE NCCL all-gather of [n_amp / N] complex numbers per rank
+        -> "scaling": "strong".
+The plan and every kernel knob are the library's defaults (deterministic: the re-planner is seeded); `--autotune`
+adds the measured choice among exact alternatives of round 1 (qxb200/tuning.py).
 """
 from __future__ import annotations
 
@@ -129,14 +134,24 @@ def cpu_sample(txt, data, w, n_bitstrings, n_slices_sample, cores):
     return amps_per_s, dt, sample
 
 
+def load_workload_numpy(name):
+    """The committed file triple with numpy only (.qx text + the .npz copy of the .jld2 arrays): the reference arm must
+    not map libqxb200.so."""
+    cache = os.path.join(ROOT, "workloads", name)
+    txt = open(cache + ".qx").read()
+    with np.load(cache + ".npz") as z:
+        data = {k: z[k] for k in z.files}
+    return txt, data, WORKLOADS[name]
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path on the host cores.  The
     real reference (Julia QXContexts) cannot be installed here (no Julia, no network;
-    DESIGN.md), so this is the oracle port."""
+    DESIGN.md), so this is the oracle port.  numpy only: no repo .so is loaded."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    txt, data, w = build_workload(args.workload)
+    txt, data, w = load_workload_numpy(args.workload)
     cores = os.cpu_count() or 1
     vals, times = [], []
     sample = ""
@@ -151,8 +166,11 @@ def run_reference(args):
         "impl": "reference", "metric": "RQC amplitudes/sec", "value": value, "unit": "amplitudes/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
-        "config": {"workload": args.workload, "n_amp": n_bs, "sample_slices": args.ref_slices},
+        "vs_baseline": None, "dtype": "f64" if w["dtype"] == "c64" else "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "n_amp": n_bs, "sample_slices": args.ref_slices, "same_config": False,
+                   "extrapolation": "each step contracts n_amp bitstrings x the first sample_slices slices of the file's own "
+                                    "contraction order (one slice of one bitstring per contraction, as QXContexts does); "
+                                    "amplitudes/s = contractions/s / total slices (slices are independent, equal-cost units)"},
         "cpu_baseline": {"value": value, "unit": "amplitudes/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "amplitudes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -204,24 +222,23 @@ class ClockSampler:
 
 
 def tune_plan(args, txt, data, w, g, dev, stream, world, dist, torch):
-    """-> (graph to run (uncompiled), its plan text, report).  Candidates: (planner model setting) x (QXB_MIN_LOB); the probe is
-    the first min(amps, 32768) bitstrings over the full slice space, 2 warm-up + 3 timed replays, CUDA events on the
-    stream the library launches on; results must agree with the baseline (default plan, default knobs) to 1e-9
-    (ComplexF64) / 1e-4 (ComplexF32) of the largest amplitude."""
+    """--autotune: -> (graph to run (uncompiled), its plan text, winning compile options, report).  Candidates: (planner
+    model setting) x (min_lob); the probe is the first min(amps, 32768) bitstrings over the full slice space, 2 warm-up +
+    3 timed replays, CUDA events on the stream the library launches on; results must agree with the baseline (default
+    plan, default knobs) to 1e-9 (ComplexF64) / 1e-4 (ComplexF32) of the largest amplitude.  The knobs travel as
+    qxb_options (compile keyword arguments): nothing is left in os.environ."""
     from qxb200.executor import Graph, autotune
     n_q = w["rows"] * w["cols"]
     n_probe = int(min(args.amps, 32768))
     from qxb200.tuning import candidates_of, plan_candidates
-    # trees of the planner under four settings of its L1 term (the first one is the graph already re-planned above) x
-    # QXB_MIN_LOB 8 / 7 / 6: the search is noisy at the +-5 % level between such settings (profiles/r1q_summary.md)
     plans = plan_candidates(txt, data, w["dtype"], args.replan_candidates, args.amps, first=g)
     cands = candidates_of(plans)
     bits = torch.from_numpy(synth_bits(n_probe, n_q)).to(dev)
     cdt = torch.complex64 if w["dtype"] == "c32" else torch.complex128
     out = torch.zeros(n_probe, dtype=cdt, device=dev)
 
-    def build(text):
-        return Graph.from_dsl(text, data, w["dtype"]).compile(amp_batch=args.amp_batch, cuda_graph=not args.no_graph)
+    def build(text, **kw):
+        return Graph.from_dsl(text, data, w["dtype"]).compile(amp_batch=args.amp_batch, cuda_graph=not args.no_graph, **kw)
 
     def probe(gc):
         S = gc.n_slices
@@ -244,24 +261,12 @@ def tune_plan(args, txt, data, w, g, dev, stream, world, dist, torch):
 
     tol = 1e-4 if w["dtype"] == "c32" else 1e-9
     best, report = autotune(cands, build, probe, reduce_times, rel_tol=tol)
-    tag, text, env = cands[best]
-    # second stage, on the winner only: the register budget of the K chunk (loads in flight per thread vs registers);
-    # 128 / 96 was 4.6 % faster than 96 / 64 on the r1p plan (profiles/r1p_summary.md) -- other plans may differ
-    stage2 = [(tag, text, env)] + [(f"{tag}/kc{m}", text, dict(env, QXB_KC_REGS_MULTI=str(m), QXB_KC_REGS_ONE=str(o)))
-                                   for m, o in ((96, 64), (160, 128))]
-    try:
-        best2, report2 = autotune(stage2, build, probe, reduce_times, rel_tol=tol)
-        if best2 > 0 and report2[best2].get("ms") is not None:
-            tag, text, env = stage2[best2]
-        report = report + report2[1:]
-    except Exception:                                        # noqa: BLE001  (keep the first-stage winner)
-        pass
+    tag, text, kw = cands[best]
     del bits, out
-    os.environ.update(env)                                   # in force for the timed graph, the profiled clone and the as-given run
     info = next(i for t, _, i in plans if tag.startswith(t + "/"))
     chosen = Graph.from_dsl(text, data, w["dtype"])
     chosen.replan_info = info
-    return chosen, text, {"chosen": tag, "probe_bitstrings": n_probe, "candidates": report}
+    return chosen, text, kw, {"chosen": tag, "options": kw, "probe_bitstrings": n_probe, "candidates": report}
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -290,18 +295,17 @@ def run_gpu(args):
     g = Graph.from_dsl(txt, data, w["dtype"], replan=0 if args.no_replan else args.replan_candidates,
                        replan_n_amp=args.amps)
     plan_txt = g.text
-    tune_report = None
-    if not args.no_replan and not args.no_autotune:
-        # Measured choice among exact alternatives before anything is timed (qxb200.executor.autotune): the tree of the
-        # L1-aware planner model vs the tree of the r1p model, each with the register-tile knob QXB_MIN_LOB = 8 / 7 / 6.
+    tune_report, knobs = None, {}
+    if not args.no_replan and args.autotune:
+        # Measured choice among exact alternatives before anything is timed (qxb200.executor.autotune).
         # Any failure in here leaves the run exactly as it was without tuning.
         try:
-            g, plan_txt, tune_report = tune_plan(args, txt, data, w, g, dev, stream, world, dist, torch)
+            g, plan_txt, knobs, tune_report = tune_plan(args, txt, data, w, g, dev, stream, world, dist, torch)
         except Exception as e:                                   # noqa: BLE001
-            tune_report = {"error": repr(e)[:300]}
-            for k in ("QXB_MIN_LOB", "QXB_PLAN_L1_BW"):
-                os.environ.pop(k, None)
-    g.compile(amp_batch=args.amp_batch, cuda_graph=not args.no_graph)
+            tune_report, knobs = {"error": repr(e)[:300]}, {}
+    import hashlib
+    plan_sha1 = hashlib.sha1(plan_txt.encode()).hexdigest()[:16]
+    g.compile(amp_batch=args.amp_batch, cuda_graph=not args.no_graph, **knobs)
     S = g.n_slices
     n_amp = args.amps
     # How the ranks share a step: either each rank takes a share of the bitstrings
@@ -337,7 +341,16 @@ def run_gpu(args):
     es = 8 if w["dtype"] == "c32" else 16
     n_mine = a1 - a0
 
+    # bitstring shards of equal size meet in ONE all-gather (each rank owns a disjoint [n_amp / N] range: nothing to
+    # sum); slice partitions and ragged shards need the sum -> all-reduce of the zero-padded vector
+    gather = world > 1 and mode == "amps" and n_amp % world == 0
+    shard_d = torch.zeros(max(n_mine, 1), dtype=cdt, device=dev) if gather else None
+
     def step_device():
+        if gather:
+            g.amplitudes_device(bits_d.data_ptr() + a0 * n_q, n_mine, shard_d.data_ptr(), 0, S)
+            dist.all_gather_into_tensor(torch.view_as_real(out_d), torch.view_as_real(shard_d))
+            return
         if mode == "amps":
             out_d.zero_()
             if n_mine:
@@ -353,6 +366,16 @@ def run_gpu(args):
         # the public host-buffer call: pinned bitstrings -> H2D -> contraction -> D2H, synchronised
         from qxb200._lib import check
         import ctypes as C
+        if gather:
+            # every rank: its shard through the host-buffer call; the shards then meet on the devices (256 KB per rank)
+            # and rank 0 reads the whole vector back -- what a job that writes one results file does
+            check(g._lib.qxb_amplitudes(g._h, C.c_void_p(bits_h.data_ptr() + a0 * n_q), n_mine, 0, S,
+                                        C.c_void_p(out_h.data_ptr() + a0 * es)))
+            shard_d.copy_(out_h[a0:a1], non_blocking=True)
+            dist.all_gather_into_tensor(torch.view_as_real(out_d), torch.view_as_real(shard_d))
+            if rank == 0:
+                out_h.copy_(out_d, non_blocking=False)
+            return
         if mode == "amps":
             out_h.zero_()
             if n_mine:
@@ -430,11 +453,11 @@ def run_gpu(args):
         # sanity: Porter-Thomas / norm check -- mean |amp|^2 * 2^n should be ~1 for an RQC
         norm = float(np.mean(np.abs(result) ** 2) * 2.0 ** n_q)
         roof = roofline(args, plan_txt, data, w, bits_d, out_d, n_amp if mode != "amps" else n_mine, s0, s1, assign,
-                        bits_off=a0 * n_q if mode == "amps" else 0)
+                        bits_off=a0 * n_q if mode == "amps" else 0, knobs=knobs, plan_sha1=plan_sha1)
         as_given = None
         if world == 1 and g.replan_info and g.replan_info.get("replanned") and not args.no_as_given:
             # the same step on the contraction order exactly as the file gives it (no re-planning)
-            g0 = Graph.from_dsl(txt, data, w["dtype"]).compile(amp_batch=args.amp_batch)
+            g0 = Graph.from_dsl(txt, data, w["dtype"]).compile(amp_batch=args.amp_batch, **knobs)
             for _ in range(3):
                 g0.amplitudes_device(bits_d.data_ptr(), n_amp, out_d.data_ptr(), 0, S)
             torch.cuda.synchronize()
@@ -453,7 +476,8 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             v, dt, sample = cpu_sample(txt, data, w, max(1, min(4, cores)), args.ref_slices, cores)
-            cpu = {"value": v, "unit": "amplitudes/s", "cores": cores, "kind": "port", "sample": sample}
+            cpu = {"value": v, "unit": "amplitudes/s", "cores": cores, "kind": "port", "sample": sample, "same_config": False,
+                   "n_amp": max(1, min(4, cores)), "sample_slices": args.ref_slices}
         es = 8 if w["dtype"] == "c32" else 16
         line = {
             "metric": "RQC amplitudes/sec", "value": value, "unit": "amplitudes/s", "n_gpus": world,
@@ -463,13 +487,18 @@ def run_gpu(args):
             "config": {"workload": args.workload, "n_amp_per_step": n_amp, "n_slices": S,
                        "n_qubits": n_q, "complex": w["dtype"],
                        "partition": ("single GPU" if world == 1 else
-                                     f"bitstrings split over {world} ranks, all slices each" if mode == "amps" else
-                                     f"all bitstrings on every rank, slice variables {[v + 1 for v in assign[0]]} fixed per rank"
-                                     if assign is not None else f"contiguous slice ranges / {world}"),
-                       "plan": ("re-planned for batched execution (qxb_graph_replan, exact re-association): "
+                                     f"bitstrings split over {world} ranks, all slices each; shards meet in one NCCL "
+                                     f"{'all-gather' if gather else 'all-reduce'}" if mode == "amps" else
+                                     f"all bitstrings on every rank, slice variables {[v + 1 for v in assign[0]]} fixed per rank; one NCCL all-reduce"
+                                     if assign is not None else f"contiguous slice ranges / {world}; one NCCL all-reduce"),
+                       "plan": ("re-planned for batched execution (qxb_graph_replan, exact re-association, seeded): "
                                 f"{g.replan_info['given_bytes'] / 1e9:.2f} -> {g.replan_info['bytes'] / 1e9:.2f} GB per "
                                 f"{g.replan_info['n_amp_model']} bitstrings") if g.replan_info and g.replan_info.get("replanned")
                                else "contraction order as given by the file",
+                       "plan_sha1": plan_sha1,
+                       "kernels": "library defaults (qxb_options all 0): block phase = one row program, chunk phase per op: "
+                                  "TMA ring kernel on rows >= 48 KB, TMA-staged / streaming contract kernels elsewhere"
+                                  if not knobs else f"autotuned options {knobs}",
                        "as_given_plan": as_given,
                        "autotune": tune_report,
                        "l2": l2_note,
@@ -486,13 +515,14 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def roofline(args, txt, data, w, bits_d, out_d, n_amp, s0, s1, assign=None, bits_off=0):
-    """Per-op CUDA-event timing of one more step (same stream, same inputs) on a
-    profiled clone of the graph; the reported kernel is the contraction kernel over
-    the DOMINANT contractions = top ops by FLOPs covering >= 80% of the step's FLOPs
-    (SURVEY.md 8d).  achieved = algorithmic bytes s*(|A|+|B|+|C|) / event time."""
+def roofline(args, txt, data, w, bits_d, out_d, n_amp, s0, s1, assign=None, bits_off=0, knobs=None, plan_sha1=""):
+    """Per-op CUDA-event timing of one more step (same stream, same inputs, same plan and knobs) on a profiled clone
+    of the graph; the reported kernels are those of the DOMINANT contractions = top ops by FLOPs covering >= 80% of
+    the step's FLOPs.  achieved = algorithmic bytes s*(|A|+|B|+|C|) / event time.
+    traffic = DRAM bytes per dominant launch from the committed ncu --set full capture, used ONLY when the capture was
+    taken on this very plan (profiles/ncu_traffic.json is keyed by workload and plan_sha1)."""
     from qxb200.executor import Graph
-    gp = Graph.from_dsl(txt, data, w["dtype"]).compile(amp_batch=args.amp_batch, profile=True)
+    gp = Graph.from_dsl(txt, data, w["dtype"]).compile(amp_batch=args.amp_batch, profile=True, **(knobs or {}))
     for _ in range(2):
         if assign is not None:
             gp.amplitudes_subspace_device(bits_d.data_ptr(), n_amp, out_d.data_ptr(), assign[0], assign[1])
@@ -516,28 +546,25 @@ def roofline(args, txt, data, w, bits_d, out_d, n_amp, s0, s1, assign=None, bits
     else:
         peak, src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-    # DRAM bytes per launch of the dominant kernels from the committed ncu --set full capture
-    # (taken at 1024 bitstrings per step; the traffic of these launches is linear in the batch)
     traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         t = json.load(open(tpath)).get(args.workload)
-        if t:
-            # the capture belongs to ONE plan: use it only while the dominant launches still move the bytes it saw
-            # (the planner's time model changed after the r1p capture, so the tree -- and its dominant ops -- did too)
-            per_launch = t["bytes_per_launch_mean_dominant"] * n_amp / float(t["at_amps"])
-            alg = by / max(launches, 1)
-            if alg > 0 and abs(per_launch - alg) / alg < 0.10:
-                traffic = per_launch
-            else:
-                traffic_note = (f"no ncu capture of this plan yet: the committed one ({t['source']}) saw {per_launch / 1e9:.2f} GB per "
-                                f"dominant launch, this step moves {alg / 1e9:.2f} GB algorithmic")
+        if t and t.get("plan_sha1") == plan_sha1 and not knobs:
+            traffic = t["bytes_per_launch_mean_dominant"] * n_amp / float(t["at_amps"])
+            traffic_note = f"ncu --set full of this plan ({t['source']}), {t['at_amps']} bitstrings, linear in the batch"
+        elif t:
+            traffic_note = (f"the committed ncu capture ({t.get('source')}) belongs to plan {t.get('plan_sha1')}, "
+                            f"this run timed plan {plan_sha1}: not used")
     all_ms = sum(o["ms"] for o in ops)
-    return {"bound": "hbm", "kernel": "contract_kernel (dominant contractions: top ops by FLOPs covering >=80%)",
+    kernels = sorted({o.get("kernel", "") for o in dom})
+    return {"bound": "hbm", "kernel": f"{' + '.join(kernels)} (dominant contractions: top ops by FLOPs covering >=80%)",
             "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s",
             "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_note": traffic_note,
             "bytes_per_launch": by / max(launches, 1), "ms_per_launch": ms / max(launches, 1),
             "dominant_ops": len(dom), "dominant_ms": ms, "all_contract_ms": all_ms,
+            "dominant": [{"op": o["name"], "kernel": o.get("kernel", ""), "nC": o.get("nC"), "nK": o.get("nK"), "ms": o["ms"],
+                          "gbs": o["bytes"] / o["ms"] / 1e6 if o["ms"] else None} for o in dom],
             "dominant_gflops": fl / (ms * 1e-3) / 1e9 if ms > 0 else 0.0,
             "all_ops_achieved": sum(o["bytes"] for o in ops) / (all_ms * 1e-3) / 1e9 if all_ms > 0 else 0.0}
 
@@ -554,8 +581,9 @@ def main():
     ap.add_argument("--ref-slices", type=int, default=64, help="slices per bitstring in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-replan", action="store_true", help="run the contraction order exactly as the file gives it")
-    ap.add_argument("--no-autotune", action="store_true",
-                    help="skip the measured choice among planner models / register-tile knobs (run the default plan and knobs)")
+    ap.add_argument("--autotune", action="store_true",
+                    help="measured choice among planner models / register-tile knobs before the timed region (round 1's default)")
+    ap.add_argument("--no-autotune", action="store_true", help="accepted for compatibility (autotune is off unless --autotune)")
     ap.add_argument("--replan-candidates", type=int, default=128, help="orders scored by the re-planner (seeded)")
     ap.add_argument("--no-as-given", action="store_true", help="skip the extra as-given-plan measurement")
     ap.add_argument("--partition", default="auto", choices=["auto", "amps", "slices"])

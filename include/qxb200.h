@@ -167,6 +167,22 @@ int  qxb_amplitudes_subspace(qxb_graph* g, const uint8_t* bits, int64_t n_amp, c
  * depend on saves nothing).  n_vars_out = 0 when the extents cannot factor n_parts (shard by
  * contiguous slice ranges instead).  Pure host logic. */
 int  qxb_partition_vars(qxb_graph* g, int n_parts, int32_t* vars_out /*may be NULL*/, int* n_vars_out);
+
+/* ---- several GPUs of one node behind the ABI (replaces the MPI layer of QXContexts.execute,
+ * bin/qxrun.jl:40-46 `-m` / `-s`, docs/src/users_guide.md:11-20).  One host thread, one compiled replica per device.
+ * qxb_multi_create takes an UNCOMPILED graph (built -- and, if wanted, re-planned -- through the calls above; it is
+ * not modified and may be destroyed afterwards), clones it onto n_devices devices (device_ids NULL: 0..n-1;
+ * n_devices <= 0: all visible) and compiles each replica there.
+ * qxb_multi_amplitudes: host buffers as qxb_amplitudes.  The devices form n_devices / sub_comm_size groups: each
+ * group takes a contiguous share of the bitstrings, the devices of a group split [slice_begin, slice_end) and their
+ * partial amplitudes are summed (on the host: 16 bytes per amplitude and device).  sub_comm_size 0 = auto: 1 (disjoint
+ * bitstring shards, nothing to reduce) when n_amp >= n_devices, else n_devices (all devices share the bitstrings). */
+typedef struct qxb_multi qxb_multi;
+int  qxb_multi_create(qxb_multi** m, const qxb_graph* g, int n_devices, const int* device_ids, const qxb_options* opts);
+void qxb_multi_destroy(qxb_multi* m);
+int  qxb_multi_num_devices(const qxb_multi* m, int* n);
+int  qxb_multi_amplitudes(qxb_multi* m, const uint8_t* bits, int64_t n_amp, int64_t slice_begin, int64_t slice_end,
+                          int sub_comm_size, void* out);
 /* Cost model of one step: algorithmic bytes moved by the non-constant nodes when the variables in
  * free_mask are batched (the others fixed) and n_amp bitstrings are contracted.  Host logic only;
  * used to choose between sharding bitstrings and sharding slice variables over the ranks. */
@@ -250,6 +266,11 @@ int  qxb_params_read(const char* yml_path, qxb_params* p, char* bitstrings, int6
 int  qxb_execute_files(const char* dsl_file, const char* input_file, const char* param_file, const char* output_file,
                        int dtype, int64_t max_amplitudes, int64_t max_slices, int replan_candidates,
                        int64_t* n_amplitudes, double* seconds);
+/* The same on n_devices GPUs of this node (qxb_multi; List / Uniform methods -- Rejection stays on one device):
+ * what `qxrun -m [-s K]` runs.  n_devices <= 0: all visible devices; sub_comm_size as in qxb_multi_amplitudes. */
+int  qxb_execute_files_multi(const char* dsl_file, const char* input_file, const char* param_file, const char* output_file,
+                             int dtype, int64_t max_amplitudes, int64_t max_slices, int replan_candidates,
+                             int n_devices, int sub_comm_size, int64_t* n_amplitudes, double* seconds);
 
 /* test hook (not part of the drop-in surface): shared-memory offset contributed by tile-index bit `bit` in the
  * tensor-core GEMM kernels' staging layouts; tests/test_mma_layout.py replays the kernels' index arithmetic on the CPU */

@@ -29,11 +29,15 @@ using namespace qxb;
 namespace {
 
 thread_local std::string g_err;
+// One host thread drives the library.  g_device is the CURRENT device; every device that was ever selected keeps its
+// own stream and SM count (qxb_multi drives several devices of one node from the same thread).
 int g_device = -1;
 cudaStream_t g_own_stream = nullptr;
 cudaStream_t g_ext_stream = nullptr;
 bool g_use_ext = false;
 int g_num_sms = 148;
+struct DevState { cudaStream_t own = nullptr; int sms = 148; };
+std::map<int, DevState> g_devs;
 
 inline cudaStream_t stream() { return g_use_ext ? g_ext_stream : g_own_stream; }
 
@@ -44,18 +48,38 @@ inline cudaStream_t stream() { return g_use_ext ? g_ext_stream : g_own_stream; }
             throw Error(QXB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));         \
     } while (0)
 
-void ensure_init() {
-    if (g_device >= 0) return;
+// make `device` current: cudaSetDevice + this device's stream and SM count (created on first use)
+void use_device(int device) {
+    if (device == g_device) return;
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0)
         throw Error(QXB_ERR_CUDA, "no CUDA device available (libqxb200 has no CPU fallback)");
-    CUDA_OK(cudaSetDevice(0));
-    g_device = 0;
-    CUDA_OK(cudaStreamCreateWithFlags(&g_own_stream, cudaStreamNonBlocking));
-    cudaDeviceProp prop;
-    CUDA_OK(cudaGetDeviceProperties(&prop, g_device));
-    g_num_sms = prop.multiProcessorCount;
+    if (device < 0 || device >= n) throw Error(QXB_ERR_ARG, "device index out of range");
+    CUDA_OK(cudaSetDevice(device));
+    auto it = g_devs.find(device);
+    if (it == g_devs.end()) {
+        DevState st;
+        CUDA_OK(cudaStreamCreateWithFlags(&st.own, cudaStreamNonBlocking));
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, device));
+        st.sms = prop.multiProcessorCount;
+        it = g_devs.emplace(device, st).first;
+    }
+    g_device = device;
+    g_own_stream = it->second.own;
+    g_num_sms = it->second.sms;
+}
+
+void ensure_init() {
+    if (g_device >= 0) return;
+    use_device(0);
+}
+
+// per-device, per-kernel one-time configuration (function attributes belong to the device's context)
+bool first_use(const void* func) {
+    static std::set<std::pair<int, const void*>> seen;
+    return seen.insert({g_device, func}).second;
 }
 
 struct DevBuf {
@@ -124,6 +148,7 @@ struct qxb_graph {
     Program prog;
     std::map<std::string, HostData> data;
     bool compiled = false;
+    int device = -1;                 // the device the graph was compiled on (its buffers, streams and CUDA graphs live there)
     qxb_options opts{};
     std::map<std::string, DevBuf> leafbuf;
     std::map<uint64_t, std::unique_ptr<Variant>> variants;
@@ -406,7 +431,10 @@ void build_templates(Variant& v, int dtype, const qxb_options& opts) {
             if (gemm_func(dtype, tmb, tnb)) { v.gemm_tmb[i] = tmb; v.gemm_tnb[i] = tnb; }
         }
         // tcgen05 / TMEM kernel (ComplexF32): 2^7 x 2^6 x 2^4 block tile
-        if (dtype == QXB_C32 && op.nK >= 4 && mall.size() >= 7 && nall.size() >= 6 && nC <= 31 && TA.span_bits <= 31 && TB.span_bits <= 31) {
+        // (K >= 2^6: with fewer than four 16-k chunks per tile the two-stage pipeline never fills -- measured on the K = 2^4
+        //  nodes of the Sycamore depth-7 plan: 10.8 TFLOP/s against 14.3 for the mma.sync kernel, profiles/r2_summary.md)
+        if (dtype == QXB_C32 && op.nK >= knob(0, "QXB_TC5_MIN_K", 6) && mall.size() >= 7 && nall.size() >= 6 && nC <= 31 &&
+            TA.span_bits <= 31 && TB.span_bits <= 31) {
             make_gemm(v.gtmpl5[i], 7, 6, 4, [&](bool is_b, int bit) { return gemm_tc5_smem_bit(is_b ? 6 : 7, bit); });
             v.gemm5[i] = 1;
         }
@@ -477,11 +505,8 @@ Node contract_node(const RunCtx& c, int i) {
         n.func = gemm_tc5_func(); n.kname = "gemm_tc5";
         n.block = dim3((unsigned)gemm_tc5_threads());
         n.smem = gemm_tc5_smem_bytes();
-        static bool tc5_configured = false;
-        if (!tc5_configured) {
+        if (first_use(n.func))
             CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n.smem));
-            tc5_configured = true;
-        }
         n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(q.tiles, (long long)g_num_sms)));
         n.arg(q);
         n.variant = c.variant_key; n.op = i;
@@ -502,14 +527,14 @@ Node contract_node(const RunCtx& c, int i) {
             n.func = tc; n.kname = "gemm_tc";
             n.block = dim3((unsigned)gemm_mma_threads(g->dtype));
             n.smem = gemm_mma_smem_bytes(g->dtype);
-            static std::map<const void*, int> resident;
-            auto it = resident.find(tc);
+            static std::map<std::pair<int, const void*>, int> resident;
+            auto it = resident.find({g_device, tc});
             if (it == resident.end()) {
                 int nb = 0;
                 if (n.smem > 48 * 1024)
                     CUDA_OK(cudaFuncSetAttribute(tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n.smem));
                 CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tc, (int)n.block.x, n.smem));
-                it = resident.emplace(tc, std::max(nb, 1)).first;
+                it = resident.emplace(std::make_pair(g_device, tc), std::max(nb, 1)).first;
             }
             n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(q.tiles, (long long)g_num_sms * it->second)));
         } else {
@@ -622,11 +647,8 @@ Node contract_node(const RunCtx& c, int i) {
                 n.smem = ring_smem_bytes(rd.n_units, nA, nB, nCe, shA, shB, stages, es);
                 n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(p.U, (long long)g_num_sms)));
                 n.block = dim3(kRowThreads);
-                static std::set<const void*> ring_configured;
-                if (!ring_configured.count(n.func)) {
+                if (first_use(n.func))
                     CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                    ring_configured.insert(n.func);
-                }
                 n.arg(R);
                 n.variant = c.variant_key; n.op = i;
                 const double u = (double)p.U;
@@ -640,21 +662,15 @@ Node contract_node(const RunCtx& c, int i) {
             n.func = tf; n.kname = "tma";
             n.smem = stage * (size_t)tma_stages + 64;
             n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(p.U, (long long)g_num_sms)));
-            static std::set<const void*> tma_configured;
-            if (!tma_configured.count(tf)) {
+            if (first_use(tf))
                 CUDA_OK(cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                tma_configured.insert(tf);
-            }
         } else if (sf) {
             p.aBits = A.span_bits; p.bBits = B.span_bits;
             n.func = sf; n.kname = "smem";
             n.smem = stage;
             n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(p.U, (long long)g_num_sms * 2)));
-            static std::set<const void*> configured;
-            if (stage > 48 * 1024 && !configured.count(sf)) {
+            if (first_use(sf))
                 CUDA_OK(cudaFuncSetAttribute(sf, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                configured.insert(sf);
-            }
         } else {
             // QXB_MINB=3 (experiment): the register allocation bounded for three resident CTAs per SM where it does not spill
             const int minb = [] { const char* e = getenv("QXB_MINB"); return e ? atoi(e) : 2; }();
@@ -949,11 +965,8 @@ Node row_node(const RunCtx& c, Variant::RowDev& rd, bool chunk, const uint8_t* d
         P.timing = (long long*)v.row_timing.p;
     }
     n.smem = row_fixed_smem_bytes(n_slots) + (chunk ? (size_t)rp.arena_elems * g->es() : 0);
-    static std::set<const void*> configured;
-    if (!configured.count(n.func)) {
+    if (first_use(n.func))
         CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured.insert(n.func);
-    }
     int per_sm = 1;
     if (chunk) {
         CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, n.func, kRowThreads, n.smem));
@@ -1295,25 +1308,14 @@ int qxb_version(void) { return 100; }
 const char* qxb_last_error(void) { return g_err.c_str(); }
 
 int qxb_init(int device) {
-    return guard([&] {
-        int n = 0;
-        cudaError_t e = cudaGetDeviceCount(&n);
-        if (e != cudaSuccess || n == 0)
-            throw Error(QXB_ERR_CUDA, "no CUDA device available (libqxb200 has no CPU fallback)");
-        if (device < 0 || device >= n) throw Error(QXB_ERR_ARG, "device index out of range");
-        CUDA_OK(cudaSetDevice(device));
-        if (g_own_stream && g_device != device) { cudaStreamDestroy(g_own_stream); g_own_stream = nullptr; }
-        g_device = device;
-        if (!g_own_stream) CUDA_OK(cudaStreamCreateWithFlags(&g_own_stream, cudaStreamNonBlocking));
-        cudaDeviceProp prop;
-        CUDA_OK(cudaGetDeviceProperties(&prop, device));
-        g_num_sms = prop.multiProcessorCount;
-    });
+    return guard([&] { use_device(device); });
 }
 
 int qxb_shutdown(void) {
     return guard([&] {
-        if (g_own_stream) { cudaStreamDestroy(g_own_stream); g_own_stream = nullptr; }
+        for (auto& kv : g_devs) if (kv.second.own) { cudaSetDevice(kv.first); cudaStreamDestroy(kv.second.own); }
+        g_devs.clear();
+        g_own_stream = nullptr;
         g_device = -1; g_use_ext = false; g_ext_stream = nullptr;
     });
 }
@@ -1551,6 +1553,7 @@ int qxb_graph_compile(qxb_graph* g, const qxb_options* opts) {
         ensure_analysed(g);
         if (opts) g->opts = *opts;
         ensure_init();
+        g->device = g_device;
         upload_leaves(g);
         g->compiled = true;
         try {
@@ -1571,6 +1574,7 @@ int qxb_amplitudes_device(qxb_graph* g, const uint8_t* d_bits, int64_t n_amp, in
         if (!g) throw Error(QXB_ERR_ARG, "null graph");
         if (n_amp > 0 && (!d_out || (!d_bits && g->prog.n_outputs > 0))) throw Error(QXB_ERR_ARG, "null buffer");
         ensure_init();
+        if (g->compiled) use_device(g->device);
         run_amplitudes(g, d_bits, n_amp, s0, s1, d_out);
         if (g->opts.profile) {
             CUDA_OK(cudaStreamSynchronize(stream()));
@@ -1587,6 +1591,7 @@ int qxb_amplitudes(qxb_graph* g, const uint8_t* bits, int64_t n_amp, int64_t s0,
         if (!out || (!bits && g->prog.n_outputs > 0)) throw Error(QXB_ERR_ARG, "null buffer");
         if (!g->compiled) throw Error(QXB_ERR_STATE, "graph not compiled");
         ensure_init();
+        use_device(g->device);
         const size_t nb = (size_t)n_amp * std::max(1, g->prog.n_outputs);
         {
             unsigned char seen = 0;                       // OR-reduction: vectorises, unlike an early-exit loop
@@ -1616,6 +1621,7 @@ int qxb_amplitudes_subspace(qxb_graph* g, const uint8_t* bits, int64_t n_amp, co
             throw Error(QXB_ERR_ARG, "null buffer");
         if (!g->compiled) throw Error(QXB_ERR_STATE, "graph not compiled");
         ensure_init();
+        use_device(g->device);
         cudaStream_t st = stream();
         if (on_device) {
             run_subspace(g, bits, n_amp, fixed_vars, fixed_vals, n_fixed, out);
@@ -1732,6 +1738,163 @@ int qxb_profile_dump(qxb_graph* g, const char* path) {
         fclose(f);
     });
 }
+
+}  // extern "C"
+
+// =============================================================== several GPUs of one node behind the C ABI
+// ("qxb_init(n_devices, ids) + one tiny reduce").  One host thread, one compiled replica of the
+// graph per device.  A call splits its work two ways, the reference's two levels of parallelism
+// (docs/src/users_guide.md:11-20; bin/qxrun.jl:40-46 `-m`, `-s`): the devices form n_devices / sub_comm_size groups;
+// every group takes a contiguous share of the BITSTRINGS, the devices of a group split the SLICE range and their
+// partial amplitudes are summed.  Disjoint bitstring shards land in disjoint ranges of the caller's buffer: with
+// sub_comm_size = 1 there is nothing to reduce at all; inside a group the sum runs over sub_comm_size partial
+// vectors of the group's amplitudes on the host (the "single tiny reduce": 16 bytes per amplitude and device).
+struct HostPinned {
+    void* p = nullptr; size_t bytes = 0;
+    void reserve(size_t n) {
+        if (n <= bytes) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr; bytes = 0;
+        if (cudaHostAlloc(&p, n, cudaHostAllocPortable) != cudaSuccess) { p = nullptr; throw Error(QXB_ERR_MEM, "cudaHostAlloc failed"); }
+        bytes = n;
+    }
+    ~HostPinned() { if (p) cudaFreeHost(p); }
+};
+struct qxb_multi {
+    std::vector<int> devs;
+    std::vector<qxb_graph*> graphs;
+    std::vector<std::unique_ptr<HostPinned>> h_bits, h_out;
+    ~qxb_multi() { for (qxb_graph* g : graphs) delete g; }
+};
+
+extern "C" {
+
+int qxb_multi_create(qxb_multi** m, const qxb_graph* proto, int n_devices, const int* device_ids, const qxb_options* opts) {
+    return guard([&] {
+        if (!m || !proto) throw Error(QXB_ERR_ARG, "null argument");
+        if (proto->compiled) throw Error(QXB_ERR_STATE, "qxb_multi_create takes an uncompiled graph (it compiles one replica per device)");
+        int avail = 0;
+        cudaError_t e = cudaGetDeviceCount(&avail);
+        if (e != cudaSuccess || avail == 0)
+            throw Error(QXB_ERR_CUDA, "no CUDA device available (libqxb200 has no CPU fallback)");
+        if (n_devices <= 0) n_devices = avail;
+        std::unique_ptr<qxb_multi> mm(new qxb_multi());
+        for (int i = 0; i < n_devices; ++i) {
+            const int d = device_ids ? device_ids[i] : i;
+            if (d < 0 || d >= avail) throw Error(QXB_ERR_ARG, "device index out of range");
+            if (std::find(mm->devs.begin(), mm->devs.end(), d) != mm->devs.end()) throw Error(QXB_ERR_ARG, "device listed twice");
+            mm->devs.push_back(d);
+        }
+        const int saved = g_device;
+        for (int d : mm->devs) {
+            use_device(d);
+            std::unique_ptr<qxb_graph> g(new qxb_graph());
+            g->dtype = proto->dtype;
+            g->prog.cmds = proto->prog.cmds;             // the (possibly re-planned) program, statement by statement
+            g->data = proto->data;
+            g->opts = opts ? *opts : proto->opts;
+            int rc = qxb_graph_compile(g.get(), nullptr);
+            if (rc != QXB_OK) throw Error(rc, g_err);
+            mm->graphs.push_back(g.release());
+            mm->h_bits.emplace_back(new HostPinned());
+            mm->h_out.emplace_back(new HostPinned());
+        }
+        if (saved >= 0) use_device(saved);
+        *m = mm.release();
+    });
+}
+
+void qxb_multi_destroy(qxb_multi* m) { delete m; }
+
+int qxb_multi_num_devices(const qxb_multi* m, int* n) {
+    return guard([&] {
+        if (!m || !n) throw Error(QXB_ERR_ARG, "null argument");
+        *n = (int)m->devs.size();
+    });
+}
+
+int qxb_multi_amplitudes(qxb_multi* m, const uint8_t* bits, int64_t n_amp, int64_t s0, int64_t s1, int sub_comm_size, void* out) {
+    return guard([&] {
+        if (!m) throw Error(QXB_ERR_ARG, "null multi-GPU handle");
+        if (n_amp < 0) throw Error(QXB_ERR_ARG, "negative amplitude count");
+        if (n_amp == 0) return;
+        qxb_graph* g0 = m->graphs[0];
+        const int n_out = g0->prog.n_outputs;
+        if (!out || (!bits && n_out > 0)) throw Error(QXB_ERR_ARG, "null buffer");
+        const int64_t S = num_slices(g0->prog);
+        if (s0 < 0 || s1 > S || s0 > s1) throw Error(QXB_ERR_ARG, "slice range out of bounds");
+        if (root_elems(g0) != 1) throw Error(QXB_ERR_UNSUPP, "qxb_multi_amplitudes: tensor-valued save (open network)");
+        {
+            unsigned char seen = 0;
+            const size_t nbits = (size_t)n_amp * n_out;
+            for (size_t i = 0; i < nbits; ++i) seen |= bits[i];
+            if (seen > 3) throw Error(QXB_ERR_ARG, "bitstring entries must be 0, 1, 2 ('+') or 3 ('-')");
+        }
+        const int n_dev = (int)m->devs.size();
+        // auto: enough bitstrings -> every device its own shard (nothing to sum); a handful of amplitudes over many
+        // slices (the Sycamore-like configuration) -> all devices share the bitstrings and split the slices
+        int k = sub_comm_size > 0 ? sub_comm_size : (n_amp >= n_dev ? 1 : n_dev);
+        if (k > n_dev || n_dev % k) throw Error(QXB_ERR_ARG, "sub_comm_size must divide the number of devices");
+        const int groups = n_dev / k;
+        const size_t es = g0->es();
+        const int saved = g_device;
+        const bool saved_ext = g_use_ext;
+        g_use_ext = false;                                // the replicas run on their own devices' streams
+        struct Part { int64_t a0, a1, b0, b1; };
+        std::vector<Part> parts(n_dev);
+        try {
+            for (int i = 0; i < n_dev; ++i) {
+                const int grp = i / k, r = i % k;
+                Part& p = parts[i];
+                p.a0 = n_amp * grp / groups; p.a1 = n_amp * (grp + 1) / groups;
+                p.b0 = s0 + (s1 - s0) * r / k; p.b1 = s0 + (s1 - s0) * (r + 1) / k;
+                const int64_t n = p.a1 - p.a0;
+                if (n == 0 || (p.b1 == p.b0 && s1 > s0)) continue;
+                qxb_graph* g = m->graphs[i];
+                use_device(m->devs[i]);
+                cudaStream_t st = stream();
+                HostPinned &hb = *m->h_bits[i], &ho = *m->h_out[i];
+                hb.reserve((size_t)n * std::max(1, n_out)); ho.reserve((size_t)n * es);
+                g->d_bits.reserve((size_t)n * std::max(1, n_out));
+                g->d_out.reserve((size_t)n * es);
+                if (n_out > 0) {
+                    memcpy(hb.p, bits + (size_t)p.a0 * n_out, (size_t)n * n_out);
+                    CUDA_OK(cudaMemcpyAsync(g->d_bits.p, hb.p, (size_t)n * n_out, cudaMemcpyHostToDevice, st));
+                }
+                run_amplitudes(g, (const uint8_t*)g->d_bits.p, n, p.b0, p.b1, g->d_out.p);
+                CUDA_OK(cudaMemcpyAsync(ho.p, g->d_out.p, (size_t)n * es, cudaMemcpyDeviceToHost, st));
+            }
+            // every device is busy now; collect in order
+            if (k > 1) memset(out, 0, (size_t)n_amp * es);
+            for (int i = 0; i < n_dev; ++i) {
+                const Part& p = parts[i];
+                const int64_t n = p.a1 - p.a0;
+                if (n == 0 || (p.b1 == p.b0 && s1 > s0)) continue;
+                use_device(m->devs[i]);
+                CUDA_OK(cudaStreamSynchronize(stream()));
+                char* dst = (char*)out + (size_t)p.a0 * es;
+                if (k == 1) { memcpy(dst, m->h_out[i]->p, (size_t)n * es); continue; }
+                if (g0->dtype == QXB_C32) {
+                    float* o = (float*)dst; const float* v = (const float*)m->h_out[i]->p;
+                    for (int64_t j = 0; j < 2 * n; ++j) o[j] += v[j];
+                } else {
+                    double* o = (double*)dst; const double* v = (const double*)m->h_out[i]->p;
+                    for (int64_t j = 0; j < 2 * n; ++j) o[j] += v[j];
+                }
+            }
+        } catch (...) {
+            g_use_ext = saved_ext;
+            if (saved >= 0) { try { use_device(saved); } catch (...) {} }
+            throw;
+        }
+        g_use_ext = saved_ext;
+        if (saved >= 0) use_device(saved);
+    });
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // test hook: the row program of one phase (qxb_rowprog.h) exactly as the executor would hand it to rowprog_kernel
 // (unit descriptors and slot table of build_row_tables; tensors outside the arena keep a null pointer and are named

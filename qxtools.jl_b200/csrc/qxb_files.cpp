@@ -439,6 +439,14 @@ int qxb_params_read(const char* yml_path, qxb_params* p, char* bitstrings, int64
 int qxb_execute_files(const char* dsl_file, const char* input_file, const char* param_file, const char* output_file,
                       int dtype, int64_t max_amplitudes, int64_t max_slices, int replan_candidates,
                       int64_t* n_amplitudes, double* seconds) {
+    return qxb_execute_files_multi(dsl_file, input_file, param_file, output_file, dtype, max_amplitudes, max_slices,
+                                   replan_candidates, 1, 1, n_amplitudes, seconds);
+}
+
+int qxb_execute_files_multi(const char* dsl_file, const char* input_file, const char* param_file, const char* output_file,
+                            int dtype, int64_t max_amplitudes, int64_t max_slices, int replan_candidates,
+                            int n_devices, int sub_comm_size, int64_t* n_amplitudes, double* seconds) {
+    qxb_multi* multi = nullptr;
     qxb_graph* g = nullptr;
     int rc = guard([&] {
         if (!dsl_file) throw Error(QXB_ERR_ARG, "no DSL file given");
@@ -473,7 +481,11 @@ int qxb_execute_files(const char* dsl_file, const char* input_file, const char* 
             }
         if (replan_candidates > 0)      // plan for the batch the run will use (Rejection: candidate batches of 1024)
             ok(qxb_graph_replan(g, replan_candidates, pr.p.method == QXB_METHOD_REJECTION ? 1024 : (n_amp > 0 ? n_amp : 1), nullptr, nullptr));
-        ok(qxb_graph_compile(g, nullptr));
+        // several GPUs (qxrun -m): one replica per device for the List / Uniform methods; the rejection sampler is
+        // sequential in its acceptance bound and stays on one device
+        const bool use_multi = n_devices != 1 && pr.p.method != QXB_METHOD_REJECTION;
+        if (use_multi) ok(qxb_multi_create(&multi, g, n_devices, nullptr, nullptr));
+        else ok(qxb_graph_compile(g, nullptr));
         int64_t n_slices = 0;
         ok(qxb_graph_num_slices(g, &n_slices));
         if (max_slices >= 0 && max_slices < n_slices) n_slices = max_slices;                  // qxrun.jl:36-39
@@ -522,7 +534,8 @@ int qxb_execute_files(const char* dsl_file, const char* input_file, const char* 
                 }
             }
         } else if (n_amp > 0) {
-            ok(qxb_amplitudes(g, bits.data(), n_amp, 0, n_slices, amps.data()));
+            if (multi) ok(qxb_multi_amplitudes(multi, bits.data(), n_amp, 0, n_slices, sub_comm_size, amps.data()));
+            else ok(qxb_amplitudes(g, bits.data(), n_amp, 0, n_slices, amps.data()));
         }
         const int64_t n_res = (int64_t)bs.size();
         double t3 = now();
@@ -547,6 +560,7 @@ int qxb_execute_files(const char* dsl_file, const char* input_file, const char* 
         if (n_amplitudes) *n_amplitudes = n_res;
         if (seconds) { seconds[0] = t1 - t0; seconds[1] = t2 - t1; seconds[2] = t3 - t2; seconds[3] = t4 - t3; }
     });
+    if (multi) qxb_multi_destroy(multi);
     if (g) qxb_graph_destroy(g);
     return rc;
 }

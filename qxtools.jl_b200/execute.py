@@ -106,7 +106,7 @@ def execute(dsl_file: str, input_file: Optional[str] = None, param_file: Optiona
         probe = bits_from_strings(bitstrings[:min(len(bitstrings), 32768)], g0.n_outputs)
         del g0
         g, tune_report = tune(text, data, dtype, np.ascontiguousarray(probe), replan_candidates=32 if replan < 0 else max(1, replan))
-        g.compile()
+        g.compile(**tune_report.get("options", {}))
     else:
         g = Graph.from_dsl(text, data, dtype, replan=replan, replan_n_amp=max(1, n_model)).compile()
     if g.root_dims:

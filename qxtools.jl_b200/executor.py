@@ -315,25 +315,56 @@ class Graph:
             return json.load(f)
 
 
+class MultiGraph:
+    """Several GPUs of one node behind the C ABI (``qxb_multi_*``, include/qxb200.h): one compiled replica of an
+    UNCOMPILED ``Graph`` per device, driven by this one process.  ``amplitudes`` splits the bitstrings across groups of
+    ``sub_comm_size`` devices and the slice range inside a group (0 = auto), like ``-m`` / ``-s`` of bin/qxrun.jl."""
+
+    def __init__(self, graph: "Graph", n_devices: int = 0, device_ids: Optional[Sequence[int]] = None, **compile_kw):
+        self._lib = graph._lib
+        self._h = C.c_void_p()
+        self.n_outputs, self.np_dtype, self.n_slices = graph.n_outputs, graph.np_dtype, graph.n_slices
+        o = Graph._options(**compile_kw)
+        ids = (C.c_int * len(device_ids))(*device_ids) if device_ids else None
+        check(self._lib.qxb_multi_create(C.byref(self._h), graph._h, len(device_ids) if device_ids else n_devices, ids, C.byref(o)))
+        n = C.c_int()
+        check(self._lib.qxb_multi_num_devices(self._h, C.byref(n)))
+        self.n_devices = n.value
+
+    def amplitudes(self, bitstrings, slice_begin: int = 0, slice_end: Optional[int] = None, sub_comm_size: int = 0) -> np.ndarray:
+        if isinstance(bitstrings, np.ndarray) and bitstrings.dtype == np.uint8:
+            bits = np.ascontiguousarray(bitstrings)
+        else:
+            bits = np.ascontiguousarray(bits_from_strings(list(bitstrings), self.n_outputs))
+        n = bits.shape[0]
+        out = np.zeros(n, dtype=self.np_dtype)
+        check(self._lib.qxb_multi_amplitudes(self._h, bits.ctypes.data_as(C.c_void_p), n, slice_begin,
+                                             self.n_slices if slice_end is None else slice_end, sub_comm_size,
+                                             out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.qxb_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+
 def autotune(candidates, build, probe, reduce_times=None, rel_tol: float = 1e-9):
     """Measured choice among EXACT alternatives of the same program (different contraction trees from the re-planner,
     different kernel-selection knobs): every candidate is built, run on the same probe input and timed; a candidate
     whose result differs from the first one's by more than ``rel_tol`` (relative to the largest amplitude), or that
     raises, is discarded.  The model picks the candidates, the GPU picks the winner.
 
-    ``candidates``: ``[(tag, plan_text, env)]`` -- ``env`` = library knobs (``os.environ`` entries) in force while the
-    candidate is compiled and run; the first candidate is the baseline.  ``build(plan_text) -> graph``;
-    ``probe(graph) -> (milliseconds, result ndarray)``; ``reduce_times(list) -> list`` combines the times over the
-    ranks of a multi-GPU job (max), so that every rank takes the same decision.
-    Returns ``(index, report)``; index 0 when nothing could be measured."""
-    import os
+    ``candidates``: ``[(tag, plan_text, options)]`` -- ``options`` = keyword arguments of ``Graph.compile`` (the fields
+    of ``qxb_options``: nothing is left behind in ``os.environ``); the first candidate is the baseline.
+    ``build(plan_text, **options) -> graph``; ``probe(graph) -> (milliseconds, result ndarray)``;
+    ``reduce_times(list) -> list`` combines the times over the ranks of a multi-GPU job (max), so that every rank takes
+    the same decision.  Returns ``(index, report)``; index 0 when nothing could be measured."""
     times, report, ref = [], [], None
-    for tag, text, env in candidates:
-        saved = {k: os.environ.get(k) for k in env}
+    for tag, text, kw in candidates:
         ms, note = float("inf"), "ok"
         try:
-            os.environ.update(env)
-            g = build(text)
+            g = build(text, **kw)
             t, res = probe(g)
             res = np.asarray(res)
             del g
@@ -351,12 +382,6 @@ def autotune(candidates, build, probe, reduce_times=None, rel_tol: float = 1e-9)
                     note = f"discarded: differs from the baseline by {diff:.2e}"
         except Exception as e:                       # a candidate must never take the run down
             note = f"failed: {e!r}"[:200]
-        finally:
-            for k, v in saved.items():
-                if v is None:
-                    os.environ.pop(k, None)
-                else:
-                    os.environ[k] = v
         times.append(ms)
         report.append({"tag": tag, "ms": None if ms == float("inf") else ms, "note": note})
     if reduce_times is not None:

@@ -6,8 +6,8 @@ that helps one plan can hurt another.  ``tune`` turns the models' proposals into
 
 * trees: the planner under several settings of its L1 term (``QXB_PLAN_L1_BW``: default 19.9 TB/s, 0 = single-rate
   model, 14, 30) -- every tree is an exact re-association of the same network;
-* register-tile knob ``QXB_MIN_LOB`` = 8 / 7 / 6 (how many C bits stay thread bits: below 8 the nodes with <= 2^8
-  elements per bitstring get a register tile; same kernel, different launch template).
+* register-tile knob ``min_lob`` = 8 / 7 / 6 (``qxb_options``: how many C bits stay thread bits: below 8 the nodes with
+  <= 2^8 elements per bitstring get a register tile; same kernel, different launch template).
 
 Every candidate is compiled, run on the same probe bitstrings and timed; one that raises, or whose amplitudes differ
 from the baseline's, is discarded (``executor.autotune``).  Used by ``bench.py`` (device buffers, CUDA events, max over
@@ -56,14 +56,14 @@ def plan_candidates(txt: str, data: Dict[str, np.ndarray], dtype: str, replan_ca
 
 
 def candidates_of(plans, min_lobs: Sequence[int] = MIN_LOBS):
-    """(planner setting) x (QXB_MIN_LOB) -> ``[(tag, plan text, env)]`` for ``executor.autotune``."""
-    return [(f"{tag}/lob{lob}", text, ({} if lob == 8 else {"QXB_MIN_LOB": str(lob)})) for tag, text, _ in plans for lob in min_lobs]
+    """(planner setting) x (min_lob) -> ``[(tag, plan text, compile options)]`` for ``executor.autotune``."""
+    return [(f"{tag}/lob{lob}", text, {"min_lob": lob}) for tag, text, _ in plans for lob in min_lobs]
 
 
 def tune(txt: str, data: Dict[str, np.ndarray], dtype: str, probe_bits: np.ndarray, replan_candidates: int = 32,
          compile_kw: Optional[dict] = None, rel_tol: Optional[float] = None):
-    """-> (uncompiled ``Graph`` of the winning tree, report).  The winning ``QXB_MIN_LOB`` stays in ``os.environ``
-    (the launch templates are built when the returned graph is compiled and run)."""
+    """-> (uncompiled ``Graph`` of the winning tree, report).  ``report["options"]`` = the winning compile options
+    (pass them to ``Graph.compile``; nothing is left in ``os.environ``)."""
     from .executor import Graph, autotune, synchronize
     compile_kw = compile_kw or {}
     plans = plan_candidates(txt, data, dtype, replan_candidates, int(probe_bits.shape[0]))
@@ -71,8 +71,8 @@ def tune(txt: str, data: Dict[str, np.ndarray], dtype: str, probe_bits: np.ndarr
         return Graph.from_dsl(txt, data, dtype), {"error": "no plan candidate"}
     cands = candidates_of(plans)
 
-    def build(text):
-        return Graph.from_dsl(text, data, dtype).compile(**compile_kw)
+    def build(text, **kw):
+        return Graph.from_dsl(text, data, dtype).compile(**dict(compile_kw, **kw))
 
     def probe(g):
         for _ in range(2):
@@ -85,8 +85,7 @@ def tune(txt: str, data: Dict[str, np.ndarray], dtype: str, probe_bits: np.ndarr
         return (time.perf_counter() - t0) * 1e3 / 3.0, out
 
     best, report = autotune(cands, build, probe, None, rel_tol if rel_tol is not None else (1e-4 if dtype == "c32" else 1e-9))
-    tag, text, env = cands[best]
-    os.environ.update(env)
+    tag, text, kw = cands[best]
     g = Graph.from_dsl(text, data, dtype)
     g.replan_info = next(i for t, _, i in plans if tag.startswith(t + "/"))
-    return g, {"chosen": tag, "probe_bitstrings": int(probe_bits.shape[0]), "candidates": report}
+    return g, {"chosen": tag, "options": kw, "probe_bitstrings": int(probe_bits.shape[0]), "candidates": report}

@@ -8,16 +8,16 @@ from qxb200.executor import autotune
 
 
 class Fake:
-    def __init__(self, text):
+    def __init__(self, text, knob=None):
         self.text = text
-        self.env = os.environ.get("QXB_FAKE_KNOB")
+        self.env = knob
 
 
 def run(cands, times, results, reduce=None, raising=()):
-    def build(text):
+    def build(text, fake_knob=None):
         if text in raising:
             raise RuntimeError("boom " + text)
-        return Fake(text)
+        return Fake(text, fake_knob)
 
     def probe(g):
         key = (g.text, g.env)
@@ -25,17 +25,17 @@ def run(cands, times, results, reduce=None, raising=()):
     return autotune(cands, build, probe, reduce)
 
 
-def test_picks_fastest_exact_candidate_and_restores_env():
-    os.environ.pop("QXB_FAKE_KNOB", None)
+def test_picks_fastest_exact_candidate_and_leaves_no_state():
+    env_before = dict(os.environ)
     a = np.array([1 + 1j, 0.5])
-    cands = [("base", "A", {}), ("knob7", "A", {"QXB_FAKE_KNOB": "7"}), ("planB", "B", {}), ("wrong", "C", {}), ("bad", "D", {})]
+    cands = [("base", "A", {}), ("knob7", "A", {"fake_knob": "7"}), ("planB", "B", {}), ("wrong", "C", {}), ("bad", "D", {})]
     times = {("A", None): 10.0, ("A", "7"): 8.0, ("B", None): 9.0, ("C", None): 1.0}
     results = {("A", None): a, ("A", "7"): a * (1 + 1e-13), ("B", None): a, ("C", None): a * 1.001}
     best, rep = run(cands, times, results, raising={"D"})
     assert best == 1 and rep[1]["ms"] == 8.0
     assert rep[3]["ms"] is None and "differs" in rep[3]["note"]           # fast but wrong: discarded
     assert rep[4]["ms"] is None and "boom" in rep[4]["note"]              # raising candidate: discarded, run continues
-    assert "QXB_FAKE_KNOB" not in os.environ                              # knobs are restored after every candidate
+    assert dict(os.environ) == env_before                                  # knobs travel as compile options, not as environment
 
 
 def test_baseline_failure_falls_back_to_index_zero():

@@ -126,9 +126,8 @@ def test_execute_with_autotune(gpu, triple):
     a single amplitude beyond rounding (every candidate is an exact re-association run by the same kernels)."""
     from qxb200.execute import execute
     prefix, cmds, data, bitstrings = triple
-    try:
-        res = execute(prefix + ".qx", dtype="c64", autotune=True)
-    finally:
-        os.environ.pop("QXB_MIN_LOB", None)
+    env_before = dict(os.environ)
+    res = execute(prefix + ".qx", dtype="c64", autotune=True)
+    assert dict(os.environ) == env_before                  # the winning knobs travel as qxb_options, not as environment
     assert list(res.keys()) == bitstrings
     assert rel_err(np.array(list(res.values())), orc.amplitudes(cmds, data, bitstrings), 9) < 1e-10
