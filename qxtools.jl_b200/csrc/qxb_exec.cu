@@ -133,10 +133,10 @@ struct EventPair { cudaEvent_t a, b; int variant, op; };
 // A whole qxb_amplitudes step captured as a CUDA graph, keyed by everything the
 // launches depend on.  Replay removes ~550 launch gaps per step.
 struct StepKey {
-    const void* bits; void* out; int64_t n_amp, s0, s1; uint64_t mask, vals_hash; cudaStream_t st;
-    bool operator<(const StepKey& o) const {
-        return std::tie(bits, out, n_amp, s0, s1, mask, vals_hash, st) <
-               std::tie(o.bits, o.out, o.n_amp, o.s0, o.s1, o.mask, o.vals_hash, o.st);
+    const void* bits; void* out; int64_t n_amp, s0, s1; uint64_t mask; std::vector<int64_t> vals; cudaStream_t st;
+    bool operator<(const StepKey& o) const {       // the fixed VALUES themselves, not a hash of them: no collisions
+        return std::tie(bits, out, n_amp, s0, s1, mask, vals, st) <
+               std::tie(o.bits, o.out, o.n_amp, o.s0, o.s1, o.mask, o.vals, o.st);
     }
 };
 struct StepGraph { cudaGraphExec_t exec = nullptr; qxb_stats stats{}; };
@@ -1241,7 +1241,7 @@ void run_amplitudes(qxb_graph* g, const uint8_t* d_bits, int64_t n_amp, int64_t 
     const int64_t S = num_slices(g->prog);
     if (s0 < 0 || s1 > S || s0 > s1) throw Error(QXB_ERR_ARG, "slice range out of bounds");
     if (n_amp < 0) throw Error(QXB_ERR_ARG, "negative amplitude count");
-    StepKey key{d_bits, d_out, n_amp, s0, s1, 0, 0, nullptr};
+    StepKey key{d_bits, d_out, n_amp, s0, s1, 0, {}, nullptr};
     run_blocks(g, decompose(g->prog, s0, s1), key, d_bits, n_amp, d_out);
 }
 
@@ -1251,7 +1251,6 @@ void run_subspace(qxb_graph* g, const uint8_t* d_bits, int64_t n_amp, const int3
     if (n_amp < 0 || n_fixed < 0) throw Error(QXB_ERR_ARG, "negative count");
     const int k = (int)g->prog.vars.size();
     Block blk; blk.free_mask = low_mask(k); blk.vals.assign(k + 1, 0);
-    uint64_t vh = 1469598103934665603ull;
     for (int i = 0; i < n_fixed; ++i) {
         const int v = fvars[i];
         if (v < 0 || v >= k) throw Error(QXB_ERR_ARG, "fixed slice variable out of range");
@@ -1260,8 +1259,7 @@ void run_subspace(qxb_graph* g, const uint8_t* d_bits, int64_t n_amp, const int3
         blk.free_mask &= ~(1ull << v);
         blk.vals[v] = fvals[i];
     }
-    for (int v = 0; v < k; ++v) vh = (vh ^ (uint64_t)blk.vals[v]) * 1099511628211ull;
-    StepKey key{d_bits, d_out, n_amp, -1, -1, blk.free_mask, vh, nullptr};
+    StepKey key{d_bits, d_out, n_amp, -1, -1, blk.free_mask, blk.vals, nullptr};
     std::vector<Block> blocks; blocks.push_back(std::move(blk));
     run_blocks(g, std::move(blocks), key, d_bits, n_amp, d_out);
 }

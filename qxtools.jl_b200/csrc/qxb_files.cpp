@@ -503,6 +503,8 @@ int qxb_execute_files_multi(const char* dsl_file, const char* input_file, const 
             if (n_out != (int)pr.p.num_qubits)
                 throw Error(QXB_ERR_ARG, "the program has " + std::to_string(n_out) + " outputs but the parameter file says num_qubits = " +
                                          std::to_string(pr.p.num_qubits));
+            if (!(pr.p.M > 0.0))
+                throw Error(QXB_ERR_ARG, "rejection sampling needs M > 0 in the parameter file (the acceptance probability is p 2^n / M)");
             int64_t want = pr.p.num_samples;
             if (max_amplitudes >= 0 && want > max_amplitudes) want = max_amplitudes;
             uint64_t rs = pr.p.has_seed ? (uint64_t)pr.p.seed : 0x5851f42d4c957f2dull;

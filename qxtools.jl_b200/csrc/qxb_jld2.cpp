@@ -103,6 +103,13 @@ struct Reader {
         if (lookup3(&buf[begin], end - begin) != (uint32_t)rd(end, 4)) ++f.checksum_failures;
     }
 
+    // offset / length sizes steer every later read (rd shifts by 8 * size): only 2, 4 and 8 bytes exist
+    void check_sizes(uint64_t sb) {
+        if ((so != 2 && so != 4 && so != 8) || (sl != 2 && sl != 4 && sl != 8))
+            bad(f.path, sb, "superblock: size of offsets " + std::to_string(so) + " / size of lengths " + std::to_string(sl) +
+                            " (must be 2, 4 or 8)");
+    }
+
     // ---------------------------------------------------------- superblock
     uint64_t superblock() {
         uint64_t sb = kUndef;
@@ -114,6 +121,7 @@ struct Reader {
         f.superblock_version = ver;
         if (ver == 0 || ver == 1) {
             so = (int)rd(sb + 13, 1); sl = (int)rd(sb + 14, 1);
+            check_sizes(sb);
             uint64_t p = sb + 24 + (ver == 1 ? 4 : 0);
             f.base_address = ra(p);
             p += 4 * so;                                  // base, free-space, eof, driver-info
@@ -121,6 +129,7 @@ struct Reader {
         }
         if (ver == 2 || ver == 3) {
             so = (int)rd(sb + 9, 1); sl = (int)rd(sb + 10, 1);
+            check_sizes(sb);
             f.base_address = ra(sb + 12);
             uint64_t root = ra(sb + 12 + 3 * so);
             check_sum(sb, sb + 12 + 4 * so);
@@ -232,9 +241,11 @@ struct Reader {
         return t;
     }
 
-    DType resolve_datatype(const Msg& m, bool& committed) {
+    DType resolve_datatype(const Msg& m, bool& committed, int depth = 0) {
         committed = false;
         if (!(m.flags & 0x02)) return datatype(m.off, m.off + m.size);
+        // a committed datatype whose object header holds another shared datatype message may point back at itself
+        if (depth > 8) bad(f.path, m.off, "committed datatype references nest deeper than 8 levels (cycle?)");
         int ver = (int)rd(m.off, 1), typ = (int)rd(m.off + 1, 1);
         uint64_t a;
         if (ver == 1) a = ra(m.off + 8);
@@ -242,7 +253,7 @@ struct Reader {
         else unsupp(f.path, "datatype stored in the shared-message heap");
         committed = true;
         for (const Msg& c : messages(abs_addr(a)))
-            if (c.type == 0x03) { bool dummy; return resolve_datatype(c, dummy); }
+            if (c.type == 0x03) { bool dummy; return resolve_datatype(c, dummy, depth + 1); }
         bad(f.path, abs_addr(a), "committed datatype object holds no datatype message");
     }
 

@@ -36,6 +36,8 @@ def rejection_sample(amplitudes: AmplitudeFn, num_qubits: int, num_samples: int,
                      fix_M: bool = False, seed: Optional[int] = None, batch: int = 1024,
                      max_batches: int = 10_000) -> Tuple[List[str], List[complex], dict]:
     """-> (accepted bitstrings, their amplitudes, info).  ``M`` follows outputs.jl:57-62."""
+    if not float(M) > 0.0:
+        raise ValueError(f"rejection sampling needs M > 0 (got {M}): the acceptance probability is p 2^n / M")
     rng = np.random.default_rng(seed)
     N = 2.0 ** num_qubits
     out_b: List[str] = []
