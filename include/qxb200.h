@@ -71,6 +71,9 @@ typedef struct qxb_options {
     int32_t row_ctas_per_sm;   /* row programs: resident CTAs per SM; 0 = as many as the arena allows, at most 2  */
     int32_t ring;              /* 0 = auto: nodes whose operand and result rows are small dense per-bitstring rows run on
                                   the TMA ring kernel (bulk copies in, bulk store out, csrc/qxb_rowprog.h); 1 = never  */
+    int32_t chain;             /* 0 = auto: the chain of dominant contractions (each one the only consumer of the previous
+                                  result, small rows) runs as ONE row-program launch, its intermediates never reach HBM;
+                                  1 = never                                                                          */
     int32_t row_chunk_max_amps;/* auto mode: largest call (bitstrings) whose chunk phase runs as a row program; 0 = 512 */
 } qxb_options;
 

@@ -124,6 +124,12 @@ struct Variant {
     std::map<std::vector<int64_t>, RowDev> rowdev;
     OpProfile prof_rows, prof_block_rows;                // profile mode: the two fused launches
     DevBuf row_timing;                                   // profile mode: per-level clock cycles of CTA 0 (chunk program)
+    // fused chain (qxb_rowplan.h select_chain): the dominant contractions as ONE row-program launch
+    std::vector<int> chain;                              // op indices (contiguous after make_contiguous); empty: none
+    RowProgramHost rp_chain;
+    struct ChainDev { DevBuf descs, slots; std::vector<int> level_start; };
+    std::vector<std::unique_ptr<ChainDev>> chain_dev;    // one per built step (pointers depend on the batch)
+    OpProfile prof_chain;
     struct RingDescs { DevBuf buf; int n_units = 0; bool tried = false; };
     std::map<int, RingDescs> ring;                       // per op: unit descriptors of the TMA ring kernel
 };
@@ -161,6 +167,10 @@ struct qxb_graph {
     void drop_step_graphs() {
         for (auto& kv : step_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         step_graphs.clear();
+        for (auto& kv : variants) {                      // the chain tables those graphs pointed at
+            for (auto& cd : kv.second->chain_dev) { cd->descs.release(); cd->slots.release(); }
+            kv.second->chain_dev.clear();
+        }
     }
     size_t es() const { return dtype == QXB_C32 ? 8 : 16; }
     ~qxb_graph() {
@@ -168,6 +178,7 @@ struct qxb_graph {
         for (auto& kv : variants) {
             kv.second->const_arena.release(); kv.second->outleaf_desc.release(); kv.second->row_timing.release();
             for (auto& r : kv.second->ring) r.second.buf.release();
+            for (auto& cd : kv.second->chain_dev) { cd->descs.release(); cd->slots.release(); }
             for (auto& rd : kv.second->rowdev) {
                 rd.second.descs_block.release(); rd.second.slots_block.release(); rd.second.descs_chunk.release();
                 rd.second.slots_chunk.release(); rd.second.leaves.release();
@@ -790,9 +801,26 @@ Variant* get_variant(qxb_graph* g, uint64_t free_mask) {
     if (it != g->variants.end()) return it->second.get();
     std::unique_ptr<Variant> v(new Variant());
     v->L = lower(g->prog, free_mask, !g->opts.sum_at_root);
+    // fused chain: pick it and make its ops contiguous BEFORE the memory plan (its intermediates never reach HBM; the
+    // arena plan and the dependency edges must see the chain as one step)
+    RowPlanOptions co;
+    const bool chain_on = knob(0, "QXB_CHAIN", 1) != 0 && g->opts.row_programs != 1 && g->opts.chain != 1;
+    if (chain_on) {
+        co.min_tt_bits = knob(0, "QXB_CHAIN_MIN_TT", 8);
+        co.tile_reg_budget = knob(g->opts.row_tile_regs, "QXB_ROW_TILE_REGS", 100);
+        // two CTAs per SM: (228 KB / 2 - 1 KB reserved) minus descriptor buffers and slot table
+        co.max_arena_bytes = knob(0, "QXB_CHAIN_ARENA_KB", 0) ? 1024ll * knob(0, "QXB_CHAIN_ARENA_KB", 0)
+                                                              : (233472 / 2 - 1024) - (long long)row_fixed_smem_bytes(512);
+        v->chain = select_chain(v->L, g->dtype, co);
+        if (!v->chain.empty()) v->chain = make_contiguous(v->L, v->chain);
+    }
     plan_memory(v->L);
     build_templates(*v, g->dtype, g->opts);
     build_row_programs(g, *v);
+    if (!v->chain.empty()) {
+        v->rp_chain = build_row_program(v->L, PH_CHUNK, g->dtype, co, &v->chain);
+        if (!v->rp_chain.ok) v->chain.clear();
+    }
     const size_t es = g->es();
     v->const_arena.reserve(std::max<int64_t>(v->L.const_elems, 2) * es);
     std::vector<OutLeafDesc> descs;
@@ -981,6 +1009,64 @@ Node row_node(const RunCtx& c, Variant::RowDev& rd, bool chunk, const uint8_t* d
     return n;
 }
 
+constexpr int kOpRowChain = -4;
+
+// The fused chain of this variant for the rows of the current pass (c.n rows; chunk-arena pointers depend on it).
+Node chain_node(const RunCtx& c) {
+    qxb_graph* g = c.g;
+    Variant& v = *c.v;
+    const RowProgramHost& rp = v.rp_chain;
+    std::vector<RowOp> ops = rp.ops;
+    auto fixed_off = [&](const LTensor& T) {
+        long long off = 0;
+        for (auto& f : T.fixed) off += (long long)c.fixed_vals[f.first] << f.second;
+        return off;
+    };
+    for (size_t j = 0; j < ops.size(); ++j) {
+        RowOp& d = ops[j];
+        if (rp.lop[j] < 0) {                              // staged input: whole tensor from its base (row 0 of this pass)
+            const LTensor& A = v.L.tensors[rp.ref_a[j]];
+            d.gA = (unsigned long long)(tensor_ptr(c, A) - fixed_off(A) * (long long)g->es());
+            continue;
+        }
+        const LTensor &A = v.L.tensors[rp.ref_a[j]], &B = v.L.tensors[rp.ref_b[j]], &C = v.L.tensors[rp.ref_c[j]];
+        d.oA += (int)fixed_off(A); d.oB += (int)fixed_off(B);          // every chain operand is staged in the arena
+        if (!rp.in_arena_c[j]) { d.gC = (unsigned long long)tensor_ptr(c, C); d.oC = 0; }
+    }
+    RowDeviceTables t = build_row_tables(rp, ops);
+    v.chain_dev.emplace_back(new Variant::ChainDev());
+    Variant::ChainDev& cd = *v.chain_dev.back();
+    cd.level_start = t.level_start;
+    cd.descs.reserve(std::max<size_t>(t.descs.size(), 1) * sizeof(RowUnitDesc));
+    cd.slots.reserve(std::max<size_t>(t.slots.size(), 1) * sizeof(uint16_t));
+    CUDA_OK(cudaMemcpy(cd.descs.p, t.descs.data(), t.descs.size() * sizeof(RowUnitDesc), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(cd.slots.p, t.slots.data(), t.slots.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    RowLaunch P;
+    memset(&P, 0, sizeof(P));
+    P.descs = (const RowUnitDesc*)cd.descs.p;
+    P.slots = (const uint16_t*)cd.slots.p;
+    P.amp0 = 0; P.n_rows = c.n; P.scale = 1.0;
+    P.n_levels = rp.n_levels;
+    for (int i = 0; i <= rp.n_levels; ++i) P.level_start[i] = cd.level_start[i];
+    const size_t n_slots = (size_t)cd.level_start[rp.n_levels];
+    P.slots_bytes = (int)row_slots_bytes(n_slots);
+    Node n;
+    n.func = rowprog_func(g->dtype); n.kname = "chain";
+    n.block = dim3(kRowThreads);
+    n.smem = row_fixed_smem_bytes(n_slots) + (size_t)rp.arena_elems * g->es();
+    if (first_use(n.func))
+        CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int per_sm = 1;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, n.func, kRowThreads, n.smem));
+    per_sm = std::max(1, std::min(per_sm, knob(g->opts.row_ctas_per_sm, "QXB_ROW_CTAS", 2)));
+    n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(c.n, (long long)g_num_sms * per_sm)));
+    n.arg(P);
+    n.variant = c.variant_key; n.op = kOpRowChain;
+    n.flops = rp.flops_per_row * (double)c.n;
+    n.bytes = (double)g->es() * (rp.elems_per_row_amp * (double)c.n + rp.elems_shared);    // algorithmic, as contract_node counts it
+    return n;
+}
+
 std::vector<Node> build_step(qxb_graph* g, const StepPlan& sp, const uint8_t* d_bits, int64_t n_amp, void* d_out) {
     std::vector<Node> nodes;
     {
@@ -1043,8 +1129,28 @@ std::vector<Node> build_step(qxb_graph* g, const StepPlan& sp, const uint8_t* d_
                 nodes.push_back(std::move(n));
             }
             std::vector<int> cnode(L.ops.size(), -1);
+            std::vector<char> in_chain(L.ops.size(), 0);
+            const bool use_chain = !v->chain.empty() && c.n >= (long long)knob(0, "QXB_CHAIN_MIN_AMPS", 2 * g_num_sms);
+            if (use_chain) for (int ci : v->chain) in_chain[ci] = 1;
             for (size_t i = 0; i < L.ops.size(); ++i) {
                 if (L.ops[i].phase != PH_CHUNK) continue;
+                if (in_chain[i]) {
+                    if ((int)i != v->chain.front()) continue;
+                    // the whole chain as one launch, at the position of its (contiguous) ops
+                    Node n = chain_node(c);
+                    for (int ci : v->chain) {
+                        for (int d : L.ops[ci].deps) {
+                            if (in_chain[d]) continue;
+                            const int nd = L.ops[d].phase == PH_CHUNK ? cnode[d] : node_of[d];
+                            if (nd >= 0) n.deps.push_back(nd);
+                        }
+                        if (L.tensors[L.ops[ci].a].is_output_leaf || L.tensors[L.ops[ci].b].is_output_leaf) n.deps.push_back(start);
+                    }
+                    if (n.deps.empty()) n.deps.push_back(start);
+                    for (int ci : v->chain) cnode[ci] = (int)nodes.size();
+                    nodes.push_back(std::move(n));
+                    continue;
+                }
                 Node n = contract_node(c, (int)i);
                 for (int d : L.ops[i].deps) {
                     const int nd = L.ops[d].phase == PH_CHUNK ? cnode[d] : node_of[d];
@@ -1105,7 +1211,7 @@ std::vector<Node> build_step(qxb_graph* g, const StepPlan& sp, const uint8_t* d_
 void account(qxb_graph* g, const std::vector<Node>& nodes) {
     for (const Node& n : nodes) {
         if (n.func) g->stats.kernel_launches++;
-        if (n.op >= 0 || n.op == kOpRowChunk || n.op == kOpRowBlock) {
+        if (n.op >= 0 || n.op == kOpRowChunk || n.op == kOpRowBlock || n.op == kOpRowChain) {
             g->stats.contract_launches++; g->stats.flops += n.flops; g->stats.bytes += n.bytes;
         }
     }
@@ -1133,12 +1239,13 @@ void launch_serial(qxb_graph* g, const std::vector<Node>& nodes) {
         if (n.op >= 0 && !ncu_ops().empty())
             for (auto& kv : g->variants)
                 if (kv.second->key == n.variant && ncu_ops().count(kv.second->L.ops[n.op].name)) bracket = true;
-        if ((n.op == kOpRowChunk && ncu_ops().count("ROWPROG_CHUNK")) || (n.op == kOpRowBlock && ncu_ops().count("ROWPROG_BLOCK")))
+        if ((n.op == kOpRowChunk && ncu_ops().count("ROWPROG_CHUNK")) || (n.op == kOpRowBlock && ncu_ops().count("ROWPROG_BLOCK")) ||
+            (n.op == kOpRowChain && ncu_ops().count("ROWPROG_CHAIN")))
             bracket = true;
         if (bracket) { CUDA_OK(cudaStreamSynchronize(st)); cudaProfilerStart(); }
         struct Stop { bool on; cudaStream_t s; ~Stop() { if (on) { cudaStreamSynchronize(s); cudaProfilerStop(); } } } stop{bracket, st};
         EventPair* ev = nullptr;
-        const bool fused = n.op == kOpRowChunk || n.op == kOpRowBlock;
+        const bool fused = n.op == kOpRowChunk || n.op == kOpRowBlock || n.op == kOpRowChain;
         if (g->opts.profile && (n.op >= 0 || fused)) {
             if (g->events_used == g->events.size()) {
                 EventPair e{};
@@ -1155,7 +1262,7 @@ void launch_serial(qxb_graph* g, const std::vector<Node>& nodes) {
             for (auto& kv : g->variants)
                 if (kv.second->key == n.variant) {
                     OpProfile& pr = n.op == kOpRowChunk ? kv.second->prof_rows : n.op == kOpRowBlock ? kv.second->prof_block_rows
-                                                                                                     : kv.second->prof[n.op];
+                                  : n.op == kOpRowChain ? kv.second->prof_chain : kv.second->prof[n.op];
                     pr.flops += n.flops; pr.bytes += n.bytes; pr.launches++; pr.kernel = n.kname;
                 }
         }
@@ -1210,7 +1317,7 @@ void run_blocks(qxb_graph* g, std::vector<Block> blocks, StepKey key, const uint
     g->events_used = 0;
     for (auto& kv : g->variants) {
         kv.second->prof.assign(kv.second->L.ops.size(), OpProfile{});
-        kv.second->prof_rows = OpProfile{}; kv.second->prof_block_rows = OpProfile{};
+        kv.second->prof_rows = OpProfile{}; kv.second->prof_block_rows = OpProfile{}; kv.second->prof_chain = OpProfile{};
     }
     if (n_amp == 0) return;
     cudaStream_t st = stream();
@@ -1222,6 +1329,18 @@ void run_blocks(qxb_graph* g, std::vector<Block> blocks, StepKey key, const uint
             g->stats = it->second.stats;
             CUDA_OK(cudaGraphLaunch(it->second.exec, st));
             return;
+        }
+    }
+    if (!use_graph) {
+        // serial-launch modes rebuild the step on every call: the chain tables of the previous call are dead once it is done
+        bool any = false;
+        for (auto& kv : g->variants) any |= !kv.second->chain_dev.empty();
+        if (any) {
+            CUDA_OK(cudaStreamSynchronize(st));
+            for (auto& kv : g->variants) {
+                for (auto& cd : kv.second->chain_dev) { cd->descs.release(); cd->slots.release(); }
+                kv.second->chain_dev.clear();
+            }
         }
     }
     StepPlan sp = prepare_step(g, std::move(blocks), n_amp);
@@ -1272,6 +1391,7 @@ void collect_profile(qxb_graph* g) {
             for (auto& kv : g->variants) {
                 if (kv.second->key != e.variant) continue;
                 if (e.op == kOpRowChunk) kv.second->prof_rows.ms += ms;
+                else if (e.op == kOpRowChain) kv.second->prof_chain.ms += ms;
                 else if (e.op == kOpRowBlock) kv.second->prof_block_rows.ms += ms;
                 else if (e.op >= 0 && e.op < (int)kv.second->prof.size()) kv.second->prof[e.op].ms += ms;
             }
@@ -1730,6 +1850,23 @@ int qxb_profile_dump(qxb_graph* g, const char* path) {
                         (long long)rp.arena_elems * (long long)g->es(), lc.c_str(), fp[q]->launches, fp[q]->flops, fp[q]->bytes, fp[q]->ms);
                 first = false;
             }
+            if (v.prof_chain.launches) {
+                const RowProgramHost& rp = v.rp_chain;
+                std::string names;
+                for (int ci : v.chain) names += (names.empty() ? "\"" : ",\"") + v.L.ops[ci].name + "\"";
+                // DRAM bytes the fused launch has to move per bitstring: its staged inputs and its results
+                double io = 0;
+                for (size_t j = 0; j < rp.ops.size(); ++j) {
+                    if (rp.lop[j] < 0) { if (v.L.tensors[rp.ref_a[j]].amp) io += std::ldexp(1.0, v.L.tensors[rp.ref_a[j]].span_bits); }
+                    else if (!rp.in_arena_c[j]) io += std::ldexp(1.0, v.L.tensors[rp.ref_c[j]].span_bits);
+                }
+                fprintf(f, "%s{\"name\":\"ROWPROG_CHAIN\",\"phase\":2,\"kernel\":\"chain\",\"fused_ops\":%d,\"fused\":[%s],\"levels\":%d,"
+                           "\"units\":%d,\"arena_bytes\":%lld,\"io_bytes_per_row\":%.0f,\"launches\":%lld,\"flops\":%.6g,\"bytes\":%.6g,\"ms\":%.6g}",
+                        first ? "" : ",", (int)v.chain.size(), names.c_str(), rp.n_levels, (int)rp.units.size(),
+                        (long long)rp.arena_elems * (long long)g->es(), io * (double)g->es(), v.prof_chain.launches,
+                        v.prof_chain.flops, v.prof_chain.bytes, v.prof_chain.ms);
+                first = false;
+            }
             fprintf(f, "]}");
         }
         fprintf(f, "]}\n");
@@ -1905,9 +2042,18 @@ int64_t qxb_debug_rowprog(qxb_graph* g, uint64_t free_mask, int phase, void* buf
     int64_t need = 0;
     int rc = guard([&] {
         if (!g) throw Error(QXB_ERR_ARG, "null graph");
-        if (phase != PH_BLOCK && phase != PH_CHUNK) throw Error(QXB_ERR_ARG, "phase must be 1 (block) or 2 (chunk)");
+        if (phase != PH_BLOCK && phase != PH_CHUNK && phase != 3)
+            throw Error(QXB_ERR_ARG, "phase must be 1 (block), 2 (chunk) or 3 (the fused chain of the chunk phase)");
         ensure_analysed(g);
         Lowered L = lower(g->prog, free_mask, !g->opts.sum_at_root);
+        std::vector<int> chain;
+        RowPlanOptions co;
+        if (phase == 3) {
+            co.min_tt_bits = knob(0, "QXB_CHAIN_MIN_TT", 8);
+            co.max_arena_bytes = (233472 / 2 - 1024) - (long long)row_fixed_smem_bytes(512);
+            chain = select_chain(L, g->dtype, co);
+            if (!chain.empty()) chain = make_contiguous(L, chain);
+        }
         plan_memory(L);
         RowPlanOptions o;
         o.min_tt_bits = knob(g->opts.row_min_tt_bits, "QXB_ROW_MIN_TT", 6);
@@ -1916,7 +2062,13 @@ int64_t qxb_debug_rowprog(qxb_graph* g, uint64_t free_mask, int phase, void* buf
         o.max_tile_bits = knob(0, "QXB_ROW_MAX_TILE", 4);
         o.stage_shared = knob(0, "QXB_ROW_STAGE", 1) != 0;
         o.max_arena_bytes = 227 * 1024 - (long long)row_fixed_smem_bytes(2048 + kRowWarps * kRowMaxLevels);
-        RowProgramHost rp = build_row_program(L, (Phase)phase, g->dtype, o);
+        RowProgramHost rp;
+        if (phase == 3) {
+            if (chain.empty()) { rp.ok = false; rp.why = "no chain worth fusing"; }
+            else rp = build_row_program(L, PH_CHUNK, g->dtype, co, &chain);
+        } else {
+            rp = build_row_program(L, (Phase)phase, g->dtype, o);
+        }
         if (!rp.ok) { set_last_error(rp.why); }
         std::vector<char> out;
         auto put = [&](const void* p, size_t n) { const char* c = (const char*)p; out.insert(out.end(), c, c + n); };
@@ -1948,6 +2100,11 @@ int64_t qxb_debug_rowprog(qxb_graph* g, uint64_t free_mask, int phase, void* buf
             put(rp.leaves.data(), rp.leaves.size() * sizeof(RowLeaf));
             puti(rp.lop); puti(rp.ref_a); puti(rp.ref_b); puti(rp.ref_c);
             putc(rp.in_arena_a); putc(rp.in_arena_b); putc(rp.in_arena_c);
+            if (phase == 3) {                                // names of the fused ops, '\n'-separated, after the fixed layout
+                std::string names;
+                for (int ci : chain) names += L.ops[ci].name + "\n";
+                put(names.data(), names.size());
+            }
         }
         need = (int64_t)out.size();
         if (buf && buflen >= need) memcpy(buf, out.data(), out.size());

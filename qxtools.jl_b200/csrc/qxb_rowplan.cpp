@@ -58,6 +58,7 @@ bool describe_row_op(const LOp& op, int dtype, const RowPlanOptions& o, RowOp& d
                      std::string& why) {
     auto bad = [&](const std::string& w) { why = w; return false; };
     memset(&d, 0, sizeof(d));
+    d.lsA = d.lsB = d.lsC = kRowShared;
     const int nC = op.nC, nK = op.nK;
     if (nC > 16 || nK > 16) return bad("op too large for a row program");
     std::vector<int> mapA(nC, -1), mapB(nC, -1);
@@ -145,14 +146,21 @@ bool describe_row_op(const LOp& op, int dtype, const RowPlanOptions& o, RowOp& d
     return true;
 }
 
-RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const RowPlanOptions& o) {
+RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const RowPlanOptions& o,
+                                 const std::vector<int>* subset) {
     RowProgramHost rp;
     rp.phase = phase;
     rp.elem_bytes = dtype == QXB_C32 ? 8 : 16;
     auto fail = [&](const std::string& why) { rp.ok = false; rp.why = why; return rp; };
     // ---- ops of the phase, producers, levels
     std::vector<int> sel;                                   // indices into L.ops
-    for (size_t i = 0; i < L.ops.size(); ++i) if (L.ops[i].phase == phase) sel.push_back((int)i);
+    if (subset) {
+        if (phase != PH_CHUNK) return fail("a fused chain lives in the chunk phase");
+        sel = *subset;
+        for (int i : sel) if (i < 0 || i >= (int)L.ops.size() || L.ops[i].phase != PH_CHUNK) return fail("bad chain op");
+    } else {
+        for (size_t i = 0; i < L.ops.size(); ++i) if (L.ops[i].phase == phase) sel.push_back((int)i);
+    }
     if (sel.empty()) return fail("no op in this phase");
     if (sel.size() > 60000) return fail("too many ops");
     std::map<int, int> local_of_lop;                        // L.ops index -> local index
@@ -198,7 +206,10 @@ RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const
         for (int j = 0; j < n; ++j)
             for (int t : {L.ops[sel[j]].a, L.ops[sel[j]].b}) {
                 const LTensor& T = L.tensors[t];
-                if (producer.count(t) || T.is_output_leaf || T.span_bits > o.stage_max_bits) continue;
+                if (producer.count(t)) continue;
+                if (subset) {
+                    if (T.span_bits > o.stage_max_bits) return fail("chain input larger than the staging limit");
+                } else if (T.is_output_leaf || T.span_bits > o.stage_max_bits) continue;
                 auto it = use.find(t);
                 if (it == use.end()) use[t] = {level[j], level[j]};
                 else { it->second.first = std::min(it->second.first, level[j]); it->second.second = std::max(it->second.second, level[j]); }
@@ -222,7 +233,7 @@ RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const
             return lv;
         };
         std::vector<Interval> live;
-        for (int t : L.output_leaves) {
+        for (int t : subset ? std::vector<int>() : L.output_leaves) {
             const LTensor& T = L.tensors[t];
             if (T.span_bits > 16) return fail("output leaf too large");
             const int lu = last_level(t);
@@ -248,15 +259,25 @@ RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const
                 if (op.nC > 16) return fail("intermediate larger than 2^16 elements");
                 const int t = op.c;
                 int until = last_level(t);
+                if (subset) {
+                    // a chain result read outside the chain (or the root) goes straight to global memory
+                    bool outside = t == L.root;
+                    for (size_t q = 0; q < L.ops.size(); ++q)
+                        if ((L.ops[q].a == t || L.ops[q].b == t) && !local_of_lop.count((int)q)) outside = true;
+                    if (outside && until >= 0) return fail("a chain tensor is read both inside and outside the chain");
+                    if (outside || until < 0) continue;           // not in the arena: in_arena_c = 0 -> global
+                }
                 if (t == L.root || until < 0) until = n_levels;       // the root (and anything unread) lives to the end
                 arena_off[t] = arena_alloc(live, 1 << op.nC, until);
                 peak = std::max(peak, arena_off[t] + (1 << op.nC));
             }
         }
         rp.arena_elems = peak;
-        if (!arena_off.count(L.root)) return fail("the root is not produced in the chunk phase");
-        rp.root_off = arena_off[L.root];
-        rp.root_span = L.tensors[L.root].span_bits;
+        if (!subset) {
+            if (!arena_off.count(L.root)) return fail("the root is not produced in the chunk phase");
+            rp.root_off = arena_off[L.root];
+            rp.root_span = L.tensors[L.root].span_bits;
+        }
         const size_t es = dtype == QXB_C32 ? 8 : 16;
         if ((size_t)peak * es > (size_t)o.max_arena_bytes) return fail("row arena of " + std::to_string((size_t)peak * es) + " bytes exceeds the budget");
     }
@@ -280,6 +301,11 @@ RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const
             else { off = 0; in_arena = 0; }
         };
         place(op.a, d.oA, rp.in_arena_a[j]); place(op.b, d.oB, rp.in_arena_b[j]); place(op.c, d.oC, rp.in_arena_c[j]);
+        if (subset) {                                        // tensors left in global memory: per-row ones carry their stride
+            if (!rp.in_arena_a[j]) return fail("chain operand not staged");
+            if (!rp.in_arena_b[j]) return fail("chain operand not staged");
+            if (!rp.in_arena_c[j] && L.tensors[op.c].amp) d.lsC = (uint8_t)L.tensors[op.c].span_bits;
+        }
         h.gen = (uint8_t)(!(rp.in_arena_a[j] && rp.in_arena_b[j] && rp.in_arena_c[j]));
         const LTensor &TA = L.tensors[op.a], &TB = L.tensors[op.b];
         rp.flops_per_row += 8.0 * op.macs_per_amp;
@@ -293,6 +319,8 @@ RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const
         memset(&d, 0, sizeof(d));
         const int span = L.tensors[st.tensor].span_bits;
         d.hot.kind = kRowKindCopy;
+        d.lsA = d.lsB = d.lsC = kRowShared;
+        if (subset && L.tensors[st.tensor].amp) d.lsA = (uint8_t)span;     // a per-row tensor another kernel produced
         d.hot.ntt = (uint8_t)std::min(span, 8);              // log2 elements per unit
         d.hot.gen = 1;
         d.oC = st.off;
@@ -323,6 +351,89 @@ RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const
 }
 
 
+std::vector<int> select_chain(const Lowered& L, int dtype, const RowPlanOptions& o) {
+    const int n = (int)L.ops.size();
+    // the only consumer of every op's result (-1: none / several / the root)
+    std::vector<int> next(n, -1), uses(L.tensors.size(), 0);
+    for (int i = 0; i < n; ++i) { ++uses[L.ops[i].a]; ++uses[L.ops[i].b]; }
+    std::vector<int> producer(L.tensors.size(), -1);
+    for (int i = 0; i < n; ++i) producer[L.ops[i].c] = i;
+    for (int i = 0; i < n; ++i) {
+        const LOp& op = L.ops[i];
+        if (op.phase != PH_CHUNK) continue;
+        for (int t : {op.a, op.b}) {
+            const int p = producer[t];
+            if (p >= 0 && L.ops[p].phase == PH_CHUNK && uses[t] == 1 && t != L.root) next[p] = i;
+        }
+    }
+    auto small = [&](int i) {
+        const LOp& op = L.ops[i];
+        return op.phase == PH_CHUNK && L.tensors[op.c].amp && op.nC <= o.stage_max_bits && op.nK <= 8 &&
+               L.tensors[op.a].span_bits <= o.stage_max_bits && L.tensors[op.b].span_bits <= o.stage_max_bits;
+    };
+    std::vector<char> has_pred(n, 0);
+    for (int i = 0; i < n; ++i) if (next[i] >= 0 && small(i) && small(next[i])) has_pred[next[i]] = 1;
+    std::vector<int> best;
+    double best_flops = 0;
+    for (int i = 0; i < n; ++i) {
+        if (!small(i) || has_pred[i]) continue;
+        std::vector<int> path;
+        double fl = 0;
+        for (int j = i; j >= 0 && small(j); j = next[j]) { path.push_back(j); fl += L.ops[j].macs_per_amp; }
+        if (path.size() >= 2 && fl > best_flops) { best = path; best_flops = fl; }
+    }
+    if (best.empty()) return best;
+    // tiny nodes at either end cost a fused row a full dependency level each (~1300 cycles of latency with two rows in
+    // flight per SM) but next to nothing as kernels of their own: keep the chain to the nodes that carry the work
+    while (best.size() >= 2 && L.ops[best.front()].macs_per_amp < o.chain_min_macs) best.erase(best.begin());
+    while (best.size() >= 2 && L.ops[best.back()].macs_per_amp < o.chain_min_macs) best.pop_back();
+    if (best.size() < 2) { best.clear(); return best; }
+    // trim the cheap ends until the chain's program fits two CTAs per SM (or give up at two ops)
+    auto fits = [&](const std::vector<int>& c) {
+        RowPlanOptions oo = o;
+        RowProgramHost rp = build_row_program(L, PH_CHUNK, dtype, oo, &c);
+        return rp.ok;
+    };
+    while (best.size() >= 2 && !fits(best)) {
+        if (L.ops[best.front()].macs_per_amp <= L.ops[best.back()].macs_per_amp) best.erase(best.begin());
+        else best.pop_back();
+    }
+    if (best.size() < 2) best.clear();
+    return best;
+}
+
+std::vector<int> make_contiguous(Lowered& L, const std::vector<int>& chain) {
+    const int n = (int)L.ops.size();
+    if (chain.size() < 2) return chain;
+    std::vector<char> in_chain(n, 0);
+    for (int i : chain) in_chain[i] = 1;
+    const int last = chain.back();
+    std::vector<int> order;                      // new position -> old index
+    for (int i = 0; i < n; ++i) {
+        if (in_chain[i] && i != last) continue;
+        if (i == last) { for (int c : chain) order.push_back(c); continue; }
+        order.push_back(i);
+    }
+    std::vector<int> new_of(n, -1);
+    for (int p = 0; p < n; ++p) new_of[order[p]] = p;
+    std::vector<LOp> ops(n);
+    for (int p = 0; p < n; ++p) {
+        ops[p] = L.ops[order[p]];
+        for (int& d : ops[p].deps) d = new_of[d];
+    }
+    L.ops.swap(ops);
+    for (LTensor& T : L.tensors) { T.first_use = -1; if (T.last_use != -1 || true) T.last_use = -1; }
+    for (int p = 0; p < n; ++p)
+        for (int t : {L.ops[p].a, L.ops[p].b}) {
+            LTensor& T = L.tensors[t];
+            if (T.first_use < 0) T.first_use = p;
+            T.last_use = p;
+        }
+    std::vector<int> out;
+    for (int c : chain) out.push_back(new_of[c]);
+    return out;
+}
+
 static int eval_segs(const RSeg* s, int n, unsigned x) {
     int r = 0;
     for (int i = 0; i < n; ++i) r |= (int)(((x >> s[i].src) & ((1u << s[i].len) - 1u)) << s[i].dst);
@@ -342,6 +453,7 @@ RowDeviceTables build_row_tables(const RowProgramHost& rp, const std::vector<Row
             d.gA = op.gA; d.gB = op.gB; d.gC = op.gC;
             memcpy(d.kA, op.kA, sizeof(d.kA)); memcpy(d.kB, op.kB, sizeof(d.kB));
             d.nkA = op.nkA; d.nkB = op.nkB;
+            d.lsA = op.lsA; d.lsB = op.lsB; d.lsC = op.lsC;
             const int ntt = op.hot.ntt;
             if (op.hot.kind == kRowKindCopy) {
                 // gA = first source element of this unit (set by the caller per op; advanced here per chunk), lC[0..1] =

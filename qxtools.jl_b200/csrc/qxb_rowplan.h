@@ -15,6 +15,7 @@ struct RowPlanOptions {
     bool alap = true;             // schedule every op as late as its consumers allow
     bool stage_shared = true;     // copy operands shared by all rows into the arena one level before their first use
     int stage_max_bits = 12;      // ... when they span at most 2^n elements
+    double chain_min_macs = 2048; // fused chain: complex MACs per row below which an end node is not worth a level
     long long max_arena_bytes = 200 * 1024;
 };
 
@@ -38,7 +39,20 @@ struct RowProgramHost {
     double elems_shared = 0;      // algorithmic elements of operands shared by all rows
 };
 
-RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const RowPlanOptions& o);
+// subset != nullptr (chunk phase only): a program for just these ops (indices into L.ops, ascending) -- a FUSED CHAIN.
+// Per-row tensors produced outside the subset are staged from global memory (row stride 2^span_bits), results that are
+// consumed outside go to global memory; no output leaves, no root reduction.
+RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const RowPlanOptions& o,
+                                 const std::vector<int>* subset = nullptr);
+
+// The chain of chunk-phase contractions worth fusing: a maximal path op -> its only consumer -> ... through nodes
+// whose rows are small, chosen by total FLOPs (the dominant contractions of the elimination-order-like plans are such
+// a chain: a growing intermediate times one small side operand after the other).  Empty when there is none.
+std::vector<int> select_chain(const Lowered& L, int dtype, const RowPlanOptions& o);
+// Move the ops of `chain` (ascending indices) so that they are contiguous at the position of the last one -- legal
+// because nothing outside the chain reads their intermediates -- and recompute dependency and use indices.
+// Returns the new indices of the chain ops.  Call BEFORE plan_memory.
+std::vector<int> make_contiguous(Lowered& L, const std::vector<int>& chain);
 
 // What the kernel reads: one resolved descriptor per unit and the slot table (levels padded to a multiple of
 // kRowWarps slots).  `ops` = rp.ops with oA/oB/oC final (fixed-variable offsets XORed in, 0 for global tensors) and

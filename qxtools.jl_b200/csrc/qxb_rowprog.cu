@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowprog_kernel(const __grid_co
                     // "all groups but the newest" at the level barrier means "every copy has landed"
                     const int n = 1 << h->ntt;
                     const unsigned dst = (unsigned)op->lC[0] | ((unsigned)op->lC[1] << 16);
-                    const R2* src = reinterpret_cast<const R2*>(op->gA);
+                    const R2* src = reinterpret_cast<const R2*>(op->gA) + (op->lsA == kRowShared ? 0ll : (P.amp0 + row) << op->lsA);
                     for (int i = lane; i < n; i += 32) cp_async_elem<R2>(arena + dst + i, src + i);
                     cp_async_commit();
                 }
@@ -228,9 +228,10 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowprog_kernel(const __grid_co
                 const R2 *pA = arena, *pB = arena;
                 R2* pC = arena;
                 if (h->gen) {
-                    if (op->gA) pA = reinterpret_cast<const R2*>(op->gA);
-                    if (op->gB) pB = reinterpret_cast<const R2*>(op->gB);
-                    if (op->gC) pC = reinterpret_cast<R2*>(op->gC);
+                    const long long r = P.amp0 + row;
+                    if (op->gA) pA = reinterpret_cast<const R2*>(op->gA) + (op->lsA == kRowShared ? 0ll : r << op->lsA);
+                    if (op->gB) pB = reinterpret_cast<const R2*>(op->gB) + (op->lsB == kRowShared ? 0ll : r << op->lsB);
+                    if (op->gC) pC = reinterpret_cast<R2*>(op->gC) + (op->lsC == kRowShared ? 0ll : r << op->lsC);
                 }
                 if (h->kind == kRowKindKred) {
                     row_kred<R2>(h, op, pA, pB, pC, bA, bB, bC, lane);

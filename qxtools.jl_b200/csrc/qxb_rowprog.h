@@ -15,6 +15,7 @@
 // Program = ops grouped into dependency LEVELS; the work of a level is cut into warp-sized UNITS (32 thread-tiles
 // of one op) that the warps of the CTA take round-robin; one __syncthreads per level.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 namespace qxb {
@@ -50,8 +51,9 @@ struct alignas(16) RowOp {
     // COLD part (host side only since the unit descriptors exist): address maps and tensor locations
     unsigned long long gA, gB, gC;   // global base pointer, or 0 when the tensor lives in the row arena
     long long rsA, rsB, rsC;         // elements between consecutive rows of a global per-row tensor (0 = shared)
-    int oA, oB, oC;                  // arena element offset (multiple of the tensor size) when g* == 0
-    uint8_t nsA, nsB, nsC, nkA, nkB, pad[3];
+    int oA, oB, oC;                  // arena element offset when g* == 0
+    uint8_t nsA, nsB, nsC, nkA, nkB;
+    uint8_t lsA, lsB, lsC;           // log2 row stride of global per-row tensors (kRowShared: none)
     RSeg tA[kRowMaxSeg], tB[kRowMaxSeg], tC[kRowMaxSeg];   // thread-tile index bits -> address bits
     RSeg kA[kRowMaxKSeg], kB[kRowMaxKSeg];                 // (k >> 4) bits -> address bits
 };
@@ -66,12 +68,17 @@ struct alignas(16) RowUnitDesc {
     RowOpHot hot;
     unsigned long long gA, gB, gC;           // global base pointers (0: the tensor lives in the row arena)
     RSeg kA[kRowMaxKSeg], kB[kRowMaxKSeg];   // (k >> 4) bits -> address bits (only read when nK > 4)
-    uint8_t nkA, nkB, pad[6];
+    uint8_t nkA, nkB;
+    uint8_t lsA, lsB, lsC;                   // log2 of the row stride (elements) of a global PER-ROW tensor (fused chains:
+                                             // inputs produced by other kernels, the chain's result); kRowShared = one
+                                             // tensor for all rows
+    uint8_t pad[3];
     uint16_t lA[32], lB[32], lC[32];         // per lane: base element offsets of its thread-tile (arena offset folded
                                              // in); lC == 0xFFFF: the lane has no thread-tile in this unit
 };
 static_assert(sizeof(RowUnitDesc) == 416, "unit descriptor must be 26 x 16 bytes");
 constexpr uint16_t kRowNull = 0xFFFF;        // slot table: no unit for this warp in this round
+constexpr uint8_t kRowShared = 0xFF;         // lsA / lsB / lsC: the global tensor does not depend on the row
 
 struct RowLeaf { int off, span_bits, out_idx; };   // output leaf materialised in the arena from the row's bitstring
 

@@ -16,14 +16,14 @@ bits = torch.from_numpy(bench.synth_bits(n_amp, nq)).cuda()
 cdt = torch.complex64 if w["dtype"] == "c32" else torch.complex128
 out = torch.zeros(n_amp, dtype=cdt, device="cuda")
 plan_txt = Graph.from_dsl(txt, data, w["dtype"], replan=128, replan_n_amp=n_amp).text
-CONFIGS = [("noring_notma", dict(ring=False, smem_tma=False), {}), ("noring_tma", dict(ring=False), {}), ("default", {}, {}),
-           ("ring_tt7", {}, {"QXB_RING_MIN_TT": "7"}), ("ring_all_rows", {}, {"QXB_RING_MIN_ROW_BYTES": "16384"})]
+CONFIGS = [("nochain_noring_notma", dict(chain=False, ring=False, smem_tma=False), {}), ("nochain", dict(chain=False), {}), ("default", {}, {}),
+           ("chain_tt7", {}, {"QXB_CHAIN_MIN_TT": "7"}), ("chain_cta1", dict(row_ctas_per_sm=1), {})]
 only = os.environ.get("PROBE_ONLY")
 if only:
     CONFIGS = [c for c in CONFIGS if c[0] in only.split(",")]
 ref, results = None, {}
 for tag, kw, env in CONFIGS:
-    for k in ("QXB_RING_MIN_TT", "QXB_RING_MIN_ROW_BYTES"):
+    for k in ("QXB_RING_MIN_TT", "QXB_RING_MIN_ROW_BYTES", "QXB_CHAIN_MIN_TT"):
         os.environ.pop(k, None)
     os.environ.update(env)
     g = Graph.from_dsl(plan_txt, data, w["dtype"]).compile(**kw)
@@ -57,7 +57,11 @@ for tag, kw, env in CONFIGS:
     dby, dms = sum(o["bytes"] for o in dom), sum(o["ms"] for o in dom)
     print(f"[{tag}] {ms:.3f} ms per {n_amp} -> {n_amp / ms * 1e3:.3e} amp/s, {st['bytes'] / ms / 1e6:.0f} GB/s alg; dominant {dby / dms / 1e6:.0f} GB/s "
           f"({dby / dms / 1e6 / 6451.5:.3f} of HBM peak); diff vs first {err:.1e}", flush=True)
-    print("    " + "  ".join(f"{o['name']}[{o['nC']},{o['nK']}]{o.get('kernel', '')} {o['ms']:.2f}ms {o['bytes'] / o['ms'] / 1e6:.0f}" for o in dom), flush=True)
+    print("    " + "  ".join(f"{o['name']}[{o.get('nC', '')},{o.get('nK', '')}]{o.get('kernel', '')} {o['ms']:.2f}ms {o['bytes'] / o['ms'] / 1e6:.0f}GB/s {o['flops'] / o['ms'] / 1e9:.1f}TF" for o in dom), flush=True)
+    for o in ops:
+        if o["name"] == "ROWPROG_CHAIN":
+            print(f"    chain: fused {o['fused']} levels {o['levels']} units {o['units']} arena {o['arena_bytes']} B, io {o['io_bytes_per_row']:.0f} B/row, "
+                  f"{o['ms']:.3f} ms, {o['flops'] / o['ms'] / 1e9:.2f} TFLOP/s, algorithmic {o['bytes'] / o['ms'] / 1e6:.0f} GB/s", flush=True)
     nring = sum(1 for o in ops if o.get("kernel") == "ring")
     print(f"    ring nodes: {nring} of {len(ops)}; sum of op ms {sum(o['ms'] for o in ops):.2f}", flush=True)
     results[tag] = {"ms": ms, "dominant_gbs": dby / dms / 1e6, "rel_diff": err, "ring_nodes": nring}

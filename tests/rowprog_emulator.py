@@ -82,7 +82,9 @@ def dump(graph, free_mask: int, phase: int):
     names = ("lop", "ref_a", "ref_b", "ref_c", "in_arena_a", "in_arena_b", "in_arena_c")
     for nm in names:
         setattr(rp, nm, np.frombuffer(raw, dtype=np.int32, count=n_ops, offset=off).tolist()); off += 4 * n_ops
-    assert off == need
+    rp.fused_names = raw[off:need].decode().split() if phase == 3 else []
+    if phase != 3:
+        assert off == need
     rp.n_levels = n_levels
     assert rp.level_start[-1] == n_slots and all(x % K_WARPS == 0 for x in rp.level_start)
     return rp

@@ -173,3 +173,31 @@ def test_ring_kernel_equals_streaming_kernels(gpu, workload, dtype, tol):
     o = orc.amplitudes(orc.parse_dsl(plan), data, bs, slice_begin=5, slice_end=8)
     big = np.tile(bits[:2], (148, 1))                    # >= 148 rows so that the ring kernel is eligible
     assert rel_err(g.amplitudes(big, 5, 8)[:2], o, nq) < max(tol, 1e-10)
+
+
+@pytest.mark.parametrize("dtype,tol", [("c64", 1e-12), ("c32", 1e-5)])
+def test_fused_chain_equals_per_op(gpu, dtype, tol):
+    """The chain of dominant contractions of the headline plan as ONE launch (inputs staged per row from global memory,
+    intermediates in shared memory, result back to global) against the same plan with every node as its own kernel."""
+    import bench, os, tempfile
+    txt, data, w = bench.build_workload("rqc_7x7_d20_c64_s4096")
+    n = 148 * 4 + 7
+    bits = bench.synth_bits(n, 49)
+    g = Graph.from_dsl(txt, data, dtype, replan=32, replan_n_amp=131072)
+    plan = g.text
+    got = g.compile(row_programs="block").amplitudes(bits)
+    ref = Graph.from_dsl(plan, data, "c64").compile(row_programs=False).amplitudes(bits)
+    assert np.max(np.abs(got - ref)) < tol * max(np.max(np.abs(ref)), 2.0 ** (-49 / 2))
+    prof = Graph.from_dsl(plan, data, dtype).compile(row_programs="block", profile=True)
+    got_p = prof.amplitudes(bits)                         # serial launches (no CUDA graph): same numbers
+    assert np.max(np.abs(got_p - got)) <= 1e-15 + 1e-6 * (dtype == "c32")
+    ops = [o for v in prof.profile_dump(os.path.join(tempfile.mkdtemp(), "p.json"))["variants"] for o in v["ops"]]
+    chain = [o for o in ops if o["name"] == "ROWPROG_CHAIN"]
+    assert chain and chain[0]["fused_ops"] >= 2, "the dominant chain was not fused"
+    off = Graph.from_dsl(plan, data, dtype).compile(row_programs="block", chain=False).amplitudes(bits)
+    assert np.max(np.abs(off - ref)) < tol * max(np.max(np.abs(ref)), 2.0 ** (-49 / 2))
+    # a slice sub-range (blocks with fixed variables: other variants, other chains) against the oracle
+    bs = ["".join("01"[b] for b in row) for row in bits[:2]]
+    o = orc.amplitudes(orc.parse_dsl(plan), data, bs, slice_begin=5, slice_end=8)
+    big = np.tile(bits[:2], (160, 1))
+    assert rel_err(g.amplitudes(big, 5, 8)[:2], o, 49) < max(tol, 1e-10)
