@@ -562,6 +562,60 @@ Node contract_node(const RunCtx& c, int i) {
     }
     if (p.nK >= 5 && p.nC <= 8 && outputs < 32768.0) {
         // reduction-shaped: too few outputs to fill the GPU with one thread each
+        // the reduction kernels index an output by ALL its C bits: undo the register-tile split of the template
+        // (since min_lob < 8 is the default, nodes of 2^7 - 2^8 outputs carry tile bits)
+        if (p.ma + p.nb > 0 || p.hb > 0) {
+            if (op.segA.size() > 8 || op.segB.size() > 8) throw Error(QXB_ERR_UNSUPP, "ncon " + op.name + ": too many address segments");
+            p.ma = p.nb = 0; p.hb = 0; p.lob = p.nC;
+            p.nsAlo = (int)op.segA.size(); p.nsBlo = (int)op.segB.size(); p.nsClo = 1;
+            for (size_t j = 0; j < op.segA.size(); ++j) p.sAlo[j] = DSeg{op.segA[j].src, op.segA[j].dst, op.segA[j].len, 0};
+            for (size_t j = 0; j < op.segB.size(); ++j) p.sBlo[j] = DSeg{op.segB[j].src, op.segB[j].dst, op.segB[j].len, 0};
+            p.sClo[0] = DSeg{0, 0, (unsigned char)p.nC, 0};
+            p.nsAhi = p.nsBhi = p.nsChi = 0;
+            p.tiles = (long long)p.U;
+        }
+        // tiled split-K: operand tiles of a K chunk staged in shared memory once per CTA (instead of one pass over K per
+        // output); needs few distinct operand rows and a single small batch of rows
+        bool tiled = false;
+        if (p.nK >= 12 && p.U <= 64 && !g->opts.no_gemm && knob(0, "QXB_KRED_TILE", 1) != 0) {
+            KredTile kt;
+            memset(&kt, 0, sizeof(kt));
+            std::map<long long, int> ra, rb;
+            bool ok = true;
+            for (int cc = 0; cc < (1 << p.nC) && ok; ++cc) {
+                long long oa = 0, ob = 0;
+                for (int sidx = 0; sidx < p.nsAlo; ++sidx) oa |= (long long)((cc >> p.sAlo[sidx].src) & ((1 << p.sAlo[sidx].len) - 1)) << p.sAlo[sidx].dst;
+                for (int sidx = 0; sidx < p.nsBlo; ++sidx) ob |= (long long)((cc >> p.sBlo[sidx].src) & ((1 << p.sBlo[sidx].len) - 1)) << p.sBlo[sidx].dst;
+                auto ia = ra.find(oa);
+                if (ia == ra.end()) { if ((int)ra.size() == kKredMaxRows) { ok = false; break; } kt.off_a[ra.size()] = oa; ia = ra.emplace(oa, (int)ra.size()).first; }
+                auto ib = rb.find(ob);
+                if (ib == rb.end()) { if ((int)rb.size() == kKredMaxRows) { ok = false; break; } kt.off_b[rb.size()] = ob; ib = rb.emplace(ob, (int)rb.size()).first; }
+                kt.row_a[cc] = (unsigned char)ia->second; kt.row_b[cc] = (unsigned char)ib->second;
+            }
+            // the low kKredTileKBits bits of k must be ordinary k bits of both operands (they always are: K bits are in A and B)
+            if (ok) {
+                kt.n_rows_a = (int)ra.size(); kt.n_rows_b = (int)rb.size();
+                const size_t smem = (size_t)(kt.n_rows_a + kt.n_rows_b) * (kKredTileK + 1) * g->es();
+                if (smem <= 96 * 1024) {
+                    n.func = kreduce_tile_func(g->dtype); n.kname = "kreduce_tile";
+                    n.smem = smem;
+                    if (smem > 48 * 1024 && first_use(n.func))
+                        CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                    const long long nchunks = 1ll << (p.nK - kKredTileKBits);
+                    n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(nchunks, (long long)g_num_sms * 3)));
+                    n.block = dim3(kThreads);
+                    n.pre_zero_ptr = p.C;
+                    n.pre_zero_bytes = (size_t)((C.amp ? c.n : 1) << C.span_bits) * g->es();
+                    n.arg(p); n.arg(kt);
+                    n.variant = c.variant_key; n.op = i;
+                    const double uu = (double)p.U;
+                    n.flops = 8.0 * op.macs_per_amp * uu;
+                    n.bytes = (double)g->es() * (op.elems_a * (A.amp ? c.n : 1) + op.elems_b * (B.amp ? c.n : 1) + op.elems_c * uu);
+                    return n;
+                }
+            }
+        }
+        (void)tiled;
         if (p.nK >= 16 && outputs * 2 <= (double)cap && !g->opts.no_gemm) {
             // huge K, a handful of outputs (root of a GEMM-shaped tree): split K over several blocks per output
             int sb = 0;
@@ -806,8 +860,9 @@ Variant* get_variant(qxb_graph* g, uint64_t free_mask) {
     RowPlanOptions co;
     const bool chain_on = knob(0, "QXB_CHAIN", 1) != 0 && g->opts.row_programs != 1 && g->opts.chain != 1;
     if (chain_on) {
-        co.min_tt_bits = knob(0, "QXB_CHAIN_MIN_TT", 8);
+        co.min_tt_bits = knob(0, "QXB_CHAIN_MIN_TT", 7);
         co.tile_reg_budget = knob(g->opts.row_tile_regs, "QXB_ROW_TILE_REGS", 100);
+        co.chain_min_macs = (double)knob(0, "QXB_CHAIN_MIN_MACS", 2048);
         // two CTAs per SM: (228 KB / 2 - 1 KB reserved) minus descriptor buffers and slot table
         co.max_arena_bytes = knob(0, "QXB_CHAIN_ARENA_KB", 0) ? 1024ll * knob(0, "QXB_CHAIN_ARENA_KB", 0)
                                                               : (233472 / 2 - 1024) - (long long)row_fixed_smem_bytes(512);
@@ -2049,7 +2104,7 @@ int64_t qxb_debug_rowprog(qxb_graph* g, uint64_t free_mask, int phase, void* buf
         std::vector<int> chain;
         RowPlanOptions co;
         if (phase == 3) {
-            co.min_tt_bits = knob(0, "QXB_CHAIN_MIN_TT", 8);
+            co.min_tt_bits = knob(0, "QXB_CHAIN_MIN_TT", 7);
             co.max_arena_bytes = (233472 / 2 - 1024) - (long long)row_fixed_smem_bytes(512);
             chain = select_chain(L, g->dtype, co);
             if (!chain.empty()) chain = make_contiguous(L, chain);

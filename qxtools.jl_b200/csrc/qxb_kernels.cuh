@@ -100,6 +100,16 @@ const void* kreduce_func(int dtype);
 const void* kreduce_block_func(int dtype);
 // split-K variant: 2^OpParams::kc blocks per output, partial sums combined with atomicAdd into a zeroed C
 const void* kreduce_split_func(int dtype);
+// tiled split-K variant (qxb_kred.cu): a CTA stages the operand tiles of a K chunk in shared memory once, a thread per
+// output accumulates over the chunk, partial sums meet by atomicAdd in a zeroed C.  Arguments (OpParams, KredTile);
+// dynamic shared memory = (n_rows_a + n_rows_b) * (kKredTileK + 1) * sizeof(element)
+constexpr int kKredTileKBits = 6, kKredTileK = 1 << kKredTileKBits, kKredMaxRows = 64;
+struct KredTile {
+    int n_rows_a, n_rows_b;                        // distinct operand rows the C bits select (<= kKredMaxRows each)
+    unsigned char row_a[256], row_b[256];          // output c -> its row of A / B
+    long long off_a[kKredMaxRows], off_b[kKredMaxRows];   // row -> element offset in the operand
+};
+const void* kreduce_tile_func(int dtype);
 // outleaf:  (R2* base, const OutLeafDesc* d, const unsigned char* bits, int n_outputs, long long amp0, long long n)
 const void* outleaf_func(int dtype);
 // reduce:   (const R2* root, long long sU, int span_bits, long long n, double scale, double* acc, long long amp0)

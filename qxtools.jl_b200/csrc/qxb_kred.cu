@@ -1,0 +1,77 @@
+// qxb200 -- tiled split-K reduction for reduction-shaped nodes (sm_100a): few outputs (<= 2^8 per bitstring row), very
+// long K.  Root-like nodes of GEMM-shaped trees (Sycamore-like 53 qubits, 12 cycles: 16 x 16 outputs, K = 2^24) went
+// through kreduce_split_kernel, which walks the whole K range once PER OUTPUT: every operand element is read 16 times
+// and the node ran at 58 GB/s (74.6 ms of a 227 ms slice, profiles/r2_summary.md).  Here a CTA takes a chunk of K,
+// stages the operand tiles A[rows of A x chunk], B[rows of B x chunk] in shared memory ONCE (a "row" = the distinct
+// operand addresses the C bits select), every thread accumulates one output over the chunk from shared memory, and the
+// partial sums are combined with atomicAdd into a zeroed C.  HBM traffic = |A| + |B|, once.
+#include <cuda_runtime.h>
+
+#include "qxb_kernels.cuh"
+
+namespace qxb {
+
+namespace {
+__device__ __forceinline__ long long kseg(const DSeg* s, int n, unsigned long long x) {
+    long long r = 0;
+    for (int i = 0; i < n; ++i) {
+        const DSeg g = s[i];
+        r |= (long long)(((x >> g.src) & ((1ull << g.len) - 1ull)) << g.dst);
+    }
+    return r;
+}
+template <typename R2>
+__device__ __forceinline__ void kmac(R2& acc, const R2 a, const R2 b) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+}
+}  // namespace
+
+template <typename R2>
+__global__ void __launch_bounds__(kThreads)
+kreduce_tile_kernel(const __grid_constant__ OpParams p, const __grid_constant__ KredTile t) {
+    constexpr int KT = kKredTileK;
+    constexpr int LD = KT + 1;                        // padded row: threads of a warp read different rows at the same k
+    extern __shared__ __align__(16) unsigned char kred_smem[];
+    R2* sA = reinterpret_cast<R2*>(kred_smem);
+    R2* sB = sA + t.n_rows_a * LD;
+    const R2* __restrict__ A = reinterpret_cast<const R2*>(p.A);
+    const R2* __restrict__ B = reinterpret_cast<const R2*>(p.B);
+    R2* __restrict__ C = reinterpret_cast<R2*>(p.C);
+    const int tid = threadIdx.x;
+    const int c = tid & ((1 << p.nC) - 1);            // this thread's output; the spare thread bits split the chunk's k
+    const int grp = tid >> p.nC, ngrp = kThreads >> p.nC;
+    const int ra = t.row_a[c] * LD, rb = t.row_b[c] * LD;
+    // staging slots: element e = tid + 256 * i of a tile -> row e / KT, k e % KT (KT divides 256: kk is fixed per thread)
+    const int kk = tid % KT, r0 = tid / KT;
+    constexpr int RSTEP = kThreads / KT;
+    const long long gAk = kseg(p.kA, p.nkA, (unsigned long long)kk), gBk = kseg(p.kB, p.nkB, (unsigned long long)kk);
+    const long long nchunks = 1ll << (p.nK - kKredTileKBits);
+    for (long long u = 0; u < p.U; ++u) {
+        const R2* Au = A + u * p.sUA;
+        const R2* Bu = B + u * p.sUB;
+        R2 acc; acc.x = 0; acc.y = 0;
+        for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+            const unsigned long long k0 = (unsigned long long)ch << kKredTileKBits;
+            const long long gA0 = kseg(p.kA, p.nkA, k0) + gAk, gB0 = kseg(p.kB, p.nkB, k0) + gBk;   // disjoint bits: k0 | kk
+            __syncthreads();                           // the previous chunk is consumed
+            for (int r = r0; r < t.n_rows_a; r += RSTEP) sA[r * LD + kk] = __ldg(Au + t.off_a[r] + gA0);
+            for (int r = r0; r < t.n_rows_b; r += RSTEP) sB[r * LD + kk] = __ldg(Bu + t.off_b[r] + gB0);
+            __syncthreads();
+#pragma unroll 8
+            for (int k = grp; k < KT; k += ngrp) kmac(acc, sA[ra + k], sB[rb + k]);
+        }
+        // one atomic per thread and row (the spare-bit groups of an output simply add up in C)
+        R2* dst = C + u * p.sUC + kseg(p.sClo, p.nsClo, (unsigned long long)c);
+        atomicAdd(&dst->x, acc.x);
+        atomicAdd(&dst->y, acc.y);
+    }
+}
+
+const void* kreduce_tile_func(int dtype) {
+    return dtype == 0 ? (const void*)&kreduce_tile_kernel<float2> : (const void*)&kreduce_tile_kernel<double2>;
+}
+
+}  // namespace qxb

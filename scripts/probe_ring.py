@@ -16,14 +16,14 @@ bits = torch.from_numpy(bench.synth_bits(n_amp, nq)).cuda()
 cdt = torch.complex64 if w["dtype"] == "c32" else torch.complex128
 out = torch.zeros(n_amp, dtype=cdt, device="cuda")
 plan_txt = Graph.from_dsl(txt, data, w["dtype"], replan=128, replan_n_amp=n_amp).text
-CONFIGS = [("nochain_noring_notma", dict(chain=False, ring=False, smem_tma=False), {}), ("nochain", dict(chain=False), {}), ("default", {}, {}),
-           ("chain_tt7", {}, {"QXB_CHAIN_MIN_TT": "7"}), ("chain_cta1", dict(row_ctas_per_sm=1), {})]
+CONFIGS = [("nochain", dict(chain=False), {}), ("default", {}, {}), ("chain_tt6", {}, {"QXB_CHAIN_MIN_TT": "6"}), ("chain_tt5", {}, {"QXB_CHAIN_MIN_TT": "5"}),
+           ("chain_tt7_regs64", dict(row_tile_regs=64), {}), ("chain_tt6_minmacs1k", {}, {"QXB_CHAIN_MIN_TT": "6", "QXB_CHAIN_MIN_MACS": "1024"})]
 only = os.environ.get("PROBE_ONLY")
 if only:
     CONFIGS = [c for c in CONFIGS if c[0] in only.split(",")]
 ref, results = None, {}
 for tag, kw, env in CONFIGS:
-    for k in ("QXB_RING_MIN_TT", "QXB_RING_MIN_ROW_BYTES", "QXB_CHAIN_MIN_TT"):
+    for k in ("QXB_RING_MIN_TT", "QXB_RING_MIN_ROW_BYTES", "QXB_CHAIN_MIN_TT", "QXB_CHAIN_MIN_MACS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     g = Graph.from_dsl(plan_txt, data, w["dtype"]).compile(**kw)

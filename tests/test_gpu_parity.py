@@ -371,6 +371,39 @@ def test_gemm_shaped_node_random(gpu, dtype, gemm_mode, seed):
 
 
 @pytest.mark.parametrize("dtype", ["c64", "c32"])
+@pytest.mark.parametrize("nk,nm,nn", [(14, 4, 4), (13, 3, 4), (12, 4, 2)])
+def test_tiled_split_k_reduction(gpu, dtype, nk, nm, nn):
+    """2^nm x 2^nn outputs (up to 16 x 16 = 2^8: the template of such a node carries register-tile bits) against
+    K = 2^nk, shuffled mode orders: the tiled split-K kernel (csrc/qxb_kred.cu: operand tiles of a K chunk staged in
+    shared memory once per CTA) -- the shape of the root-like node that was 39 % of a Sycamore-53 depth-12 slice."""
+    rng = np.random.default_rng(31 + nk)
+    ks = list(range(1, nk + 1)); ms = list(range(nk + 1, nk + nm + 1)); ns = list(range(nk + nm + 1, nk + nm + nn + 1))
+    o_lab = nk + nm + nn + 1
+    la = list(rng.permutation(ks + ms)); lb = list(rng.permutation(ks + ns)) + [o_lab]
+    lb2 = [x for x in lb if x != o_lab]
+    lc = list(rng.permutation(ms + ns))
+    A = (rng.normal(size=(2,) * len(la)) + 1j * rng.normal(size=(2,) * len(la))) / 16
+    B = (rng.normal(size=(2,) * len(lb)) + 1j * rng.normal(size=(2,) * len(lb))) / 16
+    W = rng.normal(size=(2,) * len(lc)) + 1j * rng.normal(size=(2,) * len(lc))
+    j = lambda l: ",".join(str(int(i)) for i in l)
+    txt = ("# version: 0.4.0\n"
+           f"load a dA {j([2] * len(la))}\nload b dB {j([2] * len(lb))}\nload w dW {j([2] * len(lc))}\noutput o1 1 2\n"
+           f"ncon b2 {j(lb2)} b {j(lb)} o1 {o_lab}\n"
+           f"ncon c {j(lc)} a {j(la)} b2 {j(lb2)}\n"
+           f"ncon z 0 c {j(lc)} w {j(lc)}\nsave output z\n")
+    data = {"dA": A, "dB": B, "dW": W}
+    bs = ["0", "1", "+", "-"]
+    ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
+    import os, tempfile
+    g = Graph.from_dsl(txt, data, dtype).compile(profile=True)
+    got = g.amplitudes(bs)
+    prof = g.profile_dump(os.path.join(tempfile.mkdtemp(), "p.json"))
+    o = [o for v in prof["variants"] for o in v["ops"] if o["name"] == "c"][0]
+    assert o["nK"] == nk and o["nC"] == nm + nn and o["kernel"] == "kreduce_tile", o
+    assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 5e-5)
+
+
+@pytest.mark.parametrize("dtype", ["c64", "c32"])
 def test_split_k_reduction(gpu, dtype):
     """K = 2^17 against 2 x 4 outputs: the split-K reduction kernel (several blocks per output, atomicAdd
     into a zeroed C) that the root-like nodes of GEMM-shaped trees go through."""
