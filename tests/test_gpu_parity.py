@@ -395,11 +395,13 @@ def test_tiled_split_k_reduction(gpu, dtype, nk, nm, nn):
     bs = ["0", "1", "+", "-"]
     ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
     import os, tempfile
-    g = Graph.from_dsl(txt, data, dtype).compile(profile=True)
+    g = Graph.from_dsl(txt, data, dtype).compile(profile=True, row_programs=False)     # per-op kernels (4 bitstrings would run as a row program)
     got = g.amplitudes(bs)
     prof = g.profile_dump(os.path.join(tempfile.mkdtemp(), "p.json"))
     o = [o for v in prof["variants"] for o in v["ops"] if o["name"] == "c"][0]
     assert o["nK"] == nk and o["nC"] == nm + nn and o["kernel"] == "kreduce_tile", o
+    auto = Graph.from_dsl(txt, data, dtype).compile().amplitudes(bs)                    # whatever the auto mode picks
+    assert np.max(np.abs(auto - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 5e-5)
     assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 5e-5)
 
 
