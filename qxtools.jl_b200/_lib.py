@@ -16,7 +16,7 @@ ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_STATE", -3: "ERR_CUDA", -4: "ERR_U
 
 # every symbol include/qxb200.h declares (tests check that all of them are exported)
 SYMBOLS = [
-    "qxb_version", "qxb_last_error", "qxb_init", "qxb_shutdown", "qxb_set_stream", "qxb_device_synchronize",
+    "qxb_version", "qxb_last_error", "qxb_init", "qxb_shutdown", "qxb_set_stream", "qxb_device_synchronize", "qxb_fma_peak",
     "qxb_graph_create", "qxb_graph_destroy", "qxb_graph_load", "qxb_graph_output", "qxb_graph_view",
     "qxb_graph_ncon", "qxb_graph_save", "qxb_graph_parse_dsl", "qxb_graph_set_data",
     "qxb_graph_num_outputs", "qxb_graph_root_dims", "qxb_graph_num_slice_vars", "qxb_graph_num_slices", "qxb_slice_values",
@@ -80,6 +80,7 @@ def load():
         "qxb_shutdown": (i32, []),
         "qxb_set_stream": (i32, [p]),
         "qxb_device_synchronize": (i32, []),
+        "qxb_fma_peak": (i32, [i32, C.POINTER(C.c_double)]),
         "qxb_graph_create": (i32, [C.POINTER(p), i32]),
         "qxb_graph_destroy": (None, [p]),
         "qxb_graph_load": (i32, [p, cp, cp, pi64, i32]),

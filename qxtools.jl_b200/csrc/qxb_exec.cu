@@ -1501,6 +1501,16 @@ int qxb_set_stream(void* s) {
     });
 }
 
+int qxb_fma_peak(int dtype, double* tflops) {
+    return guard([&] {
+        if (!tflops) throw Error(QXB_ERR_ARG, "null argument");
+        if (dtype != QXB_C32 && dtype != QXB_C64) throw Error(QXB_ERR_ARG, "dtype must be QXB_C32 or QXB_C64");
+        ensure_init();
+        *tflops = fma_peak_tflops(dtype, g_num_sms, stream());
+        CUDA_OK(cudaGetLastError());
+    });
+}
+
 int qxb_device_synchronize(void) {
     return guard([&] { ensure_init(); CUDA_OK(cudaStreamSynchronize(stream())); });
 }

@@ -110,6 +110,8 @@ struct KredTile {
     long long off_a[kKredMaxRows], off_b[kKredMaxRows];   // row -> element offset in the operand
 };
 const void* kreduce_tile_func(int dtype);
+// measured FMA-pipe peak of the current device in TFLOP/s (dtype 0: FFMA, 1: DFMA), see qxb_kred.cu
+double fma_peak_tflops(int dtype, int num_sms, cudaStream_t st);
 // outleaf:  (R2* base, const OutLeafDesc* d, const unsigned char* bits, int n_outputs, long long amp0, long long n)
 const void* outleaf_func(int dtype);
 // reduce:   (const R2* root, long long sU, int span_bits, long long n, double scale, double* acc, long long amp0)

@@ -74,4 +74,48 @@ const void* kreduce_tile_func(int dtype) {
     return dtype == 0 ? (const void*)&kreduce_tile_kernel<float2> : (const void*)&kreduce_tile_kernel<double2>;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// FMA-pipe peak, measured on the device the library runs on: the roofline denominator for the launches whose
+// intermediates live in shared memory (fused chain, row programs) -- those are bound by the FP64 / FP32 FMA pipe, not by
+// HBM.  16 independent accumulators per thread, no memory traffic in the loop.
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b) {
+    T acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = (T)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+    }
+    T s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// TFLOP/s (2 flops per FMA) of the FFMA (dtype 0) or DFMA (dtype 1) pipe: best of 5 timed launches on `st`
+double fma_peak_tflops(int dtype, int num_sms, cudaStream_t st) {
+    const int blocks = num_sms * 8, iters = 4096;
+    void* buf = nullptr;
+    if (cudaMalloc(&buf, (size_t)blocks * 256 * 8) != cudaSuccess) return 0.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0, st);
+        if (dtype == 0) fma_peak_kernel<float><<<blocks, 256, 0, st>>>((float*)buf, iters, 1.0000001f, 1e-9f);
+        else fma_peak_kernel<double><<<blocks, 256, 0, st>>>((double*)buf, iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 16.0 * iters * (double)blocks * 256.0 / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf);
+    return best;
+}
+
 }  // namespace qxb

@@ -400,6 +400,13 @@ def set_stream(stream_ptr: int) -> None:
     check(_lib.load().qxb_set_stream(C.c_void_p(stream_ptr)))
 
 
+def fma_peak(dtype: str = "c64") -> float:
+    """Measured FMA-pipe peak of the current device in TFLOP/s (``qxb_fma_peak``): FFMA for c32, DFMA for c64."""
+    v = C.c_double()
+    check(_lib.load().qxb_fma_peak(QXB_C32 if dtype == "c32" else QXB_C64, C.byref(v)))
+    return v.value
+
+
 def synchronize() -> None:
     check(_lib.load().qxb_device_synchronize())
 

@@ -144,3 +144,64 @@ def test_tensor_core_gemm_on_sycamore_like(gpu):
     refs = orc.amplitudes(cmds, data, bss, slice_begin=17, slice_end=18)
     assert rel_err(t64.amplitudes(bss, 17, 18), refs, 53) < 1e-10
     assert rel_err(t32.amplitudes(bss, 17, 18), refs, 53) < 1e-5
+
+
+def _oracle_range(args):
+    txt, data, bitstring, s0, s1 = args
+    from oracle import qx_oracle as o
+    return o.amplitude(o.parse_dsl(txt), data, bitstring, np.complex128, s0, s1)
+
+
+def test_rqc_7x7_one_whole_amplitude_vs_oracle(gpu):
+    """ONE complete amplitude of the full-size program -- all 4096 slices -- against the oracle (~2.4 minutes of numpy on
+    one core, spread over the host cores), through every execution mode of the library: the default of the bench (the
+    re-planned tree, fused chain, ring / TMA kernels; 2 x 148 copies of the bitstring so that the batched kernels are the
+    ones that run), the per-op kernels on the program as given, and the row program (3 launches per call)."""
+    import multiprocessing as mp
+    import os
+    txt, data, w = bench.build_workload("rqc_7x7_d20_c64_s4096")
+    bits = bench.synth_bits(1, 49, seed=77)
+    bs = "".join("01"[b] for b in bits[0])
+    cores = max(1, min(os.cpu_count() or 1, 32))
+    S = 4096
+    step = (S + cores - 1) // cores
+    tasks = [(txt, data, bs, s0, min(s0 + step, S)) for s0 in range(0, S, step)]
+    with mp.get_context("fork").Pool(cores) as pool:
+        ref = sum(pool.map(_oracle_range, tasks, chunksize=1))
+    scale = max(abs(ref), 2.0 ** (-49 / 2))
+    g = Graph.from_dsl(txt, data, "c64", replan=128, replan_n_amp=131072).compile()
+    many = np.tile(bits, (2 * 148 + 5, 1))
+    got = g.amplitudes(many)
+    assert np.max(np.abs(got - ref)) / scale < 1e-10
+    assert abs(g.amplitudes(bits)[0] - ref) / scale < 1e-10                         # one bitstring: the row program
+    as_given = Graph.from_dsl(txt, data, "c64").compile(row_programs=False, chain=False, ring=False)
+    assert abs(as_given.amplitudes(bits)[0] - ref) / scale < 1e-10
+    g32 = Graph.from_dsl(txt, data, "c32", replan=128, replan_n_amp=131072).compile()
+    assert np.max(np.abs(g32.amplitudes(many) - ref)) / scale < 1e-5
+
+
+@pytest.mark.parametrize("case", ["rqc_unsliced", "fsim"])
+def test_library_sliced_program_on_gpu(gpu, case):
+    """GPU-aware slicing (qxb_graph_replan_ex, n_free = -3): the library ADDS slice variables until no tensor exceeds the
+    budget; the sliced program it writes must produce the original amplitudes on the GPU -- all slices, sub-ranges,
+    ComplexF32 -- and equal the oracle run on the unsliced program (CPU counterpart: tests/test_replan.py)."""
+    from cases import circuit_case
+    if case == "rqc_unsliced":
+        txt, data, bs = circuit_case(q.create_rqc_circuit(4, 4, 14, 7), n_slice=0, n_amp=6)
+        n_q, lim = 16, 4
+    else:
+        txt, data, bs = circuit_case(q.create_sycamore_like_circuit(8, seed=3, n_qubits=18), n_slice=0, n_amp=6)
+        n_q, lim = 18, 5
+    ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
+    g = Graph.from_dsl(txt, data, "c64")
+    info = g.replan(8, 1, n_free=-3, budget_bytes=3 * 16 * 2 ** lim)
+    assert info["replanned"]
+    sliced = g.text
+    g2 = Graph.from_dsl(sliced, data, "c64").compile()
+    assert g2.n_slices > 1
+    assert rel_err(g2.amplitudes(bs), ref, n_q) < 1e-10
+    S = g2.n_slices
+    parts = sum(g2.amplitudes(bs, b, min(b + 5, S)) for b in range(0, S, 5))
+    assert rel_err(parts, ref, n_q) < 1e-10
+    assert rel_err(Graph.from_dsl(sliced, data, "c32").compile().amplitudes(bs), ref, n_q) < 1e-5
+    assert rel_err(Graph.from_dsl(sliced, data, "c64").compile(row_programs=False).amplitudes(bs), ref, n_q) < 1e-10
