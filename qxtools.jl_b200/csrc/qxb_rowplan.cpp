@@ -69,6 +69,67 @@ bool describe_row_op(const LOp& op, int dtype, const RowPlanOptions& o, RowOp& d
     for (auto& s : op.segKB) for (int b = 0; b < s.len; ++b) kposB[s.src + b] = s.dst + b;
     for (int b = 0; b < nC; ++b) if (mapA[b] > 15 || mapB[b] > 15) return bad("operand wider than 2^16 elements");
     for (int b = 0; b < nK; ++b) if (kposA[b] > 15 || kposB[b] > 15) return bad("operand wider than 2^16 elements");
+    // ComplexF64 with >= 3 M-only, >= 3 N-only and >= 2 K bits: 8 x 8 output tiles on the FP64 tensor pipe (kRowKindDmma)
+    if (o.dmma && dtype == QXB_C64 && nK >= 2) {
+        std::vector<int> ms, ns;
+        for (int b = 0; b < nC; ++b) {
+            if (mapA[b] >= 0 && mapB[b] < 0) ms.push_back(b);
+            else if (mapB[b] >= 0 && mapA[b] < 0) ns.push_back(b);
+        }
+        if (ms.size() >= 3 && ns.size() >= 3) {
+            // fragment index bits: the M-only (N-only) bits that sit lowest in A (B) -- nearby addresses within a fragment load
+            std::sort(ms.begin(), ms.end(), [&](int x, int y) { return mapA[x] < mapA[y]; });
+            std::sort(ns.begin(), ns.end(), [&](int x, int y) { return mapB[x] < mapB[y]; });
+            const int mb[3] = {ms[0], ms[1], ms[2]}, nbq[3] = {ns[0], ns[1], ns[2]};
+            RowOpHot& h = d.hot;
+            h.kind = kRowKindDmma; h.nK = (uint8_t)nK; h.kc = 2; h.nb = 0; h.ks = 0;
+            for (int lane = 0; lane < 32; ++lane) {
+                const int g = lane >> 2, t = lane & 3;
+                int a = 0, b = 0, c = 0;
+                for (int j = 0; j < 3; ++j) if ((g >> j) & 1) { a |= 1 << mapA[mb[j]]; c |= 1 << mb[j]; b |= 1 << mapB[nbq[j]]; }
+                for (int j = 0; j < 2; ++j) if ((t >> j) & 1) { a |= 1 << kposA[j]; b |= 1 << kposB[j]; c |= 1 << nbq[j + 1]; }
+                d.frA[lane] = (uint16_t)a; d.frB[lane] = (uint16_t)b; d.frC[lane] = (uint16_t)c;
+            }
+            d.c_n1 = (uint16_t)(1 << nbq[0]);
+            for (int k = 0; k < (1 << std::min(nK, 4)); ++k) {
+                int a = 0, b = 0;
+                for (int t = 0; t < std::min(nK, 4); ++t) if ((k >> t) & 1) {
+                    if (kposA[t] >= 0) a |= 1 << kposA[t];
+                    if (kposB[t] >= 0) b |= 1 << kposB[t];
+                }
+                h.ktA[k] = (uint16_t)a; h.ktB[k] = (uint16_t)b;
+            }
+            // warp-tile index bits: every C bit that is not a fragment bit
+            std::vector<bool> frag(nC, false);
+            for (int j = 0; j < 3; ++j) { frag[mb[j]] = true; frag[nbq[j]] = true; }
+            std::vector<std::pair<int, int>> ta, tb, tc, ka, kb;
+            int t = 0;
+            for (int b = 0; b < nC; ++b) {
+                if (frag[b]) continue;
+                tc.push_back({t, b});
+                if (mapA[b] >= 0) ta.push_back({t, mapA[b]});
+                if (mapB[b] >= 0) tb.push_back({t, mapB[b]});
+                ++t;
+            }
+            for (int b = 4; b < nK; ++b) {
+                if (kposA[b] >= 0) ka.push_back({b - 4, kposA[b]});
+                if (kposB[b] >= 0) kb.push_back({b - 4, kposB[b]});
+            }
+            const int nsA = merge_runs(ta, d.tA, kRowMaxSeg), nsB = merge_runs(tb, d.tB, kRowMaxSeg), nsC = merge_runs(tc, d.tC, kRowMaxSeg);
+            const int nkA = merge_runs(ka, d.kA, kRowMaxKSeg), nkB = merge_runs(kb, d.kB, kRowMaxKSeg);
+            if (nsA >= 0 && nsB >= 0 && nsC >= 0 && nkA >= 0 && nkB >= 0) {
+                d.nsA = (uint8_t)nsA; d.nsB = (uint8_t)nsB; d.nsC = (uint8_t)nsC; d.nkA = (uint8_t)nkA; d.nkB = (uint8_t)nkB;
+                const int tile_bits = nC - 6;                 // 2^tile_bits warp-tiles
+                int per = std::max(0, std::min(2, tile_bits - 3));   // tiles per unit: 1, 2 or 4, at least 8 units when possible
+                h.ma = (uint8_t)per;
+                h.ntt = (uint8_t)tile_bits;
+                n_units = 1 << (tile_bits - per);
+                unit_cost = std::ldexp(1.0, per + nK) * 0.25 + 8.0;
+                return true;
+            }
+            memset(&d.hot, 0, sizeof(d.hot));                 // too many segments: fall through to the SIMT tile
+        }
+    }
     // register tile: highest M-only / N-only bits, alternating sides, while >= 2^min_tt_bits thread-tiles remain
     std::vector<int> mcand, ncand, mbits, nbits;
     for (int b = nC - 1; b >= 0; --b) {
@@ -462,6 +523,25 @@ RowDeviceTables build_row_tables(const RowProgramHost& rp, const std::vector<Row
                 d.gA = op.gA + (unsigned long long)first * (unsigned long long)rp.elem_bytes;
                 const unsigned dst = (unsigned)(op.oC + first);
                 d.lC[0] = (uint16_t)(dst & 0xFFFF); d.lC[1] = (uint16_t)(dst >> 16);
+                t.slots.push_back((uint16_t)t.descs.size());
+                t.descs.push_back(d);
+                t.desc_op.push_back(un.op);
+                continue;
+            }
+            if (op.hot.kind == kRowKindDmma) {
+                const int nt = 1 << op.hot.ma;
+                for (int i = 0; i < nt; ++i) {
+                    const unsigned wt = (unsigned)(un.chunk * nt + i);
+                    d.hot.aT[i] = (uint16_t)eval_segs(op.tA, op.nsA, wt);
+                    d.hot.bT[i] = (uint16_t)eval_segs(op.tB, op.nsB, wt);
+                    d.hot.cT[i] = (uint16_t)eval_segs(op.tC, op.nsC, wt);
+                }
+                d.hot.cT[4] = op.c_n1;
+                for (int lane = 0; lane < 32; ++lane) {
+                    d.lA[lane] = (uint16_t)(op.oA + op.frA[lane]);
+                    d.lB[lane] = (uint16_t)(op.oB + op.frB[lane]);
+                    d.lC[lane] = (uint16_t)(op.oC + op.frC[lane]);
+                }
                 t.slots.push_back((uint16_t)t.descs.size());
                 t.descs.push_back(d);
                 t.desc_op.push_back(un.op);

@@ -15,6 +15,7 @@ struct RowPlanOptions {
     bool alap = true;             // schedule every op as late as its consumers allow
     bool stage_shared = true;     // copy operands shared by all rows into the arena one level before their first use
     int stage_max_bits = 12;      // ... when they span at most 2^n elements
+    bool dmma = true;             // ComplexF64 nodes with >= 3 M-only / N-only bits: 8 x 8 tiles on the FP64 tensor pipe
     double chain_min_macs = 2048; // fused chain: complex MACs per row below which an end node is not worth a level
     long long max_arena_bytes = 200 * 1024;
 };

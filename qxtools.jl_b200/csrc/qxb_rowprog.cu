@@ -120,6 +120,58 @@ __device__ __forceinline__ void row_kred(const RowOpHot* __restrict__ h, const R
     if (active && ksub == 0) pC[bC] = acc;
 }
 
+// ComplexF64 nodes with >= 3 M-only and >= 3 N-only bits on the FP64 tensor pipe (DMMA): the warp computes up to four
+// 8 x 8 output tiles at once, K in steps of 4.  Per complex k4 step and tile: 2 LDS.128 + 4 MMAs for 256 complex MACs
+// (the SIMT 4 x 4 register tile needs 8 LDS.128 + 64 DFMA per lane for 16: twice the shared-memory wavefronts and
+// sixteen times the issue slots) -- the fused launches are bound by exactly those two (profiles/r2_summary.md).
+__device__ __forceinline__ void dmma(double (&d)[2], const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+template <int NT>
+__device__ __forceinline__ void row_dmma_tiles(const RowOpHot* __restrict__ h, const RowUnitDesc* __restrict__ op,
+                                               const double2* pA, const double2* pB, double2* pC, int bA, int bB, int bC) {
+    const int nK = h->nK;
+    double cre[NT][2], cim[NT][2];
+    int ta[NT], tb[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) { cre[i][0] = cre[i][1] = cim[i][0] = cim[i][1] = 0.0; ta[i] = bA + h->aT[i]; tb[i] = bB + h->bT[i]; }
+    const int nsteps = 1 << (nK - 2);
+    for (int s = 0; s < nsteps; ++s) {
+        const int k = s << 2;
+        int ka = h->ktA[k & 15], kb = h->ktB[k & 15];
+        if (nK > 4) { ka += rseg(op->kA, op->nkA, (unsigned)k >> 4); kb += rseg(op->kB, op->nkB, (unsigned)k >> 4); }
+        double2 a[NT], b[NT];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) { a[i] = pA[ta[i] + ka]; b[i] = pB[tb[i] + kb]; }
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            dmma(cre[i], a[i].x, b[i].x);
+            dmma(cim[i], a[i].x, b[i].y);
+            dmma(cre[i], -a[i].y, b[i].y);
+            dmma(cim[i], a[i].y, b[i].x);
+        }
+    }
+    const int n1 = h->cT[4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        const int c = bC + h->cT[i];
+        pC[c] = make_double2(cre[i][0], cim[i][0]);
+        pC[c + n1] = make_double2(cre[i][1], cim[i][1]);
+    }
+}
+template <typename R2>
+__device__ __forceinline__ void row_dmma(const RowOpHot* __restrict__ h, const RowUnitDesc* __restrict__ op, const R2* pA,
+                                         const R2* pB, R2* pC, int bA, int bB, int bC) {
+    if constexpr (sizeof(R2) == 16) {
+        switch (h->ma) {
+        case 0: row_dmma_tiles<1>(h, op, pA, pB, pC, bA, bB, bC); break;
+        case 1: row_dmma_tiles<2>(h, op, pA, pB, pC, bA, bB, bC); break;
+        default: row_dmma_tiles<4>(h, op, pA, pB, pC, bA, bB, bC); break;
+        }
+    }
+}
+
 template <typename R2, int MA, int NB, int KC>
 __device__ __forceinline__ void row_tile_pick(const RowOpHot* __restrict__ h, const RowUnitDesc* __restrict__ op, R2* arena,
                                               const R2* pA, const R2* pB, R2* pC, int bA, int bB, int bC) {
@@ -235,6 +287,11 @@ __global__ void __launch_bounds__(kRowThreads, 2) rowprog_kernel(const __grid_co
                 }
                 if (h->kind == kRowKindKred) {
                     row_kred<R2>(h, op, pA, pB, pC, bA, bB, bC, lane);
+                    continue;
+                }
+                if (h->kind == kRowKindDmma) {           // all 32 lanes take part in the MMAs
+                    if (h->gen) row_dmma<R2>(h, op, pA, pB, pC, bA, bB, bC);
+                    else row_dmma<R2>(h, op, arena, arena, arena, bA, bB, bC);
                     continue;
                 }
                 if (bC == kRowNull) continue;
@@ -372,6 +429,10 @@ __global__ void __launch_bounds__(kRowThreads, 1) ring_kernel(const __grid_const
             const RowUnitDesc* __restrict__ op = descs + u;
             const RowOpHot* __restrict__ h = &op->hot;
             const int lc = op->lC[lane];
+            if (h->kind == kRowKindDmma) {
+                row_dmma<R2>(h, op, data, data, data, op->lA[lane] + offA, op->lB[lane] + offB, lc + offC);
+                continue;
+            }
             if (lc == kRowNull) continue;
             const int bA = op->lA[lane] + offA, bB = op->lB[lane] + offB, bC = lc + offC;
             switch (h->ma * 3 + h->nb) {

@@ -30,6 +30,8 @@ struct RSeg { unsigned char src, dst, len, pad; };
 
 // kinds of inner loop
 constexpr int kRowKindKred = 0;         // <= 16 thread-tiles: lanes also split K, shuffle-reduced
+constexpr int kRowKindDmma = 254;       // ComplexF64 on the FP64 tensor pipe: a warp computes 8 x 8 output tiles with
+                                        // mma.sync.m8n8k4.f64 (4 real MMAs per complex k4 step); see RowUnitDesc
 constexpr int kRowKindCopy = 255;       // staging: 2^ntt elements from global memory (gA) into the arena at lC[0] | lC[1] << 16
 // tile kinds: 1 + (((ma * 3 + nb) * 3 + kc) * 2 + gen)
 inline int row_tile_kind(int ma, int nb, int kc, int gen) { return 1 + (((ma * 3 + nb) * 3 + kc) * 2 + gen); }
@@ -54,8 +56,10 @@ struct alignas(16) RowOp {
     int oA, oB, oC;                  // arena element offset when g* == 0
     uint8_t nsA, nsB, nsC, nkA, nkB;
     uint8_t lsA, lsB, lsC;           // log2 row stride of global per-row tensors (kRowShared: none)
-    RSeg tA[kRowMaxSeg], tB[kRowMaxSeg], tC[kRowMaxSeg];   // thread-tile index bits -> address bits
+    RSeg tA[kRowMaxSeg], tB[kRowMaxSeg], tC[kRowMaxSeg];   // thread-tile (kRowKindDmma: warp-tile) index bits -> address bits
     RSeg kA[kRowMaxKSeg], kB[kRowMaxKSeg];                 // (k >> 4) bits -> address bits
+    uint16_t frA[32], frB[32], frC[32];                    // kRowKindDmma: per-lane fragment offsets (without oA / oB / oC)
+    uint16_t c_n1;                                         // kRowKindDmma: C offset of n + 1 (the lane's second output)
 };
 
 struct RowUnit { uint16_t op, chunk; };      // host side: chunk = which group of 32 thread-tiles of the op
@@ -75,6 +79,10 @@ struct alignas(16) RowUnitDesc {
     uint8_t pad[3];
     uint16_t lA[32], lB[32], lC[32];         // per lane: base element offsets of its thread-tile (arena offset folded
                                              // in); lC == 0xFFFF: the lane has no thread-tile in this unit
+                                             // kRowKindDmma: the lane's MMA fragment element -- lane = 4 g + t holds
+                                             // A[m = g][k = t], B[k = t][n = g], C[m = g][n = 2 t], [2 t + 1]; the unit's
+                                             // 2^hot.ma tiles add hot.aT / bT / cT[tile]; hot.cT[4] = offset of n + 1;
+                                             // k = 4 s + t, step s adds hot.ktA / ktB[4 s]
 };
 static_assert(sizeof(RowUnitDesc) == 416, "unit descriptor must be 26 x 16 bytes");
 constexpr uint16_t kRowNull = 0xFFFF;        // slot table: no unit for this warp in this round

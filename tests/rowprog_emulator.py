@@ -137,6 +137,22 @@ def _run_unit(op: RowUnitDesc, mA: _Mem, mB: _Mem, mC: _Mem, fixA, fixB, stores,
             kb += _rseg(op.kB, op.nkB, k >> 4)
         return ka, kb
 
+    if h.kind == 254:                 # DMMA: 8 x 8 output tiles, lane = 4 g + t holds A[g][t], B[t][g], C[g][2t], C[g][2t + 1]
+        assert dtype == np.complex128, "the FP64 tensor-pipe path exists for ComplexF64 only"
+        g_, t_ = lane >> 2, lane & 3
+        for i in range(1 << h.ma):
+            Ct = np.zeros((8, 8), dtype=dtype)
+            for s_ in range(1 << (nK - 2)):
+                ka, kb = koff(np.full(32, s_ << 2, dtype=np.int64))
+                a = mA.ld(bA + h.aT[i] + ka)
+                b = mB.ld(bB + h.bT[i] + kb)
+                Af = np.zeros((8, 4), dtype=dtype); Bf = np.zeros((4, 8), dtype=dtype)
+                Af[g_, t_] = a
+                Bf[t_, g_] = b
+                Ct += Af @ Bf
+            stores.append((mC, bC + h.cT[i], Ct[g_, 2 * t_]))
+            stores.append((mC, bC + h.cT[i] + h.cT[4], Ct[g_, 2 * t_ + 1]))
+        return
     if h.kind == 0:                   # kred: lanes split K
         ntt, ks = h.ntt, h.ks
         ksub = lane >> ntt
