@@ -74,8 +74,10 @@ typedef struct qxb_options {
     int32_t chain;             /* 0 = auto: the chain of dominant contractions (each one the only consumer of the previous
                                   result, small rows) runs as ONE row-program launch, its intermediates never reach HBM;
                                   1 = never                                                                          */
-    int32_t row_dmma;          /* 0 = auto: ComplexF64 nodes with >= 3 M-only and >= 3 N-only bits inside row programs, fused
-                                  chains and the ring kernel run on the FP64 tensor pipe (mma.sync.m8n8k4.f64); 1 = SIMT only */
+    int32_t row_dmma;          /* ComplexF64 nodes with >= 3 M-only and >= 3 N-only bits inside row programs, fused chains and
+                                  the ring kernel on the FP64 tensor pipe (mma.sync.m8n8k4.f64, 8 x 8 tiles per warp):
+                                  0 = auto (= off: measured 8 % slower than the SIMT register tiles on the headline chain,
+                                  both are latency-bound, profiles/r2_summary.md), 1 = off, 2 = on                     */
     int32_t row_chunk_max_amps;/* auto mode: largest call (bitstrings) whose chunk phase runs as a row program; 0 = 512 */
 } qxb_options;
 

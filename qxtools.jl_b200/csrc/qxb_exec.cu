@@ -688,7 +688,7 @@ Node contract_node(const RunCtx& c, int i) {
                 RowPlanOptions ro;
                 ro.min_tt_bits = knob(0, "QXB_RING_MIN_TT", 8);
                 ro.tile_reg_budget = knob(0, "QXB_RING_TILE_REGS", 100);
-                ro.dmma = knob(0, "QXB_ROW_DMMA", 1) != 0 && g->opts.row_dmma != 1;
+                ro.dmma = (g->opts.row_dmma == 2 || (g->opts.row_dmma == 0 && knob(0, "QXB_ROW_DMMA", 0) != 0));
                 std::string why;
                 std::vector<RowUnitDesc> descs = build_ring_descs(op, g->dtype, ro, why);
                 if (!descs.empty()) {
@@ -783,7 +783,7 @@ void build_row_programs(qxb_graph* g, Variant& v) {
     o.alap = knob(0, "QXB_ROW_ALAP", 1) != 0;
     o.max_tile_bits = knob(0, "QXB_ROW_MAX_TILE", 4);
     o.stage_shared = knob(0, "QXB_ROW_STAGE", 1) != 0;
-    o.dmma = knob(0, "QXB_ROW_DMMA", 1) != 0 && g->opts.row_dmma != 1;
+    o.dmma = (g->opts.row_dmma == 2 || (g->opts.row_dmma == 0 && knob(0, "QXB_ROW_DMMA", 0) != 0));
     o.max_arena_bytes = 227 * 1024 - (long long)row_fixed_smem_bytes(2048 + kRowWarps * kRowMaxLevels);   // descriptor buffers + slot table
     // block phase (slice-only nodes: hundreds of tiny contractions, pure launch latency as separate kernels)
     v.rp_block = build_row_program(v.L, PH_BLOCK, g->dtype, o);
@@ -865,7 +865,7 @@ Variant* get_variant(qxb_graph* g, uint64_t free_mask) {
         co.min_tt_bits = knob(0, "QXB_CHAIN_MIN_TT", 7);
         co.tile_reg_budget = knob(g->opts.row_tile_regs, "QXB_ROW_TILE_REGS", 100);
         co.chain_min_macs = (double)knob(0, "QXB_CHAIN_MIN_MACS", 2048);
-        co.dmma = knob(0, "QXB_ROW_DMMA", 1) != 0 && g->opts.row_dmma != 1;
+        co.dmma = (g->opts.row_dmma == 2 || (g->opts.row_dmma == 0 && knob(0, "QXB_ROW_DMMA", 0) != 0));
         // two CTAs per SM: (228 KB / 2 - 1 KB reserved) minus descriptor buffers and slot table
         co.max_arena_bytes = knob(0, "QXB_CHAIN_ARENA_KB", 0) ? 1024ll * knob(0, "QXB_CHAIN_ARENA_KB", 0)
                                                               : (233472 / 2 - 1024) - (long long)row_fixed_smem_bytes(512);
@@ -2129,7 +2129,7 @@ int64_t qxb_debug_rowprog(qxb_graph* g, uint64_t free_mask, int phase, void* buf
         o.alap = knob(0, "QXB_ROW_ALAP", 1) != 0;
         o.max_tile_bits = knob(0, "QXB_ROW_MAX_TILE", 4);
         o.stage_shared = knob(0, "QXB_ROW_STAGE", 1) != 0;
-        o.dmma = co.dmma = knob(0, "QXB_ROW_DMMA", 1) != 0 && g->opts.row_dmma != 1;
+        o.dmma = co.dmma = (g->opts.row_dmma == 2 || (g->opts.row_dmma == 0 && knob(0, "QXB_ROW_DMMA", 0) != 0));
         o.max_arena_bytes = 227 * 1024 - (long long)row_fixed_smem_bytes(2048 + kRowWarps * kRowMaxLevels);
         RowProgramHost rp;
         if (phase == 3) {

@@ -16,8 +16,8 @@ bits = torch.from_numpy(bench.synth_bits(n_amp, nq)).cuda()
 cdt = torch.complex64 if w["dtype"] == "c32" else torch.complex128
 out = torch.zeros(n_amp, dtype=cdt, device="cuda")
 plan_txt = Graph.from_dsl(txt, data, w["dtype"], replan=128, replan_n_amp=n_amp).text
-CONFIGS = [("nochain", dict(chain=False), {}), ("chain_simt", dict(row_dmma=False), {}), ("default", {}, {}),
-           ("chain_dmma_cta1", dict(row_ctas_per_sm=1), {}), ("rows_all_dmma", dict(row_programs="all"), {}), ("rows_all_simt", dict(row_programs="all", row_dmma=False), {})]
+CONFIGS = [("nochain", dict(chain=False), {}), ("default", {}, {}), ("chain_dmma", dict(row_dmma=True), {}),
+           ("rows_all", dict(row_programs="all"), {})]
 only = os.environ.get("PROBE_ONLY")
 if only:
     CONFIGS = [c for c in CONFIGS if c[0] in only.split(",")]

@@ -51,12 +51,15 @@ def test_replanned_rqc_rowprog(lib_built):
     assert rp.n_levels < len(rp.lop)                      # levels really group independent ops
 
 
+@pytest.mark.parametrize("dmma", [False, True])
 @pytest.mark.parametrize("workload", ["rqc_7x7_d20_c64_s4096", "rqc_6x6_d16_c32_s64"])
-def test_bench_workloads_rowprog(lib_built, workload):
+def test_bench_workloads_rowprog(lib_built, workload, dmma, monkeypatch):
     """The plans the bench runs (every slice variable batched: nodes of up to 2^11 elements per bitstring, 2 x 2
     register tiles, several warp units per node, K chunks) against the emulator of the lowered program -- itself
     pinned to the oracle by tests/test_lowering.py -- and, on a short slice range, against the oracle directly."""
     import bench
+    if dmma:                                              # 8 x 8 tiles on the FP64 tensor pipe (mma.sync.m8n8k4 fragments)
+        monkeypatch.setenv("QXB_ROW_DMMA", "1")
     txt, data, w = bench.build_workload(workload)
     g = Graph.from_dsl(txt, data, "c64", replan=8, replan_n_amp=131072)
     nq = w["rows"] * w["cols"]
@@ -70,6 +73,7 @@ def test_bench_workloads_rowprog(lib_built, workload):
     kinds = {op.hot.kind for op in rp.descs}
     assert 0 in kinds and max(kinds) > 1                  # both the K-splitting path and register tiles are exercised
     if workload.startswith("rqc_7x7"):
+        assert (254 in kinds) == dmma
         assert max(op.hot.ma + op.hot.nb for op in rp.descs) >= 3
     # a 3-slice range (blocks with fixed variables) against the oracle
     bs = ["".join("01"[b] for b in row) for row in bench.synth_bits(1, nq)]
