@@ -1108,6 +1108,11 @@ Node chain_node(const RunCtx& c) {
     for (int i = 0; i <= rp.n_levels; ++i) P.level_start[i] = cd.level_start[i];
     const size_t n_slots = (size_t)cd.level_start[rp.n_levels];
     P.slots_bytes = (int)row_slots_bytes(n_slots);
+    if (g->opts.profile) {                                  // per-level cycles of CTA 0 (diagnostics, profile dump)
+        if (v.row_timing.reserve(sizeof(long long) * (kRowMaxLevels + 1)))
+            CUDA_OK(cudaMemset(v.row_timing.p, 0, v.row_timing.bytes));
+        P.timing = (long long*)v.row_timing.p;
+    }
     Node n;
     n.func = rowprog_func(g->dtype); n.kname = "chain";
     n.block = dim3(kRowThreads);
@@ -1928,10 +1933,19 @@ int qxb_profile_dump(qxb_graph* g, const char* path) {
                     if (rp.lop[j] < 0) { if (v.L.tensors[rp.ref_a[j]].amp) io += std::ldexp(1.0, v.L.tensors[rp.ref_a[j]].span_bits); }
                     else if (!rp.in_arena_c[j]) io += std::ldexp(1.0, v.L.tensors[rp.ref_c[j]].span_bits);
                 }
+                std::string lc = "[]";
+                if (v.row_timing.p) {
+                    std::vector<long long> cyc(rp.n_levels, 0);
+                    if (cudaMemcpy(cyc.data(), v.row_timing.p, sizeof(long long) * rp.n_levels, cudaMemcpyDeviceToHost) == cudaSuccess) {
+                        lc = "[";
+                        for (int l = 0; l < rp.n_levels; ++l) lc += (l ? "," : "") + std::to_string(cyc[l]);
+                        lc += "]";
+                    }
+                }
                 fprintf(f, "%s{\"name\":\"ROWPROG_CHAIN\",\"phase\":2,\"kernel\":\"chain\",\"fused_ops\":%d,\"fused\":[%s],\"levels\":%d,"
-                           "\"units\":%d,\"arena_bytes\":%lld,\"io_bytes_per_row\":%.0f,\"launches\":%lld,\"flops\":%.6g,\"bytes\":%.6g,\"ms\":%.6g}",
+                           "\"units\":%d,\"arena_bytes\":%lld,\"level_cycles_cta0\":%s,\"io_bytes_per_row\":%.0f,\"launches\":%lld,\"flops\":%.6g,\"bytes\":%.6g,\"ms\":%.6g}",
                         first ? "" : ",", (int)v.chain.size(), names.c_str(), rp.n_levels, (int)rp.units.size(),
-                        (long long)rp.arena_elems * (long long)g->es(), io * (double)g->es(), v.prof_chain.launches,
+                        (long long)rp.arena_elems * (long long)g->es(), lc.c_str(), io * (double)g->es(), v.prof_chain.launches,
                         v.prof_chain.flops, v.prof_chain.bytes, v.prof_chain.ms);
                 first = false;
             }

@@ -17,7 +17,7 @@ cdt = torch.complex64 if w["dtype"] == "c32" else torch.complex128
 out = torch.zeros(n_amp, dtype=cdt, device="cuda")
 plan_txt = Graph.from_dsl(txt, data, w["dtype"], replan=128, replan_n_amp=n_amp).text
 CONFIGS = [("nochain", dict(chain=False), {}), ("default", {}, {}), ("chain_dmma", dict(row_dmma=True), {}),
-           ("rows_all", dict(row_programs="all"), {})]
+           ("chain_tt8", {}, {"QXB_CHAIN_MIN_TT": "8"})]
 only = os.environ.get("PROBE_ONLY")
 if only:
     CONFIGS = [c for c in CONFIGS if c[0] in only.split(",")]
@@ -62,6 +62,8 @@ for tag, kw, env in CONFIGS:
         if o["name"] == "ROWPROG_CHAIN":
             print(f"    chain: fused {o['fused']} levels {o['levels']} units {o['units']} arena {o['arena_bytes']} B, io {o['io_bytes_per_row']:.0f} B/row, "
                   f"{o['ms']:.3f} ms, {o['flops'] / o['ms'] / 1e9:.2f} TFLOP/s, algorithmic {o['bytes'] / o['ms'] / 1e6:.0f} GB/s", flush=True)
+            rows_cta0 = 2 * ((n_amp + 295) // 296)
+            print("    cycles per level and row (CTA 0):", [round(c / rows_cta0) for c in o.get("level_cycles_cta0", [])], flush=True)
     nring = sum(1 for o in ops if o.get("kernel") == "ring")
     print(f"    ring nodes: {nring} of {len(ops)}; sum of op ms {sum(o['ms'] for o in ops):.2f}", flush=True)
     results[tag] = {"ms": ms, "dominant_gbs": dby / dms / 1e6, "rel_diff": err, "ring_nodes": nring}
