@@ -506,6 +506,69 @@ Node contract_node(const RunCtx& c, int i) {
     Node n;
     int tma_stages = 0;                    // > 0: the node runs contract_tma_kernel (second kernel argument)
     const double outputs = (double)p.U * std::ldexp(1.0, p.nC);
+    // "big x small" streaming node (qxb_kred.cu, bigsmall_kernel): one operand huge, the other tiny with a few N-only
+    // bits -- every thread owns one position of the big operand and all 2^N outputs, so the big operand is read once
+    if (!g->opts.no_gemm && knob(0, "QXB_BIGSMALL", 1) != 0 && op.n_batch == 0 && op.nK <= 5) {
+        const bool a_big = op.elems_a >= op.elems_b;
+        const LTensor &TB = a_big ? A : B, &TS = a_big ? B : A;
+        const auto& segBig = a_big ? op.segA : op.segB;
+        const auto& segSm = a_big ? op.segB : op.segA;
+        const auto& kBig = a_big ? op.segKA : op.segKB;
+        const auto& kSm = a_big ? op.segKB : op.segKA;
+        const int nN = a_big ? op.n_n : op.n_m;
+        const double big_elems = a_big ? op.elems_a : op.elems_b;
+        const void* bf = (nN >= 1 && nN <= 5) ? bigsmall_func(g->dtype, nN) : nullptr;
+        if (bf && big_elems >= std::ldexp(1.0, knob(0, "QXB_BIGSMALL_MIN_BITS", 20)) && TS.span_bits <= 12 && TB.span_bits <= 40 &&
+            op.nK + nN >= 3) {
+            std::vector<int> mapBig(p.nC, -1), mapSm(p.nC, -1);
+            for (auto& sg : segBig) for (int b = 0; b < sg.len; ++b) mapBig[sg.src + b] = sg.dst + b;
+            for (auto& sg : segSm) for (int b = 0; b < sg.len; ++b) mapSm[sg.src + b] = sg.dst + b;
+            BigSmallParams q;
+            memset(&q, 0, sizeof(q));
+            std::vector<int> nbits;
+            int npos = 0, nta = 0, ntc = 0;
+            bool ok = true;
+            for (int b = 0; b < p.nC && ok; ++b) {
+                if (mapSm[b] >= 0) { nbits.push_back(b); continue; }
+                auto push = [&](DSeg* dst, int& cnt, int d) {
+                    if (cnt > 0 && dst[cnt - 1].src + dst[cnt - 1].len == npos && dst[cnt - 1].dst + dst[cnt - 1].len == d) { ++dst[cnt - 1].len; return; }
+                    if (cnt == 16) { ok = false; return; }
+                    dst[cnt++] = DSeg{(unsigned char)npos, (unsigned char)d, 1, 0};
+                };
+                push(q.tA, nta, mapBig[b]);
+                push(q.tC, ntc, b);
+                ++npos;
+            }
+            if (ok && (int)nbits.size() == nN) {
+                q.ntA = nta; q.ntC = ntc; q.nK = op.nK;
+                q.n_pos = 1ll << npos;
+                for (int k = 0; k < (1 << op.nK); ++k) {
+                    long long a = 0, b = 0;
+                    for (auto& sg : kBig) a |= (long long)((k >> sg.src) & ((1 << sg.len) - 1)) << sg.dst;
+                    for (auto& sg : kSm) b |= (long long)((k >> sg.src) & ((1 << sg.len) - 1)) << sg.dst;
+                    q.aK[k] = a; q.bK[k] = (int)b;
+                }
+                for (int j = 0; j < (1 << nN); ++j) {
+                    long long cc = 0, b = 0;
+                    for (int t = 0; t < nN; ++t) if ((j >> t) & 1) { cc |= 1ll << nbits[t]; b |= 1ll << mapSm[nbits[t]]; }
+                    q.cN[j] = cc; q.bN[j] = (int)b;
+                }
+                q.big = a_big ? p.A : p.B; q.small_ = a_big ? p.B : p.A; q.C = p.C;
+                q.sUbig = a_big ? p.sUA : p.sUB; q.sUsmall = a_big ? p.sUB : p.sUA; q.sUC = p.sUC;
+                q.U = p.U;
+                n.func = bf; n.kname = "bigsmall";
+                n.block = dim3(kThreads);
+                n.smem = ((size_t)1 << (op.nK + nN)) * g->es();
+                n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>((q.n_pos + kThreads - 1) / kThreads, cap * 4)));
+                n.arg(q);
+                n.variant = c.variant_key; n.op = i;
+                const double u = (double)p.U;
+                n.flops = 8.0 * op.macs_per_amp * u;
+                n.bytes = (double)g->es() * (op.elems_a * (A.amp ? c.n : 1) + op.elems_b * (B.amp ? c.n : 1) + op.elems_c * u);
+                return n;
+            }
+        }
+    }
     // tcgen05 / TMEM 3xTF32 kernel (ComplexF32): auto prefers it wherever the shape has 2^7 M-only x 2^6 N-only bits
     // (81 TFLOP/s complex-equivalent stand-alone against 49 for the mma.sync kernel); gemm_mode 1 / 2 keep the others
     const int gm = gemm_mode(g);

@@ -110,6 +110,21 @@ struct KredTile {
     long long off_a[kKredMaxRows], off_b[kKredMaxRows];   // row -> element offset in the operand
 };
 const void* kreduce_tile_func(int dtype);
+// "big x small" streaming nodes (qxb_kred.cu): a thread owns one position of the big operand's free index space and all
+// 2^n_bits outputs of it.  Arguments (BigSmallParams); dynamic shared memory = 2^(nK + n_bits) * sizeof(element)
+struct BigSmallParams {
+    const void* big;
+    const void* small_;
+    void* C;
+    long long sUbig, sUsmall, sUC;     // elements between bitstring rows (0 = shared)
+    long long n_pos;                   // positions = 2^(nC - n_bits)
+    int U, nK, ntA, ntC;
+    DSeg tA[16], tC[16];               // position index bits -> address bits of the big operand / of C
+    long long aK[32];                  // k -> offset in the big operand
+    long long cN[32];                  // n -> offset in C
+    int bK[32], bN[32];                // k, n -> offset in the small operand
+};
+const void* bigsmall_func(int dtype, int n_bits);
 // measured FMA-pipe peak of the current device in TFLOP/s (dtype 0: FFMA, 1: DFMA), see qxb_kred.cu
 double fma_peak_tflops(int dtype, int num_sms, cudaStream_t st);
 // outleaf:  (R2* base, const OutLeafDesc* d, const unsigned char* bits, int n_outputs, long long amp0, long long n)

@@ -119,3 +119,77 @@ double fma_peak_tflops(int dtype, int num_sms, cudaStream_t st) {
 }
 
 }  // namespace qxb
+
+namespace qxb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// "big x small" streaming nodes: a huge operand (2^27 - 2^30 elements) times a tiny one (<= 2^10), few N-only bits
+// (<= 5) and few K bits (<= 5), no batch bits -- the bulk of a Sycamore-like depth-12 slice (24 nodes, 16 GB each).
+// contract_kernel gives every thread a 4-wide register tile over N and walks the remaining N values as separate tiles:
+// the big operand is read once PER N-TILE (4 - 8 times) and the node ran at 1.7 - 3.2 TB/s algorithmic.  Here a thread owns
+// one position of the big operand's free index space and ALL 2^N outputs of it: it reads its 2^K elements of the big
+// operand once (coalesced along the low bits, all loads in flight), multiplies by the small operand from shared memory
+// ([k][n], broadcast reads) and writes 2^N outputs (coalesced).  HBM traffic = |big| + |C|, once.
+template <typename R2, int NN>
+__global__ void __launch_bounds__(256)
+bigsmall_kernel(const __grid_constant__ BigSmallParams p) {
+    extern __shared__ __align__(16) unsigned char bs_smem[];
+    R2* sB = reinterpret_cast<R2*>(bs_smem);                       // [k][n]
+    const R2* __restrict__ A = reinterpret_cast<const R2*>(p.big);
+    const R2* __restrict__ B = reinterpret_cast<const R2*>(p.small_);
+    R2* __restrict__ C = reinterpret_cast<R2*>(p.C);
+    const int KK = 1 << p.nK;
+    for (long long u = 0; u < p.U; ++u) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < KK * NN; i += blockDim.x) {
+            const int k = i / NN, n = i % NN;
+            sB[i] = __ldg(B + u * p.sUsmall + p.bK[k] + p.bN[n]);
+        }
+        __syncthreads();
+        const R2* Au = A + u * p.sUbig;
+        R2* Cu = C + u * p.sUC;
+        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < p.n_pos; t += (long long)gridDim.x * blockDim.x) {
+            const long long a0 = kseg(p.tA, p.ntA, (unsigned long long)t);
+            const long long c0 = kseg(p.tC, p.ntC, (unsigned long long)t);
+            R2 acc[NN];
+#pragma unroll
+            for (int n = 0; n < NN; ++n) { acc[n].x = 0; acc[n].y = 0; }
+            for (int k0 = 0; k0 < KK; k0 += 4) {                   // four elements of the big operand in flight per round
+                R2 a[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a[q] = (k0 + q < KK) ? __ldg(Au + a0 + p.aK[k0 + q]) : R2{0, 0};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (k0 + q >= KK) break;
+                    const R2* bk = sB + (k0 + q) * NN;
+#pragma unroll
+                    for (int n = 0; n < NN; ++n) kmac(acc[n], a[q], bk[n]);
+                }
+            }
+#pragma unroll
+            for (int n = 0; n < NN; ++n) Cu[c0 + p.cN[n]] = acc[n];
+        }
+    }
+}
+
+const void* bigsmall_func(int dtype, int n_bits) {
+    if (dtype == 0) {
+        switch (n_bits) {
+        case 1: return (const void*)&bigsmall_kernel<float2, 2>;
+        case 2: return (const void*)&bigsmall_kernel<float2, 4>;
+        case 3: return (const void*)&bigsmall_kernel<float2, 8>;
+        case 4: return (const void*)&bigsmall_kernel<float2, 16>;
+        case 5: return (const void*)&bigsmall_kernel<float2, 32>;
+        default: return nullptr;
+        }
+    }
+    switch (n_bits) {
+    case 1: return (const void*)&bigsmall_kernel<double2, 2>;
+    case 2: return (const void*)&bigsmall_kernel<double2, 4>;
+    case 3: return (const void*)&bigsmall_kernel<double2, 8>;
+    case 4: return (const void*)&bigsmall_kernel<double2, 16>;
+    default: return nullptr;
+    }
+}
+
+}  // namespace qxb

@@ -43,8 +43,8 @@ if not os.environ.get("PROBE_NO_PROFILE"):
     for o in ops[:12]:
         ms = o["ms"] / o["launches"]; fl = o["flops"] / o["launches"]; by = o["bytes"] / o["launches"]
         res["top_ops"].append({"name": o["name"], "nC": o["nC"], "nK": o["nK"], "m": o["m_bits"], "n": o["n_bits"], "ms": ms,
-                               "tflops": fl / ms / 1e9, "gb_s": by / ms / 1e6, "share": ms / tot})
-        print(f"    {o['name']}: nC {o['nC']} nK {o['nK']} m {o['m_bits']} n {o['n_bits']}: {ms:.2f} ms ({ms / tot:.0%}) "
+                               "tflops": fl / ms / 1e9, "gb_s": by / ms / 1e6, "share": ms / tot, "kernel": o.get("kernel", "")})
+        print(f"    {o['name']} [{o.get('kernel', '')}]: nC {o['nC']} nK {o['nK']} m {o['m_bits']} n {o['n_bits']}: {ms:.2f} ms ({ms / tot:.0%}) "
               f"{fl / ms / 1e9:.1f} TFLOP/s {by / ms / 1e6:.0f} GB/s", flush=True)
     del gp; gc.collect(); torch.cuda.empty_cache()
 if not os.environ.get("PROBE_NO_C64"):

@@ -371,6 +371,43 @@ def test_gemm_shaped_node_random(gpu, dtype, gemm_mode, seed):
 
 
 @pytest.mark.parametrize("dtype", ["c64", "c32"])
+@pytest.mark.parametrize("nk,nn,big_first", [(3, 1, True), (4, 4, True), (2, 3, False), (5, 2, False), (4, 5, True)])
+def test_big_times_small_streaming_node(gpu, dtype, nk, nn, big_first):
+    """A 2^(17 + nk)-element operand against a 2^(nk + nn)-element one (per bitstring), shuffled mode orders, either
+    operand order: the streaming kernel of csrc/qxb_kred.cu (a thread owns one position of the big operand and all
+    2^nn outputs) -- the shape of the 24 dominant nodes of a Sycamore-53 depth-12 slice."""
+    if dtype == "c64" and nn > 4:
+        pytest.skip("ComplexF64 instantiations stop at 2^4 outputs per thread")
+    rng = np.random.default_rng(7 * nk + nn)
+    nm = 17
+    ks = list(range(1, nk + 1)); ms = list(range(nk + 1, nk + nm + 1)); ns = list(range(nk + nm + 1, nk + nm + nn + 1))
+    o_lab = nk + nm + nn + 1
+    la = list(rng.permutation(ks + ms)); lb = list(rng.permutation(ks + ns)) + [o_lab]
+    lb2 = [x for x in lb if x != o_lab]
+    lc = list(rng.permutation(ms + ns))
+    A = (rng.normal(size=(2,) * len(la)) + 1j * rng.normal(size=(2,) * len(la))) / 4
+    B = (rng.normal(size=(2,) * len(lb)) + 1j * rng.normal(size=(2,) * len(lb))) / 4
+    W = (rng.normal(size=(2,) * len(lc)) + 1j * rng.normal(size=(2,) * len(lc))) / 64
+    j = lambda l: ",".join(str(int(i)) for i in l)
+    pair = f"a {j(la)} b2 {j(lb2)}" if big_first else f"b2 {j(lb2)} a {j(la)}"
+    txt = ("# version: 0.4.0\n"
+           f"load a dA {j([2] * len(la))}\nload b dB {j([2] * len(lb))}\nload w dW {j([2] * len(lc))}\noutput o1 1 2\n"
+           f"ncon b2 {j(lb2)} b {j(lb)} o1 {o_lab}\n"
+           f"ncon c {j(lc)} {pair}\n"
+           f"ncon z 0 c {j(lc)} w {j(lc)}\nsave output z\n")
+    data = {"dA": A, "dB": B, "dW": W}
+    bs = ["0", "1", "+"]
+    ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
+    import os, tempfile
+    g = Graph.from_dsl(txt, data, dtype).compile(profile=True, row_programs=False)
+    got = g.amplitudes(bs)
+    assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 2e-5)
+    prof = g.profile_dump(os.path.join(tempfile.mkdtemp(), "p.json"))
+    kern = [o["kernel"] for v in prof["variants"] for o in v["ops"] if o["name"] == "c"][0]
+    assert kern == "bigsmall", kern
+
+
+@pytest.mark.parametrize("dtype", ["c64", "c32"])
 @pytest.mark.parametrize("nk,nm,nn", [(14, 4, 4), (13, 3, 4), (12, 4, 2)])
 def test_tiled_split_k_reduction(gpu, dtype, nk, nm, nn):
     """2^nm x 2^nn outputs (up to 16 x 16 = 2^8: the template of such a node carries register-tile bits) against
