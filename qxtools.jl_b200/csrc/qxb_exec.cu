@@ -507,7 +507,8 @@ Node contract_node(const RunCtx& c, int i) {
     int tma_stages = 0;                    // > 0: the node runs contract_tma_kernel (second kernel argument)
     const double outputs = (double)p.U * std::ldexp(1.0, p.nC);
     // "big x small" streaming node (qxb_kred.cu, bigsmall_kernel): one operand huge, the other tiny with a few N-only
-    // bits -- every thread owns one position of the big operand and all 2^N outputs, so the big operand is read once
+    // bits -- every thread owns one position of the big operand and 2^nlo outputs (all of them when the small operand
+    // has <= 5 N bits; further N bits go to the CTA index, next to the thread bits so that the re-reads hit in L2)
     if (!g->opts.no_gemm && knob(0, "QXB_BIGSMALL", 1) != 0 && op.n_batch == 0 && op.nK <= 5) {
         const bool a_big = op.elems_a >= op.elems_b;
         const LTensor &TB = a_big ? A : B, &TS = a_big ? B : A;
@@ -517,49 +518,63 @@ Node contract_node(const RunCtx& c, int i) {
         const auto& kSm = a_big ? op.segKB : op.segKA;
         const int nN = a_big ? op.n_n : op.n_m;
         const double big_elems = a_big ? op.elems_a : op.elems_b;
-        const void* bf = (nN >= 1 && nN <= 5) ? bigsmall_func(g->dtype, nN) : nullptr;
-        if (bf && big_elems >= std::ldexp(1.0, knob(0, "QXB_BIGSMALL_MIN_BITS", 20)) && TS.span_bits <= 12 && TB.span_bits <= 40 &&
-            op.nK + nN >= 3) {
+        const int max_lo = g->dtype == QXB_C32 ? 5 : 4;
+        const int nlo = nN <= max_lo ? nN : 4, nhi = nN - nlo;
+        const void* bf = nN >= 1 ? bigsmall_func(g->dtype, nlo) : nullptr;
+        const size_t small_bytes = ((size_t)1 << (op.nK + nN)) * g->es();
+        if (bf && big_elems >= std::ldexp(1.0, knob(0, "QXB_BIGSMALL_MIN_BITS", 20)) && small_bytes <= 64 * 1024 && nhi <= 8 &&
+            TS.span_bits <= 24 && TB.span_bits <= 40 && op.nK + nN >= 3 && p.nC - nN >= 8) {
             std::vector<int> mapBig(p.nC, -1), mapSm(p.nC, -1);
             for (auto& sg : segBig) for (int b = 0; b < sg.len; ++b) mapBig[sg.src + b] = sg.dst + b;
             for (auto& sg : segSm) for (int b = 0; b < sg.len; ++b) mapSm[sg.src + b] = sg.dst + b;
             BigSmallParams q;
             memset(&q, 0, sizeof(q));
-            std::vector<int> nbits;
-            int npos = 0, nta = 0, ntc = 0;
-            bool ok = true;
-            for (int b = 0; b < p.nC && ok; ++b) {
-                if (mapSm[b] >= 0) { nbits.push_back(b); continue; }
-                auto push = [&](DSeg* dst, int& cnt, int d) {
-                    if (cnt > 0 && dst[cnt - 1].src + dst[cnt - 1].len == npos && dst[cnt - 1].dst + dst[cnt - 1].len == d) { ++dst[cnt - 1].len; return; }
-                    if (cnt == 16) { ok = false; return; }
-                    dst[cnt++] = DSeg{(unsigned char)npos, (unsigned char)d, 1, 0};
-                };
-                push(q.tA, nta, mapBig[b]);
-                push(q.tC, ntc, b);
-                ++npos;
+            std::vector<int> nbits, pbits;
+            for (int b = 0; b < p.nC; ++b) (mapSm[b] >= 0 ? nbits : pbits).push_back(b);
+            // position index layout: [8 position bits][nhi N bits][remaining position bits]
+            std::vector<std::pair<int, int>> lay;          // (C bit, big-operand bit or -1)
+            for (int j = 0; j < 8; ++j) lay.push_back({pbits[j], mapBig[pbits[j]]});
+            for (int j = 0; j < nhi; ++j) lay.push_back({nbits[nlo + j], -1});
+            for (size_t j = 8; j < pbits.size(); ++j) lay.push_back({pbits[j], mapBig[pbits[j]]});
+            int nta = 0, ntc = 0;
+            bool ok = (int)nbits.size() == nN;
+            auto push = [&](DSeg* dst, int& cnt, int src, int d) {
+                if (cnt > 0 && dst[cnt - 1].src + dst[cnt - 1].len == src && dst[cnt - 1].dst + dst[cnt - 1].len == d) { ++dst[cnt - 1].len; return; }
+                if (cnt == 16) { ok = false; return; }
+                dst[cnt++] = DSeg{(unsigned char)src, (unsigned char)d, 1, 0};
+            };
+            for (size_t j = 0; j < lay.size() && ok; ++j) {
+                push(q.tC, ntc, (int)j, lay[j].first);
+                if (lay[j].second >= 0) push(q.tA, nta, (int)j, lay[j].second);
             }
-            if (ok && (int)nbits.size() == nN) {
-                q.ntA = nta; q.ntC = ntc; q.nK = op.nK;
-                q.n_pos = 1ll << npos;
+            if (ok) {
+                q.ntA = nta; q.ntC = ntc; q.nK = op.nK; q.nNhi = nhi;
+                q.n_pos = 1ll << lay.size();
                 for (int k = 0; k < (1 << op.nK); ++k) {
                     long long a = 0, b = 0;
                     for (auto& sg : kBig) a |= (long long)((k >> sg.src) & ((1 << sg.len) - 1)) << sg.dst;
                     for (auto& sg : kSm) b |= (long long)((k >> sg.src) & ((1 << sg.len) - 1)) << sg.dst;
                     q.aK[k] = a; q.bK[k] = (int)b;
                 }
-                for (int j = 0; j < (1 << nN); ++j) {
+                for (int j = 0; j < (1 << nlo); ++j) {
                     long long cc = 0, b = 0;
-                    for (int t = 0; t < nN; ++t) if ((j >> t) & 1) { cc |= 1ll << nbits[t]; b |= 1ll << mapSm[nbits[t]]; }
+                    for (int t = 0; t < nlo; ++t) if ((j >> t) & 1) { cc |= 1ll << nbits[t]; b |= 1ll << mapSm[nbits[t]]; }
                     q.cN[j] = cc; q.bN[j] = (int)b;
+                }
+                for (int j = 0; j < (1 << nhi); ++j) {
+                    long long b = 0;
+                    for (int t = 0; t < nhi; ++t) if ((j >> t) & 1) b |= 1ll << mapSm[nbits[nlo + t]];
+                    q.bH[j] = (int)b;
                 }
                 q.big = a_big ? p.A : p.B; q.small_ = a_big ? p.B : p.A; q.C = p.C;
                 q.sUbig = a_big ? p.sUA : p.sUB; q.sUsmall = a_big ? p.sUB : p.sUA; q.sUC = p.sUC;
                 q.U = p.U;
                 n.func = bf; n.kname = "bigsmall";
                 n.block = dim3(kThreads);
-                n.smem = ((size_t)1 << (op.nK + nN)) * g->es();
-                n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>((q.n_pos + kThreads - 1) / kThreads, cap * 4)));
+                n.smem = small_bytes;
+                if (first_use(n.func))
+                    CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(q.n_pos >> 8, cap * 4)));
                 n.arg(q);
                 n.variant = c.variant_key; n.op = i;
                 const double u = (double)p.U;

@@ -111,18 +111,20 @@ struct KredTile {
 };
 const void* kreduce_tile_func(int dtype);
 // "big x small" streaming nodes (qxb_kred.cu): a thread owns one position of the big operand's free index space and all
-// 2^n_bits outputs of it.  Arguments (BigSmallParams); dynamic shared memory = 2^(nK + n_bits) * sizeof(element)
+// 2^n_bits outputs of it (further N bits are enumerated by the CTA index).  Arguments (BigSmallParams); dynamic shared
+// memory = the whole small operand
 struct BigSmallParams {
     const void* big;
     const void* small_;
     void* C;
     long long sUbig, sUsmall, sUC;     // elements between bitstring rows (0 = shared)
-    long long n_pos;                   // positions = 2^(nC - n_bits)
-    int U, nK, ntA, ntC;
+    long long n_pos;                   // position indices = 2^(nC - n_bits): [8 thread bits][nNhi N bits][block bits]
+    int U, nK, ntA, ntC, nNhi;
     DSeg tA[16], tC[16];               // position index bits -> address bits of the big operand / of C
     long long aK[32];                  // k -> offset in the big operand
-    long long cN[32];                  // n -> offset in C
+    long long cN[32];                  // n (register tile) -> offset in C
     int bK[32], bN[32];                // k, n -> offset in the small operand
+    int bH[256];                       // N bits beyond the register tile -> offset in the small operand
 };
 const void* bigsmall_func(int dtype, int n_bits);
 // measured FMA-pipe peak of the current device in TFLOP/s (dtype 0: FFMA, 1: DFMA), see qxb_kred.cu

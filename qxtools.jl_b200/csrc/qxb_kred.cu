@@ -134,40 +134,53 @@ template <typename R2, int NN>
 __global__ void __launch_bounds__(256)
 bigsmall_kernel(const __grid_constant__ BigSmallParams p) {
     extern __shared__ __align__(16) unsigned char bs_smem[];
-    R2* sB = reinterpret_cast<R2*>(bs_smem);                       // [k][n]
+    R2* sB = reinterpret_cast<R2*>(bs_smem);                       // [n_hi][k][n]
     const R2* __restrict__ A = reinterpret_cast<const R2*>(p.big);
     const R2* __restrict__ B = reinterpret_cast<const R2*>(p.small_);
     R2* __restrict__ C = reinterpret_cast<R2*>(p.C);
     const int KK = 1 << p.nK;
+    const int n_small = (KK * NN) << p.nNhi;
+    // position index = [8 thread bits][n_hi bits][block bits]: the thread part of both addresses is evaluated once, the
+    // block part (with the N bits beyond the register tile) is uniform over the CTA
+    const long long a_lo = kseg(p.tA, p.ntA, (unsigned long long)threadIdx.x);
+    const long long c_lo = kseg(p.tC, p.ntC, (unsigned long long)threadIdx.x);
+    const long long n_blk = p.n_pos >> 8;
     for (long long u = 0; u < p.U; ++u) {
         __syncthreads();
-        for (int i = threadIdx.x; i < KK * NN; i += blockDim.x) {
-            const int k = i / NN, n = i % NN;
-            sB[i] = __ldg(B + u * p.sUsmall + p.bK[k] + p.bN[n]);
+        for (int i = threadIdx.x; i < n_small; i += blockDim.x) {
+            const int n = i % NN, k = (i / NN) & (KK - 1), nh = i / (NN * KK);
+            sB[i] = __ldg(B + u * p.sUsmall + p.bK[k] + p.bN[n] + p.bH[nh]);
         }
         __syncthreads();
-        const R2* Au = A + u * p.sUbig;
-        R2* Cu = C + u * p.sUC;
-        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < p.n_pos; t += (long long)gridDim.x * blockDim.x) {
-            const long long a0 = kseg(p.tA, p.ntA, (unsigned long long)t);
-            const long long c0 = kseg(p.tC, p.ntC, (unsigned long long)t);
+        const R2* Au = A + u * p.sUbig + a_lo;
+        R2* Cu = C + u * p.sUC + c_lo;
+        for (long long blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
+            const unsigned long long thi = (unsigned long long)blk << 8;
+            const R2* Ab = Au + kseg(p.tA, p.ntA, thi);
+            R2* Cb = Cu + kseg(p.tC, p.ntC, thi);
+            const R2* sBh = sB + (int)(blk & ((1 << p.nNhi) - 1)) * (KK * NN);
             R2 acc[NN];
 #pragma unroll
             for (int n = 0; n < NN; ++n) { acc[n].x = 0; acc[n].y = 0; }
-            for (int k0 = 0; k0 < KK; k0 += 4) {                   // four elements of the big operand in flight per round
-                R2 a[4];
+            // four elements of the big operand per round, the next round's loads issued before this round's FMAs
+            R2 a[4], an[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) a[q] = (k0 + q < KK) ? __ldg(Au + a0 + p.aK[k0 + q]) : R2{0, 0};
+            for (int q = 0; q < 4; ++q) a[q] = (q < KK) ? __ldg(Ab + p.aK[q]) : R2{0, 0};
+            for (int k0 = 0; k0 < KK; k0 += 4) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) an[q] = (k0 + 4 + q < KK) ? __ldg(Ab + p.aK[k0 + 4 + q]) : R2{0, 0};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (k0 + q >= KK) break;
-                    const R2* bk = sB + (k0 + q) * NN;
+                    const R2* bk = sBh + (k0 + q) * NN;
 #pragma unroll
                     for (int n = 0; n < NN; ++n) kmac(acc[n], a[q], bk[n]);
                 }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a[q] = an[q];
             }
 #pragma unroll
-            for (int n = 0; n < NN; ++n) Cu[c0 + p.cN[n]] = acc[n];
+            for (int n = 0; n < NN; ++n) Cb[p.cN[n]] = acc[n];
         }
     }
 }

@@ -371,15 +371,13 @@ def test_gemm_shaped_node_random(gpu, dtype, gemm_mode, seed):
 
 
 @pytest.mark.parametrize("dtype", ["c64", "c32"])
-@pytest.mark.parametrize("nk,nn,big_first", [(3, 1, True), (4, 4, True), (2, 3, False), (5, 2, False), (4, 5, True)])
+@pytest.mark.parametrize("nk,nn,big_first", [(3, 1, True), (4, 4, True), (2, 3, False), (5, 2, False), (4, 5, True), (3, 7, True), (4, 6, False)])
 def test_big_times_small_streaming_node(gpu, dtype, nk, nn, big_first):
     """A 2^(17 + nk)-element operand against a 2^(nk + nn)-element one (per bitstring), shuffled mode orders, either
     operand order: the streaming kernel of csrc/qxb_kred.cu (a thread owns one position of the big operand and all
-    2^nn outputs) -- the shape of the 24 dominant nodes of a Sycamore-53 depth-12 slice."""
-    if dtype == "c64" and nn > 4:
-        pytest.skip("ComplexF64 instantiations stop at 2^4 outputs per thread")
+    min(2^nn, 2^4 or 2^5) outputs, further N bits go to the CTA index) -- the shape of the 24 dominant nodes of a Sycamore-53 depth-12 slice."""
     rng = np.random.default_rng(7 * nk + nn)
-    nm = 17
+    nm = max(17 if nn <= 5 else 14, 20 - nk)                                 # the kernel takes operands of >= 2^20 elements
     ks = list(range(1, nk + 1)); ms = list(range(nk + 1, nk + nm + 1)); ns = list(range(nk + nm + 1, nk + nm + nn + 1))
     o_lab = nk + nm + nn + 1
     la = list(rng.permutation(ks + ms)); lb = list(rng.permutation(ks + ns)) + [o_lab]
