@@ -673,9 +673,22 @@ Node contract_node(const RunCtx& c, int i) {
             // the low kKredTileKBits bits of k must be ordinary k bits of both operands (they always are: K bits are in A and B)
             if (ok) {
                 kt.n_rows_a = (int)ra.size(); kt.n_rows_b = (int)rb.size();
-                const size_t smem = (size_t)(kt.n_rows_a + kt.n_rows_b) * (kKredTileK + 1) * g->es();
+                size_t smem = (size_t)(kt.n_rows_a + kt.n_rows_b) * (kKredTileK + 1) * g->es();
+                // outputs = the full grid rows(A) x rows(B): 2 x 2 outputs per thread, two-stage cp.async ring
+                bool grid_ok = knob(0, "QXB_KRED_GRID", 1) != 0 && kt.n_rows_a % 2 == 0 && kt.n_rows_b % 2 == 0 &&
+                               kt.n_rows_a * kt.n_rows_b == (1 << p.nC) && 2 * smem <= 96 * 1024;
+                if (grid_ok) {
+                    std::vector<int> seen(1 << p.nC, 0);
+                    for (int cc = 0; cc < (1 << p.nC); ++cc) {
+                        const int slot = kt.row_a[cc] * kt.n_rows_b + kt.row_b[cc];
+                        if (seen[slot]++) { grid_ok = false; break; }
+                        kt.grid_c[slot] = (unsigned char)cc;
+                    }
+                }
+                if (grid_ok) smem *= 2;
                 if (smem <= 96 * 1024) {
-                    n.func = kreduce_tile_func(g->dtype); n.kname = "kreduce_tile";
+                    n.func = grid_ok ? kreduce_grid_func(g->dtype) : kreduce_tile_func(g->dtype);
+                    n.kname = grid_ok ? "kreduce_grid" : "kreduce_tile";
                     n.smem = smem;
                     if (smem > 48 * 1024 && first_use(n.func))
                         CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));

@@ -108,8 +108,13 @@ struct KredTile {
     int n_rows_a, n_rows_b;                        // distinct operand rows the C bits select (<= kKredMaxRows each)
     unsigned char row_a[256], row_b[256];          // output c -> its row of A / B
     long long off_a[kKredMaxRows], off_b[kKredMaxRows];   // row -> element offset in the operand
+    unsigned char grid_c[256];                     // kreduce_grid_kernel: (row of A) * n_rows_b + (row of B) -> output c
 };
 const void* kreduce_tile_func(int dtype);
+// Same staging, for outputs that form the full grid rows(A) x rows(B) (both even): a thread owns a 2 x 2 block of outputs
+// (half the shared-memory reads per FMA) and the K chunks arrive through a two-stage cp.async ring, so the loads of the
+// next chunk overlap the FMAs of this one.  Dynamic shared memory = 2 * (n_rows_a + n_rows_b) * (kKredTileK + 1) * sizeof(element)
+const void* kreduce_grid_func(int dtype);
 // "big x small" streaming nodes (qxb_kred.cu): a thread owns one position of the big operand's free index space and all
 // 2^n_bits outputs of it (further N bits are enumerated by the CTA index).  Arguments (BigSmallParams); dynamic shared
 // memory = the whole small operand

@@ -70,6 +70,84 @@ kreduce_tile_kernel(const __grid_constant__ OpParams p, const __grid_constant__ 
     }
 }
 
+template <typename R2>
+__global__ void __launch_bounds__(kThreads)
+kreduce_grid_kernel(const __grid_constant__ OpParams p, const __grid_constant__ KredTile t) {
+    constexpr int KT = kKredTileK;
+    constexpr int LD = KT + 1;
+    extern __shared__ __align__(16) unsigned char kred_smem[];
+    const int nA = t.n_rows_a, nB = t.n_rows_b;
+    const int stage_elems = (nA + nB) * LD;
+    R2* sbuf = reinterpret_cast<R2*>(kred_smem);
+    const R2* __restrict__ A = reinterpret_cast<const R2*>(p.A);
+    const R2* __restrict__ B = reinterpret_cast<const R2*>(p.B);
+    R2* __restrict__ C = reinterpret_cast<R2*>(p.C);
+    const int tid = threadIdx.x;
+    const int n_tiles = (nA >> 1) * (nB >> 1);        // a power of two <= 256
+    const int tile = tid & (n_tiles - 1), grp = tid / n_tiles, ngrp = kThreads / n_tiles;
+    const int ia = (tile % (nA >> 1)) * 2, ib = (tile / (nA >> 1)) * 2;
+    const int kk = tid % KT, r0 = tid / KT;
+    constexpr int RSTEP = kThreads / KT;
+    const long long gAk = kseg(p.kA, p.nkA, (unsigned long long)kk), gBk = kseg(p.kB, p.nkB, (unsigned long long)kk);
+    const long long nchunks = 1ll << (p.nK - kKredTileKBits);
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(sbuf);
+    for (long long u = 0; u < p.U; ++u) {
+        const R2* Au = A + u * p.sUA;
+        const R2* Bu = B + u * p.sUB;
+        auto issue = [&](long long ch, int stage) {
+            const unsigned long long k0 = (unsigned long long)ch << kKredTileKBits;
+            const long long gA0 = kseg(p.kA, p.nkA, k0) + gAk, gB0 = kseg(p.kB, p.nkB, k0) + gBk;
+            const unsigned sa = sbase + (unsigned)(stage * stage_elems * sizeof(R2)), sb = sa + (unsigned)(nA * LD * sizeof(R2));
+            for (int r = r0; r < nA; r += RSTEP) {
+                const R2* src = Au + t.off_a[r] + gA0;
+                const unsigned dst = sa + (unsigned)((r * LD + kk) * sizeof(R2));
+                if constexpr (sizeof(R2) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+                else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
+            for (int r = r0; r < nB; r += RSTEP) {
+                const R2* src = Bu + t.off_b[r] + gB0;
+                const unsigned dst = sb + (unsigned)((r * LD + kk) * sizeof(R2));
+                if constexpr (sizeof(R2) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+                else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
+        };
+        R2 acc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { acc[q].x = 0; acc[q].y = 0; }
+        __syncthreads();                               // the previous row's last chunk is consumed
+        if ((long long)blockIdx.x < nchunks) issue(blockIdx.x, 0);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        int stage = 0;
+        for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x, stage ^= 1) {
+            if (ch + gridDim.x < nchunks) issue(ch + gridDim.x, stage ^ 1);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncthreads();
+            const R2* sA = sbuf + stage * stage_elems;
+            const R2* sB = sA + nA * LD;
+            const R2 *a0 = sA + ia * LD, *a1 = a0 + LD, *b0 = sB + ib * LD, *b1 = b0 + LD;
+#pragma unroll 4
+            for (int k = grp; k < KT; k += ngrp) {
+                const R2 x0 = a0[k], x1 = a1[k], y0 = b0[k], y1 = b1[k];
+                kmac(acc[0], x0, y0); kmac(acc[1], x1, y0); kmac(acc[2], x0, y1); kmac(acc[3], x1, y1);
+            }
+            __syncthreads();                           // this stage is free for the chunk after next
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = t.grid_c[(ia + (q & 1)) * nB + ib + (q >> 1)];
+            R2* dst = C + u * p.sUC + kseg(p.sClo, p.nsClo, (unsigned long long)c);
+            atomicAdd(&dst->x, acc[q].x);
+            atomicAdd(&dst->y, acc[q].y);
+        }
+    }
+}
+
+const void* kreduce_grid_func(int dtype) {
+    return dtype == 0 ? (const void*)&kreduce_grid_kernel<float2> : (const void*)&kreduce_grid_kernel<double2>;
+}
+
 const void* kreduce_tile_func(int dtype) {
     return dtype == 0 ? (const void*)&kreduce_tile_kernel<float2> : (const void*)&kreduce_tile_kernel<double2>;
 }
@@ -154,21 +232,30 @@ bigsmall_kernel(const __grid_constant__ BigSmallParams p) {
         __syncthreads();
         const R2* Au = A + u * p.sUbig + a_lo;
         R2* Cu = C + u * p.sUC + c_lo;
+        // four elements of the big operand per round; the next round's loads -- the first round of the CTA's NEXT block
+        // of positions after the last one -- are issued before this round's FMAs, so loads stay in flight across blocks
+        R2 a[4], an[4];
+        const R2* Ab = Au + kseg(p.tA, p.ntA, (unsigned long long)blockIdx.x << 8);
+        if ((long long)blockIdx.x < n_blk) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[q] = (q < KK) ? __ldg(Ab + p.aK[q]) : R2{0, 0};
+        }
         for (long long blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
-            const unsigned long long thi = (unsigned long long)blk << 8;
-            const R2* Ab = Au + kseg(p.tA, p.ntA, thi);
-            R2* Cb = Cu + kseg(p.tC, p.ntC, thi);
+            R2* Cb = Cu + kseg(p.tC, p.ntC, (unsigned long long)blk << 8);
             const R2* sBh = sB + (int)(blk & ((1 << p.nNhi) - 1)) * (KK * NN);
+            const long long nxt = blk + gridDim.x;
+            const R2* Anext = Au + kseg(p.tA, p.ntA, (unsigned long long)(nxt < n_blk ? nxt : blk) << 8);
             R2 acc[NN];
 #pragma unroll
             for (int n = 0; n < NN; ++n) { acc[n].x = 0; acc[n].y = 0; }
-            // four elements of the big operand per round, the next round's loads issued before this round's FMAs
-            R2 a[4], an[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) a[q] = (q < KK) ? __ldg(Ab + p.aK[q]) : R2{0, 0};
             for (int k0 = 0; k0 < KK; k0 += 4) {
+                const bool last = k0 + 4 >= KK;
+                const R2* src = last ? Anext : Ab;
+                const int kb = last ? 0 : k0 + 4;
+                if (!last || nxt < n_blk) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) an[q] = (k0 + 4 + q < KK) ? __ldg(Ab + p.aK[k0 + 4 + q]) : R2{0, 0};
+                    for (int q = 0; q < 4; ++q) an[q] = (kb + q < KK) ? __ldg(src + p.aK[kb + q]) : R2{0, 0};
+                }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (k0 + q >= KK) break;
@@ -179,6 +266,7 @@ bigsmall_kernel(const __grid_constant__ BigSmallParams p) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) a[q] = an[q];
             }
+            Ab = Anext;
 #pragma unroll
             for (int n = 0; n < NN; ++n) Cb[p.cN[n]] = acc[n];
         }

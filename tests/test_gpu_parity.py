@@ -434,7 +434,16 @@ def test_tiled_split_k_reduction(gpu, dtype, nk, nm, nn):
     got = g.amplitudes(bs)
     prof = g.profile_dump(os.path.join(tempfile.mkdtemp(), "p.json"))
     o = [o for v in prof["variants"] for o in v["ops"] if o["name"] == "c"][0]
-    assert o["nK"] == nk and o["nC"] == nm + nn and o["kernel"] == "kreduce_tile", o
+    assert o["nK"] == nk and o["nC"] == nm + nn and o["kernel"] == "kreduce_grid", o     # 2 x 2 outputs per thread, cp.async ring
+    os.environ["QXB_KRED_GRID"] = "0"                                                      # the one-output-per-thread variant
+    try:
+        g1 = Graph.from_dsl(txt, data, dtype).compile(profile=True, row_programs=False)
+        got1 = g1.amplitudes(bs)
+        o1 = [o for v in g1.profile_dump(os.path.join(tempfile.mkdtemp(), "p.json"))["variants"] for o in v["ops"] if o["name"] == "c"][0]
+    finally:
+        del os.environ["QXB_KRED_GRID"]
+    assert o1["kernel"] == "kreduce_tile", o1
+    assert np.max(np.abs(got1 - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 5e-5)
     auto = Graph.from_dsl(txt, data, dtype).compile().amplitudes(bs)                    # whatever the auto mode picks
     assert np.max(np.abs(auto - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 5e-5)
     assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 5e-5)
