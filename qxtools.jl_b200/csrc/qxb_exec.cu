@@ -569,13 +569,27 @@ Node contract_node(const RunCtx& c, int i) {
                 q.big = a_big ? p.A : p.B; q.small_ = a_big ? p.B : p.A; q.C = p.C;
                 q.sUbig = a_big ? p.sUA : p.sUB; q.sUsmall = a_big ? p.sUB : p.sUA; q.sUC = p.sUC;
                 q.U = p.U;
-                n.func = bf; n.kname = "bigsmall";
+                // TMA variant: the 256 positions of a CTA are one contiguous run of the big operand at every k
+                const size_t small_pad = (small_bytes + 15) & ~(size_t)15;
+                const int stages = (int)std::min<size_t>(3, (110 * 1024 - small_pad - 64) / kBigSmallStageBytes);
+                const void* tf = (knob(0, "QXB_BIGSMALL_TMA", 1) != 0 && q.U == 1 && stages >= 2 && q.tA[0].src == 0 && q.tA[0].dst == 0 &&
+                                  q.tA[0].len >= 8 && (uintptr_t)q.big % 16 == 0) ? bigsmall_tma_func(g->dtype, nlo) : nullptr;
                 n.block = dim3(kThreads);
-                n.smem = small_bytes;
-                if (first_use(n.func))
-                    CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-                n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(q.n_pos >> 8, cap * 4)));
-                n.arg(q);
+                if (tf) {
+                    n.func = tf; n.kname = "bigsmall_tma";
+                    n.smem = (size_t)stages * kBigSmallStageBytes + small_pad + 8 * (size_t)stages;
+                    if (first_use(n.func))
+                        CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+                    n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(q.n_pos >> 8, (long long)g_num_sms * 2)));
+                    n.arg(q); n.arg(stages);
+                } else {
+                    n.func = bf; n.kname = "bigsmall";
+                    n.smem = small_bytes;
+                    if (first_use(n.func))
+                        CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                    n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(q.n_pos >> 8, cap * 4)));
+                    n.arg(q);
+                }
                 n.variant = c.variant_key; n.op = i;
                 const double u = (double)p.U;
                 n.flops = 8.0 * op.macs_per_amp * u;
@@ -658,6 +672,34 @@ Node contract_node(const RunCtx& c, int i) {
         if (p.nK >= 12 && p.U <= 64 && !g->opts.no_gemm && knob(0, "QXB_KRED_TILE", 1) != 0) {
             KredTile kt;
             memset(&kt, 0, sizeof(kt));
+            // The K chunk a CTA stages = the low kKredTileKBits bits of the k index.  The two operands usually store the
+            // K bits in different orders (one of them can be scrambled: every 8-byte element of a chunk in its own 32-byte
+            // sector, 4x over-fetch).  Re-number k so that the chunk bits are the K bits sitting lowest in EITHER operand
+            // (sorted by the lower of the two address positions): both operands then read whole sectors.
+            if (knob(0, "QXB_KRED_KORDER", 1) != 0 && p.nK <= kMaxKSeg) {
+                std::vector<int> posA(p.nK, 0), posB(p.nK, 0), order(p.nK);
+                for (auto& sg : op.segKA) for (int b = 0; b < sg.len; ++b) posA[sg.src + b] = sg.dst + b;
+                for (auto& sg : op.segKB) for (int b = 0; b < sg.len; ++b) posB[sg.src + b] = sg.dst + b;
+                for (int b = 0; b < p.nK; ++b) order[b] = b;
+                std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+                    return std::min(posA[x], posB[x]) < std::min(posA[y], posB[y]);
+                });
+                std::vector<int> perm(order.begin(), order.begin() + kKredTileKBits), rest(order.begin() + kKredTileKBits, order.end());
+                std::sort(perm.begin(), perm.end(), [&](int x, int y) { return posA[x] < posA[y]; });   // staging threads walk A ascending
+                std::sort(rest.begin(), rest.end());
+                perm.insert(perm.end(), rest.begin(), rest.end());
+                auto rebuild = [&](const std::vector<int>& pos, DSeg* dst) {
+                    int cnt = 0;
+                    for (int j = 0; j < p.nK; ++j) {
+                        const int d = pos[perm[j]];
+                        if (cnt > 0 && dst[cnt - 1].src + dst[cnt - 1].len == j && dst[cnt - 1].dst + dst[cnt - 1].len == d) ++dst[cnt - 1].len;
+                        else dst[cnt++] = DSeg{(unsigned char)j, (unsigned char)d, 1, 0};
+                    }
+                    return cnt;
+                };
+                p.nkA = rebuild(posA, p.kA);
+                p.nkB = rebuild(posB, p.kB);
+            }
             std::map<long long, int> ra, rb;
             bool ok = true;
             for (int cc = 0; cc < (1 << p.nC) && ok; ++cc) {

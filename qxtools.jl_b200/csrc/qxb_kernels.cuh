@@ -132,6 +132,11 @@ struct BigSmallParams {
     int bH[256];                       // N bits beyond the register tile -> offset in the small operand
 };
 const void* bigsmall_func(int dtype, int n_bits);
+// TMA variant (U == 1, the 8 thread bits of the position index = the 8 lowest address bits of the big operand): second
+// kernel argument = number of 32 KB stages; dynamic shared memory = stages * kBigSmallStageBytes + small operand
+// (rounded up to 16 B) + 8 B per stage (mbarriers)
+constexpr int kBigSmallStageBytes = 32 * 1024;
+const void* bigsmall_tma_func(int dtype, int n_bits);
 // measured FMA-pipe peak of the current device in TFLOP/s (dtype 0: FFMA, 1: DFMA), see qxb_kred.cu
 double fma_peak_tflops(int dtype, int num_sms, cudaStream_t st);
 // outleaf:  (R2* base, const OutLeafDesc* d, const unsigned char* bits, int n_outputs, long long amp0, long long n)

@@ -208,7 +208,7 @@ namespace qxb {
 // one position of the big operand's free index space and ALL 2^N outputs of it: it reads its 2^K elements of the big
 // operand once (coalesced along the low bits, all loads in flight), multiplies by the small operand from shared memory
 // ([k][n], broadcast reads) and writes 2^N outputs (coalesced).  HBM traffic = |big| + |C|, once.
-template <typename R2, int NN>
+template <typename R2, int NN, int RK>
 __global__ void __launch_bounds__(256)
 bigsmall_kernel(const __grid_constant__ BigSmallParams p) {
     extern __shared__ __align__(16) unsigned char bs_smem[];
@@ -232,13 +232,13 @@ bigsmall_kernel(const __grid_constant__ BigSmallParams p) {
         __syncthreads();
         const R2* Au = A + u * p.sUbig + a_lo;
         R2* Cu = C + u * p.sUC + c_lo;
-        // four elements of the big operand per round; the next round's loads -- the first round of the CTA's NEXT block
+        // RK elements of the big operand per round (enough bytes in flight per SM to cover the HBM latency); the next round's loads -- the first round of the CTA's NEXT block
         // of positions after the last one -- are issued before this round's FMAs, so loads stay in flight across blocks
-        R2 a[4], an[4];
+        R2 a[RK], an[RK];
         const R2* Ab = Au + kseg(p.tA, p.ntA, (unsigned long long)blockIdx.x << 8);
         if ((long long)blockIdx.x < n_blk) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) a[q] = (q < KK) ? __ldg(Ab + p.aK[q]) : R2{0, 0};
+            for (int q = 0; q < RK; ++q) a[q] = (q < KK) ? __ldg(Ab + p.aK[q]) : R2{0, 0};
         }
         for (long long blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
             R2* Cb = Cu + kseg(p.tC, p.ntC, (unsigned long long)blk << 8);
@@ -248,23 +248,23 @@ bigsmall_kernel(const __grid_constant__ BigSmallParams p) {
             R2 acc[NN];
 #pragma unroll
             for (int n = 0; n < NN; ++n) { acc[n].x = 0; acc[n].y = 0; }
-            for (int k0 = 0; k0 < KK; k0 += 4) {
-                const bool last = k0 + 4 >= KK;
+            for (int k0 = 0; k0 < KK; k0 += RK) {
+                const bool last = k0 + RK >= KK;
                 const R2* src = last ? Anext : Ab;
-                const int kb = last ? 0 : k0 + 4;
+                const int kb = last ? 0 : k0 + RK;
                 if (!last || nxt < n_blk) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) an[q] = (kb + q < KK) ? __ldg(src + p.aK[kb + q]) : R2{0, 0};
+                    for (int q = 0; q < RK; ++q) an[q] = (kb + q < KK) ? __ldg(src + p.aK[kb + q]) : R2{0, 0};
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < RK; ++q) {
                     if (k0 + q >= KK) break;
                     const R2* bk = sBh + (k0 + q) * NN;
 #pragma unroll
                     for (int n = 0; n < NN; ++n) kmac(acc[n], a[q], bk[n]);
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) a[q] = an[q];
+                for (int q = 0; q < RK; ++q) a[q] = an[q];
             }
             Ab = Anext;
 #pragma unroll
@@ -273,22 +273,126 @@ bigsmall_kernel(const __grid_constant__ BigSmallParams p) {
     }
 }
 
-const void* bigsmall_func(int dtype, int n_bits) {
+// Same node, the big operand through 1-D TMA bulk copies: when the 8 thread bits of the position index are the 8 lowest
+// address bits of the big operand, the 256 positions of a CTA at one k are one contiguous 2 KB (4 KB) run, and a stage
+// of 16 (8) k values is 32 KB brought in by one elected thread with mbarrier complete_tx.  Three stages per CTA and two
+// CTAs per SM keep ~190 KB of reads in flight per SM without holding them in registers (the register version has
+// 24 - 32 KB in flight and ran at 4.4 TB/s on the 2^4 x 2^4 nodes: FMA time + HBM time, not overlapped).
+namespace {
+__device__ __forceinline__ unsigned bs_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bs_mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+}  // namespace
+
+template <typename R2, int NN>
+__global__ void __launch_bounds__(256, 2)
+bigsmall_tma_kernel(const __grid_constant__ BigSmallParams p, const int n_stages) {
+    constexpr int KC = kBigSmallStageBytes / (256 * (int)sizeof(R2));     // k values per stage
+    extern __shared__ __align__(128) unsigned char bs_smem[];
+    const int KK = 1 << p.nK;
+    const int kcn = KK < KC ? KK : KC, nkc = KK / kcn;                    // k values per fill, fills per block of positions
+    const int n_small = (KK * NN) << p.nNhi;
+    R2* sB = reinterpret_cast<R2*>(bs_smem + (size_t)n_stages * kBigSmallStageBytes);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(bs_smem + (size_t)n_stages * kBigSmallStageBytes +
+                                                                     (((size_t)n_small * sizeof(R2) + 15) & ~(size_t)15));
+    const R2* __restrict__ A = reinterpret_cast<const R2*>(p.big);
+    const R2* __restrict__ B = reinterpret_cast<const R2*>(p.small_);
+    R2* __restrict__ C = reinterpret_cast<R2*>(p.C);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bs_u32(bars + s)), "r"(1u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < n_small; i += 256) {
+        const int n = i % NN, k = (i / NN) & (KK - 1), nh = i / (NN * KK);
+        sB[i] = __ldg(B + p.bK[k] + p.bN[n] + p.bH[nh]);
+    }
+    __syncthreads();
+    const long long n_blk = p.n_pos >> 8;
+    const long long my_blocks = (long long)blockIdx.x < n_blk ? (n_blk - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long n_fill = my_blocks * nkc;
+    const unsigned run_bytes = 256u * (unsigned)sizeof(R2);
+    auto issue = [&](long long f) {                                       // thread 0
+        const long long blk = blockIdx.x + (f / nkc) * (long long)gridDim.x;
+        const int kc = (int)(f % nkc), s = (int)(f % n_stages);
+        const R2* Ab = A + kseg(p.tA, p.ntA, (unsigned long long)blk << 8);
+        const unsigned bar = bs_u32(bars + s), dst = bs_u32(bs_smem + (size_t)s * kBigSmallStageBytes);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(run_bytes * (unsigned)kcn) : "memory");
+        for (int q = 0; q < kcn; ++q)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst + (unsigned)q * run_bytes), "l"(Ab + p.aK[kc * kcn + q]), "r"(run_bytes), "r"(bar) : "memory");
+    };
+    if (tid == 0)
+        for (long long f = 0; f < n_fill && f < n_stages; ++f) issue(f);
+    const long long c_lo = kseg(p.tC, p.ntC, (unsigned long long)tid);
+    R2 acc[NN];
+    for (long long f = 0; f < n_fill; ++f) {
+        const long long blk = blockIdx.x + (f / nkc) * (long long)gridDim.x;
+        const int kc = (int)(f % nkc), s = (int)(f % n_stages);
+        if (kc == 0) {
+#pragma unroll
+            for (int n = 0; n < NN; ++n) { acc[n].x = 0; acc[n].y = 0; }
+        }
+        bs_mbar_wait(bs_u32(bars + s), (unsigned)((f / n_stages) & 1));
+        const R2* st = reinterpret_cast<const R2*>(bs_smem + (size_t)s * kBigSmallStageBytes) + tid;
+        const R2* bk = sB + (int)(blk & ((1 << p.nNhi) - 1)) * (KK * NN) + kc * kcn * NN;
+#pragma unroll 4
+        for (int q = 0; q < kcn; ++q) {
+            const R2 a = st[q * 256];
+#pragma unroll
+            for (int n = 0; n < NN; ++n) kmac(acc[n], a, bk[q * NN + n]);
+        }
+        __syncthreads();                                                  // every thread is done with stage s
+        if (tid == 0 && f + n_stages < n_fill) issue(f + n_stages);
+        if (kc == nkc - 1) {
+            R2* Cb = C + c_lo + kseg(p.tC, p.ntC, (unsigned long long)blk << 8);
+#pragma unroll
+            for (int n = 0; n < NN; ++n) Cb[p.cN[n]] = acc[n];
+        }
+    }
+}
+
+const void* bigsmall_tma_func(int dtype, int n_bits) {
     if (dtype == 0) {
         switch (n_bits) {
-        case 1: return (const void*)&bigsmall_kernel<float2, 2>;
-        case 2: return (const void*)&bigsmall_kernel<float2, 4>;
-        case 3: return (const void*)&bigsmall_kernel<float2, 8>;
-        case 4: return (const void*)&bigsmall_kernel<float2, 16>;
-        case 5: return (const void*)&bigsmall_kernel<float2, 32>;
+        case 1: return (const void*)&bigsmall_tma_kernel<float2, 2>;
+        case 2: return (const void*)&bigsmall_tma_kernel<float2, 4>;
+        case 3: return (const void*)&bigsmall_tma_kernel<float2, 8>;
+        case 4: return (const void*)&bigsmall_tma_kernel<float2, 16>;
+        case 5: return (const void*)&bigsmall_tma_kernel<float2, 32>;
         default: return nullptr;
         }
     }
     switch (n_bits) {
-    case 1: return (const void*)&bigsmall_kernel<double2, 2>;
-    case 2: return (const void*)&bigsmall_kernel<double2, 4>;
-    case 3: return (const void*)&bigsmall_kernel<double2, 8>;
-    case 4: return (const void*)&bigsmall_kernel<double2, 16>;
+    case 1: return (const void*)&bigsmall_tma_kernel<double2, 2>;
+    case 2: return (const void*)&bigsmall_tma_kernel<double2, 4>;
+    case 3: return (const void*)&bigsmall_tma_kernel<double2, 8>;
+    case 4: return (const void*)&bigsmall_tma_kernel<double2, 16>;
+    default: return nullptr;
+    }
+}
+
+const void* bigsmall_func(int dtype, int n_bits) {
+    if (dtype == 0) {
+        switch (n_bits) {
+        case 1: return (const void*)&bigsmall_kernel<float2, 2, 8>;
+        case 2: return (const void*)&bigsmall_kernel<float2, 4, 8>;
+        case 3: return (const void*)&bigsmall_kernel<float2, 8, 8>;
+        case 4: return (const void*)&bigsmall_kernel<float2, 16, 8>;
+        case 5: return (const void*)&bigsmall_kernel<float2, 32, 4>;
+        default: return nullptr;
+        }
+    }
+    switch (n_bits) {
+    case 1: return (const void*)&bigsmall_kernel<double2, 2, 8>;
+    case 2: return (const void*)&bigsmall_kernel<double2, 4, 8>;
+    case 3: return (const void*)&bigsmall_kernel<double2, 8, 4>;
+    case 4: return (const void*)&bigsmall_kernel<double2, 16, 4>;
     default: return nullptr;
     }
 }

@@ -371,8 +371,9 @@ def test_gemm_shaped_node_random(gpu, dtype, gemm_mode, seed):
 
 
 @pytest.mark.parametrize("dtype", ["c64", "c32"])
+@pytest.mark.parametrize("aligned", [False, True])
 @pytest.mark.parametrize("nk,nn,big_first", [(3, 1, True), (4, 4, True), (2, 3, False), (5, 2, False), (4, 5, True), (3, 7, True), (4, 6, False)])
-def test_big_times_small_streaming_node(gpu, dtype, nk, nn, big_first):
+def test_big_times_small_streaming_node(gpu, dtype, nk, nn, big_first, aligned):
     """A 2^(17 + nk)-element operand against a 2^(nk + nn)-element one (per bitstring), shuffled mode orders, either
     operand order: the streaming kernel of csrc/qxb_kred.cu (a thread owns one position of the big operand and all
     min(2^nn, 2^4 or 2^5) outputs, further N bits go to the CTA index) -- the shape of the 24 dominant nodes of a Sycamore-53 depth-12 slice."""
@@ -383,6 +384,12 @@ def test_big_times_small_streaming_node(gpu, dtype, nk, nn, big_first):
     la = list(rng.permutation(ks + ms)); lb = list(rng.permutation(ks + ns)) + [o_lab]
     lb2 = [x for x in lb if x != o_lab]
     lc = list(rng.permutation(ms + ns))
+    if aligned:
+        # the 9 fastest modes of the big operand are also the 9 fastest modes of the result: a CTA's 256 positions are one
+        # contiguous run at every k, the kernel brings them in by TMA bulk copies (bigsmall_tma)
+        head = ms[:9]
+        la = head + [x for x in la if x not in head]
+        lc = head + [x for x in lc if x not in head]
     A = (rng.normal(size=(2,) * len(la)) + 1j * rng.normal(size=(2,) * len(la))) / 4
     B = (rng.normal(size=(2,) * len(lb)) + 1j * rng.normal(size=(2,) * len(lb))) / 4
     W = (rng.normal(size=(2,) * len(lc)) + 1j * rng.normal(size=(2,) * len(lc))) / 64
@@ -394,7 +401,7 @@ def test_big_times_small_streaming_node(gpu, dtype, nk, nn, big_first):
            f"ncon c {j(lc)} {pair}\n"
            f"ncon z 0 c {j(lc)} w {j(lc)}\nsave output z\n")
     data = {"dA": A, "dB": B, "dW": W}
-    bs = ["0", "1", "+"]
+    bs = ["-"] if aligned else ["0", "1", "+"]               # the TMA variant takes single-row launches
     ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
     import os, tempfile
     g = Graph.from_dsl(txt, data, dtype).compile(profile=True, row_programs=False)
@@ -402,7 +409,8 @@ def test_big_times_small_streaming_node(gpu, dtype, nk, nn, big_first):
     assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 2e-5)
     prof = g.profile_dump(os.path.join(tempfile.mkdtemp(), "p.json"))
     kern = [o["kernel"] for v in prof["variants"] for o in v["ops"] if o["name"] == "c"][0]
-    assert kern == "bigsmall", kern
+    assert kern in ("bigsmall", "bigsmall_tma"), kern
+    assert kern == ("bigsmall_tma" if aligned else "bigsmall"), kern
 
 
 @pytest.mark.parametrize("dtype", ["c64", "c32"])
