@@ -90,7 +90,7 @@ int         qxb_shutdown(void);
 /* Launch on an existing CUDA stream (a cudaStream_t, e.g. torch's current stream); NULL = library stream. */
 int         qxb_set_stream(void* cuda_stream);
 int         qxb_device_synchronize(void);
-/* Measured peak of the FMA pipe of the current device in TFLOP/s (QXB_C32: FFMA, QXB_C64: DFMA; 2 flops per FMA, no
+/* Measured peak of the FMA pipe of the current device in TFLOP/s (QXB_C32: FFMA, QXB_C64: DFMA, 2: packed FFMA2; 2 flops per FMA, no
  * memory traffic): the roofline denominator for the fused launches whose intermediates live in shared memory. */
 int         qxb_fma_peak(int dtype, double* tflops);
 

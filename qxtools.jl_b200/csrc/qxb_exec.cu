@@ -518,9 +518,10 @@ Node contract_node(const RunCtx& c, int i) {
         const auto& kSm = a_big ? op.segKB : op.segKA;
         const int nN = a_big ? op.n_n : op.n_m;
         const double big_elems = a_big ? op.elems_a : op.elems_b;
-        const int max_lo = g->dtype == QXB_C32 ? 5 : 4;
+        const bool packed = g->dtype == QXB_C32 && knob(0, "QXB_BIGSMALL_FFMA2", 1) != 0;
+        const int max_lo = (g->dtype == QXB_C32 && !packed) ? 5 : 4;
         const int nlo = nN <= max_lo ? nN : 4, nhi = nN - nlo;
-        const void* bf = nN >= 1 ? bigsmall_func(g->dtype, nlo) : nullptr;
+        const void* bf = nN >= 1 ? bigsmall_func(g->dtype, nlo, packed) : nullptr;
         const size_t small_bytes = ((size_t)1 << (op.nK + nN)) * g->es();
         if (bf && big_elems >= std::ldexp(1.0, knob(0, "QXB_BIGSMALL_MIN_BITS", 20)) && small_bytes <= 64 * 1024 && nhi <= 8 &&
             TS.span_bits <= 24 && TB.span_bits <= 40 && op.nK + nN >= 3 && p.nC - nN >= 8) {
@@ -572,7 +573,7 @@ Node contract_node(const RunCtx& c, int i) {
                 // TMA variant: the 256 positions of a CTA are one contiguous run of the big operand at every k
                 const size_t small_pad = (small_bytes + 15) & ~(size_t)15;
                 const int stages = (int)std::min<size_t>(3, (110 * 1024 - small_pad - 64) / kBigSmallStageBytes);
-                const void* tf = (knob(0, "QXB_BIGSMALL_TMA", 1) != 0 && q.U == 1 && stages >= 2 && q.tA[0].src == 0 && q.tA[0].dst == 0 &&
+                const void* tf = (knob(0, "QXB_BIGSMALL_TMA", 0) != 0 && q.U == 1 && stages >= 2 && q.tA[0].src == 0 && q.tA[0].dst == 0 &&
                                   q.tA[0].len >= 8 && (uintptr_t)q.big % 16 == 0) ? bigsmall_tma_func(g->dtype, nlo) : nullptr;
                 n.block = dim3(kThreads);
                 if (tf) {
@@ -729,7 +730,8 @@ Node contract_node(const RunCtx& c, int i) {
                 }
                 if (grid_ok) smem *= 2;
                 if (smem <= 96 * 1024) {
-                    n.func = grid_ok ? kreduce_grid_func(g->dtype) : kreduce_tile_func(g->dtype);
+                    const int gt = (kt.n_rows_a % 4 == 0 && kt.n_rows_b % 4 == 0) ? 4 : 2;
+                    n.func = grid_ok ? kreduce_grid_func(g->dtype, gt) : kreduce_tile_func(g->dtype);
                     n.kname = grid_ok ? "kreduce_grid" : "kreduce_tile";
                     n.smem = smem;
                     if (smem > 48 * 1024 && first_use(n.func))
@@ -1645,7 +1647,7 @@ int qxb_set_stream(void* s) {
 int qxb_fma_peak(int dtype, double* tflops) {
     return guard([&] {
         if (!tflops) throw Error(QXB_ERR_ARG, "null argument");
-        if (dtype != QXB_C32 && dtype != QXB_C64) throw Error(QXB_ERR_ARG, "dtype must be QXB_C32 or QXB_C64");
+        if (dtype != QXB_C32 && dtype != QXB_C64 && dtype != 2) throw Error(QXB_ERR_ARG, "dtype must be QXB_C32, QXB_C64 or 2 (packed FFMA2)");
         ensure_init();
         *tflops = fma_peak_tflops(dtype, g_num_sms, stream());
         CUDA_OK(cudaGetLastError());

@@ -111,10 +111,10 @@ struct KredTile {
     unsigned char grid_c[256];                     // kreduce_grid_kernel: (row of A) * n_rows_b + (row of B) -> output c
 };
 const void* kreduce_tile_func(int dtype);
-// Same staging, for outputs that form the full grid rows(A) x rows(B) (both even): a thread owns a 2 x 2 block of outputs
-// (half the shared-memory reads per FMA) and the K chunks arrive through a two-stage cp.async ring, so the loads of the
+// Same staging, for outputs that form the full grid rows(A) x rows(B) (both even): a thread owns a 2 x 2 or 4 x 4 block of outputs
+// (a half / a quarter of the shared-memory reads per FMA) and the K chunks arrive through a two-stage cp.async ring, so the loads of the
 // next chunk overlap the FMAs of this one.  Dynamic shared memory = 2 * (n_rows_a + n_rows_b) * (kKredTileK + 1) * sizeof(element)
-const void* kreduce_grid_func(int dtype);
+const void* kreduce_grid_func(int dtype, int tile);       // tile = 2 or 4 (rows of A and of B both multiples of it)
 // "big x small" streaming nodes (qxb_kred.cu): a thread owns one position of the big operand's free index space and all
 // 2^n_bits outputs of it (further N bits are enumerated by the CTA index).  Arguments (BigSmallParams); dynamic shared
 // memory = the whole small operand
@@ -131,7 +131,7 @@ struct BigSmallParams {
     int bK[32], bN[32];                // k, n -> offset in the small operand
     int bH[256];                       // N bits beyond the register tile -> offset in the small operand
 };
-const void* bigsmall_func(int dtype, int n_bits);
+const void* bigsmall_func(int dtype, int n_bits, bool packed);     // packed: ComplexF32 through FFMA2 (n_bits <= 4)
 // TMA variant (U == 1, the 8 thread bits of the position index = the 8 lowest address bits of the big operand): second
 // kernel argument = number of 32 KB stages; dynamic shared memory = stages * kBigSmallStageBytes + small operand
 // (rounded up to 16 B) + 8 B per stage (mbarriers)

@@ -70,33 +70,48 @@ kreduce_tile_kernel(const __grid_constant__ OpParams p, const __grid_constant__ 
     }
 }
 
-template <typename R2>
+// chunk base offsets: one segment of the K address map per lane of warp 0, OR-reduced (the maps of a scrambled operand
+// have 20+ segments; evaluated by every thread per chunk they were most of the kernel's instructions)
+__device__ __forceinline__ long long kseg_warp(const DSeg* sgs, int n, unsigned long long x, int lane) {
+    unsigned long long v = 0;
+    if (lane < n) { const DSeg g = sgs[lane]; v = ((x >> g.src) & ((1ull << g.len) - 1ull)) << g.dst; }
+    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v), hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+    return (long long)(((unsigned long long)hi << 32) | lo);
+}
+
+template <typename R2, int T>
 __global__ void __launch_bounds__(kThreads)
 kreduce_grid_kernel(const __grid_constant__ OpParams p, const __grid_constant__ KredTile t) {
     constexpr int KT = kKredTileK;
     constexpr int LD = KT + 1;
     extern __shared__ __align__(16) unsigned char kred_smem[];
+    __shared__ long long s_off[2][2];                  // [slot][A, B]: base offsets of the chunk issued next
     const int nA = t.n_rows_a, nB = t.n_rows_b;
     const int stage_elems = (nA + nB) * LD;
     R2* sbuf = reinterpret_cast<R2*>(kred_smem);
     const R2* __restrict__ A = reinterpret_cast<const R2*>(p.A);
     const R2* __restrict__ B = reinterpret_cast<const R2*>(p.B);
     R2* __restrict__ C = reinterpret_cast<R2*>(p.C);
-    const int tid = threadIdx.x;
-    const int n_tiles = (nA >> 1) * (nB >> 1);        // a power of two <= 256
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n_tiles = (nA / T) * (nB / T);           // a power of two <= 256
     const int tile = tid & (n_tiles - 1), grp = tid / n_tiles, ngrp = kThreads / n_tiles;
-    const int ia = (tile % (nA >> 1)) * 2, ib = (tile / (nA >> 1)) * 2;
+    const int ia = (tile % (nA / T)) * T, ib = (tile / (nA / T)) * T;
     const int kk = tid % KT, r0 = tid / KT;
     constexpr int RSTEP = kThreads / KT;
     const long long gAk = kseg(p.kA, p.nkA, (unsigned long long)kk), gBk = kseg(p.kB, p.nkB, (unsigned long long)kk);
     const long long nchunks = 1ll << (p.nK - kKredTileKBits);
+    const long long G = gridDim.x;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(sbuf);
     for (long long u = 0; u < p.U; ++u) {
         const R2* Au = A + u * p.sUA;
         const R2* Bu = B + u * p.sUB;
-        auto issue = [&](long long ch, int stage) {
+        auto offsets = [&](long long ch, int slot) {   // warp 0
             const unsigned long long k0 = (unsigned long long)ch << kKredTileKBits;
-            const long long gA0 = kseg(p.kA, p.nkA, k0) + gAk, gB0 = kseg(p.kB, p.nkB, k0) + gBk;
+            const long long a = kseg_warp(p.kA, p.nkA, k0, lane), b = kseg_warp(p.kB, p.nkB, k0, lane);
+            if (lane == 0) { s_off[slot][0] = a; s_off[slot][1] = b; }
+        };
+        auto issue = [&](int slot, int stage) {
+            const long long gA0 = s_off[slot][0] + gAk, gB0 = s_off[slot][1] + gBk;   // disjoint bits
             const unsigned sa = sbase + (unsigned)(stage * stage_elems * sizeof(R2)), sb = sa + (unsigned)(nA * LD * sizeof(R2));
             for (int r = r0; r < nA; r += RSTEP) {
                 const R2* src = Au + t.off_a[r] + gA0;
@@ -111,32 +126,40 @@ kreduce_grid_kernel(const __grid_constant__ OpParams p, const __grid_constant__ 
                 else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
             }
         };
-        R2 acc[4];
+        R2 acc[T * T];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { acc[q].x = 0; acc[q].y = 0; }
-        __syncthreads();                               // the previous row's last chunk is consumed
-        if ((long long)blockIdx.x < nchunks) issue(blockIdx.x, 0);
+        for (int q = 0; q < T * T; ++q) { acc[q].x = 0; acc[q].y = 0; }
+        __syncthreads();                               // the previous row's last chunk and offsets are consumed
+        if (tid < 32) { offsets(blockIdx.x, 0); offsets(blockIdx.x + G, 1); }
+        __syncthreads();
+        if ((long long)blockIdx.x < nchunks) issue(0, 0);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        int stage = 0;
-        for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x, stage ^= 1) {
-            if (ch + gridDim.x < nchunks) issue(ch + gridDim.x, stage ^ 1);
+        int it = 0;
+        for (long long ch = blockIdx.x; ch < nchunks; ch += G, ++it) {
+            const int stage = it & 1;
+            if (ch + G < nchunks) issue((it + 1) & 1, stage ^ 1);
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 1;" ::: "memory");
             __syncthreads();
-            const R2* sA = sbuf + stage * stage_elems;
-            const R2* sB = sA + nA * LD;
-            const R2 *a0 = sA + ia * LD, *a1 = a0 + LD, *b0 = sB + ib * LD, *b1 = b0 + LD;
-#pragma unroll 4
+            const R2* sA = sbuf + stage * stage_elems + ia * LD;
+            const R2* sB = sbuf + stage * stage_elems + (nA + ib) * LD;
+#pragma unroll 2
             for (int k = grp; k < KT; k += ngrp) {
-                const R2 x0 = a0[k], x1 = a1[k], y0 = b0[k], y1 = b1[k];
-                kmac(acc[0], x0, y0); kmac(acc[1], x1, y0); kmac(acc[2], x0, y1); kmac(acc[3], x1, y1);
+                R2 x[T], y[T];
+#pragma unroll
+                for (int q = 0; q < T; ++q) { x[q] = sA[q * LD + k]; y[q] = sB[q * LD + k]; }
+#pragma unroll
+                for (int j = 0; j < T; ++j)
+#pragma unroll
+                    for (int i = 0; i < T; ++i) kmac(acc[j * T + i], x[i], y[j]);
             }
+            if (tid < 32) offsets(ch + 2 * G, it & 1);  // for the chunk issued in the next iteration
             __syncthreads();                           // this stage is free for the chunk after next
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int c = t.grid_c[(ia + (q & 1)) * nB + ib + (q >> 1)];
+        for (int q = 0; q < T * T; ++q) {
+            const int c = t.grid_c[(ia + (q % T)) * nB + ib + (q / T)];
             R2* dst = C + u * p.sUC + kseg(p.sClo, p.nsClo, (unsigned long long)c);
             atomicAdd(&dst->x, acc[q].x);
             atomicAdd(&dst->y, acc[q].y);
@@ -144,8 +167,9 @@ kreduce_grid_kernel(const __grid_constant__ OpParams p, const __grid_constant__ 
     }
 }
 
-const void* kreduce_grid_func(int dtype) {
-    return dtype == 0 ? (const void*)&kreduce_grid_kernel<float2> : (const void*)&kreduce_grid_kernel<double2>;
+const void* kreduce_grid_func(int dtype, int tile) {
+    if (tile == 4) return dtype == 0 ? (const void*)&kreduce_grid_kernel<float2, 4> : (const void*)&kreduce_grid_kernel<double2, 4>;
+    return dtype == 0 ? (const void*)&kreduce_grid_kernel<float2, 2> : (const void*)&kreduce_grid_kernel<double2, 2>;
 }
 
 const void* kreduce_tile_func(int dtype) {
@@ -172,7 +196,23 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-// TFLOP/s (2 flops per FMA) of the FFMA (dtype 0) or DFMA (dtype 1) pipe: best of 5 timed launches on `st`
+__global__ void __launch_bounds__(256) fma2_peak_kernel(float* out, int iters, float a, float b) {
+    unsigned long long acc[16], av, bv;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bv) : "f"(b));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float x = (float)(threadIdx.x + i); asm("mov.b64 %0, {%1, %1};" : "=l"(acc[i]) : "f"(x)); }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i]) : "l"(av), "l"(bv));
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(acc[i])); s += x + y; }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// TFLOP/s (2 flops per FMA) of the FFMA (dtype 0), DFMA (dtype 1) or packed FFMA2 (dtype 2) pipe: best of 5 timed launches on `st`
 double fma_peak_tflops(int dtype, int num_sms, cudaStream_t st) {
     const int blocks = num_sms * 8, iters = 4096;
     void* buf = nullptr;
@@ -183,12 +223,13 @@ double fma_peak_tflops(int dtype, int num_sms, cudaStream_t st) {
     for (int rep = 0; rep < 6; ++rep) {
         cudaEventRecord(e0, st);
         if (dtype == 0) fma_peak_kernel<float><<<blocks, 256, 0, st>>>((float*)buf, iters, 1.0000001f, 1e-9f);
+        else if (dtype == 2) fma2_peak_kernel<<<blocks, 256, 0, st>>>((float*)buf, iters, 1.0000001f, 1e-9f);
         else fma_peak_kernel<double><<<blocks, 256, 0, st>>>((double*)buf, iters, 1.0000001, 1e-9);
         cudaEventRecord(e1, st);
         cudaEventSynchronize(e1);
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
-        const double tf = 2.0 * 16.0 * iters * (double)blocks * 256.0 / (ms * 1e-3) / 1e12;
+        const double tf = (dtype == 2 ? 2.0 : 1.0) * 2.0 * 16.0 * iters * (double)blocks * 256.0 / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
@@ -208,7 +249,51 @@ namespace qxb {
 // one position of the big operand's free index space and ALL 2^N outputs of it: it reads its 2^K elements of the big
 // operand once (coalesced along the low bits, all loads in flight), multiplies by the small operand from shared memory
 // ([k][n], broadcast reads) and writes 2^N outputs (coalesced).  HBM traffic = |big| + |C|, once.
-template <typename R2, int NN, int RK>
+// Accumulators of one position: NN complex outputs.  ComplexF32 uses the packed FFMA2 (fma.rn.f32x2, sm_100): per output
+// P += (a.x, a.x) * (b.x, b.y) and Q += (a.y, a.y) * (b.x, b.y), result = (P.x - Q.y, P.y + Q.x) -- two issue slots per
+// complex MAC instead of four (the scalar version of this kernel was issue-bound: 0.76 IPC per scheduler with 59 % FFMA,
+// profiles/r2_summary.md), and the small operand needs no swizzled copy.
+template <typename R2, int NN, bool PACK>
+struct BsAcc {
+    R2 acc[NN];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int n = 0; n < NN; ++n) { acc[n].x = 0; acc[n].y = 0; }
+    }
+    __device__ __forceinline__ void mac_row(const R2 a, const R2* bk) {
+#pragma unroll
+        for (int n = 0; n < NN; ++n) kmac(acc[n], a, bk[n]);
+    }
+    __device__ __forceinline__ R2 get(int n) const { return acc[n]; }
+};
+template <int NN>
+struct BsAcc<float2, NN, true> {
+    unsigned long long P[NN], Q[NN];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int n = 0; n < NN; ++n) { P[n] = 0ull; Q[n] = 0ull; }
+    }
+    __device__ __forceinline__ void mac_row(const float2 a, const float2* bk) {
+        unsigned long long ax, ay;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(ax) : "f"(a.x));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(ay) : "f"(a.y));
+        const unsigned long long* b = reinterpret_cast<const unsigned long long*>(bk);
+#pragma unroll
+        for (int n = 0; n < NN; ++n) {
+            const unsigned long long bv = b[n];
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(P[n]) : "l"(ax), "l"(bv));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(Q[n]) : "l"(ay), "l"(bv));
+        }
+    }
+    __device__ __forceinline__ float2 get(int n) const {
+        float px, py, qx, qy;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(px), "=f"(py) : "l"(P[n]));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(qx), "=f"(qy) : "l"(Q[n]));
+        return make_float2(px - qy, py + qx);
+    }
+};
+
+template <typename R2, int NN, int RK, bool PACK>
 __global__ void __launch_bounds__(256)
 bigsmall_kernel(const __grid_constant__ BigSmallParams p) {
     extern __shared__ __align__(16) unsigned char bs_smem[];
@@ -245,9 +330,8 @@ bigsmall_kernel(const __grid_constant__ BigSmallParams p) {
             const R2* sBh = sB + (int)(blk & ((1 << p.nNhi) - 1)) * (KK * NN);
             const long long nxt = blk + gridDim.x;
             const R2* Anext = Au + kseg(p.tA, p.ntA, (unsigned long long)(nxt < n_blk ? nxt : blk) << 8);
-            R2 acc[NN];
-#pragma unroll
-            for (int n = 0; n < NN; ++n) { acc[n].x = 0; acc[n].y = 0; }
+            BsAcc<R2, NN, PACK> acc;
+            acc.clear();
             for (int k0 = 0; k0 < KK; k0 += RK) {
                 const bool last = k0 + RK >= KK;
                 const R2* src = last ? Anext : Ab;
@@ -259,16 +343,14 @@ bigsmall_kernel(const __grid_constant__ BigSmallParams p) {
 #pragma unroll
                 for (int q = 0; q < RK; ++q) {
                     if (k0 + q >= KK) break;
-                    const R2* bk = sBh + (k0 + q) * NN;
-#pragma unroll
-                    for (int n = 0; n < NN; ++n) kmac(acc[n], a[q], bk[n]);
+                    acc.mac_row(a[q], sBh + (k0 + q) * NN);
                 }
 #pragma unroll
                 for (int q = 0; q < RK; ++q) a[q] = an[q];
             }
             Ab = Anext;
 #pragma unroll
-            for (int n = 0; n < NN; ++n) Cb[p.cN[n]] = acc[n];
+            for (int n = 0; n < NN; ++n) Cb[p.cN[n]] = acc.get(n);
         }
     }
 }
@@ -377,22 +459,31 @@ const void* bigsmall_tma_func(int dtype, int n_bits) {
     }
 }
 
-const void* bigsmall_func(int dtype, int n_bits) {
+const void* bigsmall_func(int dtype, int n_bits, bool packed) {
+    if (dtype == 0 && packed) {
+        switch (n_bits) {
+        case 1: return (const void*)&bigsmall_kernel<float2, 2, 8, true>;
+        case 2: return (const void*)&bigsmall_kernel<float2, 4, 8, true>;
+        case 3: return (const void*)&bigsmall_kernel<float2, 8, 8, true>;
+        case 4: return (const void*)&bigsmall_kernel<float2, 16, 4, true>;
+        default: return nullptr;
+        }
+    }
     if (dtype == 0) {
         switch (n_bits) {
-        case 1: return (const void*)&bigsmall_kernel<float2, 2, 8>;
-        case 2: return (const void*)&bigsmall_kernel<float2, 4, 8>;
-        case 3: return (const void*)&bigsmall_kernel<float2, 8, 8>;
-        case 4: return (const void*)&bigsmall_kernel<float2, 16, 8>;
-        case 5: return (const void*)&bigsmall_kernel<float2, 32, 4>;
+        case 1: return (const void*)&bigsmall_kernel<float2, 2, 8, false>;
+        case 2: return (const void*)&bigsmall_kernel<float2, 4, 8, false>;
+        case 3: return (const void*)&bigsmall_kernel<float2, 8, 8, false>;
+        case 4: return (const void*)&bigsmall_kernel<float2, 16, 8, false>;
+        case 5: return (const void*)&bigsmall_kernel<float2, 32, 4, false>;
         default: return nullptr;
         }
     }
     switch (n_bits) {
-    case 1: return (const void*)&bigsmall_kernel<double2, 2, 8>;
-    case 2: return (const void*)&bigsmall_kernel<double2, 4, 8>;
-    case 3: return (const void*)&bigsmall_kernel<double2, 8, 4>;
-    case 4: return (const void*)&bigsmall_kernel<double2, 16, 4>;
+    case 1: return (const void*)&bigsmall_kernel<double2, 2, 8, false>;
+    case 2: return (const void*)&bigsmall_kernel<double2, 4, 8, false>;
+    case 3: return (const void*)&bigsmall_kernel<double2, 8, 4, false>;
+    case 4: return (const void*)&bigsmall_kernel<double2, 16, 4, false>;
     default: return nullptr;
     }
 }

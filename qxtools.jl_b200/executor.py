@@ -401,9 +401,10 @@ def set_stream(stream_ptr: int) -> None:
 
 
 def fma_peak(dtype: str = "c64") -> float:
-    """Measured FMA-pipe peak of the current device in TFLOP/s (``qxb_fma_peak``): FFMA for c32, DFMA for c64."""
+    """Measured FMA-pipe peak of the current device in TFLOP/s (``qxb_fma_peak``): FFMA for c32, DFMA for c64,
+    packed FFMA2 (fma.rn.f32x2) for ``"c32x2"``."""
     v = C.c_double()
-    check(_lib.load().qxb_fma_peak(QXB_C32 if dtype == "c32" else QXB_C64, C.byref(v)))
+    check(_lib.load().qxb_fma_peak({"c32": QXB_C32, "c64": QXB_C64, "c32x2": 2}[dtype], C.byref(v)))
     return v.value
 
 
