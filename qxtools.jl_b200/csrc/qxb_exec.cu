@@ -518,10 +518,10 @@ Node contract_node(const RunCtx& c, int i) {
         const auto& kSm = a_big ? op.segKB : op.segKA;
         const int nN = a_big ? op.n_n : op.n_m;
         const double big_elems = a_big ? op.elems_a : op.elems_b;
-        const bool packed = g->dtype == QXB_C32 && knob(0, "QXB_BIGSMALL_FFMA2", 1) != 0;
+        const bool packed = g->dtype == QXB_C32 && knob(0, "QXB_BIGSMALL_FFMA2", 0) != 0;
         const int max_lo = (g->dtype == QXB_C32 && !packed) ? 5 : 4;
         const int nlo = nN <= max_lo ? nN : 4, nhi = nN - nlo;
-        const void* bf = nN >= 1 ? bigsmall_func(g->dtype, nlo, packed) : nullptr;
+        const void* bf = nN >= 1 ? bigsmall_func(g->dtype, nlo, knob(0, "QXB_BIGSMALL_KT", 1) != 0 ? op.nK : 0, packed) : nullptr;
         const size_t small_bytes = ((size_t)1 << (op.nK + nN)) * g->es();
         if (bf && big_elems >= std::ldexp(1.0, knob(0, "QXB_BIGSMALL_MIN_BITS", 20)) && small_bytes <= 64 * 1024 && nhi <= 8 &&
             TS.span_bits <= 24 && TB.span_bits <= 40 && op.nK + nN >= 3 && p.nC - nN >= 8) {
@@ -682,11 +682,29 @@ Node contract_node(const RunCtx& c, int i) {
                 for (auto& sg : op.segKA) for (int b = 0; b < sg.len; ++b) posA[sg.src + b] = sg.dst + b;
                 for (auto& sg : op.segKB) for (int b = 0; b < sg.len; ++b) posB[sg.src + b] = sg.dst + b;
                 for (int b = 0; b < p.nK; ++b) order[b] = b;
-                std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-                    return std::min(posA[x], posB[x]) < std::min(posA[y], posB[y]);
-                });
-                std::vector<int> perm(order.begin(), order.begin() + kKredTileKBits), rest(order.begin() + kKredTileKBits, order.end());
+                // round robin: the K bit sitting lowest in A, then the one lowest in B, ... -- each operand gets a contiguous
+                // run from its address bit 0 up (its row bits in between are read by the same CTA): 256 - 512 B pieces.
+                // (Sorting by the lower of the two positions gave 64 B pieces on the scrambled operand: 1.4 TB/s.)
+                std::vector<int> byA = order, byB = order, picked;
+                std::stable_sort(byA.begin(), byA.end(), [&](int x, int y) { return posA[x] < posA[y]; });
+                std::stable_sort(byB.begin(), byB.end(), [&](int x, int y) { return posB[x] < posB[y]; });
+                std::vector<bool> taken(p.nK, false);
+                for (size_t ia = 0, ib = 0; (int)picked.size() < kKredTileKBits;) {
+                    auto& lst = (picked.size() % 2 == 0) ? byA : byB;
+                    size_t& it = (picked.size() % 2 == 0) ? ia : ib;
+                    while (taken[lst[it]]) ++it;
+                    taken[lst[it]] = true; picked.push_back(lst[it]);
+                }
+                std::vector<int> unpicked;
+                for (int b = 0; b < p.nK; ++b) if (!taken[b]) unpicked.push_back(b);
+                std::vector<int> perm = picked, rest = unpicked;
                 std::sort(perm.begin(), perm.end(), [&](int x, int y) { return posA[x] < posA[y]; });   // staging threads walk A ascending
+                // ... and B ascending: the threads staging B take the chunk's k in B's bit order (kperm_b)
+                std::vector<int> cb(kKredTileKBits);
+                for (int j = 0; j < kKredTileKBits; ++j) cb[j] = j;
+                std::sort(cb.begin(), cb.end(), [&](int x, int y) { return posB[perm[x]] < posB[perm[y]]; });
+                for (int j = 0; j < kKredTileKBits; ++j) kt.kperm_b[j] = (unsigned char)cb[j];
+                kt.kperm_set = 1;
                 std::sort(rest.begin(), rest.end());
                 perm.insert(perm.end(), rest.begin(), rest.end());
                 auto rebuild = [&](const std::vector<int>& pos, DSeg* dst) {
@@ -719,7 +737,7 @@ Node contract_node(const RunCtx& c, int i) {
                 size_t smem = (size_t)(kt.n_rows_a + kt.n_rows_b) * (kKredTileK + 1) * g->es();
                 // outputs = the full grid rows(A) x rows(B): 2 x 2 outputs per thread, two-stage cp.async ring
                 bool grid_ok = knob(0, "QXB_KRED_GRID", 1) != 0 && kt.n_rows_a % 2 == 0 && kt.n_rows_b % 2 == 0 &&
-                               kt.n_rows_a * kt.n_rows_b == (1 << p.nC) && 2 * smem <= 96 * 1024;
+                               kt.n_rows_a * kt.n_rows_b == (1 << p.nC) && 2 * smem <= 160 * 1024;
                 if (grid_ok) {
                     std::vector<int> seen(1 << p.nC, 0);
                     for (int cc = 0; cc < (1 << p.nC); ++cc) {
@@ -729,13 +747,13 @@ Node contract_node(const RunCtx& c, int i) {
                     }
                 }
                 if (grid_ok) smem *= 2;
-                if (smem <= 96 * 1024) {
+                if (smem <= (grid_ok ? 160 : 96) * 1024) {
                     const int gt = (kt.n_rows_a % 4 == 0 && kt.n_rows_b % 4 == 0) ? 4 : 2;
                     n.func = grid_ok ? kreduce_grid_func(g->dtype, gt) : kreduce_tile_func(g->dtype);
                     n.kname = grid_ok ? "kreduce_grid" : "kreduce_tile";
                     n.smem = smem;
-                    if (smem > 48 * 1024 && first_use(n.func))
-                        CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                    if (first_use(n.func))
+                        CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
                     const long long nchunks = 1ll << (p.nK - kKredTileKBits);
                     n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(nchunks, (long long)g_num_sms * 3)));
                     n.block = dim3(kThreads);

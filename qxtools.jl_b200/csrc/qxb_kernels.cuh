@@ -103,12 +103,14 @@ const void* kreduce_split_func(int dtype);
 // tiled split-K variant (qxb_kred.cu): a CTA stages the operand tiles of a K chunk in shared memory once, a thread per
 // output accumulates over the chunk, partial sums meet by atomicAdd in a zeroed C.  Arguments (OpParams, KredTile);
 // dynamic shared memory = (n_rows_a + n_rows_b) * (kKredTileK + 1) * sizeof(element)
-constexpr int kKredTileKBits = 6, kKredTileK = 1 << kKredTileKBits, kKredMaxRows = 64;
+constexpr int kKredTileKBits = 7, kKredTileK = 1 << kKredTileKBits, kKredMaxRows = 64;
 struct KredTile {
     int n_rows_a, n_rows_b;                        // distinct operand rows the C bits select (<= kKredMaxRows each)
     unsigned char row_a[256], row_b[256];          // output c -> its row of A / B
     long long off_a[kKredMaxRows], off_b[kKredMaxRows];   // row -> element offset in the operand
     unsigned char grid_c[256];                     // kreduce_grid_kernel: (row of A) * n_rows_b + (row of B) -> output c
+    unsigned char kperm_b[8];                      // staging of B: bit j of (tid % chunk) -> bit of the chunk's k (B-ascending)
+    int kperm_set;                                 // 0: identity
 };
 const void* kreduce_tile_func(int dtype);
 // Same staging, for outputs that form the full grid rows(A) x rows(B) (both even): a thread owns a 2 x 2 or 4 x 4 block of outputs
@@ -131,7 +133,7 @@ struct BigSmallParams {
     int bK[32], bN[32];                // k, n -> offset in the small operand
     int bH[256];                       // N bits beyond the register tile -> offset in the small operand
 };
-const void* bigsmall_func(int dtype, int n_bits, bool packed);     // packed: ComplexF32 through FFMA2 (n_bits <= 4)
+const void* bigsmall_func(int dtype, int n_bits, int k_bits, bool packed);     // packed: ComplexF32 through FFMA2 (n_bits <= 4)
 // TMA variant (U == 1, the 8 thread bits of the position index = the 8 lowest address bits of the big operand): second
 // kernel argument = number of 32 KB stages; dynamic shared memory = stages * kBigSmallStageBytes + small operand
 // (rounded up to 16 B) + 8 B per stage (mbarriers)

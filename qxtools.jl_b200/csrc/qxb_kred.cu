@@ -98,7 +98,13 @@ kreduce_grid_kernel(const __grid_constant__ OpParams p, const __grid_constant__ 
     const int ia = (tile % (nA / T)) * T, ib = (tile / (nA / T)) * T;
     const int kk = tid % KT, r0 = tid / KT;
     constexpr int RSTEP = kThreads / KT;
-    const long long gAk = kseg(p.kA, p.nkA, (unsigned long long)kk), gBk = kseg(p.kB, p.nkB, (unsigned long long)kk);
+    int kkB = kk;                                      // the threads staging B walk the chunk in B's address order
+    if (t.kperm_set) {
+        kkB = 0;
+#pragma unroll
+        for (int j = 0; j < kKredTileKBits; ++j) kkB |= ((kk >> j) & 1) << t.kperm_b[j];
+    }
+    const long long gAk = kseg(p.kA, p.nkA, (unsigned long long)kk), gBk = kseg(p.kB, p.nkB, (unsigned long long)kkB);
     const long long nchunks = 1ll << (p.nK - kKredTileKBits);
     const long long G = gridDim.x;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(sbuf);
@@ -121,7 +127,7 @@ kreduce_grid_kernel(const __grid_constant__ OpParams p, const __grid_constant__ 
             }
             for (int r = r0; r < nB; r += RSTEP) {
                 const R2* src = Bu + t.off_b[r] + gB0;
-                const unsigned dst = sb + (unsigned)((r * LD + kk) * sizeof(R2));
+                const unsigned dst = sb + (unsigned)((r * LD + kkB) * sizeof(R2));
                 if constexpr (sizeof(R2) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
                 else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
             }
@@ -293,7 +299,9 @@ struct BsAcc<float2, NN, true> {
     }
 };
 
-template <typename R2, int NN, int RK, bool PACK>
+// KKT > 0: the K extent is a compile-time constant (every loop unrolls, the offset tables are read as immediate
+// constant-bank operands, no tail predicates: ~18 % fewer instructions on an issue-bound kernel); KKT = 0: run time.
+template <typename R2, int NN, int RK, bool PACK, int KKT>
 __global__ void __launch_bounds__(256)
 bigsmall_kernel(const __grid_constant__ BigSmallParams p) {
     extern __shared__ __align__(16) unsigned char bs_smem[];
@@ -301,7 +309,7 @@ bigsmall_kernel(const __grid_constant__ BigSmallParams p) {
     const R2* __restrict__ A = reinterpret_cast<const R2*>(p.big);
     const R2* __restrict__ B = reinterpret_cast<const R2*>(p.small_);
     R2* __restrict__ C = reinterpret_cast<R2*>(p.C);
-    const int KK = 1 << p.nK;
+    const int KK = KKT > 0 ? KKT : (1 << p.nK);
     const int n_small = (KK * NN) << p.nNhi;
     // position index = [8 thread bits][n_hi bits][block bits]: the thread part of both addresses is evaluated once, the
     // block part (with the N bits beyond the register tile) is uniform over the CTA
@@ -317,10 +325,45 @@ bigsmall_kernel(const __grid_constant__ BigSmallParams p) {
         __syncthreads();
         const R2* Au = A + u * p.sUbig + a_lo;
         R2* Cu = C + u * p.sUC + c_lo;
-        // RK elements of the big operand per round (enough bytes in flight per SM to cover the HBM latency); the next round's loads -- the first round of the CTA's NEXT block
-        // of positions after the last one -- are issued before this round's FMAs, so loads stay in flight across blocks
-        R2 a[RK], an[RK];
         const R2* Ab = Au + kseg(p.tA, p.ntA, (unsigned long long)blockIdx.x << 8);
+        if constexpr (KKT > 0) {
+            // RK elements of the big operand per round, next round (or the next block's first) in flight during the FMAs
+            constexpr int NR = (KKT + RK - 1) / RK;
+            R2 a[RK], an[RK];
+            if ((long long)blockIdx.x < n_blk) {
+#pragma unroll
+                for (int q = 0; q < RK; ++q) if (q < KKT) a[q] = __ldg(Ab + p.aK[q]);
+            }
+            for (long long blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
+                R2* Cb = Cu + kseg(p.tC, p.ntC, (unsigned long long)blk << 8);
+                const R2* sBh = sB + (int)(blk & ((1 << p.nNhi) - 1)) * (KKT * NN);
+                const long long nxt = blk + gridDim.x;
+                const R2* Anext = Au + kseg(p.tA, p.ntA, (unsigned long long)(nxt < n_blk ? nxt : blk) << 8);
+                BsAcc<R2, NN, PACK> acc;
+                acc.clear();
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    if (r + 1 < NR) {
+#pragma unroll
+                        for (int q = 0; q < RK; ++q) if ((r + 1) * RK + q < KKT) an[q] = __ldg(Ab + p.aK[(r + 1) * RK + q]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < RK; ++q) if (q < KKT) an[q] = __ldg(Anext + p.aK[q]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < RK; ++q) if (r * RK + q < KKT) acc.mac_row(a[q], sBh + (r * RK + q) * NN);
+#pragma unroll
+                    for (int q = 0; q < RK; ++q) a[q] = an[q];
+                }
+                Ab = Anext;
+#pragma unroll
+                for (int n = 0; n < NN; ++n) Cb[p.cN[n]] = acc.get(n);
+            }
+        } else {
+        // RK elements of the big operand per round (enough bytes in flight per SM to cover the HBM latency); the next
+        // round's loads -- the first round of the CTA's NEXT block of positions after the last one -- are issued before
+        // this round's FMAs, so loads stay in flight across blocks
+        R2 a[RK], an[RK];
         if ((long long)blockIdx.x < n_blk) {
 #pragma unroll
             for (int q = 0; q < RK; ++q) a[q] = (q < KK) ? __ldg(Ab + p.aK[q]) : R2{0, 0};
@@ -351,6 +394,7 @@ bigsmall_kernel(const __grid_constant__ BigSmallParams p) {
             Ab = Anext;
 #pragma unroll
             for (int n = 0; n < NN; ++n) Cb[p.cN[n]] = acc.get(n);
+        }
         }
     }
 }
@@ -459,31 +503,41 @@ const void* bigsmall_tma_func(int dtype, int n_bits) {
     }
 }
 
-const void* bigsmall_func(int dtype, int n_bits, bool packed) {
+template <typename R2, int NN, int RK, bool PACK>
+static const void* bigsmall_pick_k(int k_bits) {
+    switch (k_bits) {
+    case 3: return (const void*)&bigsmall_kernel<R2, NN, RK, PACK, 8>;
+    case 4: return (const void*)&bigsmall_kernel<R2, NN, RK, PACK, 16>;
+    case 5: return (const void*)&bigsmall_kernel<R2, NN, RK, PACK, 32>;
+    default: return (const void*)&bigsmall_kernel<R2, NN, RK, PACK, 0>;
+    }
+}
+
+const void* bigsmall_func(int dtype, int n_bits, int k_bits, bool packed) {
     if (dtype == 0 && packed) {
         switch (n_bits) {
-        case 1: return (const void*)&bigsmall_kernel<float2, 2, 8, true>;
-        case 2: return (const void*)&bigsmall_kernel<float2, 4, 8, true>;
-        case 3: return (const void*)&bigsmall_kernel<float2, 8, 8, true>;
-        case 4: return (const void*)&bigsmall_kernel<float2, 16, 4, true>;
+        case 1: return bigsmall_pick_k<float2, 2, 8, true>(k_bits);
+        case 2: return bigsmall_pick_k<float2, 4, 8, true>(k_bits);
+        case 3: return bigsmall_pick_k<float2, 8, 8, true>(k_bits);
+        case 4: return bigsmall_pick_k<float2, 16, 4, true>(k_bits);
         default: return nullptr;
         }
     }
     if (dtype == 0) {
         switch (n_bits) {
-        case 1: return (const void*)&bigsmall_kernel<float2, 2, 8, false>;
-        case 2: return (const void*)&bigsmall_kernel<float2, 4, 8, false>;
-        case 3: return (const void*)&bigsmall_kernel<float2, 8, 8, false>;
-        case 4: return (const void*)&bigsmall_kernel<float2, 16, 8, false>;
-        case 5: return (const void*)&bigsmall_kernel<float2, 32, 4, false>;
+        case 1: return bigsmall_pick_k<float2, 2, 8, false>(k_bits);
+        case 2: return bigsmall_pick_k<float2, 4, 8, false>(k_bits);
+        case 3: return bigsmall_pick_k<float2, 8, 8, false>(k_bits);
+        case 4: return bigsmall_pick_k<float2, 16, 8, false>(k_bits);
+        case 5: return bigsmall_pick_k<float2, 32, 4, false>(k_bits);
         default: return nullptr;
         }
     }
     switch (n_bits) {
-    case 1: return (const void*)&bigsmall_kernel<double2, 2, 8, false>;
-    case 2: return (const void*)&bigsmall_kernel<double2, 4, 8, false>;
-    case 3: return (const void*)&bigsmall_kernel<double2, 8, 4, false>;
-    case 4: return (const void*)&bigsmall_kernel<double2, 16, 4, false>;
+    case 1: return bigsmall_pick_k<double2, 2, 8, false>(k_bits);
+    case 2: return bigsmall_pick_k<double2, 4, 8, false>(k_bits);
+    case 3: return bigsmall_pick_k<double2, 8, 4, false>(k_bits);
+    case 4: return bigsmall_pick_k<double2, 16, 4, false>(k_bits);
     default: return nullptr;
     }
 }

@@ -1,0 +1,6 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "big_times_small or split_k" 2>&1 | tail -5
+PROBE_NO_C64=1 PROBE_SLICES=4 timeout 900 python scripts/probe_syc12.py > gpurun_out/r2ad_syc12.log 2>&1; tail -16 gpurun_out/r2ad_syc12.log; cp gpurun_out/probe_syc12.json gpurun_out/r2ad_probe_syc12.json; cp gpurun_out/op_profile_syc12.json gpurun_out/r2ad_op_profile_syc12.json
+QXB_BIGSMALL_KT=0 PROBE_NO_C64=1 PROBE_SLICES=4 PROBE_NO_PROFILE=1 timeout 900 python scripts/probe_syc12.py 2>&1 | grep "c32:"
+QXB_BIGSMALL_FFMA2=1 PROBE_NO_C64=1 PROBE_SLICES=4 PROBE_NO_PROFILE=1 timeout 900 python scripts/probe_syc12.py 2>&1 | grep "c32:"
