@@ -19,7 +19,7 @@ for N in (1, 2, 4, 8):
         break
     m = MultiGraph(Graph.from_dsl(txt, data, "c32"), n_devices=N, hbm_budget_bytes=int(150e9))
     a = m.amplitudes(bits)                      # first call: arenas, constant folding, step graphs on every device
-    reps = 2
+    reps = int(os.environ.get("PROBE_MULTI_REPS", "2"))
     t0 = time.perf_counter()
     for _ in range(reps):
         a = m.amplitudes(bits)
@@ -33,6 +33,9 @@ for N in (1, 2, 4, 8):
     for d in range(ndev):
         with torch.cuda.device(d):
             torch.cuda.empty_cache()
+if os.environ.get("PROBE_MULTI_ONLY") == "syc":
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "probe_multi.json"), "w"), indent=1)
+    sys.exit(0)
 txt, data, w = bench.build_workload("rqc_7x7_d20_c64_s4096")
 n_amp = 131072
 bits = bench.synth_bits(n_amp, 49)
