@@ -588,7 +588,16 @@ Node contract_node(const RunCtx& c, int i) {
                     n.smem = small_bytes;
                     if (first_use(n.func))
                         CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-                    n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(q.n_pos >> 8, cap * 4)));
+                    static std::map<std::tuple<int, const void*, size_t>, int> resident;
+                    auto key = std::make_tuple(g_device, n.func, n.smem);
+                    auto it = resident.find(key);
+                    if (it == resident.end()) {
+                        int nb = 0;
+                        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, n.func, kThreads, n.smem));
+                        it = resident.emplace(key, std::max(nb, 1)).first;
+                    }
+                    // persistent: one wave of resident CTAs, the blocks of positions dealt out round robin
+                    n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(q.n_pos >> 8, (long long)g_num_sms * it->second)));
                     n.arg(q);
                 }
                 n.variant = c.variant_key; n.op = i;
@@ -755,7 +764,17 @@ Node contract_node(const RunCtx& c, int i) {
                     if (first_use(n.func))
                         CUDA_OK(cudaFuncSetAttribute(n.func, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
                     const long long nchunks = 1ll << (p.nK - kKredTileKBits);
-                    n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(nchunks, (long long)g_num_sms * 3)));
+                    // persistent grid = SMs x resident CTAs (a partial second wave would run at half occupancy: the chunks
+                    // are dealt out statically)
+                    static std::map<std::tuple<int, const void*, size_t>, int> resident;
+                    auto key = std::make_tuple(g_device, n.func, smem);
+                    auto it = resident.find(key);
+                    if (it == resident.end()) {
+                        int nb = 0;
+                        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, n.func, kThreads, smem));
+                        it = resident.emplace(key, std::max(nb, 1)).first;
+                    }
+                    n.grid = dim3((unsigned)std::max<long long>(1, std::min<long long>(nchunks, (long long)g_num_sms * it->second)));
                     n.block = dim3(kThreads);
                     n.pre_zero_ptr = p.C;
                     n.pre_zero_bytes = (size_t)((C.amp ? c.n : 1) << C.span_bits) * g->es();
