@@ -187,22 +187,72 @@ bool describe_row_op(const LOp& op, int dtype, const RowPlanOptions& o, RowOp& d
         }
         h.ktA[k] = (uint16_t)a; h.ktB[k] = (uint16_t)b;
     }
-    std::vector<std::pair<int, int>> ta, tb, tc, ka, kb;
-    int t = 0;
-    for (int b = 0; b < nC; ++b) {
-        if (is_tile[b]) continue;
-        tc.push_back({t, b});
-        if (mapA[b] >= 0) ta.push_back({t, mapA[b]});
-        if (mapB[b] >= 0) tb.push_back({t, mapB[b]});
-        ++t;
-    }
+    // thread-tile index bits = the C bits outside the register tile; the low 5 of them are the lanes of a unit.
+    // Which C bits become the LOW lane bits decides the shared-memory bank conflicts: the lanes of one wavefront group
+    // (8 lanes for 16-byte elements, 16 for 8-byte ones) should hit distinct 128-byte residues -- or the same address --
+    // in A, in B and in C.  With the lowest C bits as lanes (conflict-free for C only) the fused chain of the headline
+    // plan spent 8960 wavefronts per row where 6016 suffice (scripts/analyze_chain_banks.py); pick the group bits that
+    // minimise the op's wavefronts, ties to the lowest bits.
+    std::vector<int> order;
+    for (int b = 0; b < nC; ++b) if (!is_tile[b]) order.push_back(b);
+    static const bool bank_opt = [] { const char* e = getenv("QXB_ROW_BANK_OPT"); return !e || atoi(e) != 0; }();
+    auto arrange = [&](bool optimise) {
+        std::vector<int> ord = order;
+        const int q = dtype == QXB_C64 ? 3 : 4;
+        if (optimise && ntt >= 5 && (int)ord.size() > q) {
+            auto waves = [&](const std::vector<int>& bits, const std::vector<int>& map) {
+                int cnt[16] = {0};
+                std::vector<int> seen;
+                for (int l = 0; l < (1 << q); ++l) {
+                    int a = 0;
+                    for (int i = 0; i < q; ++i) if (((l >> i) & 1) && map[bits[i]] >= 0) a |= 1 << map[bits[i]];
+                    if (std::find(seen.begin(), seen.end(), a) == seen.end()) { seen.push_back(a); ++cnt[a & ((1 << q) - 1)]; }
+                }
+                return *std::max_element(cnt, cnt + (1 << q));
+            };
+            std::vector<int> ident(nC);
+            for (int b = 0; b < nC; ++b) ident[b] = b;
+            const double nk = std::ldexp(1.0, nK), tm = std::ldexp(1.0, ma), tn = std::ldexp(1.0, nb);
+            std::vector<int> pick(q), best;
+            double best_cost = 0;
+            std::vector<int> idx(q);
+            for (int i = 0; i < q; ++i) idx[i] = i;
+            const int n = (int)ord.size();
+            while (true) {
+                for (int i = 0; i < q; ++i) pick[i] = ord[idx[i]];
+                const double cost = nk * (tm * waves(pick, mapA) + tn * waves(pick, mapB)) + tm * tn * waves(pick, ident);
+                if (best.empty() || cost < best_cost) { best = pick; best_cost = cost; }
+                int i = q - 1;
+                while (i >= 0 && idx[i] == n - q + i) --i;
+                if (i < 0) break;
+                ++idx[i];
+                for (int j = i + 1; j < q; ++j) idx[j] = idx[j - 1] + 1;
+            }
+            std::vector<int> rest;
+            for (int b : ord) if (std::find(best.begin(), best.end(), b) == best.end()) rest.push_back(b);
+            ord = best; ord.insert(ord.end(), rest.begin(), rest.end());
+        }
+        std::vector<std::pair<int, int>> ta, tb, tc;
+        for (int t = 0; t < (int)ord.size(); ++t) {
+            const int b = ord[t];
+            tc.push_back({t, b});
+            if (mapA[b] >= 0) ta.push_back({t, mapA[b]});
+            if (mapB[b] >= 0) tb.push_back({t, mapB[b]});
+        }
+        const int a = merge_runs(ta, d.tA, kRowMaxSeg), b2 = merge_runs(tb, d.tB, kRowMaxSeg), c = merge_runs(tc, d.tC, kRowMaxSeg);
+        if (a < 0 || b2 < 0 || c < 0) return false;
+        d.nsA = (uint8_t)a; d.nsB = (uint8_t)b2; d.nsC = (uint8_t)c;
+        return true;
+    };
+    if (!(bank_opt && arrange(true)) && !arrange(false)) return bad("too many address segments");   // permuted bits split runs
+    std::vector<std::pair<int, int>> ka, kb;
     for (int b = 4; b < nK; ++b) {
         if (kposA[b] >= 0) ka.push_back({b - 4, kposA[b]});
         if (kposB[b] >= 0) kb.push_back({b - 4, kposB[b]});
     }
-    const int nsA = merge_runs(ta, d.tA, kRowMaxSeg), nsB = merge_runs(tb, d.tB, kRowMaxSeg), nsC = merge_runs(tc, d.tC, kRowMaxSeg);
     const int nkA = merge_runs(ka, d.kA, kRowMaxKSeg), nkB = merge_runs(kb, d.kB, kRowMaxKSeg);
-    if (nsA < 0 || nsB < 0 || nsC < 0 || nkA < 0 || nkB < 0) return bad("too many address segments");
+    if (nkA < 0 || nkB < 0) return bad("too many address segments");
+    const int nsA = d.nsA, nsB = d.nsB, nsC = d.nsC;
     d.nsA = (uint8_t)nsA; d.nsB = (uint8_t)nsB; d.nsC = (uint8_t)nsC; d.nkA = (uint8_t)nkA; d.nkB = (uint8_t)nkB;
     return true;
 }
