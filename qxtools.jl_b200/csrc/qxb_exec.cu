@@ -851,6 +851,7 @@ Node contract_node(const RunCtx& c, int i) {
             if (aligned && !rd.tried) {
                 rd.tried = true;
                 RowPlanOptions ro;
+                ro.bank_search_tiles = true;
                 ro.min_tt_bits = knob(0, "QXB_RING_MIN_TT", 8);
                 ro.tile_reg_budget = knob(0, "QXB_RING_TILE_REGS", 100);
                 ro.dmma = (g->opts.row_dmma == 2 || (g->opts.row_dmma == 0 && knob(0, "QXB_ROW_DMMA", 0) != 0));
@@ -1025,6 +1026,7 @@ Variant* get_variant(qxb_graph* g, uint64_t free_mask) {
     // fused chain: pick it and make its ops contiguous BEFORE the memory plan (its intermediates never reach HBM; the
     // arena plan and the dependency edges must see the chain as one step)
     RowPlanOptions co;
+    co.bank_search_tiles = knob(0, "QXB_CHAIN_BANK_TILES", 1) != 0;
     const bool chain_on = knob(0, "QXB_CHAIN", 1) != 0 && g->opts.row_programs != 1 && g->opts.chain != 1;
     if (chain_on) {
         co.min_tt_bits = knob(0, "QXB_CHAIN_MIN_TT", 7);
@@ -2295,6 +2297,7 @@ int64_t qxb_debug_rowprog(qxb_graph* g, uint64_t free_mask, int phase, void* buf
         Lowered L = lower(g->prog, free_mask, !g->opts.sum_at_root);
         std::vector<int> chain;
         RowPlanOptions co;
+        co.bank_search_tiles = knob(0, "QXB_CHAIN_BANK_TILES", 1) != 0;
         if (phase == 3) {
             co.min_tt_bits = knob(0, "QXB_CHAIN_MIN_TT", 7);
             co.max_arena_bytes = (233472 / 2 - 1024) - (long long)row_fixed_smem_bytes(512);

@@ -54,8 +54,19 @@ int arena_alloc(std::vector<Interval>& live, int size, int until, int align = 1)
 
 // The descriptor of one contraction for the unit interpreter: register tile, K chunk, tables, thread-tile maps.
 // Tensor locations (oA / oB / oC, g*) are left to the caller.
+// Layouts of the op's tensors inside the row arena: pa / pb / pc = address-bit permutations (old bit -> new bit) of A, B
+// and C (nullptr: as lowered; C as lowered = identity).  free_operand (1 = A, 2 = B): that operand's layout is still to
+// be chosen -- the bank model counts it conflict-free; group_out receives the C bits chosen as the low lane bits.
+struct RowLayouts {
+    const int* pa = nullptr;
+    const int* pb = nullptr;
+    const int* pc = nullptr;
+    int free_operand = 0;
+    std::vector<int>* group_out = nullptr;
+};
+
 bool describe_row_op(const LOp& op, int dtype, const RowPlanOptions& o, RowOp& d, int& n_units, double& unit_cost,
-                     std::string& why) {
+                     std::string& why, const RowLayouts* lay = nullptr) {
     auto bad = [&](const std::string& w) { why = w; return false; };
     memset(&d, 0, sizeof(d));
     d.lsA = d.lsB = d.lsC = kRowShared;
@@ -69,6 +80,11 @@ bool describe_row_op(const LOp& op, int dtype, const RowPlanOptions& o, RowOp& d
     for (auto& s : op.segKB) for (int b = 0; b < s.len; ++b) kposB[s.src + b] = s.dst + b;
     for (int b = 0; b < nC; ++b) if (mapA[b] > 15 || mapB[b] > 15) return bad("operand wider than 2^16 elements");
     for (int b = 0; b < nK; ++b) if (kposA[b] > 15 || kposB[b] > 15) return bad("operand wider than 2^16 elements");
+    std::vector<int> mapC(nC);
+    for (int b = 0; b < nC; ++b) mapC[b] = (lay && lay->pc) ? lay->pc[b] : b;
+    if (lay && lay->pa) { for (int& x : mapA) if (x >= 0) x = lay->pa[x]; for (int& x : kposA) if (x >= 0) x = lay->pa[x]; }
+    if (lay && lay->pb) { for (int& x : mapB) if (x >= 0) x = lay->pb[x]; for (int& x : kposB) if (x >= 0) x = lay->pb[x]; }
+    const int free_operand = lay ? lay->free_operand : 0;
     // ComplexF64 with >= 3 M-only, >= 3 N-only and >= 2 K bits: 8 x 8 output tiles on the FP64 tensor pipe (kRowKindDmma)
     if (o.dmma && dtype == QXB_C64 && nK >= 2) {
         std::vector<int> ms, ns;
@@ -86,11 +102,11 @@ bool describe_row_op(const LOp& op, int dtype, const RowPlanOptions& o, RowOp& d
             for (int lane = 0; lane < 32; ++lane) {
                 const int g = lane >> 2, t = lane & 3;
                 int a = 0, b = 0, c = 0;
-                for (int j = 0; j < 3; ++j) if ((g >> j) & 1) { a |= 1 << mapA[mb[j]]; c |= 1 << mb[j]; b |= 1 << mapB[nbq[j]]; }
-                for (int j = 0; j < 2; ++j) if ((t >> j) & 1) { a |= 1 << kposA[j]; b |= 1 << kposB[j]; c |= 1 << nbq[j + 1]; }
+                for (int j = 0; j < 3; ++j) if ((g >> j) & 1) { a |= 1 << mapA[mb[j]]; c |= 1 << mapC[mb[j]]; b |= 1 << mapB[nbq[j]]; }
+                for (int j = 0; j < 2; ++j) if ((t >> j) & 1) { a |= 1 << kposA[j]; b |= 1 << kposB[j]; c |= 1 << mapC[nbq[j + 1]]; }
                 d.frA[lane] = (uint16_t)a; d.frB[lane] = (uint16_t)b; d.frC[lane] = (uint16_t)c;
             }
-            d.c_n1 = (uint16_t)(1 << nbq[0]);
+            d.c_n1 = (uint16_t)(1 << mapC[nbq[0]]);
             for (int k = 0; k < (1 << std::min(nK, 4)); ++k) {
                 int a = 0, b = 0;
                 for (int t = 0; t < std::min(nK, 4); ++t) if ((k >> t) & 1) {
@@ -106,7 +122,7 @@ bool describe_row_op(const LOp& op, int dtype, const RowPlanOptions& o, RowOp& d
             int t = 0;
             for (int b = 0; b < nC; ++b) {
                 if (frag[b]) continue;
-                tc.push_back({t, b});
+                tc.push_back({t, mapC[b]});
                 if (mapA[b] >= 0) ta.push_back({t, mapA[b]});
                 if (mapB[b] >= 0) tb.push_back({t, mapB[b]});
                 ++t;
@@ -149,6 +165,74 @@ bool describe_row_op(const LOp& op, int dtype, const RowPlanOptions& o, RowOp& d
     if (ntt < 5) {                                       // fewer than 32 thread-tiles: lanes split K instead
         mbits.clear(); nbits.clear(); ma = nb = 0; ntt = nC;
     }
+    static const bool bank_opt = [] { const char* e = getenv("QXB_ROW_BANK_OPT"); return !e || atoi(e) != 0; }();
+    // shared-memory wavefronts of one access of the lanes of a wavefront group (8 lanes for 16-byte elements, 16 for 8-byte
+    // ones) whose index bits are the C bits `bits`: distinct addresses falling on the same 128-byte residue serialise
+    const int q = dtype == QXB_C64 ? 3 : 4;
+    auto waves = [&](const int* bits, const std::vector<int>& map) {
+        int cnt[16] = {0}, seen[16], ns = 0;
+        for (int l = 0; l < (1 << q); ++l) {
+            int a = 0;
+            for (int i = 0; i < q; ++i) if (((l >> i) & 1) && map[bits[i]] >= 0) a |= 1 << map[bits[i]];
+            bool dup = false;
+            for (int i = 0; i < ns; ++i) dup |= seen[i] == a;
+            if (!dup) { seen[ns++] = a; ++cnt[a & ((1 << q) - 1)]; }
+        }
+        return *std::max_element(cnt, cnt + (1 << q));
+    };
+    // best group bits among the non-tile bits `ord` for a (2^tma x 2^tnb) register tile: (cost, bits)
+    auto best_group = [&](const std::vector<int>& ord, int tma, int tnb, std::vector<int>& best) {
+        const double nk = std::ldexp(1.0, nK), tm = std::ldexp(1.0, tma), tn = std::ldexp(1.0, tnb);
+        const int n = (int)ord.size();
+        double best_cost = -1;
+        int idx[4], pick[4];
+        for (int i = 0; i < q; ++i) idx[i] = i;
+        while (true) {
+            for (int i = 0; i < q; ++i) pick[i] = ord[idx[i]];
+            const double wa = free_operand == 1 ? 1 : waves(pick, mapA), wb = free_operand == 2 ? 1 : waves(pick, mapB);
+            const double cost = nk * (tm * wa + tn * wb) + tm * tn * waves(pick, mapC);
+            if (best_cost < 0 || cost < best_cost) { best.assign(pick, pick + q); best_cost = cost; }
+            int i = q - 1;
+            while (i >= 0 && idx[i] == n - q + i) --i;
+            if (i < 0) break;
+            ++idx[i];
+            for (int j = i + 1; j < q; ++j) idx[j] = idx[j - 1] + 1;
+        }
+        return best_cost;
+    };
+    if (bank_opt && o.bank_search_tiles && ntt >= 5 && ntt > q && ma + nb > 0) {
+        // which M-only / N-only bits form the register tile: every choice of ma of the M-only and nb of the N-only bits
+        std::vector<int> bm, bn;
+        double bc = -1;
+        std::vector<int> im(ma), in(nb);
+        for (int i = 0; i < ma; ++i) im[i] = i;
+        auto next_comb = [](std::vector<int>& idx, int n) {
+            const int k = (int)idx.size();
+            int i = k - 1;
+            while (i >= 0 && idx[i] == n - k + i) --i;
+            if (i < 0) return false;
+            ++idx[i];
+            for (int j = i + 1; j < k; ++j) idx[j] = idx[j - 1] + 1;
+            return true;
+        };
+        do {
+            for (int i = 0; i < nb; ++i) in[i] = i;
+            do {
+                std::vector<bool> tile(nC, false);
+                for (int i : im) tile[mcand[i]] = true;
+                for (int i : in) tile[ncand[i]] = true;
+                std::vector<int> ord, grp;
+                for (int b = 0; b < nC; ++b) if (!tile[b]) ord.push_back(b);
+                const double c = best_group(ord, ma, nb, grp);
+                if (bc < 0 || c < bc) {
+                    bc = c; bm.clear(); bn.clear();
+                    for (int i : im) bm.push_back(mcand[i]);
+                    for (int i : in) bn.push_back(ncand[i]);
+                }
+            } while (next_comb(in, (int)ncand.size()));
+        } while (next_comb(im, (int)mcand.size()));
+        mbits = bm; nbits = bn;
+    }
     std::sort(mbits.begin(), mbits.end()); std::sort(nbits.begin(), nbits.end());
     int kc = 0;
     if (ntt >= 5) {
@@ -170,11 +254,11 @@ bool describe_row_op(const LOp& op, int dtype, const RowPlanOptions& o, RowOp& d
     for (int b : nbits) is_tile[b] = true;
     for (int jm = 0; jm < (1 << ma); ++jm) {
         int a = 0, c = 0;
-        for (int t = 0; t < ma; ++t) if ((jm >> t) & 1) { a |= 1 << mapA[mbits[t]]; c |= 1 << mbits[t]; }
+        for (int t = 0; t < ma; ++t) if ((jm >> t) & 1) { a |= 1 << mapA[mbits[t]]; c |= 1 << mapC[mbits[t]]; }
         h.aT[jm] = (uint16_t)a;
         for (int jn = 0; jn < (1 << nb); ++jn) {
             int b = 0, c2 = c;
-            for (int t = 0; t < nb; ++t) if ((jn >> t) & 1) { b |= 1 << mapB[nbits[t]]; c2 |= 1 << nbits[t]; }
+            for (int t = 0; t < nb; ++t) if ((jn >> t) & 1) { b |= 1 << mapB[nbits[t]]; c2 |= 1 << mapC[nbits[t]]; }
             h.bT[jn] = (uint16_t)b;
             h.cT[jm * (1 << nb) + jn] = (uint16_t)c2;
         }
@@ -195,50 +279,22 @@ bool describe_row_op(const LOp& op, int dtype, const RowPlanOptions& o, RowOp& d
     // minimise the op's wavefronts, ties to the lowest bits.
     std::vector<int> order;
     for (int b = 0; b < nC; ++b) if (!is_tile[b]) order.push_back(b);
-    static const bool bank_opt = [] { const char* e = getenv("QXB_ROW_BANK_OPT"); return !e || atoi(e) != 0; }();
     auto arrange = [&](bool optimise) {
         std::vector<int> ord = order;
-        const int q = dtype == QXB_C64 ? 3 : 4;
         if (optimise && ntt >= 5 && (int)ord.size() > q) {
-            auto waves = [&](const std::vector<int>& bits, const std::vector<int>& map) {
-                int cnt[16] = {0};
-                std::vector<int> seen;
-                for (int l = 0; l < (1 << q); ++l) {
-                    int a = 0;
-                    for (int i = 0; i < q; ++i) if (((l >> i) & 1) && map[bits[i]] >= 0) a |= 1 << map[bits[i]];
-                    if (std::find(seen.begin(), seen.end(), a) == seen.end()) { seen.push_back(a); ++cnt[a & ((1 << q) - 1)]; }
-                }
-                return *std::max_element(cnt, cnt + (1 << q));
-            };
-            std::vector<int> ident(nC);
-            for (int b = 0; b < nC; ++b) ident[b] = b;
-            const double nk = std::ldexp(1.0, nK), tm = std::ldexp(1.0, ma), tn = std::ldexp(1.0, nb);
-            std::vector<int> pick(q), best;
-            double best_cost = 0;
-            std::vector<int> idx(q);
-            for (int i = 0; i < q; ++i) idx[i] = i;
-            const int n = (int)ord.size();
-            while (true) {
-                for (int i = 0; i < q; ++i) pick[i] = ord[idx[i]];
-                const double cost = nk * (tm * waves(pick, mapA) + tn * waves(pick, mapB)) + tm * tn * waves(pick, ident);
-                if (best.empty() || cost < best_cost) { best = pick; best_cost = cost; }
-                int i = q - 1;
-                while (i >= 0 && idx[i] == n - q + i) --i;
-                if (i < 0) break;
-                ++idx[i];
-                for (int j = i + 1; j < q; ++j) idx[j] = idx[j - 1] + 1;
-            }
-            std::vector<int> rest;
+            std::vector<int> best, rest;
+            best_group(ord, ma, nb, best);
             for (int b : ord) if (std::find(best.begin(), best.end(), b) == best.end()) rest.push_back(b);
             ord = best; ord.insert(ord.end(), rest.begin(), rest.end());
         }
         std::vector<std::pair<int, int>> ta, tb, tc;
         for (int t = 0; t < (int)ord.size(); ++t) {
             const int b = ord[t];
-            tc.push_back({t, b});
+            tc.push_back({t, mapC[b]});
             if (mapA[b] >= 0) ta.push_back({t, mapA[b]});
             if (mapB[b] >= 0) tb.push_back({t, mapB[b]});
         }
+        if (lay && lay->group_out) lay->group_out->assign(ord.begin(), ord.begin() + std::min<size_t>(ord.size(), (size_t)q));
         const int a = merge_runs(ta, d.tA, kRowMaxSeg), b2 = merge_runs(tb, d.tB, kRowMaxSeg), c = merge_runs(tc, d.tC, kRowMaxSeg);
         if (a < 0 || b2 < 0 || c < 0) return false;
         d.nsA = (uint8_t)a; d.nsB = (uint8_t)b2; d.nsC = (uint8_t)c;
@@ -398,12 +454,49 @@ RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const
     rp.in_arena_a.assign(n, 0); rp.in_arena_b.assign(n, 0); rp.in_arena_c.assign(n, 0);
     std::vector<double> unit_cost(n, 0);
     std::vector<int> n_units(n, 1);
+    // Fused chain: an intermediate lives only in the arena, so its LAYOUT is free.  Backwards over the chain: an op's result
+    // layout is what its consumer chose; the op then picks its lane-group bits with its own intermediate operand counted
+    // conflict-free, and that operand's layout puts the group's bits at address bits 0, 1, 2 (distinct 16-byte bank groups).
+    std::map<int, std::vector<int>> perm;                   // LTensor -> old address bit -> new address bit
+    static const bool layout_opt = [] { const char* e = getenv("QXB_ROW_LAYOUT_OPT"); return !e || atoi(e) != 0; }();
+    if (subset && o.bank_search_tiles && layout_opt) {
+        std::map<int, int> n_readers;
+        for (const LOp& op : L.ops) { ++n_readers[op.a]; ++n_readers[op.b]; }
+        for (int j = n - 1; j >= 0; --j) {
+            const LOp& op = L.ops[sel[j]];
+            int freeop = 0, X = -1;
+            for (int w = 1; w <= 2; ++w) {
+                const int t = w == 1 ? op.a : op.b;
+                if (producer.count(t) && arena_off.count(t) && n_readers[t] == 1 && t != L.root && op.a != op.b) { freeop = w; X = t; }
+            }
+            if (!freeop) continue;
+            std::vector<int> grp;
+            RowLayouts lay;
+            auto pc = perm.find(op.c);
+            lay.pc = pc != perm.end() ? pc->second.data() : nullptr;
+            lay.free_operand = freeop; lay.group_out = &grp;
+            RowOp tmp; int nu = 0; double uc = 0; std::string w2;
+            if (!describe_row_op(op, dtype, o, tmp, nu, uc, w2, &lay) || grp.empty()) continue;
+            const int span = L.tensors[X].span_bits;
+            std::vector<int> mapX(op.nC, -1);
+            for (auto& sg : (freeop == 1 ? op.segA : op.segB)) for (int b = 0; b < sg.len; ++b) mapX[sg.src + b] = sg.dst + b;
+            std::vector<int> pi(16, -1);
+            int cnt = 0;
+            for (int gb : grp) if (mapX[gb] >= 0 && mapX[gb] < span && pi[mapX[gb]] < 0) pi[mapX[gb]] = cnt++;
+            for (int b = 0; b < 16; ++b) if (pi[b] < 0) pi[b] = (b < span) ? cnt++ : b;
+            perm[X] = pi;
+        }
+    }
     for (int j = 0; j < n; ++j) {
         const LOp& op = L.ops[sel[j]];
         RowOp& d = rp.ops[j];
         memset(&d, 0, sizeof(d));
         rp.lop[j] = sel[j]; rp.ref_a[j] = op.a; rp.ref_b[j] = op.b; rp.ref_c[j] = op.c;
-        if (!describe_row_op(op, dtype, o, d, n_units[j], unit_cost[j], rp.why)) { rp.ok = false; return rp; }
+        RowLayouts lay;
+        { auto it = perm.find(op.a); if (it != perm.end()) lay.pa = it->second.data(); }
+        { auto it = perm.find(op.b); if (it != perm.end()) lay.pb = it->second.data(); }
+        { auto it = perm.find(op.c); if (it != perm.end()) lay.pc = it->second.data(); }
+        if (!describe_row_op(op, dtype, o, d, n_units[j], unit_cost[j], rp.why, &lay)) { rp.ok = false; return rp; }
         RowOpHot& h = d.hot;
         // where the tensors live
         auto place = [&](int tensor, int& off, char& in_arena) {
