@@ -602,7 +602,42 @@ std::vector<int> select_chain(const Lowered& L, int dtype, const RowPlanOptions&
         if (L.ops[best.front()].macs_per_amp <= L.ops[best.back()].macs_per_amp) best.erase(best.begin());
         else best.pop_back();
     }
-    if (best.size() < 2) best.clear();
+    if (best.size() < 2) { best.clear(); return best; }
+    // Side branches: the producer of a chain op's OTHER operand (small, read by nobody else) joins the program.  It sits
+    // one level before its consumer, next to the previous chain op -- whose level keeps only half of the CTA's warps
+    // busy (4 units of 32 thread-tiles for 2^11 outputs) -- so its work runs in idle issue slots and its result never
+    // goes through HBM (as kernels of their own these nodes were 4.4 ms of a 10.3 ms step at 4-6 TB/s).  Not for the first
+    // chain op (its producer would need a level of its own in front).  Greedy by work, while the arena still fits.
+    static const int side_depth = [] { const char* e = getenv("QXB_CHAIN_SIDE"); return e ? atoi(e) : 1; }();
+    if (side_depth > 0) {
+        std::vector<char> in(n, 0);
+        for (int i : best) in[i] = 1;
+        std::vector<int> level_of(n, -1);
+        for (size_t j = 0; j < best.size(); ++j) level_of[best[j]] = (int)j;
+        std::vector<int> set = best;
+        for (int round = 0; round < side_depth; ++round) {
+            std::vector<std::pair<double, int>> cand;
+            for (int i : set) {
+                if (level_of[i] <= 0) continue;
+                for (int t : {L.ops[i].a, L.ops[i].b}) {
+                    const int p = producer[t];
+                    if (p < 0 || in[p] || !small(p) || uses[t] != 1 || t == L.root || L.ops[p].nC > 10) continue;
+                    cand.push_back({-L.ops[p].macs_per_amp, p});
+                    level_of[p] = level_of[i] - 1;
+                }
+            }
+            std::sort(cand.begin(), cand.end());
+            bool any = false;
+            for (auto& c : cand) {
+                std::vector<int> trial = set;
+                trial.push_back(c.second);
+                std::sort(trial.begin(), trial.end());
+                if (fits(trial)) { set = trial; in[c.second] = 1; any = true; }
+            }
+            if (!any) break;
+        }
+        best = set;
+    }
     return best;
 }
 
