@@ -608,7 +608,10 @@ std::vector<int> select_chain(const Lowered& L, int dtype, const RowPlanOptions&
     // busy (4 units of 32 thread-tiles for 2^11 outputs) -- so its work runs in idle issue slots and its result never
     // goes through HBM (as kernels of their own these nodes were 4.4 ms of a 10.3 ms step at 4-6 TB/s).  Not for the first
     // chain op (its producer would need a level of its own in front).  Greedy by work, while the arena still fits.
-    static const int side_depth = [] { const char* e = getenv("QXB_CHAIN_SIDE"); return e ? atoi(e) : 1; }();
+    // MEASURED (profiles/r2_summary.md): not a win -- the fused launch grows from 6.52 to 8.10 ms (depth 1: 5 side nodes worth
+    // ~1 ms as kernels) / 8.81 ms (depth 2), the step from 10.26 to 10.92 / 10.83 ms: the extra staging copies and units
+    // lengthen every level.  Off by default; QXB_CHAIN_SIDE=<depth> enables it (GPU parity tests pass with it on).
+    static const int side_depth = [] { const char* e = getenv("QXB_CHAIN_SIDE"); return e ? atoi(e) : 0; }();
     if (side_depth > 0) {
         std::vector<char> in(n, 0);
         for (int i : best) in[i] = 1;
