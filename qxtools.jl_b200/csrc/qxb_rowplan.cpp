@@ -166,41 +166,30 @@ bool describe_row_op(const LOp& op, int dtype, const RowPlanOptions& o, RowOp& d
         mbits.clear(); nbits.clear(); ma = nb = 0; ntt = nC;
     }
     static const bool bank_opt = [] { const char* e = getenv("QXB_ROW_BANK_OPT"); return !e || atoi(e) != 0; }();
-    // Shared-memory wavefronts of one access.  Model (fits what ncu counts: an all-distinct LDS.128 = 4 wavefronts, an
-    // all-lanes-one-address LDS.128 = 2): the access is served a group of lanes at a time -- 16 lanes for 16-byte elements,
-    // the whole warp for 8-byte ones -- and a group costs max(ceil(distinct addresses / R), most distinct addresses on one
-    // 128-byte residue) wavefronts, R = 128 bytes / element size.  So lanes that share an operand address (an operand that
-    // does not depend on a lane bit) are as valuable as lanes on distinct banks: with two M-only and two N-only bits as the
-    // low lane bits BOTH operand loads of a ComplexF64 tile take 2 wavefronts instead of 4.
-    // `bits` = the C bits that index the lanes of a group.
-    const int q = dtype == QXB_C64 ? 4 : 5;
-    const int resid = dtype == QXB_C64 ? 8 : 16;
+    // shared-memory wavefronts of one access of the lanes of a wavefront group (8 lanes for 16-byte elements, 16 for 8-byte
+    // ones) whose index bits are the C bits `bits`: distinct addresses falling on the same 128-byte residue serialise
+    const int q = dtype == QXB_C64 ? 3 : 4;
     auto waves = [&](const int* bits, const std::vector<int>& map) {
-        int cnt[16] = {0}, seen[32], ns = 0;
+        int cnt[16] = {0}, seen[16], ns = 0;
         for (int l = 0; l < (1 << q); ++l) {
             int a = 0;
             for (int i = 0; i < q; ++i) if (((l >> i) & 1) && map[bits[i]] >= 0) a |= 1 << map[bits[i]];
             bool dup = false;
             for (int i = 0; i < ns; ++i) dup |= seen[i] == a;
-            if (!dup) { seen[ns++] = a; ++cnt[a & (resid - 1)]; }
+            if (!dup) { seen[ns++] = a; ++cnt[a & ((1 << q) - 1)]; }
         }
-        return std::max((ns + resid - 1) / resid, *std::max_element(cnt, cnt + resid));
-    };
-    auto waves_free = [&](const int* bits, const std::vector<int>& map) {      // an operand whose layout is still free
-        int present = 0;
-        for (int i = 0; i < q; ++i) present += map[bits[i]] >= 0;
-        return std::max(1, (1 << present) / resid);
+        return *std::max_element(cnt, cnt + (1 << q));
     };
     // best group bits among the non-tile bits `ord` for a (2^tma x 2^tnb) register tile: (cost, bits)
     auto best_group = [&](const std::vector<int>& ord, int tma, int tnb, std::vector<int>& best) {
         const double nk = std::ldexp(1.0, nK), tm = std::ldexp(1.0, tma), tn = std::ldexp(1.0, tnb);
         const int n = (int)ord.size();
         double best_cost = -1;
-        int idx[5], pick[5];
+        int idx[4], pick[4];
         for (int i = 0; i < q; ++i) idx[i] = i;
         while (true) {
             for (int i = 0; i < q; ++i) pick[i] = ord[idx[i]];
-            const double wa = free_operand == 1 ? waves_free(pick, mapA) : waves(pick, mapA), wb = free_operand == 2 ? waves_free(pick, mapB) : waves(pick, mapB);
+            const double wa = free_operand == 1 ? 1 : waves(pick, mapA), wb = free_operand == 2 ? 1 : waves(pick, mapB);
             const double cost = nk * (tm * wa + tn * wb) + tm * tn * waves(pick, mapC);
             if (best_cost < 0 || cost < best_cost) { best.assign(pick, pick + q); best_cost = cost; }
             int i = q - 1;

@@ -23,9 +23,8 @@ print("fused ops:", rp.fused_names, "levels", rp.n_levels, "descs", len(rp.descs
 
 
 def wavefronts(offs, act):
-    """offs: element offsets of the 32 lanes.  Model of csrc/qxb_rowplan.cpp: 16 lanes at a time for 16-byte elements, the
-    whole warp for 8-byte ones; a group costs max(ceil(distinct / R), most distinct addresses on one 128-byte residue)."""
-    per, resid = (16, 8) if es == 16 else (32, 16)
+    """offs: element offsets of the 32 lanes; 128-bit (c64) accesses go a quarter-warp at a time, 64-bit a half-warp."""
+    per = 8 if es == 16 else 16
     tot = 0
     for q in range(0, 32, per):
         o = [int(offs[l]) for l in range(q, q + per) if act[l]]
@@ -34,8 +33,8 @@ def wavefronts(offs, act):
         uniq = set(o)
         groups = {}
         for e in uniq:
-            groups.setdefault(e % resid, set()).add(e)
-        tot += max((len(uniq) + resid - 1) // resid, max(len(v) for v in groups.values()))
+            groups.setdefault(e % per, set()).add(e)
+        tot += max(len(v) for v in groups.values())
     return tot
 
 
