@@ -18,7 +18,8 @@ N > 1 : one process per GPU (torchrun).  Default partition: every rank takes a c
         bitstrings; fixing slice variables per rank instead -- `--partition slices`, what north_star names --
         leaves the slice-independent part of every node replicated and measured 0.44 efficiency at N = 8,
         profiles/r1_scaling.md); the shards meet in ONE NCCL all-gather of [n_amp / N] complex numbers per rank
-        -> "scaling": "strong".
+        -> "scaling": "strong".  The gather of step i runs on NCCL's stream while step i + 1 computes into the
+        other of two shard buffers; the pipeline is drained before the closing event of the timed region.
 The plan and every kernel knob are the library's defaults (deterministic: the re-planner is seeded); `--autotune`
 adds the measured choice among exact alternatives of round 1 (qxb200/tuning.py).
 """
@@ -345,11 +346,27 @@ def run_gpu(args):
     # sum); slice partitions and ragged shards need the sum -> all-reduce of the zero-padded vector
     gather = world > 1 and mode == "amps" and n_amp % world == 0
     shard_d = torch.zeros(max(n_mine, 1), dtype=cdt, device=dev) if gather else None
+    # the all-gather of step i runs on NCCL's stream while step i + 1 computes into the other shard buffer; a buffer is
+    # reused only after its gather has completed (stream-side wait), and drain() closes the pipeline inside the timed region
+    shard_alt = torch.zeros(max(n_mine, 1), dtype=cdt, device=dev) if gather else None
+    pending = [None, None]
+    turn = [0]
+
+    def drain():
+        for i in (0, 1):
+            if pending[i] is not None:
+                pending[i].wait()
+                pending[i] = None
 
     def step_device():
         if gather:
-            g.amplitudes_device(bits_d.data_ptr() + a0 * n_q, n_mine, shard_d.data_ptr(), 0, S)
-            dist.all_gather_into_tensor(torch.view_as_real(out_d), torch.view_as_real(shard_d))
+            i = turn[0] & 1
+            turn[0] += 1
+            buf = shard_d if i == 0 else shard_alt
+            if pending[i] is not None:
+                pending[i].wait()
+            g.amplitudes_device(bits_d.data_ptr() + a0 * n_q, n_mine, buf.data_ptr(), 0, S)
+            pending[i] = dist.all_gather_into_tensor(torch.view_as_real(out_d), torch.view_as_real(buf), async_op=True)
             return
         if mode == "amps":
             out_d.zero_()
@@ -401,6 +418,7 @@ def run_gpu(args):
 
     for _ in range(max(args.warmup, 3)):
         step_device()
+    drain()
     barrier()
     ws_bytes = g.stats()["workspace_bytes"]
     flush = ws_bytes < 4 * 126e6            # working set could sit in the 126 MB L2 -> flush between steps
@@ -414,6 +432,7 @@ def run_gpu(args):
         ev0.record(stream)
         for _ in range(args.steps):
             step_device()
+        drain()                             # the last gathers complete before the closing event
         ev1.record(stream)
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -424,6 +443,7 @@ def run_gpu(args):
             flush_buf.fill_(1)              # evicts L2; not inside the timed event pair
             a.record(stream)
             step_device()
+            drain()
             b.record(stream)
         barrier()
         ms = sum(a.elapsed_time(b) for a, b in evs)
@@ -488,7 +508,7 @@ def run_gpu(args):
                        "n_qubits": n_q, "complex": w["dtype"],
                        "partition": ("single GPU" if world == 1 else
                                      f"bitstrings split over {world} ranks, all slices each; shards meet in one NCCL "
-                                     f"{'all-gather' if gather else 'all-reduce'}" if mode == "amps" else
+                                     f"{'all-gather (asynchronous: it overlaps the next step, drained inside the timed region)' if gather else 'all-reduce'}" if mode == "amps" else
                                      f"all bitstrings on every rank, slice variables {[v + 1 for v in assign[0]]} fixed per rank; one NCCL all-reduce"
                                      if assign is not None else f"contiguous slice ranges / {world}; one NCCL all-reduce"),
                        "plan": ("re-planned for batched execution (qxb_graph_replan, exact re-association, seeded): "
