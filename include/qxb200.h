@@ -79,6 +79,16 @@ typedef struct qxb_options {
                                   0 = auto (= off: measured 8 % slower than the SIMT register tiles on the headline chain,
                                   both are latency-bound, profiles/r2_summary.md), 1 = off, 2 = on                     */
     int32_t row_chunk_max_amps;/* auto mode: largest call (bitstrings) whose chunk phase runs as a row program; 0 = 512 */
+    int32_t streaming;         /* "huge x tiny" nodes (one operand >= 2^20 elements, the other <= 64 KB, K <= 2^5, no batch bits)
+                                  on bigsmall_kernel (csrc/qxb_kred.cu: a thread owns one position of the big operand and all its
+                                  outputs, DRAM traffic |big| + |C| once): 0 = auto (on), 1 = off, 2 = on with the big operand
+                                  staged by TMA bulk copies where its layout allows, 3 = on with packed FFMA2 accumulators
+                                  (ComplexF32); 2 and 3 measured no faster than the default, profiles/r2_summary.md */
+    int32_t row_bank_opt;      /* row programs / fused chain / ring kernel: choose the lane bits of a unit (and, inside a fused
+                                  chain, the arena layout of the intermediates) by the shared-memory bank-conflict model:
+                                  0 = auto (on), 1 = off (lanes = the lowest C bits outside the register tile, as lowered) */
+    int32_t chain_side;        /* fused chain: also take the producers of the chain ops' other operands, up to this depth
+                                  (they run in the levels' idle warps); 0 = off (measured slower on the headline plan) */
 } qxb_options;
 
 /* library */

@@ -35,15 +35,32 @@ mutable struct Graph
     end
 end
 
-struct Options
-    hbm_budget_bytes::Int64
-    amp_batch::Int64
-    profile::Int32
-    no_cuda_graph::Int32
-    sum_at_root::Int32
-    no_smem_stage::Int32
-    no_gemm::Int32
-    gemm_mode::Int32        # 0 = auto, 1 = SIMT FMA GEMM only, 2 = tensor-core GEMM (DMMA / 3xTF32)
+# Mirror of `qxb_options` (include/qxb200.h), field for field; all zero = the library's defaults.  The constructors below
+# pass C_NULL (defaults); build an `Options`, wrap it in a `Ref` and pass it to `qxb_graph_compile` to change a knob.
+Base.@kwdef struct Options
+    hbm_budget_bytes::Int64 = 0
+    amp_batch::Int64 = 0
+    profile::Int32 = 0
+    no_cuda_graph::Int32 = 0
+    sum_at_root::Int32 = 0
+    no_smem_stage::Int32 = 0
+    no_gemm::Int32 = 0
+    gemm_mode::Int32 = 0            # 0 = auto, 1 = SIMT FMA GEMM only, 2 = tensor cores (tcgen05 / DMMA), 4 = mma.sync only
+    row_programs::Int32 = 0         # 0 = auto, 1 = never, 2 = both phases, 3 = block phase only
+    min_lob::Int32 = 0
+    kc_regs_multi::Int32 = 0
+    kc_regs_one::Int32 = 0
+    smem_tma::Int32 = 0
+    row_min_tt_bits::Int32 = 0
+    row_tile_regs::Int32 = 0
+    row_ctas_per_sm::Int32 = 0
+    ring::Int32 = 0
+    chain::Int32 = 0
+    row_dmma::Int32 = 0
+    row_chunk_max_amps::Int32 = 0
+    streaming::Int32 = 0            # huge x tiny nodes on bigsmall_kernel: 0 = auto (on), 1 = off, 2 = TMA staging, 3 = FFMA2
+    row_bank_opt::Int32 = 0         # 0 = auto (on), 1 = off
+    chain_side::Int32 = 0           # depth of the side branches a fused chain takes in (0 = none)
 end
 
 i64(v) = Int64.(collect(v))

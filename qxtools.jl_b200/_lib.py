@@ -44,7 +44,8 @@ class Options(C.Structure):
                 ("row_programs", C.c_int32), ("min_lob", C.c_int32), ("kc_regs_multi", C.c_int32),
                 ("kc_regs_one", C.c_int32), ("smem_tma", C.c_int32), ("row_min_tt_bits", C.c_int32),
                 ("row_tile_regs", C.c_int32), ("row_ctas_per_sm", C.c_int32), ("ring", C.c_int32),
-                ("chain", C.c_int32), ("row_dmma", C.c_int32), ("row_chunk_max_amps", C.c_int32)]
+                ("chain", C.c_int32), ("row_dmma", C.c_int32), ("row_chunk_max_amps", C.c_int32),
+                ("streaming", C.c_int32), ("row_bank_opt", C.c_int32), ("chain_side", C.c_int32)]
 
 
 class Params(C.Structure):

@@ -509,7 +509,7 @@ Node contract_node(const RunCtx& c, int i) {
     // "big x small" streaming node (qxb_kred.cu, bigsmall_kernel): one operand huge, the other tiny with a few N-only
     // bits -- every thread owns one position of the big operand and 2^nlo outputs (all of them when the small operand
     // has <= 5 N bits; further N bits go to the CTA index, next to the thread bits so that the re-reads hit in L2)
-    if (!g->opts.no_gemm && knob(0, "QXB_BIGSMALL", 1) != 0 && op.n_batch == 0 && op.nK <= 5) {
+    if (!g->opts.no_gemm && g->opts.streaming != 1 && knob(0, "QXB_BIGSMALL", 1) != 0 && op.n_batch == 0 && op.nK <= 5) {
         const bool a_big = op.elems_a >= op.elems_b;
         const LTensor &TB = a_big ? A : B, &TS = a_big ? B : A;
         const auto& segBig = a_big ? op.segA : op.segB;
@@ -518,7 +518,7 @@ Node contract_node(const RunCtx& c, int i) {
         const auto& kSm = a_big ? op.segKB : op.segKA;
         const int nN = a_big ? op.n_n : op.n_m;
         const double big_elems = a_big ? op.elems_a : op.elems_b;
-        const bool packed = g->dtype == QXB_C32 && knob(0, "QXB_BIGSMALL_FFMA2", 0) != 0;
+        const bool packed = g->dtype == QXB_C32 && (g->opts.streaming == 3 || knob(0, "QXB_BIGSMALL_FFMA2", 0) != 0);
         const int max_lo = (g->dtype == QXB_C32 && !packed) ? 5 : 4;
         const int nlo = nN <= max_lo ? nN : 4, nhi = nN - nlo;
         const void* bf = nN >= 1 ? bigsmall_func(g->dtype, nlo, knob(0, "QXB_BIGSMALL_KT", 1) != 0 ? op.nK : 0, packed) : nullptr;
@@ -573,7 +573,7 @@ Node contract_node(const RunCtx& c, int i) {
                 // TMA variant: the 256 positions of a CTA are one contiguous run of the big operand at every k
                 const size_t small_pad = (small_bytes + 15) & ~(size_t)15;
                 const int stages = (int)std::min<size_t>(3, (110 * 1024 - small_pad - 64) / kBigSmallStageBytes);
-                const void* tf = (knob(0, "QXB_BIGSMALL_TMA", 0) != 0 && q.U == 1 && stages >= 2 && q.tA[0].src == 0 && q.tA[0].dst == 0 &&
+                const void* tf = ((g->opts.streaming == 2 || knob(0, "QXB_BIGSMALL_TMA", 0) != 0) && q.U == 1 && stages >= 2 && q.tA[0].src == 0 && q.tA[0].dst == 0 &&
                                   q.tA[0].len >= 8 && (uintptr_t)q.big % 16 == 0) ? bigsmall_tma_func(g->dtype, nlo) : nullptr;
                 n.block = dim3(kThreads);
                 if (tf) {
@@ -852,6 +852,7 @@ Node contract_node(const RunCtx& c, int i) {
                 rd.tried = true;
                 RowPlanOptions ro;
                 ro.bank_search_tiles = true;
+                ro.bank_opt = g->opts.row_bank_opt != 1;
                 ro.min_tt_bits = knob(0, "QXB_RING_MIN_TT", 8);
                 ro.tile_reg_budget = knob(0, "QXB_RING_TILE_REGS", 100);
                 ro.dmma = (g->opts.row_dmma == 2 || (g->opts.row_dmma == 0 && knob(0, "QXB_ROW_DMMA", 0) != 0));
@@ -944,6 +945,7 @@ void build_row_programs(qxb_graph* g, Variant& v) {
     v.rows_block = v.rows_chunk = false;
     if (knob(0, "QXB_ROWPROG", 1) == 0 || g->opts.row_programs == 1) return;
     RowPlanOptions o;
+    o.bank_opt = g->opts.row_bank_opt != 1;
     o.min_tt_bits = knob(g->opts.row_min_tt_bits, "QXB_ROW_MIN_TT", 6);
     o.tile_reg_budget = knob(g->opts.row_tile_regs, "QXB_ROW_TILE_REGS", 100);
     o.alap = knob(0, "QXB_ROW_ALAP", 1) != 0;
@@ -1027,6 +1029,8 @@ Variant* get_variant(qxb_graph* g, uint64_t free_mask) {
     // arena plan and the dependency edges must see the chain as one step)
     RowPlanOptions co;
     co.bank_search_tiles = knob(0, "QXB_CHAIN_BANK_TILES", 1) != 0;
+    co.bank_opt = g->opts.row_bank_opt != 1;
+    co.chain_side = g->opts.chain_side;
     const bool chain_on = knob(0, "QXB_CHAIN", 1) != 0 && g->opts.row_programs != 1 && g->opts.chain != 1;
     if (chain_on) {
         co.min_tt_bits = knob(0, "QXB_CHAIN_MIN_TT", 7);
@@ -2298,6 +2302,8 @@ int64_t qxb_debug_rowprog(qxb_graph* g, uint64_t free_mask, int phase, void* buf
         std::vector<int> chain;
         RowPlanOptions co;
         co.bank_search_tiles = knob(0, "QXB_CHAIN_BANK_TILES", 1) != 0;
+        co.bank_opt = g->opts.row_bank_opt != 1;
+        co.chain_side = g->opts.chain_side;
         if (phase == 3) {
             co.min_tt_bits = knob(0, "QXB_CHAIN_MIN_TT", 7);
             co.max_arena_bytes = (233472 / 2 - 1024) - (long long)row_fixed_smem_bytes(512);
@@ -2306,6 +2312,7 @@ int64_t qxb_debug_rowprog(qxb_graph* g, uint64_t free_mask, int phase, void* buf
         }
         plan_memory(L);
         RowPlanOptions o;
+        o.bank_opt = g->opts.row_bank_opt != 1;
         o.min_tt_bits = knob(g->opts.row_min_tt_bits, "QXB_ROW_MIN_TT", 6);
         o.tile_reg_budget = knob(g->opts.row_tile_regs, "QXB_ROW_TILE_REGS", 100);
         o.alap = knob(0, "QXB_ROW_ALAP", 1) != 0;

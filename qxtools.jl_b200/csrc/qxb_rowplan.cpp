@@ -165,7 +165,8 @@ bool describe_row_op(const LOp& op, int dtype, const RowPlanOptions& o, RowOp& d
     if (ntt < 5) {                                       // fewer than 32 thread-tiles: lanes split K instead
         mbits.clear(); nbits.clear(); ma = nb = 0; ntt = nC;
     }
-    static const bool bank_opt = [] { const char* e = getenv("QXB_ROW_BANK_OPT"); return !e || atoi(e) != 0; }();
+    static const bool bank_env = [] { const char* e = getenv("QXB_ROW_BANK_OPT"); return !e || atoi(e) != 0; }();
+    const bool bank_opt = bank_env && o.bank_opt;
     // shared-memory wavefronts of one access of the lanes of a wavefront group (8 lanes for 16-byte elements, 16 for 8-byte
     // ones) whose index bits are the C bits `bits`: distinct addresses falling on the same 128-byte residue serialise
     const int q = dtype == QXB_C64 ? 3 : 4;
@@ -459,7 +460,7 @@ RowProgramHost build_row_program(const Lowered& L, Phase phase, int dtype, const
     // conflict-free, and that operand's layout puts the group's bits at address bits 0, 1, 2 (distinct 16-byte bank groups).
     std::map<int, std::vector<int>> perm;                   // LTensor -> old address bit -> new address bit
     static const bool layout_opt = [] { const char* e = getenv("QXB_ROW_LAYOUT_OPT"); return !e || atoi(e) != 0; }();
-    if (subset && o.bank_search_tiles && layout_opt) {
+    if (subset && o.bank_search_tiles && o.bank_opt && layout_opt) {
         std::map<int, int> n_readers;
         for (const LOp& op : L.ops) { ++n_readers[op.a]; ++n_readers[op.b]; }
         for (int j = n - 1; j >= 0; --j) {
@@ -610,8 +611,9 @@ std::vector<int> select_chain(const Lowered& L, int dtype, const RowPlanOptions&
     // chain op (its producer would need a level of its own in front).  Greedy by work, while the arena still fits.
     // MEASURED (profiles/r2_summary.md): not a win -- the fused launch grows from 6.52 to 8.10 ms (depth 1: 5 side nodes worth
     // ~1 ms as kernels) / 8.81 ms (depth 2), the step from 10.26 to 10.92 / 10.83 ms: the extra staging copies and units
-    // lengthen every level.  Off by default; QXB_CHAIN_SIDE=<depth> enables it (GPU parity tests pass with it on).
-    static const int side_depth = [] { const char* e = getenv("QXB_CHAIN_SIDE"); return e ? atoi(e) : 0; }();
+    // lengthen every level.  Off by default; qxb_options.chain_side (or QXB_CHAIN_SIDE=<depth>) enables it (GPU parity tests pass with it on).
+    static const int side_env = [] { const char* e = getenv("QXB_CHAIN_SIDE"); return e ? atoi(e) : 0; }();
+    const int side_depth = o.chain_side > 0 ? o.chain_side : side_env;
     if (side_depth > 0) {
         std::vector<char> in(n, 0);
         for (int i : best) in[i] = 1;

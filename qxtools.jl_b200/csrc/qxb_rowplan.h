@@ -18,6 +18,8 @@ struct RowPlanOptions {
     bool dmma = true;             // ComplexF64 nodes with >= 3 M-only / N-only bits: 8 x 8 tiles on the FP64 tensor pipe
     double chain_min_macs = 2048; // fused chain: complex MACs per row below which an end node is not worth a level
     long long max_arena_bytes = 200 * 1024;
+    bool bank_opt = true;             // choose the low lane bits of a unit (and chain-intermediate layouts) by the bank-conflict model
+    int chain_side = 0;               // select_chain: depth of side branches taken into the fused program (0 = a pure path)
     bool bank_search_tiles = false;   // also choose WHICH M-only / N-only bits form the register tile by the bank-conflict model
                                       // (a few 10^5 evaluations per op: for the handful of ops of a fused chain or a ring launch)
 };

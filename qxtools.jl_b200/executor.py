@@ -240,15 +240,20 @@ class Graph:
                  cuda_graph: bool = True, sum_at_root: bool = False, smem_stage: bool = True,
                  gemm: bool = True, gemm_mode: int = 0, row_programs=True, min_lob: int = 0,
                  kc_regs_multi: int = 0, kc_regs_one: int = 0, smem_tma: bool = True, row_min_tt_bits: int = 0,
-                 row_tile_regs: int = 0, row_ctas_per_sm: int = 0, row_chunk_max_amps: int = 0, ring: bool = True, chain: bool = True, row_dmma: bool = False) -> Options:
+                 row_tile_regs: int = 0, row_ctas_per_sm: int = 0, row_chunk_max_amps: int = 0, ring: bool = True, chain: bool = True, row_dmma: bool = False,
+                 streaming=True, row_bank_opt: bool = True, chain_side: int = 0) -> Options:
         """``qxb_options`` (include/qxb200.h); 0 / default = the library's own choice.
         ``row_programs``: True = auto (block phase always, chunk phase for small calls), False = never,
-        "all" = both phases whenever the row fits shared memory, "block" = block phase only."""
+        "all" = both phases whenever the row fits shared memory, "block" = block phase only.
+        ``streaming``: True = auto (huge x tiny nodes on ``bigsmall_kernel``), False = never, "tma" / "ffma2" = its
+        opt-in variants.  ``row_bank_opt``: bank-aware lane bits / arena layouts in row programs.  ``chain_side``: depth of
+        the side branches a fused chain takes in (0 = none)."""
         rp = {True: 0, False: 1, "auto": 0, "never": 1, "all": 2, "block": 3}[row_programs]
         return Options(hbm_budget_bytes, amp_batch, 1 if profile else 0, 0 if cuda_graph else 1,
                        1 if sum_at_root else 0, 0 if smem_stage else 1, 0 if gemm else 1, gemm_mode,
                        rp, min_lob, kc_regs_multi, kc_regs_one, 0 if smem_tma else 2,
-                       row_min_tt_bits, row_tile_regs, row_ctas_per_sm, 0 if ring else 1, 0 if chain else 1, 2 if row_dmma else 0, row_chunk_max_amps)
+                       row_min_tt_bits, row_tile_regs, row_ctas_per_sm, 0 if ring else 1, 0 if chain else 1, 2 if row_dmma else 0, row_chunk_max_amps,
+                       {True: 0, False: 1, "tma": 2, "ffma2": 3}[streaming], 0 if row_bank_opt else 1, chain_side)
 
     def configure(self, **kw) -> "Graph":
         o = self._options(**kw)

@@ -140,3 +140,38 @@ def test_plain_c_consumer_on_gpu(gpu, tmp_path):
     r = subprocess.run([exe, "gpu"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "gpu amplitudes ok" in r.stdout
+
+
+def _header_option_fields():
+    """(type, name) of every field of `qxb_options` in include/qxb200.h, in order."""
+    import re
+    txt = open(os.path.join(ROOT, "include", "qxb200.h")).read()
+    body = txt[txt.index("typedef struct qxb_options {"):txt.index("} qxb_options;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    return re.findall(r"\b(int64_t|int32_t)\s+(\w+)\s*;", body)
+
+
+def test_options_mirrors_match_the_header():
+    """The ctypes mirror (qxb200/_lib.py) and the Julia mirror (julia/QXB200.jl) of `qxb_options` list the header's fields
+    in the header's order with the header's widths; sizeof agrees with a C compile of the header."""
+    import ctypes as C
+    import re
+    import subprocess
+    import tempfile
+    from qxb200 import _lib
+    fields = _header_option_fields()
+    assert len(fields) >= 23
+    want = [(n, C.c_int64 if t == "int64_t" else C.c_int32) for t, n in fields]
+    assert [(n, t) for n, t in _lib.Options._fields_] == want
+    jl = open(os.path.join(ROOT, "julia", "QXB200.jl")).read()
+    body = jl[jl.index("struct Options"):]
+    body = body[:body.index("\nend")]
+    jfields = re.findall(r"^\s+(\w+)::(Int64|Int32)", body, flags=re.M)
+    assert jfields == [(n, "Int64" if t == "int64_t" else "Int32") for t, n in fields]
+    d = tempfile.mkdtemp()
+    src = os.path.join(d, "sz.c")
+    with open(src, "w") as f:
+        f.write('#include <stdio.h>\n#include "%s"\nint main(void) { printf("%%zu", sizeof(qxb_options)); return 0; }\n'
+                % os.path.join(ROOT, "include", "qxb200.h"))
+    subprocess.check_call(["gcc", src, "-o", os.path.join(d, "sz")])
+    assert int(subprocess.check_output([os.path.join(d, "sz")]).decode()) == C.sizeof(_lib.Options)
