@@ -404,27 +404,21 @@ def test_big_times_small_streaming_node(gpu, dtype, nk, nn, big_first, aligned):
     bs = ["-"] if aligned else ["0", "1", "+"]               # the TMA variant takes single-row launches
     ref = orc.amplitudes(orc.parse_dsl(txt), data, bs)
     import os, tempfile
-    if aligned:
-        os.environ["QXB_BIGSMALL_TMA"] = "1"                  # opt-in variant (measured no faster than the register one)
-    try:
-        g = Graph.from_dsl(txt, data, dtype).compile(profile=True, row_programs=False)
-        got = g.amplitudes(bs)
-    finally:
-        os.environ.pop("QXB_BIGSMALL_TMA", None)
+    # aligned layouts also go through the opt-in TMA-staged variant (measured no faster than the register one)
+    g = Graph.from_dsl(txt, data, dtype).compile(profile=True, row_programs=False, streaming="tma" if aligned else True)
+    got = g.amplitudes(bs)
     assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 2e-5)
     prof = g.profile_dump(os.path.join(tempfile.mkdtemp(), "p.json"))
     kern = [o["kernel"] for v in prof["variants"] for o in v["ops"] if o["name"] == "c"][0]
     assert kern == ("bigsmall_tma" if aligned else "bigsmall"), kern
-    if aligned:                                               # the default (register) kernel on the same layout ...
-        got2 = Graph.from_dsl(txt, data, dtype).compile(row_programs=False).amplitudes(bs)
-        assert np.max(np.abs(got2 - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 2e-5)
-    elif dtype == "c32" and nn <= 4:                          # ... and the packed-FFMA2 accumulators (opt-in)
-        os.environ["QXB_BIGSMALL_FFMA2"] = "1"
-        try:
-            got3 = Graph.from_dsl(txt, data, dtype).compile(row_programs=False).amplitudes(bs)
-        finally:
-            del os.environ["QXB_BIGSMALL_FFMA2"]
-        assert np.max(np.abs(got3 - ref)) / np.max(np.abs(ref)) < 2e-5
+    variants = [dict(streaming=False)]                        # the node through the general kernels
+    if aligned:
+        variants.append(dict())                               # the default (register) kernel on the aligned layout
+    elif dtype == "c32":
+        variants.append(dict(streaming="ffma2"))              # packed-FFMA2 accumulators (opt-in)
+    for kw in variants:
+        alt = Graph.from_dsl(txt, data, dtype).compile(row_programs=False, **kw).amplitudes(bs)
+        assert np.max(np.abs(alt - ref)) / np.max(np.abs(ref)) < (1e-12 if dtype == "c64" else 2e-5), kw
 
 
 @pytest.mark.parametrize("dtype", ["c64", "c32"])

@@ -107,7 +107,7 @@ def test_many_rows_per_cta(gpu):
 
 
 @pytest.mark.parametrize("kw", [dict(cuda_graph=False), dict(profile=True), dict(row_min_tt_bits=8), dict(row_min_tt_bits=6),
-                                dict(row_tile_regs=64), dict(row_ctas_per_sm=1), dict(row_dmma=True)])
+                                dict(row_tile_regs=64), dict(row_ctas_per_sm=1), dict(row_dmma=True), dict(row_bank_opt=False)])
 def test_row_options_agree(gpu, kw):
     txt, data, bs = rqc_case(4, 4, 12, 4, n_amp=32)
     ref = Graph.from_dsl(txt, data, "c64", replan=16, replan_n_amp=1024).compile(row_programs=False).amplitudes(bs)
@@ -199,6 +199,10 @@ def test_fused_chain_equals_per_op(gpu, dtype, tol):
     # the same chain with its big nodes on the FP64 tensor pipe (8 x 8 DMMA tiles; ComplexF64 only, a no-op for c32)
     tc = Graph.from_dsl(plan, data, dtype).compile(row_programs="block", row_dmma=True).amplitudes(bits)
     assert np.max(np.abs(tc - ref)) < tol * max(np.max(np.abs(ref)), 2.0 ** (-49 / 2))
+    # lanes as lowered (no bank-aware lane bits, no re-laid-out intermediates), and the chain with side branches in its levels
+    for kw in (dict(row_bank_opt=False), dict(chain_side=1), dict(chain_side=2, row_bank_opt=False)):
+        alt = Graph.from_dsl(plan, data, dtype).compile(row_programs="block", **kw).amplitudes(bits)
+        assert np.max(np.abs(alt - ref)) < tol * max(np.max(np.abs(ref)), 2.0 ** (-49 / 2)), kw
     # a slice sub-range (blocks with fixed variables: other variants, other chains) against the oracle
     bs = ["".join("01"[b] for b in row) for row in bits[:2]]
     o = orc.amplitudes(orc.parse_dsl(plan), data, bs, slice_begin=5, slice_end=8)
