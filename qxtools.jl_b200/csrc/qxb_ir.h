@@ -145,6 +145,9 @@ struct Lowered {
     double root_scale = 1.0;                 // prod of extents of free vars the root does not depend on
     // arena sizes in elements: const, block, and chunk = per_amp * n_amp
     int64_t const_elems = 0, block_elems = 0, chunk_elems_per_amp = 0;
+    // ops [fused_first, fused_last] run as ONE launch (a fused chain, qxb_rowplan.h make_contiguous): every row of the
+    // batch reads the launch's inputs at its own time, so plan_memory releases no operand of these ops before the last one
+    int fused_first = -1, fused_last = -1;
 };
 
 // Lower for a given set of free (batched) slice variables.

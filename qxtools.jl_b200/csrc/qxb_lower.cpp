@@ -523,6 +523,7 @@ void plan_memory(Lowered& L) {
     Arena ar[3];
     struct Freed { int phase; int64_t off, size; int last_reader; };
     std::vector<Freed> freed;
+    std::vector<int> deferred;               // operands of a fused launch waiting for its last op
     for (int ti : L.output_leaves) {
         LTensor& t = L.tensors[ti];
         t.offset = ar[PH_CHUNK].alloc(unit_elems(t));
@@ -536,14 +537,27 @@ void plan_memory(Lowered& L) {
             if (f.phase == (int)op.phase && f.off < C.offset + n && C.offset < f.off + f.size &&
                 std::find(op.deps.begin(), op.deps.end(), f.last_reader) == op.deps.end())
                 op.deps.push_back(f.last_reader);
+        // Inside a fused launch nothing is released before its last op: one launch works through all rows of the batch,
+        // so a result row written early (any op's C that leaves the launch) must not land on an operand row another CTA has
+        // still to read.  The deferred operands go back to the arena at the last op, after its C has its place.
+        const bool in_fused = L.fused_first >= 0 && (int)oi >= L.fused_first && (int)oi <= L.fused_last;
         for (int ti : {op.a, op.b}) {
             LTensor& T = L.tensors[ti];
             if (T.is_leaf || T.persistent || T.offset < 0) continue;
             if (T.last_use == (int)oi && T.phase == op.phase && unit_elems(T) >= kNoReuseBelow) {
+                if (in_fused && (int)oi < L.fused_last) { deferred.push_back(ti); T.last_use = -2; continue; }
                 ar[T.phase].release(T.offset, unit_elems(T));
                 freed.push_back(Freed{(int)T.phase, T.offset, unit_elems(T), (int)oi});
                 T.last_use = -2;          // released once, even if it is both operands
             }
+        }
+        if (in_fused && (int)oi == L.fused_last) {
+            for (int ti : deferred) {
+                LTensor& T = L.tensors[ti];
+                ar[T.phase].release(T.offset, unit_elems(T));
+                freed.push_back(Freed{(int)T.phase, T.offset, unit_elems(T), (int)oi});
+            }
+            deferred.clear();
         }
     }
     L.const_elems = ar[PH_CONST].peak;

@@ -675,6 +675,7 @@ std::vector<int> make_contiguous(Lowered& L, const std::vector<int>& chain) {
         }
     std::vector<int> out;
     for (int c : chain) out.push_back(new_of[c]);
+    L.fused_first = out.front(); L.fused_last = out.back();      // plan_memory: no operand released inside the launch
     return out;
 }
 
