@@ -305,6 +305,9 @@ int64_t qxb_debug_templates(qxb_graph* g, int n_free, void* buf, int64_t buflen)
  * free_mask, serialised (layout in csrc/qxb_exec.cu) for tests/rowprog_emulator.py; returns the bytes needed.
  * Host logic only. */
 int64_t qxb_debug_rowprog(qxb_graph* g, uint64_t free_mask, int phase, void* buf, int64_t buflen);
+/* Test hook: the chunk-phase HBM arena plan of a variant with its fused chain, as text ("fused first last", "op ...",
+ * "tensor index offset elems amp leaf" lines); returns the bytes needed (including the final NUL), negative = error. */
+int64_t qxb_debug_fused_plan(qxb_graph* g, uint64_t free_mask, char* buf, int64_t buflen);
 /* test hook: the lookup3 checksum of HDF5 version-2 metadata, checked against Jenkins' published vectors */
 uint32_t qxb_debug_lookup3(const void* data, size_t n, uint32_t initval);
 

@@ -25,7 +25,7 @@ SYMBOLS = [
     "qxb_last_stats", "qxb_profile_dump", "qxb_debug_mma_smem_bit",
     "qxb_jld2_open", "qxb_jld2_close", "qxb_jld2_count", "qxb_jld2_info", "qxb_jld2_read", "qxb_jld2_write",
     "qxb_graph_load_jld2", "qxb_params_read", "qxb_execute_files", "qxb_debug_lookup3", "qxb_debug_templates",
-    "qxb_debug_rowprog", "qxb_debug_tc5_smem_bit",
+    "qxb_debug_rowprog", "qxb_debug_fused_plan", "qxb_debug_tc5_smem_bit",
     "qxb_multi_create", "qxb_multi_destroy", "qxb_multi_num_devices", "qxb_multi_amplitudes", "qxb_execute_files_multi",
 ]
 
@@ -124,6 +124,7 @@ def load():
         "qxb_params_read": (i32, [cp, C.POINTER(Params), p, i64]),
         "qxb_debug_templates": (i64, [p, i32, p, i64]),
         "qxb_debug_rowprog": (i64, [p, C.c_uint64, i32, p, i64]),
+        "qxb_debug_fused_plan": (i64, [p, C.c_uint64, p, i64]),
         "qxb_debug_lookup3": (C.c_uint32, [p, C.c_size_t, C.c_uint32]),
         "qxb_execute_files": (i32, [cp, cp, cp, cp, i32, i64, i64, i32, pi64, C.POINTER(C.c_double)]),
         "qxb_execute_files_multi": (i32, [cp, cp, cp, cp, i32, i64, i64, i32, i32, i32, pi64, C.POINTER(C.c_double)]),

@@ -2370,6 +2370,47 @@ int64_t qxb_debug_rowprog(qxb_graph* g, uint64_t free_mask, int phase, void* buf
     return rc == QXB_OK ? need : rc;
 }
 
+// test hook: the HBM arena plan of the chunk phase as the executor builds it for a variant WITH its fused chain
+// (select_chain -> make_contiguous -> plan_memory).  Text, one record per line:
+//   fused <first op> <last op>            (-1 -1: no chain)
+//   op <index> <name> <a> <b> <c>         chunk-phase ops in launch order (tensor indices)
+//   tensor <index> <offset> <elems> <amp> <leaf>     per-row element offset / size in the chunk arena (offset -1: not there)
+int64_t qxb_debug_fused_plan(qxb_graph* g, uint64_t free_mask, char* buf, int64_t buflen) {
+    int64_t need = 0;
+    int rc = guard([&] {
+        if (!g) throw Error(QXB_ERR_ARG, "null graph");
+        ensure_analysed(g);
+        Lowered L = lower(g->prog, free_mask, !g->opts.sum_at_root);
+        RowPlanOptions co;
+        co.bank_opt = g->opts.row_bank_opt != 1;
+        co.chain_side = g->opts.chain_side;
+        co.min_tt_bits = knob(0, "QXB_CHAIN_MIN_TT", 7);
+        co.max_arena_bytes = (233472 / 2 - 1024) - (long long)row_fixed_smem_bytes(512);
+        std::vector<int> chain = select_chain(L, g->dtype, co);
+        if (!chain.empty()) chain = make_contiguous(L, chain);
+        plan_memory(L);
+        std::ostringstream o;
+        o << "fused " << L.fused_first << " " << L.fused_last << "\n";
+        std::set<int> ts;
+        for (size_t i = 0; i < L.ops.size(); ++i) {
+            const LOp& op = L.ops[i];
+            if (op.phase != PH_CHUNK) continue;
+            o << "op " << i << " " << op.name << " " << op.a << " " << op.b << " " << op.c << "\n";
+            ts.insert(op.a); ts.insert(op.b); ts.insert(op.c);
+        }
+        for (int t : ts) {
+            const LTensor& T = L.tensors[t];
+            const bool here = T.phase == PH_CHUNK && !T.is_leaf;
+            o << "tensor " << t << " " << (here ? (long long)T.offset : -1ll) << " " << std::max<int64_t>(2, int64_t(1) << T.span_bits) << " "
+              << (T.amp ? 1 : 0) << " " << (T.is_leaf ? 1 : 0) << "\n";
+        }
+        const std::string out = o.str();
+        need = (int64_t)out.size() + 1;
+        if (buf && buflen >= need) memcpy(buf, out.c_str(), out.size() + 1);
+    });
+    return rc == QXB_OK ? need : rc;
+}
+
 // test hook: byte offset a tile-index bit contributes in the tcgen05 kernel's canonical K-major staging layout
 int qxb_debug_tc5_smem_bit(int tile_bits, int bit) { return qxb::gemm_tc5_smem_bit(tile_bits, bit); }
 

@@ -145,3 +145,49 @@ def test_arena_plan_stages_shared_operands_and_fits(lib_built):
         if rp.lop[j] < 0:
             assert lvl_of_desc[di] == first_use[rp.ref_a[j]] - 1
     assert rp.arena_elems * 16 <= 226 * 1024              # fits one SM's shared memory (<= 113 KB: two CTAs per SM)
+
+
+def _fused_plan(graph, free_mask):
+    import ctypes as C
+    lib = graph._lib
+    need = lib.qxb_debug_fused_plan(graph._h, free_mask, None, 0)
+    assert need > 0, lib.qxb_last_error().decode()
+    buf = C.create_string_buffer(need)
+    assert lib.qxb_debug_fused_plan(graph._h, free_mask, buf, need) == need
+    fused, ops, tensors = (-1, -1), [], {}
+    for ln in buf.value.decode().splitlines():
+        f = ln.split()
+        if f[0] == "fused":
+            fused = (int(f[1]), int(f[2]))
+        elif f[0] == "op":
+            ops.append((int(f[1]), f[2], int(f[3]), int(f[4]), int(f[5])))
+        else:
+            tensors[int(f[1])] = dict(off=int(f[2]), size=int(f[3]), amp=int(f[4]), leaf=int(f[5]))
+    return fused, ops, tensors
+
+
+@pytest.mark.parametrize("chain_side", [0, 1, 2])
+def test_fused_launch_results_never_alias_its_inputs(chain_side):
+    """One fused launch works through all rows of the batch: a result it writes to HBM must not share arena space with
+    ANY tensor the launch reads from HBM (another CTA may still have to read that row).  plan_memory therefore releases no
+    operand of the fused ops before the last one.  Checked on the headline plan (where the unfixed planner put the chain's
+    result on an operand of an earlier chain op once side branches changed the allocation order) and on a 6x6 plan."""
+    import bench
+    for wl, fm, replan in (("rqc_7x7_d20_c64_s4096", 4095, 32), ("rqc_6x6_d16_c32_s64", 63, 16)):
+        txt, data, w = bench.build_workload(wl)
+        g = Graph.from_dsl(txt, data, w["dtype"], replan=replan, replan_n_amp=131072)
+        g.configure(chain_side=chain_side)
+        (first, last), ops, T = _fused_plan(g, fm)
+        if first < 0:
+            continue
+        inside = [o for o in ops if first <= o[0] <= last]
+        assert len(inside) == last - first + 1 >= 2
+        produced = {o[4] for o in inside}
+        read_later = {t for o in ops if o[0] > last for t in (o[2], o[3])}
+        inputs = {t for o in inside for t in (o[2], o[3]) if t not in produced and T[t]["off"] >= 0 and T[t]["amp"]}
+        results = {o[4] for o in inside if o[4] in read_later or o[0] == last}
+        assert inputs and results
+        for r in results:
+            for i in inputs:
+                a, b = T[r], T[i]
+                assert a["off"] + a["size"] <= b["off"] or b["off"] + b["size"] <= a["off"], (wl, chain_side, r, i, a, b)
