@@ -168,7 +168,8 @@ int  qxb_graph_compile(qxb_graph* g, const qxb_options* opts);
  * out:  [n_amp] interleaved complex of the graph's dtype ([n_amp][prod(root dims)] for an open network,
  *       see qxb_graph_root_dims).
  * Host-pointer form: H2D of bits, compute, D2H of out, synchronised on return
- * (replaces the "Simulation" section of QXContexts.execute and contract_tn!). */
+ * (replaces the "Simulation" section of QXContexts.execute and contract_tn!).  The entries of `bits` are validated on
+ * the host while the device works: a call with an entry > 3 returns QXB_ERR_ARG and leaves `out` unspecified. */
 int  qxb_amplitudes(qxb_graph* g, const uint8_t* bits, int64_t n_amp,
                     int64_t slice_begin, int64_t slice_end, void* out);
 /* Device-pointer form: bits and out already in HBM; asynchronous on the stream. */
