@@ -62,10 +62,12 @@ def decompose(dims, b, e):
     return out
 
 
-def run_block(desc, data, bits, fixed_vals, dtype=np.complex128, shuffle_seed=None):
+def run_block(desc, data, bits, fixed_vals, dtype=np.complex128, shuffle_seed=None, state=None):
     """Execute one aligned block; returns the per-bitstring partial sums.
     shuffle_seed: run the non-const ops in a RANDOM topological order of their `deps`
-    edges (what a CUDA graph is allowed to do) instead of program order."""
+    edges (what a CUDA graph is allowed to do) instead of program order.
+    state: a dict that receives ``locate`` (tensor description -> (buffer, base element, row stride)) so that a caller
+    can read every tensor of the block afterwards (the fused-chain test of tests/test_rowprog.py)."""
     n = bits.shape[0]
     T = desc["tensors"]
     ar = desc["arena_elems"]
@@ -86,6 +88,8 @@ def run_block(desc, data, bits, fixed_vals, dtype=np.complex128, shuffle_seed=No
             return arenas["chunk"], t["offset"] * n + off, sU
         return arenas[t["phase"]], t["offset"] + off, sU
 
+    if state is not None:
+        state["locate"] = locate
     for t in T:
         if t["output_leaf"]:
             buf, base, sU = locate({**t, "fixed": []})

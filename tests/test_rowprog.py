@@ -191,3 +191,53 @@ def test_fused_launch_results_never_alias_its_inputs(chain_side):
             for i in inputs:
                 a, b = T[r], T[i]
                 assert a["off"] + a["size"] <= b["off"] or b["off"] + b["size"] <= a["off"], (wl, chain_side, r, i, a, b)
+
+
+@pytest.mark.parametrize("knobs", [dict(), dict(row_bank_opt=False), dict(chain_side=1)])
+def test_fused_chain_program_on_the_cpu(knobs):
+    """The fused chain of the headline plan, replayed from its exact device tables (levels with a barrier in between,
+    staged copies of the per-row inputs, lane tables with the bank-aware lane bits, re-laid-out intermediates in a
+    NaN-filled arena, results written to global rows) against the lowered program executed op by op."""
+    import bench
+    txt, data, w = bench.build_workload("rqc_7x7_d20_c64_s4096")      # the headline plan: a chain of six 2^9 - 2^11-element nodes
+    g = Graph.from_dsl(txt, data, "c64", replan=32, replan_n_amp=131072)
+    g.configure(**knobs)
+    bits = bench.synth_bits(2, 49)
+    n = bits.shape[0]
+    fm = (1 << 12) - 1                                                 # all twelve slice variables batched, as the plan runs
+    desc = g.describe(fm)
+    rp = rpe.dump(g, fm, 3)
+    if rp is None:
+        pytest.skip("no chain in this plan: " + g._lib.qxb_last_error().decode())
+    assert len(rp.fused_names) >= 2
+    # the reference keeps EVERY tensor (the memory plan recycles arena space after a tensor's last reader; here the
+    # chain's inputs must still be there afterwards): disjoint offsets per phase
+    nxt = {"const": 0, "block": 0, "chunk": 0}
+    for t in desc["tensors"]:
+        if t["leaf"] and not t["output_leaf"]:
+            continue
+        t["offset"] = nxt[t["phase"]]
+        nxt[t["phase"]] += max(2, 1 << t["span_bits"])
+    desc["arena_elems"] = {"const": nxt["const"], "block": nxt["block"], "chunk_per_amp": nxt["chunk"]}
+    state = {}
+    le.run_block(desc, data, bits, np.zeros(64, dtype=np.int64), state=state)
+    T, locate = desc["tensors"], state["locate"]
+    outs = {}                                            # tensors the chain writes to global memory: fresh buffers
+
+    for u in range(n):
+        def resolve(ti, base=False):
+            t = {**T[ti], "fixed": []} if base else T[ti]
+            if ti in outs:
+                return rpe._Mem(outs[ti], u << T[ti]["span_bits"])
+            buf, b0, sU = locate(t)
+            return rpe._Mem(buf, b0 + u * sU)
+        for j in range(len(rp.ref_c)):
+            if rp.lop[j] >= 0 and not rp.in_arena_c[j] and rp.ref_c[j] not in outs:
+                outs[rp.ref_c[j]] = np.full(n << T[rp.ref_c[j]]["span_bits"], np.nan + 0j, dtype=np.complex128)
+        arena = np.full(max(rp.arena_elems, 1), np.nan + 0j, dtype=np.complex128)
+        rpe.run_program(rp, resolve, arena, np.complex128)
+    assert outs
+    for ti, got in outs.items():
+        buf, b0, sU = locate(T[ti])
+        want = np.concatenate([buf[b0 + u * sU: b0 + u * sU + (1 << T[ti]["span_bits"])] for u in range(n)])
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-14), ti
