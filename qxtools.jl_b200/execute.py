@@ -46,13 +46,18 @@ def write_results(output_file: str, bitstrings, amplitudes, **extra) -> None:
     save_jld2(output_file, arrays, commit_types=False)
 
 
-def _bitstrings_from_params(params: dict, max_amplitudes: Optional[int]):
-    """List / Uniform give the bitstrings up front; Rejection returns None (sampled on the fly)."""
+def _bitstrings_from_params(params: dict, max_amplitudes: Optional[int], param_file: Optional[str] = None):
+    """List / Uniform give the bitstrings up front; Rejection returns None (sampled on the fly).
+    Uniform with a parameter FILE draws through the library (``qxb_params_read``: its documented splitmix64 stream), so
+    that ``python -m qxb200.execute``, ``qxrun`` and ``QXB200.execute`` give the same bitstrings for the same file and seed."""
     out = params["output"]
     method, p = out["method"], out["params"]
     if method == "List":                                  # outputs.jl:63-68
         bs = list(p["bitstrings"])
-    elif method == "Uniform":                             # outputs.jl:69-72
+    elif method == "Uniform" and param_file is not None:  # outputs.jl:69-72, simulation.jl:24-28
+        from .jld2 import read_params
+        bs = list(read_params(param_file)["bitstrings"])
+    elif method == "Uniform":
         bs = list(amplitudes_uniform(int(p["num_qubits"]), p.get("seed"), int(p["num_samples"])))
     elif method == "Rejection":                           # outputs.jl:57-62
         return None
@@ -96,7 +101,7 @@ def execute(dsl_file: str, input_file: Optional[str] = None, param_file: Optiona
             td.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
         rank, world = td.get_rank(), td.get_world_size()
     init(int(os.environ.get("LOCAL_RANK", "0")))
-    bitstrings = _bitstrings_from_params(params, max_amplitudes)
+    bitstrings = _bitstrings_from_params(params, max_amplitudes, param_file)
     n_model = len(bitstrings) if bitstrings is not None else 1024
     tune_report = None
     if autotune and not use_mpi and bitstrings:

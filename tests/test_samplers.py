@@ -41,3 +41,23 @@ def test_rejection_sampling_follows_distribution():
 def test_uniform_bitstrings_seeded():
     a, b = uniform_bitstrings(9, 5, 3), uniform_bitstrings(9, 5, 3)
     assert a.shape == (5, 9) and np.array_equal(a, b) and set(np.unique(a)) <= {0, 1}
+
+
+def test_uniform_bitstrings_of_execute_are_the_library_stream(tmp_path):
+    """`execute` (Python), `qxrun` and the Julia shim read a Uniform parameter file through `qxb_params_read`: one RNG
+    stream (splitmix64, documented in include/qxb200.h), so the same file and seed give the same bitstrings everywhere."""
+    import yaml
+    from qxb200.execute import _bitstrings_from_params
+    from qxb200.jld2 import read_params
+    path = str(tmp_path / "u.yml")
+    doc = {"output": {"method": "Uniform", "params": {"num_qubits": 9, "num_samples": 7, "seed": 123}}}
+    with open(path, "w") as f:
+        yaml.safe_dump(doc, f)
+    via_execute = _bitstrings_from_params(yaml.safe_load(open(path)), None, path)
+    via_library = read_params(path)["bitstrings"]
+    assert via_execute == via_library and len(via_execute) == 7 and all(len(b) == 9 and set(b) <= {"0", "1"} for b in via_execute)
+    assert _bitstrings_from_params(yaml.safe_load(open(path)), 3, path) == via_library[:3]          # qxrun.jl:32-39: the FIRST n
+    doc["output"]["params"]["seed"] = 124
+    with open(path, "w") as f:
+        yaml.safe_dump(doc, f)
+    assert read_params(path)["bitstrings"] != via_library
