@@ -208,3 +208,20 @@ def test_fused_chain_equals_per_op(gpu, dtype, tol):
     o = orc.amplitudes(orc.parse_dsl(plan), data, bs, slice_begin=5, slice_end=8)
     big = np.tile(bits[:2], (160, 1))
     assert rel_err(g.amplitudes(big, 5, 8)[:2], o, 49) < max(tol, 1e-10)
+
+
+def test_hoisted_block_phase_is_refreshed(gpu):
+    """The block phase of a one-block step lives outside the captured graph and is re-run only when the block arena holds
+    another block's results.  Alternate full-range calls (all slices batched: no fixed value), single slices (every variable
+    fixed, a different value each time), a repeated slice and a multi-block range on ONE graph, replaying each captured step:
+    every call must match the oracle for ITS slices."""
+    txt, data, bs = rqc_case(4, 4, 12, 3, n_amp=8)
+    cmds = orc.parse_dsl(txt)
+    g = Graph.from_dsl(txt, data, "c64").compile()
+    S = g.n_slices
+    assert S == 8
+    calls = [(0, S), (3, 4), (0, S), (5, 6), (3, 4), (3, 4), (1, 7), (5, 6), (0, S), (0, S), (2, 3)]
+    want = {r: orc.amplitudes(cmds, data, bs, slice_begin=r[0], slice_end=r[1]) for r in set(calls)}
+    for r in calls:
+        got = g.amplitudes(bs, r[0], r[1])
+        assert rel_err(got, want[r], 16) < 1e-10, r
