@@ -1629,12 +1629,8 @@ void run_blocks(qxb_graph* g, std::vector<Block> blocks, StepKey key, const uint
         sg.hoisted = true;
         sg.block_variant = sp.variants[0]->key;
         sg.block_vals = sp.blocks[0].vals;
-        nodes.push_back(*sg.block_launch);            // counted in the statistics of the step (it runs at least once)
-        account(g, nodes);
-        nodes.pop_back();
-    } else {
-        account(g, nodes);
     }
+    account(g, nodes);                                // the statistics of a REPLAYED step: without the hoisted block launch
     if (!use_graph || nodes.size() > 100000) { g->block_owner_variant = -1; launch_serial(g, nodes); return; }   // huge steps: not worth a graph
     if (g->step_graphs.size() >= 32) g->drop_step_graphs();
     sg.exec = instantiate(nodes);
